@@ -1,0 +1,183 @@
+/*
+ * libb200coll — intra-node collective library for 8×B200 (sm_100a) over NVLink 5 / NVSwitch.
+ *
+ * Role parity: this is the payload the transport-installer DaemonSet drops into
+ * /home/kubernetes/bin/nvidia/lib64 and the device plugin's Allocate mounts into the pod —
+ * the slot the reference fills with pre-built NCCL net plugins
+ * (reference: fast-socket-installer/fast-socket-installer.yaml:41-45,
+ *  gpudirect-rdma/nccl-rdma-installer.yaml:70-77, gpudirect-tcpxo/nccl-tcpxo-installer.yaml:83-91).
+ * On a single NVSwitch box a *net* plugin is never on the data path, so the product here is the
+ * collective itself: one-shot (Lamport/LL), two-shot P2P and NVLS-multimem kernels with the
+ * cast/scale epilogue fused, chosen per (op, bytes, nranks) by a measured table (the
+ * libnccl-tuner.so analogue, reference: gpudirect-tcpxo/README.md:80-81).
+ *
+ * C ABI, no C++ types cross the boundary. All collectives are asynchronous on `stream`
+ * and never block the host on a peer.
+ */
+#ifndef B200COLL_H_
+#define B200COLL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200COLL_VERSION_MAJOR 0
+#define B200COLL_VERSION_MINOR 1
+#define B200COLL_MAX_RANKS 8
+#define B200COLL_UNIQUE_ID_BYTES 128
+
+typedef struct b200collComm* b200collComm_t;
+typedef struct { char internal[B200COLL_UNIQUE_ID_BYTES]; } b200collUniqueId;
+typedef void* b200collStream_t; /* cudaStream_t */
+
+typedef enum {
+  b200collSuccess = 0,
+  b200collUnhandledCudaError = 1,
+  b200collSystemError = 2,
+  b200collInternalError = 3,
+  b200collInvalidArgument = 4,
+  b200collInvalidUsage = 5,
+  b200collRemoteError = 6,   /* a peer timed out or aborted (watchdog) */
+  b200collInProgress = 7,
+  b200collOutOfMemory = 8,
+  b200collNoDriver = 9       /* libcuda / GPU not present (CPU-only box) */
+} b200collResult_t;
+
+typedef enum {
+  b200collFloat32 = 0,
+  b200collFloat16 = 1,
+  b200collBfloat16 = 2,
+  b200collFloat8e4m3 = 3,   /* output / wire type only */
+  b200collNumTypes = 4
+} b200collDataType_t;
+
+typedef enum { b200collSum = 0, b200collAvg = 1 } b200collRedOp_t;
+
+typedef enum {
+  b200collOpAllReduce = 0,
+  b200collOpAllGather = 1,
+  b200collOpReduceScatter = 2,
+  b200collOpAllToAll = 3,
+  b200collNumOps = 4
+} b200collOp_t;
+
+/* Algorithm ids (tuner output; B200COLL_ALGO overrides). */
+typedef enum {
+  b200collAlgoAuto = 0,
+  b200collAlgoLL = 1,        /* Lamport flag-in-payload push, zero barriers  (tiny)  */
+  b200collAlgoOneShot = 2,   /* barrier + pull all peers + reduce in regs    (small) */
+  b200collAlgoTwoShot = 3,   /* P2P pull-reduce own slice + push to peers    (mid/large, no multicast needed) */
+  b200collAlgoNvls = 4,      /* multimem.ld_reduce / multimem.st through the switch (large) */
+  b200collAlgoCopy = 5,      /* nranks == 1: fused scale/cast copy */
+  b200collNumAlgos = 6
+} b200collAlgo_t;
+
+/* Fused epilogue: out = cast<out_dtype>(reduce(in) * scale). scale==1.0f and equal dtypes is the plain collective. */
+typedef struct {
+  b200collDataType_t in_dtype;
+  b200collDataType_t out_dtype;
+  float scale;
+} b200collEpilogue;
+
+typedef struct {
+  size_t arena_bytes;        /* symmetric user heap per rank (default: env B200COLL_ARENA_MB or 2560 MiB) */
+  int enable_nvls;           /* -1 auto (probe), 0 off, 1 require */
+  int max_ctas;              /* 0 = auto */
+  int timeout_ms;            /* device-side watchdog for every cross-GPU spin (default 20000) */
+  int debug;                 /* 0 quiet, 1 info, 2 trace (env B200COLL_DEBUG) */
+} b200collConfig;
+
+typedef struct {
+  int rank, nranks, device;
+  int nvls;                  /* multicast window mapped */
+  int p2p_ok;                /* full P2P matrix */
+  int same_device_loopback;  /* virtual ranks share one GPU (test mode) */
+  size_t arena_bytes;
+  size_t arena_used;
+  int sm_count;
+  int driver_version;
+} b200collCommInfo;
+
+typedef struct {
+  uint64_t calls[b200collNumOps];
+  uint64_t bytes[b200collNumOps];
+  uint64_t algo_calls[b200collNumAlgos];
+  uint64_t kernel_launches;
+  uint64_t staged_calls;     /* calls that went through the staging copy (unregistered buffers) */
+} b200collStats;
+
+/* Device-written watchdog record (host-pinned). code != 0 means the comm is poisoned. */
+typedef struct {
+  uint32_t code;             /* 0 ok, 1 barrier timeout, 2 LL data timeout */
+  uint32_t rank, peer, block;
+  uint32_t expected, observed;
+  uint32_t op, reserved;
+} b200collFault;
+
+const char* b200collGetErrorString(b200collResult_t r);
+const char* b200collGetLastError(void);
+int b200collGetVersion(void);
+
+void b200collConfigDefault(b200collConfig* cfg);
+
+/* --- multi-process: one rank per process, rendezvous over an abstract Unix socket (SCM_RIGHTS fd passing). */
+b200collResult_t b200collGetUniqueId(b200collUniqueId* id);
+/* Deterministic id from a string (e.g. "$MASTER_ADDR:$MASTER_PORT/0") so torchrun ranks need no side channel. */
+b200collResult_t b200collUniqueIdFromString(const char* s, b200collUniqueId* id);
+b200collResult_t b200collCommInitRank(b200collComm_t* comm, int nranks, const b200collUniqueId* id, int rank,
+                                      const b200collConfig* cfg);
+/* --- single process: n ranks, one per entry of devs (entries may repeat: virtual ranks on one GPU for tests). */
+b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* devs, const b200collConfig* cfg);
+b200collResult_t b200collCommDestroy(b200collComm_t comm);
+b200collResult_t b200collCommInfoGet(b200collComm_t comm, b200collCommInfo* info);
+b200collResult_t b200collCommStatsGet(b200collComm_t comm, b200collStats* stats);
+b200collResult_t b200collCommGetAsyncError(b200collComm_t comm, b200collFault* fault);
+/* Host-level barrier over the bootstrap channel (multi-process comms only; no-op for InitAll comms). */
+b200collResult_t b200collHostBarrier(b200collComm_t comm);
+
+/* --- symmetric memory: collective calls, same order and size on every rank (ncclMemAlloc analogue). */
+b200collResult_t b200collMemAlloc(b200collComm_t comm, void** ptr, size_t bytes);
+b200collResult_t b200collMemFree(b200collComm_t comm, void* ptr);
+/* 1 if [ptr, ptr+bytes) lies in this rank's symmetric arena. */
+int b200collIsSymmetric(b200collComm_t comm, const void* ptr, size_t bytes);
+
+/* --- collectives. count is in elements of ep->in_dtype.
+ * Buffers inside the symmetric arena take the zero-copy paths; any other device pointer is staged. */
+b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep,
+                                   b200collRedOp_t op, b200collComm_t comm, b200collStream_t stream);
+/* recv holds nranks*sendcount elements; rank r's contribution lands at r*sendcount. */
+b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcount, const b200collEpilogue* ep,
+                                   b200collComm_t comm, b200collStream_t stream);
+/* send holds nranks*recvcount elements; rank r receives the reduction of slice r. */
+b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recvcount, const b200collEpilogue* ep,
+                                       b200collRedOp_t op, b200collComm_t comm, b200collStream_t stream);
+/* send/recv hold nranks*count elements; block p of send goes to block `rank` of peer p's recv. */
+b200collResult_t b200collAllToAll(const void* send, void* recv, size_t count, const b200collEpilogue* ep,
+                                  b200collComm_t comm, b200collStream_t stream);
+/* Expert-dispatch shape: rows of `row_elems` elements; send_rows[p] rows go to peer p starting at row
+ * send_row_off[p] of send; they land at row recv_row_off[src] of the destination (all four arrays are
+ * host arrays of length nranks; recv_row_off[src] = where rank `src`'s rows start in MY recv). */
+b200collResult_t b200collAllToAllv(const void* send, void* recv, size_t row_elems, const int64_t* send_rows,
+                                   const int64_t* send_row_off, const int64_t* recv_row_off_at_peer,
+                                   const b200collEpilogue* ep, b200collComm_t comm, b200collStream_t stream);
+b200collResult_t b200collBarrier(b200collComm_t comm, b200collStream_t stream);
+
+/* --- tuner (libnccl-tuner.so analogue). */
+b200collAlgo_t b200collTunerPick(b200collOp_t op, size_t bytes, int nranks, int nvls_available);
+/* Force an algorithm for subsequent calls on this comm (b200collAlgoAuto restores the table). */
+b200collResult_t b200collCommSetAlgo(b200collComm_t comm, b200collAlgo_t algo);
+b200collResult_t b200collCommSetMaxCtas(b200collComm_t comm, int max_ctas);
+const char* b200collAlgoName(b200collAlgo_t a);
+size_t b200collTypeSize(b200collDataType_t t);
+
+/* --- start-up self check (guest-config-checker analogue, reference: gpudirect-tcpxo/README.md:84,239).
+ * Writes a human-readable report into buf; returns b200collSuccess iff the box can run the fast paths. */
+b200collResult_t b200collSelfCheck(char* buf, size_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200COLL_H_ */

@@ -1,0 +1,387 @@
+// libb200coll collective entry points: argument validation, algorithm choice (tuner table +
+// feasibility), staging for buffers outside the symmetric arena, type dispatch, kernel launch.
+#include <algorithm>
+
+#include "comm.h"
+#include "kernels.cuh"
+
+namespace b200coll {
+
+template <typename T> struct Tag { using type = T; };
+using bf16 = __nv_bfloat16;
+using f8 = __nv_fp8_e4m3;
+
+// Supported (in, out) pairs: same type, widen to f32, narrow f32 to 16-bit, quantise to e4m3.
+template <typename F>
+static b200collResult_t dispatch_types(b200collDataType_t in, b200collDataType_t out, F&& f) {
+  if (in == b200collFloat32) {
+    switch (out) {
+      case b200collFloat32: return f(Tag<float>{}, Tag<float>{});
+      case b200collBfloat16: return f(Tag<float>{}, Tag<bf16>{});
+      case b200collFloat16: return f(Tag<float>{}, Tag<__half>{});
+      case b200collFloat8e4m3: return f(Tag<float>{}, Tag<f8>{});
+      default: break;
+    }
+  } else if (in == b200collBfloat16) {
+    switch (out) {
+      case b200collBfloat16: return f(Tag<bf16>{}, Tag<bf16>{});
+      case b200collFloat32: return f(Tag<bf16>{}, Tag<float>{});
+      case b200collFloat8e4m3: return f(Tag<bf16>{}, Tag<f8>{});
+      default: break;
+    }
+  } else if (in == b200collFloat16) {
+    switch (out) {
+      case b200collFloat16: return f(Tag<__half>{}, Tag<__half>{});
+      case b200collFloat32: return f(Tag<__half>{}, Tag<float>{});
+      case b200collFloat8e4m3: return f(Tag<__half>{}, Tag<f8>{});
+      default: break;
+    }
+  }
+  set_last_error("unsupported (in_dtype, out_dtype) pair");
+  return b200collInvalidArgument;
+}
+
+#define LAUNCH_CHECK(c)                                                                                  \
+  do {                                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ != cudaSuccess) { set_last_error(std::string("kernel launch failed: ") + cudaGetErrorString(e__)); return b200collUnhandledCudaError; } \
+    (c)->stats.kernel_launches++;                                                                        \
+  } while (0)
+
+struct Grid { int blocks, threads; };
+
+// Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs).
+static Grid pick_grid(size_t vecs, int unroll, int max_ctas) {
+  for (int t : {128, 256, 512}) {
+    size_t b = (vecs + (size_t)t * unroll - 1) / ((size_t)t * unroll);
+    if (b <= (size_t)max_ctas || t == 512) return Grid{(int)std::max<size_t>(1, std::min<size_t>(b, (size_t)max_ctas)), t};
+  }
+  return Grid{1, 128};
+}
+
+static size_t arena_off(b200collComm* c, const void* p) { return reinterpret_cast<CUdeviceptr>(p) - c->peer_va[c->rank]; }
+static char* stage_ptr(b200collComm* c, int half) { return reinterpret_cast<char*>(c->peer_va[c->rank]) + kOffStage + (size_t)half * kStageHalfBytes; }
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static size_t out_align(size_t in_sz, size_t out_sz) { return std::min<size_t>(16, 16 / in_sz * out_sz); }
+
+static b200collResult_t check_common(b200collComm* c, const void* send, void* recv, const b200collEpilogue* ep) {
+  if (!c || !send || !recv || !ep) { set_last_error("null argument"); return b200collInvalidArgument; }
+  if (ep->in_dtype == b200collFloat8e4m3 || b200collTypeSize(ep->in_dtype) == 0 || b200collTypeSize(ep->out_dtype) == 0) { set_last_error("bad dtype (e4m3 is an output type only)"); return b200collInvalidArgument; }
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  if (!aligned(send, 16) || !aligned(recv, out_align(is, os))) { set_last_error("send must be 16-byte aligned and recv aligned to one output vector"); return b200collInvalidArgument; }
+  if (c->fault_host && *const_cast<volatile uint32_t*>(&c->fault_host->code) != 0) { set_last_error("communicator is poisoned by an earlier watchdog fault"); return b200collRemoteError; }
+  return b200collSuccess;
+}
+
+static void account(b200collComm* c, b200collOp_t op, size_t bytes, b200collAlgo_t algo) {
+  c->stats.calls[op]++; c->stats.bytes[op] += bytes; c->stats.algo_calls[algo]++;
+}
+
+// ------------------------------------------------------------------------------------------------ nranks == 1
+static b200collResult_t copy_scale(b200collComm* c, const void* send, void* recv, size_t count, const b200collEpilogue* ep, float scale, cudaStream_t st) {
+  if (send == recv && ep->in_dtype == ep->out_dtype && scale == 1.0f) return b200collSuccess;
+  return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+    using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+    Grid g = pick_grid(count / Epv<InT>::value + 1, 1, c->max_ctas * 4);
+    k_copy_scale<InT, OutT><<<g.blocks, g.threads, 0, st>>>(static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale);
+    LAUNCH_CHECK(c);
+    return b200collSuccess;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ LL (all ops)
+static b200collResult_t launch_ll(b200collComm* c, b200collOp_t op, const void* send, void* recv, size_t count, const b200collEpilogue* ep, float scale, cudaStream_t st) {
+  return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+    using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+    constexpr int E = Epv<InT>::value;
+    const size_t nv = (count + E - 1) / E;
+    Grid g = pick_grid(nv, 1, std::min(c->max_ctas, 148));
+    const InT* in = static_cast<const InT*>(send); OutT* out = static_cast<OutT*>(recv);
+    const bool mc = c->nvls;
+    switch (op) {
+      case b200collOpAllReduce:
+        if (mc) k_ll<InT, OutT, false, true, true><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        else k_ll<InT, OutT, false, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        break;
+      case b200collOpAllGather:
+        if (mc) k_ll<InT, OutT, false, false, true><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        else k_ll<InT, OutT, false, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        break;
+      case b200collOpReduceScatter:
+        k_ll<InT, OutT, true, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        break;
+      default:
+        k_ll<InT, OutT, true, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        break;
+    }
+    LAUNCH_CHECK(c);
+    return b200collSuccess;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ all-reduce on symmetric buffers
+static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const void* send, void* recv, size_t count, const b200collEpilogue* ep, float scale, cudaStream_t st) {
+  const int identity = (ep->in_dtype == ep->out_dtype && scale == 1.0f) ? 1 : 0;
+  return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+    using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+    constexpr int E = Epv<InT>::value;
+    const size_t nvec = count / E;
+    const size_t in_off = arena_off(c, send);
+    if (algo == b200collAlgoOneShot) {
+      Grid g = pick_grid(nvec, 2, c->max_ctas);
+      k_pull_reduce<InT, OutT, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
+    } else if (algo == b200collAlgoTwoShot) {
+      Grid g = pick_grid(nvec / c->nranks + 1, 2, c->max_ctas);
+      k_ar_twoshot<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, b200collOpAllReduce);
+    } else {
+      Grid g = pick_grid(nvec / c->nranks + 1, 4, c->max_ctas);
+      k_ar_nvls<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
+    }
+    LAUNCH_CHECK(c);
+    return b200collSuccess;
+  });
+}
+
+}  // namespace b200coll
+
+using namespace b200coll;
+
+extern "C" {
+
+b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep, b200collRedOp_t rop, b200collComm_t c, b200collStream_t stream) {
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (count == 0) return b200collSuccess;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const size_t bytes = count * is;
+  const float scale = ep->scale * (rop == b200collAvg ? 1.0f / (float)c->nranks : 1.0f);
+  if (c->nranks == 1) { account(c, b200collOpAllReduce, bytes, b200collAlgoCopy); return copy_scale(c, send, recv, count, ep, scale, st); }
+  const bool inplace = send == recv;
+  if (inplace && is != os) { set_last_error("in-place all-reduce needs in_dtype and out_dtype of equal size"); return b200collInvalidArgument; }
+  const bool sym_in = b200collIsSymmetric(c, send, bytes), sym_out = b200collIsSymmetric(c, recv, count * os);
+  b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllReduce, bytes, c->nranks, c->nvls);
+  auto feasible = [&](b200collAlgo_t a) {
+    switch (a) {
+      case b200collAlgoLL: return bytes <= kLLMaxBytes;
+      case b200collAlgoOneShot: return sym_in && !inplace;
+      case b200collAlgoTwoShot: return sym_in && sym_out;
+      case b200collAlgoNvls: return c->nvls && sym_in && sym_out;
+      default: return false;
+    }
+  };
+  if (!feasible(algo)) {
+    algo = b200collAlgoAuto;
+    for (b200collAlgo_t a : {b200collAlgoNvls, b200collAlgoTwoShot, b200collAlgoOneShot, b200collAlgoLL})
+      if (feasible(a) && !(a == b200collAlgoNvls && c->nranks == 2)) { algo = a; break; }
+  }
+  if (algo == b200collAlgoLL) { account(c, b200collOpAllReduce, bytes, algo); return launch_ll(c, b200collOpAllReduce, send, recv, count, ep, scale, st); }
+  if (algo != b200collAlgoAuto) { account(c, b200collOpAllReduce, bytes, algo); return ar_symmetric(c, algo, send, recv, count, ep, scale, st); }
+  // ---- staged: buffers outside the arena and too big for LL. Chunk through the two staging halves.
+  c->stats.staged_calls++;
+  b200collAlgo_t inner = (c->nvls && c->nranks > 2) ? b200collAlgoNvls : b200collAlgoTwoShot;
+  const size_t chunk = std::min(kStageHalfBytes / is, kStageHalfBytes / os) / 64 * 64;
+  for (size_t done = 0; done < count; done += chunk) {
+    const size_t n = std::min(chunk, count - done);
+    cudaError_t e = cudaMemcpyAsync(stage_ptr(c, 0), static_cast<const char*>(send) + done * is, n * is, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+    account(c, b200collOpAllReduce, n * is, inner);
+    rc = ar_symmetric(c, inner, stage_ptr(c, 0), stage_ptr(c, 1), n, ep, scale, st);
+    if (rc != b200collSuccess) return rc;
+    e = cudaMemcpyAsync(static_cast<char*>(recv) + done * os, stage_ptr(c, 1), n * os, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+  }
+  return b200collSuccess;
+}
+
+b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcount, const b200collEpilogue* ep, b200collComm_t c, b200collStream_t stream) {
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (sendcount == 0) return b200collSuccess;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const size_t bytes = sendcount * is;
+  const float scale = ep->scale;
+  if (c->nranks == 1) { account(c, b200collOpAllGather, bytes, b200collAlgoCopy); return copy_scale(c, send, recv, sendcount, ep, scale, st); }
+  if (sendcount % (16 / is) != 0) { set_last_error("all-gather sendcount must be a multiple of 16 bytes / sizeof(in_dtype)"); return b200collInvalidArgument; }
+  const bool sym_out = b200collIsSymmetric(c, recv, (size_t)c->nranks * sendcount * os);
+  b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllGather, bytes, c->nranks, c->nvls);
+  if (algo == b200collAlgoOneShot) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL && bytes > kLLMaxBytes) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoNvls && !c->nvls) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL) { account(c, b200collOpAllGather, bytes, algo); return launch_ll(c, b200collOpAllGather, send, recv, sendcount, ep, scale, st); }
+  const int identity = (ep->in_dtype == ep->out_dtype && scale == 1.0f) ? 1 : 0;
+  auto push = [&](const void* s, void* r, size_t n) -> b200collResult_t {
+    account(c, b200collOpAllGather, n * is, algo);
+    return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+      using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+      Grid g = pick_grid(n / Epv<InT>::value, 4, c->max_ctas);
+      if (algo == b200collAlgoNvls) k_ag_push<InT, OutT, true><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
+      else k_ag_push<InT, OutT, false><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
+      LAUNCH_CHECK(c);
+      return b200collSuccess;
+    });
+  };
+  if (sym_out) return push(send, recv, sendcount);
+  // staged: gather chunks into staging half 1 laid out [nranks][chunk], then scatter locally into recv
+  c->stats.staged_calls++;
+  const size_t chunk = (kStageHalfBytes / os / c->nranks) / 64 * 64;
+  for (size_t done = 0; done < sendcount; done += chunk) {
+    const size_t n = std::min(chunk, sendcount - done);
+    rc = push(static_cast<const char*>(send) + done * is, stage_ptr(c, 1), n);
+    if (rc != b200collSuccess) return rc;
+    for (int r = 0; r < c->nranks; r++) {
+      cudaError_t e = cudaMemcpyAsync(static_cast<char*>(recv) + ((size_t)r * sendcount + done) * os, stage_ptr(c, 1) + (size_t)r * n * os, n * os, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+    }
+  }
+  return b200collSuccess;
+}
+
+b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recvcount, const b200collEpilogue* ep, b200collRedOp_t rop, b200collComm_t c, b200collStream_t stream) {
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (recvcount == 0) return b200collSuccess;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const size_t bytes = recvcount * is;
+  const float scale = ep->scale * (rop == b200collAvg ? 1.0f / (float)c->nranks : 1.0f);
+  if (c->nranks == 1) { account(c, b200collOpReduceScatter, bytes, b200collAlgoCopy); return copy_scale(c, send, recv, recvcount, ep, scale, st); }
+  if (recvcount % (16 / is) != 0) { set_last_error("reduce-scatter recvcount must be a multiple of 16 bytes / sizeof(in_dtype)"); return b200collInvalidArgument; }
+  const bool sym_in = b200collIsSymmetric(c, send, (size_t)c->nranks * bytes);
+  b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpReduceScatter, bytes, c->nranks, c->nvls);
+  if (algo == b200collAlgoOneShot) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL && bytes > kLLMaxBytes) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoNvls && !c->nvls) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL) { account(c, b200collOpReduceScatter, bytes, algo); return launch_ll(c, b200collOpReduceScatter, send, recv, recvcount, ep, scale, st); }
+  auto pull = [&](const void* s_slice_of_mine, void* r, size_t n) -> b200collResult_t {
+    account(c, b200collOpReduceScatter, n * is, algo);
+    return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+      using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+      Grid g = pick_grid(n / Epv<InT>::value, 2, c->max_ctas);
+      if (algo == b200collAlgoNvls) k_pull_reduce<InT, OutT, false, true><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
+      else k_pull_reduce<InT, OutT, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
+      LAUNCH_CHECK(c);
+      return b200collSuccess;
+    });
+  };
+  if (sym_in) return pull(static_cast<const char*>(send) + (size_t)c->rank * bytes, recv, recvcount);
+  // staged: copy chunk j of every slice into staging half 0 laid out [nranks][chunk]; each rank pulls its row
+  c->stats.staged_calls++;
+  const size_t chunk = (kStageHalfBytes / is / c->nranks) / 64 * 64;
+  for (size_t done = 0; done < recvcount; done += chunk) {
+    const size_t n = std::min(chunk, recvcount - done);
+    for (int r = 0; r < c->nranks; r++) {
+      cudaError_t e = cudaMemcpyAsync(stage_ptr(c, 0) + (size_t)r * n * is, static_cast<const char*>(send) + ((size_t)r * recvcount + done) * is, n * is, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+    }
+    rc = pull(stage_ptr(c, 0) + (size_t)c->rank * n * is, static_cast<char*>(recv) + done * os, n);
+    if (rc != b200collSuccess) return rc;
+  }
+  return b200collSuccess;
+}
+
+static b200collResult_t a2av_launch(b200collComm* c, const void* send, void* recv_sym, const A2AvArgs& a, const b200collEpilogue* ep, cudaStream_t st) {
+  const int identity = (ep->in_dtype == ep->out_dtype && ep->scale == 1.0f) ? 1 : 0;
+  return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+    using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+    Grid g = pick_grid((size_t)a.prefix[c->nranks] + 1, 4, c->max_ctas);
+    k_a2av_push<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), arena_off(c, recv_sym), a, ep->scale, identity, b200collOpAllToAll);
+    LAUNCH_CHECK(c);
+    return b200collSuccess;
+  });
+}
+
+// Fill the flattened prefix in the kernel's staggered order (j -> peer rank+1+j).
+static void a2av_prefix(const b200collComm* c, const unsigned long long* nvec_by_peer, A2AvArgs* a) {
+  a->prefix[0] = 0;
+  for (int j = 0; j < c->nranks; j++) {
+    int p = c->rank + 1 + j; if (p >= c->nranks) p -= c->nranks;
+    a->prefix[j + 1] = a->prefix[j] + nvec_by_peer[p];
+  }
+  for (int j = c->nranks + 1; j <= kMaxRanks; j++) a->prefix[j] = a->prefix[c->nranks];
+}
+
+b200collResult_t b200collAllToAll(const void* send, void* recv, size_t count, const b200collEpilogue* ep, b200collComm_t c, b200collStream_t stream) {
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (count == 0) return b200collSuccess;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const size_t bytes = count * is;
+  if (c->nranks == 1) { account(c, b200collOpAllToAll, bytes, b200collAlgoCopy); return copy_scale(c, send, recv, count, ep, ep->scale, st); }
+  if (send == recv) { set_last_error("in-place all-to-all is not supported"); return b200collInvalidUsage; }
+  const size_t E = 16 / is;
+  if (count % E != 0) { set_last_error("all-to-all count must be a multiple of 16 bytes / sizeof(in_dtype)"); return b200collInvalidArgument; }
+  b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllToAll, bytes, c->nranks, c->nvls);
+  if (algo != b200collAlgoLL || bytes > kLLMaxBytes) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL) { account(c, b200collOpAllToAll, bytes * c->nranks, algo); return launch_ll(c, b200collOpAllToAll, send, recv, count, ep, ep->scale, st); }
+  const bool sym_out = b200collIsSymmetric(c, recv, (size_t)c->nranks * count * os);
+  auto run = [&](const void* s, size_t s_stride_elems, void* r_sym, size_t n) -> b200collResult_t {
+    // block p of this chunk starts at element p*s_stride_elems of s; lands at block `rank` (stride n) of r_sym on peer p
+    A2AvArgs a = {};
+    unsigned long long nv[kMaxRanks] = {};
+    for (int p = 0; p < c->nranks; p++) { a.src_vec[p] = (unsigned long long)p * s_stride_elems / E; a.dst_vec[p] = (unsigned long long)c->rank * n / E; nv[p] = n / E; }
+    a2av_prefix(c, nv, &a);
+    account(c, b200collOpAllToAll, n * is * c->nranks, algo);
+    return a2av_launch(c, s, r_sym, a, ep, st);
+  };
+  if (sym_out) return run(send, count, recv, count);
+  c->stats.staged_calls++;
+  const size_t chunk = (kStageHalfBytes / os / c->nranks) / 64 * 64;
+  for (size_t done = 0; done < count; done += chunk) {
+    const size_t n = std::min(chunk, count - done);
+    rc = run(static_cast<const char*>(send) + done * is, count, stage_ptr(c, 1), n);
+    if (rc != b200collSuccess) return rc;
+    for (int r = 0; r < c->nranks; r++) {
+      cudaError_t e = cudaMemcpyAsync(static_cast<char*>(recv) + ((size_t)r * count + done) * os, stage_ptr(c, 1) + (size_t)r * n * os, n * os, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+    }
+  }
+  return b200collSuccess;
+}
+
+b200collResult_t b200collAllToAllv(const void* send, void* recv, size_t row_elems, const int64_t* send_rows, const int64_t* send_row_off,
+                                   const int64_t* recv_row_off_at_peer, const b200collEpilogue* ep, b200collComm_t c, b200collStream_t stream) {
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (!send_rows || !send_row_off || !recv_row_off_at_peer || row_elems == 0) { set_last_error("alltoallv: null/zero argument"); return b200collInvalidArgument; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const size_t E = 16 / is;
+  if (row_elems % E != 0) { set_last_error("alltoallv: row_elems must be a multiple of 16 bytes / sizeof(in_dtype)"); return b200collInvalidArgument; }
+  if (send == recv) { set_last_error("in-place all-to-all is not supported"); return b200collInvalidUsage; }
+  const size_t row_vecs = row_elems / E;
+  if (c->nranks == 1) {
+    account(c, b200collOpAllToAll, (size_t)send_rows[0] * row_elems * is, b200collAlgoCopy);
+    if (send_rows[0] <= 0) return b200collSuccess;
+    return copy_scale(c, static_cast<const char*>(send) + (size_t)send_row_off[0] * row_elems * is, static_cast<char*>(recv) + (size_t)recv_row_off_at_peer[0] * row_elems * os,
+                      (size_t)send_rows[0] * row_elems, ep, ep->scale, st);
+  }
+  // The receive side is written by peers, so it must be symmetric; expert-dispatch buffers are long-lived, allocate them with MemAlloc.
+  if (!b200collIsSymmetric(c, recv, 1)) { set_last_error("alltoallv: recv must come from b200collMemAlloc (peers write into it)"); return b200collInvalidUsage; }
+  A2AvArgs a = {};
+  unsigned long long nv[kMaxRanks] = {};
+  size_t total_bytes = 0;
+  for (int p = 0; p < c->nranks; p++) {
+    if (send_rows[p] < 0 || send_row_off[p] < 0 || recv_row_off_at_peer[p] < 0) { set_last_error("alltoallv: negative count/offset"); return b200collInvalidArgument; }
+    a.src_vec[p] = (unsigned long long)send_row_off[p] * row_vecs;
+    a.dst_vec[p] = (unsigned long long)recv_row_off_at_peer[p] * row_vecs;
+    nv[p] = (unsigned long long)send_rows[p] * row_vecs;
+    total_bytes += (size_t)send_rows[p] * row_elems * is;
+  }
+  a2av_prefix(c, nv, &a);
+  account(c, b200collOpAllToAll, total_bytes, b200collAlgoTwoShot);
+  return a2av_launch(c, send, recv, a, ep, st);
+}
+
+b200collResult_t b200collBarrier(b200collComm_t c, b200collStream_t stream) {
+  if (!c) return b200collInvalidArgument;
+  if (c->nranks == 1) return b200collSuccess;
+  k_barrier<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, 99);
+  LAUNCH_CHECK(c);
+  return b200collSuccess;
+}
+
+}  // extern "C"

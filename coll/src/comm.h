@@ -1,0 +1,95 @@
+// Host-side communicator state for libb200coll.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../include/b200coll.h"
+#include "bootstrap.h"
+#include "device.cuh"
+
+namespace b200coll {
+
+// Driver entry points resolved at run time (cudaGetDriverEntryPoint) so the library loads — and its
+// CPU-side logic is testable — on a box without libcuda.
+#define B200COLL_DRV_FUNCS(X)                                                                                          \
+  X(cuMemCreate) X(cuMemRelease) X(cuMemMap) X(cuMemUnmap) X(cuMemAddressReserve) X(cuMemAddressFree)                   \
+  X(cuMemSetAccess) X(cuMemExportToShareableHandle) X(cuMemImportFromShareableHandle)                                  \
+  X(cuMemGetAllocationGranularity) X(cuMulticastCreate) X(cuMulticastAddDevice) X(cuMulticastBindMem)                  \
+  X(cuMulticastUnbind) X(cuMulticastGetGranularity) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuGetErrorString)         \
+  X(cuDriverGetVersion) X(cuDeviceGetUuid)
+
+struct Drv {
+#define X(n) decltype(&::n) n = nullptr;
+  B200COLL_DRV_FUNCS(X)
+#undef X
+  bool ok = false;
+  std::string why;
+};
+const Drv& drv();
+
+void set_last_error(const std::string& s);
+void dbg(int level, const char* fmt, ...);
+int debug_level();
+
+struct FreeBlock { size_t off, len; };
+
+struct Arena {
+  CUmemGenericAllocationHandle handle = 0;
+  size_t total = 0;               // bytes, granularity-rounded (control + heap)
+  int device = -1;
+};
+
+struct SharedGroup;   // in-process groups (InitAll) share ownership bookkeeping
+
+}  // namespace b200coll
+
+struct b200collComm {
+  int rank = 0, nranks = 1, device = 0;
+  b200collConfig cfg{};
+  b200coll::Arena arena;
+  CUdeviceptr peer_va[B200COLL_MAX_RANKS] = {};
+  CUmemGenericAllocationHandle peer_handle[B200COLL_MAX_RANKS] = {};   // imported (multi-process) or borrowed (in-process)
+  bool peer_handle_owned[B200COLL_MAX_RANKS] = {};
+  CUdeviceptr mc_va = 0;
+  CUmemGenericAllocationHandle mc_handle = 0;
+  bool mc_owned = false, mc_bound = false;
+  bool nvls = false, loopback = false;
+  int sm_count = 0, driver_version = 0;
+  uint32_t* state_dev = nullptr;
+  b200collFault* fault_host = nullptr;
+  b200collFault* fault_dev = nullptr;
+  b200coll::CommDev dev{};
+  std::unique_ptr<b200coll::Bootstrap> boot;
+  // symmetric heap allocator (offsets relative to arena base)
+  std::vector<b200coll::FreeBlock> free_list;
+  std::map<size_t, size_t> live;   // off -> len
+  std::mutex mu;
+  b200collAlgo_t forced_algo = b200collAlgoAuto;
+  int max_ctas = 0;
+  b200collStats stats{};
+  std::shared_ptr<b200coll::SharedGroup> group;
+  void* stats_shm = nullptr;       // exported stats page (metrics exporter reads it)
+  std::string stats_shm_name;
+};
+
+namespace b200coll {
+
+struct LaunchPlan {
+  b200collAlgo_t algo;
+  int blocks;
+  int threads;
+};
+
+// tuner.cc
+int tuner_blocks(b200collOp_t op, b200collAlgo_t algo, size_t work_vecs, int max_ctas, int unroll);
+
+// collectives.cu
+b200collResult_t launch_fill_sentinel(b200collComm* c, cudaStream_t s);
+
+}  // namespace b200coll

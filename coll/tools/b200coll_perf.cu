@@ -1,0 +1,323 @@
+// b200coll_perf — nccl-tests-style benchmark + correctness checker for libb200coll.
+// The reference's benchmark protocol (reference: gpudirect-tcpx/nccl-config.yaml:61-62,
+// gpudirect-rdma/nccl-test-a4x-max-jobset.yaml:141-153): `-b <min> -e <max> -f 2 -g 1 -w 5 --iters 100 -c 1`,
+// one rank per GPU, out-of-place and in-place, time = avg over iters, algbw = bytes/time,
+// busbw = algbw * {AR: 2(N-1)/N; AG/RS/A2A: (N-1)/N}.
+//
+// Modes:  default      one process, one host thread per rank, ranks from --devs (repeat a device id for
+//                      virtual ranks on one GPU: protocol tests on a single-GPU box)
+//         --procs      fork one process per rank and rendezvous over the Unix-socket bootstrap
+// Timing: CUDA events on each rank's stream around `iters` back-to-back launches, max over ranks.
+// Buffers rotate through a >L2 window so every timed launch sees cold lines.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/b200coll.h"
+
+#define RT(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s:%d %s -> %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); exit(2); } } while (0)
+#define CC(x) do { b200collResult_t r_ = (x); if (r_ != b200collSuccess) { fprintf(stderr, "b200coll %s:%d %s -> %s (%s)\n", __FILE__, __LINE__, #x, b200collGetErrorString(r_), b200collGetLastError()); exit(3); } } while (0)
+
+struct Opts {
+  std::string op = "all_reduce";
+  std::vector<int> devs;
+  int nranks = 0;
+  bool procs = false;
+  size_t min_bytes = 1024, max_bytes = 1ull << 30;
+  int factor = 2;
+  b200collDataType_t in_dt = b200collBfloat16, out_dt = b200collBfloat16;
+  float scale = 1.0f;
+  std::string algo = "auto";
+  int iters = 20, warmup = 5, check = 1;
+  int inplace = 2;   // 0 out-of-place only, 1 in-place only, 2 both
+  int max_ctas = 0;
+  size_t window = 192ull << 20;
+  std::string json;
+  int skew_us = 0;   // delay rank 0's launches (race hunting)
+};
+
+static size_t parse_size(const char* s) {
+  char* end; double v = strtod(s, &end);
+  if (*end == 'K' || *end == 'k') v *= 1024; else if (*end == 'M' || *end == 'm') v *= 1 << 20; else if (*end == 'G' || *end == 'g') v *= 1 << 30;
+  return (size_t)v;
+}
+static b200collDataType_t parse_dt(const char* s) {
+  if (!strcmp(s, "f32") || !strcmp(s, "float")) return b200collFloat32;
+  if (!strcmp(s, "f16") || !strcmp(s, "half")) return b200collFloat16;
+  if (!strcmp(s, "bf16")) return b200collBfloat16;
+  if (!strcmp(s, "fp8") || !strcmp(s, "e4m3")) return b200collFloat8e4m3;
+  fprintf(stderr, "bad dtype %s\n", s); exit(1);
+}
+static const char* dt_name(b200collDataType_t t) { return t == b200collFloat32 ? "f32" : t == b200collFloat16 ? "f16" : t == b200collBfloat16 ? "bf16" : "e4m3"; }
+
+// deterministic input: multiples of 0.25 in [-2, 2] so sums over <= 8 ranks are exact in bf16/f16/f32
+static inline float gen(int rank, size_t i) { return (float)((int)((i * 7 + (size_t)rank * 13 + (i >> 9)) % 17) - 8) * 0.25f; }
+
+template <typename T> __global__ void k_fill(T* p, size_t n, int rank, size_t base) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t g = base + i;
+    float v = (float)((int)((g * 7 + (size_t)rank * 13 + (g >> 9)) % 17) - 8) * 0.25f;
+    p[i] = T(v);
+  }
+}
+static void fill(void* p, size_t n, b200collDataType_t dt, int rank, size_t base, cudaStream_t st) {
+  if (dt == b200collFloat32) k_fill<float><<<256, 256, 0, st>>>((float*)p, n, rank, base);
+  else if (dt == b200collFloat16) k_fill<__half><<<256, 256, 0, st>>>((__half*)p, n, rank, base);
+  else k_fill<__nv_bfloat16><<<256, 256, 0, st>>>((__nv_bfloat16*)p, n, rank, base);
+}
+
+static float to_f(const void* p, size_t i, b200collDataType_t dt) {
+  switch (dt) {
+    case b200collFloat32: return ((const float*)p)[i];
+    case b200collFloat16: return __half2float(((const __half*)p)[i]);
+    case b200collBfloat16: return __bfloat162float(((const __nv_bfloat16*)p)[i]);
+    default: return (float)(((const __nv_fp8_e4m3*)p)[i]);
+  }
+}
+
+struct Shared {   // cross-process (mmap MAP_SHARED) or cross-thread rendezvous for timing
+  std::atomic<int> arrive[4];
+  float ms[B200COLL_MAX_RANKS];
+  long errors[B200COLL_MAX_RANKS];
+};
+
+static void spin_barrier(Shared* sh, int which, int n, int* gen) {
+  (*gen)++;
+  sh->arrive[which].fetch_add(1);
+  const time_t t0 = time(nullptr);
+  while (sh->arrive[which].load() < (*gen) * n) {
+    sched_yield();
+    if (time(nullptr) - t0 > 90) { fprintf(stderr, "host barrier %d timed out (a rank died?)\n", which); _exit(6); }
+  }
+}
+
+struct RankCtx { int rank, nranks; b200collComm_t comm; int dev; };
+
+// expected value of output element e (element index in the op's output) for this rank
+static float expected(const Opts& o, int rank, int n, size_t e, size_t count) {
+  if (o.op == "all_reduce") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, e); return s * o.scale; }
+  if (o.op == "all_gather") { int src = (int)(e / count); return gen(src, e % count) * o.scale; }
+  if (o.op == "reduce_scatter") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, (size_t)rank * count + e); return s * o.scale; }
+  /* alltoall */ { int src = (int)(e / count); return gen(src, (size_t)rank * count + e % count) * o.scale; }
+}
+
+static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
+  const int n = ctx.nranks, rank = ctx.rank;
+  RT(cudaSetDevice(ctx.dev));
+  cudaStream_t st; RT(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1; RT(cudaEventCreate(&e0)); RT(cudaEventCreate(&e1));
+  if (o.algo != "auto") {
+    for (int a = 0; a < b200collNumAlgos; a++) if (o.algo == b200collAlgoName((b200collAlgo_t)a)) CC(b200collCommSetAlgo(ctx.comm, (b200collAlgo_t)a));
+  }
+  if (o.max_ctas > 0) CC(b200collCommSetMaxCtas(ctx.comm, o.max_ctas));
+  const size_t is = b200collTypeSize(o.in_dt), os = b200collTypeSize(o.out_dt);
+  const bool is_ar = o.op == "all_reduce", is_ag = o.op == "all_gather", is_rs = o.op == "reduce_scatter";
+  // nccl-tests convention: "size" is the larger of the two buffers in bytes of the input type
+  const size_t max_in_bytes = o.max_bytes, max_out_bytes = o.max_bytes / is * os;
+  const size_t send_cap = std::max(o.window, max_in_bytes), recv_cap = std::max(o.window / is * os, max_out_bytes);
+  void *send = nullptr, *recv = nullptr;
+  CC(b200collMemAlloc(ctx.comm, &send, send_cap + 4096));
+  CC(b200collMemAlloc(ctx.comm, &recv, recv_cap + 4096));
+  b200collEpilogue ep{o.in_dt, o.out_dt, o.scale};
+  int gen_ctr[4] = {0, 0, 0, 0};
+  std::vector<char> host;
+  b200collCommInfo info; CC(b200collCommInfoGet(ctx.comm, &info));
+  if (rank == 0) {
+    printf("# b200coll_perf op=%s nranks=%d in=%s out=%s scale=%g algo=%s nvls=%d loopback=%d mode=%s\n", o.op.c_str(), n, dt_name(o.in_dt), dt_name(o.out_dt), o.scale, o.algo.c_str(),
+           info.nvls, info.same_device_loopback, o.procs ? "procs" : "threads");
+    printf("#%13s %12s %6s %8s | %10s %8s %8s %6s | %10s %8s %8s %6s\n", "size(B)", "count", "type", "algo", "oop us", "algbw", "busbw", "#wrong", "ip us", "algbw", "busbw", "#wrong");
+    fflush(stdout);
+  }
+  FILE* jf = (rank == 0 && !o.json.empty()) ? fopen(o.json.c_str(), "a") : nullptr;
+  long total_errors = 0;
+  for (size_t bytes = o.min_bytes; bytes <= o.max_bytes; bytes *= o.factor) {
+    // element counts per the op
+    size_t count;          // the `count` argument of the API
+    size_t in_elems, out_elems;
+    if (is_ar) { count = bytes / is; in_elems = out_elems = count; }
+    else if (is_ag) { count = bytes / is / n; in_elems = count; out_elems = count * n; }
+    else if (is_rs) { count = bytes / is / n; in_elems = count * n; out_elems = count; }
+    else { count = bytes / is / n; in_elems = out_elems = count * n; }
+    const size_t E = 16 / is;
+    if (!is_ar) count = count / E * E;
+    if (count == 0) continue;
+    if (!is_ar) { in_elems = is_ag ? count : count * n; out_elems = is_rs ? count : count * n; }
+    const size_t in_b = in_elems * is, out_b = out_elems * os;
+    const size_t slot_b = (std::max(in_b, out_b / os * is) + 4095) / 4096 * 4096;
+    int slots = (int)std::min<size_t>(64, std::max<size_t>(1, o.window / slot_b));
+    double res_us[2] = {-1, -1}; long res_err[2] = {0, 0};
+    const char* algo_used = "?";
+    for (int ip = 0; ip < 2; ip++) {
+      if ((ip == 0 && o.inplace == 1) || (ip == 1 && o.inplace == 0)) continue;
+      if (ip == 1 && (o.op == "alltoall" || is != os)) continue;
+      auto sbuf = [&](int slot) -> char* {
+        char* base = ip ? (char*)recv : (char*)send;
+        size_t off = (size_t)slot * slot_b;
+        if (ip && is_ag) off += (size_t)rank * count * os;     // in-place all-gather: send = recv + rank*count
+        return base + off;
+      };
+      auto rbuf = [&](int slot) -> char* {
+        size_t off = (size_t)slot * (ip ? slot_b : slot_b / is * os);
+        if (ip && is_rs) off += (size_t)rank * count * is;     // in-place reduce-scatter: recv = send + rank*count
+        return (char*)recv + off;
+      };
+      auto launch = [&](int slot) {
+        if (is_ar) CC(b200collAllReduce(sbuf(slot), rbuf(slot), count, &ep, b200collSum, ctx.comm, st));
+        else if (is_ag) CC(b200collAllGather(sbuf(slot), rbuf(slot), count, &ep, ctx.comm, st));
+        else if (is_rs) CC(b200collReduceScatter(sbuf(slot), rbuf(slot), count, &ep, b200collSum, ctx.comm, st));
+        else CC(b200collAllToAll(sbuf(slot), rbuf(slot), count, &ep, ctx.comm, st));
+      };
+      // ---- correctness on slot 0 (fresh data, poisoned output)
+      long errs = 0;
+      if (o.check) {
+        if (!ip) RT(cudaMemsetAsync(rbuf(0), 0x5A, out_b, st));
+        if (ip && is_ag) fill(sbuf(0), in_elems, o.in_dt, rank, 0, st);
+        else if (ip && is_rs) fill((char*)recv, in_elems, o.in_dt, rank, 0, st);
+        else fill(sbuf(0), in_elems, o.in_dt, rank, 0, st);
+        RT(cudaStreamSynchronize(st));
+        spin_barrier(sh, 0, n, &gen_ctr[0]);
+        if (o.skew_us && rank == 0) usleep(o.skew_us);
+        launch(0);
+        RT(cudaStreamSynchronize(st));
+        spin_barrier(sh, 1, n, &gen_ctr[1]);
+        b200collFault f;
+        if (b200collCommGetAsyncError(ctx.comm, &f) != b200collSuccess) { fprintf(stderr, "rank %d WATCHDOG code=%u peer=%u block=%u expected=%u observed=%u op=%u\n", rank, f.code, f.peer, f.block, f.expected, f.observed, f.op); _exit(5); }
+        const char* outp = (ip && is_rs) ? rbuf(0) : (ip ? (char*)recv : rbuf(0));
+        const size_t check_elems = out_elems;
+        host.resize(check_elems * os);
+        RT(cudaMemcpy(host.data(), outp, check_elems * os, cudaMemcpyDeviceToHost));
+        const size_t stride = check_elems > (1u << 22) ? 61 : 1;   // sample large buffers
+        for (size_t e = 0; e < check_elems; e += stride) {
+          const float want = expected(o, rank, n, e, count), got = to_f(host.data(), e, o.out_dt);
+          const float tol = o.out_dt == b200collFloat8e4m3 ? fabsf(want) * 0.0725f + 0.002f : 0.0f;
+          if (!(fabsf(got - want) <= tol)) { if (errs < 4) fprintf(stderr, "rank %d %s size %zu %s elem %zu: got %g want %g\n", rank, o.op.c_str(), bytes, ip ? "ip" : "oop", e, got, want); errs++; }
+        }
+      }
+      // ---- timing
+      for (int i = 0; i < o.warmup; i++) launch(i % slots);
+      RT(cudaStreamSynchronize(st));
+      spin_barrier(sh, 2, n, &gen_ctr[2]);
+      RT(cudaEventRecord(e0, st));
+      for (int i = 0; i < o.iters; i++) launch(i % slots);
+      RT(cudaEventRecord(e1, st));
+      RT(cudaEventSynchronize(e1));
+      float ms = 0; RT(cudaEventElapsedTime(&ms, e0, e1));
+      sh->ms[rank] = ms / o.iters; sh->errors[rank] = errs;
+      spin_barrier(sh, 3, n, &gen_ctr[3]);
+      float worst = 0; long es = 0;
+      for (int r = 0; r < n; r++) { worst = std::max(worst, sh->ms[r]); es += sh->errors[r]; }
+      res_us[ip] = worst * 1e3; res_err[ip] = es; total_errors += es;
+      spin_barrier(sh, 0, n, &gen_ctr[0]);   // keep ms[] stable until everyone has read it
+      b200collFault f;
+      if (b200collCommGetAsyncError(ctx.comm, &f) != b200collSuccess) { fprintf(stderr, "rank %d WATCHDOG (timing) code=%u peer=%u block=%u expected=%u observed=%u\n", rank, f.code, f.peer, f.block, f.expected, f.observed); _exit(5); }
+    }
+    if (rank == 0) {
+      size_t tb = is_ar ? count * is : count * is * n;   // nccl-tests "size"
+      b200collOp_t opid = is_ar ? b200collOpAllReduce : is_ag ? b200collOpAllGather : is_rs ? b200collOpReduceScatter : b200collOpAllToAll;
+      if (o.algo == "auto") algo_used = b200collAlgoName(b200collTunerPick(opid, is_ar ? count * is : count * is, n, info.nvls)); else algo_used = o.algo.c_str();
+      const double factor = is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
+      double ab[2], bb[2];
+      for (int ip = 0; ip < 2; ip++) { ab[ip] = res_us[ip] > 0 ? tb / res_us[ip] / 1e3 : 0; bb[ip] = n > 1 ? ab[ip] * factor : ab[ip]; }
+      printf("%14zu %12zu %6s %8s | %10.2f %8.2f %8.2f %6ld | %10.2f %8.2f %8.2f %6ld\n", tb, count, dt_name(o.in_dt), algo_used, res_us[0], ab[0], bb[0], res_err[0], res_us[1], ab[1], bb[1], res_err[1]);
+      fflush(stdout);
+      if (jf) {
+        fprintf(jf, "{\"op\":\"%s\",\"nranks\":%d,\"bytes\":%zu,\"in\":\"%s\",\"out\":\"%s\",\"scale\":%g,\"algo\":\"%s\",\"oop_us\":%.3f,\"ip_us\":%.3f,\"oop_busbw\":%.3f,\"ip_busbw\":%.3f,\"errors\":%ld,\"mode\":\"%s\"}\n",
+                o.op.c_str(), n, tb, dt_name(o.in_dt), dt_name(o.out_dt), o.scale, algo_used, res_us[0], res_us[1], bb[0], bb[1], res_err[0] + res_err[1], o.procs ? "procs" : "threads");
+        fflush(jf);
+      }
+    }
+  }
+  if (jf) fclose(jf);
+  b200collStats s; CC(b200collCommStatsGet(ctx.comm, &s));
+  if (rank == 0) printf("# launches=%llu staged_calls=%llu errors=%ld\n", (unsigned long long)s.kernel_launches, (unsigned long long)s.staged_calls, total_errors);
+  CC(b200collMemFree(ctx.comm, recv));
+  CC(b200collMemFree(ctx.comm, send));
+  RT(cudaStreamDestroy(st));
+  return total_errors ? 4 : 0;
+}
+
+int main(int argc, char** argv) {
+  Opts o;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return argv[++i]; };
+    if (a == "--op") o.op = next();
+    else if (a == "--ranks") o.nranks = atoi(next());
+    else if (a == "--devs") { std::string s = next(); size_t p = 0; while (p < s.size()) { o.devs.push_back(atoi(s.c_str() + p)); p = s.find(',', p); if (p == std::string::npos) break; p++; } }
+    else if (a == "--procs") o.procs = true;
+    else if (a == "-b" || a == "--min") o.min_bytes = parse_size(next());
+    else if (a == "-e" || a == "--max") o.max_bytes = parse_size(next());
+    else if (a == "-f" || a == "--factor") o.factor = atoi(next());
+    else if (a == "--dtype") o.in_dt = o.out_dt = parse_dt(next());
+    else if (a == "--out-dtype") o.out_dt = parse_dt(next());
+    else if (a == "--scale") o.scale = (float)atof(next());
+    else if (a == "--algo") o.algo = next();
+    else if (a == "--iters" || a == "-n") o.iters = atoi(next());
+    else if (a == "--warmup" || a == "-w") o.warmup = atoi(next());
+    else if (a == "--check" || a == "-c") o.check = atoi(next());
+    else if (a == "--inplace") o.inplace = atoi(next());
+    else if (a == "--max-ctas") o.max_ctas = atoi(next());
+    else if (a == "--window") o.window = parse_size(next());
+    else if (a == "--json") o.json = next();
+    else if (a == "--skew-us") o.skew_us = atoi(next());
+    else if (a == "--selfcheck") { char buf[4096]; b200collResult_t r = b200collSelfCheck(buf, sizeof(buf)); fputs(buf, stdout); return r == b200collSuccess ? 0 : 1; }
+    else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 1; }
+  }
+  if (o.factor < 2) o.factor = 2;
+  if (o.devs.empty()) {
+    int nd = 0; cudaGetDeviceCount(&nd);
+    if (o.nranks == 0) o.nranks = nd > 0 ? nd : 1;
+    for (int i = 0; i < o.nranks; i++) o.devs.push_back(nd > 0 ? i % nd : 0);
+  }
+  o.nranks = (int)o.devs.size();
+  const int n = o.nranks;
+  Shared* sh = (Shared*)mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  memset(sh, 0, sizeof(Shared));
+  b200collConfig cfg; b200collConfigDefault(&cfg);
+  // arena: two windows (+ max buffers) and slack
+  const size_t is_ = b200collTypeSize(o.in_dt), os_ = b200collTypeSize(o.out_dt);
+  size_t need = std::max(o.window, o.max_bytes) + std::max(o.window / is_ * os_, o.max_bytes / is_ * os_) + (64u << 20);
+  if (!getenv("B200COLL_ARENA_MB")) cfg.arena_bytes = need;
+  if (o.procs) {
+    b200collUniqueId id; CC(b200collGetUniqueId(&id));
+    std::vector<pid_t> kids;
+    for (int r = 0; r < n; r++) {
+      pid_t p = fork();
+      if (p == 0) {
+        RT(cudaSetDevice(o.devs[r]));
+        b200collComm_t comm;
+        CC(b200collCommInitRank(&comm, n, &id, r, &cfg));
+        int rc = run_rank(o, RankCtx{r, n, comm, o.devs[r]}, sh);
+        CC(b200collCommDestroy(comm));
+        _exit(rc);
+      }
+      kids.push_back(p);
+    }
+    int worst = 0;
+    for (pid_t p : kids) { int stt = 0; waitpid(p, &stt, 0); int rc = WIFEXITED(stt) ? WEXITSTATUS(stt) : 128; worst = std::max(worst, rc); }
+    return worst;
+  }
+  std::vector<b200collComm_t> comms(n);
+  CC(b200collCommInitAll(comms.data(), n, o.devs.data(), &cfg));
+  std::vector<std::thread> th;
+  std::vector<int> rcs(n, 0);
+  for (int r = 0; r < n; r++) th.emplace_back([&, r] { rcs[r] = run_rank(o, RankCtx{r, n, comms[r], o.devs[r]}, sh); });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < n; r++) CC(b200collCommDestroy(comms[r]));
+  int worst = 0; for (int rc : rcs) worst = std::max(worst, rc);
+  return worst;
+}
