@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Headline benchmark: all_reduce_perf bus GB/s, 1 KB - 1 GB, bf16 sum (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 --steps 20 --warmup 5
+    ... --impl reference      # stock NCCL through its C API under the reference's env profile (see nccl_ref.py)
+
+A "step" is one pass over the 21-size sweep (1 KB..1 GB, x2), out-of-place and in-place. Following the
+reference's nccl-tests protocol each size's `--steps` iterations are launched back to back and timed with
+CUDA events on the launching stream (after `--warmup` untimed launches), bracketed by a cross-rank barrier
+and torch.cuda.synchronize(); every number is the max over ranks. `value` is nccl-tests' "Avg bus bandwidth".
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def parse_size(s: str) -> int:
+    s = s.strip().upper()
+    mult = {"K": 1 << 10, "M": 1 << 20, "G": 1 << 30}
+    return int(float(s[:-1]) * mult[s[-1]]) if s[-1] in mult else int(s)
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--op", default="all_reduce", choices=["all_reduce", "all_gather", "reduce_scatter", "alltoall"])
+    ap.add_argument("--min", default="1K")
+    ap.add_argument("--max", default="1G")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--table", action="store_true", help="also print the nccl-tests style table to stderr")
+    args = ap.parse_args()
+    warmup = max(3, args.warmup)
+
+    try:
+        import torch
+    except Exception as e:   # pragma: no cover
+        print(json.dumps({"impl": args.impl, "unavailable": f"torch import failed: {e}"}))
+        return 0
+    from container_engine_accelerators_b200.parallel import harness
+    from container_engine_accelerators_b200.utils.clocks import ClockSampler
+
+    dist = harness.Dist()
+    if dist.world != args.gpus:
+        if dist.rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={dist.world}; launch with torchrun --nproc-per-node {args.gpus}", file=sys.stderr)
+        return 2
+    if not torch.cuda.is_available():
+        if dist.rank == 0:
+            print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device visible"}))
+        return 0
+    torch.cuda.set_device(dist.local_rank)
+    dtype = torch.bfloat16
+    min_b, max_b = parse_size(args.min), parse_size(args.max)
+    cap = max(max_b, harness.WINDOW) // 2 + 4096
+
+    if args.impl == "reference":
+        try:
+            backend = harness.NcclBackend(dist, cap, dtype)
+        except Exception as e:
+            if dist.rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": f"stock NCCL could not be initialised: {e}"[:300]}))
+            return 0
+    else:
+        backend = harness.OursBackend(dist, cap, dtype)   # raises if libb200coll.so is missing: no silent fallback
+
+    n = dist.world
+    verified = harness.verify(backend, dist, args.op, dtype) if n > 1 else True
+    launches0 = backend.launches()
+    t_wall = time.time()
+    with ClockSampler(dist.local_rank) as clk:
+        rows = harness.sweep(backend, dist, args.op, dtype, args.steps, warmup, min_b, max_b, placements=(0, 1))
+    launches = backend.launches() - launches0
+    clocks = clk.summary()
+    e2e = None
+    if not args.no_e2e:
+        e2e_rows = harness.sweep(backend, dist, args.op, dtype, max(2, min(args.steps, 10)), min(warmup, 3), min_b, max_b, placements=(), e2e=True)
+        s2 = harness.summarize(e2e_rows, args.op, n)
+        h2d = sum(r.in_bytes for r in e2e_rows)
+        e2e = {"value": round(s2["avg_e2e_busbw"] or 0.0, 3), "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4096 * len(e2e_rows),
+               "note": "per size: pinned-host->device copy of the input, the collective, 4 KiB device->host read of the result, all on one stream"}
+    wall = time.time() - t_wall
+    summ = harness.summarize(rows, args.op, n)
+    if dist.rank == 0:
+        if args.table:
+            print(harness.format_table(rows, args.op, n, f"{backend.version} {args.op} nranks={n}"), file=sys.stderr)
+        metric = f"{args.op}_perf avg bus GB/s 1KB-1GB bf16 sum (nccl-tests protocol, device-timed, max over ranks)"
+        if n == 1:
+            metric += " [1 rank: busbw factor is 0 by definition, value is algbw of the fused scale/cast copy]"
+        out = {
+            "metric": metric, "value": round(summ["avg_busbw"], 3), "unit": "GB/s", "n_gpus": n, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": round(summ["sweep_ms"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (deterministic random-like bf16 buffers; no network, no dataset)",
+            "impl": "reference" if args.impl == "reference" else "ours",
+            "config": {"model": "none (collective benchmark: the reference has no model code)", "benchmark": f"{args.op}_perf", "sizes": f"{args.min}..{args.max} x2",
+                       "global_batch": None, "seq_len": None, "parallelism": f"1 rank per GPU x{n}", "placements": "out-of-place + in-place",
+                       "l2": "buffers rotate through a 192 MiB window (> 126 MB L2); sizes >= 192 MiB exceed L2 by themselves",
+                       "backend": backend.version, "aggregate": "nccl-tests bus bandwidth (per-link hardware rate), not multiplied by N"},
+            "peak_busbw": round(summ["peak_busbw"], 2), "aggregate_bus_gbs": round(summ["avg_busbw"] * n, 2), "verified_vs_torch_fp32": bool(verified),
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "power_w_max": clocks["power_w_max"]},
+            "gpu_launches": int(summ["measurements"] * args.steps) if args.impl == "ours" else 0, "gpu_launches_incl_warmup": int(launches), "e2e": e2e, "wall_s": round(wall, 2), "table": harness.rows_json(rows, args.op, n),
+        }
+        if args.impl == "reference":
+            out["reference_note"] = ("the reference repo ships no collective code or Python package; its nccl-test manifests run NCCL's *_perf on the node "
+                                     "(net plugins are off the intra-node path), so this arm is the image's stock libnccl called through its C API with the "
+                                     "reference's NCCL env profile (gpudirect-tcpxo/README.md:71-103); pip install of /root/reference: see DESIGN.md")
+        print(json.dumps(out), flush=True)
+    backend.close()
+    dist.close()
+    return 0 if verified else 3
+
+
+if __name__ == "__main__":
+    sys.exit(main())

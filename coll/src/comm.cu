@@ -103,6 +103,7 @@ static long env_long(const char* name, long dflt) {
 // In-process groups: rank 0's record owns nothing special, but arenas must outlive every mapping.
 struct SharedGroup {
   std::atomic<int> alive{0};
+  std::atomic<int> mc_refs{0};
 };
 
 static CUmemAllocationProp arena_prop(int device) {
@@ -225,7 +226,9 @@ static void destroy_resources(b200collComm* c) {
     CUdevice dev;
     if (d.cuDeviceGet(&dev, c->device) == CUDA_SUCCESS) d.cuMulticastUnbind(c->mc_handle, dev, 0, c->arena.total);
   }
-  if (c->mc_handle && c->mc_owned) d.cuMemRelease(c->mc_handle);
+  bool release_mc = c->mc_owned;
+  if (c->group) release_mc = c->mc_handle && (--c->group->mc_refs == 0);   // in-process group: last one out releases
+  if (c->mc_handle && release_mc) d.cuMemRelease(c->mc_handle);
   c->mc_handle = 0;
   for (int r = 0; r < c->nranks; r++) {
     if (c->peer_va[r]) { unmap_va(c->peer_va[r], c->arena.total); c->peer_va[r] = 0; }
@@ -470,7 +473,7 @@ b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* de
     for (int i = 0; ok && i < n; i++) { CUdevice cudev; d.cuDeviceGet(&cudev, cs[i]->device); ok = d.cuMulticastAddDevice(mch, cudev) == CUDA_SUCCESS; }
     for (int i = 0; ok && i < n; i++) { ok = d.cuMulticastBindMem(mch, 0, cs[i]->arena.handle, 0, g.total, 0) == CUDA_SUCCESS; if (ok) { cs[i]->mc_bound = true; cs[i]->mc_handle = mch; } }
     for (int i = 0; ok && i < n; i++) ok = map_handle(cs[i]->device, mch, g.total, g.mc_gran, &cs[i]->mc_va) == b200collSuccess;
-    if (ok) { cs[0]->mc_owned = true; for (auto& c : cs) { c->mc_handle = mch; c->nvls = true; } }
+    if (ok) { group->mc_refs = n; for (auto& c : cs) { c->mc_handle = mch; c->nvls = true; } }
     else {
       dbg(1, "NVLS disabled for in-process group: %s", cu_err(cr).c_str());
       for (auto& c : cs) { if (c->mc_va) { unmap_va(c->mc_va, g.total); c->mc_va = 0; } c->nvls = false; }

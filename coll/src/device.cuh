@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t load_seq(const CommDev& c, int which) { retu
 
 __device__ __forceinline__ bool last_block_ticket(const CommDev& c) {
   // call from one thread per block after the block's work is complete
+  if (gridDim.x == 1) return true;
   __threadfence();
   uint32_t t = atomicAdd(c.state + kTicket, 1u);
   if (t == gridDim.x - 1) { c.state[kTicket] = 0; return true; }
@@ -90,6 +91,13 @@ __device__ __forceinline__ bool last_block_ticket(const CommDev& c) {
 
 // Block b of every rank meets block b of every other rank. RELEASE=true publishes this block's prior
 // writes (local or peer) system-wide before signalling; the wait side is always an acquire.
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 template <bool RELEASE>
 __device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch, uint32_t op) {
   __syncthreads();
@@ -98,16 +106,18 @@ __device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch,
     uint32_t* remote = reinterpret_cast<uint32_t*>(c.peer[t] + kOffFlags) + (size_t)blockIdx.x * kMaxRanks + c.rank;
     if (RELEASE) st_release_sys(remote, epoch); else st_relaxed_sys(remote, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.peer[c.rank] + kOffFlags) + (size_t)blockIdx.x * kMaxRanks + t;
-    uint32_t v = ld_acquire_sys(mine);
+    // Poll with relaxed loads (an acquire per poll would re-fence every iteration), then one acquire fence.
+    uint32_t v = ld_relaxed_sys(mine);
     if ((int32_t)(v - epoch) < 0) {
       const unsigned long long t0 = globaltimer_ns();
       uint32_t spins = 0;
-      while ((int32_t)((v = ld_acquire_sys(mine)) - epoch) < 0) {
+      while ((int32_t)((v = ld_relaxed_sys(mine)) - epoch) < 0) {
         if (((++spins) & 0x3FF) == 0) {
           if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 1, t, epoch, v, op); break; }
         }
       }
     }
+    fence_acq_rel_sys();
   }
   __syncthreads();
 }

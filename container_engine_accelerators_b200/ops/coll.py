@@ -1,0 +1,309 @@
+"""ctypes binding for libb200coll (coll/lib/libb200coll.so) — the only thing PyTorch is used for here is
+launching ranks and holding the synthetic buffers (BASELINE.json north-star: "PyTorch is only the harness").
+
+The library is the transport-installer payload (reference role: gpudirect-rdma/nccl-rdma-installer.yaml:70-77);
+this module is what a pod's Python code imports once the device plugin's Allocate has mounted it.
+Fails loudly when the shared object is missing on a GPU box — there is no eager/PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+REPO_ROOT = Path(__file__).resolve().parents[2]
+_LIB_CANDIDATES = [
+    os.environ.get("B200COLL_LIB", ""),
+    str(REPO_ROOT / "coll" / "lib" / "libb200coll.so"),
+    "/usr/local/nvidia/lib64/libb200coll.so",   # where Allocate mounts the installer's drop
+    "libb200coll.so",
+]
+
+SUCCESS = 0
+NO_DRIVER = 9
+MAX_RANKS = 8
+
+F32, F16, BF16, FP8_E4M3 = 0, 1, 2, 3
+SUM, AVG = 0, 1
+OP_ALLREDUCE, OP_ALLGATHER, OP_REDUCESCATTER, OP_ALLTOALL = 0, 1, 2, 3
+ALGO_AUTO, ALGO_LL, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_COPY = range(6)
+ALGO_NAMES = ["auto", "ll", "oneshot", "twoshot", "nvls", "copy"]
+DTYPE_SIZE = {F32: 4, F16: 2, BF16: 2, FP8_E4M3: 1}
+
+
+class UniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("in_dtype", C.c_int), ("out_dtype", C.c_int), ("scale", C.c_float)]
+
+
+class Config(C.Structure):
+    _fields_ = [("arena_bytes", C.c_size_t), ("enable_nvls", C.c_int), ("max_ctas", C.c_int), ("timeout_ms", C.c_int), ("debug", C.c_int)]
+
+
+class CommInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int), ("nvls", C.c_int), ("p2p_ok", C.c_int),
+                ("same_device_loopback", C.c_int), ("arena_bytes", C.c_size_t), ("arena_used", C.c_size_t), ("sm_count", C.c_int),
+                ("driver_version", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("calls", C.c_uint64 * 4), ("bytes", C.c_uint64 * 4), ("algo_calls", C.c_uint64 * 6), ("kernel_launches", C.c_uint64),
+                ("staged_calls", C.c_uint64)]
+
+
+class Fault(C.Structure):
+    _fields_ = [("code", C.c_uint32), ("rank", C.c_uint32), ("peer", C.c_uint32), ("block", C.c_uint32), ("expected", C.c_uint32),
+                ("observed", C.c_uint32), ("op", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class B200CollError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str):
+        super().__init__(f"{what}: {detail}" if detail else what)
+        self.code = code
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> Optional[str]:
+    for cand in _LIB_CANDIDATES[:-1]:
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def load() -> C.CDLL:
+    """dlopen the library once and declare prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    last = None
+    for cand in _LIB_CANDIDATES:
+        if not cand:
+            continue
+        try:
+            _lib = C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            break
+        except OSError as e:   # keep looking
+            last = e
+    if _lib is None:
+        raise ImportError(f"libb200coll.so not found (run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C coll`): {last}")
+    L = _lib
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+    L.b200collGetErrorString.restype = C.c_char_p; L.b200collGetErrorString.argtypes = [ci]
+    L.b200collGetLastError.restype = C.c_char_p
+    L.b200collGetVersion.restype = ci
+    L.b200collConfigDefault.argtypes = [C.POINTER(Config)]
+    L.b200collGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+    L.b200collUniqueIdFromString.argtypes = [C.c_char_p, C.POINTER(UniqueId)]
+    L.b200collCommInitRank.argtypes = [C.POINTER(vp), ci, C.POINTER(UniqueId), ci, C.POINTER(Config)]
+    L.b200collCommInitAll.argtypes = [C.POINTER(vp), ci, C.POINTER(ci), C.POINTER(Config)]
+    L.b200collCommDestroy.argtypes = [vp]
+    L.b200collCommInfoGet.argtypes = [vp, C.POINTER(CommInfo)]
+    L.b200collCommStatsGet.argtypes = [vp, C.POINTER(Stats)]
+    L.b200collCommGetAsyncError.argtypes = [vp, C.POINTER(Fault)]
+    L.b200collHostBarrier.argtypes = [vp]
+    L.b200collMemAlloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.b200collMemFree.argtypes = [vp, vp]
+    L.b200collIsSymmetric.argtypes = [vp, vp, sz]
+    L.b200collAllReduce.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
+    L.b200collAllGather.argtypes = [vp, vp, sz, C.POINTER(Epilogue), vp, vp]
+    L.b200collReduceScatter.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
+    L.b200collAllToAll.argtypes = [vp, vp, sz, C.POINTER(Epilogue), vp, vp]
+    L.b200collAllToAllv.argtypes = [vp, vp, sz, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Epilogue), vp, vp]
+    L.b200collBarrier.argtypes = [vp, vp]
+    L.b200collTunerPick.argtypes = [ci, sz, ci, ci]; L.b200collTunerPick.restype = ci
+    L.b200collCommSetAlgo.argtypes = [vp, ci]
+    L.b200collCommSetMaxCtas.argtypes = [vp, ci]
+    L.b200collAlgoName.argtypes = [ci]; L.b200collAlgoName.restype = C.c_char_p
+    L.b200collTypeSize.argtypes = [ci]; L.b200collTypeSize.restype = sz
+    L.b200collSelfCheck.argtypes = [C.c_char_p, sz]
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != SUCCESS:
+        L = load()
+        raise B200CollError(rc, f"{what}: {L.b200collGetErrorString(rc).decode()}", L.b200collGetLastError().decode())
+
+
+def tuner_pick(op: int, nbytes: int, nranks: int, nvls: bool) -> str:
+    return ALGO_NAMES[load().b200collTunerPick(op, nbytes, nranks, 1 if nvls else 0)]
+
+
+def self_check() -> tuple[bool, str]:
+    buf = C.create_string_buffer(8192)
+    rc = load().b200collSelfCheck(buf, len(buf))
+    return rc == SUCCESS, buf.value.decode()
+
+
+def torch_dtype_code(dtype) -> int:
+    import torch
+    return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float8_e4m3fn: FP8_E4M3}[dtype]
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias arena memory without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+@dataclass
+class SymBuffer:
+    ptr: int
+    nbytes: int
+
+
+class Comm:
+    """One communicator rank. `Comm.from_env()` under torchrun; `Comm.init_all()` for in-process groups."""
+
+    def __init__(self, handle: int, owner_group=None):
+        self._h = C.c_void_p(handle)
+        self._group = owner_group
+        self._allocs: dict[int, int] = {}
+        info = CommInfo()
+        _check(load().b200collCommInfoGet(self._h, C.byref(info)), "CommInfoGet")
+        self.rank, self.nranks, self.device, self.nvls = info.rank, info.nranks, info.device, bool(info.nvls)
+        self.loopback = bool(info.same_device_loopback)
+        self.sm_count = info.sm_count
+
+    # ---------------------------------------------------------------- construction
+    @staticmethod
+    def make_config(arena_mb: Optional[int] = None, nvls: Optional[int] = None, timeout_ms: Optional[int] = None) -> Config:
+        cfg = Config()
+        load().b200collConfigDefault(C.byref(cfg))
+        if arena_mb is not None:
+            cfg.arena_bytes = int(arena_mb) << 20
+        if nvls is not None:
+            cfg.enable_nvls = nvls
+        if timeout_ms is not None:
+            cfg.timeout_ms = timeout_ms
+        return cfg
+
+    @classmethod
+    def from_env(cls, arena_mb: Optional[int] = None, tag: str = "0", **kw) -> "Comm":
+        """torchrun-style: RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT. The caller has already
+        selected its GPU (torch.cuda.set_device(LOCAL_RANK))."""
+        rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+        key = f"{os.environ.get('MASTER_ADDR', '127.0.0.1')}:{os.environ.get('MASTER_PORT', '0')}/{os.environ.get('TORCHELASTIC_RUN_ID', '')}/{tag}"
+        return cls.init_rank(rank, world, key, arena_mb=arena_mb, **kw)
+
+    @classmethod
+    def init_rank(cls, rank: int, nranks: int, key: str, arena_mb: Optional[int] = None, **kw) -> "Comm":
+        L = load()
+        uid = UniqueId()
+        _check(L.b200collUniqueIdFromString(key.encode(), C.byref(uid)), "UniqueIdFromString")
+        cfg = cls.make_config(arena_mb, **kw)
+        h = C.c_void_p()
+        _check(L.b200collCommInitRank(C.byref(h), nranks, C.byref(uid), rank, C.byref(cfg)), "CommInitRank")
+        return cls(h.value)
+
+    @classmethod
+    def init_all(cls, devices: list[int], arena_mb: Optional[int] = None, **kw) -> list["Comm"]:
+        L = load()
+        n = len(devices)
+        hs = (C.c_void_p * n)()
+        devs = (C.c_int * n)(*devices)
+        cfg = cls.make_config(arena_mb, **kw)
+        _check(L.b200collCommInitAll(hs, n, devs, C.byref(cfg)), "CommInitAll")
+        return [cls(hs[i]) for i in range(n)]
+
+    def destroy(self) -> None:
+        if self._h:
+            load().b200collCommDestroy(self._h)
+            self._h = None
+
+    # ---------------------------------------------------------------- memory
+    def alloc(self, nbytes: int) -> SymBuffer:
+        p = C.c_void_p()
+        _check(load().b200collMemAlloc(self._h, C.byref(p), nbytes), "MemAlloc")
+        self._allocs[p.value] = nbytes
+        return SymBuffer(p.value, nbytes)
+
+    def free(self, buf: SymBuffer) -> None:
+        _check(load().b200collMemFree(self._h, C.c_void_p(buf.ptr)), "MemFree")
+        self._allocs.pop(buf.ptr, None)
+
+    def empty(self, numel: int, dtype):
+        """A torch tensor living in the symmetric arena (zero-copy fast paths, NVLS capable)."""
+        import torch
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        buf = self.alloc(numel * itemsize)
+        raw = torch.as_tensor(_CudaArray(buf.ptr, buf.nbytes, self), device=torch.device("cuda", self.device))
+        t = raw.view(dtype)[:numel]
+        t._b200coll_buf = buf   # keep the allocation discoverable
+        return t
+
+    def is_symmetric(self, tensor) -> bool:
+        return bool(load().b200collIsSymmetric(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size()))
+
+    # ---------------------------------------------------------------- collectives (tensors)
+    @staticmethod
+    def _stream(stream) -> C.c_void_p:
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream()
+        return C.c_void_p(s.cuda_stream)
+
+    def _ep(self, src, dst, scale: float) -> Epilogue:
+        return Epilogue(torch_dtype_code(src.dtype), torch_dtype_code(dst.dtype), float(scale))
+
+    def all_reduce(self, src, dst=None, scale: float = 1.0, op: int = SUM, stream=None):
+        dst = src if dst is None else dst
+        ep = self._ep(src, dst, scale)
+        _check(load().b200collAllReduce(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), op, self._h, self._stream(stream)), "AllReduce")
+        return dst
+
+    def all_gather(self, src, dst, scale: float = 1.0, stream=None):
+        ep = self._ep(src, dst, scale)
+        _check(load().b200collAllGather(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), self._h, self._stream(stream)), "AllGather")
+        return dst
+
+    def reduce_scatter(self, src, dst, scale: float = 1.0, op: int = SUM, stream=None):
+        ep = self._ep(src, dst, scale)
+        _check(load().b200collReduceScatter(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), dst.numel(), C.byref(ep), op, self._h, self._stream(stream)), "ReduceScatter")
+        return dst
+
+    def all_to_all(self, src, dst, scale: float = 1.0, stream=None):
+        ep = self._ep(src, dst, scale)
+        _check(load().b200collAllToAll(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel() // self.nranks, C.byref(ep), self._h, self._stream(stream)), "AllToAll")
+        return dst
+
+    def all_to_all_v(self, src, dst, row_elems: int, send_rows, send_row_off, recv_row_off_at_peer, scale: float = 1.0, stream=None):
+        ep = self._ep(src, dst, scale)
+        n = self.nranks
+        arr = lambda xs: (C.c_int64 * n)(*[int(x) for x in xs])
+        _check(load().b200collAllToAllv(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), row_elems, arr(send_rows), arr(send_row_off), arr(recv_row_off_at_peer),
+                                        C.byref(ep), self._h, self._stream(stream)), "AllToAllv")
+        return dst
+
+    def barrier(self, stream=None) -> None:
+        _check(load().b200collBarrier(self._h, self._stream(stream)), "Barrier")
+
+    def host_barrier(self) -> None:
+        _check(load().b200collHostBarrier(self._h), "HostBarrier")
+
+    # ---------------------------------------------------------------- control / introspection
+    def set_algo(self, name: str) -> None:
+        _check(load().b200collCommSetAlgo(self._h, ALGO_NAMES.index(name)), "CommSetAlgo")
+
+    def set_max_ctas(self, n: int) -> None:
+        _check(load().b200collCommSetMaxCtas(self._h, n), "CommSetMaxCtas")
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(load().b200collCommStatsGet(self._h, C.byref(s)), "CommStatsGet")
+        return {"calls": list(s.calls), "bytes": list(s.bytes), "algo_calls": dict(zip(ALGO_NAMES, s.algo_calls)),
+                "kernel_launches": s.kernel_launches, "staged_calls": s.staged_calls}
+
+    def check_async_error(self) -> None:
+        f = Fault()
+        rc = load().b200collCommGetAsyncError(self._h, C.byref(f))
+        if rc != SUCCESS:
+            raise B200CollError(rc, "watchdog", f"code={f.code} rank={f.rank} peer={f.peer} block={f.block} expected={f.expected} observed={f.observed} op={f.op}")

@@ -1,0 +1,348 @@
+"""nccl-tests-protocol sweep harness shared by bench.py and bench/*_perf.py.
+
+Protocol (reference: gpudirect-tcpx/nccl-config.yaml:61-62 `-b .. -e .. -f 2 -g 1 -w 5 --iters 100`,
+gpudirect-rdma/nccl-test-a4x-max-jobset.yaml:141-153): one rank per GPU, per message size `warmup` untimed
+launches then `steps` back-to-back launches timed with CUDA events on the launching stream, bracketed by a
+cross-rank barrier + device synchronize; time = max over ranks; algbw = bytes/time; busbw = algbw x
+{all_reduce: 2(N-1)/N, others: (N-1)/N}; out-of-place and in-place; "Avg bus bandwidth" = mean over every
+measured (size, placement). Buffers rotate through a >L2 window (192 MiB > 126 MB) so no timed launch
+re-reads lines left in L2 by the previous one.
+
+Two arms, same harness, same buffers sizes, same ctypes-level call overhead:
+  ours       libb200coll on symmetric-arena tensors (container_engine_accelerators_b200.ops.coll)
+  reference  stock libnccl through its C API (container_engine_accelerators_b200.parallel.nccl_ref)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from dataclasses import dataclass, field
+
+OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall")
+WINDOW = 192 << 20
+
+
+def bus_factor(op: str, n: int) -> float:
+    if n <= 1:
+        return 1.0   # nccl-tests prints busbw 0 for one rank; we report algbw there and say so
+    return 2.0 * (n - 1) / n if op == "all_reduce" else (n - 1) / n
+
+
+@dataclass
+class Row:
+    nbytes: int
+    count: int
+    algo: str
+    oop_us: float = -1.0
+    ip_us: float = -1.0
+    e2e_us: float = -1.0
+    in_bytes: int = 0
+
+    def bw(self, op: str, n: int) -> dict:
+        f = bus_factor(op, n)
+        ab = lambda us: (self.nbytes / us / 1e3) if us > 0 else 0.0
+        return {"oop_algbw": ab(self.oop_us), "ip_algbw": ab(self.ip_us), "oop_busbw": ab(self.oop_us) * f, "ip_busbw": ab(self.ip_us) * f,
+                "e2e_busbw": ab(self.e2e_us) * f}
+
+
+class Dist:
+    """CPU-side control plane (gloo): barrier and max-over-ranks. world_size 1 is a no-op."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29500")
+                dist.init_process_group("gloo")
+            self.pg = dist
+
+    def barrier(self):
+        if self.pg:
+            self.pg.barrier()
+
+    def max_(self, values):
+        import torch
+        t = torch.tensor(values, dtype=torch.float64)
+        if self.pg:
+            self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_(self, values):
+        import torch
+        t = torch.tensor(values, dtype=torch.float64)
+        if self.pg:
+            self.pg.all_reduce(t, op=self.pg.ReduceOp.SUM)
+        return t.tolist()
+
+    def bcast_bytes(self, b: bytes | None, n: int) -> bytes:
+        import torch
+        t = torch.zeros(n, dtype=torch.uint8)
+        if self.rank == 0:
+            t.copy_(torch.frombuffer(bytearray(b), dtype=torch.uint8))
+        if self.pg:
+            self.pg.broadcast(t, src=0)
+        return bytes(t.numpy().tobytes())
+
+    def close(self):
+        if self.pg and self.pg.is_initialized():
+            self.pg.destroy_process_group()
+
+
+class OursBackend:
+    name = "b200coll"
+
+    def __init__(self, dist: Dist, capacity_elems: int, dtype, tag: str = "bench"):
+        import torch
+        from ..ops import coll
+        self.coll, self.torch = coll, torch
+        itemsize = 2
+        arena_mb = (2 * capacity_elems * itemsize >> 20) + 128
+        if dist.world > 1:
+            self.comm = coll.Comm.from_env(arena_mb=arena_mb, tag=tag)
+        else:
+            self.comm = coll.Comm.init_all([dist.local_rank], arena_mb=arena_mb)[0]
+        self.send = self.comm.empty(capacity_elems, dtype)
+        self.recv = self.comm.empty(capacity_elems, dtype)
+        self.L = coll.load()
+        self.ep = coll.Epilogue(coll.torch_dtype_code(dtype), coll.torch_dtype_code(dtype), 1.0)
+        self.h = self.comm._h
+        self.nvls = self.comm.nvls
+        self.version = f"libb200coll {self.L.b200collGetVersion()} nvls={int(self.nvls)}"
+
+    def algo(self, op: str, nbytes_per_rank: int) -> str:
+        opid = OPS.index(op)
+        return self.coll.tuner_pick(opid, nbytes_per_rank, self.comm.nranks, self.nvls)
+
+    def launch(self, op: str, send_ptr: int, recv_ptr: int, count: int, stream: int) -> None:
+        L, ep = self.L, C.byref(self.ep)
+        if op == "all_reduce":
+            rc = L.b200collAllReduce(send_ptr, recv_ptr, count, ep, 0, self.h, stream)
+        elif op == "all_gather":
+            rc = L.b200collAllGather(send_ptr, recv_ptr, count, ep, self.h, stream)
+        elif op == "reduce_scatter":
+            rc = L.b200collReduceScatter(send_ptr, recv_ptr, count, ep, 0, self.h, stream)
+        else:
+            rc = L.b200collAllToAll(send_ptr, recv_ptr, count, ep, self.h, stream)
+        if rc != 0:
+            raise RuntimeError(f"b200coll {op}: {L.b200collGetErrorString(rc).decode()}: {L.b200collGetLastError().decode()}")
+
+    def launches(self) -> int:
+        return int(self.comm.stats()["kernel_launches"])
+
+    def check(self) -> None:
+        self.comm.check_async_error()
+
+    def close(self):
+        self.comm.destroy()
+
+
+class NcclBackend:
+    name = "nccl"
+
+    def __init__(self, dist: Dist, capacity_elems: int, dtype):
+        import torch
+        from . import nccl_ref
+        self.torch = torch
+        for k, v in nccl_ref.REFERENCE_ENV.items():
+            os.environ.setdefault(k, v)
+        uid = nccl_ref.NcclComm.new_unique_id() if dist.rank == 0 else None
+        uid = dist.bcast_bytes(uid, 128)
+        self.comm = nccl_ref.NcclComm(dist.rank, dist.world, uid)
+        self.send = torch.empty(capacity_elems, dtype=dtype, device="cuda")
+        self.recv = torch.empty(capacity_elems, dtype=dtype, device="cuda")
+        self.dt = {torch.bfloat16: nccl_ref.NCCL_BFLOAT16, torch.float16: nccl_ref.NCCL_FLOAT16, torch.float32: nccl_ref.NCCL_FLOAT32}[dtype]
+        self.itemsize = self.send.element_size()
+        self.nvls = None
+        self.version = f"NCCL {self.comm.version} ({os.path.basename(self.comm.path)})"
+        self._launches = 0
+
+    def algo(self, op, nbytes):
+        return "nccl"
+
+    def launch(self, op: str, send_ptr: int, recv_ptr: int, count: int, stream: int) -> None:
+        c = self.comm
+        if op == "all_reduce":
+            c.all_reduce(send_ptr, recv_ptr, count, self.dt, stream)
+        elif op == "all_gather":
+            c.all_gather(send_ptr, recv_ptr, count, self.dt, stream)
+        elif op == "reduce_scatter":
+            c.reduce_scatter(send_ptr, recv_ptr, count, self.dt, stream)
+        else:
+            c.all_to_all(send_ptr, recv_ptr, count, self.dt, self.itemsize, stream)
+        self._launches += 1
+
+    def launches(self) -> int:
+        return 0   # NCCL's kernels are not ours
+
+    def check(self):
+        pass
+
+    def close(self):
+        self.comm.destroy()
+
+
+def _gen_expected(torch, op, rank, n, count, device):
+    """Deterministic integers in [-8, 8] x 0.25: sums over <= 8 ranks are exact in bf16."""
+    def gen(r, idx):
+        return (((idx * 7 + r * 13 + (idx >> 9)) % 17) - 8).to(torch.float32) * 0.25
+    return gen
+
+
+def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
+    """One correctness pass against a plain PyTorch fp32 reference of the same op."""
+    import torch
+    n, rank = dist.world, dist.rank
+    dev = backend.send.device
+    gen = _gen_expected(torch, op, rank, n, count, dev)
+    E = 8
+    count = max(E, count // E * E)
+    if op == "all_reduce":
+        in_elems, out_elems = count, count
+    elif op == "all_gather":
+        in_elems, out_elems = count, count * n
+    elif op == "reduce_scatter":
+        in_elems, out_elems = count * n, count
+    else:
+        in_elems, out_elems = count * n, count * n
+    idx = torch.arange(in_elems, device=dev)
+    backend.send[:in_elems] = gen(rank, idx).to(dtype)
+    backend.recv[:out_elems] = 77.0
+    torch.cuda.synchronize(); dist.barrier()
+    st = torch.cuda.current_stream().cuda_stream
+    backend.launch(op, backend.send.data_ptr(), backend.recv.data_ptr(), count, st)
+    torch.cuda.synchronize(); dist.barrier()
+    backend.check()
+    got = backend.recv[:out_elems].float()
+    if op == "all_reduce":
+        want = sum(gen(r, idx) for r in range(n))
+    elif op == "all_gather":
+        j = torch.arange(count, device=dev)
+        want = torch.cat([gen(r, j) for r in range(n)])
+    elif op == "reduce_scatter":
+        j = torch.arange(count, device=dev) + rank * count
+        want = sum(gen(r, j) for r in range(n))
+    else:
+        j = torch.arange(count, device=dev) + rank * count
+        want = torch.cat([gen(r, j) for r in range(n)])
+    ok = bool(torch.equal(got, want.to(dtype).float()))
+    oks = dist.sum_([1.0 if ok else 0.0])[0]
+    return oks == n
+
+
+def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_bytes: int, max_bytes: int, factor: int = 2,
+          placements=(0, 1), e2e: bool = False) -> list[Row]:
+    import torch
+    n, rank = dist.world, dist.rank
+    itemsize = backend.send.element_size()
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    rows: list[Row] = []
+    raw = []   # per (row, placement) local ms
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    host_in = host_out = None
+    if e2e:
+        host_in = torch.empty(max_bytes // itemsize, dtype=dtype).pin_memory()
+        host_in.fill_(0.25)
+        host_out = torch.empty(4096 // itemsize, dtype=dtype).pin_memory()
+    nbytes = min_bytes
+    while nbytes <= max_bytes:
+        E = 16 // itemsize
+        if op == "all_reduce":
+            count = nbytes // itemsize
+            in_elems = out_elems = count
+        else:
+            count = nbytes // itemsize // n // E * E
+            in_elems = count if op == "all_gather" else count * n
+            out_elems = count if op == "reduce_scatter" else count * n
+        if count == 0:
+            nbytes *= factor
+            continue
+        total = (count if op == "all_reduce" else count * n) * itemsize
+        slot_elems = (max(in_elems, out_elems) * itemsize + 4095) // 4096 * 4096 // itemsize
+        slots = max(1, min(64, WINDOW // (slot_elems * itemsize)))
+        per_rank_bytes = count * itemsize
+        row = Row(total, count, backend.algo(op, per_rank_bytes), in_bytes=in_elems * itemsize)
+        sbase, rbase = backend.send.data_ptr(), backend.recv.data_ptr()
+        for ip in placements:
+            if ip == 1 and (op == "alltoall" or n == 1):
+                continue
+
+            def ptrs(slot: int):
+                off = slot * slot_elems * itemsize
+                if not ip:
+                    return sbase + off, rbase + off
+                if op == "all_gather":
+                    return rbase + off + rank * count * itemsize, rbase + off
+                if op == "reduce_scatter":
+                    return rbase + off, rbase + off + rank * count * itemsize
+                return rbase + off, rbase + off
+            for i in range(warmup):
+                s, r = ptrs(i % slots)
+                backend.launch(op, s, r, count, st)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0.record(stream)
+            for i in range(steps):
+                s, r = ptrs(i % slots)
+                backend.launch(op, s, r, count, st)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            raw.append((len(rows), "ip" if ip else "oop", e0.elapsed_time(e1) / steps))
+        if e2e:
+            # the user-visible call: pinned host -> device, collective, small device -> host read of the result
+            for i in range(min(warmup, 2)):
+                backend.send[:in_elems].copy_(host_in[:in_elems], non_blocking=True)
+                backend.launch(op, sbase, rbase, count, st)
+                host_out.copy_(backend.recv[:host_out.numel()], non_blocking=True)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0.record(stream)
+            for i in range(steps):
+                off = (i % slots) * slot_elems
+                backend.send[off:off + in_elems].copy_(host_in[:in_elems], non_blocking=True)
+                backend.launch(op, sbase + off * itemsize, rbase + off * itemsize, count, st)
+                host_out.copy_(backend.recv[off:off + host_out.numel()], non_blocking=True)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            raw.append((len(rows), "e2e", e0.elapsed_time(e1) / steps))
+        rows.append(row)
+        nbytes *= factor
+    backend.check()
+    worst = dist.max_([r[2] for r in raw]) if raw else []
+    for (ri, kind, _), ms in zip(raw, worst):
+        setattr(rows[ri], f"{kind}_us", ms * 1e3)
+    return rows
+
+
+def summarize(rows: list[Row], op: str, n: int) -> dict:
+    vals, e2e_vals, peak = [], [], 0.0
+    for r in rows:
+        b = r.bw(op, n)
+        for k, us in (("oop_busbw", r.oop_us), ("ip_busbw", r.ip_us)):
+            if us > 0:
+                vals.append(b[k]); peak = max(peak, b[k])
+        if r.e2e_us > 0:
+            e2e_vals.append(b["e2e_busbw"])
+    sweep_ms = sum((r.oop_us if r.oop_us > 0 else 0) + (r.ip_us if r.ip_us > 0 else 0) for r in rows) / 1e3
+    return {"avg_busbw": sum(vals) / len(vals) if vals else 0.0, "peak_busbw": peak, "sweep_ms": sweep_ms,
+            "avg_e2e_busbw": sum(e2e_vals) / len(e2e_vals) if e2e_vals else None, "measurements": len(vals)}
+
+
+def format_table(rows: list[Row], op: str, n: int, title: str) -> str:
+    out = [f"# {title}", f"#{'size(B)':>13} {'count':>12} {'algo':>8} | {'oop us':>10} {'algbw':>8} {'busbw':>8} | {'ip us':>10} {'algbw':>8} {'busbw':>8}"]
+    for r in rows:
+        b = r.bw(op, n)
+        out.append(f"{r.nbytes:>14} {r.count:>12} {r.algo:>8} | {r.oop_us:>10.2f} {b['oop_algbw']:>8.2f} {b['oop_busbw']:>8.2f} | {r.ip_us:>10.2f} {b['ip_algbw']:>8.2f} {b['ip_busbw']:>8.2f}")
+    s = summarize(rows, op, n)
+    out.append(f"# Avg bus bandwidth : {s['avg_busbw']:.3f} GB/s   peak {s['peak_busbw']:.2f} GB/s")
+    return "\n".join(out)
+
+
+def rows_json(rows: list[Row], op: str, n: int) -> list[dict]:
+    return [{"bytes": r.nbytes, "algo": r.algo, "oop_us": round(r.oop_us, 3), "ip_us": round(r.ip_us, 3), "oop_busbw": round(r.bw(op, n)["oop_busbw"], 2),
+             "ip_busbw": round(r.bw(op, n)["ip_busbw"], 2), **({"e2e_us": round(r.e2e_us, 3)} if r.e2e_us > 0 else {})} for r in rows]

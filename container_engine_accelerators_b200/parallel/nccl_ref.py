@@ -1,0 +1,106 @@
+"""Stock NCCL driven through its own C API (ctypes) — the reference arm of every benchmark.
+
+The reference ships no collective code: its nccl-test manifests mount an installer-dropped NCCL and run
+nccl-tests' `*_perf` binaries (reference: gpudirect-rdma/nccl-test-a4.yaml:42-77,
+gpudirect-tcpx/nccl-config.yaml:30-63). On one NVSwitch box the net plugin is never on the data path, so
+"the reference's NCCL build on this box" is the image's libnccl called exactly the way nccl-tests calls it:
+ncclAllReduce/ncclAllGather/ncclReduceScatter/ncclSend+ncclRecv on raw device pointers, one rank per GPU.
+None of this repo's kernels are on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+from typing import Optional
+
+NCCL_FLOAT16, NCCL_FLOAT32, NCCL_BFLOAT16 = 6, 7, 9
+NCCL_SUM = 0
+
+# The reference's canonical environment profile for the intra-node part (gpudirect-tcpxo/README.md:71-103).
+REFERENCE_ENV = {
+    "NCCL_NVLS_ENABLE": "1",
+    "NCCL_PROTO": "Simple,LL128",
+    "NCCL_MIN_NCHANNELS": "4",
+    "NCCL_P2P_NVL_CHUNKSIZE": "1048576",
+    "NCCL_BUFFSIZE": "8388608",
+    "NCCL_NVLSTREE_MAX_CHUNKSIZE": "131072",
+}
+
+
+class NcclUniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+def find_libnccl() -> Optional[str]:
+    cands = []
+    try:
+        import torch
+        base = os.path.dirname(os.path.dirname(torch.__file__))
+        cands += glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so*"))
+        cands += glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libnccl.so*"))
+    except Exception:
+        pass
+    cands += glob.glob("/usr/lib/x86_64-linux-gnu/libnccl.so*")
+    return cands[0] if cands else None
+
+
+class NcclComm:
+    def __init__(self, rank: int, nranks: int, uid_bytes: bytes, lib_path: Optional[str] = None):
+        path = lib_path or find_libnccl()
+        if not path:
+            raise ImportError("libnccl not found")
+        self.lib = L = C.CDLL(path)
+        self.path = path
+        vp = C.c_void_p
+        L.ncclGetErrorString.restype = C.c_char_p
+        L.ncclCommInitRank.argtypes = [C.POINTER(vp), C.c_int, NcclUniqueId, C.c_int]
+        L.ncclAllReduce.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.ncclAllGather.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, vp]
+        L.ncclReduceScatter.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.ncclSend.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.ncclRecv.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.ncclCommDestroy.argtypes = [vp]
+        uid = NcclUniqueId()
+        C.memmove(C.byref(uid), uid_bytes, 128)
+        self.comm = vp()
+        self.rank, self.nranks = rank, nranks
+        self._ck(L.ncclCommInitRank(C.byref(self.comm), nranks, uid, rank), "ncclCommInitRank")
+        v = C.c_int()
+        L.ncclGetVersion(C.byref(v))
+        self.version = v.value
+
+    @staticmethod
+    def new_unique_id(lib_path: Optional[str] = None) -> bytes:
+        L = C.CDLL(lib_path or find_libnccl())
+        uid = NcclUniqueId()
+        rc = L.ncclGetUniqueId(C.byref(uid))
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId -> {rc}")
+        return bytes(uid)
+
+    def _ck(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.ncclGetErrorString(rc).decode()}")
+
+    def all_reduce(self, send: int, recv: int, count: int, dtype: int, stream: int) -> None:
+        self._ck(self.lib.ncclAllReduce(send, recv, count, dtype, NCCL_SUM, self.comm, stream), "ncclAllReduce")
+
+    def all_gather(self, send: int, recv: int, sendcount: int, dtype: int, stream: int) -> None:
+        self._ck(self.lib.ncclAllGather(send, recv, sendcount, dtype, self.comm, stream), "ncclAllGather")
+
+    def reduce_scatter(self, send: int, recv: int, recvcount: int, dtype: int, stream: int) -> None:
+        self._ck(self.lib.ncclReduceScatter(send, recv, recvcount, dtype, NCCL_SUM, self.comm, stream), "ncclReduceScatter")
+
+    def all_to_all(self, send: int, recv: int, count: int, dtype: int, elem_size: int, stream: int) -> None:
+        # nccl-tests' alltoall: grouped ncclSend/ncclRecv to every peer
+        self._ck(self.lib.ncclGroupStart(), "ncclGroupStart")
+        for p in range(self.nranks):
+            self._ck(self.lib.ncclSend(send + p * count * elem_size, count, dtype, p, self.comm, stream), "ncclSend")
+            self._ck(self.lib.ncclRecv(recv + p * count * elem_size, count, dtype, p, self.comm, stream), "ncclRecv")
+        self._ck(self.lib.ncclGroupEnd(), "ncclGroupEnd")
+
+    def destroy(self) -> None:
+        if self.comm:
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
