@@ -1,5 +1,7 @@
 // libb200coll collective entry points: argument validation, algorithm choice (tuner table +
 // feasibility), staging for buffers outside the symmetric arena, type dispatch, kernel launch.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "comm.h"
@@ -52,6 +54,11 @@ struct Grid { int blocks, threads; };
 
 // Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs).
 static Grid pick_grid(size_t vecs, int unroll, int max_ctas) {
+  static const int forced = [] { const char* e = getenv("B200COLL_FORCE_THREADS"); return e ? atoi(e) : 0; }();
+  if (forced >= 32 && forced <= 512) {
+    size_t b = (vecs + (size_t)forced * unroll - 1) / ((size_t)forced * unroll);
+    return Grid{(int)std::max<size_t>(1, std::min<size_t>(b, (size_t)max_ctas)), forced};
+  }
   for (int t : {128, 256, 512}) {
     size_t b = (vecs + (size_t)t * unroll - 1) / ((size_t)t * unroll);
     if (b <= (size_t)max_ctas || t == 512) return Grid{(int)std::max<size_t>(1, std::min<size_t>(b, (size_t)max_ctas)), t};

@@ -106,7 +106,8 @@ __device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch,
     uint32_t* remote = reinterpret_cast<uint32_t*>(c.peer[t] + kOffFlags) + (size_t)blockIdx.x * kMaxRanks + c.rank;
     if (RELEASE) st_release_sys(remote, epoch); else st_relaxed_sys(remote, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.peer[c.rank] + kOffFlags) + (size_t)blockIdx.x * kMaxRanks + t;
-    // Poll with relaxed loads (an acquire per poll would re-fence every iteration), then one acquire fence.
+    // Poll with relaxed loads, then a single load-acquire of the same flag: acquire ordering for the data that
+    // follows without a full fence (a fence.sys here would also wait for my own flag store's round trip).
     uint32_t v = ld_relaxed_sys(mine);
     if ((int32_t)(v - epoch) < 0) {
       const unsigned long long t0 = globaltimer_ns();
@@ -117,7 +118,7 @@ __device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch,
         }
       }
     }
-    fence_acq_rel_sys();
+    (void)ld_acquire_sys(mine);
   }
   __syncthreads();
 }

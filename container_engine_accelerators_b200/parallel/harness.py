@@ -152,6 +152,7 @@ class NcclBackend:
         self.torch = torch
         for k, v in nccl_ref.REFERENCE_ENV.items():
             os.environ.setdefault(k, v)
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200_REF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         uid = nccl_ref.NcclComm.new_unique_id() if dist.rank == 0 else None
         uid = dist.bcast_bytes(uid, 128)
         self.comm = nccl_ref.NcclComm(dist.rank, dist.world, uid)
