@@ -1,0 +1,189 @@
+"""Prometheus metrics server: per-container and per-node GPU duty cycle / memory gauges + request counts,
+and (new) per-collective counters read from the stats pages libb200coll exports in /dev/shm.
+
+Contract: reference pkg/gpu/nvidia/metrics/{metrics,devices,util}.go: gauge names and labels,
+`make="nvidia"`, accelerator_id = GPU UUID, model = NVML name, resource_name = nvidia.com/gpu; duty cycle =
+integer mean of utilisation samples newer than now-10 s, > 100 => device skipped this tick; container->device map
+from the kubelet PodResources v1alpha1 List, virtual (shared) ids dropped; all series reset once a minute so dead
+containers disappear. Fixes: connection closed only if it was opened (devices.go:59-68); zero-sample guard lives
+in the native sampler (util.go:82).
+"""
+from __future__ import annotations
+
+import glob
+import logging
+import struct
+import threading
+import time
+from typing import Optional
+
+import grpc
+from prometheus_client import CollectorRegistry, Gauge, start_http_server
+
+from . import protos, sharing
+from .protos import podresources as prpb
+
+log = logging.getLogger("b200-device-plugin")
+
+GPU_RESOURCE_NAME = "nvidia.com/gpu"
+POD_RESOURCES_SOCKET = "/var/lib/kubelet/pod-resources/kubelet.sock"
+RESET_INTERVAL_S = 60.0
+DUTY_CYCLE_WINDOW_S = 10
+_CONTAINER_LABELS = ["namespace", "pod", "container", "make", "accelerator_id", "model"]
+_NODE_LABELS = ["make", "accelerator_id", "model"]
+COLL_OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall")
+COLL_ALGOS = ("auto", "ll", "oneshot", "twoshot", "nvls", "copy")
+
+
+def get_devices_for_all_containers(socket_path: str = POD_RESOURCES_SOCKET, timeout: float = 5.0) -> dict:
+    """{(namespace, pod, container): [device ids]} from the kubelet's PodResourcesLister."""
+    out: dict = {}
+    try:
+        channel = grpc.insecure_channel(f"unix:{socket_path}")
+    except Exception as e:
+        raise RuntimeError(f"error connecting to kubelet PodResourceLister service: {e}") from e
+    try:
+        call = channel.unary_unary(f"/{protos.POD_RESOURCES_SERVICE}/List", request_serializer=prpb.ListPodResourcesRequest.SerializeToString,
+                                   response_deserializer=prpb.ListPodResourcesResponse.FromString)
+        try:
+            resp = call(prpb.ListPodResourcesRequest(), timeout=timeout)
+        except grpc.RpcError as e:
+            raise RuntimeError(f"error listing pod resources: {e}") from e
+        for pod in resp.pod_resources:
+            for c in pod.containers:
+                key = (pod.namespace, pod.name, c.name)
+                for d in c.devices:
+                    if not d.device_ids or d.resource_name != GPU_RESOURCE_NAME:
+                        continue
+                    ids = [i for i in d.device_ids if not sharing.is_virtual_device_id(i)]
+                    out.setdefault(key, []).extend(ids)
+    finally:
+        channel.close()
+    return out
+
+
+def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*") -> list:
+    """Parse the 4 KiB pages written by libb200coll (coll/src/comm.cu stats_page_publish)."""
+    pages = []
+    for path in glob.glob(pattern):
+        try:
+            with open(path, "rb") as f:
+                raw = f.read(4096)
+            if len(raw) < 64 + 8 * 16 or raw[:8] != b"B200COLL":
+                continue
+            version, pid, rank, nranks, device, nvls = struct.unpack_from("<6I", raw, 8)
+            vals = struct.unpack_from("<16Q", raw, 64)
+            pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "calls": vals[0:4], "bytes": vals[4:8],
+                          "algo_calls": vals[8:14], "kernel_launches": vals[14], "staged_calls": vals[15]})
+        except OSError:
+            continue
+    return pages
+
+
+class MetricServer:
+    def __init__(self, nvml, collection_interval_ms: int = 30000, port: int = 2112, pod_resources_socket: str = POD_RESOURCES_SOCKET,
+                 registry: Optional[CollectorRegistry] = None, coll_stats_glob: str = "/dev/shm/b200coll.*", now=time.time):
+        self.nvml, self.interval_ms, self.port, self.socket = nvml, collection_interval_ms, port, pod_resources_socket
+        self.registry = registry or CollectorRegistry()
+        self.coll_stats_glob = coll_stats_glob
+        self._now = now
+        self.last_reset = now()
+        self.gpu_devices: dict = {}        # "nvidiaN" -> DeviceInfo
+        self._stop = threading.Event()
+        g = lambda name, help_, labels: Gauge(name, help_, labels, registry=self.registry)
+        self.duty_cycle_node = g("duty_cycle_gpu_node", "Percent of time when the GPU was actively processing", _NODE_LABELS)
+        self.memory_total_node = g("memory_total_gpu_node", "Total memory available on the GPU in bytes", _NODE_LABELS)
+        self.memory_used_node = g("memory_used_gpu_node", "Allocated GPU memory in bytes", _NODE_LABELS)
+        self.duty_cycle = g("duty_cycle", "Percent of time when the GPU was actively processing", _CONTAINER_LABELS)
+        self.memory_total = g("memory_total", "Total memory available on the GPU in bytes", _CONTAINER_LABELS)
+        self.memory_used = g("memory_used", "Allocated GPU memory in bytes", _CONTAINER_LABELS)
+        self.requests = g("request", "Number of accelerator devices requested by the container", ["namespace", "pod", "container", "resource_name"])
+        self.coll_calls = g("b200coll_calls", "Collective calls issued through libb200coll", ["pid", "rank", "op"])
+        self.coll_bytes = g("b200coll_bytes", "Bytes moved by libb200coll collectives", ["pid", "rank", "op"])
+        self.coll_algo = g("b200coll_algo_calls", "libb200coll calls per chosen algorithm", ["pid", "rank", "algo"])
+        self._all = [self.duty_cycle_node, self.memory_total_node, self.memory_used_node, self.duty_cycle, self.memory_total, self.memory_used,
+                     self.requests, self.coll_calls, self.coll_bytes, self.coll_algo]
+
+    def discover_gpu_devices(self) -> None:
+        self.gpu_devices = {}
+        for i in range(self.nvml.device_count()):
+            info = self.nvml.device(i)
+            self.gpu_devices[f"nvidia{info.minor}"] = info
+            log.info("Found device nvidia%d for metrics collection", info.minor)
+
+    def average_gpu_utilization(self, uuid: str, window_s: int = DUTY_CYCLE_WINDOW_S) -> int:
+        since_us = int((self._now() - window_s) * 1e6)
+        util = self.nvml.average_usage(uuid, since_us)
+        if util > 100:
+            raise ValueError(f"utilization ({util}) is out of range")
+        return util
+
+    def _metrics_info(self, device: str):
+        info = self.gpu_devices.get(device)
+        if info is None:
+            raise KeyError(f"device {device} not found")
+        fresh = self.nvml.device(info.index)
+        return self.average_gpu_utilization(fresh.uuid), fresh
+
+    def reset_if_needed(self) -> bool:
+        if self._now() > self.last_reset + RESET_INTERVAL_S:
+            for gauge in self._all:
+                gauge.clear()
+            self.last_reset = self._now()
+            return True
+        return False
+
+    def update_metrics(self, container_devices: dict) -> None:
+        self.reset_if_needed()
+        for (ns, pod, ctr), devices in container_devices.items():
+            self.requests.labels(ns, pod, ctr, GPU_RESOURCE_NAME).set(len(devices))
+            for dev in devices:
+                try:
+                    duty, info = self._metrics_info(dev)
+                except Exception as e:
+                    log.info("Error calculating duty cycle for device: %s: %s. Skipping this device", dev, e)
+                    continue
+                labels = (ns, pod, ctr, "nvidia", info.uuid, info.name)
+                self.duty_cycle.labels(*labels).set(duty)
+                self.memory_total.labels(*labels).set(info.mem_total)
+                self.memory_used.labels(*labels).set(info.mem_used)
+        for dev in self.gpu_devices:
+            try:
+                duty, info = self._metrics_info(dev)
+            except Exception as e:
+                log.info("Error calculating duty cycle for device: %s: %s. Skipping this device", dev, e)
+                continue
+            labels = ("nvidia", info.uuid, info.name)
+            self.duty_cycle_node.labels(*labels).set(duty)
+            self.memory_total_node.labels(*labels).set(info.mem_total)
+            self.memory_used_node.labels(*labels).set(info.mem_used)
+        for page in read_coll_stats_pages(self.coll_stats_glob):
+            pid, rank = str(page["pid"]), str(page["rank"])
+            for i, op in enumerate(COLL_OPS):
+                self.coll_calls.labels(pid, rank, op).set(page["calls"][i])
+                self.coll_bytes.labels(pid, rank, op).set(page["bytes"][i])
+            for i, algo in enumerate(COLL_ALGOS):
+                self.coll_algo.labels(pid, rank, algo).set(page["algo_calls"][i])
+
+    def collect_once(self) -> None:
+        try:
+            devices = get_devices_for_all_containers(self.socket)
+        except Exception as e:
+            log.error("Failed to get devices for containers: %s", e)
+            return
+        self.update_metrics(devices)
+
+    def start(self, serve_http: bool = True) -> None:
+        log.info("Starting metrics server")
+        log.info("nvml initialized successfully. Driver version: %s", self.nvml.driver_version())
+        self.discover_gpu_devices()
+        if serve_http:
+            start_http_server(self.port, registry=self.registry)
+        threading.Thread(target=self._loop, daemon=True).start()
+
+    def _loop(self) -> None:
+        while not self._stop.wait(self.interval_ms / 1000.0):
+            self.collect_once()
+
+    def stop(self) -> None:
+        self._stop.set()

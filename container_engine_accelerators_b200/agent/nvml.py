@@ -56,8 +56,9 @@ class NvmlOperations(Protocol):
 def numa_topology(bus_id: str, pci_root: str = PCI_DEVICES_ROOT) -> Optional[int]:
     """NUMA node of a GPU, or None when the platform reports none (< 0). Raises on unreadable sysfs."""
     bus = bus_id.split("\x00")[0]
-    if bus.startswith("0000"):
-        bus = bus[4:]           # NVML pads the domain to 8 hex digits; sysfs uses 4
+    domain = bus.split(":", 1)[0]
+    if len(domain) == 8 and domain.startswith("0000"):
+        bus = bus[4:]           # NVML pads the domain to 8 hex digits; sysfs uses 4 (the reference strips blindly, nvmlutil.go:131)
     bus = bus.lower()
     path = os.path.join(pci_root, bus, "numa_node")
     try:

@@ -94,3 +94,124 @@ def make_fake_pci(root: str, bus_id: str, numa_node: int) -> str:
     d.mkdir(parents=True, exist_ok=True)
     (d / "numa_node").write_text(f"{numa_node}\n")
     return str(pci)
+
+
+# ------------------------------------------------------------------------------------------------- fake kube-apiserver
+import json as _json
+import re as _re
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from urllib.parse import parse_qs, urlparse
+
+
+class FakeKubeApi:
+    """In-process kube-apiserver double (the role of client-go's fake clientset in the reference's tests,
+    health_checker_test.go:235,315-338): nodes, pods, events; `fail_next_gets` injects transient GET failures."""
+
+    def __init__(self):
+        self.nodes: dict = {}
+        self.pods: dict = {}        # (ns, name) -> pod
+        self.events: list = []
+        self.requests: list = []    # (method, path, content-type)
+        self.fail_next_gets = 0
+        self._srv = None
+        self.url = ""
+
+    def add_node(self, name: str, boot_id: str = "boot-1", labels=None, annotations=None, conditions=None, allocatable=None, taints=None) -> dict:
+        node = {"apiVersion": "v1", "kind": "Node", "metadata": {"name": name, "uid": f"uid-{name}", "labels": dict(labels or {}), "annotations": dict(annotations or {})},
+                "spec": {"taints": list(taints or [])},
+                "status": {"nodeInfo": {"bootID": boot_id}, "conditions": list(conditions or [{"type": "Ready", "status": "True"}]), "allocatable": dict(allocatable or {})}}
+        self.nodes[name] = node
+        return node
+
+    def add_pod(self, pod: dict) -> None:
+        self.pods[(pod["metadata"].get("namespace", "default"), pod["metadata"]["name"])] = pod
+
+    def start(self) -> "FakeKubeApi":
+        api = self
+
+        class H(BaseHTTPRequestHandler):
+            def log_message(self, *a):
+                pass
+
+            def _send(self, code, obj):
+                body = _json.dumps(obj).encode()
+                self.send_response(code); self.send_header("Content-Type", "application/json"); self.send_header("Content-Length", str(len(body))); self.end_headers()
+                self.wfile.write(body)
+
+            def _body(self):
+                n = int(self.headers.get("Content-Length") or 0)
+                return _json.loads(self.rfile.read(n) or b"{}")
+
+            def _route(self, method):
+                u = urlparse(self.path)
+                q = parse_qs(u.query)
+                api.requests.append((method, u.path, self.headers.get("Content-Type", "")))
+                m = _re.fullmatch(r"/api/v1/nodes/([^/]+)(/status)?", u.path)
+                if m:
+                    name, status = m.group(1), bool(m.group(2))
+                    if method == "GET":
+                        if api.fail_next_gets > 0:
+                            api.fail_next_gets -= 1
+                            return self._send(500, {"message": "injected failure"})
+                        return self._send(200, api.nodes[name]) if name in api.nodes else self._send(404, {"message": "not found"})
+                    if name not in api.nodes:
+                        return self._send(404, {"message": "not found"})
+                    body = self._body()
+                    if method == "PUT":
+                        if status:
+                            api.nodes[name]["status"] = body.get("status", {})
+                        else:
+                            api.nodes[name] = body
+                        return self._send(200, api.nodes[name])
+                    if method == "PATCH":
+                        ctype = self.headers.get("Content-Type", "")
+                        meta = body.get("metadata", {})
+                        if "apply-patch" in ctype and not q.get("fieldManager"):
+                            return self._send(422, {"message": "fieldManager is required for apply"})
+                        for key in ("labels", "annotations"):
+                            for k, v in (meta.get(key) or {}).items():
+                                if v is None:
+                                    api.nodes[name]["metadata"].setdefault(key, {}).pop(k, None)
+                                else:
+                                    api.nodes[name]["metadata"].setdefault(key, {})[k] = v
+                        return self._send(200, api.nodes[name])
+                if u.path == "/api/v1/nodes" and method == "GET":
+                    return self._send(200, {"items": list(api.nodes.values())})
+                m = _re.fullmatch(r"/api/v1/namespaces/([^/]+)/events", u.path)
+                if m and method == "POST":
+                    ev = self._body(); api.events.append(ev)
+                    return self._send(201, ev)
+                m = _re.fullmatch(r"/api/v1(?:/namespaces/([^/]+))?/pods", u.path)
+                if m and method == "GET":
+                    items = [p for (ns, _), p in api.pods.items() if not m.group(1) or ns == m.group(1)]
+                    for sel in (q.get("fieldSelector") or [""])[0].split(","):
+                        if sel.startswith("status.phase="):
+                            items = [p for p in items if p.get("status", {}).get("phase") == sel.split("=", 1)[1]]
+                        if sel.startswith("spec.nodeName="):
+                            items = [p for p in items if p.get("spec", {}).get("nodeName") == sel.split("=", 1)[1]]
+                    return self._send(200, {"items": items})
+                m = _re.fullmatch(r"/api/v1/namespaces/([^/]+)/pods/([^/]+)", u.path)
+                if m:
+                    key = (m.group(1), m.group(2))
+                    if key not in api.pods:
+                        return self._send(404, {"message": "not found"})
+                    if method == "GET":
+                        return self._send(200, api.pods[key])
+                    if method == "PUT":
+                        api.pods[key] = self._body()
+                        return self._send(200, api.pods[key])
+                return self._send(404, {"message": f"no route {method} {u.path}"})
+
+            def do_GET(self): self._route("GET")
+            def do_PUT(self): self._route("PUT")
+            def do_POST(self): self._route("POST")
+            def do_PATCH(self): self._route("PATCH")
+
+        self._srv = ThreadingHTTPServer(("127.0.0.1", 0), H)
+        self.url = f"http://127.0.0.1:{self._srv.server_address[1]}"
+        threading.Thread(target=self._srv.serve_forever, daemon=True).start()
+        return self
+
+    def stop(self) -> None:
+        if self._srv:
+            self._srv.shutdown(); self._srv.server_close(); self._srv = None
