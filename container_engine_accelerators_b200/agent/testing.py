@@ -215,3 +215,62 @@ class FakeKubeApi:
     def stop(self) -> None:
         if self._srv:
             self._srv.shutdown(); self._srv.server_close(); self._srv = None
+
+
+# ------------------------------------------------------------------------------------------------- fake NRI runtime
+class FakeNriRuntime:
+    """containerd's side of NRI for tests: accepts one plugin on a Unix socket, serves Runtime.RegisterPlugin on mux
+    conn 2 and drives Plugin.Configure / Synchronize / CreateContainer on mux conn 1."""
+
+    def __init__(self, socket_path: str):
+        import socket as _socket
+        self.socket_path = socket_path
+        self.registered = threading.Event()
+        self.registration = None
+        self._listener = _socket.socket(_socket.AF_UNIX, _socket.SOCK_STREAM)
+        if os.path.exists(socket_path):
+            os.unlink(socket_path)
+        self._listener.bind(socket_path)
+        self._listener.listen(1)
+        self.client = None
+        self.mux = None
+        threading.Thread(target=self._accept, daemon=True).start()
+
+    def _accept(self) -> None:
+        from . import nri
+        conn, _ = self._listener.accept()
+        self.mux = nri.Mux(conn)
+
+        def register(req):
+            self.registration = req
+            self.registered.set()
+            return protos.nri.Empty()
+        self.client = nri.TtrpcClient(nri.MuxStream(self.mux, nri.PLUGIN_SERVICE_CONN))
+        server = nri.TtrpcServer(nri.MuxStream(self.mux, nri.RUNTIME_SERVICE_CONN), protos.NRI_RUNTIME_SERVICE, {"RegisterPlugin": (protos.nri.RegisterPluginRequest, register)})
+        threading.Thread(target=server.serve, daemon=True).start()
+
+    def wait_registered(self, timeout: float = 10.0):
+        if not self.registered.wait(timeout):
+            raise TimeoutError("plugin did not register")
+        return self.registration
+
+    def configure(self):
+        return self.client.call(protos.NRI_PLUGIN_SERVICE, "Configure", protos.nri.ConfigureRequest(runtime_name="containerd", runtime_version="2.0"), protos.nri.ConfigureResponse)
+
+    def synchronize(self):
+        return self.client.call(protos.NRI_PLUGIN_SERVICE, "Synchronize", protos.nri.SynchronizeRequest(), protos.nri.SynchronizeResponse)
+
+    def create_container(self, pod_name: str, ctr_name: str, annotations: dict, namespace: str = "default"):
+        req = protos.nri.CreateContainerRequest()
+        req.pod.name, req.pod.namespace = pod_name, namespace
+        for k, v in annotations.items():
+            req.pod.annotations[k] = v
+        req.container.name = ctr_name
+        return self.client.call(protos.NRI_PLUGIN_SERVICE, "CreateContainer", req, protos.nri.CreateContainerResponse)
+
+    def close(self) -> None:
+        if self.mux:
+            self.mux.close()
+        self._listener.close()
+        if os.path.exists(self.socket_path):
+            os.unlink(self.socket_path)

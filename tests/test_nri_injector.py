@@ -1,0 +1,80 @@
+"""NRI device injector: annotation parsing (reference nri_device_injector_test.go:95-190 YAML cases), lstat-derived
+device identity (:25-93, which needs root for mknod — here a fake lstat covers b/c/p and a real FIFO covers the syscall),
+and the full wire path against a fake containerd NRI runtime (mux + ttrpc), which the reference does not test."""
+import os
+import stat
+import threading
+import types
+
+import pytest
+
+from container_engine_accelerators_b200.agent import nri, testing
+
+KEY = "devices.gke.io/container."
+
+
+def test_get_devices_cases():
+    assert nri.get_devices("c", {}) == []
+    assert nri.get_devices("c", {KEY + "other": "- path: /dev/x"}) == []
+    devs = nri.get_devices("c", {KEY + "c": "- path: /dev/nvidia0\n- path: /dev/nvidiactl\n  file_mode: 438\n- path: /dev/nvidia0\n  uid: 7\n"})
+    assert [d["path"] for d in devs] == ["/dev/nvidia0", "/dev/nvidiactl"]       # duplicate path: first wins
+    assert devs[1]["file_mode"] == 438 and "uid" not in devs[0]
+    with pytest.raises(nri.DeviceError, match="invalid device annotation"):
+        nri.get_devices("c", {KEY + "c": "- path: [unclosed"})
+    with pytest.raises(nri.DeviceError, match="invalid device annotation"):
+        nri.get_devices("c", {KEY + "c": "just a string"})
+
+
+def fake_lstat(mode, major=195, minor=3):
+    return lambda path: types.SimpleNamespace(st_mode=mode, st_rdev=os.makedev(major, minor))
+
+
+@pytest.mark.parametrize("mode,want", [(stat.S_IFCHR | 0o666, "c"), (stat.S_IFBLK | 0o660, "b"), (stat.S_IFIFO | 0o600, "p")])
+def test_to_nri_device_types(mode, want):
+    d = nri.to_nri_device({"path": "/dev/nvidia3", "type": "ignored", "major": 1, "minor": 2}, fake_lstat(mode))
+    assert (d.type, d.major, d.minor, d.path) == (want, 195, 3, "/dev/nvidia3")    # type/major/minor re-derived, annotation values ignored
+    assert not d.HasField("file_mode") and not d.HasField("uid") and not d.HasField("gid")
+
+
+def test_to_nri_device_optional_fields_and_errors(tmp_path):
+    d = nri.to_nri_device({"path": "/dev/x", "file_mode": 0o666, "uid": 1000, "gid": 44}, fake_lstat(stat.S_IFCHR))
+    assert (d.file_mode.value, d.uid.value, d.gid.value) == (0o666, 1000, 44)
+    with pytest.raises(nri.DeviceError, match="invalid device type"):
+        nri.to_nri_device({"path": "/tmp"}, fake_lstat(stat.S_IFDIR))
+    with pytest.raises(nri.DeviceError, match="failed to get info from device path"):
+        nri.to_nri_device({"path": str(tmp_path / "missing")})
+    fifo = tmp_path / "fifo"
+    os.mkfifo(fifo)
+    assert nri.to_nri_device({"path": str(fifo)}).type == "p"
+
+
+def test_create_container_nil_pod_is_noop():
+    from container_engine_accelerators_b200.agent.protos import nri as pb
+    adj = nri.create_container(None, pb.Container(name="c"))
+    assert len(adj.linux.devices) == 0
+
+
+def test_wire_register_configure_create_container(tmp_path):
+    sock = str(tmp_path / "nri.sock")
+    rt = testing.FakeNriRuntime(sock)
+    fifo = tmp_path / "dev-fifo"
+    os.mkfifo(fifo)
+    plugin = nri.DeviceInjectorPlugin(sock)
+    t = threading.Thread(target=plugin.run, daemon=True)
+    t.start()
+    try:
+        reg = rt.wait_registered()
+        assert (reg.plugin_name, reg.plugin_idx) == ("device_injector_nri", "10")
+        cfg = rt.configure()
+        assert cfg.events & (1 << 3)                      # subscribed to CREATE_CONTAINER
+        rt.synchronize()
+        resp = rt.create_container("pod", "rxdm", {KEY + "rxdm": f"- path: {fifo}\n  gid: 5\n- path: {fifo}\n", KEY + "other": "- path: /nonexistent"})
+        devs = resp.adjust.linux.devices
+        assert len(devs) == 1 and devs[0].path == str(fifo) and devs[0].type == "p" and devs[0].gid.value == 5
+        assert len(rt.create_container("pod", "plain", {}).adjust.linux.devices) == 0
+        with pytest.raises(RuntimeError, match="failed to get info from device path /nonexistent"):
+            rt.create_container("pod", "other", {KEY + "other": "- path: /nonexistent"})      # error => container creation fails
+    finally:
+        rt.close()
+        t.join(5)
+    assert not t.is_alive()                                # plugin returns when the runtime goes away
