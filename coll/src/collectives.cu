@@ -52,12 +52,17 @@ static b200collResult_t dispatch_types(b200collDataType_t in, b200collDataType_t
 
 struct Grid { int blocks, threads; };
 
-// Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs).
-static Grid pick_grid(size_t vecs, int unroll, int max_ctas) {
+// Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs),
+// unless the family's shape pins the thread count.
+enum { kShapeNvls = 0, kShapeP2p = 1, kShapeLL = 2 };
+static Grid pick_grid(const b200collComm* c, int kind, size_t vecs, int unroll) {
   static const int forced = [] { const char* e = getenv("B200COLL_FORCE_THREADS"); return e ? atoi(e) : 0; }();
-  if (forced >= 32 && forced <= 512) {
-    size_t b = (vecs + (size_t)forced * unroll - 1) / ((size_t)forced * unroll);
-    return Grid{(int)std::max<size_t>(1, std::min<size_t>(b, (size_t)max_ctas)), forced};
+  const int max_ctas = std::max(1, std::min(c->shape[kind].max_ctas > 0 ? c->shape[kind].max_ctas : c->max_ctas, c->max_ctas));
+  int pinned = c->shape[kind].threads;
+  if (forced >= 32 && forced <= 512) pinned = forced;
+  if (pinned) {
+    size_t b = (vecs + (size_t)pinned * unroll - 1) / ((size_t)pinned * unroll);
+    return Grid{(int)std::max<size_t>(1, std::min<size_t>(b, (size_t)max_ctas)), pinned};
   }
   for (int t : {128, 256, 512}) {
     size_t b = (vecs + (size_t)t * unroll - 1) / ((size_t)t * unroll);
@@ -90,7 +95,7 @@ static b200collResult_t copy_scale(b200collComm* c, const void* send, void* recv
   if (send == recv && ep->in_dtype == ep->out_dtype && scale == 1.0f) return b200collSuccess;
   return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-    Grid g = pick_grid(count / Epv<InT>::value + 1, 1, c->max_ctas * 4);
+    Grid g = pick_grid(c, kShapeP2p, count / Epv<InT>::value + 1, 4);
     k_copy_scale<InT, OutT><<<g.blocks, g.threads, 0, st>>>(static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale);
     LAUNCH_CHECK(c);
     return b200collSuccess;
@@ -103,7 +108,7 @@ static b200collResult_t launch_ll(b200collComm* c, b200collOp_t op, const void* 
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
     constexpr int E = Epv<InT>::value;
     const size_t nv = (count + E - 1) / E;
-    Grid g = pick_grid(nv, 1, std::min(c->max_ctas, 148));
+    Grid g = pick_grid(c, kShapeLL, nv, 1);
     const InT* in = static_cast<const InT*>(send); OutT* out = static_cast<OutT*>(recv);
     const bool mc = c->nvls;
     switch (op) {
@@ -136,13 +141,13 @@ static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const
     const size_t nvec = count / E;
     const size_t in_off = arena_off(c, send);
     if (algo == b200collAlgoOneShot) {
-      Grid g = pick_grid(nvec, 2, c->max_ctas);
+      Grid g = pick_grid(c, kShapeP2p, nvec, 2);
       k_pull_reduce<InT, OutT, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
     } else if (algo == b200collAlgoTwoShot) {
-      Grid g = pick_grid(nvec / c->nranks + 1, 2, c->max_ctas);
+      Grid g = pick_grid(c, kShapeP2p, nvec / c->nranks + 1, 2);
       k_ar_twoshot<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, b200collOpAllReduce);
     } else {
-      Grid g = pick_grid(nvec / c->nranks + 1, 4, c->max_ctas);
+      Grid g = pick_grid(c, kShapeNvls, nvec / c->nranks + 1, 4);
       k_ar_nvls<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
     }
     LAUNCH_CHECK(c);
@@ -223,7 +228,7 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
     account(c, b200collOpAllGather, n * is, algo);
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-      Grid g = pick_grid(n / Epv<InT>::value, 4, c->max_ctas);
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvls : kShapeP2p, n / Epv<InT>::value, 4);
       if (algo == b200collAlgoNvls) k_ag_push<InT, OutT, true><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
       else k_ag_push<InT, OutT, false><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
       LAUNCH_CHECK(c);
@@ -266,7 +271,7 @@ b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recv
     account(c, b200collOpReduceScatter, n * is, algo);
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-      Grid g = pick_grid(n / Epv<InT>::value, 2, c->max_ctas);
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvls : kShapeP2p, n / Epv<InT>::value, 2);
       if (algo == b200collAlgoNvls) k_pull_reduce<InT, OutT, false, true><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
       else k_pull_reduce<InT, OutT, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
       LAUNCH_CHECK(c);
@@ -293,7 +298,7 @@ static b200collResult_t a2av_launch(b200collComm* c, const void* send, void* rec
   const int identity = (ep->in_dtype == ep->out_dtype && ep->scale == 1.0f) ? 1 : 0;
   return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-    Grid g = pick_grid((size_t)a.prefix[c->nranks] + 1, 4, c->max_ctas);
+    Grid g = pick_grid(c, kShapeP2p, (size_t)a.prefix[c->nranks] + 1, 4);
     k_a2av_push<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), arena_off(c, recv_sym), a, ep->scale, identity, b200collOpAllToAll);
     LAUNCH_CHECK(c);
     return b200collSuccess;

@@ -209,6 +209,11 @@ static void finalize_comm(b200collComm* c) {
   if (c->cfg.max_ctas > 0) c->max_ctas = c->cfg.max_ctas;
   if (c->max_ctas <= 0) c->max_ctas = c->sm_count > 0 ? 2 * c->sm_count : 128;
   if (c->max_ctas > kMaxBlocks) c->max_ctas = kMaxBlocks;
+  c->shape[0].max_ctas = std::min<int>((int)env_long("B200COLL_NVLS_CTAS", c->shape[0].max_ctas), c->max_ctas);
+  c->shape[0].threads = (int)env_long("B200COLL_NVLS_THREADS", c->shape[0].threads);
+  c->shape[1].max_ctas = std::min<int>((int)env_long("B200COLL_P2P_CTAS", c->max_ctas), c->max_ctas);
+  c->shape[1].threads = (int)env_long("B200COLL_P2P_THREADS", 0);
+  c->shape[2].max_ctas = std::min(c->shape[2].max_ctas, c->max_ctas);
   const char* fa = getenv("B200COLL_ALGO");
   if (fa && *fa) {
     for (int a = 0; a < b200collNumAlgos; a++) if (!strcasecmp(fa, b200collAlgoName((b200collAlgo_t)a))) c->forced_algo = (b200collAlgo_t)a;
@@ -414,6 +419,7 @@ b200collResult_t b200collCommInitRank(b200collComm_t* out, int nranks, const b20
     int same = 0;
     for (int r = 0; r < nranks; r++) if (!memcmp(infos[r].uuid, mine.uuid, 16)) same++;
     c->max_ctas = std::max(1, std::min(c->max_ctas, c->sm_count / std::max(1, same)));
+    for (auto& sh : c->shape) sh.max_ctas = std::min(sh.max_ctas, c->max_ctas);
   }
   BOOT_TRY(c->boot->barrier());
   *out = c.release();
@@ -487,7 +493,10 @@ b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* de
     rc = init_local_state(c.get());
     if (rc != b200collSuccess) return fail(rc);
     finalize_comm(c.get());
-    if (dup) c->max_ctas = std::max(1, std::min(c->max_ctas, c->sm_count / std::max(1, per_dev[c->device % 64])));
+    if (dup) {
+      c->max_ctas = std::max(1, std::min(c->max_ctas, c->sm_count / std::max(1, per_dev[c->device % 64])));
+      for (auto& sh : c->shape) sh.max_ctas = std::min(sh.max_ctas, c->max_ctas);
+    }
   }
   group->alive = n;
   for (int i = 0; i < n; i++) comms[i] = cs[i].release();
@@ -591,6 +600,15 @@ b200collResult_t b200collCommSetAlgo(b200collComm_t c, b200collAlgo_t a) {
 b200collResult_t b200collCommSetMaxCtas(b200collComm_t c, int m) {
   if (!c || m < 1) return b200collInvalidArgument;
   c->max_ctas = std::min(m, kMaxBlocks);
+  for (auto& sh : c->shape) sh.max_ctas = c->max_ctas;
+  return b200collSuccess;
+}
+
+b200collResult_t b200collCommSetLaunchShape(b200collComm_t c, int kind, int max_ctas, int threads) {
+  if (!c || kind < 0 || kind > 2) return b200collInvalidArgument;
+  if (threads != 0 && (threads < 32 || threads > 512 || threads % 32)) return b200collInvalidArgument;
+  if (max_ctas > 0) c->shape[kind].max_ctas = std::min(max_ctas, kMaxBlocks);
+  c->shape[kind].threads = threads;
   return b200collSuccess;
 }
 
@@ -633,3 +651,21 @@ b200collResult_t b200collSelfCheck(char* buf, size_t buflen) {
 }
 
 }  // extern "C"
+
+// Test hook (CPU-only): run the rendezvous protocol with arbitrary descriptors (memfd in the unit tests) so the
+// SCM_RIGHTS plumbing is covered without a GPU. out_fds must hold nranks ints; bcast_fd receives rank 0's descriptor.
+extern "C" int b200collBootstrapSelfTest(const char* name, int rank, int nranks, int my_fd, int* out_fds, int* bcast_fd, int timeout_ms) {
+  b200coll::Bootstrap b;
+  std::string e = b.init(name ? name : "selftest", rank, nranks, timeout_ms);
+  if (!e.empty()) { b200coll::set_last_error(e); return 1; }
+  std::vector<char> all;
+  int mine = rank * 7 + 1;
+  if (!(e = b.allgather(&mine, sizeof(mine), &all)).empty()) { b200coll::set_last_error(e); return 2; }
+  for (int r = 0; r < nranks; r++) { int v; memcpy(&v, all.data() + r * sizeof(int), sizeof(int)); if (v != r * 7 + 1) { b200coll::set_last_error("allgather payload mismatch"); return 3; } }
+  std::vector<int> fds;
+  if (!(e = b.exchange_fds(my_fd, &fds)).empty()) { b200coll::set_last_error(e); return 4; }
+  for (int r = 0; r < nranks; r++) out_fds[r] = fds[r];
+  if (!(e = b.broadcast_fd(0, rank == 0 ? my_fd : -1, bcast_fd)).empty()) { b200coll::set_last_error(e); return 5; }
+  if (!(e = b.barrier()).empty()) { b200coll::set_last_error(e); return 6; }
+  return 0;
+}

@@ -72,6 +72,7 @@ struct b200collComm {
   std::mutex mu;
   b200collAlgo_t forced_algo = b200collAlgoAuto;
   int max_ctas = 0;
+  struct Shape { int max_ctas; int threads; } shape[3] = {{32, 256}, {0, 0}, {148, 0}};   // NVLS, P2P, LL
   b200collStats stats{};
   std::shared_ptr<b200coll::SharedGroup> group;
   void* stats_shm = nullptr;       // exported stats page (metrics exporter reads it)

@@ -27,19 +27,18 @@ static const Row kBuiltin[] = {
   // ---- all-reduce
   {b200collOpAllReduce,     2, 2, -1,  256ull << 10, b200collAlgoLL},
   {b200collOpAllReduce,     2, 2, -1,  INF,          b200collAlgoTwoShot},   // N=2: NVLS would bounce my own half through the switch
-  {b200collOpAllReduce,     3, 8, -1,  128ull << 10, b200collAlgoLL},
+  {b200collOpAllReduce,     3, 8, -1,  256ull << 10, b200collAlgoLL},     // 8xB200: LL 12.7 us vs NVLS 15.2 us at 256 KiB; NVLS wins from 512 KiB
   {b200collOpAllReduce,     3, 8,  1,  INF,          b200collAlgoNvls},
   {b200collOpAllReduce,     3, 8,  0,  INF,          b200collAlgoTwoShot},
   // ---- all-gather (bytes = per-rank contribution)
-  {b200collOpAllGather,     2, 8, -1,   32ull << 10, b200collAlgoLL},
-  {b200collOpAllGather,     3, 8,  1,  INF,          b200collAlgoNvls},
+  {b200collOpAllGather,     2, 8, -1,  256ull << 10, b200collAlgoLL},     // 8xB200: 2 MiB total in 13 us (push+barrier: 17 us at 1 MiB)
   {b200collOpAllGather,     2, 8, -1,  INF,          b200collAlgoTwoShot},
   // ---- reduce-scatter (bytes = per-rank result)
-  {b200collOpReduceScatter, 2, 8, -1,   32ull << 10, b200collAlgoLL},
+  {b200collOpReduceScatter, 2, 8, -1,  256ull << 10, b200collAlgoLL},
   {b200collOpReduceScatter, 3, 8,  1,  INF,          b200collAlgoNvls},
   {b200collOpReduceScatter, 2, 8, -1,  INF,          b200collAlgoTwoShot},
   // ---- all-to-all (bytes = per-peer block)
-  {b200collOpAllToAll,      2, 8, -1,   32ull << 10, b200collAlgoLL},
+  {b200collOpAllToAll,      2, 8, -1,  256ull << 10, b200collAlgoLL},
   {b200collOpAllToAll,      2, 8, -1,  INF,          b200collAlgoTwoShot},
 };
 // clang-format on

@@ -48,6 +48,8 @@ struct Opts {
   size_t window = 192ull << 20;
   std::string json;
   int skew_us = 0;   // delay rank 0's launches (race hunting)
+  struct Shape { int kind, ctas, threads; };
+  std::vector<Shape> shapes;   // --sweep kind:ctas:threads,... (launch-shape tuning inside one process)
 };
 
 static size_t parse_size(const char* s) {
@@ -159,6 +161,9 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
     const size_t in_b = in_elems * is, out_b = out_elems * os;
     const size_t slot_b = (std::max(in_b, out_b / os * is) + 4095) / 4096 * 4096;
     int slots = (int)std::min<size_t>(64, std::max<size_t>(1, o.window / slot_b));
+    const size_t nshapes = o.shapes.empty() ? 1 : o.shapes.size();
+    for (size_t si = 0; si < nshapes; si++) {
+    if (!o.shapes.empty()) CC(b200collCommSetLaunchShape(ctx.comm, o.shapes[si].kind, o.shapes[si].ctas, o.shapes[si].threads));
     double res_us[2] = {-1, -1}; long res_err[2] = {0, 0};
     const char* algo_used = "?";
     for (int ip = 0; ip < 2; ip++) {
@@ -232,14 +237,16 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
       const double factor = is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
       double ab[2], bb[2];
       for (int ip = 0; ip < 2; ip++) { ab[ip] = res_us[ip] > 0 ? tb / res_us[ip] / 1e3 : 0; bb[ip] = n > 1 ? ab[ip] * factor : ab[ip]; }
+      if (!o.shapes.empty()) printf("[k%d c%d t%d] ", o.shapes[si].kind, o.shapes[si].ctas, o.shapes[si].threads);
       printf("%14zu %12zu %6s %8s | %10.2f %8.2f %8.2f %6ld | %10.2f %8.2f %8.2f %6ld\n", tb, count, dt_name(o.in_dt), algo_used, res_us[0], ab[0], bb[0], res_err[0], res_us[1], ab[1], bb[1], res_err[1]);
       fflush(stdout);
       if (jf) {
-        fprintf(jf, "{\"op\":\"%s\",\"nranks\":%d,\"bytes\":%zu,\"in\":\"%s\",\"out\":\"%s\",\"scale\":%g,\"algo\":\"%s\",\"oop_us\":%.3f,\"ip_us\":%.3f,\"oop_busbw\":%.3f,\"ip_busbw\":%.3f,\"errors\":%ld,\"mode\":\"%s\"}\n",
-                o.op.c_str(), n, tb, dt_name(o.in_dt), dt_name(o.out_dt), o.scale, algo_used, res_us[0], res_us[1], bb[0], bb[1], res_err[0] + res_err[1], o.procs ? "procs" : "threads");
+        fprintf(jf, "{\"op\":\"%s\",\"nranks\":%d,\"bytes\":%zu,\"in\":\"%s\",\"out\":\"%s\",\"scale\":%g,\"algo\":\"%s\",\"oop_us\":%.3f,\"ip_us\":%.3f,\"oop_busbw\":%.3f,\"ip_busbw\":%.3f,\"errors\":%ld,\"mode\":\"%s\",\"shape\":\"%d:%d:%d\"}\n",
+                o.op.c_str(), n, tb, dt_name(o.in_dt), dt_name(o.out_dt), o.scale, algo_used, res_us[0], res_us[1], bb[0], bb[1], res_err[0] + res_err[1], o.procs ? "procs" : "threads", o.shapes.empty() ? -1 : o.shapes[si].kind, o.shapes.empty() ? 0 : o.shapes[si].ctas, o.shapes.empty() ? 0 : o.shapes[si].threads);
         fflush(jf);
       }
     }
+    }   // shapes
   }
   if (jf) fclose(jf);
   b200collStats s; CC(b200collCommStatsGet(ctx.comm, &s));
@@ -274,6 +281,14 @@ int main(int argc, char** argv) {
     else if (a == "--window") o.window = parse_size(next());
     else if (a == "--json") o.json = next();
     else if (a == "--skew-us") o.skew_us = atoi(next());
+    else if (a == "--sweep") {
+      std::string v = next(); size_t p = 0;
+      while (p < v.size()) {
+        Opts::Shape sh{0, 0, 0};
+        if (sscanf(v.c_str() + p, "%d:%d:%d", &sh.kind, &sh.ctas, &sh.threads) == 3) o.shapes.push_back(sh);
+        p = v.find(',', p); if (p == std::string::npos) break; p++;
+      }
+    }
     else if (a == "--selfcheck") { char buf[4096]; b200collResult_t r = b200collSelfCheck(buf, sizeof(buf)); fputs(buf, stdout); return r == b200collSuccess ? 0 : 1; }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 1; }
   }

@@ -152,16 +152,30 @@ class NcclBackend:
         self.torch = torch
         for k, v in nccl_ref.REFERENCE_ENV.items():
             os.environ.setdefault(k, v)
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200_REF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        uid = nccl_ref.NcclComm.new_unique_id() if dist.rank == 0 else None
-        uid = dist.bcast_bytes(uid, 128)
-        self.comm = nccl_ref.NcclComm(dist.rank, dist.world, uid)
+        if os.environ.get("B200_REF_PROFILE", "1") == "0":      # stock NCCL defaults instead of the reference's env profile
+            for k in nccl_ref.REFERENCE_ENV:
+                os.environ.pop(k, None)
+        # NCCL prints "NCCL version ..." on stdout at any debug level >= VERSION: keep stdout to the one JSON line
+        if "B200_REF_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["B200_REF_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            uid = nccl_ref.NcclComm.new_unique_id() if dist.rank == 0 else None
+            uid = dist.bcast_bytes(uid, 128)
+            self.comm = nccl_ref.NcclComm(dist.rank, dist.world, uid)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        self.profile = "reference env profile" if os.environ.get("B200_REF_PROFILE", "1") != "0" else "NCCL defaults"
         self.send = torch.empty(capacity_elems, dtype=dtype, device="cuda")
         self.recv = torch.empty(capacity_elems, dtype=dtype, device="cuda")
         self.dt = {torch.bfloat16: nccl_ref.NCCL_BFLOAT16, torch.float16: nccl_ref.NCCL_FLOAT16, torch.float32: nccl_ref.NCCL_FLOAT32}[dtype]
         self.itemsize = self.send.element_size()
         self.nvls = None
-        self.version = f"NCCL {self.comm.version} ({os.path.basename(self.comm.path)})"
+        self.version = f"NCCL {self.comm.version} ({os.path.basename(self.comm.path)}; {self.profile})"
         self._launches = 0
 
     def algo(self, op, nbytes):

@@ -1,0 +1,108 @@
+"""libb200coll host-side logic that needs no GPU: tuner table, config/env, unique ids, graceful no-driver paths, and the
+Unix-socket rendezvous (SCM_RIGHTS) exercised across real processes with memfd descriptors."""
+import ctypes as C
+import multiprocessing as mp
+import os
+
+import pytest
+
+from container_engine_accelerators_b200.ops import coll
+
+
+@pytest.fixture(scope="module")
+def lib(coll_lib):
+    return coll.load()
+
+
+def test_version_and_names(lib):
+    assert lib.b200collGetVersion() >= 1
+    assert [lib.b200collAlgoName(i).decode() for i in range(6)] == coll.ALGO_NAMES
+    assert [lib.b200collTypeSize(t) for t in (coll.F32, coll.F16, coll.BF16, coll.FP8_E4M3)] == [4, 2, 2, 1]
+
+
+@pytest.mark.parametrize("op,nbytes,n,nvls,want", [
+    (coll.OP_ALLREDUCE, 1024, 1, True, "copy"),
+    (coll.OP_ALLREDUCE, 1024, 8, True, "ll"), (coll.OP_ALLREDUCE, 256 << 10, 8, True, "ll"), (coll.OP_ALLREDUCE, 512 << 10, 8, True, "nvls"),
+    (coll.OP_ALLREDUCE, 1 << 30, 8, True, "nvls"), (coll.OP_ALLREDUCE, 1 << 30, 8, False, "twoshot"),
+    (coll.OP_ALLREDUCE, 1 << 30, 2, True, "twoshot"),            # N=2: NVLS would bounce my own half through the switch
+    (coll.OP_ALLGATHER, 4096, 4, True, "ll"), (coll.OP_ALLGATHER, 64 << 20, 8, True, "twoshot"),
+    (coll.OP_REDUCESCATTER, 64 << 20, 8, True, "nvls"), (coll.OP_REDUCESCATTER, 64 << 20, 8, False, "twoshot"),
+    (coll.OP_ALLTOALL, 1 << 10, 8, True, "ll"), (coll.OP_ALLTOALL, 32 << 20, 8, True, "twoshot"),
+])
+def test_tuner_table(lib, op, nbytes, n, nvls, want):
+    assert coll.tuner_pick(op, nbytes, n, nvls) == want
+
+
+def test_tuner_file_override(coll_lib, tmp_path):
+    import subprocess, sys
+    tbl = tmp_path / "t.tbl"
+    tbl.write_text("# op nmin nmax nvls max_bytes algo\nall_reduce 2 8 * 1024 oneshot\nall_reduce 2 8 * inf twoshot\n")
+    code = "from container_engine_accelerators_b200.ops import coll; print(coll.tuner_pick(0, 512, 8, True), coll.tuner_pick(0, 1<<20, 8, True), coll.tuner_pick(1, 64, 8, True))"
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "B200COLL_TUNER_FILE": str(tbl)}, capture_output=True, text=True)
+    assert r.stdout.split() == ["oneshot", "twoshot", "ll"], r.stderr
+
+
+def test_config_defaults_follow_env(lib, monkeypatch):
+    monkeypatch.setenv("B200COLL_ARENA_MB", "123"); monkeypatch.setenv("B200COLL_NVLS", "0"); monkeypatch.setenv("B200COLL_TIMEOUT_MS", "777")
+    cfg = coll.Comm.make_config()
+    assert (cfg.arena_bytes, cfg.enable_nvls, cfg.timeout_ms) == (123 << 20, 0, 777)
+
+
+def test_unique_id_from_string_is_deterministic(lib):
+    a, b, c = coll.UniqueId(), coll.UniqueId(), coll.UniqueId()
+    lib.b200collUniqueIdFromString(b"127.0.0.1:29500/x", C.byref(a)); lib.b200collUniqueIdFromString(b"127.0.0.1:29500/x", C.byref(b)); lib.b200collUniqueIdFromString(b"127.0.0.1:29501/x", C.byref(c))
+    assert a.internal == b.internal != c.internal
+    lib.b200collGetUniqueId(C.byref(a)); lib.b200collGetUniqueId(C.byref(b))
+    assert a.internal != b.internal
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="GPU box: the no-driver path is not reachable")
+def test_no_driver_is_reported_not_crashed(lib):
+    ok, report = coll.self_check()
+    assert not ok and "driver" in report
+    with pytest.raises(coll.B200CollError) as ei:
+        coll.Comm.init_all([0], arena_mb=8)
+    assert ei.value.code == coll.NO_DRIVER
+
+
+def _boot_rank(lib_path, name, rank, n, q):
+    L = C.CDLL(lib_path)
+    fd = os.memfd_create(f"r{rank}")
+    os.write(fd, f"payload-from-rank-{rank}".encode())
+    out = (C.c_int * n)()
+    bc = C.c_int(-1)
+    rc = L.b200collBootstrapSelfTest(name.encode(), rank, n, fd, out, C.byref(bc), 20000)
+    got = []
+    if rc == 0:
+        for r in range(n):
+            os.lseek(out[r], 0, os.SEEK_SET)
+            got.append(os.read(out[r], 64).decode())
+        os.lseek(bc.value, 0, os.SEEK_SET)
+        got.append(os.read(bc.value, 64).decode())
+    q.put((rank, rc, got))
+
+
+@pytest.mark.parametrize("n", [2, 5])
+def test_bootstrap_fd_exchange_across_processes(coll_lib, n):
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    name = f"pytest-{os.getpid()}-{n}"
+    procs = [ctx.Process(target=_boot_rank, args=(coll_lib, name, r, n, q)) for r in range(n)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=60) for _ in range(n))
+    for p in procs:
+        p.join(10)
+    want = [f"payload-from-rank-{r}" for r in range(n)] + ["payload-from-rank-0"]
+    for rank, rc, got in results:
+        assert rc == 0 and got == want, (rank, rc, got)
+
+
+def test_bootstrap_times_out_when_a_rank_is_missing(coll_lib):
+    L = C.CDLL(coll_lib)
+    L.b200collGetLastError.restype = C.c_char_p
+    out = (C.c_int * 2)()
+    bc = C.c_int(-1)
+    fd = os.memfd_create("x")
+    rc = L.b200collBootstrapSelfTest(f"pytest-timeout-{os.getpid()}".encode(), 0, 2, fd, out, C.byref(bc), 300)
+    assert rc == 1 and b"timed out" in L.b200collGetLastError()

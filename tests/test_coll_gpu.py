@@ -1,0 +1,269 @@
+"""GPU tests for libb200coll (run with `pytest -m gpu` on a B200 box). Every numerics check compares the CUDA kernel with a
+plain PyTorch fp32 reference of the same op. On a one-GPU box the P2P protocols are exercised with virtual ranks that
+share cuda:0 (in-process group, one stream per rank); NVLS/multicast and true multi-process tests need >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PERF = os.path.join(ROOT, "build", "b200coll_perf")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def coll_mod(coll_lib):
+    from container_engine_accelerators_b200.ops import coll
+    coll.load()          # raises if the .so is missing: GPU tests must never pass on a fallback
+    return coll
+
+
+@pytest.fixture
+def group(torch_cuda, coll_mod, request):
+    n = getattr(request, "param", 2)
+    comms = coll_mod.Comm.init_all([0] * n, arena_mb=96)
+    streams = [torch_cuda.cuda.Stream() for _ in comms]
+    yield comms, streams
+    torch_cuda.cuda.synchronize()
+    for c in comms:
+        c.destroy()
+
+
+def fill(torch, comms, count, dtype):
+    srcs = []
+    for r, c in enumerate(comms):
+        t = c.empty(count, dtype)
+        t.copy_((((torch.arange(count, device="cuda") * (2 * r + 3) + r) % 17) - 8).to(dtype) * 0.25)
+        srcs.append(t)
+    torch.cuda.synchronize()
+    return srcs
+
+
+def run_all(torch, comms, streams, fn):
+    for r, c in enumerate(comms):
+        fn(r, c, streams[r])
+    torch.cuda.synchronize()
+    for c in comms:
+        c.check_async_error()
+
+
+def test_self_check_and_arena_tensor_aliasing(torch_cuda, coll_mod):
+    ok, report = coll_mod.self_check()
+    assert ok, report
+    (c,) = coll_mod.Comm.init_all([0], arena_mb=16)
+    t = c.empty(1024, torch_cuda.bfloat16)
+    assert c.is_symmetric(t) and t.data_ptr() == t._b200coll_buf.ptr       # zero-copy view of arena memory
+    t.fill_(3.0)
+    out = c.empty(1024, torch_cuda.float32)
+    c.all_reduce(t, out, scale=0.5)                                        # nranks == 1: fused scale/cast copy kernel
+    torch_cuda.cuda.synchronize()
+    assert torch_cuda.equal(out, torch_cuda.full((1024,), 1.5, device="cuda"))
+    assert c.stats()["kernel_launches"] == 1
+    c.destroy()
+
+
+@pytest.mark.parametrize("group", [2, 4], indirect=True)
+@pytest.mark.parametrize("algo", ["ll", "oneshot", "twoshot"])
+@pytest.mark.parametrize("count", [8, 1000, 1 << 15])
+def test_all_reduce_matches_fp32_reference(torch_cuda, group, algo, count):
+    torch = torch_cuda
+    comms, streams = group
+    srcs = fill(torch, comms, count, torch.bfloat16)
+    dsts = [c.empty(count, torch.bfloat16) for c in comms]
+    want = sum(s.float() for s in srcs)
+    for c in comms:
+        c.set_algo(algo)
+    run_all(torch, comms, streams, lambda r, c, st: c.all_reduce(srcs[r], dsts[r], stream=st))
+    for d in dsts:
+        assert torch.equal(d.float(), want)
+    for a, b in zip(dsts, dsts[1:]):
+        assert torch.equal(a, b)                # every rank holds bit-identical results
+
+
+@pytest.mark.parametrize("group", [4], indirect=True)
+def test_in_place_and_repeated_launches_rotate_lamport_buffers(torch_cuda, group):
+    torch = torch_cuda
+    comms, streams = group
+    for c in comms:
+        c.set_algo("ll")
+    for it, count in enumerate([4096, 64, 9000, 16, 4096, 4096, 128]):     # shrinking/growing sizes: stale-slot clearing must follow
+        srcs = fill(torch, comms, count, torch.bfloat16)
+        want = sum(s.float() for s in srcs)
+        run_all(torch, comms, streams, lambda r, c, st: c.all_reduce(srcs[r], stream=st))
+        for s in srcs:
+            assert torch.equal(s.float(), want), f"iteration {it} count {count}"
+
+
+@pytest.mark.parametrize("group", [2], indirect=True)
+@pytest.mark.parametrize("in_dt,out_dt,scale", [("bfloat16", "float32", 0.5), ("float32", "bfloat16", 0.25), ("float16", "float16", 2.0), ("bfloat16", "float8_e4m3fn", 0.125)])
+def test_fused_scale_cast_epilogue(torch_cuda, group, in_dt, out_dt, scale):
+    torch = torch_cuda
+    comms, streams = group
+    count = 4096
+    srcs = fill(torch, comms, count, getattr(torch, in_dt))
+    dsts = [c.empty(count, getattr(torch, out_dt)) for c in comms]
+    want = (sum(s.float() for s in srcs) * scale)
+    for algo in ("ll", "twoshot"):
+        for c in comms:
+            c.set_algo(algo)
+        run_all(torch, comms, streams, lambda r, c, st: c.all_reduce(srcs[r], dsts[r], scale=scale, stream=st))
+        for d in dsts:
+            if out_dt == "float8_e4m3fn":
+                assert torch.allclose(d.float(), want.to(torch.float8_e4m3fn).float())
+            else:
+                assert torch.equal(d.float(), want.to(getattr(torch, out_dt)).float()), algo
+
+
+@pytest.mark.parametrize("group", [4], indirect=True)
+@pytest.mark.parametrize("algo", ["ll", "twoshot"])
+def test_all_gather_reduce_scatter_all_to_all(torch_cuda, group, algo):
+    torch = torch_cuda
+    comms, streams = group
+    n, count = len(comms), 2048
+    for c in comms:
+        c.set_algo(algo)
+    srcs = fill(torch, comms, count, torch.bfloat16)
+    gat = [c.empty(count * n, torch.bfloat16) for c in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.all_gather(srcs[r], gat[r], stream=st))
+    for g in gat:
+        assert torch.equal(g, torch.cat(srcs))
+    big = fill(torch, comms, count * n, torch.bfloat16)
+    rs = [c.empty(count, torch.bfloat16) for c in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.reduce_scatter(big[r], rs[r], stream=st))
+    total = sum(b.float() for b in big)
+    for r in range(n):
+        assert torch.equal(rs[r].float(), total[r * count:(r + 1) * count])
+    a2a = [c.empty(count * n, torch.bfloat16) for c in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.all_to_all(big[r], a2a[r], stream=st))
+    for r in range(n):
+        want = torch.cat([big[s][r * count:(r + 1) * count] for s in range(n)])
+        assert torch.equal(a2a[r], want)
+
+
+@pytest.mark.parametrize("group", [4], indirect=True)
+def test_all_to_all_v_expert_dispatch(torch_cuda, group):
+    """Skewed per-peer row counts (MoE dispatch shape): rows land at the offsets the receiver advertised."""
+    torch = torch_cuda
+    comms, streams = group
+    n, hidden = len(comms), 256
+    rows = [[(3 * s + 5 * d) % 7 for d in range(n)] for s in range(n)]                 # rows[s][d]: s -> d
+    send = []
+    for s, c in enumerate(comms):
+        t = c.empty(sum(rows[s]) * hidden + hidden, torch.bfloat16)
+        t.copy_(((torch.arange(t.numel(), device="cuda") + 100 * s) % 251).to(torch.bfloat16))
+        send.append(t)
+    recv = [c.empty(sum(rows[s][d] for s in range(n)) * hidden + hidden, torch.bfloat16) for d, c in enumerate(comms)]
+    for t in recv:
+        t.zero_()
+    torch.cuda.synchronize()
+    send_off = [[sum(rows[s][:d]) for d in range(n)] for s in range(n)]
+    recv_off = [[sum(rows[x][d] for x in range(s)) for s in range(n)] for d in range(n)]  # recv_off[d][s]: where s's rows start at d
+    run_all(torch, comms, streams, lambda r, c, st: c.all_to_all_v(send[r], recv[r], hidden, rows[r], send_off[r], [recv_off[d][r] for d in range(n)], stream=st))
+    for d in range(n):
+        for s in range(n):
+            got = recv[d][recv_off[d][s] * hidden:(recv_off[d][s] + rows[s][d]) * hidden]
+            want = send[s][send_off[s][d] * hidden:(send_off[s][d] + rows[s][d]) * hidden]
+            assert torch.equal(got, want), (s, d)
+
+
+@pytest.mark.parametrize("group", [2], indirect=True)
+def test_buffers_outside_the_arena_are_staged(torch_cuda, group):
+    torch = torch_cuda
+    comms, streams = group
+    count = 1 << 20                                             # 2 MiB > LL limit: must take the staging path
+    srcs = [(((torch.arange(count, device="cuda") * (r + 2)) % 9) - 4).to(torch.bfloat16) for r in range(len(comms))]
+    dsts = [torch.empty(count, dtype=torch.bfloat16, device="cuda") for _ in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.all_reduce(srcs[r], dsts[r], stream=st))
+    want = sum(s.float() for s in srcs)
+    for d in dsts:
+        assert torch.equal(d.float(), want)
+    assert all(c.stats()["staged_calls"] == 1 for c in comms)
+
+
+@pytest.mark.parametrize("group", [2], indirect=True)
+def test_cuda_graph_replay(torch_cuda, group):
+    """Epochs and Lamport phases live in device memory, so a captured collective replays correctly."""
+    torch = torch_cuda
+    comms, streams = group
+    count = 2048
+    srcs = fill(torch, comms, count, torch.bfloat16)
+    dsts = [c.empty(count, torch.bfloat16) for c in comms]
+    graphs = []
+    for algo in ("ll", "twoshot"):
+        for c in comms:
+            c.set_algo(algo)
+        graphs = []
+        for r, c in enumerate(comms):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=streams[r]):
+                c.all_reduce(srcs[r], dsts[r], stream=streams[r])
+            graphs.append(g)
+        for it in range(5):
+            for r in range(len(comms)):
+                srcs[r].add_(1.0)
+            torch.cuda.synchronize()
+            want = sum(s.float() for s in srcs)
+            for r, g in enumerate(graphs):
+                with torch.cuda.stream(streams[r]):
+                    g.replay()
+            torch.cuda.synchronize()
+            for d in dsts:
+                assert torch.equal(d.float(), want), (algo, it)
+
+
+def test_watchdog_reports_instead_of_hanging(torch_cuda, coll_mod):
+    """Only one of two ranks launches: its spin must time out, record a fault and return."""
+    torch = torch_cuda
+    comms = coll_mod.Comm.init_all([0, 0], arena_mb=32, timeout_ms=300)
+    src = comms[0].empty(1024, torch.bfloat16); src.fill_(1.0)
+    comms[0].set_algo("twoshot")
+    comms[0].all_reduce(src)
+    torch.cuda.synchronize()
+    with pytest.raises(coll_mod.B200CollError, match="watchdog"):
+        comms[0].check_async_error()
+    with pytest.raises(coll_mod.B200CollError):
+        comms[0].all_reduce(src)                  # poisoned communicator refuses further work
+    for c in comms:
+        c.destroy()
+
+
+def test_perf_tool_virtual_ranks_zero_errors(torch_cuda, coll_lib):
+    assert os.path.exists(PERF), "build/b200coll_perf missing (python -c 'import __graft_entry__ as g; g.build()')"
+    for op in ("all_reduce", "all_gather", "reduce_scatter", "alltoall"):
+        r = subprocess.run([PERF, "--devs", "0,0,0,0", "--op", op, "-b", "1K", "-e", "1M", "-f", "4", "--iters", "3", "--warmup", "1"], capture_output=True, text=True, timeout=120,
+                           env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "errors=0" in r.stdout
+
+
+def test_multi_gpu_procs_nvls(torch_cuda, coll_lib):
+    n = torch_cuda.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    devs = ",".join(str(i) for i in range(n))
+    for algo in ("auto", "nvls", "twoshot"):
+        r = subprocess.run([PERF, "--devs", devs, "--procs", "--op", "all_reduce", "--algo", algo, "-b", "1K", "-e", "64M", "-f", "16", "--iters", "3", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
+        assert r.returncode == 0 and "errors=0" in r.stdout, r.stdout + r.stderr
+
+
+def test_bench_contract_one_gpu(torch_cuda):
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--max", "16M"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(line) == 1
+    d = json.loads(line[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
+        assert k in d
+    assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
