@@ -72,7 +72,8 @@ typedef enum {
   b200collAlgoTwoShot = 3,   /* P2P pull-reduce own slice + push to peers    (mid/large, no multicast needed) */
   b200collAlgoNvls = 4,      /* multimem.ld_reduce / multimem.st through the switch (large) */
   b200collAlgoCopy = 5,      /* nranks == 1: fused scale/cast copy */
-  b200collNumAlgos = 6
+  b200collAlgoLL2 = 6,       /* two-shot Lamport all-reduce: zero barriers, 2S bytes received instead of N*S (mid) */
+  b200collNumAlgos = 7
 } b200collAlgo_t;
 
 /* Fused epilogue: out = cast<out_dtype>(reduce(in) * scale). scale==1.0f and equal dtypes is the plain collective. */

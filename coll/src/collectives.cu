@@ -132,6 +132,26 @@ static b200collResult_t launch_ll(b200collComm* c, b200collOp_t op, const void* 
   });
 }
 
+// Two-shot Lamport all-reduce (same-size in/out types only; any local pointers, in-place allowed).
+template <typename InT, typename OutT>
+static b200collResult_t launch_ll2_typed(b200collComm* c, const void* send, void* recv, size_t count, float scale, cudaStream_t st) {
+  constexpr int E = Epv<InT>::value;
+  const size_t nslice = ((count + E - 1) / E + c->nranks - 1) / c->nranks;
+  Grid g = pick_grid(c, kShapeLL, nslice, 1);
+  if (c->nvls) k_ll_twoshot<InT, OutT, true><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
+  else k_ll_twoshot<InT, OutT, false><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
+  LAUNCH_CHECK(c);
+  return b200collSuccess;
+}
+static b200collResult_t launch_ll2(b200collComm* c, const void* send, void* recv, size_t count, const b200collEpilogue* ep, float scale, cudaStream_t st) {
+  const b200collDataType_t i = ep->in_dtype, o = ep->out_dtype;
+  if (i == b200collFloat32 && o == b200collFloat32) return launch_ll2_typed<float, float>(c, send, recv, count, scale, st);
+  if (i == b200collBfloat16 && o == b200collBfloat16) return launch_ll2_typed<bf16, bf16>(c, send, recv, count, scale, st);
+  if (i == b200collFloat16 && o == b200collFloat16) return launch_ll2_typed<__half, __half>(c, send, recv, count, scale, st);
+  set_last_error("two-shot LL needs in_dtype == out_dtype");
+  return b200collInvalidArgument;
+}
+
 // ------------------------------------------------------------------------------------------------ all-reduce on symmetric buffers
 static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const void* send, void* recv, size_t count, const b200collEpilogue* ep, float scale, cudaStream_t st) {
   const int identity = (ep->in_dtype == ep->out_dtype && scale == 1.0f) ? 1 : 0;
@@ -176,7 +196,8 @@ b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, c
   b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllReduce, bytes, c->nranks, c->nvls);
   auto feasible = [&](b200collAlgo_t a) {
     switch (a) {
-      case b200collAlgoLL: return bytes <= kLLMaxBytes;
+      case b200collAlgoLL: return bytes <= kLLOneShotMaxBytes;
+      case b200collAlgoLL2: return is == os && bytes <= kLLOneShotMaxBytes * (size_t)c->nranks;
       case b200collAlgoOneShot: return sym_in && !inplace;
       case b200collAlgoTwoShot: return sym_in && sym_out;
       case b200collAlgoNvls: return c->nvls && sym_in && sym_out;
@@ -185,10 +206,11 @@ b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, c
   };
   if (!feasible(algo)) {
     algo = b200collAlgoAuto;
-    for (b200collAlgo_t a : {b200collAlgoNvls, b200collAlgoTwoShot, b200collAlgoOneShot, b200collAlgoLL})
+    for (b200collAlgo_t a : {b200collAlgoNvls, b200collAlgoTwoShot, b200collAlgoOneShot, b200collAlgoLL, b200collAlgoLL2})
       if (feasible(a) && !(a == b200collAlgoNvls && c->nranks == 2)) { algo = a; break; }
   }
   if (algo == b200collAlgoLL) { account(c, b200collOpAllReduce, bytes, algo); return launch_ll(c, b200collOpAllReduce, send, recv, count, ep, scale, st); }
+  if (algo == b200collAlgoLL2) { account(c, b200collOpAllReduce, bytes, algo); return launch_ll2(c, send, recv, count, ep, scale, st); }
   if (algo != b200collAlgoAuto) { account(c, b200collOpAllReduce, bytes, algo); return ar_symmetric(c, algo, send, recv, count, ep, scale, st); }
   // ---- staged: buffers outside the arena and too big for LL. Chunk through the two staging halves.
   c->stats.staged_calls++;
@@ -220,7 +242,8 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
   const bool sym_out = b200collIsSymmetric(c, recv, (size_t)c->nranks * sendcount * os);
   b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllGather, bytes, c->nranks, c->nvls);
   if (algo == b200collAlgoOneShot) algo = b200collAlgoTwoShot;
-  if (algo == b200collAlgoLL && bytes > kLLMaxBytes) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL2) algo = b200collAlgoLL;
+  if (algo == b200collAlgoLL && bytes > kLLOneShotMaxBytes) algo = b200collAlgoTwoShot;
   if (algo == b200collAlgoNvls && !c->nvls) algo = b200collAlgoTwoShot;
   if (algo == b200collAlgoLL) { account(c, b200collOpAllGather, bytes, algo); return launch_ll(c, b200collOpAllGather, send, recv, sendcount, ep, scale, st); }
   const int identity = (ep->in_dtype == ep->out_dtype && scale == 1.0f) ? 1 : 0;
@@ -264,7 +287,8 @@ b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recv
   const bool sym_in = b200collIsSymmetric(c, send, (size_t)c->nranks * bytes);
   b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpReduceScatter, bytes, c->nranks, c->nvls);
   if (algo == b200collAlgoOneShot) algo = b200collAlgoTwoShot;
-  if (algo == b200collAlgoLL && bytes > kLLMaxBytes) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL2) algo = b200collAlgoLL;
+  if (algo == b200collAlgoLL && bytes > kLLOneShotMaxBytes) algo = b200collAlgoTwoShot;
   if (algo == b200collAlgoNvls && !c->nvls) algo = b200collAlgoTwoShot;
   if (algo == b200collAlgoLL) { account(c, b200collOpReduceScatter, bytes, algo); return launch_ll(c, b200collOpReduceScatter, send, recv, recvcount, ep, scale, st); }
   auto pull = [&](const void* s_slice_of_mine, void* r, size_t n) -> b200collResult_t {
@@ -327,7 +351,8 @@ b200collResult_t b200collAllToAll(const void* send, void* recv, size_t count, co
   const size_t E = 16 / is;
   if (count % E != 0) { set_last_error("all-to-all count must be a multiple of 16 bytes / sizeof(in_dtype)"); return b200collInvalidArgument; }
   b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllToAll, bytes, c->nranks, c->nvls);
-  if (algo != b200collAlgoLL || bytes > kLLMaxBytes) algo = b200collAlgoTwoShot;
+  if (algo == b200collAlgoLL2) algo = b200collAlgoLL;
+  if (algo != b200collAlgoLL || bytes > kLLOneShotMaxBytes) algo = b200collAlgoTwoShot;
   if (algo == b200collAlgoLL) { account(c, b200collOpAllToAll, bytes * c->nranks, algo); return launch_ll(c, b200collOpAllToAll, send, recv, count, ep, ep->scale, st); }
   const bool sym_out = b200collIsSymmetric(c, recv, (size_t)c->nranks * count * os);
   auto run = [&](const void* s, size_t s_stride_elems, void* r_sym, size_t n) -> b200collResult_t {

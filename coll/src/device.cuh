@@ -22,8 +22,10 @@ constexpr int kMaxBlocks = 1024;                        // flag rows
 constexpr size_t kOffFlags = 0;                         // u32 [kMaxBlocks][kMaxRanks]
 constexpr size_t kFlagsBytes = (size_t)kMaxBlocks * kMaxRanks * 4;
 constexpr size_t kOffLL = 1 << 20;                      // Lamport scratch: [3][kMaxRanks][kLLMaxVecs] x 16 B
-constexpr size_t kLLMaxBytes = 512 << 10;               // per-source slot
+constexpr size_t kLLMaxBytes = 1 << 20;                 // per-source slot: lo half = one-shot / phase 1, hi half = two-shot phase 2
 constexpr size_t kLLMaxVecs = kLLMaxBytes / 16;
+constexpr size_t kLLHalfVecs = kLLMaxVecs / 2;
+constexpr size_t kLLOneShotMaxBytes = kLLHalfVecs * 16; // 512 KiB per source
 constexpr size_t kLLBytes = 3 * (size_t)kMaxRanks * kLLMaxBytes;
 constexpr size_t kOffStage = kOffLL + kLLBytes;         // staging for buffers outside the arena (2 halves)
 constexpr size_t kStageHalfBytes = 32u << 20;
@@ -32,7 +34,7 @@ constexpr uint32_t kLLSentinel = 0xFFFFFFFFu;           // a NaN pattern in f32/
 constexpr uint32_t kLLSanitized = 0x7FFF7FFFu;          // still NaN in every supported type
 
 // local (non-symmetric) per-comm state words
-enum { kSeqBarrier = 0, kSeqLL = 1, kTicket = 2, kLLUsed0 = 3 /* 3,4,5 */, kStateWords = 8 };
+enum { kSeqBarrier = 0, kSeqLL = 1, kTicket = 2, kLLUsedLo0 = 3 /* 3,4,5 */, kLLUsedHi0 = 6 /* 6,7,8 */, kStateWords = 16 };
 
 struct CommDev {
   int rank, nranks;

@@ -108,8 +108,9 @@ __global__ void __launch_bounds__(kThreads) k_ll(CommDev c, const InT* __restric
   const uint32_t k = load_seq(c, kSeqLL);
   const uint32_t buf = k % 3, prev = (k + 2) % 3;
   const size_t nv = (count + E - 1) / E;
-  const size_t used_prev = c.state[kLLUsed0 + prev];
-  const size_t span = nv > used_prev ? nv : used_prev;
+  const size_t used_prev = c.state[kLLUsedLo0 + prev], used_prev_hi = c.state[kLLUsedHi0 + prev];
+  size_t span = nv > used_prev ? nv : used_prev;
+  if (used_prev_hi > span) span = used_prev_hi;
   char* const me = c.peer[c.rank];
   const uint4 empty = make_uint4(kLLSentinel, kLLSentinel, kLLSentinel, kLLSentinel);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < span; i += (size_t)gridDim.x * blockDim.x) {
@@ -140,6 +141,10 @@ __global__ void __launch_bounds__(kThreads) k_ll(CommDev c, const InT* __restric
 #pragma unroll
       for (int r = 0; r < kMaxRanks; r++) if (r < c.nranks) st_vec(ll_slot(me, prev, r, i), empty);
     }
+    if (i < used_prev_hi) {
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; r++) if (r < c.nranks) st_vec(ll_slot(me, prev, r, kLLHalfVecs + i), empty);
+    }
     if (i < nv) {
       if (SUM) {
         float acc[E] = {};
@@ -162,7 +167,100 @@ __global__ void __launch_bounds__(kThreads) k_ll(CommDev c, const InT* __restric
   }
   __syncthreads();
   if (threadIdx.x == 0 && last_block_ticket(c)) {
-    c.state[kLLUsed0 + buf] = (uint32_t)nv;
+    c.state[kLLUsedLo0 + buf] = (uint32_t)nv;
+    c.state[kLLUsedHi0 + buf] = 0;
+    c.state[kSeqLL] = k + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-shot Lamport all-reduce: zero barriers like k_ll, but each rank receives 2S instead of N*S bytes.
+// Phase 1 (reduce-scatter): rank s pushes vector i of slice p into peer p's lo slot (buf, s, i); rank p sums the
+// N copies of its slice in fp32, applies scale/cast. Phase 2 (all-gather): p publishes the finished vector into
+// everybody's hi slot (buf, p, i) — one multimem.st when MC — and every rank copies the N slices into out.
+// One thread owns vector i of *every* slice end to end, so there is no intra-kernel dependency between threads
+// and in-place is safe (a thread reads all its inputs before its first write). Needs sizeof(OutT) == sizeof(InT).
+template <typename OutT, int E>
+__device__ __forceinline__ void store_raw_guarded(OutT* out, size_t vec, size_t count, const uint4& w) {
+  if ((vec + 1) * E <= count) { st_vec(out + vec * E, w); return; }
+  union { OutT e[E]; uint4 v; } u;
+  u.v = w;
+#pragma unroll
+  for (int k = 0; k < E; k++) if (vec * E + k < count) out[vec * E + k] = u.e[k];
+}
+
+template <typename InT, typename OutT, bool MC>
+__global__ void __launch_bounds__(kThreads) k_ll_twoshot(CommDev c, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+  static_assert(sizeof(InT) == sizeof(OutT), "two-shot LL keeps one vector geometry for both phases");
+  constexpr int E = Epv<InT>::value;
+  const uint32_t k = load_seq(c, kSeqLL);
+  const uint32_t buf = k % 3, prev = (k + 2) % 3;
+  const size_t nvec = (count + E - 1) / E;
+  const size_t nslice = (nvec + c.nranks - 1) / c.nranks;
+  const size_t used_lo = c.state[kLLUsedLo0 + prev], used_hi = c.state[kLLUsedHi0 + prev];
+  size_t span = nslice > used_lo ? nslice : used_lo;
+  if (used_hi > span) span = used_hi;
+  char* const me = c.peer[c.rank];
+  const uint4 empty = make_uint4(kLLSentinel, kLLSentinel, kLLSentinel, kLLSentinel);
+  const size_t my0 = (size_t)c.rank * nslice;
+  const size_t my_len = my0 >= nvec ? 0 : (nvec - my0 < nslice ? nvec - my0 : nslice);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < span; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 own = make_uint4(0, 0, 0, 0);
+    if (i < nslice) {
+#pragma unroll
+      for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) {
+        int p = c.rank + j; if (p >= c.nranks) p -= c.nranks;
+        const size_t v = (size_t)p * nslice + i;
+        if (v < nvec) {
+          uint4 d = ll_sanitize(load_in_guarded<InT, E>(in, v, count));
+          if (j == 0) own = d; else st_vec_volatile(ll_slot(c.peer[p], buf, c.rank, i), d);
+        }
+      }
+    }
+    if (i < used_lo) {
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; r++) if (r < c.nranks) st_vec(ll_slot(me, prev, r, i), empty);
+    }
+    if (i < used_hi) {
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; r++) if (r < c.nranks) st_vec(ll_slot(me, prev, r, kLLHalfVecs + i), empty);
+    }
+    if (i < my_len) {
+      float acc[E] = {};
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; r++) if (r < c.nranks) {
+        uint4 d = (r == c.rank) ? own : ll_wait(c, ll_slot(me, buf, r, i), r, op);
+        unpack_add<InT>(acc, d);
+      }
+#pragma unroll
+      for (int e = 0; e < E; e++) acc[e] *= scale;
+      uint32_t w[4];
+      Pack<OutT, E>::run(acc, w);
+      const uint4 red = ll_sanitize(make_uint4(w[0], w[1], w[2], w[3]));
+      if (MC) {
+        const uint32_t rw[4] = {red.x, red.y, red.z, red.w};
+        mc_st_words(ll_slot(c.mc, buf, c.rank, kLLHalfVecs + i), rw, 4);
+      } else {
+#pragma unroll
+        for (int j = 1; j < kMaxRanks; j++) if (j < c.nranks) {
+          int p = c.rank + j; if (p >= c.nranks) p -= c.nranks;
+          st_vec_volatile(ll_slot(c.peer[p], buf, c.rank, kLLHalfVecs + i), red);
+        }
+      }
+      store_raw_guarded<OutT, E>(out, my0 + i, count, red);
+    }
+    if (i < nslice) {
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; r++) if (r < c.nranks && r != c.rank) {
+        const size_t v = (size_t)r * nslice + i;
+        if (v < nvec) store_raw_guarded<OutT, E>(out, v, count, ll_wait(c, ll_slot(me, buf, r, kLLHalfVecs + i), r, op));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && last_block_ticket(c)) {
+    c.state[kLLUsedLo0 + buf] = (uint32_t)nslice;
+    c.state[kLLUsedHi0 + buf] = (uint32_t)nslice;
     c.state[kSeqLL] = k + 1;
   }
 }

@@ -26,8 +26,10 @@ static const unsigned long long INF = ~0ull;
 static const Row kBuiltin[] = {
   // ---- all-reduce
   {b200collOpAllReduce,     2, 2, -1,  256ull << 10, b200collAlgoLL},
+  {b200collOpAllReduce,     2, 2, -1,  1ull << 20,   b200collAlgoLL2},
   {b200collOpAllReduce,     2, 2, -1,  INF,          b200collAlgoTwoShot},   // N=2: NVLS would bounce my own half through the switch
   {b200collOpAllReduce,     3, 8, -1,  256ull << 10, b200collAlgoLL},     // 8xB200: LL 12.7 us vs NVLS 15.2 us at 256 KiB; NVLS wins from 512 KiB
+  {b200collOpAllReduce,     3, 8, -1,  2ull << 20,   b200collAlgoLL2},    // two-shot Lamport: 2S received, no barrier (cap: nranks x 512 KiB)
   {b200collOpAllReduce,     3, 8,  1,  INF,          b200collAlgoNvls},
   {b200collOpAllReduce,     3, 8,  0,  INF,          b200collAlgoTwoShot},
   // ---- all-gather (bytes = per-rank contribution)
@@ -99,6 +101,7 @@ const char* b200collAlgoName(b200collAlgo_t a) {
     case b200collAlgoTwoShot: return "twoshot";
     case b200collAlgoNvls: return "nvls";
     case b200collAlgoCopy: return "copy";
+    case b200collAlgoLL2: return "ll2";
     default: return "?";
   }
 }

@@ -19,11 +19,12 @@ run n1_ar --devs 0 --op all_reduce -b 1K -e 16M -f 16 --iters 5 --warmup 1 --sca
 # virtual ranks on GPU 0 (P2P protocols only)
 for n in 2 4; do
   devs=$(python3 -c "print(','.join(['0']*$n))")
-  for algo in ll oneshot twoshot; do
+  for algo in ll ll2 oneshot twoshot; do
     run v${n}_ar_${algo} --devs $devs --op all_reduce --algo $algo -b 1K -e 256K -f 4 --iters 5 --warmup 2
   done
   run v${n}_ar_tail --devs $devs --op all_reduce --algo twoshot -b 1030 -e 70000 -f 3 --iters 3 --warmup 1
   run v${n}_ar_ll_tail --devs $devs --op all_reduce --algo ll -b 1030 -e 70000 -f 3 --iters 3 --warmup 1
+  run v${n}_ar_ll2_tail --devs $devs --op all_reduce --algo ll2 -b 1030 -e 700000 -f 3 --iters 3 --warmup 1
   for op in all_gather reduce_scatter alltoall; do
     run v${n}_${op}_ll --devs $devs --op $op --algo ll -b 1K -e 256K -f 4 --iters 5 --warmup 2
     run v${n}_${op}_p2p --devs $devs --op $op --algo twoshot -b 1K -e 4M -f 8 --iters 5 --warmup 2
@@ -35,7 +36,7 @@ if [ "$NG" -ge 2 ]; then
   all=$(python3 -c "print(','.join(str(i) for i in range($NG)))")
   for mode in "" "--procs"; do
     tag=${mode:+p}
-    for algo in ll oneshot twoshot nvls; do
+    for algo in ll ll2 oneshot twoshot nvls; do
       run g${NG}${tag}_ar_${algo} --devs $all $mode --op all_reduce --algo $algo -b 1K -e 64M -f 16 --iters 5 --warmup 2
     done
     run g${NG}${tag}_ar_auto --devs $all $mode --op all_reduce -b 1K -e 256M -f 4 --iters 5 --warmup 2

@@ -32,7 +32,7 @@ DUTY_CYCLE_WINDOW_S = 10
 _CONTAINER_LABELS = ["namespace", "pod", "container", "make", "accelerator_id", "model"]
 _NODE_LABELS = ["make", "accelerator_id", "model"]
 COLL_OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall")
-COLL_ALGOS = ("auto", "ll", "oneshot", "twoshot", "nvls", "copy")
+COLL_ALGOS = ("auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2")
 
 
 def get_devices_for_all_containers(socket_path: str = POD_RESOURCES_SOCKET, timeout: float = 5.0) -> dict:
@@ -69,12 +69,12 @@ def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*") -> list:
         try:
             with open(path, "rb") as f:
                 raw = f.read(4096)
-            if len(raw) < 64 + 8 * 16 or raw[:8] != b"B200COLL":
+            if len(raw) < 64 + 8 * 17 or raw[:8] != b"B200COLL":
                 continue
             version, pid, rank, nranks, device, nvls = struct.unpack_from("<6I", raw, 8)
-            vals = struct.unpack_from("<16Q", raw, 64)
+            vals = struct.unpack_from("<17Q", raw, 64)
             pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "calls": vals[0:4], "bytes": vals[4:8],
-                          "algo_calls": vals[8:14], "kernel_launches": vals[14], "staged_calls": vals[15]})
+                          "algo_calls": vals[8:15], "kernel_launches": vals[15], "staged_calls": vals[16]})
         except OSError:
             continue
     return pages

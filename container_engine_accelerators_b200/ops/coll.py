@@ -28,8 +28,8 @@ MAX_RANKS = 8
 F32, F16, BF16, FP8_E4M3 = 0, 1, 2, 3
 SUM, AVG = 0, 1
 OP_ALLREDUCE, OP_ALLGATHER, OP_REDUCESCATTER, OP_ALLTOALL = 0, 1, 2, 3
-ALGO_AUTO, ALGO_LL, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_COPY = range(6)
-ALGO_NAMES = ["auto", "ll", "oneshot", "twoshot", "nvls", "copy"]
+ALGO_AUTO, ALGO_LL, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_COPY, ALGO_LL2 = range(7)
+ALGO_NAMES = ["auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2"]
 DTYPE_SIZE = {F32: 4, F16: 2, BF16: 2, FP8_E4M3: 1}
 
 
@@ -52,7 +52,7 @@ class CommInfo(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("calls", C.c_uint64 * 4), ("bytes", C.c_uint64 * 4), ("algo_calls", C.c_uint64 * 6), ("kernel_launches", C.c_uint64),
+    _fields_ = [("calls", C.c_uint64 * 4), ("bytes", C.c_uint64 * 4), ("algo_calls", C.c_uint64 * 7), ("kernel_launches", C.c_uint64),
                 ("staged_calls", C.c_uint64)]
 
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
     L.b200collTunerPick.argtypes = [ci, sz, ci, ci]; L.b200collTunerPick.restype = ci
     L.b200collCommSetAlgo.argtypes = [vp, ci]
     L.b200collCommSetMaxCtas.argtypes = [vp, ci]
+    L.b200collCommSetLaunchShape.argtypes = [vp, ci, ci, ci]
     L.b200collAlgoName.argtypes = [ci]; L.b200collAlgoName.restype = C.c_char_p
     L.b200collTypeSize.argtypes = [ci]; L.b200collTypeSize.restype = sz
     L.b200collSelfCheck.argtypes = [C.c_char_p, sz]
@@ -295,6 +296,9 @@ class Comm:
 
     def set_max_ctas(self, n: int) -> None:
         _check(load().b200collCommSetMaxCtas(self._h, n), "CommSetMaxCtas")
+
+    def set_launch_shape(self, kind: str, max_ctas: int = 0, threads: int = 0) -> None:
+        _check(load().b200collCommSetLaunchShape(self._h, {"nvls": 0, "p2p": 1, "ll": 2}[kind], max_ctas, threads), "CommSetLaunchShape")
 
     def stats(self) -> dict:
         s = Stats()

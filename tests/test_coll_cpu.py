@@ -16,13 +16,13 @@ def lib(coll_lib):
 
 def test_version_and_names(lib):
     assert lib.b200collGetVersion() >= 1
-    assert [lib.b200collAlgoName(i).decode() for i in range(6)] == coll.ALGO_NAMES
+    assert [lib.b200collAlgoName(i).decode() for i in range(7)] == coll.ALGO_NAMES
     assert [lib.b200collTypeSize(t) for t in (coll.F32, coll.F16, coll.BF16, coll.FP8_E4M3)] == [4, 2, 2, 1]
 
 
 @pytest.mark.parametrize("op,nbytes,n,nvls,want", [
     (coll.OP_ALLREDUCE, 1024, 1, True, "copy"),
-    (coll.OP_ALLREDUCE, 1024, 8, True, "ll"), (coll.OP_ALLREDUCE, 256 << 10, 8, True, "ll"), (coll.OP_ALLREDUCE, 512 << 10, 8, True, "nvls"),
+    (coll.OP_ALLREDUCE, 1024, 8, True, "ll"), (coll.OP_ALLREDUCE, 256 << 10, 8, True, "ll"), (coll.OP_ALLREDUCE, 512 << 10, 8, True, "ll2"), (coll.OP_ALLREDUCE, 4 << 20, 8, True, "nvls"),
     (coll.OP_ALLREDUCE, 1 << 30, 8, True, "nvls"), (coll.OP_ALLREDUCE, 1 << 30, 8, False, "twoshot"),
     (coll.OP_ALLREDUCE, 1 << 30, 2, True, "twoshot"),            # N=2: NVLS would bounce my own half through the switch
     (coll.OP_ALLGATHER, 4096, 4, True, "ll"), (coll.OP_ALLGATHER, 64 << 20, 8, True, "twoshot"),

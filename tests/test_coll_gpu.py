@@ -73,7 +73,7 @@ def test_self_check_and_arena_tensor_aliasing(torch_cuda, coll_mod):
 
 
 @pytest.mark.parametrize("group", [2, 4], indirect=True)
-@pytest.mark.parametrize("algo", ["ll", "oneshot", "twoshot"])
+@pytest.mark.parametrize("algo", ["ll", "ll2", "oneshot", "twoshot"])
 @pytest.mark.parametrize("count", [8, 1000, 1 << 15])
 def test_all_reduce_matches_fp32_reference(torch_cuda, group, algo, count):
     torch = torch_cuda
@@ -94,9 +94,10 @@ def test_all_reduce_matches_fp32_reference(torch_cuda, group, algo, count):
 def test_in_place_and_repeated_launches_rotate_lamport_buffers(torch_cuda, group):
     torch = torch_cuda
     comms, streams = group
-    for c in comms:
-        c.set_algo("ll")
-    for it, count in enumerate([4096, 64, 9000, 16, 4096, 4096, 128]):     # shrinking/growing sizes: stale-slot clearing must follow
+    for it, (algo, count) in enumerate([("ll", 4096), ("ll2", 64), ("ll", 9000), ("ll2", 70001), ("ll2", 16), ("ll", 4096), ("ll2", 4096), ("ll", 128), ("ll", 128)]):
+        # shrinking/growing sizes and alternating one-/two-shot Lamport kernels: stale-slot clearing (lo and hi halves) must follow
+        for c in comms:
+            c.set_algo(algo)
         srcs = fill(torch, comms, count, torch.bfloat16)
         want = sum(s.float() for s in srcs)
         run_all(torch, comms, streams, lambda r, c, st: c.all_reduce(srcs[r], stream=st))
@@ -158,11 +159,12 @@ def test_all_to_all_v_expert_dispatch(torch_cuda, group):
     n, hidden = len(comms), 256
     rows = [[(3 * s + 5 * d) % 7 for d in range(n)] for s in range(n)]                 # rows[s][d]: s -> d
     send = []
+    cap = max(max(sum(rows[s]) for s in range(n)), max(sum(rows[s][d] for s in range(n)) for d in range(n))) + 1
     for s, c in enumerate(comms):
-        t = c.empty(sum(rows[s]) * hidden + hidden, torch.bfloat16)
+        t = c.empty(cap * hidden, torch.bfloat16)            # symmetric allocation: same size, same order on every rank
         t.copy_(((torch.arange(t.numel(), device="cuda") + 100 * s) % 251).to(torch.bfloat16))
         send.append(t)
-    recv = [c.empty(sum(rows[s][d] for s in range(n)) * hidden + hidden, torch.bfloat16) for d, c in enumerate(comms)]
+    recv = [c.empty(cap * hidden, torch.bfloat16) for c in comms]
     for t in recv:
         t.zero_()
     torch.cuda.synchronize()
@@ -199,7 +201,7 @@ def test_cuda_graph_replay(torch_cuda, group):
     srcs = fill(torch, comms, count, torch.bfloat16)
     dsts = [c.empty(count, torch.bfloat16) for c in comms]
     graphs = []
-    for algo in ("ll", "twoshot"):
+    for algo in ("ll", "ll2", "twoshot"):
         for c in comms:
             c.set_algo(algo)
         graphs = []

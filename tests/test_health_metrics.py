@@ -183,7 +183,7 @@ def test_coll_stats_page_is_exported(tmp_path):
     page = bytearray(4096)
     page[0:8] = b"B200COLL"
     struct.pack_into("<6I", page, 8, 1, 4242, 3, 8, 3, 1)
-    struct.pack_into("<16Q", page, 64, 10, 0, 0, 2, 1 << 30, 0, 0, 4096, 0, 7, 0, 1, 2, 0, 12, 0)
+    struct.pack_into("<17Q", page, 64, 10, 0, 0, 2, 1 << 30, 0, 0, 4096, 0, 7, 0, 1, 2, 0, 5, 12, 0)
     (tmp_path / "b200coll.4242.3").write_bytes(page)
     pages = metrics.read_coll_stats_pages(str(tmp_path / "b200coll.*"))
     assert pages[0]["pid"] == 4242 and pages[0]["calls"][0] == 10 and pages[0]["algo_calls"][1] == 7 and pages[0]["kernel_launches"] == 12
