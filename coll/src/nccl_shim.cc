@@ -1,0 +1,182 @@
+// libb200coll_nccl.so — the subset of the NCCL C API that nccl-tests' *_perf binaries (and most framework glue) call,
+// implemented on libb200coll, so an unmodified `all_reduce_perf` can be pointed at this library (LD_PRELOAD or a
+// libnccl.so.2 symlink in LD_LIBRARY_PATH=/usr/local/nvidia/lib64, which is how the reference's pods pick up the
+// installer-dropped NCCL: gpudirect-rdma/nccl-test-a4.yaml:42-68). SURVEY §5.8-6.
+// User buffers are ordinary cudaMalloc memory here, so calls take the Lamport path (<= 512 KiB) or the staged path;
+// ncclMemAlloc hands out symmetric-arena memory once a communicator exists (zero-copy + NVLS).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../include/b200coll.h"
+
+extern "C" {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0, ncclUnhandledCudaError = 1, ncclSystemError = 2, ncclInternalError = 3, ncclInvalidArgument = 4, ncclInvalidUsage = 5, ncclRemoteError = 6, ncclInProgress = 7 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8, ncclBfloat16 = 9 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4 } ncclRedOp_t;
+
+}  // extern "C"
+
+namespace {
+
+struct ShimComm { b200collComm_t comm; int nranks, rank, device; };
+struct P2pOp { bool send; const void* sbuf; void* rbuf; size_t count; ncclDataType_t dt; int peer; ShimComm* comm; cudaStream_t stream; };
+thread_local int g_group_depth = 0;
+thread_local std::vector<P2pOp> g_group_ops;
+std::mutex g_mu;
+ShimComm* g_last_comm = nullptr;   // ncclMemAlloc has no communicator argument
+
+ncclResult_t map_rc(b200collResult_t r) {
+  switch (r) {
+    case b200collSuccess: return ncclSuccess;
+    case b200collUnhandledCudaError: return ncclUnhandledCudaError;
+    case b200collSystemError: return ncclSystemError;
+    case b200collInvalidArgument: return ncclInvalidArgument;
+    case b200collInvalidUsage: return ncclInvalidUsage;
+    case b200collRemoteError: return ncclRemoteError;
+    default: return ncclInternalError;
+  }
+}
+
+bool map_dt(ncclDataType_t dt, b200collDataType_t* out) {
+  switch (dt) {
+    case ncclFloat32: *out = b200collFloat32; return true;
+    case ncclFloat16: *out = b200collFloat16; return true;
+    case ncclBfloat16: *out = b200collBfloat16; return true;
+    default: return false;   // integer / fp64 reductions are not implemented by libb200coll
+  }
+}
+
+ncclResult_t flush_group() {
+  std::vector<P2pOp> ops;
+  ops.swap(g_group_ops);
+  if (ops.empty()) return ncclSuccess;
+  // The only grouped pattern nccl-tests issues is alltoall: one send and one recv per peer, equal counts, contiguous blocks.
+  ShimComm* c = ops[0].comm;
+  const int n = c->nranks;
+  std::vector<const P2pOp*> sends(n, nullptr), recvs(n, nullptr);
+  for (const P2pOp& o : ops) {
+    if (o.comm != c || o.peer < 0 || o.peer >= n) return ncclInvalidUsage;
+    (o.send ? sends : recvs)[o.peer] = &o;
+  }
+  b200collDataType_t dt;
+  if ((int)ops.size() != 2 * n || !map_dt(ops[0].dt, &dt)) return ncclInvalidUsage;
+  const size_t count = ops[0].count, esz = b200collTypeSize(dt);
+  for (int p = 0; p < n; p++) {
+    if (!sends[p] || !recvs[p] || sends[p]->count != count || recvs[p]->count != count) return ncclInvalidUsage;
+    if ((const char*)sends[p]->sbuf != (const char*)sends[0]->sbuf + (size_t)p * count * esz) return ncclInvalidUsage;
+    if ((char*)recvs[p]->rbuf != (char*)recvs[0]->rbuf + (size_t)p * count * esz) return ncclInvalidUsage;
+  }
+  b200collEpilogue ep{dt, dt, 1.0f};
+  return map_rc(b200collAllToAll(sends[0]->sbuf, recvs[0]->rbuf, count, &ep, c->comm, ops[0].stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+ncclResult_t ncclGetVersion(int* v) { if (!v) return ncclInvalidArgument; *v = 22809; return ncclSuccess; }   // advertises the 2.28 API level
+const char* ncclGetErrorString(ncclResult_t r) { return b200collGetErrorString((b200collResult_t)r); }
+const char* ncclGetLastError(ncclComm_t) { return b200collGetLastError(); }
+
+ncclResult_t ncclGetUniqueId(ncclUniqueId* id) {
+  if (!id) return ncclInvalidArgument;
+  static_assert(sizeof(ncclUniqueId) == sizeof(b200collUniqueId), "id sizes must match");
+  return map_rc(b200collGetUniqueId(reinterpret_cast<b200collUniqueId*>(id)));
+}
+
+ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank) {
+  if (!comm) return ncclInvalidArgument;
+  ShimComm* s = new ShimComm{nullptr, nranks, rank, 0};
+  cudaGetDevice(&s->device);
+  b200collResult_t r = b200collCommInitRank(&s->comm, nranks, reinterpret_cast<const b200collUniqueId*>(&id), rank, nullptr);
+  if (r != b200collSuccess) { delete s; return map_rc(r); }
+  { std::lock_guard<std::mutex> lk(g_mu); g_last_comm = s; }
+  *comm = reinterpret_cast<ncclComm_t>(s);
+  return ncclSuccess;
+}
+
+ncclResult_t ncclCommInitAll(ncclComm_t* comms, int ndev, const int* devlist) {
+  if (!comms || ndev < 1 || ndev > B200COLL_MAX_RANKS) return ncclInvalidArgument;
+  b200collComm_t cs[B200COLL_MAX_RANKS];
+  b200collResult_t r = b200collCommInitAll(cs, ndev, devlist, nullptr);
+  if (r != b200collSuccess) return map_rc(r);
+  for (int i = 0; i < ndev; i++) comms[i] = reinterpret_cast<ncclComm_t>(new ShimComm{cs[i], ndev, i, devlist ? devlist[i] : i});
+  return ncclSuccess;
+}
+
+ncclResult_t ncclCommDestroy(ncclComm_t comm) {
+  ShimComm* s = reinterpret_cast<ShimComm*>(comm);
+  if (!s) return ncclInvalidArgument;
+  { std::lock_guard<std::mutex> lk(g_mu); if (g_last_comm == s) g_last_comm = nullptr; }
+  b200collResult_t r = b200collCommDestroy(s->comm);
+  delete s;
+  return map_rc(r);
+}
+ncclResult_t ncclCommFinalize(ncclComm_t) { return ncclSuccess; }
+ncclResult_t ncclCommAbort(ncclComm_t comm) { return ncclCommDestroy(comm); }
+ncclResult_t ncclCommCount(const ncclComm_t comm, int* n) { if (!comm || !n) return ncclInvalidArgument; *n = reinterpret_cast<ShimComm*>(comm)->nranks; return ncclSuccess; }
+ncclResult_t ncclCommUserRank(const ncclComm_t comm, int* r) { if (!comm || !r) return ncclInvalidArgument; *r = reinterpret_cast<ShimComm*>(comm)->rank; return ncclSuccess; }
+ncclResult_t ncclCommCuDevice(const ncclComm_t comm, int* d) { if (!comm || !d) return ncclInvalidArgument; *d = reinterpret_cast<ShimComm*>(comm)->device; return ncclSuccess; }
+ncclResult_t ncclCommGetAsyncError(ncclComm_t comm, ncclResult_t* out) {
+  if (!comm || !out) return ncclInvalidArgument;
+  *out = map_rc(b200collCommGetAsyncError(reinterpret_cast<ShimComm*>(comm)->comm, nullptr));
+  return ncclSuccess;
+}
+
+ncclResult_t ncclMemAlloc(void** ptr, size_t size) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_last_comm) return map_rc(b200collMemAlloc(g_last_comm->comm, ptr, size));
+  return cudaMalloc(ptr, size) == cudaSuccess ? ncclSuccess : ncclUnhandledCudaError;
+}
+ncclResult_t ncclMemFree(void* ptr) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_last_comm && b200collIsSymmetric(g_last_comm->comm, ptr, 1)) return map_rc(b200collMemFree(g_last_comm->comm, ptr));
+  return cudaFree(ptr) == cudaSuccess ? ncclSuccess : ncclUnhandledCudaError;
+}
+
+ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
+  b200collDataType_t t;
+  if (!comm || !map_dt(dt, &t) || (op != ncclSum && op != ncclAvg)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, 1.0f};
+  return map_rc(b200collAllReduce(send, recv, count, &ep, op == ncclAvg ? b200collAvg : b200collSum, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+}
+ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t dt, ncclComm_t comm, cudaStream_t stream) {
+  b200collDataType_t t;
+  if (!comm || !map_dt(dt, &t)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, 1.0f};
+  return map_rc(b200collAllGather(send, recv, sendcount, &ep, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+}
+ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
+  b200collDataType_t t;
+  if (!comm || !map_dt(dt, &t) || (op != ncclSum && op != ncclAvg)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, 1.0f};
+  return map_rc(b200collReduceScatter(send, recv, recvcount, &ep, op == ncclAvg ? b200collAvg : b200collSum, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+}
+
+ncclResult_t ncclGroupStart(void) { g_group_depth++; return ncclSuccess; }
+ncclResult_t ncclGroupEnd(void) {
+  if (g_group_depth <= 0) return ncclInvalidUsage;
+  if (--g_group_depth > 0) return ncclSuccess;
+  return flush_group();
+}
+ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm, cudaStream_t stream) {
+  if (!comm) return ncclInvalidArgument;
+  if (g_group_depth == 0) return ncclInvalidUsage;   // lone send/recv would need a matching call on the peer: only grouped all-to-all is mapped
+  g_group_ops.push_back(P2pOp{true, buf, nullptr, count, dt, peer, reinterpret_cast<ShimComm*>(comm), stream});
+  return ncclSuccess;
+}
+ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm, cudaStream_t stream) {
+  if (!comm) return ncclInvalidArgument;
+  if (g_group_depth == 0) return ncclInvalidUsage;
+  g_group_ops.push_back(P2pOp{false, nullptr, buf, count, dt, peer, reinterpret_cast<ShimComm*>(comm), stream});
+  return ncclSuccess;
+}
+
+}  // extern "C"
