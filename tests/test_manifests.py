@@ -1,0 +1,178 @@
+"""deploy/: the generated tree is up to date, parses, and keeps the invariants the node agents rely on; the embedded shell
+programs run against stubs. The reference has no tests for any manifest or script."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEPLOY = os.path.join(ROOT, "deploy")
+SCRIPTS = os.path.join(DEPLOY, "scripts")
+
+
+def docs(rel):
+    with open(os.path.join(DEPLOY, rel)) as f:
+        return [d for d in yaml.safe_load_all(f) if d]
+
+
+def test_generated_tree_is_current():
+    r = subprocess.run([sys.executable, os.path.join(DEPLOY, "generate.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_every_manifest_parses_and_has_kind():
+    files = glob.glob(os.path.join(DEPLOY, "**", "*.yaml"), recursive=True)
+    assert len(files) >= 74                      # the reference ships 74 YAML files
+    for f in files:
+        for d in yaml.safe_load_all(open(f)):
+            assert d and "kind" in d and "apiVersion" in d, f
+
+
+def test_device_plugin_daemonset_contract():
+    (ds,) = docs("device-plugin/device-plugin.yaml")
+    spec = ds["spec"]["template"]["spec"]
+    c = spec["containers"][0]
+    assert "--enable-container-gpu-metrics" in c["command"] and "--enable-health-monitoring" in c["command"]
+    paths = {v["name"]: v["hostPath"]["path"] for v in spec["volumes"]}
+    assert paths["device-plugin"] == "/var/lib/kubelet/device-plugins" and paths["nvidia"] == "/home/kubernetes/bin/nvidia" and paths["pod-resources"] == "/var/lib/kubelet/pod-resources"
+    mounts = {m["name"]: m["mountPath"] for m in c["volumeMounts"]}
+    assert mounts["device-plugin"] == "/device-plugin" and mounts["nvidia"] == "/usr/local/nvidia" and mounts["nvidia-config"] == "/etc/nvidia"
+    env = {e["name"]: e for e in c["env"]}
+    assert env["XID_CONFIG"]["valueFrom"]["configMapKeyRef"] == {"name": "xid-config", "key": "HealthCriticalXid", "optional": True}
+    assert env["NODE_NAME"]["valueFrom"]["fieldRef"]["fieldPath"] == "spec.nodeName"          # not GCE metadata
+    assert c["securityContext"]["privileged"] and spec["priorityClassName"] == "system-node-critical"
+    assert c["ports"][0]["containerPort"] == 2112
+    rbac = docs("device-plugin/rbac.yaml")
+    role = [d for d in rbac if d["kind"] == "ClusterRole"][0]
+    assert any("nodes/status" in r["resources"] and "patch" in r["verbs"] for r in role["rules"])
+
+
+def test_installer_shape_init_does_the_work_pause_keeps_running():
+    for rel in ("transport/b200coll-installer.yaml", "transport/compat/nccl-rdma-installer.yaml", "driver-installer/cos/daemonset-preloaded-latest.yaml", "partition-gpu/partition-gpu.yaml"):
+        ds = [d for d in docs(rel) if d["kind"] == "DaemonSet"][0]
+        spec = ds["spec"]["template"]["spec"]
+        assert spec["initContainers"] and spec["containers"][-1]["name"] == "pause", rel
+        assert spec["tolerations"] == [{"operator": "Exists"}] and spec["hostNetwork"] and spec["hostPID"], rel
+        assert ds["spec"]["updateStrategy"]["type"] == "RollingUpdate"
+
+
+def test_b200coll_installer_targets_b200_and_mounts_host_lib_dir():
+    (ds,) = docs("transport/b200coll-installer.yaml")
+    spec = ds["spec"]["template"]["spec"]
+    terms = spec["affinity"]["nodeAffinity"]["requiredDuringSchedulingIgnoredDuringExecution"]["nodeSelectorTerms"][0]["matchExpressions"]
+    assert {"key": "cloud.google.com/gke-accelerator", "operator": "In", "values": ["nvidia-b200"]} in terms
+    init = spec["initContainers"][0]
+    assert "libb200coll.so" in init["command"][2] and "--selfcheck" in init["command"][2]
+    assert {"name": "library-dir-host", "mountPath": "/usr/local/nvidia"} in init["volumeMounts"]
+
+
+def test_mig_and_a4x_variants():
+    mig = docs("driver-installer/cos/daemonset-nvidia-mig.yaml")[0]["spec"]["template"]["spec"]
+    assert [c["name"] for c in mig["initContainers"]] == ["nvidia-driver-installer", "partition-gpus"]
+    a4x = docs("driver-installer/cos/daemonset-preloaded-latest-a4x.yaml")[0]["spec"]["template"]["spec"]
+    assert [c["name"] for c in a4x["initContainers"]] == ["nvidia-driver-installer"]                     # GB200: no MIG step
+    conf = docs("driver-installer/cos/daemonset-confidential-latest.yaml")[0]["spec"]["template"]["spec"]
+    assert conf["initContainers"][1]["restartPolicy"] == "Always" and "confidential_node_type.txt" in conf["initContainers"][0]["command"][2]
+    vgpu = docs("driver-installer/cos/daemonset-vgpu-latest.yaml")[0]["spec"]["template"]["spec"]
+    assert vgpu["containers"][0]["name"] == "nvidia-daemon-installer" and "machine_type.txt" in vgpu["initContainers"][0]["command"][2]
+    for rel, ver in (("R525", "525"), ("R570", "570")):
+        env = {e["name"]: e.get("value") for e in docs(f"driver-installer/ubuntu/daemonset-preloaded-{rel}.yaml")[0]["spec"]["template"]["spec"]["initContainers"][0]["env"]}
+        assert env["NVIDIA_DRIVER_VERSION"].startswith(ver)
+
+
+def test_nccl_test_pods():
+    a4 = [d for d in docs("nccl-test/rdma/nccl-test-a4.yaml") if d["kind"] == "Pod"]
+    assert len(a4) == 2
+    import json
+    ifaces = json.loads(a4[0]["metadata"]["annotations"]["networking.gke.io/interfaces"])
+    assert len(ifaces) == 9 and ifaces[1] == {"interfaceName": "eth2", "network": "rdma-0"}               # 8 RDMA NICs
+    c = a4[0]["spec"]["containers"][0]
+    assert c["resources"]["limits"]["nvidia.com/gpu"] == 8 and "set_nccl_env.sh" in c["args"][0]
+    shm = [v for v in a4[0]["spec"]["volumes"] if v["name"] == "shared-memory"][0]
+    assert shm["emptyDir"] == {"medium": "Memory", "sizeLimit": "250Gi"}
+    tcpxo = [d for d in docs("nccl-test/tcpxo/nccl-test-latest.yaml") if d["kind"] == "Pod"][0]
+    ann = tcpxo["metadata"]["annotations"]
+    injected = yaml.safe_load(ann["devices.gke.io/container.tcpxo-daemon"])
+    assert {"path": "/dev/dmabuf_import_helper"} in injected and len(injected) == 11                      # 8 GPUs + nvidiactl + nvidia-uvm + helper
+    assert tcpxo["spec"]["initContainers"][0]["restartPolicy"] == "Always"
+    imex = docs("nccl-test/rdma/nccl-test-imex-a4x.yaml")
+    assert imex[0]["kind"] == "ComputeDomain" and [d for d in imex if d["kind"] == "Pod"][0]["spec"]["containers"][0]["resources"]["limits"]["nvidia.com/gpu"] == 4
+    js = [d for d in docs("nccl-test/rdma/nccl-test-a4x-max-jobset.yaml") if d["kind"] == "JobSet"][0]
+    assert "all_gather_perf" in str(js) and "-b 1K -e 8G -f 2 -g 1 -w 5 --iters 100 -c 1" in str(js)
+    ours = docs("nccl-test/b200coll-test.yaml")[0]
+    assert "b200coll_perf --procs --ranks 8" in ours["spec"]["containers"][0]["args"][0]
+
+
+def test_scripts_have_valid_syntax():
+    for f in glob.glob(os.path.join(SCRIPTS, "*.sh")):
+        assert subprocess.run(["bash", "-n", f]).returncode == 0, f
+
+
+def stub(tmp_path, name, body="exit 0"):
+    p = tmp_path / name
+    p.write_text(f"#!/bin/bash\necho \"{name} $*\" >> {tmp_path}/calls.log\n{body}\n")
+    p.chmod(0o755)
+    return str(p)
+
+
+def test_cos_driver_install_skips_when_module_loaded(tmp_path):
+    inst = stub(tmp_path, "cos-gpu-installer")
+    (tmp_path / "root/home/kubernetes/bin/nvidia").mkdir(parents=True)
+    env = {**os.environ, "COS_GPU_INSTALLER": inst, "ROOT_MOUNT_DIR": str(tmp_path / "root"), "LSMOD": stub(tmp_path, "lsmod", "echo 'nvidia 123 0'")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "cos-driver-install.sh")], env=env).returncode == 0
+    assert "cos-gpu-installer" not in (tmp_path / "calls.log").read_text()
+    env["LSMOD"] = stub(tmp_path, "lsmod2", "echo 'ext4 1 1'")
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "cos-driver-install.sh")], env=env).returncode == 0
+    assert "cos-gpu-installer install --version=latest" in (tmp_path / "calls.log").read_text()
+    assert oct((tmp_path / "root/home/kubernetes/bin/nvidia").stat().st_mode)[-3:] == "755"
+
+
+def test_transport_install_copies_tree(tmp_path):
+    src = tmp_path / "src"; (src / "sub").mkdir(parents=True); (src / "libnccl-net.so").write_text("x"); (src / "sub" / "tuner.textproto").write_text("y")
+    extra = tmp_path / "gib"; extra.mkdir(); (extra / "set_nccl_env.sh").write_text("z")
+    env = {**os.environ, "TRANSPORT_SRC_DIR": str(src), "NCCL_INSTALL_DIR": str(tmp_path / "dst"), "TRANSPORT_ENTRY": stub(tmp_path, "container_entry.sh"),
+           "TRANSPORT_EXTRA_SRC": str(extra), "TRANSPORT_EXTRA_DST": str(tmp_path / "gib-host")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "transport-install.sh")], env=env).returncode == 0
+    assert (tmp_path / "dst/libnccl-net.so").exists() and (tmp_path / "dst/sub/tuner.textproto").exists() and (tmp_path / "gib-host/set_nccl_env.sh").exists()
+    assert "container_entry.sh install --install-nccl" in (tmp_path / "calls.log").read_text()
+
+
+def test_b200coll_install_and_env_profile(tmp_path):
+    src = tmp_path / "opt"; (src / "lib").mkdir(parents=True); (src / "bin").mkdir(); (src / "tuner").mkdir()
+    for f in ("lib/libb200coll.so", "lib/libb200coll_nccl.so", "b200coll-env-profile.sh", "tuner/b200_nvswitch.tbl"):
+        (src / f).write_text("x")
+    perf = src / "bin" / "b200coll_perf"; perf.write_text("#!/bin/bash\necho selfcheck-ran > %s/selfcheck\nexit 0\n" % tmp_path); perf.chmod(0o755)
+    env = {**os.environ, "B200COLL_SRC_DIR": str(src), "NCCL_INSTALL_DIR": str(tmp_path / "lib64"), "B200COLL_BIN_DIR": str(tmp_path / "bin")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "b200coll-install.sh")], env=env).returncode == 0
+    assert (tmp_path / "lib64/libb200coll.so").exists() and (tmp_path / "lib64/b200_nvswitch.tbl").exists() and (tmp_path / "selfcheck").exists()
+    out = subprocess.run(["bash", "-c", f"B200COLL_LIB_DIR={tmp_path}/lib64 source {SCRIPTS}/b200coll-env-profile.sh; echo $B200COLL_LIB $B200COLL_ALGO $B200COLL_TUNER_FILE"], capture_output=True, text=True).stdout.split()
+    assert out == [f"{tmp_path}/lib64/libb200coll.so", "auto", f"{tmp_path}/lib64/b200_nvswitch.tbl"]
+
+
+def test_tcpxo_host_prep_exposes_only_matching_pci_functions(tmp_path):
+    pci = tmp_path / "pci"
+    for bdf, ven, dev in (("0000:06:00.0", "0x1ae0", "0x0084"), ("0000:07:00.0", "0x1ae0", "0x0042"), ("0000:08:00.0", "0x10de", "0x2901")):
+        d = pci / bdf; d.mkdir(parents=True); (d / "vendor").write_text(ven + "\n"); (d / "device").write_text(dev + "\n"); (d / "resource0").write_text("")
+    env = {**os.environ, "SYS_PCI_DEVICES": str(pci), "APERTURE_DIR": str(tmp_path / "ap"), "IPTABLES": stub(tmp_path, "iptables"), "MODPROBE": stub(tmp_path, "modprobe"), "MOUNT": stub(tmp_path, "mount")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "tcpxo-host-prep.sh")], env=env).returncode == 0
+    log = (tmp_path / "calls.log").read_text()
+    assert "modprobe import-helper" in log and "iptables -I INPUT -p tcp -m tcp -j ACCEPT" in log
+    assert log.count("mount --bind") == 1 and "0000:06:00.0" in log and os.path.isdir(tmp_path / "ap/0000:06:00.0")
+
+
+def test_optmem_and_confidential_scripts(tmp_path):
+    (tmp_path / "net/core").mkdir(parents=True); (tmp_path / "net/core/optmem_max").write_text("20480\n")
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "optmem-max.sh")], env={**os.environ, "PROC_SYS": str(tmp_path)}).returncode == 0
+    assert (tmp_path / "net/core/optmem_max").read_text().strip() == "131072"
+    root = tmp_path / "root"; (root / "home/kubernetes/bin/nvidia").mkdir(parents=True)
+    nv = tmp_path / "nv"; (nv / "bin").mkdir(parents=True)
+    (nv / "bin/nvidia-modprobe").write_text("#!/bin/bash\nexit 0\n"); (nv / "bin/nvidia-modprobe").chmod(0o755)
+    env = {**os.environ, "ROOT_MOUNT_DIR": str(root), "NVIDIA_INSTALL_DIR_CONTAINER": str(nv), "COS_GPU_INSTALLER": stub(tmp_path, "installer"), "LSMOD": stub(tmp_path, "lsmod", "true"),
+           "INSMOD": stub(tmp_path, "insmod"), "CURL": stub(tmp_path, "curl", "echo 'a=b,cloud.google.com/gke-confidential-nodes-instance-type=TDX,c=d'")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "cos-confidential-install.sh")], env=env).returncode == 0
+    assert (root / "etc/nvidia/confidential_node_type.txt").read_text().strip() == "TDX"
+    log = (tmp_path / "calls.log").read_text()
+    assert "installer install --version=latest --no-verify" in log and log.count("insmod ") == 4
