@@ -176,3 +176,62 @@ def test_optmem_and_confidential_scripts(tmp_path):
     assert (root / "etc/nvidia/confidential_node_type.txt").read_text().strip() == "TDX"
     log = (tmp_path / "calls.log").read_text()
     assert "installer install --version=latest --no-verify" in log and log.count("insmod ") == 4
+
+
+# ------------------------------------------------------------------------------------------------- .run driver installers
+DRV = os.path.join(DEPLOY, "driver-installer")
+
+
+def run_installer(tmp_path, entry, extra_env=None, prime_cache=None):
+    inst = tmp_path / "nvidia"; (inst / "bin").mkdir(parents=True, exist_ok=True)
+    for tool in ("nvidia-smi", "nvidia-modprobe"):
+        p = inst / "bin" / tool; p.write_text(f"#!/bin/bash\necho \"{tool} $*\" >> {tmp_path}/calls.log\n"); p.chmod(0o755)
+    root = tmp_path / "root"; (root / "etc").mkdir(parents=True, exist_ok=True)
+    (tmp_path / "ldconf").mkdir(exist_ok=True)
+    if prime_cache:
+        (inst / ".cache").write_text(prime_cache)
+    env = {**os.environ, "NVIDIA_INSTALL_DIR_CONTAINER": str(inst), "NVIDIA_INSTALL_DIR_HOST": "/home/kubernetes/bin/nvidia", "ROOT_MOUNT_DIR": str(root), "KERNEL_VERSION": "6.8.0-1021-gke",
+           "NVIDIA_DRIVER_VERSION": "570.124.06", "LD_SO_CONF_D": str(tmp_path / "ldconf"), "OVERLAY_ROOT": str(tmp_path / "ovl"),
+           "MOUNT": stub(tmp_path, "mount"), "UMOUNT": stub(tmp_path, "umount"), "LDCONFIG": stub(tmp_path, "ldconfig"), "LSMOD": stub(tmp_path, "lsmod", "echo none"),
+           "INSMOD": stub(tmp_path, "insmod"), "CURL": stub(tmp_path, "curl"), "SH": stub(tmp_path, "sh"), "APT_GET": stub(tmp_path, "apt-get"),
+           "TAR": stub(tmp_path, "tar"), "MAKE": stub(tmp_path, "make"), "KERNEL_SRC_DIR": str(tmp_path / "ksrc"), **(extra_env or {})}
+    (tmp_path / "ksrc/include/generated").mkdir(parents=True, exist_ok=True)
+    r = subprocess.run(["bash", os.path.join(DRV, entry)], env=env, capture_output=True, text=True)
+    log = (tmp_path / "calls.log").read_text() if (tmp_path / "calls.log").exists() else ""
+    return r, log, inst, root
+
+
+def test_ubuntu_installer_fresh_install(tmp_path):
+    r, log, inst, root = run_installer(tmp_path, "ubuntu/entrypoint.sh")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "apt-get install -y linux-headers-6.8.0-1021-gke" in log
+    assert log.count("mount -t overlay") == 3 and "lowerdir=/lib/modules/6.8.0-1021-gke/video" in log
+    assert "NVIDIA-Linux-x86_64-570.124.06.run" in log and "--kernel-module-type=open" in log and "--no-drm --silent --accept-license" in log
+    assert (inst / ".cache").read_text() == "CACHE_KERNEL_VERSION=6.8.0-1021-gke\nCACHE_NVIDIA_DRIVER_VERSION=570.124.06\n"
+    assert "nvidia-modprobe -c0 -u" in log and log.count("umount") == 3
+    assert (root / "etc/ld.so.conf").read_text() == "/home/kubernetes/bin/nvidia/lib64\n"
+
+
+def test_ubuntu_installer_cache_hit_skips_download(tmp_path):
+    r, log, inst, root = run_installer(tmp_path, "ubuntu/entrypoint.sh", prime_cache="CACHE_KERNEL_VERSION=6.8.0-1021-gke\nCACHE_NVIDIA_DRIVER_VERSION=570.124.06\n")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "curl" not in log and "apt-get" not in log and "mount -t overlay" not in log
+    assert "insmod " + str(inst / "drivers/nvidia.ko") in log and "nvidia-uvm.ko" in log
+    r2, _, _, root = run_installer(tmp_path, "ubuntu/entrypoint.sh", prime_cache="CACHE_KERNEL_VERSION=6.8.0-1021-gke\nCACHE_NVIDIA_DRIVER_VERSION=570.124.06\n")
+    assert (root / "etc/ld.so.conf").read_text().count("nvidia/lib64") == 1          # idempotent
+
+
+def test_old_driver_keeps_proprietary_modules_and_failure_propagates(tmp_path):
+    r, log, _, _ = run_installer(tmp_path, "ubuntu/entrypoint.sh", extra_env={"NVIDIA_DRIVER_VERSION": "535.230.02"})
+    assert r.returncode == 0 and "--kernel-module-type" not in log
+    bad = stub(tmp_path, "sh-fail", "exit 3")
+    r, log, inst, _ = run_installer(tmp_path / "x" if False else tmp_path, "ubuntu/entrypoint.sh", extra_env={"SH": bad, "NVIDIA_DRIVER_VERSION": "580.1.1"})
+    assert r.returncode != 0
+
+
+def test_minikube_installer_builds_kernel_source(tmp_path):
+    r, log, inst, _ = run_installer(tmp_path, "minikube/entrypoint.sh", extra_env={"KERNEL_VERSION": "5.10.0-minikube"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "https://cdn.kernel.org/pub/linux/kernel/v5.x/linux-5.10.tar.xz" in log and "make modules_prepare" in log
+    assert f"--kernel-source-path={tmp_path}/ksrc" in log
+    assert (tmp_path / "ksrc/include/generated/utsrelease.h").read_text().strip() == '#define UTS_RELEASE "5.10.0-minikube"'
