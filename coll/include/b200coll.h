@@ -171,7 +171,7 @@ b200collAlgo_t b200collTunerPick(b200collOp_t op, size_t bytes, int nranks, int 
 /* Force an algorithm for subsequent calls on this comm (b200collAlgoAuto restores the table). */
 b200collResult_t b200collCommSetAlgo(b200collComm_t comm, b200collAlgo_t algo);
 b200collResult_t b200collCommSetMaxCtas(b200collComm_t comm, int max_ctas);
-/* Launch shape per kernel family: kind 0 = NVLS (multimem) kernels, 1 = P2P pull/push kernels, 2 = LL.
+/* Launch shape per kernel family: kind 0 = NVLS all-reduce/all-gather, 1 = P2P pull/push kernels, 2 = LL, 3 = NVLS reduce-scatter.
  * max_ctas <= 0 keeps the current cap; threads == 0 lets the library pick {128,256,512} by work size.
  * Defaults come from the 8xB200 sweep in profiles/ (NVLS wants few CTAs: 32 x 256 threads). */
 b200collResult_t b200collCommSetLaunchShape(b200collComm_t comm, int kind, int max_ctas, int threads);

@@ -54,7 +54,7 @@ struct Grid { int blocks, threads; };
 
 // Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs),
 // unless the family's shape pins the thread count.
-enum { kShapeNvls = 0, kShapeP2p = 1, kShapeLL = 2 };
+enum { kShapeNvls = 0, kShapeP2p = 1, kShapeLL = 2, kShapeNvlsRs = 3 };
 static Grid pick_grid(const b200collComm* c, int kind, size_t vecs, int unroll) {
   static const int forced = [] { const char* e = getenv("B200COLL_FORCE_THREADS"); return e ? atoi(e) : 0; }();
   const int max_ctas = std::max(1, std::min(c->shape[kind].max_ctas > 0 ? c->shape[kind].max_ctas : c->max_ctas, c->max_ctas));
@@ -295,7 +295,7 @@ b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recv
     account(c, b200collOpReduceScatter, n * is, algo);
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvls : kShapeP2p, n / Epv<InT>::value, 2);
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvlsRs : kShapeP2p, n / Epv<InT>::value, 2);
       if (algo == b200collAlgoNvls) k_pull_reduce<InT, OutT, false, true><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
       else k_pull_reduce<InT, OutT, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
       LAUNCH_CHECK(c);

@@ -214,6 +214,7 @@ static void finalize_comm(b200collComm* c) {
   c->shape[1].max_ctas = std::min<int>((int)env_long("B200COLL_P2P_CTAS", c->max_ctas), c->max_ctas);
   c->shape[1].threads = (int)env_long("B200COLL_P2P_THREADS", 0);
   c->shape[2].max_ctas = std::min(c->shape[2].max_ctas, c->max_ctas);
+  c->shape[3].max_ctas = std::min(c->shape[3].max_ctas, c->max_ctas);
   const char* fa = getenv("B200COLL_ALGO");
   if (fa && *fa) {
     for (int a = 0; a < b200collNumAlgos; a++) if (!strcasecmp(fa, b200collAlgoName((b200collAlgo_t)a))) c->forced_algo = (b200collAlgo_t)a;
@@ -605,7 +606,7 @@ b200collResult_t b200collCommSetMaxCtas(b200collComm_t c, int m) {
 }
 
 b200collResult_t b200collCommSetLaunchShape(b200collComm_t c, int kind, int max_ctas, int threads) {
-  if (!c || kind < 0 || kind > 2) return b200collInvalidArgument;
+  if (!c || kind < 0 || kind > 3) return b200collInvalidArgument;
   if (threads != 0 && (threads < 32 || threads > 512 || threads % 32)) return b200collInvalidArgument;
   if (max_ctas > 0) c->shape[kind].max_ctas = std::min(max_ctas, kMaxBlocks);
   c->shape[kind].threads = threads;

@@ -72,7 +72,10 @@ struct b200collComm {
   std::mutex mu;
   b200collAlgo_t forced_algo = b200collAlgoAuto;
   int max_ctas = 0;
-  struct Shape { int max_ctas; int threads; } shape[3] = {{32, 256}, {0, 0}, {148, 0}};   // NVLS, P2P, LL
+  // NVLS all-reduce/all-gather, P2P, LL, NVLS reduce-scatter. Measured on 8xB200 (profiles/launch_shapes_n8.md): the
+  // multimem all-reduce saturates with 16-64 CTAs x 256 threads and degrades above ~100 CTAs; the ld_reduce-only
+  // reduce-scatter kernel (2 loads in flight per thread) needs 64 x 512.
+  struct Shape { int max_ctas; int threads; } shape[4] = {{32, 256}, {0, 0}, {148, 0}, {64, 512}};
   b200collStats stats{};
   std::shared_ptr<b200coll::SharedGroup> group;
   void* stats_shm = nullptr;       // exported stats page (metrics exporter reads it)

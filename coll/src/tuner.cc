@@ -29,7 +29,7 @@ static const Row kBuiltin[] = {
   {b200collOpAllReduce,     2, 2, -1,  1ull << 20,   b200collAlgoLL2},
   {b200collOpAllReduce,     2, 2, -1,  INF,          b200collAlgoTwoShot},   // N=2: NVLS would bounce my own half through the switch
   {b200collOpAllReduce,     3, 8, -1,  256ull << 10, b200collAlgoLL},     // 8xB200: LL 12.7 us vs NVLS 15.2 us at 256 KiB; NVLS wins from 512 KiB
-  {b200collOpAllReduce,     3, 8, -1,  2ull << 20,   b200collAlgoLL2},    // two-shot Lamport: 2S received, no barrier (cap: nranks x 512 KiB)
+  {b200collOpAllReduce,     3, 8,  0,  2ull << 20,   b200collAlgoLL2},    // no multicast: two-shot Lamport (2S received, no barrier) before the P2P two-shot
   {b200collOpAllReduce,     3, 8,  1,  INF,          b200collAlgoNvls},
   {b200collOpAllReduce,     3, 8,  0,  INF,          b200collAlgoTwoShot},
   // ---- all-gather (bytes = per-rank contribution)

@@ -298,7 +298,7 @@ class Comm:
         _check(load().b200collCommSetMaxCtas(self._h, n), "CommSetMaxCtas")
 
     def set_launch_shape(self, kind: str, max_ctas: int = 0, threads: int = 0) -> None:
-        _check(load().b200collCommSetLaunchShape(self._h, {"nvls": 0, "p2p": 1, "ll": 2}[kind], max_ctas, threads), "CommSetLaunchShape")
+        _check(load().b200collCommSetLaunchShape(self._h, {"nvls": 0, "p2p": 1, "ll": 2, "nvls_rs": 3}[kind], max_ctas, threads), "CommSetLaunchShape")
 
     def stats(self) -> dict:
         s = Stats()

@@ -22,7 +22,7 @@ def test_version_and_names(lib):
 
 @pytest.mark.parametrize("op,nbytes,n,nvls,want", [
     (coll.OP_ALLREDUCE, 1024, 1, True, "copy"),
-    (coll.OP_ALLREDUCE, 1024, 8, True, "ll"), (coll.OP_ALLREDUCE, 256 << 10, 8, True, "ll"), (coll.OP_ALLREDUCE, 512 << 10, 8, True, "ll2"), (coll.OP_ALLREDUCE, 4 << 20, 8, True, "nvls"),
+    (coll.OP_ALLREDUCE, 1024, 8, True, "ll"), (coll.OP_ALLREDUCE, 256 << 10, 8, True, "ll"), (coll.OP_ALLREDUCE, 512 << 10, 8, True, "nvls"), (coll.OP_ALLREDUCE, 512 << 10, 8, False, "ll2"), (coll.OP_ALLREDUCE, 4 << 20, 8, True, "nvls"),
     (coll.OP_ALLREDUCE, 1 << 30, 8, True, "nvls"), (coll.OP_ALLREDUCE, 1 << 30, 8, False, "twoshot"),
     (coll.OP_ALLREDUCE, 1 << 30, 2, True, "twoshot"),            # N=2: NVLS would bounce my own half through the switch
     (coll.OP_ALLGATHER, 4096, 4, True, "ll"), (coll.OP_ALLGATHER, 64 << 20, 8, True, "twoshot"),
