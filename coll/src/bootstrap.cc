@@ -1,3 +1,4 @@
+// Star-topology rendezvous over an abstract Unix socket: blob allgather, barrier, SCM_RIGHTS fd exchange (see bootstrap.h).
 #include "bootstrap.h"
 
 #include <errno.h>

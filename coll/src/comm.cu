@@ -302,7 +302,7 @@ b200collResult_t b200collUniqueIdFromString(const char* s, b200collUniqueId* id)
 }
 
 b200collResult_t b200collCommInitRank(b200collComm_t* out, int nranks, const b200collUniqueId* id, int rank, const b200collConfig* cfg_in) {
-  if (!out || !id || nranks < 1 || nranks > B200COLL_MAX_RANKS || rank < 0 || rank >= nranks) { set_last_error("CommInitRank: bad arguments"); return b200collInvalidArgument; }
+  if (!out || !id || nranks < 1 || nranks > B200COLL_MAX_RANKS || rank < 0 || rank >= nranks) { set_last_error("bad arguments to CommInitRank"); return b200collInvalidArgument; }
   *out = nullptr;
   const Drv& d = drv();
   if (!d.ok) { set_last_error("driver unavailable:" + d.why); return b200collNoDriver; }
@@ -428,7 +428,7 @@ b200collResult_t b200collCommInitRank(b200collComm_t* out, int nranks, const b20
 }
 
 b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* devs, const b200collConfig* cfg_in) {
-  if (!comms || n < 1 || n > B200COLL_MAX_RANKS) { set_last_error("CommInitAll: bad arguments"); return b200collInvalidArgument; }
+  if (!comms || n < 1 || n > B200COLL_MAX_RANKS) { set_last_error("bad arguments to CommInitAll"); return b200collInvalidArgument; }
   const Drv& d = drv();
   if (!d.ok) { set_last_error("driver unavailable:" + d.why); return b200collNoDriver; }
   int prev_dev = 0;
@@ -576,7 +576,7 @@ b200collResult_t b200collMemFree(b200collComm_t c, void* ptr) {
   std::lock_guard<std::mutex> lk(c->mu);
   const size_t off = reinterpret_cast<CUdeviceptr>(ptr) - c->peer_va[c->rank];
   auto it = c->live.find(off);
-  if (it == c->live.end()) { set_last_error("MemFree: pointer was not returned by MemAlloc"); return b200collInvalidArgument; }
+  if (it == c->live.end()) { set_last_error("pointer passed to MemFree was not returned by MemAlloc"); return b200collInvalidArgument; }
   FreeBlock nb{off, it->second};
   c->live.erase(it);
   auto pos = std::lower_bound(c->free_list.begin(), c->free_list.end(), nb, [](const FreeBlock& a, const FreeBlock& b) { return a.off < b.off; });

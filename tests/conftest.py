@@ -1,3 +1,4 @@
+"""pytest configuration: registers the `gpu` marker and builds native artefacts once per session."""
 import os
 import subprocess
 import sys
