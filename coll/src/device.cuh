@@ -52,12 +52,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-static __device__ __noinline__ void record_fault(const CommDev& c, uint32_t code, uint32_t peer, uint32_t expected, uint32_t observed, uint32_t op) {
-  b200collFault* f = c.fault;
+// Takes scalars, not the CommDev: passing the kernel-parameter struct by reference to a noinline function forces a
+// 104-byte stack copy of it in every kernel and turns each peer[] lookup into a local-memory load.
+static __device__ __noinline__ void record_fault_impl(b200collFault* f, uint32_t rank, uint32_t code, uint32_t peer, uint32_t expected, uint32_t observed, uint32_t op) {
   if (atomicCAS(&f->code, 0u, code) == 0u) {
-    f->rank = c.rank; f->peer = peer; f->block = blockIdx.x; f->expected = expected; f->observed = observed; f->op = op;
+    f->rank = rank; f->peer = peer; f->block = blockIdx.x; f->expected = expected; f->observed = observed; f->op = op;
     __threadfence_system();
   }
+}
+__device__ __forceinline__ void record_fault(const CommDev& c, uint32_t code, uint32_t peer, uint32_t expected, uint32_t observed, uint32_t op) {
+  record_fault_impl(c.fault, (uint32_t)c.rank, code, peer, expected, observed, op);
 }
 
 // ---------------------------------------------------------------- flags

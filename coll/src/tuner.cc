@@ -25,7 +25,7 @@ static const unsigned long long INF = ~0ull;
 // clang-format off
 static const Row kBuiltin[] = {
   // ---- all-reduce
-  {b200collOpAllReduce,     2, 2, -1,  256ull << 10, b200collAlgoLL},
+  {b200collOpAllReduce,     2, 2, -1,  512ull << 10, b200collAlgoLL},     // 2xB200: LL 10.3 us vs two-shot LL 11.8 us at 512 KiB
   {b200collOpAllReduce,     2, 2, -1,  1ull << 20,   b200collAlgoLL2},
   {b200collOpAllReduce,     2, 2, -1,  INF,          b200collAlgoTwoShot},   // N=2: NVLS would bounce my own half through the switch
   {b200collOpAllReduce,     3, 8, -1,  256ull << 10, b200collAlgoLL},     // 8xB200: LL 12.7 us vs NVLS 15.2 us at 256 KiB; NVLS wins from 512 KiB
