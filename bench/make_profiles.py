@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Turn the raw outputs of the gpurun calls (gpurun_out/) into the tracked summaries under profiles/.
+Roofline: bytes that must cross NVLink per GPU and direction / link bandwidth, with the MEASURED 770 GB/s per direction
+(B200_PROFILING.md; 900 nominal): NVLS all-reduce busbw <= 2(N-1)/N * 770/(1+1/N); two-shot / all-gather / reduce-scatter /
+all-to-all busbw <= 770."""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+LINK = 770.0
+
+
+def load_json(name):
+    path = os.path.join(G, name)
+    if not os.path.exists(path):
+        return None
+    lines = [l for l in open(path) if l.startswith("{")]
+    return json.loads(lines[0]) if lines else None
+
+
+def ar_bound(n, algo):
+    if n <= 1:
+        return None
+    if algo == "nvls":
+        return 2 * (n - 1) / n * LINK / (1 + 1 / n)
+    return LINK
+
+
+def allreduce_md():
+    out = ["# all_reduce_perf sweep — libb200coll vs stock NCCL on the same box (bf16 sum, nccl-tests protocol)\n",
+           "Device-timed (CUDA events), max over ranks, 20 timed iterations after 5 warm-ups per size, buffers rotating through a 192 MiB window (> L2).",
+           "`ref profile` = NCCL 2.28.9 under the reference's env profile (NCCL_PROTO=Simple,LL128, NCCL_NVLS_ENABLE=1, ...; gpudirect-tcpxo/README.md:71-103); `defaults` = same library, no env.",
+           f"Roofline uses the measured {LINK:.0f} GB/s per direction per GPU (900 nominal): NVLS busbw <= 2(N-1)/N x {LINK:.0f}/(1+1/N); P2P two-shot busbw <= {LINK:.0f}.\n"]
+    for n, prefix in ((8, "t8"), (4, "s4"), (2, "s2")):
+        ours = load_json(f"{prefix}_bench.json")
+        ref = load_json(f"{prefix}_ref.json") or (load_json("n8_ref_all_reduce.json") if n == 8 else None)
+        refd = load_json(f"{prefix}_ref_defaults.json")
+        if not ours:
+            continue
+        out.append(f"## {n} x B200\n")
+        hdr = f"avg busbw: **ours {ours['value']:.1f} GB/s**"
+        if ref:
+            hdr += f", NCCL ref profile {ref['value']:.1f}"
+        if refd:
+            hdr += f", NCCL defaults {refd['value']:.1f}"
+        hdr += f" · peak: ours {ours['peak_busbw']:.1f}" + (f", NCCL {max((ref or {}).get('peak_busbw', 0), (refd or {}).get('peak_busbw', 0)):.1f}" if (ref or refd) else "")
+        c = ours.get("clocks") or {}
+        hdr += f" · clocks during the sweep: SM {c.get('sm_mhz')} / {c.get('sm_max_mhz')} MHz, reasons {c.get('reasons')}, {ours.get('gpu_launches')} libb200coll launches timed"
+        out.append(hdr + "\n")
+        out.append("| bytes | algo | ours oop us | ours busbw oop / ip | NCCL ref-profile us / busbw | NCCL defaults us / busbw | ours / best NCCL | of roofline |")
+        out.append("|---:|---|---:|---:|---:|---:|---:|---:|")
+        rt = {r["bytes"]: r for r in (ref or {}).get("table", [])}
+        dt = {r["bytes"]: r for r in (refd or {}).get("table", [])}
+        for r in ours["table"]:
+            a, b = rt.get(r["bytes"]), dt.get(r["bytes"])
+            best = max([x["oop_busbw"] for x in (a, b) if x] or [0])
+            bound = ar_bound(n, r["algo"])
+            frac = f"{r['oop_busbw'] / bound:.2f}" if bound and r["bytes"] >= (1 << 24) else ""
+            out.append(f"| {r['bytes']} | {r['algo']} | {r['oop_us']:.2f} | {r['oop_busbw']:.2f} / {r['ip_busbw']:.2f} | " + (f"{a['oop_us']:.2f} / {a['oop_busbw']:.2f}" if a else "–") + " | " +
+                       (f"{b['oop_us']:.2f} / {b['oop_busbw']:.2f}" if b else "–") + f" | {r['oop_busbw'] / best:.2f}x | {frac} |" if best else f"| {r['bytes']} | {r['algo']} | {r['oop_us']:.2f} | {r['oop_busbw']:.2f} / {r['ip_busbw']:.2f} | – | – | – | {frac} |")
+        if ours.get("e2e"):
+            out.append(f"\nEnd to end through the public API (pinned host -> device copy of the input + 4 KiB read-back inside the timed region): avg busbw {ours['e2e']['value']:.2f} GB/s "
+                       f"({ours['e2e']['h2d_bytes_per_step']} B H2D per sweep — PCIe-bound by construction).\n")
+    n1 = load_json("bench_n1.json")
+    if n1:
+        out.append(f"## 1 x B200\n\nOne rank: nccl-tests' bus factor is 0; the value is the algbw of the fused scale/cast copy kernel: avg {n1['value']:.1f} GB/s, peak {n1['peak_busbw']:.1f} GB/s "
+                   "(read + write traffic is 2x that; measured HBM copy peak on this pool: 6585 GB/s).\n")
+    open(os.path.join(P, "allreduce_sweep.md"), "w").write("\n".join(out) + "\n")
+
+
+def shapes_md():
+    out = ["# Launch-shape sweep on 8 x B200 (bench/run_tune8.sh) — why the defaults are what they are\n",
+           "`[kK cC tT]` = kernel family K (0 NVLS, 1 P2P), max CTAs C, threads per CTA T. Out-of-place, 10 timed iterations; columns: bytes, time (us), bus GB/s.\n"]
+    for title, f in (("all_reduce / multimem (k_ar_nvls)", "t8_ar_nvls_shape.txt"), ("all_reduce / P2P two-shot (k_ar_twoshot)", "t8_ar_p2p_shape.txt"), ("all_gather / P2P push", "t8_all_gather_p2p_shape.txt"),
+                     ("all_gather / multimem.st", "t8_all_gather_nvls_shape.txt"), ("reduce_scatter / P2P pull", "t8_reduce_scatter_p2p_shape.txt"),
+                     ("reduce_scatter / multimem.ld_reduce", "t8_reduce_scatter_nvls_shape.txt"), ("alltoall / P2P push", "t8_a2a_p2p_shape.txt")):
+        path = os.path.join(G, f)
+        if not os.path.exists(path):
+            continue
+        rows = {}
+        for line in open(path):
+            m = re.match(r"\[k(\d) c(\d+) t(\d+)\]\s+(\d+)\s+\d+\s+\S+\s+\S+\s+\|\s+([\d.]+)\s+[\d.]+\s+([\d.]+)", line)
+            if m:
+                rows.setdefault(int(m.group(4)), []).append((int(m.group(2)), int(m.group(3)), float(m.group(5)), float(m.group(6))))
+        if not rows:
+            continue
+        sizes = sorted(rows)[-3:]
+        out.append(f"## {title}\n")
+        out.append("| CTAs x threads | " + " | ".join(f"{s >> 20} MiB: us / GB/s" for s in sizes) + " |")
+        out.append("|---|" + "---:|" * len(sizes))
+        shapes = [(c, t) for c, t, _, _ in rows[sizes[0]]]
+        for i, (c, t) in enumerate(shapes):
+            out.append(f"| {c} x {t} | " + " | ".join(f"{rows[s][i][2]:.1f} / {rows[s][i][3]:.1f}" for s in sizes) + " |")
+        out.append("")
+    out.append("Take-aways: the multimem all-reduce is flat from 16 to 64 CTAs and needs only 8 warps each (846 GB/s at 1 GiB); the first 8-GPU run used 296 CTAs x 512 and got 520 GB/s "
+               "out-of-place at 1 GiB (gpurun_out/n8_nvls_shape.txt) — more CTAs spread the switch's reduction over more concurrent address streams and lose 35 %. "
+               "The ld_reduce-only reduce-scatter keeps 2 vectors in flight per thread and therefore needs 64 x 512. P2P push/pull kernels want the whole chip (2 CTAs per SM).\n")
+    open(os.path.join(P, "launch_shapes_n8.md"), "w").write("\n".join(out) + "\n")
+
+
+def other_ops_md():
+    out = ["# all_gather / reduce_scatter / alltoall on 8 x B200 — libb200coll vs stock NCCL (reference env profile)\n",
+           "bf16, out-of-place; `size` is nccl-tests' size (total buffer). NCCL through its C API, same harness. Bus-bandwidth factor (N-1)/N.\n"]
+    for op, ours_files, ref in (("all_gather", ("n8_all_gather_ll.txt", "n8_all_gather_p2p.txt"), "n8_ref_all_gather.json"), ("reduce_scatter", ("n8_reduce_scatter_ll.txt", "n8_reduce_scatter_nvls.txt"), "n8_ref_reduce_scatter.json"),
+                                ("alltoall", ("n8_a2a_ll.txt", "n8_a2a_p2p.txt"), "n8_ref_alltoall.json")):
+        mine = {}
+        for f in ours_files:
+            path = os.path.join(G, f)
+            if not os.path.exists(path):
+                continue
+            for line in open(path):
+                m = re.match(r"\s*(\d+)\s+\d+\s+\S+\s+(\S+)\s+\|\s+([\d.]+)\s+[\d.]+\s+([\d.]+)", line)
+                if m:
+                    size, algo, us, bw = int(m.group(1)), m.group(2), float(m.group(3)), float(m.group(4))
+                    if size not in mine or us < mine[size][1]:
+                        mine[size] = (algo, us, bw)
+        r = load_json(ref)
+        if not mine or not r:
+            continue
+        rt = {x["bytes"]: x for x in r["table"]}
+        out.append(f"## {op}\n\n| size | ours algo | ours us | ours busbw | NCCL us | NCCL busbw | ratio | of 770 |\n|---:|---|---:|---:|---:|---:|---:|---:|")
+        for size in sorted(mine):
+            algo, us, bw = mine[size]
+            b = rt.get(size)
+            if not b:
+                continue
+            algo = {"twoshot": "p2p"}.get(algo, algo)
+            out.append(f"| {size} | {algo} | {us:.2f} | {bw:.2f} | {b['oop_us']:.2f} | {b['oop_busbw']:.2f} | {bw / max(b['oop_busbw'], 1e-9):.2f}x | {bw / LINK:.2f} |" if size >= (1 << 24) else
+                       f"| {size} | {algo} | {us:.2f} | {bw:.2f} | {b['oop_us']:.2f} | {b['oop_busbw']:.2f} | {bw / max(b['oop_busbw'], 1e-9):.2f}x | |")
+        out.append("")
+    open(os.path.join(P, "other_ops_n8.md"), "w").write("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    os.makedirs(P, exist_ok=True)
+    allreduce_md(); shapes_md(); other_ops_md()
+    print("profiles:", sorted(os.listdir(P)))

@@ -167,8 +167,17 @@ static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const
       Grid g = pick_grid(c, kShapeP2p, nvec / c->nranks + 1, 2);
       k_ar_twoshot<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, b200collOpAllReduce);
     } else {
-      Grid g = pick_grid(c, kShapeNvls, nvec / c->nranks + 1, 4);
-      k_ar_nvls<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
+      static const int forced_u = [] { const char* e = getenv("B200COLL_NVLS_UNROLL"); return e ? atoi(e) : 0; }();
+      const size_t slice = nvec / c->nranks + 1;
+      Grid g = pick_grid(c, kShapeNvls, slice, 4);
+      const bool few_passes = slice < (size_t)g.blocks * g.threads * 16;      // fewer than 4 passes at U=4
+      const int u = forced_u ? forced_u : (few_passes ? 1 : 4);
+      if (u == 1) {
+        g = pick_grid(c, kShapeNvls, slice, 1);
+        k_ar_nvls<InT, OutT, 1><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
+      } else {
+        k_ar_nvls<InT, OutT, 4><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
+      }
     }
     LAUNCH_CHECK(c);
     return b200collSuccess;

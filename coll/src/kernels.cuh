@@ -390,11 +390,12 @@ __global__ void __launch_bounds__(kThreads) k_ar_twoshot(CommDev c, size_t in_of
 
 // NVLS all-reduce: the switch does the reduction (fp32 accumulate) and the broadcast.
 // Per GPU and direction: ~S(1+1/N) bytes -> algbw bound = link/(1+1/N).
-template <typename InT, typename OutT>
+// U = vectors in flight per thread. Large messages use U=4; mid sizes use U=1 so that a slice takes several passes and
+// the multimem.st of pass k (ingress-heavy) overlaps the ld_reduce of pass k+1 (egress-heavy) instead of running back to back.
+template <typename InT, typename OutT, int U>
 __global__ void __launch_bounds__(kThreads) k_ar_nvls(CommDev c, size_t in_off, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
-  constexpr int U = 4;
   const uint32_t s = load_seq(c, kSeqBarrier);
   barrier_blocks<false>(c, 2 * s + 1, op);
   const size_t nvec = count / E;
