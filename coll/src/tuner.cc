@@ -24,12 +24,14 @@ static const unsigned long long INF = ~0ull;
 
 // clang-format off
 static const Row kBuiltin[] = {
-  // ---- all-reduce
-  {b200collOpAllReduce,     2, 2, -1,  512ull << 10, b200collAlgoLL},     // 2xB200: LL 10.3 us vs two-shot LL 11.8 us at 512 KiB
-  {b200collOpAllReduce,     2, 2, -1,  1ull << 20,   b200collAlgoLL2},
-  {b200collOpAllReduce,     2, 2, -1,  INF,          b200collAlgoTwoShot},   // N=2: NVLS would bounce my own half through the switch
-  {b200collOpAllReduce,     3, 8, -1,  256ull << 10, b200collAlgoLL},     // 8xB200: LL 12.7 us vs NVLS 15.2 us at 256 KiB; NVLS wins from 512 KiB
-  {b200collOpAllReduce,     3, 8,  0,  2ull << 20,   b200collAlgoLL2},    // no multicast: two-shot Lamport (2S received, no barrier) before the P2P two-shot
+  // ---- all-reduce (crossovers measured at 2, 4 and 8 x B200: profiles/allreduce_sweep.md, gpurun_out/s{2,4}_ar_*.txt)
+  {b200collOpAllReduce,     2, 2, -1,  512ull << 10, b200collAlgoLL},      // 2 GPUs: LL 10.3 us vs two-shot LL 11.8 us at 512 KiB
+  {b200collOpAllReduce,     2, 2, -1,  1ull << 20,   b200collAlgoLL2},     //          two-shot LL 13.0 us vs barrier two-shot 16.1 us at 1 MiB
+  {b200collOpAllReduce,     2, 2, -1,  INF,          b200collAlgoTwoShot}, //          NVLS would bounce my own half through the switch
+  {b200collOpAllReduce,     3, 4, -1,  512ull << 10, b200collAlgoLL},      // 4 GPUs: LL 12.3 us at 512 KiB
+  {b200collOpAllReduce,     3, 4, -1,  2ull << 20,   b200collAlgoLL2},     //          two-shot LL 14.9 / 17.3 us vs NVLS 18.6 / 19.6 us at 1 / 2 MiB
+  {b200collOpAllReduce,     5, 8, -1,  256ull << 10, b200collAlgoLL},      // 8 GPUs: LL 13.1 us vs NVLS 15.8 us at 256 KiB; NVLS 16.0 us vs LL 17.2 us at 512 KiB
+  {b200collOpAllReduce,     5, 8,  0,  2ull << 20,   b200collAlgoLL2},     //          without multicast: two-shot LL before the barrier two-shot
   {b200collOpAllReduce,     3, 8,  1,  INF,          b200collAlgoNvls},
   {b200collOpAllReduce,     3, 8,  0,  INF,          b200collAlgoTwoShot},
   // ---- all-gather (bytes = per-rank contribution)
