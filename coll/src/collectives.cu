@@ -4,6 +4,8 @@
 
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "comm.h"
 #include "kernels.cuh"
 
@@ -86,8 +88,18 @@ static b200collResult_t check_common(b200collComm* c, const void* send, void* re
   return b200collSuccess;
 }
 
+// B200COLL_NVTX=1: one NVTX mark per collective ("b200coll all_reduce nvls 67108864 B") so timelines show which algorithm
+// a call took (the reference only passes NCCL_DEBUG through to opaque payloads).
 static void account(b200collComm* c, b200collOp_t op, size_t bytes, b200collAlgo_t algo) {
   c->stats.calls[op]++; c->stats.bytes[op] += bytes; c->stats.algo_calls[algo]++;
+  static const bool nvtx = [] { const char* e = getenv("B200COLL_NVTX"); return e && *e && *e != '0'; }();
+  if (nvtx || debug_level() >= 2) {
+    static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall"};
+    char msg[96];
+    snprintf(msg, sizeof(msg), "b200coll %s %s %zu B", kOps[op], b200collAlgoName(algo), bytes);
+    if (nvtx) nvtxMarkA(msg);
+    dbg(2, "rank %d: %s", c->rank, msg);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ nranks == 1

@@ -190,3 +190,16 @@ def test_labeler_from_metadata_and_nvml(api, tmp_path):
     pci = testing.make_fake_pci(str(tmp_path), "0000:1b:00.0", 1)
     labs = labeler.labels_from_nvml(nvml.MockNvml(dev, bus_id="00000000:1B:00.0"), pci)
     assert labs["b200.gke.io/gpu-count"] == "8" and labs["b200.gke.io/gpu-model"] == "NVIDIA-B200" and labs["b200.gke.io/numa-nodes"] == "1" and len(labs["b200.gke.io/nvlink-domain"]) == 12
+
+
+def test_expert_dispatch_plan_is_consistent():
+    from container_engine_accelerators_b200.models.workloads import expert_dispatch_plan, uniform_plan
+    p = expert_dispatch_plan(8, 4096, 1024, top_k=2, skew=1.0, seed=3)
+    assert p.rows.shape == (8, 8) and (p.rows.sum(axis=1) == 4096 * 2).all()            # every token goes to top_k experts
+    for s in range(8):
+        assert list(p.send_off[s]) == [int(p.rows[s, :d].sum()) for d in range(8)]
+    for d in range(8):
+        assert list(p.recv_off[d]) == [int(p.rows[:s, d].sum()) for s in range(8)]
+    assert p.max_rows >= p.rows.sum(axis=0).max() and p.rows.sum(axis=0).max() > p.rows.sum(axis=0).mean()      # skewed
+    u = uniform_plan(4, 10, 64)
+    assert (u.rows == 10).all() and list(u.recv_off[2]) == [0, 10, 20, 30] and u.max_rows == 40
