@@ -107,7 +107,9 @@ static b200collResult_t copy_scale(b200collComm* c, const void* send, void* recv
   if (send == recv && ep->in_dtype == ep->out_dtype && scale == 1.0f) return b200collSuccess;
   return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-    Grid g = pick_grid(c, kShapeP2p, count / Epv<InT>::value + 1, 4);
+    // streaming copy: no peers to wait for, so oversubscribe the chip (8 CTAs of 256 threads per SM) instead of the collective cap
+    const size_t vecs = count / Epv<InT>::value + 1;
+    Grid g{(int)std::max<size_t>(1, std::min<size_t>((vecs + 1023) / 1024, (size_t)std::max(1, c->sm_count) * 8)), 256};
     k_copy_scale<InT, OutT><<<g.blocks, g.threads, 0, st>>>(static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale);
     LAUNCH_CHECK(c);
     return b200collSuccess;

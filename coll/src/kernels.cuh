@@ -31,11 +31,18 @@ __device__ __forceinline__ void finish_store_local(OutT* dst, const float* acc, 
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(kThreads) k_copy_scale(const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale) {
   constexpr int E = Epv<InT>::value;
+  constexpr int U = 4;                       // 4 x 16 B loads in flight per thread: HBM-latency hiding for a pure streaming kernel
   const size_t nvec = count / E;
-  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
-    float acc[E] = {};
-    unpack_add<InT>(acc, ld_vec(in + v * E));
-    finish_store_local<InT, OutT, E>(out + v * E, acc, scale);
+  const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
+    uint4 d[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { const size_t v = base + (size_t)u * blockDim.x; if (v < nvec) d[u] = ld_vec(in + v * E); }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t v = base + (size_t)u * blockDim.x;
+      if (v < nvec) { float acc[E] = {}; unpack_add<InT>(acc, d[u]); finish_store_local<InT, OutT, E>(out + v * E, acc, scale); }
+    }
   }
   if (blockIdx.x == 0) {
     const size_t e = nvec * E + threadIdx.x;
