@@ -40,6 +40,8 @@ def main() -> int:
     ap.add_argument("--max", default="1G")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--table", action="store_true", help="also print the nccl-tests style table to stderr")
+    ap.add_argument("--extra-ops", default="", help="comma list of further collectives to sweep in the same process group; results go to --extra-out, never to stdout")
+    ap.add_argument("--extra-out", default="gpurun_out/extra_ops.json")
     args = ap.parse_args()
     warmup = max(3, args.warmup)
 
@@ -116,6 +118,19 @@ def main() -> int:
                                      "(net plugins are off the intra-node path), so this arm is the image's stock libnccl called through its C API with the "
                                      "reference's NCCL env profile (gpudirect-tcpxo/README.md:71-103); pip install of /root/reference: see DESIGN.md")
         print(json.dumps(out), flush=True)
+    if args.extra_ops:
+        extra = {}
+        for op in [o for o in args.extra_ops.split(",") if o and o != args.op]:
+            ok = harness.verify(backend, dist, op, dtype) if n > 1 else True
+            rws = harness.sweep(backend, dist, op, dtype, args.steps, warmup, min_b, max_b, placements=(0, 1))
+            sm = harness.summarize(rws, op, n)
+            extra[op] = {"avg_busbw": round(sm["avg_busbw"], 3), "peak_busbw": round(sm["peak_busbw"], 2), "verified": bool(ok), "table": harness.rows_json(rws, op, n)}
+            if dist.rank == 0 and args.table:
+                print(harness.format_table(rws, op, n, f"{backend.version} {op} nranks={n}"), file=sys.stderr)
+        if dist.rank == 0:
+            os.makedirs(os.path.dirname(args.extra_out) or ".", exist_ok=True)
+            with open(args.extra_out, "w") as f:
+                json.dump({"impl": args.impl, "n_gpus": n, "backend": backend.version, "ops": extra}, f)
     backend.close()
     dist.close()
     return 0 if verified else 3
