@@ -1,0 +1,1 @@
+"""Node agent: device plugin, MIG, sharing, health, metrics, NRI injector and their test doubles."""

@@ -242,6 +242,9 @@ class GPUHealthChecker:
 
     def stop(self) -> None:
         self._stop.set()
+        for t in self._threads:            # the listener may be inside events_wait(): let it return before freeing the set
+            if t is not threading.current_thread():
+                t.join(timeout=self.wait_ms / 1000.0 + 1.0)
         if self._event_set is not None:
             try:
                 self.nvml.events_close(self._event_set)

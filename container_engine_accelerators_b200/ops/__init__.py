@@ -1,0 +1,1 @@
+"""Bindings for the native collective library (coll/lib/libb200coll.so)."""

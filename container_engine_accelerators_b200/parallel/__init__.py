@@ -1,0 +1,1 @@
+"""One-rank-per-GPU launch plumbing: nccl-tests-protocol harness and the stock-NCCL reference arm."""

@@ -1,0 +1,1 @@
+"""Topology-aware gang scheduler and node labeler."""

@@ -1,0 +1,1 @@
+"""Small helpers (clock/throttle sampling for benchmark hygiene)."""
