@@ -10,4 +10,6 @@ timeout 240 $TR --master-port 29721 bench.py --gpus $NG --steps 20 --warmup 5 --
 timeout 240 $TR --master-port 29722 bench.py --gpus $NG --steps 20 --warmup 5 --table --no-e2e --impl reference --extra-ops $OPS --extra-out ${O}_extra_ref.json > ${O}_ref.json 2> ${O}_ref.err
 B200_REF_PROFILE=0 timeout 200 $TR --master-port 29723 bench.py --gpus $NG --steps 20 --warmup 5 --table --no-e2e --impl reference > ${O}_ref_defaults.json 2> ${O}_ref_defaults.err
 timeout 200 $TR --master-port 29724 bench/alltoallv_perf.py > ${O}_alltoallv.jsonl 2> ${O}_alltoallv.err
+ALL=$(python3 -c "print(','.join(str(i) for i in range($NG)))")
+timeout 90 ./build/b200coll_perf --devs $ALL --procs --op all_reduce -b 1K -e 256M -f 2 --iters 10 --warmup 3 --json ${O}_perf.jsonl > ${O}_perf_ar.txt 2>&1; tail -1 ${O}_perf_ar.txt
 grep -h "Avg bus" ${O}_*.err; cat ${O}_alltoallv.jsonl | cut -c1-400
