@@ -1,0 +1,633 @@
+// b200-device-plugin — native kubelet device plugin (static C++ binary, no Python, no gRPC library).
+//
+// Same contract as container_engine_accelerators_b200/agent (reference: cmd/nvidia_gpu/nvidia_gpu.go:78-186,
+// pkg/gpu/nvidia/{manager,beta_plugin,mig/mig,gpusharing/gpusharing,metrics/*}.go):
+//   boot: flags + gpu_config.json -> wait for nvidiactl/nvidia-uvm -> NVML -> discovery (+MIG, +MPS probe) -> serve
+//   serve: DevicePlugin v1beta1 on <plugin-dir>/nvidiaGPU-<ts>.sock, Register with kubelet.sock, restart on socket removal /
+//          kubelet restart / hot-added GPU
+//   Allocate: requested specs + default devices + mounts + MPS envs (+ b200coll transport profile)
+//   health: NVML Xid events -> Unhealthy via ListAndWatch (48 always critical + XID_CONFIG)
+//   metrics: :2112/metrics, per-container (kubelet PodResources) and per-node duty cycle / memory gauges
+// Kubernetes-API side effects (Events, Node condition, driver-version annotations) need TLS and stay in the Python
+// agent (`python -m container_engine_accelerators_b200.agent.main`), which shares every rule implemented here.
+// The same conformance suite drives both (tests/test_native_device_plugin.py).
+#include <dirent.h>
+#include <netinet/in.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <time.h>
+
+#include <algorithm>
+#include <deque>
+#include <fstream>
+#include <regex>
+#include <set>
+#include <sstream>
+
+#include "h2.hpp"
+#include "json.hpp"
+#include "pb.hpp"
+
+// ---- the NVML binding (agent/native/b200agent_nvml.cc is compiled into this binary)
+extern "C" {
+typedef struct { int index; int minor_number; char uuid[96]; char name[96]; char bus_id[32]; unsigned long long mem_total; unsigned long long mem_used; int mig_mode_current; int mig_mode_pending; } b200nvml_device_info;
+typedef struct { char uuid[96]; unsigned long long event_type; unsigned long long event_data; unsigned int gpu_instance_id; unsigned int compute_instance_id; } b200nvml_event;
+const char* b200nvml_last_error(void);
+int b200nvml_init(void);
+int b200nvml_device_count(int*);
+int b200nvml_device_info_get(int, b200nvml_device_info*);
+int b200nvml_average_usage(const char*, unsigned long long, unsigned int*);
+int b200nvml_driver_version(char*, unsigned int);
+int b200nvml_events_open(void**);
+int b200nvml_events_register_xid(void*, int);
+int b200nvml_events_wait(void*, unsigned int, b200nvml_event*);
+int b200nvml_events_close(void*);
+}
+
+namespace {
+
+const char* kResourceName = "nvidia.com/gpu";
+const char* kHealthy = "Healthy";
+const char* kUnhealthy = "Unhealthy";
+const std::regex kNvidiaDeviceRe("^nvidia[0-9]*$");
+const std::regex kVgpuDefault("nvidia([0-9]+)/vgpu([0-9]+)$");
+const std::regex kVgpuMig("nvidia([0-9]+)/gi([0-9]+)/vgpu([0-9]+)$");
+const std::regex kVgpuSuffix("/vgpu([0-9]+)$");
+const unsigned kNotMig = 0xFFFFFFFFu;
+
+int g_verbosity = 0;
+void logf(char level, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  fprintf(stderr, "%c b200-device-plugin] ", level); vfprintf(stderr, fmt, ap); fputc('\n', stderr);
+  va_end(ap);
+}
+#define LOGI(...) logf('I', __VA_ARGS__)
+#define LOGE(...) logf('E', __VA_ARGS__)
+
+bool exists(const std::string& p) { struct stat st; return ::stat(p.c_str(), &st) == 0; }
+std::string join(const std::string& a, const std::string& b) { return a.empty() || a.back() == '/' ? a + b : a + "/" + b; }
+std::string read_file(const std::string& p, bool* ok) { std::ifstream f(p); std::stringstream ss; ss << f.rdbuf(); *ok = (bool)f; return ss.str(); }
+std::vector<std::string> list_dir(const std::string& p, bool* ok, bool files_only) {
+  std::vector<std::string> out; *ok = false;
+  DIR* d = opendir(p.c_str()); if (!d) return out;
+  *ok = true;
+  while (dirent* e = readdir(d)) {
+    std::string n = e->d_name; if (n == "." || n == "..") continue;
+    if (files_only) { struct stat st; if (::stat(join(p, n).c_str(), &st) != 0 || S_ISDIR(st.st_mode)) continue; }
+    out.push_back(n);
+  }
+  closedir(d); std::sort(out.begin(), out.end());
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------ config
+struct Profile { const char* size; int id; int max_count; const char* families; };
+#define MIG_PROFILE(size, id, count, fam) {size, id, count, fam},
+const Profile kProfiles[] = {
+#include "../mig_profiles.inc"
+};
+#undef MIG_PROFILE
+
+struct Config {
+  std::string partition_size, strategy, transport, lib_dir_host = "/home/kubernetes/bin/nvidia/lib64", lib_dir_container = "/usr/local/nvidia/lib64";
+  long max_time_shared = 0, max_shared = 0;
+  std::vector<long> xids;
+  std::map<std::string, std::string> transport_env;
+};
+
+// "" on success; the caller falls back to the empty config on any error (reference nvidia_gpu.go:89-94)
+std::string parse_config_text(const std::string& text, Config* cfg) {
+  json::Value v; std::string err;
+  if (!json::Parser(text).parse(&v, &err) || v.kind != json::Value::Object) return "gpu config must be a JSON object: " + err;
+  cfg->partition_size = v.get_string("GPUPartitionSize");
+  cfg->max_time_shared = v.get_int("MaxTimeSharedClientsPerGPU");
+  if (const json::Value* sh = v.get("GPUSharingConfig")) { cfg->strategy = sh->get_string("GPUSharingStrategy"); cfg->max_shared = sh->get_int("MaxSharedClientsPerGPU"); }
+  if (const json::Value* x = v.get("HealthCriticalXid")) for (auto& e : x->arr) if (e.kind == json::Value::Number) cfg->xids.push_back((long)e.num);
+  if (const json::Value* t = v.get("Transport")) {
+    if (t->kind == json::Value::String) cfg->transport = t->str;
+    else { cfg->transport = t->get_string("Name"); cfg->lib_dir_host = t->get_string("LibDirHost", cfg->lib_dir_host); cfg->lib_dir_container = t->get_string("LibDirContainer", cfg->lib_dir_container);
+           if (const json::Value* e = t->get("Env")) for (auto& kv : e->obj) if (kv.second.kind == json::Value::String) cfg->transport_env[kv.first] = kv.second.str; }
+  }
+  return "";
+}
+std::string add_defaults_and_validate(Config* c) {
+  if (c->max_time_shared > 0) {
+    if (!c->strategy.empty() || c->max_shared > 0) LOGI("Both MaxTimeSharedClientsPerGPU and GPUSharingConfig are set, use the value of MaxTimeSharedClientsPerGPU");
+    c->strategy = "time-sharing"; c->max_shared = c->max_time_shared;
+  } else if (c->strategy == "time-sharing" || c->strategy == "mps") {
+    if (c->max_shared <= 0) return "MaxSharedClientsPerGPU should be > 0 for time-sharing or mps GPU sharing strategies";
+  } else if (c->strategy.empty()) {
+    if (c->max_shared > 0) return "GPU sharing strategy needs to be specified when MaxSharedClientsPerGPU > 0";
+  } else return "invalid GPU Sharing strategy: " + c->strategy + ", should be one of time-sharing or mps";
+  if (!c->transport.empty() && c->transport != "b200coll") return "invalid Transport: " + c->transport + ", should be empty or b200coll";
+  return "";
+}
+Config load_config(const std::string& path) {
+  Config empty;
+  bool ok; std::string text = read_file(path, &ok);
+  if (!ok) { LOGI("No GPU config file (%s); using defaults", path.c_str()); return empty; }
+  Config c; std::string err = parse_config_text(text, &c);
+  if (err.empty()) err = add_defaults_and_validate(&c);
+  if (!err.empty()) { LOGE("failed to parse GPU config file %s: %s; falling back to default GPU config", path.c_str(), err.c_str()); return empty; }
+  return c;
+}
+std::string add_health_critical_xid(Config* c) {
+  const char* e = getenv("XID_CONFIG");
+  if (!e || !*e) { LOGI("There is no Xid config specified"); return ""; }
+  std::vector<long> out; std::stringstream ss(e); std::string tok;
+  while (std::getline(ss, tok, ',')) {
+    size_t a = tok.find_first_not_of(" \t"), b = tok.find_last_not_of(" \t");
+    tok = a == std::string::npos ? "" : tok.substr(a, b - a + 1);
+    char* end = nullptr; long v = strtol(tok.c_str(), &end, 10);
+    if (tok.empty() || *end) return "Invalid HealthCriticalXid input : " + tok;
+    out.push_back(v);
+  }
+  c->xids = out;
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------ sharing
+bool is_virtual_device_id(const std::string& id) { return std::regex_search(id, kVgpuDefault) || std::regex_search(id, kVgpuMig); }
+std::string validate_request(const std::vector<std::string>& ids, size_t physical_count, const std::string& strategy) {
+  if (ids.size() > 1 && is_virtual_device_id(ids[0])) {
+    if (strategy == "time-sharing") return "invalid request for sharing GPU (time-sharing), at most 1 nvidia.com/gpu can be requested on GPU nodes";
+    if (strategy == "mps" && physical_count > 1) return "invalid request for sharing GPU (MPS), at most 1 nvidia.com/gpu can be requested on multi-GPU nodes";
+  }
+  return "";
+}
+bool virtual_to_physical(const std::string& vid, std::string* out) {
+  if (!is_virtual_device_id(vid)) return false;
+  *out = std::regex_replace(vid, kVgpuSuffix, "");
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ manager
+struct Mount { std::string host, container; bool read_only; };
+
+class Manager {
+ public:
+  std::string dev_dir = "/dev", proc_dir = "/proc", pci_root = "/sys/bus/pci/devices", mps_control_bin = "/usr/local/nvidia/bin/nvidia-cuda-mps-control";
+  std::vector<Mount> mounts;
+  Config cfg;
+  double gpu_check_interval = 10.0, socket_check_interval = 1.0;
+  std::vector<std::string> default_devices;
+  unsigned long long total_mem_per_gpu = 0;
+  std::map<std::string, std::string> uuid_of;     // device id -> GPU uuid (health matching, metrics)
+  std::map<std::string, int> index_of;            // "nvidiaN" -> NVML index
+
+  bool numa_topology(const std::string& bus_id, long* node) const {   // false = none / unknown
+    std::string bus = bus_id;
+    const std::string domain = bus.substr(0, bus.find(':'));
+    if (domain.size() == 8 && domain.compare(0, 4, "0000") == 0) bus = bus.substr(4);
+    std::transform(bus.begin(), bus.end(), bus.begin(), ::tolower);
+    bool ok; std::string text = read_file(join(join(pci_root, bus), "numa_node"), &ok);
+    if (!ok) return false;
+    char* end = nullptr; long v = strtol(text.c_str(), &end, 10);
+    if (end == text.c_str() || v < 0) return false;
+    *node = v; return true;
+  }
+
+  std::map<std::string, pb::Device> list_physical() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return cfg.partition_size.empty() ? devices_ : partitions_;
+  }
+  std::map<std::string, pb::Device> list_devices() {
+    auto phys = list_physical();
+    if (cfg.max_shared <= 0) return phys;
+    std::map<std::string, pb::Device> out;
+    for (auto& kv : phys) for (long i = 0; i < cfg.max_shared; i++) { pb::Device d = kv.second; d.id = kv.first + "/vgpu" + std::to_string(i); out[d.id] = d; }   // vGPUs inherit health
+    return out;
+  }
+  // "" on success
+  std::string device_spec(std::string id, std::vector<pb::DeviceSpec>* out) {
+    if (cfg.max_shared > 0) { std::string phys; if (!virtual_to_physical(id, &phys)) return "virtual device ID (" + id + ") is not valid"; id = phys; }
+    std::lock_guard<std::mutex> lk(mu_);
+    if (cfg.partition_size.empty()) {
+      auto it = devices_.find(id);
+      if (it == devices_.end()) return "invalid allocation request with non-existing device " + id;
+      if (it->second.health != kHealthy) return "invalid allocation request with unhealthy device " + id;
+      const std::string p = join(dev_dir, id);
+      out->push_back({p, p, "mrw"});
+      return "";
+    }
+    auto it = partition_specs_.find(id);
+    if (it == partition_specs_.end()) return "invalid allocation request with non-existing GPU partition: " + id;
+    out->insert(out->end(), it->second.begin(), it->second.end());
+    return "";
+  }
+  void set_device_health(const std::string& name, const std::string& health) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto& m = std::regex_match(name, kNvidiaDeviceRe) ? devices_ : partitions_;
+    auto it = m.find(name);
+    if (it != m.end()) it->second.health = health; else { pb::Device d; d.id = name; d.health = health; m[name] = d; }
+  }
+  void report_unhealthy(const std::string& id) {   // never blocks the NVML listener
+    std::lock_guard<std::mutex> lk(hmu_);
+    if (health_q_.size() < 1024) { health_q_.push_back(id); hcv_.notify_all(); } else LOGE("health queue full; dropping update for %s", id.c_str());
+  }
+  bool pop_health(std::string* id, int timeout_ms) {
+    std::unique_lock<std::mutex> lk(hmu_);
+    if (!hcv_.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !health_q_.empty(); })) return false;
+    *id = health_q_.front(); health_q_.pop_front(); return true;
+  }
+
+  std::string discover_gpus() {
+    int n = 0;
+    if (b200nvml_device_count(&n) != 0) return std::string("failed to get devices count: ") + b200nvml_last_error();
+    for (int i = 0; i < n; i++) {
+      b200nvml_device_info info;
+      if (b200nvml_device_info_get(i, &info) != 0) return "failed to get the device handle for index " + std::to_string(i) + ": " + b200nvml_last_error();
+      pb::Device d; d.id = "nvidia" + std::to_string(info.minor_number); d.health = kHealthy;
+      long node; if (info.bus_id[0] && numa_topology(info.bus_id, &node)) { d.has_numa = true; d.numa = node; }
+      std::lock_guard<std::mutex> lk(mu_);
+      devices_[d.id] = d; uuid_of[d.id] = info.uuid; index_of[d.id] = i;
+    }
+    return "";
+  }
+  int discover_num_gpus() const {
+    bool ok; int n = 0;
+    for (auto& f : list_dir(dev_dir, &ok, true)) if (std::regex_match(f, kNvidiaDeviceRe)) n++;
+    return ok ? n : -1;
+  }
+  bool has_additional_gpus() {
+    size_t have; { std::lock_guard<std::mutex> lk(mu_); have = devices_.size(); }
+    int n = discover_num_gpus();
+    if (n > (int)have) { LOGI("Found %d GPUs, while only %zu are registered. Stopping device-plugin server.", n, have); return true; }
+    return false;
+  }
+  bool check_device_paths() const { return exists(join(dev_dir, "nvidiactl")) && exists(join(dev_dir, "nvidia-uvm")); }
+
+  std::string mig_start() {
+    const Profile* prof = nullptr;
+    for (auto& p : kProfiles) if (cfg.partition_size == p.size) prof = &p;
+    if (!prof) return cfg.partition_size + " is not a valid GPU partition size";
+    std::map<std::string, std::vector<pb::DeviceSpec>> specs; std::map<std::string, pb::Device> parts;
+    const std::string cap_dir = join(proc_dir, "driver/nvidia/capabilities");
+    bool ok; auto entries = list_dir(cap_dir, &ok, false);
+    if (!ok) return "failed to read capabilities directory (" + cap_dir + ")";
+    static const std::regex gpu_re("gpu([0-9]+)"), gi_re("gi([0-9]+)"), minor_re("DeviceFileMinor: ([0-9]+)");
+    int partitioned = 0;
+    for (auto& e : entries) {
+      std::smatch m; if (!std::regex_search(e, m, gpu_re)) continue;
+      const std::string gpu_id = m[1]; partitioned++;
+      const std::string gi_base = join(join(cap_dir, e), "mig");
+      auto gis = list_dir(gi_base, &ok, false);
+      if (!ok) return "failed to read GPU instance capabilities dir (" + gi_base + ")";
+      int count = 0;
+      for (auto& gi : gis) {
+        if (!std::regex_search(gi, gi_re)) continue;
+        count++;
+        auto minor_of = [&](const std::string& path, const char* what, int* out) -> std::string {
+          bool rok; std::string text = read_file(path, &rok);
+          if (!rok) return std::string("failed to read ") + what + " access file (" + path + ")";
+          std::smatch mm; if (!std::regex_search(text, mm, minor_re)) return std::string("unexpected contents in ") + what + " access file(" + path + ")";
+          *out = atoi(mm[1].str().c_str()); return "";
+        };
+        int gi_minor = 0, ci_minor = 0; std::string err;
+        if (!(err = minor_of(join(join(gi_base, gi), "access"), "GPU instance", &gi_minor)).empty()) return err;
+        if (!(err = minor_of(join(join(join(gi_base, gi), "ci0"), "access"), "compute instance", &ci_minor)).empty()) return err;   // only ci0 is considered
+        const std::string gpu_dev = join(dev_dir, "nvidia" + gpu_id), gi_dev = join(join(dev_dir, "nvidia-caps"), "nvidia-cap" + std::to_string(gi_minor)),
+                          ci_dev = join(join(dev_dir, "nvidia-caps"), "nvidia-cap" + std::to_string(ci_minor));
+        for (auto& p : {gpu_dev, gi_dev, ci_dev}) if (!exists(p)) return "device (" + p + ") not found";
+        const std::string id = "nvidia" + gpu_id + "/" + gi;
+        LOGI("Discovered GPU partition: %s", id.c_str());
+        specs[id] = {{gpu_dev, gpu_dev, "mrw"}, {gi_dev, gi_dev, "mrw"}, {ci_dev, ci_dev, "mrw"}};
+        pb::Device d; d.id = id; d.health = kHealthy;
+        { std::lock_guard<std::mutex> lk(mu_); auto it = devices_.find("nvidia" + gpu_id); if (it != devices_.end()) { d.has_numa = it->second.has_numa; d.numa = it->second.numa; uuid_of[id] = uuid_of["nvidia" + gpu_id]; } }
+        parts[id] = d;
+      }
+      if (count != prof->max_count) return "Number of partitions (" + std::to_string(count) + ") for GPU " + gpu_id + " does not match expected partition count (" + std::to_string(prof->max_count) + ")";
+    }
+    const int gpus = discover_num_gpus();
+    if (partitioned != gpus) return "Not all GPUs are partitioned as expected. Total number of GPUs: " + std::to_string(gpus) + ", number of partitioned GPUs: " + std::to_string(partitioned);
+    std::lock_guard<std::mutex> lk(mu_);
+    partition_specs_ = specs; partitions_ = parts;
+    return "";
+  }
+
+  std::string mps_healthy() const {
+    int in[2], out[2];
+    if (pipe(in) != 0 || pipe(out) != 0) return "pipe failed";
+    pid_t pid = fork();
+    if (pid < 0) return "fork failed";
+    if (pid == 0) { dup2(in[0], 0); dup2(out[1], 1); close(in[1]); close(out[0]); execl(mps_control_bin.c_str(), mps_control_bin.c_str(), (char*)nullptr); _exit(127); }
+    close(in[0]); close(out[1]);
+    const char* cmd = "get_default_active_thread_percentage";
+    if (write(in[1], cmd, strlen(cmd)) < 0) { /* reported through the exit status */ }
+    close(in[1]);
+    char buf[256]; std::string text; ssize_t n;
+    while ((n = read(out[0], buf, sizeof(buf))) > 0) text.append(buf, (size_t)n);
+    close(out[0]);
+    int st = 0; waitpid(pid, &st, 0);
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) return "failed to health check NVIDIA MPS: exit status " + std::to_string(WIFEXITED(st) ? WEXITSTATUS(st) : -1);
+    LOGI("MPS is healthy, active thread percentage = %s", text.c_str());
+    return "";
+  }
+
+  std::map<std::string, std::string> envs(size_t requested) const {
+    std::map<std::string, std::string> e;
+    if (cfg.strategy == "mps") {
+      e["CUDA_MPS_ACTIVE_THREAD_PERCENTAGE"] = std::to_string((long)requested * 100 / cfg.max_shared);
+      const unsigned long long mem = (unsigned long long)requested * total_mem_per_gpu / (unsigned long long)cfg.max_shared;
+      e["CUDA_MPS_PINNED_DEVICE_MEM_LIMIT"] = "0=" + std::to_string(mem / (1024ull * 1024ull)) + "M";
+    }
+    return e;
+  }
+
+  std::string start() {
+    default_devices = {join(dev_dir, "nvidiactl"), join(dev_dir, "nvidia-uvm")};
+    for (const char* extra : {"nvidia-modeset", "nvidia-uvm-tools"}) if (exists(join(dev_dir, extra))) default_devices.push_back(join(dev_dir, extra));
+    std::string err = discover_gpus();
+    if (!err.empty()) return err;
+    if (!cfg.partition_size.empty() && !(err = mig_start()).empty()) return "failed to start mig device manager: " + err;
+    if (cfg.strategy == "mps") {
+      if (!(err = mps_healthy()).empty()) return "NVIDIA MPS is not running on this node: " + err;
+      bool have = false; for (auto& m : mounts) have |= m.host == "/tmp/nvidia-mps";
+      if (!have) mounts.push_back({"/tmp/nvidia-mps", "/tmp/nvidia-mps", false});
+      b200nvml_device_info info;
+      if (b200nvml_device_info_get(0, &info) != 0) return "failed to query total memory available per GPU";
+      total_mem_per_gpu = info.mem_total;
+    }
+    return "";
+  }
+
+ private:
+  std::mutex mu_, hmu_;
+  std::condition_variable hcv_;
+  std::deque<std::string> health_q_;
+  std::map<std::string, pb::Device> devices_, partitions_;
+  std::map<std::string, std::vector<pb::DeviceSpec>> partition_specs_;
+};
+
+// ------------------------------------------------------------------------------------------------ transport hook
+void apply_transport(const Config& cfg, const std::vector<Mount>& mounts, pb::ContainerAllocateResponse* r) {
+  if (cfg.transport != "b200coll") return;
+  std::map<std::string, std::string> env = {{"B200COLL_LIB_DIR", cfg.lib_dir_container}, {"B200COLL_LIB", cfg.lib_dir_container + "/libb200coll.so"}, {"LD_LIBRARY_PATH", cfg.lib_dir_container},
+                                            {"B200COLL_NVLS", "-1"}, {"B200COLL_ALGO", "auto"}, {"B200COLL_TIMEOUT_MS", "20000"}, {"B200COLL_DEBUG", "WARN"}};
+  for (auto& kv : cfg.transport_env) env[kv.first] = kv.second;
+  for (auto& kv : env) r->envs.insert(kv);
+  bool covered = false;
+  for (auto& m : mounts) covered |= cfg.lib_dir_host == m.host || cfg.lib_dir_host.compare(0, m.host.size() + 1, m.host + "/") == 0;
+  if (!covered) r->mounts.push_back({cfg.lib_dir_container, cfg.lib_dir_host, true});
+}
+
+// ------------------------------------------------------------------------------------------------ gRPC service
+std::vector<pb::Device> device_vector(Manager* m) { std::vector<pb::Device> v; for (auto& kv : m->list_devices()) v.push_back(kv.second); return v; }
+
+void register_service(h2::Server* srv, Manager* ngm) {
+  const std::string svc = "/v1beta1.DevicePlugin/";
+  srv->add_unary(svc + "GetDevicePluginOptions", [](const std::string&, std::string* resp) { resp->clear(); return h2::Status{}; });   // empty options
+  srv->add_unary(svc + "PreStartContainer", [](const std::string&, std::string* resp) { LOGE("device-plugin: PreStart should NOT be called for the B200 GPU device plugin"); resp->clear(); return h2::Status{}; });
+  srv->add_unary(svc + "GetPreferredAllocation", [](const std::string&, std::string* resp) { LOGE("device-plugin: GetPreferredAllocation should NOT be called for the B200 GPU device plugin"); resp->clear(); return h2::Status{}; });
+  srv->add_stream(svc + "ListAndWatch", [ngm](const std::string&, h2::ServerStream* stream) {
+    LOGI("device-plugin: ListAndWatch start");
+    if (!stream->send(pb::encode_list_and_watch(device_vector(ngm)))) return h2::Status{};
+    while (!stream->cancelled()) {
+      std::string id;
+      if (!ngm->pop_health(&id, 500)) continue;
+      LOGI("device-plugin: %s device marked as Unhealthy", id.c_str());
+      ngm->set_device_health(id, kUnhealthy);
+      if (!stream->send(pb::encode_list_and_watch(device_vector(ngm)))) break;
+    }
+    return h2::Status{};
+  });
+  srv->add_unary(svc + "Allocate", [ngm](const std::string& req, std::string* resp) {
+    std::vector<std::vector<std::string>> containers;
+    if (!pb::decode_allocate_request(req, &containers)) return h2::Status{13, "malformed AllocateRequest"};
+    std::vector<pb::ContainerAllocateResponse> out;
+    for (auto& ids : containers) {
+      std::string err = validate_request(ids, ngm->list_physical().size(), ngm->cfg.strategy);
+      if (!err.empty()) return h2::Status{2, err};
+      pb::ContainerAllocateResponse r;
+      for (auto& id : ids) if (!(err = ngm->device_spec(id, &r.devices)).empty()) return h2::Status{2, err};
+      for (auto& d : ngm->default_devices) r.devices.push_back({d, d, "mrw"});
+      for (auto& m : ngm->mounts) r.mounts.push_back({m.container, m.host, m.read_only});
+      r.envs = ngm->envs(ids.size());
+      apply_transport(ngm->cfg, ngm->mounts, &r);
+      out.push_back(r);
+    }
+    *resp = pb::encode_allocate_response(out);
+    return h2::Status{};
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ health
+void health_loop(Manager* ngm, std::atomic<bool>* stop) {
+  std::set<long> critical(ngm->cfg.xids.begin(), ngm->cfg.xids.end());
+  critical.insert(48);                                   // double-bit ECC is always health-critical
+  void* set = nullptr;
+  if (b200nvml_events_open(&set) != 0) { LOGE("failed to create NVML event set: %s", b200nvml_last_error()); return; }
+  for (auto& kv : ngm->index_of) {
+    int rc = b200nvml_events_register_xid(set, kv.second);
+    if (rc == -3) LOGI("Warning: %s is too old to support healthchecking. It will always be marked healthy.", kv.first.c_str());
+    else if (rc != 0) LOGE("failed to register %s for NVML events: %s", kv.first.c_str(), b200nvml_last_error());
+  }
+  LOGI("Starting GPU Health Checker");
+  while (!*stop) {
+    b200nvml_event ev;
+    int rc = b200nvml_events_wait(set, 1000, &ev);
+    if (rc != 0) continue;                               // timeout or transient error
+    if (ev.event_type != 8) { LOGI("Skip error Xid=%llu as it is not Xid Critical", ev.event_data); continue; }
+    if (!critical.count((long)ev.event_data)) { LOGI("Health checker is skipping Xid %llu error", ev.event_data); continue; }
+    auto phys = ngm->list_physical();
+    if (!ev.uuid[0]) { LOGE("XidCriticalError: Xid=%llu, All devices will go unhealthy.", ev.event_data); for (auto& kv : phys) ngm->report_unhealthy(kv.first); continue; }
+    bool found = false;
+    for (auto& kv : phys) {
+      auto u = ngm->uuid_of.find(kv.first);
+      if (u == ngm->uuid_of.end() || u->second != ev.uuid) continue;
+      unsigned gi = kNotMig;
+      std::smatch m; static const std::regex gi_re("/gi([0-9]+)");
+      if (std::regex_search(kv.first, m, gi_re)) gi = (unsigned)atoi(m[1].str().c_str());
+      if (gi != ev.gpu_instance_id) continue;
+      LOGE("XidCriticalError: Xid=%llu on Device=%s, the device will go unhealthy.", ev.event_data, kv.first.c_str());
+      ngm->report_unhealthy(kv.first); found = true;
+    }
+    if (!found) LOGE("XidCriticalError: Xid=%llu on unknown device.", ev.event_data);
+  }
+  b200nvml_events_close(set);
+}
+
+// ------------------------------------------------------------------------------------------------ metrics
+std::string esc(const std::string& s) { std::string o; for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); } return o; }
+std::string collect_metrics(Manager* ngm, const std::string& pod_resources_socket) {
+  std::ostringstream os;
+  struct Info { std::string uuid, name; unsigned long long total, used; unsigned duty; bool ok; };
+  std::map<std::string, Info> gpus;
+  const unsigned long long since = (unsigned long long)((time(nullptr) - 10)) * 1000000ull;
+  for (auto& kv : ngm->index_of) {
+    b200nvml_device_info di; Info inf{};
+    if (b200nvml_device_info_get(kv.second, &di) != 0) continue;
+    inf.uuid = di.uuid; inf.name = di.name; inf.total = di.mem_total; inf.used = di.mem_used;
+    inf.ok = b200nvml_average_usage(di.uuid, since, &inf.duty) == 0 && inf.duty <= 100;       // > 100 => skipped this tick
+    gpus[kv.first] = inf;
+  }
+  auto help = [&](const char* n, const char* h) { os << "# HELP " << n << " " << h << "\n# TYPE " << n << " gauge\n"; };
+  std::vector<pb::ContainerDevices> cds;
+  std::string resp, err;
+  if (h2::unary_call(pod_resources_socket, "/v1alpha1.PodResourcesLister/List", "", &resp, &err, 3000) == 0) pb::decode_pod_resources(resp, &cds);
+  else if (g_verbosity > 0) LOGE("Failed to get devices for containers: %s", err.c_str());
+  std::map<std::string, std::vector<std::string>> per_ctr;   // label prefix -> physical ids
+  std::map<std::string, size_t> requests;
+  for (auto& cd : cds) {
+    if (cd.resource != kResourceName || cd.ids.empty()) continue;
+    const std::string lab = "namespace=\"" + esc(cd.ns) + "\",pod=\"" + esc(cd.pod) + "\",container=\"" + esc(cd.container) + "\"";
+    for (auto& id : cd.ids) if (!is_virtual_device_id(id)) per_ctr[lab].push_back(id);
+    requests[lab] += per_ctr[lab].size();
+    per_ctr[lab];
+  }
+  help("request", "Number of accelerator devices requested by the container");
+  for (auto& kv : per_ctr) os << "request{" << kv.first << ",resource_name=\"nvidia.com/gpu\"} " << kv.second.size() << "\n";
+  const char* names[3] = {"duty_cycle", "memory_total", "memory_used"};
+  const char* helps[3] = {"Percent of time when the GPU was actively processing", "Total memory available on the GPU in bytes", "Allocated GPU memory in bytes"};
+  for (int k = 0; k < 3; k++) {
+    help(names[k], helps[k]);
+    for (auto& kv : per_ctr) for (auto& id : kv.second) {
+      auto g = gpus.find(id); if (g == gpus.end() || !g->second.ok) continue;
+      const unsigned long long v = k == 0 ? g->second.duty : k == 1 ? g->second.total : g->second.used;
+      os << names[k] << "{" << kv.first << ",make=\"nvidia\",accelerator_id=\"" << esc(g->second.uuid) << "\",model=\"" << esc(g->second.name) << "\"} " << v << "\n";
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    const std::string n = std::string(names[k]) + "_gpu_node";
+    help(n.c_str(), helps[k]);
+    for (auto& g : gpus) { if (!g.second.ok) continue; const unsigned long long v = k == 0 ? g.second.duty : k == 1 ? g.second.total : g.second.used;
+      os << n << "{make=\"nvidia\",accelerator_id=\"" << esc(g.second.uuid) << "\",model=\"" << esc(g.second.name) << "\"} " << v << "\n"; }
+  }
+  return os.str();
+}
+
+void metrics_server(Manager* ngm, int port, int interval_ms, const std::string& pod_resources_socket, std::atomic<bool>* stop) {
+  int fd = ::socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC, 0);
+  int one = 1; setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+  sockaddr_in a{}; a.sin_family = AF_INET; a.sin_addr.s_addr = htonl(INADDR_ANY); a.sin_port = htons((uint16_t)port);
+  if (::bind(fd, reinterpret_cast<sockaddr*>(&a), sizeof(a)) < 0 || ::listen(fd, 16) < 0) { LOGE("Failed to start metric server on port %d: %s", port, strerror(errno)); ::close(fd); return; }
+  std::mutex mu; std::string snapshot = collect_metrics(ngm, pod_resources_socket);
+  std::thread collector([&] { while (!*stop) { for (int i = 0; i < interval_ms / 100 && !*stop; i++) usleep(100000); std::string s = collect_metrics(ngm, pod_resources_socket); std::lock_guard<std::mutex> lk(mu); snapshot = s; } });
+  while (!*stop) {
+    pollfd p{fd, POLLIN, 0};
+    if (poll(&p, 1, 500) <= 0) continue;
+    int c = ::accept4(fd, nullptr, nullptr, SOCK_CLOEXEC);
+    if (c < 0) continue;
+    char req[2048]; ssize_t n = ::recv(c, req, sizeof(req) - 1, 0); req[n > 0 ? n : 0] = 0;
+    std::string body, status = "200 OK";
+    if (strncmp(req, "GET /metrics", 12) == 0) { std::lock_guard<std::mutex> lk(mu); body = snapshot; } else { status = "404 Not Found"; body = "not found\n"; }
+    const std::string resp = "HTTP/1.1 " + status + "\r\nContent-Type: text/plain; version=0.0.4\r\nContent-Length: " + std::to_string(body.size()) + "\r\nConnection: close\r\n\r\n" + body;
+    h2::write_all(c, resp.data(), resp.size());
+    ::close(c);
+  }
+  collector.join();
+  ::close(fd);
+}
+
+// ------------------------------------------------------------------------------------------------ serve loop
+std::atomic<bool> g_stop{false};
+void on_signal(int) { g_stop = true; }
+
+ino_t inode_of(const std::string& p) { struct stat st; return ::stat(p.c_str(), &st) == 0 ? st.st_ino : 0; }
+
+int serve(Manager* ngm, const std::string& plugin_dir, const std::string& kubelet_endpoint, const std::string& plugin_endpoint) {
+  const std::string kubelet_path = join(plugin_dir, kubelet_endpoint);
+  bool do_register = exists(kubelet_path);
+  LOGI(do_register ? "will register with the kubelet (beta API)" : "no kubelet.sock to register.");
+  while (!g_stop) {
+    const std::string sock = join(plugin_dir, plugin_endpoint);
+    h2::Server server;
+    register_service(&server, ngm);
+    std::string err;
+    if (!server.listen_unix(sock, &err)) { LOGE("cannot listen on %s: %s", sock.c_str(), err.c_str()); return 1; }
+    LOGI("device-plugin: serving on %s", sock.c_str());
+    if (do_register) {
+      std::string resp;
+      int st = h2::unary_call(kubelet_path, "/v1beta1.Registration/Register", pb::encode_register_request("v1beta1", plugin_endpoint, kResourceName), &resp, &err);
+      if (st != 0) { server.stop(); LOGE("device-plugin: cannot register to kubelet service: %s", err.c_str()); return 1; }   // pod restarts (reference: glog.Fatal)
+      LOGI("device-plugin registered with the kubelet");
+    }
+    const ino_t kubelet_ino = inode_of(kubelet_path);
+    auto next_gpu_check = std::chrono::steady_clock::now() + std::chrono::milliseconds((int)(ngm->gpu_check_interval * 1000));
+    bool rediscover = false;
+    while (!g_stop) {
+      usleep((useconds_t)(ngm->socket_check_interval * 1e6));
+      if (!exists(sock)) { LOGI("plugin socket %s was removed; restarting the server", sock.c_str()); break; }
+      const ino_t ino = inode_of(kubelet_path);
+      if (do_register && ino && ino != kubelet_ino) { LOGI("kubelet socket was re-created (kubelet restart); re-registering"); break; }
+      if (!do_register && ino) { do_register = true; LOGI("kubelet socket appeared; registering"); break; }
+      if (std::chrono::steady_clock::now() >= next_gpu_check) {
+        next_gpu_check = std::chrono::steady_clock::now() + std::chrono::milliseconds((int)(ngm->gpu_check_interval * 1000));
+        if (ngm->has_additional_gpus()) { rediscover = true; break; }
+      }
+    }
+    server.stop();
+    ::unlink(sock.c_str());
+    if (rediscover) {
+      double backoff = 1.0;
+      while (!g_stop) { std::string e = ngm->discover_gpus(); if (e.empty()) break; LOGE("rediscovery failed: %s; retrying in %.0fs", e.c_str(), backoff); usleep((useconds_t)(backoff * 1e6)); backoff = std::min(backoff * 2, 30.0); }
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::string host_path = "/home/kubernetes/bin/nvidia", container_path = "/usr/local/nvidia", host_vulkan = "/home/kubernetes/bin/nvidia/vulkan/icd.d", container_vulkan = "/etc/vulkan/icd.d",
+              plugin_dir = "/device-plugin", gpu_config = "/etc/nvidia/gpu_config.json", plugin_endpoint, pod_resources = "/var/lib/kubelet/pod-resources/kubelet.sock";
+  bool enable_metrics = false, enable_health = false;
+  int metrics_port = 2112, metrics_interval = 30000;
+  Manager ngm;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    while (!a.empty() && a[0] == '-') a.erase(0, 1);
+    std::string val; bool has = false;
+    size_t eq = a.find('=');
+    if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has = true; }
+    auto need = [&]() -> std::string { if (has) return val; if (i + 1 < argc) return argv[++i]; fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); };
+    if (a == "host-path") host_path = need();
+    else if (a == "container-path") container_path = need();
+    else if (a == "host-vulkan-icd-path") host_vulkan = need();
+    else if (a == "container-vulkan-icd-path") container_vulkan = need();
+    else if (a == "plugin-directory") plugin_dir = need();
+    else if (a == "gpu-config") gpu_config = need();
+    else if (a == "gpu-metrics-port") metrics_port = atoi(need().c_str());
+    else if (a == "gpu-metrics-collection-interval") metrics_interval = atoi(need().c_str());
+    else if (a == "enable-container-gpu-metrics") enable_metrics = !has || val != "false";
+    else if (a == "enable-health-monitoring") enable_health = !has || val != "false";
+    else if (a == "publish-driver-version") { /* needs the Kubernetes API: handled by the Python agent */ }
+    else if (a == "dev-directory") ngm.dev_dir = need();
+    else if (a == "proc-directory") ngm.proc_dir = need();
+    else if (a == "pci-root") ngm.pci_root = need();
+    else if (a == "mps-control-bin") ngm.mps_control_bin = need();
+    else if (a == "plugin-endpoint") plugin_endpoint = need();
+    else if (a == "pod-resources-socket") pod_resources = need();
+    else if (a == "gpu-check-interval") ngm.gpu_check_interval = atof(need().c_str());
+    else if (a == "socket-check-interval") ngm.socket_check_interval = atof(need().c_str());
+    else if (a == "v") g_verbosity = atoi(need().c_str());
+    else if (a == "logtostderr" || a == "alsologtostderr") {}
+    else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
+  }
+  signal(SIGINT, on_signal); signal(SIGTERM, on_signal); signal(SIGPIPE, SIG_IGN);
+  LOGI("device-plugin started");
+  ngm.mounts = {{host_path, container_path, true}, {host_vulkan, container_vulkan, true}};
+  ngm.cfg = load_config(gpu_config);
+  std::string err = add_health_critical_xid(&ngm.cfg);
+  if (!err.empty()) LOGE("failed to add HealthCriticalXid: %s", err.c_str());
+  while (!g_stop && !ngm.check_device_paths()) { if (g_verbosity >= 3) LOGI("nvidiactl / nvidia-uvm not present yet; waiting for the driver installer"); sleep(5); }
+  LOGI("Initializing nvml");
+  if (b200nvml_init() != 0) { LOGE("nvml init failed: %s", b200nvml_last_error()); return 1; }
+  while (!g_stop) { err = ngm.start(); if (err.empty()) break; LOGE("failed to start GPU device manager: %s", err.c_str()); sleep(5); }
+  if (g_stop) return 0;
+  std::vector<std::thread> side;
+  if (enable_metrics) {
+    if (!ngm.cfg.partition_size.empty()) LOGI("metrics are disabled when MIG partitioning is on");
+    else { LOGI("Starting metrics server on port: %d, collection interval: %d", metrics_port, metrics_interval); side.emplace_back(metrics_server, &ngm, metrics_port, metrics_interval, pod_resources, &g_stop); }
+  }
+  if (enable_health) side.emplace_back(health_loop, &ngm, &g_stop);
+  if (plugin_endpoint.empty()) plugin_endpoint = "nvidiaGPU-" + std::to_string((long)time(nullptr)) + ".sock";
+  int rc = serve(&ngm, plugin_dir, "kubelet.sock", plugin_endpoint);
+  g_stop = true;
+  for (auto& t : side) t.join();
+  return rc;
+}

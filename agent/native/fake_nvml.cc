@@ -10,7 +10,27 @@
 #include <unistd.h>
 #include <cstdint>
 
-static int gpus() { const char* e = getenv("FAKE_NVML_GPUS"); return e ? atoi(e) : 2; }
+#include <dirent.h>
+#include <ctype.h>
+// FAKE_NVML_DEV_DIR: count nvidia<N> files there (lets a test hot-add a GPU by touching a file), else FAKE_NVML_GPUS.
+static int gpus() {
+  if (const char* d = getenv("FAKE_NVML_DEV_DIR")) {
+    int n = 0;
+    if (DIR* dir = opendir(d)) {
+      while (dirent* e = readdir(dir)) {
+        const char* s = e->d_name;
+        if (strncmp(s, "nvidia", 6) != 0 || !s[6]) continue;
+        bool digits = true;
+        for (const char* p = s + 6; *p; p++) digits = digits && isdigit((unsigned char)*p);
+        if (digits) n++;
+      }
+      closedir(dir);
+    }
+    return n;
+  }
+  const char* e = getenv("FAKE_NVML_GPUS");
+  return e ? atoi(e) : 2;
+}
 static long g_event_pos = 0;
 
 extern "C" {

@@ -1,0 +1,209 @@
+"""The native C++ device plugin (build/agent/b200-device-plugin) driven by the same conformance doubles as the Python agent:
+real grpcio client <-> hand-written HTTP/2 + HPACK server, and the binary's own HTTP/2 client <-> a grpcio stub kubelet.
+Scenarios mirror tests/test_device_plugin.py (reference shape: pkg/gpu/nvidia/beta_plugin_test.go:36-614)."""
+import json
+import os
+import signal
+import subprocess
+import time
+import urllib.request
+
+import grpc
+import pytest
+
+from container_engine_accelerators_b200.agent import sharing, testing
+from container_engine_accelerators_b200.agent.plugin import DevicePluginClient
+
+
+class Native:
+    def __init__(self, tmp_path, native_build, gpus=2, mig_parts=0, config=None, with_kubelet=True, extra_args=(), env=None, pci=None):
+        self.root = str(tmp_path)
+        self.dev = testing.make_fake_dev(self.root, gpus)
+        self.proc = testing.make_fake_mig(self.root, self.dev, gpus, mig_parts) if mig_parts else str(tmp_path / "proc")
+        self.plugin_dir = str(tmp_path / "dp"); os.makedirs(self.plugin_dir, exist_ok=True)
+        self.kubelet = testing.KubeletStub(self.plugin_dir).start() if with_kubelet else None
+        cfg = tmp_path / "gpu_config.json"
+        if config is not None:
+            cfg.write_text(config if isinstance(config, str) else json.dumps(config))
+        self.endpoint = "nvidiaGPU-native.sock"
+        self.log = open(tmp_path / "plugin.log", "w")
+        e = {**os.environ, "B200AGENT_NVML_LIB": os.path.join(native_build, "libfake_nvml.so"), "FAKE_NVML_DEV_DIR": self.dev, **(env or {})}
+        self.proc_handle = subprocess.Popen([os.path.join(native_build, "b200-device-plugin"), "-plugin-directory", self.plugin_dir, "-gpu-config", str(cfg), "--dev-directory", self.dev,
+                                             "--proc-directory", self.proc, "--pci-root", pci or str(tmp_path / "nopci"), "--plugin-endpoint", self.endpoint, "--gpu-check-interval", "0.6",
+                                             "--socket-check-interval", "0.1", *extra_args], env=e, stderr=self.log, stdout=self.log)
+        self.client = None
+
+    def connect(self, timeout=10):
+        path = os.path.join(self.plugin_dir, self.endpoint)
+        deadline = time.time() + timeout
+        while not os.path.exists(path):
+            assert time.time() < deadline and self.proc_handle.poll() is None, open(self.log.name).read()
+            time.sleep(0.05)
+        self.client = DevicePluginClient(path)
+        self.client.wait_ready()
+        return self.client
+
+    def logs(self):
+        self.log.flush()
+        return open(self.log.name).read()
+
+    def close(self):
+        if self.client:
+            self.client.close()
+        if self.proc_handle.poll() is None:
+            self.proc_handle.send_signal(signal.SIGTERM)
+            try:
+                self.proc_handle.wait(5)
+            except subprocess.TimeoutExpired:
+                self.proc_handle.kill()
+        if self.kubelet:
+            self.kubelet.stop()
+        self.log.close()
+
+
+@pytest.fixture
+def native(tmp_path, native_build):
+    made = []
+
+    def make(**kw):
+        n = Native(tmp_path, native_build, **kw)
+        made.append(n)
+        return n
+    yield make
+    for n in made:
+        n.close()
+
+
+def first_list(client):
+    stream = client.list_and_watch()
+    return stream, {d.ID: d for d in next(stream).devices}
+
+
+def test_register_list_allocate(native):
+    n = native()
+    reg = n.kubelet.wait_registration()                       # the binary's own HTTP/2 client against a grpcio server
+    assert (reg.version, reg.endpoint, reg.resource_name) == ("v1beta1", n.endpoint, "nvidia.com/gpu") and not reg.HasField("options")
+    c = n.connect()
+    opts = c.options()
+    assert not opts.pre_start_required and not opts.get_preferred_allocation_available
+    stream, devs = first_list(c)
+    assert set(devs) == {"nvidia0", "nvidia1"} and all(d.health == "Healthy" for d in devs.values())
+    cr = c.allocate(["nvidia0"]).container_responses[0]
+    assert len(cr.devices) == 5 and len(cr.mounts) == 2
+    assert cr.devices[0].host_path.endswith("/dev/nvidia0") and all(d.permissions == "mrw" and d.host_path == d.container_path for d in cr.devices)
+    assert [(m.host_path, m.container_path, m.read_only) for m in cr.mounts] == [("/home/kubernetes/bin/nvidia", "/usr/local/nvidia", True), ("/home/kubernetes/bin/nvidia/vulkan/icd.d", "/etc/vulkan/icd.d", True)]
+    assert dict(cr.envs) == {}
+    resp = c.allocate(["nvidia0", "nvidia1"], ["nvidia1"])
+    assert [len(r.devices) for r in resp.container_responses] == [6, 5]
+    with pytest.raises(grpc.RpcError) as ei:
+        c.allocate(["nvidia9"])
+    assert ei.value.code() == grpc.StatusCode.UNKNOWN and "invalid allocation request with non-existing device nvidia9" in ei.value.details()
+    stream.cancel()
+
+
+def test_many_sequential_calls_reuse_one_connection(native):
+    """HPACK dynamic-table state must survive across requests on one HTTP/2 connection (grpcio indexes repeated headers)."""
+    c = native().connect()
+    for i in range(50):
+        assert len(c.allocate([f"nvidia{i % 2}"]).container_responses[0].devices) == 5
+
+
+def test_numa_topology_is_advertised(native, tmp_path):
+    pci = testing.make_fake_pci(str(tmp_path), "0000:1b:00.0", 1)
+    c = native(gpus=1, pci=pci).connect()
+    _, devs = first_list(c)
+    assert [n.ID for n in devs["nvidia0"].topology.nodes] == [1]
+
+
+def test_time_sharing_and_mig(native, tmp_path):
+    n = native(config={"GPUSharingConfig": {"GPUSharingStrategy": "time-sharing", "MaxSharedClientsPerGPU": 3}})
+    c = n.connect()
+    _, devs = first_list(c)
+    assert set(devs) == {f"nvidia{g}/vgpu{k}" for g in range(2) for k in range(3)}
+    assert c.allocate(["nvidia1/vgpu2"]).container_responses[0].devices[0].host_path.endswith("/dev/nvidia1")
+    with pytest.raises(grpc.RpcError) as ei:
+        c.allocate(["nvidia0/vgpu0", "nvidia0/vgpu1"])
+    assert sharing.ERR_TIME_SHARING in ei.value.details()
+
+
+def test_mig_seven_slices(native):
+    c = native(gpus=1, mig_parts=7, config={"GPUPartitionSize": "1g.23gb"}).connect()
+    _, devs = first_list(c)
+    assert set(devs) == {f"nvidia0/gi{i}" for i in range(1, 8)}
+    cr = c.allocate(["nvidia0/gi3"]).container_responses[0]
+    assert len(cr.devices) == 7 and "/nvidia-caps/nvidia-cap" in cr.devices[1].host_path
+    with pytest.raises(grpc.RpcError) as ei:
+        c.allocate(["nvidia0/gi9"])
+    assert "invalid allocation request with non-existing GPU partition: nvidia0/gi9" in ei.value.details()
+
+
+def test_bad_config_falls_back_and_transport_profile(native):
+    n = native(config="{broken json")
+    c = n.connect()
+    _, devs = first_list(c)
+    assert set(devs) == {"nvidia0", "nvidia1"} and "falling back to default GPU config" in n.logs()
+    n2 = native(config={"Transport": {"Name": "b200coll", "Env": {"B200COLL_ALGO": "nvls"}}}, with_kubelet=False)
+    n2.plugin_dir  # separate dir per instance is not needed: different endpoint names would collide -> close the first
+    n.close()
+    env = dict(n2.connect().allocate(["nvidia0"]).container_responses[0].envs)
+    assert env["B200COLL_LIB"] == "/usr/local/nvidia/lib64/libb200coll.so" and env["B200COLL_ALGO"] == "nvls" and env["LD_LIBRARY_PATH"] == "/usr/local/nvidia/lib64"
+
+
+def test_hot_add_and_socket_removal_restart(native):
+    n = native()
+    n.kubelet.wait_registration()
+    c = n.connect()
+    stream, devs = first_list(c)
+    stream.cancel()
+    testing.add_fake_gpu(n.dev, 2)
+    assert n.kubelet.wait_registration(timeout=10).endpoint == n.endpoint
+    c.close()
+    c = n.connect()
+    _, devs = first_list(c)
+    assert set(devs) == {"nvidia0", "nvidia1", "nvidia2"}
+    c.close(); n.client = None
+    os.unlink(os.path.join(n.plugin_dir, n.endpoint))
+    assert n.kubelet.wait_registration(timeout=10).endpoint == n.endpoint
+
+
+def test_xid_event_streams_unhealthy_and_blocks_allocation(native, tmp_path):
+    events = tmp_path / "events.txt"
+    events.write_text("")
+    n = native(extra_args=["-enable-health-monitoring"], env={"FAKE_NVML_EVENTS": str(events), "XID_CONFIG": "31"})
+    c = n.connect()
+    stream = c.list_and_watch()
+    assert {d.ID: d.health for d in next(stream).devices} == {"nvidia0": "Healthy", "nvidia1": "Healthy"}
+    time.sleep(0.5)
+    events.write_text("0 13\n1 31\n")                 # 13 is not critical; 31 is (XID_CONFIG)
+    assert {d.ID: d.health for d in next(stream).devices} == {"nvidia0": "Healthy", "nvidia1": "Unhealthy"}
+    with pytest.raises(grpc.RpcError) as ei:
+        c.allocate(["nvidia1"])
+    assert "invalid allocation request with unhealthy device nvidia1" in ei.value.details()
+    stream.cancel()
+
+
+def test_metrics_endpoint(native, tmp_path):
+    from tests.test_health_metrics import PodResourcesStub
+    sock = str(tmp_path / "pr.sock")
+    stub = PodResourcesStub(sock, [("default", "p1", "c1", "nvidia.com/gpu", ["nvidia0"]), ("default", "p2", "c1", "nvidia.com/gpu", ["nvidia1/vgpu0"])])
+    import socket as _s
+    s = _s.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    try:
+        n = native(extra_args=["-enable-container-gpu-metrics", "-gpu-metrics-port", str(port), "-gpu-metrics-collection-interval", "200", "--pod-resources-socket", sock], env={"FAKE_NVML_UTIL": "40,60,80"})
+        n.connect()
+        deadline = time.time() + 10
+        body = ""
+        while time.time() < deadline:
+            try:
+                body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=2).read().decode()
+                if "duty_cycle{" in body:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.2)
+        assert 'duty_cycle{namespace="default",pod="p1",container="c1",make="nvidia",accelerator_id="GPU-fake-0",model="NVIDIA B200"} 60' in body
+        assert 'request{namespace="default",pod="p1",container="c1",resource_name="nvidia.com/gpu"} 1' in body
+        assert 'request{namespace="default",pod="p2",container="c1",resource_name="nvidia.com/gpu"} 0' in body            # virtual ids dropped
+        assert 'memory_total_gpu_node{make="nvidia",accelerator_id="GPU-fake-1",model="NVIDIA B200"} ' in body
+    finally:
+        stub.server.stop(0)
