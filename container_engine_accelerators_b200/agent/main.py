@@ -39,6 +39,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--publish-driver-version", action="store_true")
     p.add_argument("--dev-directory", default=DEV_DIR)
     p.add_argument("--proc-directory", default=PROC_DIR)
+    p.add_argument("--status-only", action="store_true",
+                   help="do not serve the kubelet API (the native b200-device-plugin does); only publish Kubernetes-side status: Xid Events + Node condition, driver-version annotations")
     p.add_argument("-v", "--verbosity", type=int, default=0)
     return p
 
@@ -88,7 +90,8 @@ def main(argv=None) -> int:
         except Exception as e:
             log.error("failed to build kube client: %s", e)
     if args.enable_health_monitoring:
-        hc = health.GPUHealthChecker(ngm.list_physical_devices(), ngm.report_unhealthy, ngm.list_health_critical_xid(), kc, api, util.node_name())
+        report = (lambda d: True) if args.status_only else ngm.report_unhealthy
+        hc = health.GPUHealthChecker(ngm.list_physical_devices(), report, ngm.list_health_critical_xid(), kc, api, util.node_name())
         try:
             hc.start()
         except Exception as e:
@@ -100,6 +103,10 @@ def main(argv=None) -> int:
             except Exception as e:
                 log.error("failed to publish driver version annotations: %s", e)
         threading.Thread(target=publish, daemon=True).start()
+    if args.status_only:
+        log.info("status-only mode: the kubelet-facing API is served by the native plugin")
+        threading.Event().wait()
+        return 0
     ngm.serve(args.plugin_directory, KUBELET_ENDPOINT, f"{PLUGIN_ENDPOINT_PREFIX}-{int(time.time())}.sock")
     return 0
 

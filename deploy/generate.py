@@ -36,6 +36,7 @@ REG = "ghcr.io/b200-node-accelerators"
 VERSION = "v0.1.0"
 IMG = {
     "device-plugin": f"{REG}/b200-device-plugin:{VERSION}",
+    "device-plugin-native": f"{REG}/b200-device-plugin-native:{VERSION}",
     "partition-gpu": f"{REG}/b200-partition-gpu:{VERSION}",
     "nri-injector": f"{REG}/b200-nri-device-injector:{VERSION}",
     "persistenced": f"{REG}/b200-persistenced:{VERSION}",
@@ -164,6 +165,21 @@ def device_plugin_ds(*, name="b200-gpu-device-plugin", health=True, metrics=True
     ds = daemonset(name, containers=[ctr], volumes=vols, affinity=node_affinity(expr(selector_key, "Exists")), host_network=False, host_pid=False, tolerate_all=False,
                    extra_spec={"serviceAccountName": "gpu-device-plugin", "restartPolicy": "Always", "securityContext": {"seccompProfile": {"type": "RuntimeDefault"}},
                                "tolerations": [{"effect": "NoExecute", "operator": "Exists"}, {"effect": "NoSchedule", "operator": "Exists"}]})
+    return ds
+
+
+def device_plugin_native_ds() -> dict:
+    """Native variant: the C++ binary owns the kubelet socket, metrics and Unhealthy marking; a small Python sidecar in
+    --status-only mode publishes the Kubernetes-side status (Events, Node condition, driver-version annotations)."""
+    ds = device_plugin_ds(name="b200-gpu-device-plugin-native")
+    spec = ds["spec"]["template"]["spec"]
+    py = spec["containers"][0]
+    native = copy.deepcopy(py)
+    native.update({"name": "b200-device-plugin", "image": IMG["device-plugin-native"],
+                   "command": ["/usr/bin/b200-device-plugin", "-logtostderr", "-enable-container-gpu-metrics", "-enable-health-monitoring"], "resources": {"requests": {"cpu": "50m", "memory": "20Mi"}, "limits": {"memory": "100Mi"}}})
+    py.update({"name": "node-status", "command": ["python", "-m", "container_engine_accelerators_b200.agent.main", "--status-only", "--enable-health-monitoring", "--publish-driver-version"]})
+    py.pop("ports", None)
+    spec["containers"] = [native, py]
     return ds
 
 
@@ -611,6 +627,7 @@ def test_fixture_docs() -> dict:
 def build_tree() -> dict:
     t: dict = {}
     t["device-plugin/device-plugin.yaml"] = [device_plugin_ds()]
+    t["device-plugin/device-plugin-native.yaml"] = [device_plugin_native_ds()]
     t["device-plugin/rbac.yaml"] = device_plugin_rbac()
     t["device-plugin/xid-config.yaml"] = [xid_config()]
     t["device-plugin/gpu-config-b200coll.yaml"] = [gpu_config_map()]
