@@ -235,7 +235,7 @@ def persistenced_container(restart_always: bool = False) -> dict:
 
 def nri_injector_ds(autopilot: bool = False) -> dict:
     ns = "gpudirect-system" if autopilot else "kube-system"
-    ctr = {"name": "device-injector", "image": IMG["nri-injector"], "command": ["python", "-m", "container_engine_accelerators_b200.agent.nri", "--idx", "10"],
+    ctr = {"name": "device-injector", "image": IMG["nri-injector"], "command": ["/usr/bin/b200-nri-device-injector", "--idx", "10"],   # native binary; `python -m ...agent.nri` is the equivalent
            "resources": {"requests": {"cpu": "10m", "memory": "50Mi"}, **({"limits": {"cpu": "100m", "memory": "100Mi"}} if autopilot else {})},
            "securityContext": {"privileged": True}, "volumeMounts": [mount("nri-socket", "/var/run/nri"), mount("dev", "/dev")]}
     aff = node_affinity(expr(ACCEL_KEY, "In", ["nvidia-b200", "nvidia-h100-80gb", "nvidia-h100-mega-80gb", "nvidia-rtx-pro-6000"]))

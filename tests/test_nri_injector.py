@@ -78,3 +78,37 @@ def test_wire_register_configure_create_container(tmp_path):
         rt.close()
         t.join(5)
     assert not t.is_alive()                                # plugin returns when the runtime goes away
+
+
+def test_native_injector_wire_path(tmp_path, native_build):
+    """The C++ plugin (build/agent/b200-nri-device-injector) against the same fake containerd NRI runtime."""
+    import subprocess
+    sock = str(tmp_path / "nri.sock")
+    rt = testing.FakeNriRuntime(sock)
+    fifo = tmp_path / "dev-fifo"
+    os.mkfifo(fifo)
+    proc = subprocess.Popen([os.path.join(native_build, "b200-nri-device-injector"), "--socket", sock], stderr=subprocess.PIPE)
+    try:
+        reg = rt.wait_registered()
+        assert (reg.plugin_name, reg.plugin_idx) == ("device_injector_nri", "10")
+        assert rt.configure().events & (1 << 3)
+        rt.synchronize()
+        resp = rt.create_container("pod", "rxdm", {KEY + "rxdm": f"- path: {fifo}\n  gid: 5\n  type: ignored\n- path: {fifo}\n", KEY + "other": "- path: /nonexistent"})
+        devs = resp.adjust.linux.devices
+        assert len(devs) == 1 and devs[0].path == str(fifo) and devs[0].type == "p" and devs[0].gid.value == 5 and not devs[0].HasField("uid")
+        flow = rt.create_container("pod", "flow", {KEY + "flow": f"[{{path: {fifo}, file_mode: 438}}]"})
+        assert flow.adjust.linux.devices[0].file_mode.value == 438
+        assert len(rt.create_container("pod", "plain", {}).adjust.linux.devices) == 0
+        with pytest.raises(RuntimeError, match="failed to get info from device path /nonexistent"):
+            rt.create_container("pod", "other", {KEY + "other": "- path: /nonexistent"})
+        with pytest.raises(RuntimeError, match="invalid device annotation"):
+            rt.create_container("pod", "bad", {KEY + "bad": "- path: [unclosed"})
+        with pytest.raises(RuntimeError, match="invalid device annotation"):
+            rt.create_container("pod", "bad2", {KEY + "bad2": "just a string"})
+    finally:
+        rt.close()
+        try:
+            proc.wait(5)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+    assert proc.returncode == 0           # exits cleanly when the runtime goes away
