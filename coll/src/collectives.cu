@@ -54,6 +54,23 @@ static b200collResult_t dispatch_types(b200collDataType_t in, b200collDataType_t
 
 struct Grid { int blocks, threads; };
 
+// Every kernel goes through cudaLaunchKernelEx so that back-to-back collectives can use programmatic dependent launch
+// (B200COLL_PDL=1): the next kernel's launch latency overlaps the current kernel's execution; each kernel starts with
+// griddepcontrol.launch_dependents + griddepcontrol.wait, so it still observes its predecessor's completed memory.
+static bool pdl_enabled() { static const bool on = [] { const char* e = getenv("B200COLL_PDL"); return e && *e && *e != '0'; }(); return on; }
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr;
+  if (pdl_enabled()) {
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+  }
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // the error is picked up by LAUNCH_CHECK's cudaGetLastError
+}
+
 // Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs),
 // unless the family's shape pins the thread count.
 enum { kShapeNvls = 0, kShapeP2p = 1, kShapeLL = 2, kShapeNvlsRs = 3 };
@@ -110,7 +127,7 @@ static b200collResult_t copy_scale(b200collComm* c, const void* send, void* recv
     // streaming copy: no peers to wait for, so oversubscribe the chip (8 CTAs of 256 threads per SM) instead of the collective cap
     const size_t vecs = count / Epv<InT>::value + 1;
     Grid g{(int)std::max<size_t>(1, std::min<size_t>((vecs + 1023) / 1024, (size_t)std::max(1, c->sm_count) * 8)), 256};
-    k_copy_scale<InT, OutT><<<g.blocks, g.threads, 0, st>>>(static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale);
+    launch_k(k_copy_scale<InT, OutT>, g.blocks, g.threads, st, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale);
     LAUNCH_CHECK(c);
     return b200collSuccess;
   });
@@ -127,18 +144,18 @@ static b200collResult_t launch_ll(b200collComm* c, b200collOp_t op, const void* 
     const bool mc = c->nvls;
     switch (op) {
       case b200collOpAllReduce:
-        if (mc) k_ll<InT, OutT, false, true, true><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
-        else k_ll<InT, OutT, false, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        if (mc) launch_k(k_ll<InT, OutT, false, true, true>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);
+        else launch_k(k_ll<InT, OutT, false, true, false>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);
         break;
       case b200collOpAllGather:
-        if (mc) k_ll<InT, OutT, false, false, true><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
-        else k_ll<InT, OutT, false, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        if (mc) launch_k(k_ll<InT, OutT, false, false, true>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);
+        else launch_k(k_ll<InT, OutT, false, false, false>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);
         break;
       case b200collOpReduceScatter:
-        k_ll<InT, OutT, true, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        launch_k(k_ll<InT, OutT, true, true, false>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);
         break;
       default:
-        k_ll<InT, OutT, true, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in, out, count, scale, op);
+        launch_k(k_ll<InT, OutT, true, false, false>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);
         break;
     }
     LAUNCH_CHECK(c);
@@ -152,8 +169,8 @@ static b200collResult_t launch_ll2_typed(b200collComm* c, const void* send, void
   constexpr int E = Epv<InT>::value;
   const size_t nslice = ((count + E - 1) / E + c->nranks - 1) / c->nranks;
   Grid g = pick_grid(c, kShapeLL, nslice, 1);
-  if (c->nvls) k_ll_twoshot<InT, OutT, true><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
-  else k_ll_twoshot<InT, OutT, false><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
+  if (c->nvls) launch_k(k_ll_twoshot<InT, OutT, true>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
+  else launch_k(k_ll_twoshot<InT, OutT, false>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(send), static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
   LAUNCH_CHECK(c);
   return b200collSuccess;
 }
@@ -176,10 +193,10 @@ static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const
     const size_t in_off = arena_off(c, send);
     if (algo == b200collAlgoOneShot) {
       Grid g = pick_grid(c, kShapeP2p, nvec, 2);
-      k_pull_reduce<InT, OutT, true, false><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
+      launch_k(k_pull_reduce<InT, OutT, true, false>, g.blocks, g.threads, st, c->dev, in_off, static_cast<OutT*>(recv), count, scale, b200collOpAllReduce);
     } else if (algo == b200collAlgoTwoShot) {
       Grid g = pick_grid(c, kShapeP2p, nvec / c->nranks + 1, 2);
-      k_ar_twoshot<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, b200collOpAllReduce);
+      launch_k(k_ar_twoshot<InT, OutT>, g.blocks, g.threads, st, c->dev, in_off, arena_off(c, recv), count, scale, b200collOpAllReduce);
     } else {
       static const int forced_u = [] { const char* e = getenv("B200COLL_NVLS_UNROLL"); return e ? atoi(e) : 0; }();
       const size_t slice = nvec / c->nranks + 1;
@@ -188,9 +205,9 @@ static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const
       const int u = forced_u ? forced_u : (few_passes ? 1 : 4);
       if (u == 1) {
         g = pick_grid(c, kShapeNvls, slice, 1);
-        k_ar_nvls<InT, OutT, 1><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
+        launch_k(k_ar_nvls<InT, OutT, 1>, g.blocks, g.threads, st, c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
       } else {
-        k_ar_nvls<InT, OutT, 4><<<g.blocks, g.threads, 0, st>>>(c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
+        launch_k(k_ar_nvls<InT, OutT, 4>, g.blocks, g.threads, st, c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
       }
     }
     LAUNCH_CHECK(c);
@@ -275,8 +292,8 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
       Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvls : kShapeP2p, n / Epv<InT>::value, 4);
-      if (algo == b200collAlgoNvls) k_ag_push<InT, OutT, true><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
-      else k_ag_push<InT, OutT, false><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
+      if (algo == b200collAlgoNvls) launch_k(k_ag_push<InT, OutT, true>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
+      else launch_k(k_ag_push<InT, OutT, false>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(s), arena_off(c, r), n, scale, identity, b200collOpAllGather);
       LAUNCH_CHECK(c);
       return b200collSuccess;
     });
@@ -319,8 +336,8 @@ b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recv
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
       Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvlsRs : kShapeP2p, n / Epv<InT>::value, 2);
-      if (algo == b200collAlgoNvls) k_pull_reduce<InT, OutT, false, true><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
-      else k_pull_reduce<InT, OutT, false, false><<<g.blocks, g.threads, 0, st>>>(c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
+      if (algo == b200collAlgoNvls) launch_k(k_pull_reduce<InT, OutT, false, true>, g.blocks, g.threads, st, c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
+      else launch_k(k_pull_reduce<InT, OutT, false, false>, g.blocks, g.threads, st, c->dev, arena_off(c, s_slice_of_mine), static_cast<OutT*>(r), n, scale, b200collOpReduceScatter);
       LAUNCH_CHECK(c);
       return b200collSuccess;
     });
@@ -346,7 +363,7 @@ static b200collResult_t a2av_launch(b200collComm* c, const void* send, void* rec
   return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
     Grid g = pick_grid(c, kShapeP2p, (size_t)a.prefix[c->nranks] + 1, 4);
-    k_a2av_push<InT, OutT><<<g.blocks, g.threads, 0, st>>>(c->dev, static_cast<const InT*>(send), arena_off(c, recv_sym), a, ep->scale, identity, b200collOpAllToAll);
+    launch_k(k_a2av_push<InT, OutT>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(send), arena_off(c, recv_sym), a, ep->scale, identity, b200collOpAllToAll);
     LAUNCH_CHECK(c);
     return b200collSuccess;
   });
@@ -439,7 +456,7 @@ b200collResult_t b200collAllToAllv(const void* send, void* recv, size_t row_elem
 b200collResult_t b200collBarrier(b200collComm_t c, b200collStream_t stream) {
   if (!c) return b200collInvalidArgument;
   if (c->nranks == 1) return b200collSuccess;
-  k_barrier<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, 99);
+  launch_k(k_barrier, 1, 32, static_cast<cudaStream_t>(stream), c->dev, 99u);
   LAUNCH_CHECK(c);
   return b200collSuccess;
 }

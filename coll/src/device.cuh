@@ -64,6 +64,13 @@ __device__ __forceinline__ void record_fault(const CommDev& c, uint32_t code, ui
   record_fault_impl(c.fault, (uint32_t)c.rank, code, peer, expected, observed, op);
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start launching now, then wait until the previous
+// kernel's memory is visible. Both are no-ops unless the launch carried the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- flags
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

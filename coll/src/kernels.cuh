@@ -30,6 +30,7 @@ __device__ __forceinline__ void finish_store_local(OutT* dst, const float* acc, 
 // ------------------------------------------------------------------------------------------------
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(kThreads) k_copy_scale(const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int U = 4;                       // 4 x 16 B loads in flight per thread: HBM-latency hiding for a pure streaming kernel
   const size_t nvec = count / E;
@@ -111,6 +112,7 @@ __device__ __forceinline__ void store_out_guarded(OutT* out, size_t i, size_t co
 // SUM=true: out[i] = sum over sources (AR, RS). SUM=false: out[src*count + i] = source's data (AG, A2A).
 template <typename InT, typename OutT, bool SLICED, bool SUM, bool MC>
 __global__ void __launch_bounds__(kThreads) k_ll(CommDev c, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   const uint32_t k = load_seq(c, kSeqLL);
   const uint32_t buf = k % 3, prev = (k + 2) % 3;
@@ -198,6 +200,7 @@ __device__ __forceinline__ void store_raw_guarded(OutT* out, size_t vec, size_t 
 
 template <typename InT, typename OutT, bool MC>
 __global__ void __launch_bounds__(kThreads) k_ll_twoshot(CommDev c, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+  pdl_prologue();
   static_assert(sizeof(InT) == sizeof(OutT), "two-shot LL keeps one vector geometry for both phases");
   constexpr int E = Epv<InT>::value;
   const uint32_t k = load_seq(c, kSeqLL);
@@ -290,6 +293,7 @@ __device__ __forceinline__ void ar_tail_rank0(const CommDev& c, size_t in_off, s
 // FIXED_ORDER: sum in rank order so every rank computes bit-identical results (one-shot AR).
 template <typename InT, typename OutT, bool FIXED_ORDER, bool MC>
 __global__ void __launch_bounds__(kThreads) k_pull_reduce(CommDev c, size_t in_off, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int U = 2;
   const uint32_t s = load_seq(c, kSeqBarrier);
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(kThreads) k_pull_reduce(CommDev c, size_t in_o
 // S(N-1)/N pulled + S(N-1)/N pushed -> bus bandwidth bound = link bandwidth.
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(kThreads) k_ar_twoshot(CommDev c, size_t in_off, size_t out_off, size_t count, float scale, uint32_t op) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 2;
@@ -401,6 +406,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_twoshot(CommDev c, size_t in_of
 // the multimem.st of pass k (ingress-heavy) overlaps the ld_reduce of pass k+1 (egress-heavy) instead of running back to back.
 template <typename InT, typename OutT, int U>
 __global__ void __launch_bounds__(kThreads) k_ar_nvls(CommDev c, size_t in_off, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
   const uint32_t s = load_seq(c, kSeqBarrier);
@@ -442,6 +448,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_nvls(CommDev c, size_t in_off, 
 // MC: one multimem.st per vector (egress S/N instead of S(N-1)/N).
 template <typename InT, typename OutT, bool MC>
 __global__ void __launch_bounds__(kThreads) k_ag_push(CommDev c, const InT* __restrict__ in, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 4;
@@ -498,6 +505,7 @@ struct A2AvArgs {
 };
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(kThreads) k_a2av_push(CommDev c, const InT* __restrict__ in, size_t out_off, A2AvArgs a, float scale, int identity, uint32_t op) {
+  pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 4;
@@ -547,12 +555,14 @@ __global__ void __launch_bounds__(kThreads) k_a2av_push(CommDev c, const InT* __
 }
 
 __global__ void k_barrier(CommDev c, uint32_t op) {
+  pdl_prologue();
   const uint32_t s = load_seq(c, kSeqBarrier);
   barrier_blocks<true>(c, 2 * s + 2, op);
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
 __global__ void k_fill_u32(uint32_t* p, size_t n, uint32_t v) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
