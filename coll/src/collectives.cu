@@ -201,8 +201,10 @@ static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const
       static const int forced_u = [] { const char* e = getenv("B200COLL_NVLS_UNROLL"); return e ? atoi(e) : 0; }();
       const size_t slice = nvec / c->nranks + 1;
       Grid g = pick_grid(c, kShapeNvls, slice, 4);
-      const bool few_passes = slice < (size_t)g.blocks * g.threads * 16;      // fewer than 4 passes at U=4
-      const int u = forced_u ? forced_u : (few_passes ? 1 : 4);
+      // U=1 (more, thinner passes so multimem.st overlaps the next ld_reduce) was measured on 8xB200 and LOST to U=4 at every
+      // mid size (512 KiB: 20.1 vs 16.0 us, 8 MiB: 38.7 vs 33.9 us): it needs 4x the CTAs, and every extra CTA adds 8 flag
+      // stores + a membar.sys to both barriers. U=4 ships; B200COLL_NVLS_UNROLL=1 keeps the variant reachable.
+      const int u = forced_u ? forced_u : 4;
       if (u == 1) {
         g = pick_grid(c, kShapeNvls, slice, 1);
         launch_k(k_ar_nvls<InT, OutT, 1>, g.blocks, g.threads, st, c->dev, in_off, arena_off(c, recv), count, scale, identity, b200collOpAllReduce);
