@@ -8,9 +8,11 @@
 //   Allocate: requested specs + default devices + mounts + MPS envs (+ b200coll transport profile)
 //   health: NVML Xid events -> Unhealthy via ListAndWatch (48 always critical + XID_CONFIG)
 //   metrics: :2112/metrics, per-container (kubelet PodResources) and per-node duty cycle / memory gauges
-// Kubernetes-API side effects (Events, Node condition, driver-version annotations) need TLS and stay in the Python
-// agent (`python -m container_engine_accelerators_b200.agent.main`), which shares every rule implemented here.
-// The same conformance suite drives both (tests/test_native_device_plugin.py).
+//   Kubernetes side effects (kube.hpp: HTTP/1.1 + TLS through the system libssl): Event per critical Xid, Node condition
+//          XidCriticalError with a 60 s heartbeat and boot-id based auto-clear (health_check/health_checker.go:103-160,
+//          288-358), driver-version annotations by server-side apply (version_visibility/version_visibility.go:38-86)
+// The Python agent (`python -m container_engine_accelerators_b200.agent.main`) implements the same rules; the same
+// conformance suite drives both (tests/test_native_device_plugin.py).
 #include <dirent.h>
 #include <netinet/in.h>
 #include <signal.h>
@@ -30,6 +32,7 @@
 
 #include "h2.hpp"
 #include "json.hpp"
+#include "kube.hpp"
 #include "pb.hpp"
 
 // ---- the NVML binding (agent/native/b200agent_nvml.cc is compiled into this binary)
@@ -416,9 +419,133 @@ void register_service(h2::Server* srv, Manager* ngm) {
 }
 
 // ------------------------------------------------------------------------------------------------ health
-void health_loop(Manager* ngm, std::atomic<bool>* stop) {
+const char* kXidCondition = "XidCriticalError";
+const char* kEventSource = "nvidia-gpu-device-plugin";
+const long kMonitorXids[] = {48, 63, 64, 79, 119, 120, 123, 140};    // Xids that put the repair condition on the Node
+
+std::string node_name() {
+  if (const char* n = getenv("NODE_NAME")) if (*n) return n;
+  char b[256] = ""; gethostname(b, sizeof b - 1); return b;
+}
+
+// Node-object side of the health checker. Every method is best effort: a failing API server never stops the
+// ListAndWatch path from reporting the device Unhealthy.
+struct NodeStatus {
+  kube::Client api;
+  std::string node;
+
+  bool fetch(json::Value* out, const char* why) {
+    kube::Response r = api.get_node(node);
+    std::string err;
+    if (!r.ok()) { LOGE("Failed to get node %s %s: %s", node.c_str(), why, r.describe().c_str()); return false; }
+    if (!json::Parser(r.body).parse(out, &err)) { LOGE("Failed to decode node %s: %s", node.c_str(), err.c_str()); return false; }
+    return true;
+  }
+  static std::string boot_id(json::Value& n) {
+    json::Value* info = n.at("status").find("nodeInfo");
+    return info ? info->get_string("bootID") : "";
+  }
+  bool put(const json::Value& n, const char* why) {
+    kube::Response r = api.update_node_status(node, n);
+    if (!r.ok()) { LOGE("Failed to update node %s status %s: %s", node.c_str(), why, r.describe().c_str()); return false; }
+    return true;
+  }
+  // After a reboot (bootID differs from the one stored in the condition's message) the repair happened: drop the condition.
+  bool reset_condition(bool* removed) {
+    json::Value n;
+    *removed = false;
+    if (!fetch(&n, "to reset the XID condition")) return false;
+    const std::string boot = boot_id(n);
+    json::Value* conds = n.at("status").find("conditions");
+    if (conds && conds->kind == json::Value::Array) {
+      std::vector<json::Value> kept;
+      for (auto& c : conds->arr) {
+        const std::string last = c.get_string("message");
+        if (c.get_string("type") == kXidCondition && c.get_string("status") == "True" && !boot.empty() && !last.empty() && boot != last) continue;
+        kept.push_back(c);
+      }
+      if (kept.size() != conds->arr.size()) {
+        conds->arr = kept;
+        if (!put(n, "to remove the XID condition")) return false;
+        *removed = true;
+        LOGI("Successfully removed XIDCriticalError condition from node %s.", node.c_str());
+        return true;
+      }
+    }
+    LOGI("XIDCriticalError condition doesn't exist for node %s.", node.c_str());
+    return true;
+  }
+  void reset_condition_with_backoff(std::atomic<bool>* stop, double timeout_s = 120.0) {
+    double backoff = 1.0, spent = 0;
+    bool removed;
+    while (!*stop) {
+      if (reset_condition(&removed)) return;
+      if (spent + backoff > timeout_s) { LOGE("Timeout resetting XID condition after %.0f s.", timeout_s); return; }
+      LOGE("Failed to reset XID condition, will retry in %.0fs.", backoff);
+      for (double t = 0; t < backoff && !*stop; t += 0.1) usleep(100000);
+      spent += backoff; backoff = std::min(backoff * 2, 30.0);
+    }
+  }
+  // Adds the Xid to the condition's reason (a JSON object used as a set), creating the condition if needed.
+  void monitor_xid(long xid) {
+    if (std::find(std::begin(kMonitorXids), std::end(kMonitorXids), xid) == std::end(kMonitorXids)) return;
+    json::Value n;
+    if (!fetch(&n, "to record the XID condition")) return;
+    json::Value& conds = n.at("status").at("conditions");
+    if (conds.kind != json::Value::Array) conds = json::Value::array();
+    const std::string key = std::to_string(xid);
+    bool found = false;
+    for (auto& c : conds.arr) {
+      if (c.get_string("type") != kXidCondition) continue;
+      found = true;
+      json::Value reason; std::string err, text = c.get_string("reason");
+      if (text.empty()) text = "{}";
+      if (!json::Parser(text).parse(&reason, &err) || reason.kind != json::Value::Object) { LOGE("Can't decode the value of condition.Reason %s", text.c_str()); return; }
+      if (reason.get(key)) { LOGI("XIDCriticalError condition already includes this XID %ld, skip", xid); return; }
+      reason.at(key) = json::Value::of(true);
+      c.at("reason") = json::Value::of(json::dump(reason));
+    }
+    if (!found) {
+      const std::string now = kube::now_rfc3339();
+      json::Value reason = json::Value::object(); reason.at(key) = json::Value::of(true);
+      json::Value c = json::Value::object();
+      c.at("type") = json::Value::of(kXidCondition); c.at("status") = json::Value::of("True");
+      c.at("lastHeartbeatTime") = json::Value::of(now); c.at("lastTransitionTime") = json::Value::of(now);
+      c.at("reason") = json::Value::of(json::dump(reason)); c.at("message") = json::Value::of(boot_id(n));
+      conds.arr.push_back(c);
+    }
+    if (put(n, "to add the XIDCriticalError condition")) LOGI("Successfully add XIDCriticalError condition on node %s.", node.c_str());
+  }
+  void heartbeat() {
+    json::Value n;
+    if (!fetch(&n, "for heartbeat update")) return;
+    json::Value* conds = n.at("status").find("conditions");
+    bool modified = false;
+    if (conds && conds->kind == json::Value::Array)
+      for (auto& c : conds->arr)
+        if (c.get_string("type") == kXidCondition && c.get_string("status") == "True") { c.at("lastHeartbeatTime") = json::Value::of(kube::now_rfc3339()); modified = true; }
+    if (modified) put(n, "to update the XIDCondition heartbeat");
+  }
+  void record_event(long xid) {
+    json::Value n;
+    if (!fetch(&n, "to record the XID event")) return;
+    json::Value* meta = n.find("metadata");
+    kube::Response r = api.create_node_event(node, meta ? meta->get_string("uid") : "", "Warning", "XIDError", "Caught XID error, XID=" + std::to_string(xid), kEventSource);
+    if (!r.ok()) LOGE("Failed to record XID=%ld for node %s with err %s", xid, node.c_str(), r.describe().c_str());
+  }
+};
+
+void health_loop(Manager* ngm, NodeStatus* ns, double heartbeat_s, std::atomic<bool>* stop) {
   std::set<long> critical(ngm->cfg.xids.begin(), ngm->cfg.xids.end());
   critical.insert(48);                                   // double-bit ECC is always health-critical
+  std::vector<std::thread> helpers;
+  if (ns) {
+    helpers.emplace_back([ns, stop] { ns->reset_condition_with_backoff(stop); });
+    helpers.emplace_back([ns, stop, heartbeat_s] {
+      while (!*stop) { ns->heartbeat(); for (double t = 0; t < heartbeat_s && !*stop; t += 0.1) usleep(100000); }
+    });
+  }
+  struct Join { std::vector<std::thread>* t; ~Join() { for (auto& x : *t) x.join(); } } join{&helpers};
   void* set = nullptr;
   if (b200nvml_events_open(&set) != 0) { LOGE("failed to create NVML event set: %s", b200nvml_last_error()); return; }
   for (auto& kv : ngm->index_of) {
@@ -432,6 +559,7 @@ void health_loop(Manager* ngm, std::atomic<bool>* stop) {
     int rc = b200nvml_events_wait(set, 1000, &ev);
     if (rc != 0) continue;                               // timeout or transient error
     if (ev.event_type != 8) { LOGI("Skip error Xid=%llu as it is not Xid Critical", ev.event_data); continue; }
+    if (ns) { ns->record_event((long)ev.event_data); ns->monitor_xid((long)ev.event_data); }
     if (!critical.count((long)ev.event_data)) { LOGI("Health checker is skipping Xid %llu error", ev.event_data); continue; }
     auto phys = ngm->list_physical();
     if (!ev.uuid[0]) { LOGE("XidCriticalError: Xid=%llu, All devices will go unhealthy.", ev.event_data); for (auto& kv : phys) ngm->report_unhealthy(kv.first); continue; }
@@ -449,6 +577,29 @@ void health_loop(Manager* ngm, std::atomic<bool>* stop) {
     if (!found) LOGE("XidCriticalError: Xid=%llu on unknown device.", ev.event_data);
   }
   b200nvml_events_close(set);
+}
+
+// ------------------------------------------------------------------------------------------------ driver version annotations
+// "570.124.06" -> cloud.google.com/cuda.driver-version.{major,minor,revision,full}; two-part versions leave revision empty.
+bool parse_driver_annotations(const std::string& version, std::map<std::string, std::string>* out) {
+  std::vector<std::string> parts; std::string cur;
+  for (char ch : version) { if (ch == '.') { parts.push_back(cur); cur.clear(); } else cur.push_back(ch); }
+  parts.push_back(cur);
+  if (parts.size() < 2 || parts.size() > 3) return false;
+  for (auto& p : parts) if (p.empty() || !std::all_of(p.begin(), p.end(), [](char ch) { return ch >= '0' && ch <= '9'; })) return false;
+  const std::string pre = "cloud.google.com/cuda.driver-version.";
+  (*out)[pre + "major"] = parts[0]; (*out)[pre + "minor"] = parts[1]; (*out)[pre + "revision"] = parts.size() == 3 ? parts[2] : ""; (*out)[pre + "full"] = version;
+  return true;
+}
+
+void publish_driver_version(NodeStatus* ns) {
+  char v[96] = "";
+  if (b200nvml_driver_version(v, sizeof v) != 0) { LOGE("failed to read the driver version: %s", b200nvml_last_error()); return; }
+  std::map<std::string, std::string> ann;
+  if (!parse_driver_annotations(v, &ann)) { LOGE("failed to publish driver version annotations: unexpected driver version format: %s", v); return; }
+  kube::Response r = ns->api.apply_node_annotations(ns->node, ann, "gpu-device-plugin", true);
+  if (!r.ok()) { LOGE("failed to publish driver version annotations: %s", r.describe().c_str()); return; }
+  LOGI("published driver version %s on node %s", v, ns->node.c_str());
 }
 
 // ------------------------------------------------------------------------------------------------ metrics
@@ -575,7 +726,8 @@ int serve(Manager* ngm, const std::string& plugin_dir, const std::string& kubele
 int main(int argc, char** argv) {
   std::string host_path = "/home/kubernetes/bin/nvidia", container_path = "/usr/local/nvidia", host_vulkan = "/home/kubernetes/bin/nvidia/vulkan/icd.d", container_vulkan = "/etc/vulkan/icd.d",
               plugin_dir = "/device-plugin", gpu_config = "/etc/nvidia/gpu_config.json", plugin_endpoint, pod_resources = "/var/lib/kubelet/pod-resources/kubelet.sock";
-  bool enable_metrics = false, enable_health = false;
+  bool enable_metrics = false, enable_health = false, publish_version = false;
+  double xid_heartbeat_s = 60.0;
   int metrics_port = 2112, metrics_interval = 30000;
   Manager ngm;
   for (int i = 1; i < argc; i++) {
@@ -595,7 +747,8 @@ int main(int argc, char** argv) {
     else if (a == "gpu-metrics-collection-interval") metrics_interval = atoi(need().c_str());
     else if (a == "enable-container-gpu-metrics") enable_metrics = !has || val != "false";
     else if (a == "enable-health-monitoring") enable_health = !has || val != "false";
-    else if (a == "publish-driver-version") { /* needs the Kubernetes API: handled by the Python agent */ }
+    else if (a == "publish-driver-version") publish_version = !has || val != "false";
+    else if (a == "xid-heartbeat-interval") xid_heartbeat_s = atof(need().c_str());
     else if (a == "dev-directory") ngm.dev_dir = need();
     else if (a == "proc-directory") ngm.proc_dir = need();
     else if (a == "pci-root") ngm.pci_root = need();
@@ -624,7 +777,16 @@ int main(int argc, char** argv) {
     if (!ngm.cfg.partition_size.empty()) LOGI("metrics are disabled when MIG partitioning is on");
     else { LOGI("Starting metrics server on port: %d, collection interval: %d", metrics_port, metrics_interval); side.emplace_back(metrics_server, &ngm, metrics_port, metrics_interval, pod_resources, &g_stop); }
   }
-  if (enable_health) side.emplace_back(health_loop, &ngm, &g_stop);
+  NodeStatus node_status;
+  bool have_kube = false;
+  if (enable_health || publish_version) {
+    node_status.node = node_name();
+    std::string why = kube::Client::from_env(&node_status.api);
+    have_kube = why.empty();
+    if (!have_kube) LOGE("failed to build kube client: %s; Xid Events, the Node condition and driver-version annotations are disabled", why.c_str());
+  }
+  if (enable_health) side.emplace_back(health_loop, &ngm, have_kube ? &node_status : nullptr, xid_heartbeat_s, &g_stop);
+  if (publish_version && have_kube) side.emplace_back(publish_driver_version, &node_status);
   if (plugin_endpoint.empty()) plugin_endpoint = "nvidiaGPU-" + std::to_string((long)time(nullptr)) + ".sock";
   int rc = serve(&ngm, plugin_dir, "kubelet.sock", plugin_endpoint);
   g_stop = true;

@@ -57,7 +57,13 @@ struct Grid { int blocks, threads; };
 // Every kernel goes through cudaLaunchKernelEx so that back-to-back collectives can use programmatic dependent launch
 // (B200COLL_PDL=1): the next kernel's launch latency overlaps the current kernel's execution; each kernel starts with
 // griddepcontrol.launch_dependents + griddepcontrol.wait, so it still observes its predecessor's completed memory.
-static bool pdl_enabled() { static const bool on = [] { const char* e = getenv("B200COLL_PDL"); return e && *e && *e != '0'; }(); return on; }
+// Never with virtual ranks (several communicators on one GPU): a pre-launched dependent grid parks its CTAs on SMs
+// that another rank's current kernel still needs, and ranks that spin on each other then deadlock (seen at 1 MiB with
+// 4 ranks on one B200). With one rank per GPU every CTA of kernel i is resident before kernel i+1 may start.
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B200COLL_PDL"); return e && *e && *e != '0'; }();
+  return on && g_loopback_comms.load(std::memory_order_relaxed) == 0;
+}
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -221,12 +221,16 @@ static void finalize_comm(b200collComm* c) {
   }
   stats_page_open(c);
   stats_page_publish(c);
+  if (c->loopback) { c->loopback_counted = true; g_loopback_comms.fetch_add(1); }
   dbg(1, "rank %d/%d dev %d arena %zu MiB nvls=%d loopback=%d max_ctas=%d", c->rank, c->nranks, c->device, c->arena.total >> 20, (int)c->nvls,
       (int)c->loopback, c->max_ctas);
 }
 
+std::atomic<int> g_loopback_comms{0};
+
 static void destroy_resources(b200collComm* c) {
   const Drv& d = drv();
+  if (c->loopback_counted) { c->loopback_counted = false; g_loopback_comms.fetch_sub(1); }
   if (c->mc_va) { unmap_va(c->mc_va, c->arena.total); c->mc_va = 0; }
   if (c->mc_bound && c->mc_handle) {
     CUdevice dev;

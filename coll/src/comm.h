@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -45,6 +46,8 @@ struct Arena {
   int device = -1;
 };
 
+extern std::atomic<int> g_loopback_comms;   // live communicators whose ranks share a GPU (virtual ranks): PDL stays off
+
 struct SharedGroup;   // in-process groups (InitAll) share ownership bookkeeping
 
 }  // namespace b200coll
@@ -59,7 +62,7 @@ struct b200collComm {
   CUdeviceptr mc_va = 0;
   CUmemGenericAllocationHandle mc_handle = 0;
   bool mc_owned = false, mc_bound = false;
-  bool nvls = false, loopback = false;
+  bool nvls = false, loopback = false, loopback_counted = false;
   int sm_count = 0, driver_version = 0;
   uint32_t* state_dev = nullptr;
   b200collFault* fault_host = nullptr;

@@ -112,6 +112,7 @@ class FakeKubeApi:
         self.pods: dict = {}        # (ns, name) -> pod
         self.events: list = []
         self.requests: list = []    # (method, path, content-type)
+        self.bearer_tokens: list = []
         self.fail_next_gets = 0
         self._srv = None
         self.url = ""
@@ -126,7 +127,8 @@ class FakeKubeApi:
     def add_pod(self, pod: dict) -> None:
         self.pods[(pod["metadata"].get("namespace", "default"), pod["metadata"]["name"])] = pod
 
-    def start(self) -> "FakeKubeApi":
+    def start(self, tls_cert: str = "", tls_key: str = "") -> "FakeKubeApi":
+        """Plain HTTP by default; with a certificate/key pair the same server speaks HTTPS (TLS path of the native client)."""
         api = self
 
         class H(BaseHTTPRequestHandler):
@@ -146,6 +148,7 @@ class FakeKubeApi:
                 u = urlparse(self.path)
                 q = parse_qs(u.query)
                 api.requests.append((method, u.path, self.headers.get("Content-Type", "")))
+                api.bearer_tokens.append(self.headers.get("Authorization", ""))
                 m = _re.fullmatch(r"/api/v1/nodes/([^/]+)(/status)?", u.path)
                 if m:
                     name, status = m.group(1), bool(m.group(2))
@@ -208,13 +211,44 @@ class FakeKubeApi:
             def do_PATCH(self): self._route("PATCH")
 
         self._srv = ThreadingHTTPServer(("127.0.0.1", 0), H)
-        self.url = f"http://127.0.0.1:{self._srv.server_address[1]}"
+        scheme = "http"
+        if tls_cert:
+            import ssl
+            ctx = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
+            ctx.load_cert_chain(tls_cert, tls_key)
+            self._srv.socket = ctx.wrap_socket(self._srv.socket, server_side=True)
+            scheme = "https"
+        self.url = f"{scheme}://127.0.0.1:{self._srv.server_address[1]}"
         threading.Thread(target=self._srv.serve_forever, daemon=True).start()
         return self
 
     def stop(self) -> None:
         if self._srv:
             self._srv.shutdown(); self._srv.server_close(); self._srv = None
+
+
+def make_self_signed_cert(directory: str, ip: str = "127.0.0.1", dns: str = "localhost"):
+    """(cert.pem, key.pem) for a throwaway CA-less server certificate with IP and DNS subject-alt-names."""
+    import datetime
+    import ipaddress
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import ec
+    from cryptography.x509.oid import NameOID
+    key = ec.generate_private_key(ec.SECP256R1())
+    name = x509.Name([x509.NameAttribute(NameOID.COMMON_NAME, "fake-kube-apiserver")])
+    now = datetime.datetime.now(datetime.timezone.utc)
+    cert = (x509.CertificateBuilder().subject_name(name).issuer_name(name).public_key(key.public_key()).serial_number(x509.random_serial_number())
+            .not_valid_before(now - datetime.timedelta(minutes=5)).not_valid_after(now + datetime.timedelta(days=1))
+            .add_extension(x509.SubjectAlternativeName([x509.IPAddress(ipaddress.ip_address(ip)), x509.DNSName(dns)]), critical=False)
+            .add_extension(x509.BasicConstraints(ca=True, path_length=None), critical=True)
+            .sign(key, hashes.SHA256()))
+    cert_path, key_path = os.path.join(directory, "cert.pem"), os.path.join(directory, "key.pem")
+    with open(cert_path, "wb") as f:
+        f.write(cert.public_bytes(serialization.Encoding.PEM))
+    with open(key_path, "wb") as f:
+        f.write(key.private_bytes(serialization.Encoding.PEM, serialization.PrivateFormat.TraditionalOpenSSL, serialization.NoEncryption()))
+    return cert_path, key_path
 
 
 # ------------------------------------------------------------------------------------------------- fake NRI runtime

@@ -169,17 +169,15 @@ def device_plugin_ds(*, name="b200-gpu-device-plugin", health=True, metrics=True
 
 
 def device_plugin_native_ds() -> dict:
-    """Native variant: the C++ binary owns the kubelet socket, metrics and Unhealthy marking; a small Python sidecar in
-    --status-only mode publishes the Kubernetes-side status (Events, Node condition, driver-version annotations)."""
+    """Native variant: one C++ binary owns the kubelet socket, metrics, Unhealthy marking and the Kubernetes-side status
+    (Xid Events, the XidCriticalError Node condition, driver-version annotations; agent/native/dp/kube.hpp). No Python in the pod."""
     ds = device_plugin_ds(name="b200-gpu-device-plugin-native")
     spec = ds["spec"]["template"]["spec"]
-    py = spec["containers"][0]
-    native = copy.deepcopy(py)
+    native = spec["containers"][0]
     native.update({"name": "b200-device-plugin", "image": IMG["device-plugin-native"],
-                   "command": ["/usr/bin/b200-device-plugin", "-logtostderr", "-enable-container-gpu-metrics", "-enable-health-monitoring"], "resources": {"requests": {"cpu": "50m", "memory": "20Mi"}, "limits": {"memory": "100Mi"}}})
-    py.update({"name": "node-status", "command": ["python", "-m", "container_engine_accelerators_b200.agent.main", "--status-only", "--enable-health-monitoring", "--publish-driver-version"]})
-    py.pop("ports", None)
-    spec["containers"] = [native, py]
+                   "command": ["/usr/bin/b200-device-plugin", "-logtostderr", "-enable-container-gpu-metrics", "-enable-health-monitoring", "-publish-driver-version"],
+                   "resources": {"requests": {"cpu": "50m", "memory": "20Mi"}, "limits": {"memory": "100Mi"}}})
+    spec["containers"] = [native]
     return ds
 
 

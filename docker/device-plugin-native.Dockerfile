@@ -6,4 +6,5 @@ COPY third_party/nvml/nvml.h /usr/local/include/nvml.h
 RUN g++ -O2 -std=c++17 -static-libstdc++ -static-libgcc -I/usr/local/include /src/dp/device_plugin.cc /src/b200agent_nvml.cc -o /b200-device-plugin -ldl -lpthread
 FROM gcr.io/distroless/base
 COPY --from=build /b200-device-plugin /usr/bin/b200-device-plugin
-CMD ["/usr/bin/b200-device-plugin", "-logtostderr", "-enable-container-gpu-metrics", "-enable-health-monitoring"]
+# distroless/base ships libssl/libcrypto, which the Kubernetes API client dlopens for https (agent/native/dp/kube.hpp).
+CMD ["/usr/bin/b200-device-plugin", "-logtostderr", "-enable-container-gpu-metrics", "-enable-health-monitoring", "-publish-driver-version"]

@@ -207,3 +207,148 @@ def test_metrics_endpoint(native, tmp_path):
         assert 'memory_total_gpu_node{make="nvidia",accelerator_id="GPU-fake-1",model="NVIDIA B200"} ' in body
     finally:
         stub.server.stop(0)
+
+
+# ------------------------------------------------------------------------------------------------- Kubernetes side effects
+def _wait(pred, timeout=10.0, what=""):
+    deadline = time.time() + timeout
+    while time.time() < deadline:
+        if pred():
+            return
+        time.sleep(0.05)
+    raise AssertionError(f"timed out waiting for {what}")
+
+
+def _xid_condition(api, node="node-a"):
+    return next((c for c in api.nodes[node]["status"]["conditions"] if c["type"] == "XidCriticalError"), None)
+
+
+def test_xid_event_condition_and_heartbeat_through_kube_api(native, tmp_path):
+    """health_check/health_checker.go:288-358,395-449: Event per critical Xid, Node condition whose reason is the JSON set
+    of Xids and whose message is the boot id, heartbeat refresh; non-monitored Xids only produce the Event."""
+    api = testing.FakeKubeApi().start()
+    try:
+        api.add_node("node-a", boot_id="boot-7")
+        events = tmp_path / "events.txt"; events.write_text("")
+        n = native(extra_args=["-enable-health-monitoring", "--xid-heartbeat-interval", "0.2"],
+                   env={"FAKE_NVML_EVENTS": str(events), "B200_KUBE_URL": api.url, "NODE_NAME": "node-a", "XID_CONFIG": "31"})
+        c = n.connect()
+        stream = c.list_and_watch(); next(stream)
+        time.sleep(0.5)
+        events.write_text("0 79\n")                       # monitored (condition) but not health-critical here
+        _wait(lambda: _xid_condition(api) is not None, what="XidCriticalError condition")
+        cond = _xid_condition(api)
+        assert cond["status"] == "True" and json.loads(cond["reason"]) == {"79": True} and cond["message"] == "boot-7"
+        assert [e["message"] for e in api.events] == ["Caught XID error, XID=79"]
+        ev = api.events[0]
+        assert ev["involvedObject"] == {"kind": "Node", "name": "node-a", "uid": "uid-node-a", "apiVersion": "v1"}
+        assert ev["type"] == "Warning" and ev["reason"] == "XIDError" and ev["source"] == {"component": "nvidia-gpu-device-plugin"}
+        assert api.nodes["node-a"]["status"]["nodeInfo"]["bootID"] == "boot-7"          # the rest of the status survived the round trip
+        assert any(c2["type"] == "Ready" for c2 in api.nodes["node-a"]["status"]["conditions"])
+        first_beat = cond["lastHeartbeatTime"]
+        with open(events, "a") as f:                      # the fake NVML reads the file as an append-only log
+            f.write("0 79\n1 48\n1 31\n")                # 79 again (dedup), 48 (always critical + monitored), 31 (critical via XID_CONFIG, not monitored)
+        assert {d.ID: d.health for d in next(stream).devices} == {"nvidia0": "Healthy", "nvidia1": "Unhealthy"}
+        _wait(lambda: len(api.events) == 4, what="4 events")
+        _wait(lambda: json.loads(_xid_condition(api)["reason"]) == {"48": True, "79": True}, what="reason set {48,79}")
+        assert "already includes this XID 79" in n.logs()
+        time.sleep(1.3)                                   # RFC 3339 stamps have 1 s resolution
+        _wait(lambda: _xid_condition(api)["lastHeartbeatTime"] > first_beat, timeout=5, what="heartbeat refresh")
+        assert ("PUT", "/api/v1/nodes/node-a/status", "application/json") in api.requests
+        stream.cancel()
+    finally:
+        api.stop()
+
+
+def test_stale_xid_condition_is_cleared_after_reboot_and_kept_otherwise(native, tmp_path):
+    """health_checker.go:129-160: boot id differs from the one recorded in the condition -> repaired -> remove it."""
+    api = testing.FakeKubeApi().start()
+    try:
+        stale = {"type": "XidCriticalError", "status": "True", "reason": "{\"48\":true}", "message": "boot-old"}
+        api.add_node("node-a", boot_id="boot-new", conditions=[{"type": "Ready", "status": "True"}, dict(stale)])
+        api.add_node("node-b", boot_id="boot-old", conditions=[{"type": "Ready", "status": "True"}, dict(stale)])
+        api.fail_next_gets = 1                            # first GET fails: the reset retries with backoff
+        n = native(extra_args=["-enable-health-monitoring"], env={"B200_KUBE_URL": api.url, "NODE_NAME": "node-a"})
+        n.connect()
+        _wait(lambda: _xid_condition(api, "node-a") is None, timeout=8, what="stale condition removal")
+        _wait(lambda: "Successfully removed XIDCriticalError condition from node node-a." in n.logs(), what="removal log line")
+        assert [c["type"] for c in api.nodes["node-a"]["status"]["conditions"]] == ["Ready"]
+        n.close()
+        n2 = Native(tmp_path / "b", os.path.dirname(n.proc_handle.args[0]), extra_args=["-enable-health-monitoring"], env={"B200_KUBE_URL": api.url, "NODE_NAME": "node-b"})
+        try:
+            n2.connect()
+            _wait(lambda: "XIDCriticalError condition doesn't exist for node node-b." in n2.logs(), what="no-op reset")
+            assert _xid_condition(api, "node-b") is not None      # same boot: the fault is still current
+        finally:
+            n2.close()
+    finally:
+        api.stop()
+
+
+def test_driver_version_annotations_by_server_side_apply(native):
+    """version_visibility.go:38-86: four annotations, apply patch with fieldManager gpu-device-plugin and force."""
+    api = testing.FakeKubeApi().start()
+    try:
+        api.add_node("node-a", annotations={"keep": "me"})
+        n = native(extra_args=["--publish-driver-version"], env={"B200_KUBE_URL": api.url, "NODE_NAME": "node-a", "FAKE_NVML_DRIVER": "570.124.06"})
+        n.connect()
+        _wait(lambda: "cloud.google.com/cuda.driver-version.full" in api.nodes["node-a"]["metadata"]["annotations"], what="annotations")
+        ann = api.nodes["node-a"]["metadata"]["annotations"]
+        assert ann == {"keep": "me", "cloud.google.com/cuda.driver-version.major": "570", "cloud.google.com/cuda.driver-version.minor": "124",
+                       "cloud.google.com/cuda.driver-version.revision": "06", "cloud.google.com/cuda.driver-version.full": "570.124.06"}
+        assert ("PATCH", "/api/v1/nodes/node-a", "application/apply-patch+yaml") in api.requests
+    finally:
+        api.stop()
+
+
+def test_malformed_driver_version_is_not_published(native):
+    api = testing.FakeKubeApi().start()
+    try:
+        api.add_node("node-a")
+        n = native(extra_args=["--publish-driver-version"], env={"B200_KUBE_URL": api.url, "NODE_NAME": "node-a", "FAKE_NVML_DRIVER": "570.x"})
+        n.connect()
+        _wait(lambda: "unexpected driver version format: 570.x" in n.logs(), what="format error")
+        assert api.nodes["node-a"]["metadata"]["annotations"] == {}
+    finally:
+        api.stop()
+
+
+def test_kube_client_over_tls_verifies_the_server(native, tmp_path):
+    """The in-cluster path: https + bearer token + CA bundle. A certificate the CA bundle does not cover must be refused."""
+    certs = tmp_path / "pki"; certs.mkdir()
+    cert, key = testing.make_self_signed_cert(str(certs))
+    other = tmp_path / "other"; other.mkdir()
+    other_cert, _ = testing.make_self_signed_cert(str(other))
+    token = tmp_path / "token"; token.write_text("s3cr3t\n")
+    api = testing.FakeKubeApi().start(tls_cert=cert, tls_key=key)
+    try:
+        assert api.url.startswith("https://")
+        api.add_node("node-a")
+        env = {"B200_KUBE_URL": api.url, "B200_KUBE_TOKEN_FILE": str(token), "NODE_NAME": "node-a", "FAKE_NVML_DRIVER": "580.159.03"}
+        n = native(extra_args=["--publish-driver-version"], env={**env, "B200_KUBE_CA_FILE": cert})
+        n.connect()
+        _wait(lambda: api.nodes["node-a"]["metadata"]["annotations"].get("cloud.google.com/cuda.driver-version.major") == "580", what="annotations over TLS")
+        assert api.bearer_tokens[-1] == "Bearer s3cr3t"
+        n.close()
+        api.nodes["node-a"]["metadata"]["annotations"].clear()
+        n2 = Native(tmp_path / "b", os.path.dirname(n.proc_handle.args[0]), extra_args=["--publish-driver-version"], env={**env, "B200_KUBE_CA_FILE": other_cert})
+        try:
+            n2.connect()
+            _wait(lambda: "TLS handshake with 127.0.0.1 failed" in n2.logs(), what="handshake refusal")
+            assert api.nodes["node-a"]["metadata"]["annotations"] == {}
+        finally:
+            n2.close()
+    finally:
+        api.stop()
+
+
+def test_health_monitoring_without_a_cluster_still_reports_devices(native, tmp_path):
+    events = tmp_path / "events.txt"; events.write_text("")
+    n = native(extra_args=["-enable-health-monitoring"], env={"FAKE_NVML_EVENTS": str(events), "KUBERNETES_SERVICE_HOST": "", "B200_KUBE_URL": ""})
+    c = n.connect()
+    stream = c.list_and_watch(); next(stream)
+    time.sleep(0.5)
+    events.write_text("0 48\n")
+    assert {d.ID: d.health for d in next(stream).devices} == {"nvidia0": "Unhealthy", "nvidia1": "Healthy"}
+    assert "failed to build kube client: not running in a cluster" in n.logs()
+    stream.cancel()
