@@ -61,7 +61,9 @@ typedef enum {
   b200collOpAllGather = 1,
   b200collOpReduceScatter = 2,
   b200collOpAllToAll = 3,
-  b200collNumOps = 4
+  b200collOpBroadcast = 4,
+  b200collOpReduce = 5,
+  b200collNumOps = 6
 } b200collOp_t;
 
 /* Algorithm ids (tuner output; B200COLL_ALGO overrides). */
@@ -164,6 +166,13 @@ b200collResult_t b200collAllToAll(const void* send, void* recv, size_t count, co
 b200collResult_t b200collAllToAllv(const void* send, void* recv, size_t row_elems, const int64_t* send_rows,
                                    const int64_t* send_row_off, const int64_t* recv_row_off_at_peer,
                                    const b200collEpilogue* ep, b200collComm_t comm, b200collStream_t stream);
+/* Rooted collectives (ncclBroadcast / ncclReduce). Broadcast: root's send -> every rank's recv (cast/scale fused);
+ * send is read on the root only. Reduce: root's recv = scale * sum over ranks of send; recv is written on the root only.
+ * Ranks that do not use a buffer may pass any 16-byte aligned device pointer for it. */
+b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, const b200collEpilogue* ep, int root,
+                                   b200collComm_t comm, b200collStream_t stream);
+b200collResult_t b200collReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep,
+                                b200collRedOp_t op, int root, b200collComm_t comm, b200collStream_t stream);
 b200collResult_t b200collBarrier(b200collComm_t comm, b200collStream_t stream);
 
 /* --- tuner (libnccl-tuner.so analogue). */

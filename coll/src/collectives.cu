@@ -117,7 +117,7 @@ static void account(b200collComm* c, b200collOp_t op, size_t bytes, b200collAlgo
   c->stats.calls[op]++; c->stats.bytes[op] += bytes; c->stats.algo_calls[algo]++;
   static const bool nvtx = [] { const char* e = getenv("B200COLL_NVTX"); return e && *e && *e != '0'; }();
   if (nvtx || debug_level() >= 2) {
-    static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall"};
+    static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce"};
     char msg[96];
     snprintf(msg, sizeof(msg), "b200coll %s %s %zu B", kOps[op], b200collAlgoName(algo), bytes);
     if (nvtx) nvtxMarkA(msg);
@@ -459,6 +459,84 @@ b200collResult_t b200collAllToAllv(const void* send, void* recv, size_t row_elem
   a2av_prefix(c, nv, &a);
   account(c, b200collOpAllToAll, total_bytes, b200collAlgoTwoShot);
   return a2av_launch(c, send, recv, a, ep, st);
+}
+
+b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, const b200collEpilogue* ep, int root, b200collComm_t c, b200collStream_t stream) {
+  // send is only read on the root; other ranks may pass any aligned non-null pointer (their recv is the usual choice).
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (root < 0 || root >= c->nranks) { set_last_error("broadcast root out of range"); return b200collInvalidArgument; }
+  if (count == 0) return b200collSuccess;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const float scale = ep->scale;
+  if (c->nranks == 1) { account(c, b200collOpBroadcast, count * is, b200collAlgoCopy); return copy_scale(c, send, recv, count, ep, scale, st); }
+  if (send == recv && is != os) { set_last_error("in-place broadcast needs in_dtype and out_dtype of equal size"); return b200collInvalidArgument; }
+  b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpBroadcast, count * is, c->nranks, c->nvls);
+  if (algo != b200collAlgoNvls || !c->nvls) algo = b200collAlgoTwoShot;     // two families only: multimem.st or P2P push
+  const int identity = (ep->in_dtype == ep->out_dtype && scale == 1.0f) ? 1 : 0;
+  auto push = [&](const void* s, void* r_sym, size_t n) -> b200collResult_t {
+    account(c, b200collOpBroadcast, n * is, algo);
+    return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+      using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvls : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), 4);
+      if (algo == b200collAlgoNvls) launch_k(k_bcast<InT, OutT, true>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(s), arena_off(c, r_sym), n, scale, identity, root, b200collOpBroadcast);
+      else launch_k(k_bcast<InT, OutT, false>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(s), arena_off(c, r_sym), n, scale, identity, root, b200collOpBroadcast);
+      LAUNCH_CHECK(c);
+      return b200collSuccess;
+    });
+  };
+  if (b200collIsSymmetric(c, recv, count * os)) return push(send, recv, count);
+  // staged: the root pushes a chunk into everybody's staging half 1, each rank copies it out locally
+  c->stats.staged_calls++;
+  const size_t chunk = std::min(kStageHalfBytes / is, kStageHalfBytes / os) / 64 * 64;
+  for (size_t done = 0; done < count; done += chunk) {
+    const size_t n = std::min(chunk, count - done);
+    rc = push(static_cast<const char*>(send) + done * is, stage_ptr(c, 1), n);
+    if (rc != b200collSuccess) return rc;
+    cudaError_t e = cudaMemcpyAsync(static_cast<char*>(recv) + done * os, stage_ptr(c, 1), n * os, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+  }
+  return b200collSuccess;
+}
+
+b200collResult_t b200collReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep, b200collRedOp_t rop, int root, b200collComm_t c, b200collStream_t stream) {
+  // recv is only written on the root; other ranks may pass any aligned non-null pointer.
+  b200collResult_t rc = check_common(c, send, recv, ep);
+  if (rc != b200collSuccess) return rc;
+  if (root < 0 || root >= c->nranks) { set_last_error("reduce root out of range"); return b200collInvalidArgument; }
+  if (count == 0) return b200collSuccess;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
+  const float scale = ep->scale * (rop == b200collAvg ? 1.0f / (float)c->nranks : 1.0f);
+  if (c->nranks == 1) { account(c, b200collOpReduce, count * is, b200collAlgoCopy); return copy_scale(c, send, recv, count, ep, scale, st); }
+  if (send == recv && is != os) { set_last_error("in-place reduce needs in_dtype and out_dtype of equal size"); return b200collInvalidArgument; }
+  b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpReduce, count * is, c->nranks, c->nvls);
+  if (algo != b200collAlgoNvls || !c->nvls) algo = b200collAlgoTwoShot;     // multimem.ld_reduce by the root, or the root pulls from every peer
+  auto pull = [&](const void* s_sym, void* r, size_t n) -> b200collResult_t {
+    account(c, b200collOpReduce, n * is, algo);
+    return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
+      using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvlsRs : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), 2);
+      if (c->rank != root) launch_k(k_sync_only, g.blocks, g.threads, st, c->dev, (uint32_t)b200collOpReduce);
+      else if (algo == b200collAlgoNvls) launch_k(k_pull_reduce<InT, OutT, false, true>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, b200collOpReduce);
+      else launch_k(k_pull_reduce<InT, OutT, false, false>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, b200collOpReduce);
+      LAUNCH_CHECK(c);
+      return b200collSuccess;
+    });
+  };
+  if (b200collIsSymmetric(c, send, count * is)) return pull(send, recv, count);
+  // staged: every rank copies a chunk of its send buffer into staging half 0, the root reduces the chunk into recv
+  c->stats.staged_calls++;
+  const size_t chunk = std::min(kStageHalfBytes / is, kStageHalfBytes / os) / 64 * 64;
+  for (size_t done = 0; done < count; done += chunk) {
+    const size_t n = std::min(chunk, count - done);
+    cudaError_t e = cudaMemcpyAsync(stage_ptr(c, 0), static_cast<const char*>(send) + done * is, n * is, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+    rc = pull(stage_ptr(c, 0), static_cast<char*>(recv) + done * os, n);
+    if (rc != b200collSuccess) return rc;
+  }
+  return b200collSuccess;
 }
 
 b200collResult_t b200collBarrier(b200collComm_t c, b200collStream_t stream) {

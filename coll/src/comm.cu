@@ -170,11 +170,12 @@ static void stats_page_open(b200collComm* c) {
   c->stats_shm = p; c->stats_shm_name = name;
 }
 
+// Page layout: 64-byte header, then b200collStats. version 1 had 4 ops (17 counters), version 2 has 6 (21 counters).
 static void stats_page_publish(b200collComm* c) {
   if (!c->stats_shm) return;
   struct Header { char magic[8]; uint32_t version, pid, rank, nranks, device, nvls; } h = {};
   memcpy(h.magic, "B200COLL", 8);
-  h.version = 1; h.pid = (uint32_t)getpid(); h.rank = c->rank; h.nranks = c->nranks; h.device = c->device; h.nvls = c->nvls;
+  h.version = 2; h.pid = (uint32_t)getpid(); h.rank = c->rank; h.nranks = c->nranks; h.device = c->device; h.nvls = c->nvls;
   memcpy(c->stats_shm, &h, sizeof(h));
   memcpy(static_cast<char*>(c->stats_shm) + 64, &c->stats, sizeof(c->stats));
 }

@@ -9,6 +9,8 @@
 //   k_ar_nvls         NVLS all-reduce              multimem.ld_reduce own slice -> scale/cast -> multimem.st
 //   k_ag_push         all-gather                   P2P push or one multimem.st per vector
 //   k_a2av_push       all-to-all(v)                per-peer row ranges, flattened for load balance
+//   k_bcast           broadcast                    root pushes (P2P or one multimem.st per vector); the others only synchronise
+//   k_sync_only       reduce (non-root ranks)      the two barriers of k_pull_reduce, which the root runs over the whole buffer
 //   k_barrier
 #pragma once
 #include "device.cuh"
@@ -550,6 +552,79 @@ __global__ void __launch_bounds__(kThreads) k_a2av_push(CommDev c, const InT* __
       }
     }
   }
+  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Broadcast: the root's `count` elements land at out_off of every rank (its own copy included, so in-place and
+// out-of-place behave the same). MC: one multimem.st per vector -> root egress S instead of S(N-1).
+// Every rank launches the same grid; non-root CTAs only take part in the two barriers.
+template <typename InT, typename OutT, bool MC>
+__global__ void __launch_bounds__(kThreads) k_bcast(CommDev c, const InT* __restrict__ in, size_t out_off, size_t count, float scale, int identity, int root, uint32_t op) {
+  pdl_prologue();
+  constexpr int E = Epv<InT>::value;
+  constexpr int W = Pack<OutT, E>::W;
+  constexpr int U = 4;
+  const uint32_t s = load_seq(c, kSeqBarrier);
+  barrier_blocks<false>(c, 2 * s + 1, op);          // every rank is done with the previous contents of its out
+  if (c.rank == root) {
+    const size_t nvec = count / E;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
+      uint4 d[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { const size_t v = base + (size_t)u * blockDim.x; if (v < nvec) d[u] = ld_vec(in + v * E); }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t v = base + (size_t)u * blockDim.x;
+        if (v < nvec) {
+          uint32_t w[W];
+          if (identity) {
+            const uint32_t raw[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+            for (int i = 0; i < W && i < 4; i++) w[i] = raw[i];
+          } else {
+            float acc[E] = {};
+            unpack_add<InT>(acc, d[u]);
+#pragma unroll
+            for (int i = 0; i < E; i++) acc[i] *= scale;
+            Pack<OutT, E>::run(acc, w);
+          }
+          const size_t off = out_off + v * (E * sizeof(OutT));
+          if (MC) {
+            mc_st_wordsW<W>(c.mc + off, w);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) {
+              int r = c.rank + j; if (r >= c.nranks) r -= c.nranks;
+              st_words<W>(c.peer[r] + off, w);
+            }
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0) {                          // scalar tail (count not a multiple of one vector)
+      const size_t e = nvec * E + threadIdx.x;
+      if (e < count) {
+        OutT o = from_float<OutT>(to_float<InT>(in[e]) * scale);
+        if constexpr (sizeof(InT) == sizeof(OutT)) {
+          if (identity) { const InT x = in[e]; memcpy(&o, &x, sizeof(o)); }   // bit-exact, like the vector path (payload may not be a float at all)
+        }
+        for (int r = 0; r < c.nranks; r++) reinterpret_cast<OutT*>(c.peer[r] + out_off)[e] = o;
+      }
+    }
+  }
+  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
+}
+
+// Non-root side of a rooted reduce: same barrier pair, same grid as the root's k_pull_reduce, no data movement.
+// The first barrier tells the root my send buffer is ready; the second tells me the root has finished reading it.
+__global__ void __launch_bounds__(kThreads) k_sync_only(CommDev c, uint32_t op) {
+  pdl_prologue();
+  const uint32_t s = load_seq(c, kSeqBarrier);
+  barrier_blocks<false>(c, 2 * s + 1, op);
   barrier_blocks<true>(c, 2 * s + 2, op);
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }

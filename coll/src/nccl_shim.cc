@@ -160,6 +160,34 @@ ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, n
   return map_rc(b200collReduceScatter(send, recv, recvcount, &ep, op == ncclAvg ? b200collAvg : b200collSum, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
 
+// Broadcast moves bits, so every NCCL dtype works: the payload is described to the library as f16/f32 words
+// (scale 1, same type in and out = the bit-exact identity path).
+static bool map_dt_as_words(ncclDataType_t dt, size_t count, b200collDataType_t* t, size_t* n) {
+  switch (dt) {
+    case ncclInt8: case ncclUint8: if (count % 2) return false; *t = b200collFloat16; *n = count / 2; return true;
+    case ncclFloat16: case ncclBfloat16: *t = b200collFloat16; *n = count; return true;
+    case ncclInt32: case ncclUint32: case ncclFloat32: *t = b200collFloat32; *n = count; return true;
+    case ncclInt64: case ncclUint64: case ncclFloat64: *t = b200collFloat32; *n = count * 2; return true;
+    default: return false;
+  }
+}
+ncclResult_t ncclBroadcast(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t comm, cudaStream_t stream) {
+  b200collDataType_t t; size_t n = 0;
+  if (!comm || !map_dt_as_words(dt, count, &t, &n)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, 1.0f};
+  return map_rc(b200collBroadcast(send ? send : recv, recv, n, &ep, root, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+}
+ncclResult_t ncclBcast(void* buf, size_t count, ncclDataType_t dt, int root, ncclComm_t comm, cudaStream_t stream) {   // legacy in-place form
+  return ncclBroadcast(buf, buf, count, dt, root, comm, stream);
+}
+ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, int root, ncclComm_t comm, cudaStream_t stream) {
+  b200collDataType_t t;
+  if (!comm || !map_dt(dt, &t) || (op != ncclSum && op != ncclAvg)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, 1.0f};
+  // NCCL lets non-root ranks pass recv == NULL; the library wants an aligned pointer it will not touch
+  return map_rc(b200collReduce(send, recv ? recv : const_cast<void*>(send), count, &ep, op == ncclAvg ? b200collAvg : b200collSum, root, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+}
+
 ncclResult_t ncclGroupStart(void) { g_group_depth++; return ncclSuccess; }
 ncclResult_t ncclGroupEnd(void) {
   if (g_group_depth <= 0) return ncclInvalidUsage;

@@ -44,6 +44,11 @@ static const Row kBuiltin[] = {
   // ---- all-to-all (bytes = per-peer block)
   {b200collOpAllToAll,      2, 8, -1,  256ull << 10, b200collAlgoLL},
   {b200collOpAllToAll,      2, 8, -1,  INF,          b200collAlgoTwoShot},
+  // ---- rooted ops (bytes = message): the switch does the fan-out / the reduction when it can
+  {b200collOpBroadcast,     3, 8,  1,  INF,          b200collAlgoNvls},
+  {b200collOpBroadcast,     2, 8, -1,  INF,          b200collAlgoTwoShot},
+  {b200collOpReduce,        3, 8,  1,  INF,          b200collAlgoNvls},
+  {b200collOpReduce,        2, 8, -1,  INF,          b200collAlgoTwoShot},
 };
 // clang-format on
 
@@ -55,6 +60,8 @@ static int parse_op(const char* s) {
   if (!strcasecmp(s, "allgather") || !strcasecmp(s, "all_gather")) return b200collOpAllGather;
   if (!strcasecmp(s, "reducescatter") || !strcasecmp(s, "reduce_scatter")) return b200collOpReduceScatter;
   if (!strcasecmp(s, "alltoall") || !strcasecmp(s, "all_to_all")) return b200collOpAllToAll;
+  if (!strcasecmp(s, "broadcast") || !strcasecmp(s, "bcast")) return b200collOpBroadcast;
+  if (!strcasecmp(s, "reduce")) return b200collOpReduce;
   return -1;
 }
 

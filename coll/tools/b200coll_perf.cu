@@ -107,11 +107,14 @@ static void spin_barrier(Shared* sh, int which, int n, int* gen) {
   }
 }
 
+constexpr int kRoot = 0;   // rooted ops (broadcast, reduce) are driven from rank 0, like nccl-tests' default
+
 struct RankCtx { int rank, nranks; b200collComm_t comm; int dev; };
 
 // expected value of output element e (element index in the op's output) for this rank
 static float expected(const Opts& o, int rank, int n, size_t e, size_t count) {
-  if (o.op == "all_reduce") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, e); return s * o.scale; }
+  if (o.op == "all_reduce" || o.op == "reduce") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, e); return s * o.scale; }
+  if (o.op == "broadcast") return gen(kRoot, e) * o.scale;
   if (o.op == "all_gather") { int src = (int)(e / count); return gen(src, e % count) * o.scale; }
   if (o.op == "reduce_scatter") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, (size_t)rank * count + e); return s * o.scale; }
   /* alltoall */ { int src = (int)(e / count); return gen(src, (size_t)rank * count + e % count) * o.scale; }
@@ -127,7 +130,10 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
   }
   if (o.max_ctas > 0) CC(b200collCommSetMaxCtas(ctx.comm, o.max_ctas));
   const size_t is = b200collTypeSize(o.in_dt), os = b200collTypeSize(o.out_dt);
-  const bool is_ar = o.op == "all_reduce", is_ag = o.op == "all_gather", is_rs = o.op == "reduce_scatter";
+  const bool is_bc = o.op == "broadcast", is_rd = o.op == "reduce";
+  const bool is_ar = o.op == "all_reduce" || is_bc || is_rd;      // "whole message" geometry: count elements in, count out
+  const bool is_ag = o.op == "all_gather", is_rs = o.op == "reduce_scatter";
+  if (!is_ar && !is_ag && !is_rs && o.op != "alltoall") { fprintf(stderr, "unknown --op %s\n", o.op.c_str()); return 2; }
   // nccl-tests convention: "size" is the larger of the two buffers in bytes of the input type
   const size_t max_in_bytes = o.max_bytes, max_out_bytes = o.max_bytes / is * os;
   const size_t send_cap = std::max(o.window, max_in_bytes), recv_cap = std::max(o.window / is * os, max_out_bytes);
@@ -181,7 +187,9 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
         return (char*)recv + off;
       };
       auto launch = [&](int slot) {
-        if (is_ar) CC(b200collAllReduce(sbuf(slot), rbuf(slot), count, &ep, b200collSum, ctx.comm, st));
+        if (is_bc) CC(b200collBroadcast(sbuf(slot), rbuf(slot), count, &ep, kRoot, ctx.comm, st));
+        else if (is_rd) CC(b200collReduce(sbuf(slot), rbuf(slot), count, &ep, b200collSum, kRoot, ctx.comm, st));
+        else if (is_ar) CC(b200collAllReduce(sbuf(slot), rbuf(slot), count, &ep, b200collSum, ctx.comm, st));
         else if (is_ag) CC(b200collAllGather(sbuf(slot), rbuf(slot), count, &ep, ctx.comm, st));
         else if (is_rs) CC(b200collReduceScatter(sbuf(slot), rbuf(slot), count, &ep, b200collSum, ctx.comm, st));
         else CC(b200collAllToAll(sbuf(slot), rbuf(slot), count, &ep, ctx.comm, st));
@@ -202,7 +210,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
         b200collFault f;
         if (b200collCommGetAsyncError(ctx.comm, &f) != b200collSuccess) { fprintf(stderr, "rank %d WATCHDOG code=%u peer=%u block=%u expected=%u observed=%u op=%u\n", rank, f.code, f.peer, f.block, f.expected, f.observed, f.op); _exit(5); }
         const char* outp = (ip && is_rs) ? rbuf(0) : (ip ? (char*)recv : rbuf(0));
-        const size_t check_elems = out_elems;
+        const size_t check_elems = (is_rd && rank != kRoot) ? 0 : out_elems;   // a rooted reduce defines the root's output only
         host.resize(check_elems * os);
         RT(cudaMemcpy(host.data(), outp, check_elems * os, cudaMemcpyDeviceToHost));
         const size_t stride = check_elems > (1u << 22) ? 61 : 1;   // sample large buffers
@@ -232,9 +240,9 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
     }
     if (rank == 0) {
       size_t tb = is_ar ? count * is : count * is * n;   // nccl-tests "size"
-      b200collOp_t opid = is_ar ? b200collOpAllReduce : is_ag ? b200collOpAllGather : is_rs ? b200collOpReduceScatter : b200collOpAllToAll;
+      b200collOp_t opid = is_bc ? b200collOpBroadcast : is_rd ? b200collOpReduce : is_ar ? b200collOpAllReduce : is_ag ? b200collOpAllGather : is_rs ? b200collOpReduceScatter : b200collOpAllToAll;
       if (o.algo == "auto") algo_used = b200collAlgoName(b200collTunerPick(opid, is_ar ? count * is : count * is, n, info.nvls)); else algo_used = o.algo.c_str();
-      const double factor = is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
+      const double factor = (is_bc || is_rd) ? 1.0 : is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
       double ab[2], bb[2];
       for (int ip = 0; ip < 2; ip++) { ab[ip] = res_us[ip] > 0 ? tb / res_us[ip] / 1e3 : 0; bb[ip] = n > 1 ? ab[ip] * factor : ab[ip]; }
       if (!o.shapes.empty()) printf("[k%d c%d t%d] ", o.shapes[si].kind, o.shapes[si].ctas, o.shapes[si].threads);

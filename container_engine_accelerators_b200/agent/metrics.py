@@ -31,7 +31,7 @@ RESET_INTERVAL_S = 60.0
 DUTY_CYCLE_WINDOW_S = 10
 _CONTAINER_LABELS = ["namespace", "pod", "container", "make", "accelerator_id", "model"]
 _NODE_LABELS = ["make", "accelerator_id", "model"]
-COLL_OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall")
+COLL_OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce")
 COLL_ALGOS = ("auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2")
 
 
@@ -69,12 +69,15 @@ def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*") -> list:
         try:
             with open(path, "rb") as f:
                 raw = f.read(4096)
-            if len(raw) < 64 + 8 * 17 or raw[:8] != b"B200COLL":
+            if len(raw) < 64 + 8 * 21 or raw[:8] != b"B200COLL":
                 continue
             version, pid, rank, nranks, device, nvls = struct.unpack_from("<6I", raw, 8)
-            vals = struct.unpack_from("<17Q", raw, 64)
-            pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "calls": vals[0:4], "bytes": vals[4:8],
-                          "algo_calls": vals[8:15], "kernel_launches": vals[15], "staged_calls": vals[16]})
+            nops = 4 if version == 1 else 6          # v1 pages (older library): no broadcast / reduce counters
+            vals = struct.unpack_from(f"<{2 * nops + 9}Q", raw, 64)
+            pad = (0,) * (len(COLL_OPS) - nops)
+            pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "version": version,
+                          "calls": vals[0:nops] + pad, "bytes": vals[nops:2 * nops] + pad,
+                          "algo_calls": vals[2 * nops:2 * nops + 7], "kernel_launches": vals[2 * nops + 7], "staged_calls": vals[2 * nops + 8]})
         except OSError:
             continue
     return pages

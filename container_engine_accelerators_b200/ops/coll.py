@@ -52,7 +52,7 @@ class CommInfo(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("calls", C.c_uint64 * 4), ("bytes", C.c_uint64 * 4), ("algo_calls", C.c_uint64 * 7), ("kernel_launches", C.c_uint64),
+    _fields_ = [("calls", C.c_uint64 * 6), ("bytes", C.c_uint64 * 6), ("algo_calls", C.c_uint64 * 7), ("kernel_launches", C.c_uint64),
                 ("staged_calls", C.c_uint64)]
 
 
@@ -116,6 +116,8 @@ def load() -> C.CDLL:
     L.b200collReduceScatter.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
     L.b200collAllToAll.argtypes = [vp, vp, sz, C.POINTER(Epilogue), vp, vp]
     L.b200collAllToAllv.argtypes = [vp, vp, sz, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Epilogue), vp, vp]
+    L.b200collBroadcast.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
+    L.b200collReduce.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, ci, vp, vp]
     L.b200collBarrier.argtypes = [vp, vp]
     L.b200collTunerPick.argtypes = [ci, sz, ci, ci]; L.b200collTunerPick.restype = ci
     L.b200collCommSetAlgo.argtypes = [vp, ci]
@@ -282,6 +284,20 @@ class Comm:
         arr = lambda xs: (C.c_int64 * n)(*[int(x) for x in xs])
         _check(load().b200collAllToAllv(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), row_elems, arr(send_rows), arr(send_row_off), arr(recv_row_off_at_peer),
                                         C.byref(ep), self._h, self._stream(stream)), "AllToAllv")
+        return dst
+
+    def broadcast(self, src, dst=None, root: int = 0, scale: float = 1.0, stream=None):
+        """dst on every rank = cast(scale * src of `root`). src is read on the root only (ncclBroadcast)."""
+        dst = src if dst is None else dst
+        ep = self._ep(src, dst, scale)
+        _check(load().b200collBroadcast(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), dst.numel(), C.byref(ep), root, self._h, self._stream(stream)), "Broadcast")
+        return dst
+
+    def reduce(self, src, dst=None, root: int = 0, scale: float = 1.0, op: int = SUM, stream=None):
+        """dst on `root` = cast(scale * sum over ranks of src); dst is untouched elsewhere (ncclReduce)."""
+        dst = src if dst is None else dst
+        ep = self._ep(src, dst, scale)
+        _check(load().b200collReduce(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), op, root, self._h, self._stream(stream)), "Reduce")
         return dst
 
     def barrier(self, stream=None) -> None:

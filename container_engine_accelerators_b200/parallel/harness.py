@@ -20,13 +20,17 @@ import os
 import time
 from dataclasses import dataclass, field
 
-OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall")
+OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce")   # index = b200collOp_t
+ROOT = 0   # rooted ops are measured from rank 0, as nccl-tests does by default
+FULL_MESSAGE_OPS = ("all_reduce", "broadcast", "reduce")   # count = whole message; the others split it over the ranks
 WINDOW = 192 << 20
 
 
 def bus_factor(op: str, n: int) -> float:
     if n <= 1:
         return 1.0   # nccl-tests prints busbw 0 for one rank; we report algbw there and say so
+    if op in ("broadcast", "reduce"):
+        return 1.0   # nccl-tests: rooted ops move the whole message over one rank's links, busbw = algbw
     return 2.0 * (n - 1) / n if op == "all_reduce" else (n - 1) / n
 
 
@@ -128,6 +132,10 @@ class OursBackend:
             rc = L.b200collAllGather(send_ptr, recv_ptr, count, ep, self.h, stream)
         elif op == "reduce_scatter":
             rc = L.b200collReduceScatter(send_ptr, recv_ptr, count, ep, 0, self.h, stream)
+        elif op == "broadcast":
+            rc = L.b200collBroadcast(send_ptr, recv_ptr, count, ep, ROOT, self.h, stream)
+        elif op == "reduce":
+            rc = L.b200collReduce(send_ptr, recv_ptr, count, ep, 0, ROOT, self.h, stream)
         else:
             rc = L.b200collAllToAll(send_ptr, recv_ptr, count, ep, self.h, stream)
         if rc != 0:
@@ -189,6 +197,10 @@ class NcclBackend:
             c.all_gather(send_ptr, recv_ptr, count, self.dt, stream)
         elif op == "reduce_scatter":
             c.reduce_scatter(send_ptr, recv_ptr, count, self.dt, stream)
+        elif op == "broadcast":
+            c.broadcast(send_ptr, recv_ptr, count, self.dt, ROOT, stream)
+        elif op == "reduce":
+            c.reduce(send_ptr, recv_ptr, count, self.dt, ROOT, stream)
         else:
             c.all_to_all(send_ptr, recv_ptr, count, self.dt, self.itemsize, stream)
         self._launches += 1
@@ -218,7 +230,7 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
     gen = _gen_expected(torch, op, rank, n, count, dev)
     E = 8
     count = max(E, count // E * E)
-    if op == "all_reduce":
+    if op in FULL_MESSAGE_OPS:
         in_elems, out_elems = count, count
     elif op == "all_gather":
         in_elems, out_elems = count, count * n
@@ -237,6 +249,10 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
     got = backend.recv[:out_elems].float()
     if op == "all_reduce":
         want = sum(gen(r, idx) for r in range(n))
+    elif op == "broadcast":
+        want = gen(ROOT, idx)
+    elif op == "reduce":                                   # only the root's recv is defined
+        want = sum(gen(r, idx) for r in range(n)) if rank == ROOT else torch.full_like(got, 77.0)
     elif op == "all_gather":
         j = torch.arange(count, device=dev)
         want = torch.cat([gen(r, j) for r in range(n)])
@@ -269,7 +285,7 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
     nbytes = min_bytes
     while nbytes <= max_bytes:
         E = 16 // itemsize
-        if op == "all_reduce":
+        if op in FULL_MESSAGE_OPS:
             count = nbytes // itemsize
             in_elems = out_elems = count
         else:
@@ -279,7 +295,7 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
         if count == 0:
             nbytes *= factor
             continue
-        total = (count if op == "all_reduce" else count * n) * itemsize
+        total = (count if op in FULL_MESSAGE_OPS else count * n) * itemsize
         slot_elems = (max(in_elems, out_elems) * itemsize + 4095) // 4096 * 4096 // itemsize
         slots = max(1, min(64, WINDOW // (slot_elems * itemsize)))
         per_rank_bytes = count * itemsize

@@ -4,7 +4,7 @@ The reference ships no collective code: its nccl-test manifests mount an install
 nccl-tests' `*_perf` binaries (reference: gpudirect-rdma/nccl-test-a4.yaml:42-77,
 gpudirect-tcpx/nccl-config.yaml:30-63). On one NVSwitch box the net plugin is never on the data path, so
 "the reference's NCCL build on this box" is the image's libnccl called exactly the way nccl-tests calls it:
-ncclAllReduce/ncclAllGather/ncclReduceScatter/ncclSend+ncclRecv on raw device pointers, one rank per GPU.
+ncclAllReduce/ncclAllGather/ncclReduceScatter/ncclBroadcast/ncclReduce/ncclSend+ncclRecv on raw device pointers, one rank per GPU.
 None of this repo's kernels are on this path.
 """
 from __future__ import annotations
@@ -58,6 +58,8 @@ class NcclComm:
         L.ncclAllReduce.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
         L.ncclAllGather.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, vp]
         L.ncclReduceScatter.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.ncclBroadcast.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.ncclReduce.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp]
         L.ncclSend.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
         L.ncclRecv.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
         L.ncclCommDestroy.argtypes = [vp]
@@ -91,6 +93,12 @@ class NcclComm:
 
     def reduce_scatter(self, send: int, recv: int, recvcount: int, dtype: int, stream: int) -> None:
         self._ck(self.lib.ncclReduceScatter(send, recv, recvcount, dtype, NCCL_SUM, self.comm, stream), "ncclReduceScatter")
+
+    def broadcast(self, send: int, recv: int, count: int, dtype: int, root: int, stream: int) -> None:
+        self._ck(self.lib.ncclBroadcast(send, recv, count, dtype, root, self.comm, stream), "ncclBroadcast")
+
+    def reduce(self, send: int, recv: int, count: int, dtype: int, root: int, stream: int) -> None:
+        self._ck(self.lib.ncclReduce(send, recv, count, dtype, NCCL_SUM, root, self.comm, stream), "ncclReduce")
 
     def all_to_all(self, send: int, recv: int, count: int, dtype: int, elem_size: int, stream: int) -> None:
         # nccl-tests' alltoall: grouped ncclSend/ncclRecv to every peer

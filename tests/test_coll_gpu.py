@@ -151,6 +151,61 @@ def test_all_gather_reduce_scatter_all_to_all(torch_cuda, group, algo):
         assert torch.equal(a2a[r], want)
 
 
+@pytest.mark.parametrize("group", [2, 4], indirect=True)
+@pytest.mark.parametrize("count", [8, 1003, 1 << 16])
+def test_broadcast_and_reduce_rooted(torch_cuda, group, count):
+    """ncclBroadcast / ncclReduce semantics incl. a count that is not a whole number of 16-byte vectors, every root,
+    in-place, and the fused cast/scale epilogue (fp32 reference)."""
+    torch = torch_cuda
+    comms, streams = group
+    n = len(comms)
+    srcs = fill(torch, comms, count, torch.bfloat16)
+    for root in range(n):
+        outs = [c.empty(count, torch.bfloat16) for c in comms]
+        for o in outs:
+            o.fill_(55.0)
+        torch.cuda.synchronize()
+        run_all(torch, comms, streams, lambda r, c, st: c.broadcast(srcs[r], outs[r], root=root, stream=st))
+        for o in outs:
+            assert torch.equal(o, srcs[root]), root
+        red = [c.empty(count, torch.float32) for c in comms]
+        for o in red:
+            o.fill_(55.0)
+        torch.cuda.synchronize()
+        run_all(torch, comms, streams, lambda r, c, st: c.reduce(srcs[r], red[r], root=root, scale=0.5, stream=st))   # bf16 in, fp32 out, x0.5 fused
+        want = sum(t.float() for t in srcs) * 0.5
+        for r in range(n):
+            assert torch.equal(red[r], want if r == root else torch.full_like(want, 55.0)), (root, r)
+    # in-place broadcast from rank 1 with a fused fp32 -> (scale 2) -> fp32 epilogue
+    bufs = [c.empty(count, torch.float32) for c in comms]
+    for r, b in enumerate(bufs):
+        b.copy_(torch.arange(count, device="cuda").float() * 0.5 + r)
+    torch.cuda.synchronize()
+    want = bufs[1].clone() * 2.0
+    run_all(torch, comms, streams, lambda r, c, st: c.broadcast(bufs[r], root=1, scale=2.0, stream=st))
+    for b in bufs:
+        assert torch.equal(b, want)
+    for c in comms:
+        st = c.stats()
+        assert st["calls"][4] == n + 1 and st["calls"][5] == n          # broadcast, reduce counters (b200collOp_t order)
+
+
+@pytest.mark.parametrize("group", [2], indirect=True)
+def test_rooted_ops_outside_the_arena_are_staged(torch_cuda, group):
+    torch = torch_cuda
+    comms, streams = group
+    count = (1 << 20) + 24
+    srcs = [(((torch.arange(count, device="cuda") * (r + 2)) % 9) - 4).to(torch.bfloat16) for r in range(len(comms))]
+    dsts = [torch.full((count,), 9.0, dtype=torch.bfloat16, device="cuda") for _ in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.broadcast(srcs[r], dsts[r], root=1, stream=st))
+    for d in dsts:
+        assert torch.equal(d, srcs[1])
+    red = [torch.full((count,), 9.0, dtype=torch.bfloat16, device="cuda") for _ in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.reduce(srcs[r], red[r], root=0, stream=st))
+    assert torch.equal(red[0].float(), sum(s.float() for s in srcs)) and torch.equal(red[1], torch.full_like(red[1], 9.0))
+    assert all(c.stats()["staged_calls"] == 2 for c in comms)
+
+
 @pytest.mark.parametrize("group", [4], indirect=True)
 def test_all_to_all_v_expert_dispatch(torch_cuda, group):
     """Skewed per-peer row counts (MoE dispatch shape): rows land at the offsets the receiver advertised."""
@@ -241,7 +296,7 @@ def test_watchdog_reports_instead_of_hanging(torch_cuda, coll_mod):
 
 def test_perf_tool_virtual_ranks_zero_errors(torch_cuda, coll_lib):
     assert os.path.exists(PERF), "build/b200coll_perf missing (python -c 'import __graft_entry__ as g; g.build()')"
-    for op in ("all_reduce", "all_gather", "reduce_scatter", "alltoall"):
+    for op in ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce"):
         r = subprocess.run([PERF, "--devs", "0,0,0,0", "--op", op, "-b", "1K", "-e", "1M", "-f", "4", "--iters", "3", "--warmup", "1"], capture_output=True, text=True, timeout=120,
                            env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
         assert r.returncode == 0, r.stdout + r.stderr
@@ -255,6 +310,10 @@ def test_multi_gpu_procs_nvls(torch_cuda, coll_lib):
     devs = ",".join(str(i) for i in range(n))
     for algo in ("auto", "nvls", "twoshot"):
         r = subprocess.run([PERF, "--devs", devs, "--procs", "--op", "all_reduce", "--algo", algo, "-b", "1K", "-e", "64M", "-f", "16", "--iters", "3", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
+        assert r.returncode == 0 and "errors=0" in r.stdout, r.stdout + r.stderr
+    for op in ("broadcast", "reduce"):                     # multimem.st fan-out / multimem.ld_reduce by the root (N >= 3) or P2P (N == 2)
+        r = subprocess.run([PERF, "--devs", devs, "--procs", "--op", op, "-b", "1K", "-e", "64M", "-f", "16", "--iters", "3", "--warmup", "1"],
                            capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
         assert r.returncode == 0 and "errors=0" in r.stdout, r.stdout + r.stderr
 

@@ -193,6 +193,25 @@ def test_coll_stats_page_is_exported(tmp_path):
     ms.update_metrics({})
     assert sample(reg, "b200coll_calls", {"pid": "4242", "rank": "3", "op": "all_reduce"}) == 10
     assert sample(reg, "b200coll_algo_calls", {"pid": "4242", "rank": "3", "algo": "ll"}) == 7
+    assert sample(reg, "b200coll_calls", {"pid": "4242", "rank": "3", "op": "broadcast"}) == 0      # v1 page: no rooted-op counters
+
+
+def test_coll_stats_page_v2_has_broadcast_and_reduce(tmp_path):
+    import struct
+    page = bytearray(4096)
+    page[0:8] = b"B200COLL"
+    struct.pack_into("<6I", page, 8, 2, 77, 0, 8, 0, 1)
+    #                                 calls (6 ops)        bytes (6 ops)                     algo_calls (7)        launches staged
+    struct.pack_into("<21Q", page, 64, 1, 2, 3, 4, 5, 6, 10, 20, 30, 40, 50, 60, 0, 1, 0, 2, 9, 0, 0, 21, 3)
+    (tmp_path / "b200coll.77.0").write_bytes(page)
+    pg = metrics.read_coll_stats_pages(str(tmp_path / "b200coll.*"))[0]
+    assert pg["version"] == 2 and pg["calls"] == (1, 2, 3, 4, 5, 6) and pg["bytes"][4:] == (50, 60)
+    assert pg["algo_calls"] == (0, 1, 0, 2, 9, 0, 0) and pg["kernel_launches"] == 21 and pg["staged_calls"] == 3
+    reg = CollectorRegistry()
+    ms = metrics.MetricServer(nvml.MockNvml(testing.make_fake_dev(str(tmp_path), 1)), registry=reg, coll_stats_glob=str(tmp_path / "b200coll.*"))
+    ms.update_metrics({})
+    assert sample(reg, "b200coll_calls", {"pid": "77", "rank": "0", "op": "reduce"}) == 6
+    assert sample(reg, "b200coll_bytes", {"pid": "77", "rank": "0", "op": "broadcast"}) == 50
 
 
 # ------------------------------------------------------------------------------------------------- native binding
