@@ -604,6 +604,41 @@ void publish_driver_version(NodeStatus* ns) {
 
 // ------------------------------------------------------------------------------------------------ metrics
 std::string esc(const std::string& s) { std::string o; for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); } return o; }
+// libb200coll publishes one 4 KiB counters page per communicator under /dev/shm (coll/src/comm.cu stats_page_publish):
+// 64-byte header {"B200COLL", version, pid, rank, nranks, device, nvls} then calls[ops], bytes[ops], algo_calls[7],
+// kernel_launches, staged_calls as u64. version 1 has 4 ops, version 2 adds broadcast and reduce.
+std::string g_coll_stats_dir = "/dev/shm";
+void append_coll_stats(std::ostringstream& os) {
+  static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce"};
+  static const char* kAlgos[] = {"auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2"};
+  struct Page { uint32_t pid, rank; uint64_t calls[6], bytes[6], algo[7]; };
+  std::vector<Page> pages;
+  if (DIR* d = opendir(g_coll_stats_dir.c_str())) {
+    while (dirent* e = readdir(d)) {
+      if (strncmp(e->d_name, "b200coll.", 9) != 0) continue;
+      std::ifstream f(join(g_coll_stats_dir, e->d_name), std::ios::binary);
+      char raw[64 + 21 * 8] = {};
+      if (!f.read(raw, sizeof raw) || memcmp(raw, "B200COLL", 8) != 0) continue;
+      uint32_t hdr[6]; memcpy(hdr, raw + 8, sizeof hdr);
+      const int nops = hdr[0] == 1 ? 4 : 6;
+      uint64_t v[21]; memcpy(v, raw + 64, sizeof v);
+      Page p{}; p.pid = hdr[1]; p.rank = hdr[2];
+      for (int i = 0; i < nops; i++) { p.calls[i] = v[i]; p.bytes[i] = v[nops + i]; }
+      for (int i = 0; i < 7; i++) p.algo[i] = v[2 * nops + i];
+      pages.push_back(p);
+    }
+    closedir(d);
+  }
+  if (pages.empty()) return;
+  auto help = [&](const char* n, const char* h) { os << "# HELP " << n << " " << h << "\n# TYPE " << n << " gauge\n"; };
+  help("b200coll_calls", "Collective calls issued through libb200coll");
+  for (auto& p : pages) for (int i = 0; i < 6; i++) os << "b200coll_calls{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",op=\"" << kOps[i] << "\"} " << p.calls[i] << "\n";
+  help("b200coll_bytes", "Bytes moved by libb200coll collectives");
+  for (auto& p : pages) for (int i = 0; i < 6; i++) os << "b200coll_bytes{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",op=\"" << kOps[i] << "\"} " << p.bytes[i] << "\n";
+  help("b200coll_algo_calls", "libb200coll calls per chosen algorithm");
+  for (auto& p : pages) for (int i = 0; i < 7; i++) os << "b200coll_algo_calls{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",algo=\"" << kAlgos[i] << "\"} " << p.algo[i] << "\n";
+}
+
 std::string collect_metrics(Manager* ngm, const std::string& pod_resources_socket) {
   std::ostringstream os;
   struct Info { std::string uuid, name; unsigned long long total, used; unsigned duty; bool ok; };
@@ -648,6 +683,7 @@ std::string collect_metrics(Manager* ngm, const std::string& pod_resources_socke
     for (auto& g : gpus) { if (!g.second.ok) continue; const unsigned long long v = k == 0 ? g.second.duty : k == 1 ? g.second.total : g.second.used;
       os << n << "{make=\"nvidia\",accelerator_id=\"" << esc(g.second.uuid) << "\",model=\"" << esc(g.second.name) << "\"} " << v << "\n"; }
   }
+  append_coll_stats(os);
   return os.str();
 }
 
@@ -755,6 +791,7 @@ int main(int argc, char** argv) {
     else if (a == "mps-control-bin") ngm.mps_control_bin = need();
     else if (a == "plugin-endpoint") plugin_endpoint = need();
     else if (a == "pod-resources-socket") pod_resources = need();
+    else if (a == "coll-stats-dir") g_coll_stats_dir = need();
     else if (a == "gpu-check-interval") ngm.gpu_check_interval = atof(need().c_str());
     else if (a == "socket-check-interval") ngm.socket_check_interval = atof(need().c_str());
     else if (a == "v") g_verbosity = atoi(need().c_str());

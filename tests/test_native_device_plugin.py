@@ -189,7 +189,14 @@ def test_metrics_endpoint(native, tmp_path):
     import socket as _s
     s = _s.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     try:
-        n = native(extra_args=["-enable-container-gpu-metrics", "-gpu-metrics-port", str(port), "-gpu-metrics-collection-interval", "200", "--pod-resources-socket", sock], env={"FAKE_NVML_UTIL": "40,60,80"})
+        import struct
+        shm = tmp_path / "shm"; shm.mkdir()
+        page = bytearray(4096); page[0:8] = b"B200COLL"
+        struct.pack_into("<6I", page, 8, 2, 4242, 3, 8, 3, 1)
+        struct.pack_into("<21Q", page, 64, 10, 0, 0, 2, 7, 1, 1 << 30, 0, 0, 4096, 512, 64, 0, 5, 0, 2, 13, 0, 0, 21, 0)
+        (shm / "b200coll.4242.3").write_bytes(page)
+        n = native(extra_args=["-enable-container-gpu-metrics", "-gpu-metrics-port", str(port), "-gpu-metrics-collection-interval", "200", "--pod-resources-socket", sock,
+                               "--coll-stats-dir", str(shm)], env={"FAKE_NVML_UTIL": "40,60,80"})
         n.connect()
         deadline = time.time() + 10
         body = ""
@@ -205,6 +212,9 @@ def test_metrics_endpoint(native, tmp_path):
         assert 'request{namespace="default",pod="p1",container="c1",resource_name="nvidia.com/gpu"} 1' in body
         assert 'request{namespace="default",pod="p2",container="c1",resource_name="nvidia.com/gpu"} 0' in body            # virtual ids dropped
         assert 'memory_total_gpu_node{make="nvidia",accelerator_id="GPU-fake-1",model="NVIDIA B200"} ' in body
+        assert 'b200coll_calls{pid="4242",rank="3",op="all_reduce"} 10' in body and 'b200coll_calls{pid="4242",rank="3",op="broadcast"} 7' in body
+        assert f'b200coll_bytes{{pid="4242",rank="3",op="all_reduce"}} {1 << 30}' in body
+        assert 'b200coll_algo_calls{pid="4242",rank="3",algo="nvls"} 13' in body
     finally:
         stub.server.stop(0)
 
