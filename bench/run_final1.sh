@@ -3,7 +3,7 @@
 # short default bench run. Everything is wrapped in `timeout` so a hang costs seconds, not the box.
 mkdir -p gpurun_out
 echo "== $(date -u +%T) pytest -m gpu"
-timeout 240 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"
+timeout 200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"
 tail -n 3 gpurun_out/pytest_gpu_final.log
 echo "== $(date -u +%T) smoke"
 timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"

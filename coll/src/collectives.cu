@@ -518,9 +518,8 @@ b200collResult_t b200collReduce(const void* send, void* recv, size_t count, cons
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
       Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvlsRs : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), 2);
-      if (c->rank != root) launch_k(k_sync_only, g.blocks, g.threads, st, c->dev, (uint32_t)b200collOpReduce);
-      else if (algo == b200collAlgoNvls) launch_k(k_pull_reduce<InT, OutT, false, true>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, b200collOpReduce);
-      else launch_k(k_pull_reduce<InT, OutT, false, false>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, b200collOpReduce);
+      if (algo == b200collAlgoNvls) launch_k(k_reduce_root<InT, OutT, true>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, root, b200collOpReduce);
+      else launch_k(k_reduce_root<InT, OutT, false>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, root, b200collOpReduce);
       LAUNCH_CHECK(c);
       return b200collSuccess;
     });

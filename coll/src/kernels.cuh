@@ -10,7 +10,7 @@
 //   k_ag_push         all-gather                   P2P push or one multimem.st per vector
 //   k_a2av_push       all-to-all(v)                per-peer row ranges, flattened for load balance
 //   k_bcast           broadcast                    root pushes (P2P or one multimem.st per vector); the others only synchronise
-//   k_sync_only       reduce (non-root ranks)      the two barriers of k_pull_reduce, which the root runs over the whole buffer
+//   k_reduce_root     reduce                       the root pulls (or multimem.ld_reduce) the whole buffer; the others only synchronise
 //   k_barrier
 #pragma once
 #include "device.cuh"
@@ -619,12 +619,62 @@ __global__ void __launch_bounds__(kThreads) k_bcast(CommDev c, const InT* __rest
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
-// Non-root side of a rooted reduce: same barrier pair, same grid as the root's k_pull_reduce, no data movement.
-// The first barrier tells the root my send buffer is ready; the second tells me the root has finished reading it.
-__global__ void __launch_bounds__(kThreads) k_sync_only(CommDev c, uint32_t op) {
+// Rooted reduce: out@root[i] = scale * sum_r peer_r[in_off + i]. Every rank launches this same kernel with the same grid
+// (a different kernel on the non-root ranks would need its own lazy module load, and with virtual ranks that load cannot
+// complete while the root's kernel is already spinning on the GPU -> deadlock); non-root CTAs only take the two barriers:
+// the first tells the root my send buffer is ready, the second tells me the root has finished reading it.
+// MC: the root issues multimem.ld_reduce (the switch adds, the root receives S bytes instead of S(N-1)).
+template <typename InT, typename OutT, bool MC>
+__global__ void __launch_bounds__(kThreads) k_reduce_root(CommDev c, size_t in_off, OutT* __restrict__ out, size_t count, float scale, int root, uint32_t op) {
   pdl_prologue();
+  constexpr int E = Epv<InT>::value;
+  constexpr int U = 2;
   const uint32_t s = load_seq(c, kSeqBarrier);
   barrier_blocks<false>(c, 2 * s + 1, op);
+  if (c.rank == root) {
+    const size_t nvec = count / E;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
+      if (MC) {
+        uint4 d[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const size_t v = base + (size_t)u * blockDim.x; if (v < nvec) d[u] = mc_ld_reduce<InT>(c.mc + in_off + v * 16); }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = base + (size_t)u * blockDim.x;
+          if (v < nvec) { float acc[E] = {}; unpack_add<InT>(acc, d[u]); finish_store_local<InT, OutT, E>(out + v * E, acc, scale); }
+        }
+      } else {
+        uint4 d[U][kMaxRanks];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = base + (size_t)u * blockDim.x;
+          if (v < nvec) {
+#pragma unroll
+            for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) d[u][j] = ld_vec(c.peer[j] + in_off + v * 16);   // rank order: deterministic sum
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = base + (size_t)u * blockDim.x;
+          if (v < nvec) {
+            float acc[E] = {};
+#pragma unroll
+            for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) unpack_add<InT>(acc, d[u][j]);
+            finish_store_local<InT, OutT, E>(out + v * E, acc, scale);
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0) {   // scalar tail
+      const size_t e = nvec * E + threadIdx.x;
+      if (e < count) {
+        float acc = 0.f;
+        for (int r = 0; r < c.nranks; r++) acc += to_float<InT>(reinterpret_cast<const volatile InT*>(c.peer[r] + in_off)[e]);
+        out[e] = from_float<OutT>(acc * scale);
+      }
+    }
+  }
   barrier_blocks<true>(c, 2 * s + 2, op);
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
