@@ -85,6 +85,7 @@ class HpackDecoder {
         out->emplace_back(name, value); add(name, value);
       } else if (b & 0x20) {                            // dynamic table size update
         uint64_t sz; if (!integer(p, n, &i, 5, &sz)) return false;
+        if (sz > kSettingsTableSize) return false;      // RFC 7541 6.3: must not exceed SETTINGS_HEADER_TABLE_SIZE (we keep the 4096 default)
         max_size_ = (size_t)sz; evict();
       } else {                                          // literal without indexing / never indexed
         std::string name, value; if (!literal(p, n, &i, 4, &name, &value)) return false;
@@ -113,7 +114,7 @@ class HpackDecoder {
     if (*i >= n) return false;
     const bool huff = p[*i] & 0x80;
     uint64_t len; if (!integer(p, n, i, 7, &len)) return false;
-    if (*i + len > n) return false;
+    if (len > n - *i) return false;                   // (not `*i + len > n`: a hostile length must not wrap)
     if (huff) { if (!huffman().decode(p + *i, (size_t)len, out)) return false; }
     else out->assign(reinterpret_cast<const char*>(p + *i), (size_t)len);
     *i += (size_t)len;
@@ -138,7 +139,8 @@ class HpackDecoder {
   }
   void evict() { while (size_ > max_size_ && !dyn_.empty()) { size_ -= dyn_.back().first.size() + dyn_.back().second.size() + 32; dyn_.pop_back(); } }
   std::vector<std::pair<std::string, std::string>> dyn_;
-  size_t size_ = 0, max_size_ = 4096;
+  static constexpr uint64_t kSettingsTableSize = 4096;
+  size_t size_ = 0, max_size_ = kSettingsTableSize;
 };
 
 // Encoder: "literal header field without indexing, new name", raw strings — always valid, no shared state to get wrong.

@@ -101,6 +101,7 @@ class Parser {
  public:
   explicit Parser(const std::string& s) : s_(s) {}
   bool parse(Value* out, std::string* err) {
+    *out = Value();          // a reused Value must not keep members of the previous document
     ws();
     if (!value(out)) { *err = err_.empty() ? "invalid JSON" : err_; return false; }
     ws();
@@ -111,11 +112,15 @@ class Parser {
  private:
   void ws() { while (i_ < s_.size() && (s_[i_] == ' ' || s_[i_] == '\t' || s_[i_] == '\n' || s_[i_] == '\r')) i_++; }
   bool lit(const char* w) { size_t n = strlen(w); if (s_.compare(i_, n, w) == 0) { i_ += n; return true; } return false; }
+  struct Depth { int& d; explicit Depth(int& x) : d(x) { d++; } ~Depth() { d--; } };
   bool value(Value* v) {
     if (i_ >= s_.size()) return false;
     const char c = s_[i_];
-    if (c == '{') return object(v);
-    if (c == '[') return array(v);
+    if (c == '{' || c == '[') {
+      Depth guard(depth_);
+      if (depth_ > kMaxDepth) { err_ = "JSON nested too deeply"; return false; }
+      return c == '{' ? object(v) : array(v);
+    }
     if (c == '"') { v->kind = Value::String; return string(&v->str); }
     if (lit("true")) { v->kind = Value::Bool; v->b = true; return true; }
     if (lit("false")) { v->kind = Value::Bool; v->b = false; return true; }
@@ -197,8 +202,10 @@ class Parser {
       return false;
     }
   }
+  static constexpr int kMaxDepth = 128;   // Kubernetes objects nest < 20 levels; bounds the recursion on hostile input
   const std::string& s_;
   size_t i_ = 0;
+  int depth_ = 0;
   std::string err_;
 };
 

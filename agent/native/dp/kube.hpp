@@ -121,6 +121,7 @@ class Client {
   std::string host; int port = 443; bool tls = true;
   std::string token, ca_file;
   int timeout_s = 30;
+  static constexpr size_t kMaxResponseBytes = 32u << 20;   // a Node object is tens of KiB; anything near this is not one
 
   // B200_KUBE_URL wins; otherwise the pod's in-cluster environment. Returns "" on success, else why not.
   static std::string from_env(Client* c) {
@@ -182,6 +183,7 @@ class Client {
       if (n < 0) { if (raw.empty()) { r.error = "read from API server failed: " + c.error; return r; } break; }
       if (n == 0) break;
       raw.append(buf, (size_t)n);
+      if (raw.size() > kMaxResponseBytes) { r.error = "API server response exceeds " + std::to_string(kMaxResponseBytes >> 20) + " MiB"; return r; }
       if (complete(raw)) break;
     }
     parse(raw, &r);
@@ -213,6 +215,10 @@ class Client {
     ev.at("firstTimestamp") = json::Value::of(ts); ev.at("lastTimestamp") = json::Value::of(ts); ev.at("count") = json::Value::of(1L);
     return request("POST", "/api/v1/namespaces/default/events", "application/json", json::dump(ev));
   }
+
+  // ---- wire helpers (public so the native self-test can drive them without a socket)
+  static bool response_complete(const std::string& raw) { return complete(raw); }
+  static void parse_response(const std::string& raw, Response* r) { parse(raw, r); }
 
  private:
   struct Conn {

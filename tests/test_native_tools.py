@@ -209,3 +209,12 @@ def test_gridd_only_on_g4(native_build, tmp_path):
     r = run_persistenced(native_build, tmp_path, prefix, None, machine="g4-standard-12\n", extra_env={"ROOT_MOUNT_DIR": str(root)})
     assert r.returncode == 0
     assert (tmp_path / "gridd.log").read_text().strip() == f"--library-path {prefix}/gridd-libs:{root}/lib64:{root}/usr/lib64 {prefix}/bin/nvidia-gridd"
+
+
+# ------------------------------------------------------------------------------------------------- native building blocks
+def test_native_selftest_json_kube_hpack_protobuf(native_build):
+    """agent/native/dp/selftest.cc: JSON reader/writer (escapes, int64 fidelity, depth bound), HTTP response parsing,
+    HPACK against the RFC 7541 Appendix C vectors plus hostile input, protobuf varints and truncated messages."""
+    r = subprocess.run([os.path.join(native_build, "b200-native-selftest")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ", 0 failed" in r.stdout
