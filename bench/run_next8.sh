@@ -1,0 +1,22 @@
+#!/bin/bash
+# Open items that need a multi-GPU box (none of them has been measured on NVLink yet):
+#   1. rooted collectives on the NVLS path (multimem.st fan-out, root-side multimem.ld_reduce): correctness + busbw vs NCCL
+#   2. programmatic dependent launch (B200COLL_PDL=1) at one rank per GPU: small-message latency with and without
+#   3. the multi-process NVLS test that a one-GPU box skips
+# Usage: gpurun --gpus 8 --timeout 600 -- 'bash bench/run_next8.sh 8'
+NG=${1:-8}
+mkdir -p gpurun_out; export B200COLL_TIMEOUT_MS=5000
+O=gpurun_out/x${NG}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+ALL=$(python3 -c "print(','.join(str(i) for i in range($NG)))")
+echo "== $(date -u +%T) multi-process NVLS tests"
+timeout 300 python -m pytest tests/test_coll_gpu.py -q -k "multi_gpu" > ${O}_pytest_multi.log 2>&1; echo "pytest rc=$?"; tail -n 2 ${O}_pytest_multi.log
+echo "== $(date -u +%T) rooted ops, both arms"
+timeout 200 $TR --master-port 29731 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --extra-ops reduce --extra-out ${O}_rooted_ours.json > ${O}_bcast.json 2> ${O}_bcast.err
+timeout 200 $TR --master-port 29732 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --impl reference --extra-ops reduce --extra-out ${O}_rooted_ref.json > ${O}_bcast_ref.json 2> ${O}_bcast_ref.err
+grep -h "Avg bus" ${O}_bcast.err ${O}_bcast_ref.err
+echo "== $(date -u +%T) PDL off / on, all_reduce 1 KiB .. 4 MiB"
+for pdl in 0 1; do
+  B200COLL_PDL=$pdl timeout 90 ./build/b200coll_perf --devs $ALL --procs --op all_reduce -b 1K -e 4M -f 4 --iters 200 --warmup 20 > ${O}_pdl${pdl}.txt 2>&1; echo "pdl=$pdl rc=$?"; grep -E "^ +[0-9]" ${O}_pdl${pdl}.txt | awk '{print $1, $4, $6}' | tr '\n' ';'; echo
+done
+echo "== $(date -u +%T) done"
