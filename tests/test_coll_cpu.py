@@ -74,11 +74,10 @@ def _boot_rank(lib_path, name, rank, n, q):
     rc = L.b200collBootstrapSelfTest(name.encode(), rank, n, fd, out, C.byref(bc), 20000)
     got = []
     if rc == 0:
+        # pread, not lseek+read: descriptors passed with SCM_RIGHTS share one open file description (one offset) across ranks
         for r in range(n):
-            os.lseek(out[r], 0, os.SEEK_SET)
-            got.append(os.read(out[r], 64).decode())
-        os.lseek(bc.value, 0, os.SEEK_SET)
-        got.append(os.read(bc.value, 64).decode())
+            got.append(os.pread(out[r], 64, 0).decode())
+        got.append(os.pread(bc.value, 64, 0).decode())
     q.put((rank, rc, got))
 
 
