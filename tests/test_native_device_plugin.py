@@ -142,9 +142,8 @@ def test_bad_config_falls_back_and_transport_profile(native):
     c = n.connect()
     _, devs = first_list(c)
     assert set(devs) == {"nvidia0", "nvidia1"} and "falling back to default GPU config" in n.logs()
+    n.close()           # same plugin dir and endpoint name: the first instance must be gone (it unlinks the socket on exit)
     n2 = native(config={"Transport": {"Name": "b200coll", "Env": {"B200COLL_ALGO": "nvls"}}}, with_kubelet=False)
-    n2.plugin_dir  # separate dir per instance is not needed: different endpoint names would collide -> close the first
-    n.close()
     env = dict(n2.connect().allocate(["nvidia0"]).container_responses[0].envs)
     assert env["B200COLL_LIB"] == "/usr/local/nvidia/lib64/libb200coll.so" and env["B200COLL_ALGO"] == "nvls" and env["LD_LIBRARY_PATH"] == "/usr/local/nvidia/lib64"
 
