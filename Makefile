@@ -9,16 +9,37 @@ test: build                  ## CPU test-suite (GPU tests: `make test-gpu` on a 
 	$(PY) -m pytest tests -x -q -m "not gpu"
 test-gpu: build
 	$(PY) -m pytest tests -x -q -m gpu
-presubmit:                   ## header + style + manifest freshness
+presubmit: vet                ## header + style + manifest freshness
 	$(PY) build_tools/boilerplate.py
 	bash build_tools/check_style.sh
 	$(PY) deploy/generate.py --check
 bench:
 	$(PY) bench.py --table
-containers:                  ## build every image under docker/ (needs docker + network)
-	for f in docker/*.Dockerfile; do n=$$(basename $$f .Dockerfile); docker build -f $$f -t b200-$$n:dev . || exit 1; done
+vet:                         ## static checks (role of reference Makefile:27-29 `go vet`): warnings-as-errors syntax pass + byte-compile
+	for f in agent/native/*.cc agent/native/dp/*.cc; do $(CXX) -std=c++17 -Wall -Wextra -Werror -fsyntax-only -Iagent/native/dp $$f || exit 1; done
+	$(PY) -m compileall -q container_engine_accelerators_b200 deploy bench build_tools bench.py __graft_entry__.py
+
+# ---- images (role of reference Makefile:49-99: container, container-multi-arch, push*, partition-gpu*, nri-device-injector*,
+# nvidia_persistenced_installer*, fastsocket_installer). One Dockerfile per image under docker/; IMAGE-<name> builds one,
+# `containers` builds all, `push` pushes all, `containers-multi-arch` builds amd64+arm64 (GB200/GB300 nodes) with buildx.
+REGISTRY ?= gcr.io/b200-node-accelerators
+TAG ?= $(shell git describe --tags --always --dirty 2>/dev/null || echo dev)
+IMAGES := $(patsubst docker/%.Dockerfile,%,$(wildcard docker/*.Dockerfile))
+MULTI_ARCH_IMAGES := device-plugin-native nri-device-injector partition-gpu persistenced topology-scheduler device-plugin
+$(addprefix image-,$(IMAGES)): image-%:
+	docker build -f docker/$*.Dockerfile -t $(REGISTRY)/b200-$*:$(TAG) .
+containers: $(addprefix image-,$(IMAGES))   ## build every image under docker/ (needs docker + network)
+push: containers
+	for n in $(IMAGES); do docker push $(REGISTRY)/b200-$$n:$(TAG) || exit 1; done
+containers-multi-arch:       ## CPU-only images for linux/amd64 + linux/arm64 (the CUDA images are built per arch by their base image)
+	for n in $(MULTI_ARCH_IMAGES); do docker buildx build --platform linux/amd64,linux/arm64 -f docker/$$n.Dockerfile -t $(REGISTRY)/b200-$$n:$(TAG) --push . || exit 1; done
+device-plugin: image-device-plugin image-device-plugin-native
+partition-gpu: image-partition-gpu
+nri-device-injector: image-nri-device-injector
+nvidia-persistenced-installer: image-persistenced
+transport-installer: image-b200coll-installer     ## the fastsocket_installer analogue
 sass:                        ## SASS listing of the collective kernels -> profiles/
 	cuobjdump -sass coll/lib/libb200coll.so > profiles/libb200coll.sass
 clean:
 	$(MAKE) -C coll clean; $(MAKE) -C tools clean; $(MAKE) -C agent/native clean
-.PHONY: all build manifests test test-gpu presubmit bench containers sass clean
+.PHONY: all build manifests test test-gpu vet presubmit bench containers push containers-multi-arch device-plugin partition-gpu nri-device-injector nvidia-persistenced-installer transport-installer sass clean

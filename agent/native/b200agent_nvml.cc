@@ -10,7 +10,7 @@
 // NVML is resolved at run time so the library loads (and its error paths are testable) on a GPU-less box;
 // B200AGENT_NVML_LIB overrides the library path (tests point it at a fake NVML).
 #include <dlfcn.h>
-#include <nvml.h>
+#include "nvml_abi.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>

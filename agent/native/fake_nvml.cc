@@ -3,7 +3,7 @@
 // Scripted by environment: FAKE_NVML_GPUS (count, default 2), FAKE_NVML_UTIL ("50,60,70" sample values,
 // empty = no samples), FAKE_NVML_EVENTS (file with "gpu_index xid [gi ci]" lines; each Wait pops one line,
 // "-1 xid" = event without a device), FAKE_NVML_NO_EVENTS=1 (RegisterEvents returns NOT_SUPPORTED).
-#include <nvml.h>
+#include "nvml_abi.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>

@@ -2,8 +2,7 @@
 # (reference Dockerfile:15-36 builds a cgo binary onto distroless/base; envelope 50m CPU / 100Mi, cmd/nvidia_gpu/device-plugin.yaml:47-52).
 FROM gcc:14 AS build
 COPY agent/native /src
-COPY third_party/nvml/nvml.h /usr/local/include/nvml.h
-RUN g++ -O2 -std=c++17 -static-libstdc++ -static-libgcc -I/usr/local/include /src/dp/device_plugin.cc /src/b200agent_nvml.cc -o /b200-device-plugin -ldl -lpthread
+RUN g++ -O2 -std=c++17 -static-libstdc++ -static-libgcc /src/dp/device_plugin.cc /src/b200agent_nvml.cc -o /b200-device-plugin -ldl -lpthread
 FROM gcr.io/distroless/base
 COPY --from=build /b200-device-plugin /usr/bin/b200-device-plugin
 # distroless/base ships libssl/libcrypto, which the Kubernetes API client dlopens for https (agent/native/dp/kube.hpp).

@@ -2,8 +2,7 @@
 FROM python:3.12-slim AS build
 RUN apt-get update && apt-get install -y --no-install-recommends g++ make && rm -rf /var/lib/apt/lists/*
 COPY agent/native /src/agent/native
-COPY third_party/nvml /usr/local/cuda/include
-RUN make -C /src/agent/native CUDA_INC=/usr/local/cuda/include ../../build/agent/libb200agent_nvml.so
+RUN make -C /src/agent/native ../../build/agent/libb200agent_nvml.so
 FROM python:3.12-slim
 RUN pip install --no-cache-dir grpcio protobuf prometheus_client pyyaml requests
 COPY container_engine_accelerators_b200 /app/container_engine_accelerators_b200
