@@ -218,3 +218,29 @@ def test_native_selftest_json_kube_hpack_protobuf(native_build):
     r = subprocess.run([os.path.join(native_build, "b200-native-selftest")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     assert ", 0 failed" in r.stdout
+
+
+def test_nvml_abi_header_matches_the_toolkit_header(tmp_path):
+    """agent/native/nvml_abi.h restates enumerator values and struct layouts; pin them against NVIDIA's nvml.h when a CUDA
+    toolkit is present (the native build itself never needs it)."""
+    real = "/usr/local/cuda/include/nvml.h"
+    if not os.path.exists(real):
+        pytest.skip("no CUDA toolkit header to compare against")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mine = open(os.path.join(root, "agent", "native", "nvml_abi.h")).read()
+    import re
+    enums = dict(re.findall(r"\b(NVML_[A-Z_]+) = (\d+)", mine))
+    assert len(enums) >= 15
+    checks = " && ".join(f"{k} == {v}" for k, v in enums.items())
+    src = tmp_path / "abi.cc"
+    src.write_text(f"""#include <nvml.h>
+#include <cstddef>
+static_assert({checks}, "enumerators");
+static_assert(sizeof(nvmlPciInfo_t) == 68 && offsetof(nvmlPciInfo_t, domain) == 16 && offsetof(nvmlPciInfo_t, busId) == 36, "pci");
+static_assert(sizeof(nvmlEventData_t) == 32 && offsetof(nvmlEventData_t, eventData) == 16 && offsetof(nvmlEventData_t, computeInstanceId) == 28, "event");
+static_assert(sizeof(nvmlSample_t) == 16 && offsetof(nvmlSample_t, sampleValue) == 8 && sizeof(nvmlMemory_t) == 24 && offsetof(nvmlMemory_t, used) == 16, "sample/memory");
+static_assert(nvmlEventTypeXidCriticalError == 8, "event type");
+int main() {{ return 0; }}
+""")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I/usr/local/cuda/include", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
