@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
+#include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -60,7 +61,7 @@ static size_t parse_size(const char* s) {
 static b200collDataType_t parse_dt(const char* s) {
   if (!strcmp(s, "f32") || !strcmp(s, "float")) return b200collFloat32;
   if (!strcmp(s, "f16") || !strcmp(s, "half")) return b200collFloat16;
-  if (!strcmp(s, "bf16")) return b200collBfloat16;
+  if (!strcmp(s, "bf16") || !strcmp(s, "bfloat16")) return b200collBfloat16;
   if (!strcmp(s, "fp8") || !strcmp(s, "e4m3")) return b200collFloat8e4m3;
   fprintf(stderr, "bad dtype %s\n", s); exit(1);
 }
@@ -152,6 +153,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
   }
   FILE* jf = (rank == 0 && !o.json.empty()) ? fopen(o.json.c_str(), "a") : nullptr;
   long total_errors = 0;
+  double busbw_sum = 0; int busbw_n = 0;   // nccl-tests' "Avg bus bandwidth": mean over every (size, placement) measured
   for (size_t bytes = o.min_bytes; bytes <= o.max_bytes; bytes *= o.factor) {
     // element counts per the op
     size_t count;          // the `count` argument of the API
@@ -244,7 +246,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
       if (o.algo == "auto") algo_used = b200collAlgoName(b200collTunerPick(opid, is_ar ? count * is : count * is, n, info.nvls)); else algo_used = o.algo.c_str();
       const double factor = (is_bc || is_rd) ? 1.0 : is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
       double ab[2], bb[2];
-      for (int ip = 0; ip < 2; ip++) { ab[ip] = res_us[ip] > 0 ? tb / res_us[ip] / 1e3 : 0; bb[ip] = n > 1 ? ab[ip] * factor : ab[ip]; }
+      for (int ip = 0; ip < 2; ip++) { ab[ip] = res_us[ip] > 0 ? tb / res_us[ip] / 1e3 : 0; bb[ip] = n > 1 ? ab[ip] * factor : ab[ip]; if (res_us[ip] > 0) { busbw_sum += bb[ip]; busbw_n++; } }
       if (!o.shapes.empty()) printf("[k%d c%d t%d] ", o.shapes[si].kind, o.shapes[si].ctas, o.shapes[si].threads);
       printf("%14zu %12zu %6s %8s | %10.2f %8.2f %8.2f %6ld | %10.2f %8.2f %8.2f %6ld\n", tb, count, dt_name(o.in_dt), algo_used, res_us[0], ab[0], bb[0], res_err[0], res_us[1], ab[1], bb[1], res_err[1]);
       fflush(stdout);
@@ -258,15 +260,52 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
   }
   if (jf) fclose(jf);
   b200collStats s; CC(b200collCommStatsGet(ctx.comm, &s));
-  if (rank == 0) printf("# launches=%llu staged_calls=%llu errors=%ld\n", (unsigned long long)s.kernel_launches, (unsigned long long)s.staged_calls, total_errors);
+  if (rank == 0) {
+    printf("# Out of bounds values : %ld %s\n", total_errors, total_errors ? "FAILED" : "OK");
+    printf("# Avg bus bandwidth    : %g\n", busbw_n ? busbw_sum / busbw_n : 0.0);
+    printf("# launches=%llu staged_calls=%llu errors=%ld\n", (unsigned long long)s.kernel_launches, (unsigned long long)s.staged_calls, total_errors);
+  }
   CC(b200collMemFree(ctx.comm, recv));
   CC(b200collMemFree(ctx.comm, send));
   RT(cudaStreamDestroy(st));
   return total_errors ? 4 : 0;
 }
 
+// nccl-tests compatibility (the reference's pods run `<op>_perf -b .. -e .. -f 2 -g 1 -w 5 --iters 100 -c 0` under mpirun,
+// gpudirect-tcpx/nccl-config.yaml:61-62, gpudirect-rdma/nccl-test-a4x-max-jobset.yaml:153): the binary answers to those
+// names through symlinks, takes the same flags, and when a launcher exported a rank (OpenMPI, PMI, torchrun) it is ONE rank
+// of the job instead of forking its own.
+static const char* op_from_argv0(const char* argv0) {
+  const char* base = strrchr(argv0, '/'); base = base ? base + 1 : argv0;
+  static const struct { const char* name; const char* op; } kNames[] = {{"all_reduce_perf", "all_reduce"}, {"all_gather_perf", "all_gather"}, {"reduce_scatter_perf", "reduce_scatter"},
+                                                                        {"alltoall_perf", "alltoall"}, {"broadcast_perf", "broadcast"}, {"reduce_perf", "reduce"}};
+  for (auto& k : kNames) if (!strcmp(base, k.name)) return k.op;
+  return nullptr;
+}
+struct LauncherRank { int rank = -1, size = 0, local_rank = 0; std::string job; };
+static LauncherRank launcher_rank() {
+  LauncherRank l;
+  static const char* kRank[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "RANK"};
+  static const char* kSize[] = {"OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "", "WORLD_SIZE"};
+  static const char* kLocal[] = {"OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "", "LOCAL_RANK"};
+  for (int i = 0; i < 4; i++) {
+    const char* r = getenv(kRank[i]); const char* s = *kSize[i] ? getenv(kSize[i]) : nullptr;
+    if (!r || !s) continue;
+    l.rank = atoi(r); l.size = atoi(s);
+    const char* lr = *kLocal[i] ? getenv(kLocal[i]) : nullptr;
+    l.local_rank = lr ? atoi(lr) : l.rank;
+    break;
+  }
+  // every rank must derive the same id: an explicit job id, else the launcher's, else the rendezvous address
+  for (const char* k : {"B200COLL_JOB_ID", "OMPI_MCA_ess_base_jobid", "PMIX_NAMESPACE", "PMI_JOBID", "TORCHELASTIC_RUN_ID"}) if (const char* v = getenv(k)) { l.job = std::string(k) + "=" + v; break; }
+  if (l.job.empty()) { const char* a = getenv("MASTER_ADDR"); const char* p = getenv("MASTER_PORT"); l.job = std::string(a ? a : "local") + ":" + (p ? p : "0"); }
+  return l;
+}
+
 int main(int argc, char** argv) {
   Opts o;
+  int gpus_per_proc = 0;
+  if (const char* op = op_from_argv0(argv[0])) o.op = op;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return argv[++i]; };
@@ -277,7 +316,11 @@ int main(int argc, char** argv) {
     else if (a == "-b" || a == "--min") o.min_bytes = parse_size(next());
     else if (a == "-e" || a == "--max") o.max_bytes = parse_size(next());
     else if (a == "-f" || a == "--factor") o.factor = atoi(next());
-    else if (a == "--dtype") o.in_dt = o.out_dt = parse_dt(next());
+    else if (a == "--dtype" || a == "-d" || a == "--datatype") o.in_dt = o.out_dt = parse_dt(next());
+    else if (a == "-g" || a == "--ngpus") gpus_per_proc = atoi(next());
+    else if (a == "-o" || a == "--redop") { std::string v = next(); if (v != "sum") { fprintf(stderr, "only -o sum is benchmarked (avg is a fused scale: use --scale)\n"); return 1; } }
+    else if (a == "-t" || a == "--nthreads" || a == "-m" || a == "--agg_iters" || a == "-p" || a == "--parallel_init" || a == "-z" || a == "--blocking" || a == "-a" || a == "--average" ||
+             a == "-G" || a == "--cudagraph" || a == "-C" || a == "--report_cputime" || a == "-R" || a == "--local_register" || a == "-T" || a == "--timeout" || a == "-r" || a == "--root") (void)next();   // accepted, no effect here
     else if (a == "--out-dtype") o.out_dt = parse_dt(next());
     else if (a == "--scale") o.scale = (float)atof(next());
     else if (a == "--algo") o.algo = next();
@@ -301,6 +344,39 @@ int main(int argc, char** argv) {
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 1; }
   }
   if (o.factor < 2) o.factor = 2;
+  const LauncherRank lr = launcher_rank();
+  if (lr.size > 1 && o.devs.empty() && !o.procs) {
+    // one rank of an mpirun / torchrun job (nccl-tests' -g 1 layout): rendezvous on the job id, timing page in /dev/shm
+    if (gpus_per_proc > 1) { fprintf(stderr, "-g %d under a launcher is not supported: run one rank per GPU (-g 1)\n", gpus_per_proc); return 1; }
+    if (lr.size > B200COLL_MAX_RANKS) { fprintf(stderr, "libb200coll is an intra-node transport: %d ranks > %d GPUs of one NVSwitch domain\n", lr.size, B200COLL_MAX_RANKS); return 1; }
+    int nd = 0; RT(cudaGetDeviceCount(&nd));
+    const int dev = nd > 0 ? lr.local_rank % nd : 0;
+    unsigned h = 2166136261u; for (char ch : lr.job) h = (h ^ (unsigned char)ch) * 16777619u;
+    char shm_name[64]; snprintf(shm_name, sizeof shm_name, "/b200coll_perf.%08x", h);
+    int fd = shm_open(shm_name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, sizeof(Shared)) != 0) { perror("shm_open"); return 1; }
+    Shared* sh = (Shared*)mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (sh == MAP_FAILED) { perror("mmap"); return 1; }
+    o.nranks = lr.size; o.procs = true;
+    b200collConfig cfg; b200collConfigDefault(&cfg);
+    const size_t is_ = b200collTypeSize(o.in_dt), os_ = b200collTypeSize(o.out_dt);
+    if (!getenv("B200COLL_ARENA_MB")) cfg.arena_bytes = std::max(o.window, o.max_bytes) + std::max(o.window / is_ * os_, o.max_bytes / is_ * os_) + (64u << 20);
+    b200collUniqueId id; CC(b200collUniqueIdFromString(("perf/" + lr.job).c_str(), &id));
+    RT(cudaSetDevice(dev));
+    b200collComm_t comm;
+    CC(b200collCommInitRank(&comm, lr.size, &id, lr.rank, &cfg));
+    // a crashed earlier job with the same id may have left counters behind: wipe the page between two host barriers,
+    // i.e. after everybody mapped it and before anybody counts on it
+    CC(b200collHostBarrier(comm));
+    if (lr.rank == 0) memset((void*)sh, 0, sizeof(Shared));
+    CC(b200collHostBarrier(comm));
+    int rc = run_rank(o, RankCtx{lr.rank, lr.size, comm, dev}, sh);
+    CC(b200collCommDestroy(comm));          // ends with a host barrier: every rank is past its last use of the page
+    if (lr.rank == 0) shm_unlink(shm_name);
+    return rc;
+  }
+  if (gpus_per_proc > 0 && o.devs.empty() && o.nranks == 0) o.nranks = gpus_per_proc;     // nccl-tests -g N without a launcher: N ranks in this process
   if (o.devs.empty()) {
     int nd = 0; cudaGetDeviceCount(&nd);
     if (o.nranks == 0) o.nranks = nd > 0 ? nd : 1;

@@ -402,8 +402,8 @@ GPU_DEV_PATHS = [f"/dev/nvidia{i}" for i in range(8)] + ["/dev/nvidiactl", "/dev
 def b200coll_test_pod(gpus: int = 8, autopilot: bool = False) -> list:
     """Single 8xB200 box: run the nccl-tests-style sweep of libb200coll next to stock NCCL (the repo's benchmark, BASELINE configs 2-4)."""
     cmd = ("source /usr/local/nvidia/lib64/b200coll-env-profile.sh\n"
-           "for op in all_reduce all_gather reduce_scatter alltoall; do\n"
-           f"  /usr/local/nvidia/bin/b200coll_perf --procs --ranks {gpus} --op $op -b 1K -e 1G -f 2 -w 5 --iters 100 -c 1 | tee /tmp/${{op}}_perf.txt\n"
+           "for op in all_reduce all_gather reduce_scatter alltoall broadcast reduce; do\n"
+           f"  /usr/local/nvidia/bin/${{op}}_perf --procs --ranks {gpus} -b 1K -e 1G -f 2 -w 5 --iters 100 -c 1 | tee /tmp/${{op}}_perf.txt\n"
            "done\nsleep infinity\n")
     pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "b200coll-test", "labels": {"name": "b200coll-test"}},
            "spec": {"hostNetwork": False, "hostPID": False, "restartPolicy": "Never",

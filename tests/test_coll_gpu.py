@@ -303,6 +303,25 @@ def test_perf_tool_virtual_ranks_zero_errors(torch_cuda, coll_lib):
         assert "errors=0" in r.stdout
 
 
+def test_nccl_tests_names_and_launcher_rank_mode(torch_cuda, coll_lib):
+    """`all_reduce_perf -b .. -e .. -g 1 -w .. -n .. -c 1` as the reference's pods invoke nccl-tests: the op comes from argv[0], and
+    with a launcher's rank variables in the environment (torchrun's here; OpenMPI's / PMI's are read the same way) each process is
+    one rank of the job. Two ranks share cuda:0 when the box has a single GPU."""
+    exe = os.path.join(ROOT, "build", "all_reduce_perf")
+    assert os.path.islink(exe), "build/all_reduce_perf symlink missing (make -C coll)"
+    ngpu = torch_cuda.cuda.device_count()
+    base = {**os.environ, "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(20000 + os.getpid() % 20000), "B200COLL_TIMEOUT_MS": "5000"}
+    procs = [subprocess.Popen([exe, "-b", "1K", "-e", "1M", "-f", "4", "-g", "1", "-w", "1", "-n", "3", "-c", "1", "-d", "bfloat16", "-o", "sum"],
+                              env={**base, "RANK": str(r), "LOCAL_RANK": str(r % ngpu)}, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "# Avg bus bandwidth" in outs[0][0] and "# Out of bounds values : 0 OK" in outs[0][0] and "op=all_reduce nranks=2" in outs[0][0]
+    assert outs[1][0] == ""                                  # only rank 0 prints the table
+    r = subprocess.run([os.path.join(ROOT, "build", "broadcast_perf"), "-g", "2", "-b", "4K", "-e", "64K", "-f", "4", "-n", "2", "-w", "1"], capture_output=True, text=True, timeout=120,
+                       env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    assert r.returncode == 0 and "op=broadcast nranks=2" in r.stdout and "FAILED" not in r.stdout, r.stdout + r.stderr
+
+
 def test_multi_gpu_procs_nvls(torch_cuda, coll_lib):
     n = torch_cuda.cuda.device_count()
     if n < 2:

@@ -103,7 +103,8 @@ def test_nccl_test_pods():
     js = [d for d in docs("nccl-test/rdma/nccl-test-a4x-max-jobset.yaml") if d["kind"] == "JobSet"][0]
     assert "all_gather_perf" in str(js) and "-b 1K -e 8G -f 2 -g 1 -w 5 --iters 100 -c 1" in str(js)
     ours = docs("nccl-test/b200coll-test.yaml")[0]
-    assert "b200coll_perf --procs --ranks 8" in ours["spec"]["containers"][0]["args"][0]
+    script = ours["spec"]["containers"][0]["args"][0]
+    assert "${op}_perf --procs --ranks 8" in script and "broadcast reduce" in script          # nccl-tests names, all six collectives
 
 
 def test_scripts_have_valid_syntax():
@@ -148,6 +149,8 @@ def test_b200coll_install_and_env_profile(tmp_path):
     env = {**os.environ, "B200COLL_SRC_DIR": str(src), "NCCL_INSTALL_DIR": str(tmp_path / "lib64"), "B200COLL_BIN_DIR": str(tmp_path / "bin")}
     assert subprocess.run(["bash", os.path.join(SCRIPTS, "b200coll-install.sh")], env=env).returncode == 0
     assert (tmp_path / "lib64/libb200coll.so").exists() and (tmp_path / "lib64/b200_nvswitch.tbl").exists() and (tmp_path / "selfcheck").exists()
+    for name in ("all_reduce_perf", "all_gather_perf", "reduce_scatter_perf", "alltoall_perf", "broadcast_perf", "reduce_perf"):       # nccl-tests names
+        assert os.readlink(tmp_path / "bin" / name) == "b200coll_perf"
     out = subprocess.run(["bash", "-c", f"B200COLL_LIB_DIR={tmp_path}/lib64 source {SCRIPTS}/b200coll-env-profile.sh; echo $B200COLL_LIB $B200COLL_ALGO $B200COLL_TUNER_FILE"], capture_output=True, text=True).stdout.split()
     assert out == [f"{tmp_path}/lib64/libb200coll.so", "auto", f"{tmp_path}/lib64/b200_nvswitch.tbl"]
 
