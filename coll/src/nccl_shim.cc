@@ -4,6 +4,7 @@
 // installer-dropped NCCL: gpudirect-rdma/nccl-test-a4.yaml:42-68). SURVEY §5.8-6.
 // User buffers are ordinary cudaMalloc memory here, so calls take the Lamport path (<= 512 KiB) or the staged path;
 // ncclMemAlloc hands out symmetric-arena memory once a communicator exists (zero-copy + NVLS).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -51,6 +52,21 @@ bool map_dt(ncclDataType_t dt, b200collDataType_t* out) {
     case ncclBfloat16: *out = b200collBfloat16; return true;
     default: return false;   // integer / fp64 reductions are not implemented by libb200coll
   }
+}
+
+// ncclRedOpCreatePreMulSum: "multiply every input by a scalar, then sum". With one scalar per communicator call that is
+// scale * sum, i.e. the library's fused epilogue scale. Handles are ncclNumOps + slot.
+constexpr int kNcclNumOps = 5;
+std::vector<float> g_premul;          // slot -> scalar (NaN = free)
+bool map_op(ncclRedOp_t op, b200collRedOp_t* rop, float* scale) {
+  *scale = 1.0f;
+  if (op == ncclSum) { *rop = b200collSum; return true; }
+  if (op == ncclAvg) { *rop = b200collAvg; return true; }
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int slot = (int)op - kNcclNumOps;
+  if (slot < 0 || slot >= (int)g_premul.size() || g_premul[slot] != g_premul[slot]) return false;   // prod/min/max or a stale handle
+  *rop = b200collSum; *scale = g_premul[slot];
+  return true;
 }
 
 ncclResult_t flush_group() {
@@ -119,6 +135,42 @@ ncclResult_t ncclCommDestroy(ncclComm_t comm) {
   delete s;
   return map_rc(r);
 }
+// Config structs, registration handles and splits of newer NCCL APIs: accepted where a no-op is faithful, refused where it is not.
+ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank, void* /*ncclConfig_t*: blocking, cgaClusterSize, ... have no analogue */) {
+  return ncclCommInitRank(comm, nranks, id, rank);
+}
+ncclResult_t ncclCommSplit(ncclComm_t, int, int, ncclComm_t*, void*) { return ncclInvalidUsage; }      // one communicator per NVSwitch domain
+ncclResult_t ncclCommRegister(const ncclComm_t comm, void* buff, size_t, void** handle) {              // arena memory is registered by construction
+  if (!comm || !handle) return ncclInvalidArgument;
+  *handle = buff;
+  return ncclSuccess;
+}
+ncclResult_t ncclCommDeregister(const ncclComm_t, void*) { return ncclSuccess; }
+ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t* op, void* scalar, ncclDataType_t dt, int residence /* 0 device, 1 host immediate */, ncclComm_t comm) {
+  if (!op || !scalar || !comm) return ncclInvalidArgument;
+  unsigned char raw[8] = {};
+  const size_t sz = dt == ncclFloat64 ? 8 : dt == ncclFloat32 ? 4 : (dt == ncclFloat16 || dt == ncclBfloat16) ? 2 : 0;
+  if (!sz) return ncclInvalidArgument;
+  if (residence == 1) memcpy(raw, scalar, sz);
+  else if (cudaMemcpy(raw, scalar, sz, cudaMemcpyDeviceToHost) != cudaSuccess) return ncclUnhandledCudaError;
+  float v;
+  if (dt == ncclFloat64) { double d; memcpy(&d, raw, 8); v = (float)d; }
+  else if (dt == ncclFloat32) memcpy(&v, raw, 4);
+  else { unsigned short h; memcpy(&h, raw, 2); if (dt == ncclBfloat16) { unsigned int w = (unsigned int)h << 16; memcpy(&v, &w, 4); } else { __half hh; memcpy(&hh, &h, 2); v = __half2float(hh); } }
+  std::lock_guard<std::mutex> lk(g_mu);
+  size_t slot = 0;
+  while (slot < g_premul.size() && g_premul[slot] == g_premul[slot]) slot++;
+  if (slot == g_premul.size()) g_premul.push_back(v); else g_premul[slot] = v;
+  *op = (ncclRedOp_t)(kNcclNumOps + (int)slot);
+  return ncclSuccess;
+}
+ncclResult_t ncclRedOpDestroy(ncclRedOp_t op, ncclComm_t) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int slot = (int)op - kNcclNumOps;
+  if (slot < 0 || slot >= (int)g_premul.size()) return ncclInvalidArgument;
+  g_premul[slot] = __builtin_nanf("");
+  return ncclSuccess;
+}
 ncclResult_t ncclCommFinalize(ncclComm_t) { return ncclSuccess; }
 ncclResult_t ncclCommAbort(ncclComm_t comm) { return ncclCommDestroy(comm); }
 ncclResult_t ncclCommCount(const ncclComm_t comm, int* n) { if (!comm || !n) return ncclInvalidArgument; *n = reinterpret_cast<ShimComm*>(comm)->nranks; return ncclSuccess; }
@@ -143,9 +195,10 @@ ncclResult_t ncclMemFree(void* ptr) {
 
 ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
-  if (!comm || !map_dt(dt, &t) || (op != ncclSum && op != ncclAvg)) return ncclInvalidArgument;
-  b200collEpilogue ep{t, t, 1.0f};
-  return map_rc(b200collAllReduce(send, recv, count, &ep, op == ncclAvg ? b200collAvg : b200collSum, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+  b200collRedOp_t rop; float scale;
+  if (!comm || !map_dt(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, scale};
+  return map_rc(b200collAllReduce(send, recv, count, &ep, rop, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
 ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t dt, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
@@ -155,9 +208,10 @@ ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclD
 }
 ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
-  if (!comm || !map_dt(dt, &t) || (op != ncclSum && op != ncclAvg)) return ncclInvalidArgument;
-  b200collEpilogue ep{t, t, 1.0f};
-  return map_rc(b200collReduceScatter(send, recv, recvcount, &ep, op == ncclAvg ? b200collAvg : b200collSum, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+  b200collRedOp_t rop; float scale;
+  if (!comm || !map_dt(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, scale};
+  return map_rc(b200collReduceScatter(send, recv, recvcount, &ep, rop, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
 
 // Broadcast moves bits, so every NCCL dtype works: the payload is described to the library as f16/f32 words
@@ -182,10 +236,11 @@ ncclResult_t ncclBcast(void* buf, size_t count, ncclDataType_t dt, int root, ncc
 }
 ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, int root, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
-  if (!comm || !map_dt(dt, &t) || (op != ncclSum && op != ncclAvg)) return ncclInvalidArgument;
-  b200collEpilogue ep{t, t, 1.0f};
+  b200collRedOp_t rop; float scale;
+  if (!comm || !map_dt(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, scale};
   // NCCL lets non-root ranks pass recv == NULL; the library wants an aligned pointer it will not touch
-  return map_rc(b200collReduce(send, recv ? recv : const_cast<void*>(send), count, &ep, op == ncclAvg ? b200collAvg : b200collSum, root, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+  return map_rc(b200collReduce(send, recv ? recv : const_cast<void*>(send), count, &ep, rop, root, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
 
 ncclResult_t ncclGroupStart(void) { g_group_depth++; return ncclSuccess; }

@@ -105,3 +105,24 @@ def test_bootstrap_times_out_when_a_rank_is_missing(coll_lib):
     fd = os.memfd_create("x")
     rc = L.b200collBootstrapSelfTest(f"pytest-timeout-{os.getpid()}".encode(), 0, 2, fd, out, C.byref(bc), 300)
     assert rc == 1 and b"timed out" in L.b200collGetLastError()
+
+
+def test_nccl_shim_exports_the_api_nccl_tests_links_against(coll_lib):
+    """Every NCCL entry point nccl-tests' *_perf binaries reference must resolve, or the dynamic loader refuses to start them."""
+    import subprocess
+    shim = os.path.join(os.path.dirname(coll_lib), "libb200coll_nccl.so")
+    syms = {l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", shim], capture_output=True, text=True, check=True).stdout.splitlines() if " T " in l}
+    need = {"ncclGetVersion", "ncclGetUniqueId", "ncclGetErrorString", "ncclGetLastError", "ncclCommInitRank", "ncclCommInitRankConfig", "ncclCommInitAll", "ncclCommDestroy",
+            "ncclCommFinalize", "ncclCommAbort", "ncclCommCount", "ncclCommUserRank", "ncclCommCuDevice", "ncclCommGetAsyncError", "ncclCommSplit", "ncclCommRegister",
+            "ncclCommDeregister", "ncclMemAlloc", "ncclMemFree", "ncclAllReduce", "ncclAllGather", "ncclReduceScatter", "ncclBroadcast", "ncclBcast", "ncclReduce", "ncclSend",
+            "ncclRecv", "ncclGroupStart", "ncclGroupEnd", "ncclRedOpCreatePreMulSum", "ncclRedOpDestroy"}
+    assert need <= syms, sorted(need - syms)
+    L = C.CDLL(shim)
+    L.ncclGetErrorString.restype = C.c_char_p
+    v = C.c_int()
+    assert L.ncclGetVersion(C.byref(v)) == 0 and v.value >= 22000
+    assert L.ncclGroupEnd() != 0                                   # unbalanced group
+    if not os.path.exists("/dev/nvidiactl"):
+        comms = (C.c_void_p * 1)()
+        rc = L.ncclCommInitAll(comms, 1, (C.c_int * 1)(0))
+        assert rc != 0 and L.ncclGetErrorString(rc)               # no driver: an error code, not a crash

@@ -347,3 +347,112 @@ def test_bench_contract_one_gpu(torch_cuda):
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
         assert k in d
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+
+
+# ------------------------------------------------------------------------------------------------- NCCL-API shim
+class _NcclShim:
+    """ctypes view of libb200coll_nccl.so with NCCL's own prototypes (what an nccl-tests binary would call)."""
+    F32, F16, BF16, U8, I64 = 7, 6, 9, 1, 4
+    SUM, AVG = 0, 4
+
+    def __init__(self):
+        import ctypes as C
+        self.C = C
+        self.L = L = C.CDLL(os.path.join(ROOT, "coll", "lib", "libb200coll_nccl.so"))
+        vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+        L.ncclGetErrorString.restype = C.c_char_p
+        L.ncclCommInitAll.argtypes = [C.POINTER(vp), ci, C.POINTER(ci)]
+        L.ncclCommDestroy.argtypes = [vp]
+        L.ncclAllReduce.argtypes = [vp, vp, sz, ci, ci, vp, vp]
+        L.ncclAllGather.argtypes = [vp, vp, sz, ci, vp, vp]
+        L.ncclReduceScatter.argtypes = [vp, vp, sz, ci, ci, vp, vp]
+        L.ncclBroadcast.argtypes = [vp, vp, sz, ci, ci, vp, vp]
+        L.ncclReduce.argtypes = [vp, vp, sz, ci, ci, ci, vp, vp]
+        L.ncclSend.argtypes = [vp, sz, ci, ci, vp, vp]
+        L.ncclRecv.argtypes = [vp, sz, ci, ci, vp, vp]
+        L.ncclRedOpCreatePreMulSum.argtypes = [C.POINTER(ci), vp, ci, ci, vp]
+        L.ncclRedOpDestroy.argtypes = [ci, vp]
+        L.ncclCommCount.argtypes = [vp, C.POINTER(ci)]
+        L.ncclCommUserRank.argtypes = [vp, C.POINTER(ci)]
+        L.ncclCommGetAsyncError.argtypes = [vp, C.POINTER(ci)]
+
+    def ck(self, rc):
+        assert rc == 0, self.L.ncclGetErrorString(rc).decode()
+
+
+def test_nccl_api_shim_collectives(torch_cuda, coll_lib):
+    """An NCCL-API program (plain cudaMalloc buffers, NCCL dtypes/ops/handles) running on libb200coll through the shim."""
+    torch = torch_cuda
+    s = _NcclShim()
+    C, L, n = s.C, s.L, 2
+    comms = (C.c_void_p * n)()
+    s.ck(L.ncclCommInitAll(comms, n, (C.c_int * n)(0, 0)))
+    try:
+        cnt, rk, ver = C.c_int(), C.c_int(), C.c_int()
+        s.ck(L.ncclCommCount(comms[1], C.byref(cnt))); s.ck(L.ncclCommUserRank(comms[1], C.byref(rk))); s.ck(L.ncclGetVersion(C.byref(ver)))
+        assert (cnt.value, rk.value) == (2, 1) and ver.value >= 22000
+        streams = [torch.cuda.Stream() for _ in range(n)]
+        st = [C.c_void_p(x.cuda_stream) for x in streams]
+        p = lambda t: C.c_void_p(t.data_ptr())
+
+        def every(fn):
+            for r in range(n):
+                s.ck(fn(r))
+            torch.cuda.synchronize()
+            for r in range(n):
+                err = C.c_int(-1)
+                s.ck(L.ncclCommGetAsyncError(comms[r], C.byref(err)))
+                assert err.value == 0
+
+        for count in (1000, 3 << 19):                                           # Lamport path, then staged (3 MiB of bf16 > 512 KiB)
+            src = [(((torch.arange(count, device="cuda") * (r + 3)) % 13) - 6).to(torch.bfloat16) for r in range(n)]
+            dst = [torch.empty(count, dtype=torch.bfloat16, device="cuda") for _ in range(n)]
+            every(lambda r: L.ncclAllReduce(p(src[r]), p(dst[r]), count, s.BF16, s.SUM, comms[r], st[r]))
+            want = sum(t.float() for t in src)
+            assert all(torch.equal(d.float(), want) for d in dst)
+        # ncclAvg and a pre-multiplied sum (host scalar 0.25, fp32)
+        src = [torch.full((4096,), float(r + 1), device="cuda") for r in range(n)]
+        dst = [torch.empty(4096, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclAllReduce(p(src[r]), p(dst[r]), 4096, s.F32, s.AVG, comms[r], st[r]))
+        assert all(torch.equal(d, torch.full_like(d, 1.5)) for d in dst)
+        op, scalar = C.c_int(), C.c_float(0.25)
+        s.ck(L.ncclRedOpCreatePreMulSum(C.byref(op), C.byref(scalar), s.F32, 1, comms[0]))
+        assert op.value >= 5
+        every(lambda r: L.ncclAllReduce(p(src[r]), p(dst[r]), 4096, s.F32, op.value, comms[r], st[r]))
+        assert all(torch.equal(d, torch.full_like(d, 0.75)) for d in dst)
+        s.ck(L.ncclRedOpDestroy(op.value, comms[0]))
+        assert L.ncclAllReduce(p(src[0]), p(dst[0]), 4096, s.F32, op.value, comms[0], st[0]) != 0          # stale handle is refused
+        assert L.ncclAllReduce(p(src[0]), p(dst[0]), 4096, s.F32, 2, comms[0], st[0]) != 0                 # ncclMax is not implemented
+        # all-gather / reduce-scatter
+        part = [torch.arange(2048, device="cuda", dtype=torch.float16) + 2048 * r for r in range(n)]
+        full = [torch.empty(2048 * n, dtype=torch.float16, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclAllGather(p(part[r]), p(full[r]), 2048, s.F16, comms[r], st[r]))
+        assert all(torch.equal(f, torch.cat(part)) for f in full)
+        rs = [torch.empty(2048, dtype=torch.float16, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclReduceScatter(p(full[r]), p(rs[r]), 2048, s.F16, s.SUM, comms[r], st[r]))
+        assert all(torch.equal(rs[r], (full[0].float() * n)[r * 2048:(r + 1) * 2048].half()) for r in range(n))
+        # broadcast moves bits for any dtype (int64 here, odd byte count refused for uint8), reduce lands on the root only
+        ints = [torch.arange(1001, device="cuda", dtype=torch.int64) * (r + 1) - 7 for r in range(n)]
+        every(lambda r: L.ncclBroadcast(p(ints[r]), p(ints[r]), 1001, s.I64, 1, comms[r], st[r]))
+        assert torch.equal(ints[0], ints[1]) and ints[0][1000].item() == 1000 * 2 - 7
+        assert L.ncclBroadcast(p(ints[0]), p(ints[0]), 3, s.U8, 0, comms[0], st[0]) != 0
+        red = [torch.full((4096,), -1.0, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclReduce(p(src[r]), p(red[r]) if r == 0 else None, 4096, s.F32, s.SUM, 0, comms[r], st[r]))
+        assert torch.equal(red[0], torch.full_like(red[0], 3.0)) and torch.equal(red[1], torch.full_like(red[1], -1.0))
+        # nccl-tests' alltoall: grouped send/recv to every peer
+        a2a_in = [torch.arange(n * 512, device="cuda", dtype=torch.float32) + 10000 * r for r in range(n)]
+        a2a_out = [torch.empty(n * 512, device="cuda") for _ in range(n)]
+
+        def grouped(r):
+            s.ck(L.ncclGroupStart())
+            for peer in range(n):
+                s.ck(L.ncclSend(C.c_void_p(a2a_in[r].data_ptr() + peer * 512 * 4), 512, s.F32, peer, comms[r], st[r]))
+                s.ck(L.ncclRecv(C.c_void_p(a2a_out[r].data_ptr() + peer * 512 * 4), 512, s.F32, peer, comms[r], st[r]))
+            return L.ncclGroupEnd()
+        every(grouped)
+        for r in range(n):
+            assert torch.equal(a2a_out[r], torch.cat([a2a_in[q][r * 512:(r + 1) * 512] for q in range(n)]))
+    finally:
+        torch.cuda.synchronize()
+        for c in comms:
+            L.ncclCommDestroy(c)
