@@ -256,8 +256,9 @@ class Server {
   }
   void stop() {
     stop_ = true;
-    if (fd_ >= 0) { ::shutdown(fd_, SHUT_RDWR); ::close(fd_); fd_ = -1; }
+    if (fd_ >= 0) ::shutdown(fd_, SHUT_RDWR);           // wakes accept4(); the descriptor stays valid until the thread is gone
     if (accept_thread_.joinable()) accept_thread_.join();
+    if (fd_ >= 0) { ::close(fd_); fd_ = -1; }
     std::vector<std::shared_ptr<Conn>> conns;
     { std::lock_guard<std::mutex> lk(mu_); conns.swap(conns_); }
     for (auto& c : conns) { c->close(); if (c->thread.joinable()) c->thread.join(); }
@@ -274,7 +275,8 @@ class Server {
     bool cancelled() const override;
   };
   struct Conn {
-    Server* srv = nullptr; int fd = -1; std::thread thread; std::mutex wmu; std::condition_variable wcv; std::atomic<bool> closed{false};
+    Server* srv = nullptr; int fd = -1; std::thread thread; std::mutex wmu; std::condition_variable wcv; std::atomic<bool> closed{false}, done{false};
+    ~Conn() { if (fd >= 0) ::close(fd); }     // only after `thread` was joined: close() from another thread may still shutdown(fd) until then
     int64_t conn_window = 65535; uint32_t peer_initial_window = 65535, peer_max_frame = 16384;
     HpackDecoder dec; std::map<uint32_t, std::shared_ptr<StreamState>> streams;
     void close() { closed = true; if (fd >= 0) ::shutdown(fd, SHUT_RDWR); wcv.notify_all(); }
@@ -295,13 +297,20 @@ class Server {
   };
 
   void accept_loop() {
+    const int lfd = fd_;                                   // set before this thread was started; stop() closes it only after joining us
     while (!stop_) {
-      int c = ::accept4(fd_, nullptr, nullptr, SOCK_CLOEXEC);
+      int c = ::accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
       if (c < 0) { if (errno == EINTR) continue; break; }
       auto conn = std::make_shared<Conn>();
       conn->srv = this; conn->fd = c;
-      { std::lock_guard<std::mutex> lk(mu_); conns_.push_back(conn); }
-      conn->thread = std::thread([this, conn] { serve(conn.get()); });
+      std::vector<std::shared_ptr<Conn>> finished;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto it = conns_.begin(); it != conns_.end();) { if ((*it)->done) { finished.push_back(*it); it = conns_.erase(it); } else ++it; }
+        conns_.push_back(conn);
+        conn->thread = std::thread([this, conn] { serve(conn.get()); });     // under mu_: stop() must never see a Conn without its thread
+      }
+      for (auto& f : finished) if (f->thread.joinable()) f->thread.join();     // connections that ended since the last accept: join, then ~Conn closes the fd
     }
   }
 
@@ -418,7 +427,7 @@ class Server {
     for (auto& kv : streams) { kv.second->dead = true; }
     c->wcv.notify_all();
     for (auto& kv : streams) if (kv.second->worker.joinable()) kv.second->worker.join();
-    ::close(c->fd); c->fd = -1;
+    c->done = true;                                        // the descriptor is closed by ~Conn once this thread has been joined
   }
 
   void finish_headers(Conn* c, uint32_t stream, uint8_t flags, std::string* block) {

@@ -161,7 +161,7 @@ class Mux {
  public:
   explicit Mux(int fd) : fd_(fd) { reader_ = std::thread([this] { loop(); }); }
   ~Mux() { close(); if (reader_.joinable()) reader_.join(); }
-  void close() { closed_ = true; ::shutdown(fd_, SHUT_RDWR); cv_.notify_all(); }
+  void close() { mark_closed(); ::shutdown(fd_, SHUT_RDWR); }
   bool write(uint32_t conn, const std::string& data) { std::lock_guard<std::mutex> lk(wmu_); std::string f = be32(conn) + be32((uint32_t)data.size()) + data; return write_all(fd_, f.data(), f.size()); }
   bool read(uint32_t conn, size_t n, std::string* out) {   // blocking byte-stream read on one logical connection
     std::unique_lock<std::mutex> lk(mu_);
@@ -183,8 +183,10 @@ class Mux {
       { std::lock_guard<std::mutex> lk(mu_); buf_[conn].insert(buf_[conn].end(), payload.begin(), payload.end()); }
       cv_.notify_all();
     }
-    closed_ = true; cv_.notify_all();
+    mark_closed();
   }
+  // under mu_: a reader that has just evaluated the wait predicate must not miss the wake-up
+  void mark_closed() { { std::lock_guard<std::mutex> lk(mu_); closed_ = true; } cv_.notify_all(); }
   int fd_; std::thread reader_; std::mutex mu_, wmu_; std::condition_variable cv_; bool closed_ = false;
   std::map<uint32_t, std::deque<char>> buf_;
 };

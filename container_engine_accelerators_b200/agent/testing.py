@@ -31,8 +31,10 @@ class KubeletStub:
         return pb.Empty()
 
     def start(self) -> "KubeletStub":
-        if os.path.exists(self.socket_path):
-            os.unlink(self.socket_path)
+        try:
+            os.unlink(self.socket_path)         # grpc may remove it itself while shutting down
+        except FileNotFoundError:
+            pass
         self._server = grpc.server(futures.ThreadPoolExecutor(max_workers=2))
         handler = grpc.method_handlers_generic_handler(protos.REGISTRATION_SERVICE, {
             "Register": grpc.unary_unary_rpc_method_handler(self._register, pb.RegisterRequest.FromString, pb.Empty.SerializeToString)})
@@ -51,8 +53,10 @@ class KubeletStub:
         if self._server:
             self._server.stop(grace=0)
             self._server = None
-        if os.path.exists(self.socket_path):
-            os.unlink(self.socket_path)
+        try:
+            os.unlink(self.socket_path)         # grpc may remove it itself while shutting down
+        except FileNotFoundError:
+            pass
 
 
 def make_fake_dev(root: str, gpus: int = 2, with_optional: bool = True) -> str:
@@ -306,5 +310,7 @@ class FakeNriRuntime:
         if self.mux:
             self.mux.close()
         self._listener.close()
-        if os.path.exists(self.socket_path):
-            os.unlink(self.socket_path)
+        try:
+            os.unlink(self.socket_path)         # grpc may remove it itself while shutting down
+        except FileNotFoundError:
+            pass

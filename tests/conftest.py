@@ -16,8 +16,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def native_build():
     """Build the native artefacts once per session (g++ / nvcc cross-compile; no GPU needed)."""
-    subprocess.run(["make", "-C", os.path.join(ROOT, "agent", "native"), "-j4"], check=True, capture_output=True)
-    return os.path.join(ROOT, "build", "agent")
+    san = os.environ.get("B200_NATIVE_SAN", "")          # "thread" or "address": run the suite against instrumented binaries
+    subprocess.run(["make", "-C", os.path.join(ROOT, "agent", "native"), "-j4"] + ([f"SAN={san}"] if san else []), check=True, capture_output=True)
+    return os.path.join(ROOT, "build", "agent" + (f"-{san}" if san else ""))
 
 
 @pytest.fixture(scope="session")

@@ -32,6 +32,7 @@ class Native:
                                              "--proc-directory", self.proc, "--pci-root", pci or str(tmp_path / "nopci"), "--plugin-endpoint", self.endpoint, "--gpu-check-interval", "0.6",
                                              "--socket-check-interval", "0.1", *extra_args], env=e, stderr=self.log, stdout=self.log)
         self.client = None
+        self.checked = False
 
     def connect(self, timeout=10):
         path = os.path.join(self.plugin_dir, self.endpoint)
@@ -59,6 +60,10 @@ class Native:
         if self.kubelet:
             self.kubelet.stop()
         self.log.close()
+        if os.environ.get("B200_NATIVE_SAN") and not self.checked:       # instrumented build: any report fails the test that produced it
+            self.checked = True
+            text = open(self.log.name).read()
+            assert "Sanitizer" not in text and "runtime error:" not in text, text[-4000:]
 
 
 @pytest.fixture
