@@ -598,8 +598,12 @@ def demo_docs() -> dict:
         out[f"demo/tpu-training/{model}-tpu.yaml"] = [{"apiVersion": "batch/v1", "kind": "Job", "metadata": {"name": f"{model}-tpu"}, "spec": {"template": {"metadata": {"annotations": {"tf-version.cloud-tpus.google.com": "1.9"}},
                                                        "spec": {"restartPolicy": "Never", "containers": [{"name": model, "image": "gcr.io/tensorflow/tpu-models:r1.9", "command": ["python", f"/tensorflow_tpu_models/models/official/{model.split('-')[0]}/{model.replace('-', '_')}_main.py"],
                                                                                                              "resources": {"limits": {"cloud-tpus.google.com/v2": 8}}}]}}}}]
-    out["demo/minikube/pv.yaml"] = [{"apiVersion": "v1", "kind": "PersistentVolume", "metadata": {"name": "imagenet-pv"}, "spec": {"capacity": {"storage": "200Gi"}, "accessModes": ["ReadWriteOnce"], "hostPath": {"path": "/data/imagenet"}}}]
-    out["demo/minikube/pvc.yaml"] = [{"apiVersion": "v1", "kind": "PersistentVolumeClaim", "metadata": {"name": "imagenet-pvc"}, "spec": {"accessModes": ["ReadWriteOnce"], "resources": {"requests": {"storage": "200Gi"}}}}]
+    # volume + claim in one file (the reference keeps demo/minikube/pv.yaml and pvc.yaml apart)
+    out["demo/minikube/imagenet-storage.yaml"] = [
+        {"apiVersion": "v1", "kind": "PersistentVolume", "metadata": {"name": "imagenet-pv", "labels": {"dataset": "imagenet"}},
+         "spec": {"capacity": {"storage": "200Gi"}, "accessModes": ["ReadWriteOnce"], "persistentVolumeReclaimPolicy": "Retain", "hostPath": {"path": "/data/imagenet"}}},
+        {"apiVersion": "v1", "kind": "PersistentVolumeClaim", "metadata": {"name": "imagenet-pvc"},
+         "spec": {"accessModes": ["ReadWriteOnce"], "storageClassName": "", "selector": {"matchLabels": {"dataset": "imagenet"}}, "resources": {"requests": {"storage": "200Gi"}}}}]
     out["demo/minikube/resnet-gpu.yaml"] = [{"apiVersion": "batch/v1", "kind": "Job", "metadata": {"name": "resnet-gpu"}, "spec": {"template": {"spec": {"restartPolicy": "Never", "volumes": [{"name": "data", "persistentVolumeClaim": {"claimName": "imagenet-pvc"}}],
                                                                                                                                                       "containers": [{"name": "resnet", "image": "gcr.io/vishnuk-cloud/tf-models-gpu:1.0", "volumeMounts": [mount("data", "/data")], "resources": {"limits": {"nvidia.com/gpu": 1}}}]}}}}]
     out["demo/gpu-error/xid-inject-job.yaml"] = [{"apiVersion": "batch/v1", "kind": "Job", "metadata": {"name": "xid-inject"}, "spec": {"backoffLimit": 0, "template": {"spec": {"restartPolicy": "Never",
@@ -692,7 +696,7 @@ _Dumper.add_representer(str, _str_representer)
 
 
 def render(docs: list) -> str:
-    return HEADER + "---\n".join(yaml.dump(d, Dumper=_Dumper, sort_keys=False, default_flow_style=False, width=200) for d in docs)
+    return HEADER + "---\n".join(yaml.dump(d, Dumper=_Dumper, sort_keys=True, default_flow_style=False, width=200) for d in docs)
 
 
 def main(argv=None) -> int:
