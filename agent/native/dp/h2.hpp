@@ -269,7 +269,8 @@ class Server {
  private:
   struct Conn;
   struct StreamState : ServerStream {
-    Conn* conn = nullptr; uint32_t id = 0; std::string path, data; std::atomic<bool> dead{false}; bool headers_sent = false; int64_t send_window = 65535;
+    Conn* conn = nullptr; uint32_t id = 0; std::string path, data; std::atomic<bool> dead{false}, finished{false}; bool headers_sent = false, dispatched = false;
+    int64_t send_window = 65535;
     std::thread worker;
     bool send(const std::string& pb) override;
     bool cancelled() const override;
@@ -327,15 +328,28 @@ class Server {
     c->write(frame_bytes(HEADERS, END_HEADERS | END_STREAM, s->id, hpack_encode(h)));
   }
 
+  // Streams that answered (unary) or whose handler returned (server-streaming) leave the table, so a kubelet connection that
+  // lives for months does not accumulate one entry per Allocate.
+  static void forget(Conn* c, uint32_t id) { std::lock_guard<std::mutex> lk(c->wmu); c->streams.erase(id); }
+  static void reap_finished(Conn* c) {
+    std::vector<std::shared_ptr<StreamState>> done;
+    { std::lock_guard<std::mutex> lk(c->wmu);
+      for (auto it = c->streams.begin(); it != c->streams.end();) { if (it->second->finished) { done.push_back(it->second); it = c->streams.erase(it); } else ++it; } }
+    for (auto& s : done) if (s->worker.joinable()) s->worker.join();
+  }
+
   void dispatch(Conn* c, std::shared_ptr<StreamState> s) {
+    if (s->dispatched) return;                       // a second END_STREAM on the same stream: ignore (never start a second worker)
+    s->dispatched = true;
     std::vector<std::string> msgs;
-    if (!grpc_split(&s->data, &msgs) || msgs.size() != 1) { send_trailers(c, s.get(), {13, "malformed gRPC request"}); return; }
+    if (!grpc_split(&s->data, &msgs) || msgs.size() != 1) { send_trailers(c, s.get(), {13, "malformed gRPC request"}); forget(c, s->id); return; }
     auto u = unary_.find(s->path);
     if (u != unary_.end()) {
       std::string resp;
       Status st = u->second(msgs[0], &resp);
       if (st.code == 0) { send_headers(c, s.get()); c->write_data(s.get(), grpc_message(resp)); }
       send_trailers(c, s.get(), st);
+      forget(c, s->id);
       return;
     }
     auto sh = stream_.find(s->path);
@@ -346,19 +360,21 @@ class Server {
         send_headers(c, s.get());
         Status st = h(req, s.get());
         if (!s->dead && !c->closed) send_trailers(c, s.get(), st);
+        s->finished = true;                          // joined and dropped by reap_finished() or at connection end
       });
       return;
     }
     send_trailers(c, s.get(), {12, "unknown method " + s->path});
+    forget(c, s->id);
   }
 
   void serve(Conn* c) {
     char pre[24];
-    if (!read_exact(c->fd, pre, 24) || memcmp(pre, kPreface, 24) != 0) { c->close(); ::close(c->fd); return; }
+    if (!read_exact(c->fd, pre, 24) || memcmp(pre, kPreface, 24) != 0) { c->close(); c->done = true; return; }
     c->write(frame_bytes(SETTINGS, 0, 0, ""));
     Frame f;
     std::string header_block; uint32_t header_stream = 0; uint8_t header_flags = 0;
-    while (!c->closed && read_frame(c->fd, &f)) {
+    while (!c->closed && read_frame(c->fd, &f, kMaxFrame)) {
       switch (f.type) {
         case SETTINGS:
           if (f.flags & ACK) break;
@@ -391,17 +407,26 @@ class Server {
           if (off + pad > f.payload.size()) break;
           header_block = f.payload.substr(off, f.payload.size() - off - pad);
           header_stream = f.stream; header_flags = f.flags;
+          if (header_block.size() > kMaxHeaderBlock) { goaway(c, 11); break; }
           if (f.flags & END_HEADERS) finish_headers(c, header_stream, header_flags, &header_block);
           break;
         }
         case CONTINUATION:
-          if (f.stream == header_stream) { header_block += f.payload; if (f.flags & END_HEADERS) finish_headers(c, header_stream, header_flags, &header_block); }
+          if (f.stream != header_stream || header_stream == 0) break;
+          if (header_block.size() + f.payload.size() > kMaxHeaderBlock) { goaway(c, 11); break; }     // ENHANCE_YOUR_CALM
+          header_block += f.payload;
+          if (f.flags & END_HEADERS) finish_headers(c, header_stream, header_flags, &header_block);
           break;
         case DATA: {
           std::shared_ptr<StreamState> s;
           { std::lock_guard<std::mutex> lk(c->wmu); auto it = c->streams.find(f.stream); if (it != c->streams.end()) s = it->second; }
           size_t off = 0, pad = 0;
           if (f.flags & PADDED) { if (f.payload.empty()) break; pad = (uint8_t)f.payload[0]; off = 1; }
+          if (s && s->dispatched) s.reset();                                                     // data after END_STREAM: drop
+          if (s && s->data.size() + f.payload.size() > kMaxRequest) {                            // requests here are a few hundred bytes
+            c->write(frame_bytes(RST_STREAM, 0, f.stream, u32be(11)));
+            s->dead = true; forget(c, f.stream); s.reset();
+          }
           if (s && off + pad <= f.payload.size()) s->data.append(f.payload, off, f.payload.size() - off - pad);
           if (!f.payload.empty()) {   // give the credit straight back: requests here are tiny
             c->write(frame_bytes(WINDOW_UPDATE, 0, 0, u32be((uint32_t)f.payload.size())));
@@ -434,12 +459,22 @@ class Server {
     Headers hs;
     if (!c->dec.decode(reinterpret_cast<const uint8_t*>(block->data()), block->size(), &hs)) { c->write(frame_bytes(GOAWAY, 0, 0, u32be(0) + u32be(9))); c->close(); return; }   // COMPRESSION_ERROR
     block->clear();
+    reap_finished(c);
     auto s = std::make_shared<StreamState>();
     s->conn = c; s->id = stream;
     for (auto& h : hs) if (h.first == ":path") s->path = h.second;
-    { std::lock_guard<std::mutex> lk(c->wmu); s->send_window = c->peer_initial_window; c->streams[stream] = s; }
+    bool refuse = false, protocol_error = false;
+    { std::lock_guard<std::mutex> lk(c->wmu);
+      if (stream == 0 || (stream & 1) == 0 || c->streams.count(stream)) protocol_error = true;        // client streams are odd and opened once
+      else if (c->streams.size() >= kMaxStreams) refuse = true;
+      else { s->send_window = c->peer_initial_window; c->streams[stream] = s; } }
+    if (protocol_error) { goaway(c, 1); return; }
+    if (refuse) { c->write(frame_bytes(RST_STREAM, 0, stream, u32be(7))); return; }                    // REFUSED_STREAM
     if (flags & END_STREAM) dispatch(c, s);
   }
+  static void goaway(Conn* c, uint32_t code) { c->write(frame_bytes(GOAWAY, 0, 0, u32be(0) + u32be(code))); c->close(); }
+
+  static constexpr size_t kMaxFrame = 1u << 20, kMaxHeaderBlock = 64u << 10, kMaxRequest = 4u << 20, kMaxStreams = 256;
 
   int fd_ = -1;
   std::atomic<bool> stop_{true};

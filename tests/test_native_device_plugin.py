@@ -366,3 +366,82 @@ def test_health_monitoring_without_a_cluster_still_reports_devices(native, tmp_p
     assert {d.ID: d.health for d in next(stream).devices} == {"nvidia0": "Unhealthy", "nvidia1": "Healthy"}
     assert "failed to build kube client: not running in a cluster" in n.logs()
     stream.cancel()
+
+
+# ------------------------------------------------------------------------------------------------- hostile HTTP/2 peers
+def _frame(ftype, flags, stream, payload=b""):
+    return len(payload).to_bytes(3, "big") + bytes([ftype, flags]) + stream.to_bytes(4, "big") + payload
+
+
+def _hpack_literal(headers):
+    out = b""
+    for k, v in headers:
+        out += b"\x00" + bytes([len(k)]) + k.encode() + bytes([len(v)]) + v.encode()
+    return out
+
+
+def test_malformed_http2_traffic_does_not_take_the_plugin_down(native):
+    """A privileged daemon must shrug off garbage on its socket: every abusive connection is dropped or answered with an error and
+    the next well-formed kubelet call still works (run under ASan/TSan with B200_NATIVE_SAN to catch memory errors, not just crashes)."""
+    import random
+    import socket
+    n = native()
+    c = n.connect()
+    path = os.path.join(n.plugin_dir, n.endpoint)
+    preface = b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n"
+    req_headers = _hpack_literal([(":method", "POST"), (":scheme", "http"), (":path", "/v1beta1.DevicePlugin/ListAndWatch"), ("content-type", "application/grpc"), ("te", "trailers")])
+    grpc_empty = b"\x00\x00\x00\x00\x00"
+    rng = random.Random(7)
+    attacks = [
+        b"GET / HTTP/1.1\r\nHost: x\r\n\r\n",                                                   # not HTTP/2 at all
+        preface[:10],                                                                           # truncated preface, then close
+        preface + b"\xff\xff\xff\x00\x00\x00\x00\x00\x01",                                     # 16 MiB frame announced
+        preface + _frame(1, 0x4, 1, b"\x80"),                                                   # HPACK index 0
+        preface + _frame(1, 0x4, 1, b"\x00\x7f\xff\xff\xff\xff\xff\xff\xff\xff\x7f"),           # HPACK string length that would wrap
+        preface + _frame(1, 0x4, 0, req_headers),                                               # HEADERS on stream 0
+        preface + _frame(1, 0x4, 2, req_headers),                                               # even (server-initiated) stream id
+        preface + _frame(1, 0x4 | 0x8, 1, b"\xff" + req_headers),                               # pad length > payload
+        preface + _frame(9, 0x4, 5, req_headers),                                               # CONTINUATION without HEADERS
+        preface + _frame(1, 0x0, 1, req_headers[:7]) + b"".join(_frame(9, 0, 1, b"A" * 16000) for _ in range(6)),      # endless header block
+        preface + _frame(1, 0x4, 1, req_headers) + _frame(0, 0x1, 1, grpc_empty) + _frame(0, 0x1, 1, grpc_empty)       # END_STREAM twice on a streaming RPC
+        + _frame(1, 0x4, 1, req_headers),                                                                                # ... and the stream id reused
+        preface + _frame(1, 0x4, 1, req_headers) + _frame(0, 0x0, 1, b"\x00\xff\xff\xff\xff" + b"B" * 100) + _frame(0, 0x1, 1, b""),   # gRPC length prefix of 4 GiB
+        preface + _frame(8, 0, 0, b"\x7f\xff\xff\xff") * 4 + _frame(4, 0, 0, b"\x00\x04\xff\xff\xff\xff") + _frame(3, 0, 9, b"\x00\x00\x00\x08"),  # window overflow, huge initial window, RST of unknown stream
+        preface + bytes(rng.getrandbits(8) for _ in range(4096)),                               # noise after a valid preface
+    ]
+    for raw in attacks:
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(0.5)
+        s.connect(path)
+        try:
+            s.sendall(raw)
+            try:
+                while s.recv(65536):
+                    pass                                      # drain whatever it answers until it closes or goes quiet
+            except (socket.timeout, ConnectionResetError):
+                pass
+        except BrokenPipeError:
+            pass
+        finally:
+            s.close()
+        assert n.proc_handle.poll() is None, n.logs()[-2000:]
+    many = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)   # more concurrent streams than the server admits: the surplus is refused, not served
+    many.settimeout(1); many.connect(path)
+    many.sendall(preface + b"".join(_frame(1, 0x4, 2 * i + 1, req_headers) for i in range(300)))
+    got = b""
+    try:
+        while True:
+            chunk = many.recv(65536)
+            if not chunk:
+                break
+            got += chunk
+    except socket.timeout:
+        pass
+    many.close()
+    assert _frame(3, 0, 2 * 299 + 1, (7).to_bytes(4, "big")) in got           # RST_STREAM(REFUSED_STREAM) for the last one
+    # and the kubelet's own connection, opened before the abuse, still works, as does a fresh one
+    assert len(c.allocate(["nvidia0"]).container_responses[0].devices) == 5
+    c2 = DevicePluginClient(path); c2.wait_ready()
+    stream = c2.list_and_watch()
+    assert {d.ID for d in next(stream).devices} == {"nvidia0", "nvidia1"}
+    stream.cancel(); c2.close()
