@@ -699,6 +699,8 @@ void metrics_server(Manager* ngm, int port, int interval_ms, const std::string& 
     if (poll(&p, 1, 500) <= 0) continue;
     int c = ::accept4(fd, nullptr, nullptr, SOCK_CLOEXEC);
     if (c < 0) continue;
+    struct timeval tv = {2, 0};                           // one silent client must not stall the (single-threaded) endpoint
+    setsockopt(c, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv); setsockopt(c, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
     char req[2048]; ssize_t n = ::recv(c, req, sizeof(req) - 1, 0); req[n > 0 ? n : 0] = 0;
     std::string body, status = "200 OK";
     if (strncmp(req, "GET /metrics", 12) == 0) { std::lock_guard<std::mutex> lk(mu); body = snapshot; } else { status = "404 Not Found"; body = "not found\n"; }
