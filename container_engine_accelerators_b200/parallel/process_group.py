@@ -1,0 +1,387 @@
+"""`torch.distributed` backend "b200coll": `dist.init_process_group("b200coll")` puts DDP / FSDP / user collectives on libb200coll.
+
+Why: the reference's transports are drop-in for frameworks because frameworks speak NCCL and the installers swap the NCCL under them
+(gpudirect-rdma/nccl-rdma-installer.yaml:70-77, LD_LIBRARY_PATH=/usr/local/nvidia/lib64). PyTorch's NCCL process group uses far more
+of the NCCL API than nccl-tests does, so for PyTorch the faithful drop-in is a process group, not the symbol shim.
+
+How: a Python subclass of `torch.distributed.ProcessGroup` (c10d dispatches to it through its trampoline, the mechanism PyTorch's own
+tests use for Python process groups). CUDA tensors that the library can take as they are — contiguous, 16-byte aligned, fp32 / fp16 /
+bf16, sum or avg — go straight to the collective kernels **on the caller's current stream**, so ordering with the surrounding compute
+is plain stream order and `Work.wait()` has nothing to wait for (NCCL's side stream + event dance is not needed). Tensors allocated
+with `pg.empty()` live in the symmetric arena and take the zero-copy / NVLS paths; any other device tensor is staged by the library.
+Everything else (CPU tensors, integer reductions, min/max/product, point-to-point, gather/scatter, odd shapes) is executed by an
+internal Gloo group over host copies: slow but correct, which keeps DDP's bookkeeping collectives and object broadcasts working.
+
+Status: the fallback and dispatch logic is exercised on CPU (tests/test_process_group.py); the CUDA fast paths reuse the calls the GPU
+suite covers through `ops.coll.Comm`, but the process group itself has not run on a GPU box yet (tests/test_process_group.py has the
+two-process GPU test, opt-in until it has).
+"""
+from __future__ import annotations
+
+import os
+import uuid
+from datetime import timedelta
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import coll
+
+BACKEND_NAME = "b200coll"
+_FAST_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
+
+
+class _Work(dist._Work):
+    """Completed-at-enqueue work handle: the collective is already ordered on the caller's stream."""
+
+    def __init__(self, result, sync_on_wait: bool = False):
+        super().__init__()
+        self._result = result
+        self._sync = sync_on_wait
+        self._future: Optional[torch.futures.Future] = None
+
+    def wait(self, timeout: Optional[timedelta] = None) -> bool:
+        if self._sync and torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
+        return True
+
+    def is_completed(self) -> bool:
+        return True
+
+    def is_success(self) -> bool:
+        return True
+
+    def result(self):
+        return self._result
+
+    def get_future(self) -> torch.futures.Future:
+        if self._future is None:
+            self._future = torch.futures.Future()
+            self._future.set_result(self._result)
+        return self._future
+
+
+def _fast(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.is_contiguous() and t.dtype in _FAST_DTYPES and t.data_ptr() % 16 == 0 and t.numel() > 0
+
+
+def _sum_or_avg(op) -> Optional[int]:
+    if op == dist.ReduceOp.SUM:
+        return coll.SUM
+    if op == dist.ReduceOp.AVG:
+        return coll.AVG
+    return None
+
+
+def alltoallv_layout(split_matrix: list[list[int]], rank: int) -> tuple[list[int], list[int], list[int], int]:
+    """Given M[src][dst] = rows src sends to dst, return for `rank`: (send_rows, send_row_off, recv_row_off_at_peer, max_recv_rows).
+    Rows from lower-ranked sources land first on every destination (the order all_to_all_single promises)."""
+    n = len(split_matrix)
+    send_rows = list(split_matrix[rank])
+    send_off = [sum(send_rows[:d]) for d in range(n)]
+    recv_off_at_peer = [sum(split_matrix[s][d] for s in range(rank)) for d in range(n)]
+    max_recv = max(sum(split_matrix[s][d] for s in range(n)) for d in range(n))
+    return send_rows, send_off, recv_off_at_peer, max_recv
+
+
+class B200CollProcessGroup(dist.ProcessGroup):
+    def __init__(self, store, rank: int, size: int, timeout: timedelta = timedelta(minutes=10)):
+        super().__init__(rank, size)
+        self._store, self._rank, self._size, self._timeout = store, rank, size, timeout
+        self._comm: Optional[coll.Comm] = None
+        self._gloo = None
+        self._scratch: dict = {}          # (nbytes class) -> symmetric uint8 tensor, for all-to-all-v receive staging
+        self.fast_calls = 0               # collectives that ran on libb200coll
+        self.fallback_calls = 0           # collectives that ran on the Gloo group
+
+    # ------------------------------------------------------------------ plumbing
+    def getBackendName(self) -> str:
+        return BACKEND_NAME
+
+    @property
+    def comm(self) -> coll.Comm:
+        """The libb200coll communicator, created on first use on the caller's current CUDA device."""
+        if self._comm is None:
+            if self._rank == 0:
+                self._store.set("b200coll/key", uuid.uuid4().hex)
+            key = self._store.get("b200coll/key").decode()
+            arena = os.environ.get("B200COLL_ARENA_MB")
+            self._comm = coll.Comm.init_rank(self._rank, self._size, f"pg/{key}", arena_mb=int(arena) if arena else None)
+        return self._comm
+
+    @property
+    def gloo(self):
+        if self._gloo is None:
+            self._gloo = dist.ProcessGroupGloo(dist.PrefixStore("b200coll-gloo", self._store), self._rank, self._size, self._timeout)
+        return self._gloo
+
+    def empty(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        """A tensor in the symmetric arena (same call order and sizes on every rank): zero-copy collectives, NVLS capable."""
+        return self.comm.empty(numel, dtype)
+
+    def shutdown(self) -> None:
+        if self._comm is not None:
+            torch.cuda.synchronize()
+            self._scratch.clear()
+            self._comm.destroy()
+            self._comm = None
+
+    abort = shutdown
+
+    def _via_gloo(self, tensors, run):
+        """Run `run(cpu_tensors)` on the Gloo group and copy results back into the (possibly CUDA) originals."""
+        self.fallback_calls += 1
+        flat = list(tensors)
+        host = [t.detach().cpu() if t.is_cuda else t for t in flat]
+        work = run(host)
+        if work is not None:
+            work.wait()
+        for t, h in zip(flat, host):
+            if t.is_cuda:
+                t.copy_(h)
+        return host
+
+    # ------------------------------------------------------------------ collectives
+    def allreduce(self, tensors, opts=None):
+        op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
+        if op is not None and all(_fast(t) for t in tensors):
+            for t in tensors:
+                self.comm.all_reduce(t, op=op)
+            self.fast_calls += 1
+            return _Work(tensors)
+        gopts = dist.AllreduceOptions()
+        if opts is not None:
+            gopts.reduceOp = opts.reduceOp
+        avg = opts is not None and opts.reduceOp == dist.ReduceOp.AVG       # Gloo has no AVG
+        if avg:
+            gopts.reduceOp = dist.ReduceOp.SUM
+        self._via_gloo(tensors, lambda h: self.gloo.allreduce(h, gopts))
+        if avg:
+            for t in tensors:
+                t.div_(self._size)
+        return _Work(tensors)
+
+    def allreduce_coalesced(self, tensors, opts=None):
+        return self.allreduce(tensors, opts)
+
+    def broadcast(self, tensors, opts=None):
+        root = opts.rootRank if opts is not None else 0
+        done = []
+        for t in tensors:
+            words = self._as_words(t)
+            if words is None:
+                break
+            self.comm.broadcast(words, root=root)
+            done.append(t)
+        if len(done) == len(tensors):
+            self.fast_calls += 1
+            return _Work(tensors)
+        gopts = dist.BroadcastOptions()
+        gopts.rootRank = root
+        def run(host):
+            for x in host:
+                self.gloo.broadcast([x], gopts).wait()
+        self._via_gloo(tensors[len(done):], run)
+        return _Work(tensors)
+
+    @staticmethod
+    def _as_words(t: torch.Tensor) -> Optional[torch.Tensor]:
+        """View any contiguous CUDA tensor as fp16/fp32 words for bit-exact movement (broadcast does not care about the dtype)."""
+        if not (t.is_cuda and t.is_contiguous() and t.numel() > 0 and t.data_ptr() % 16 == 0):
+            return None
+        if t.dtype in _FAST_DTYPES:
+            return t.view(-1)
+        nbytes = t.numel() * t.element_size()
+        raw = t.view(-1).view(torch.uint8)
+        if nbytes % 4 == 0:
+            return raw.view(torch.float32)
+        if nbytes % 2 == 0:
+            return raw.view(torch.float16)
+        return None
+
+    def reduce(self, tensors, opts=None):
+        root = opts.rootRank if opts is not None else 0
+        op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
+        if op is not None and all(_fast(t) for t in tensors):
+            for t in tensors:
+                self.comm.reduce(t, root=root, op=op)
+            self.fast_calls += 1
+            return _Work(tensors)
+        gopts = dist.ReduceOptions()
+        gopts.rootRank = root
+        if opts is not None:
+            gopts.reduceOp = opts.reduceOp
+        self._via_gloo(tensors, lambda h: self.gloo.reduce(h, gopts))
+        return _Work(tensors)
+
+    def _allgather_base(self, output, input, opts=None):
+        if _fast(output) and _fast(input) and output.dtype == input.dtype and (input.numel() * input.element_size()) % 16 == 0 \
+                and output.numel() == input.numel() * self._size:
+            self.comm.all_gather(input.view(-1), output.view(-1))
+            self.fast_calls += 1
+            return _Work(output)
+        chunks = list(output.view(-1).chunk(self._size))
+        self.allgather([chunks], [input.view(-1)])
+        return _Work(output)
+
+    def allgather(self, output_tensors, input_tensors, opts=None):
+        for outs, inp in zip(output_tensors, input_tensors):
+            same = all(o.shape == inp.shape and o.dtype == inp.dtype for o in outs)
+            if same and _fast(inp) and all(o.is_cuda for o in outs) and (inp.numel() * inp.element_size()) % 16 == 0:
+                flat = torch.empty(inp.numel() * self._size, dtype=inp.dtype, device=inp.device)
+                self.comm.all_gather(inp.view(-1), flat)
+                for o, piece in zip(outs, flat.chunk(self._size)):
+                    o.copy_(piece.view_as(o))
+                self.fast_calls += 1
+            else:
+                self.fallback_calls += 1
+                host_in = inp.detach().cpu() if inp.is_cuda else inp
+                host_out = [torch.empty_like(o, device="cpu") for o in outs]
+                self.gloo.allgather([host_out], [host_in]).wait()
+                for o, h in zip(outs, host_out):
+                    o.copy_(h)
+        return _Work(output_tensors)
+
+    def allgather_into_tensor_coalesced(self, outputs, inputs, opts=None):
+        for o, i in zip(outputs, inputs):
+            self._allgather_base(o, i, opts)
+        return _Work(outputs)
+
+    def _reduce_scatter_base(self, output, input, opts=None):
+        op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
+        if op is not None and _fast(output) and _fast(input) and output.dtype == input.dtype and (output.numel() * output.element_size()) % 16 == 0 \
+                and input.numel() == output.numel() * self._size:
+            self.comm.reduce_scatter(input.view(-1), output.view(-1), op=op)
+            self.fast_calls += 1
+            return _Work(output)
+        # generic: all-reduce a copy, keep my slice
+        tmp = input.detach().clone().view(-1)
+        self.allreduce([tmp], opts)
+        output.view(-1).copy_(tmp.chunk(self._size)[self._rank])
+        return _Work(output)
+
+    def reduce_scatter(self, output_tensors, input_tensors, opts=None):
+        for out, ins in zip(output_tensors, input_tensors):
+            flat = torch.cat([i.reshape(-1) for i in ins])
+            self._reduce_scatter_base(out, flat, opts)
+        return _Work(output_tensors)
+
+    def reduce_scatter_tensor_coalesced(self, outputs, inputs, opts=None):
+        for o, i in zip(outputs, inputs):
+            self._reduce_scatter_base(o, i, opts)
+        return _Work(outputs)
+
+    def alltoall_base(self, output, input, output_split_sizes, input_split_sizes, opts=None):
+        n = self._size
+        even = not output_split_sizes and not input_split_sizes
+        if even and _fast(output) and _fast(input) and output.dtype == input.dtype and output.data_ptr() != input.data_ptr() \
+                and input.numel() % n == 0 and (input.numel() // n * input.element_size()) % 16 == 0 and output.numel() == input.numel():
+            self.comm.all_to_all(input.view(-1), output.view(-1))
+            self.fast_calls += 1
+            return _Work(output)
+        row_elems = input[0].numel() if input.dim() > 0 and input.shape[0] > 0 else 0
+        if not even and row_elems and _fast(input) and output.is_cuda and output.is_contiguous() and output.dtype == input.dtype \
+                and (row_elems * input.element_size()) % 16 == 0:
+            return self._alltoallv_rows(output, input, list(input_split_sizes), row_elems)
+        # Gloo: works on host copies for any layout
+        self.fallback_calls += 1
+        host_in = input.detach().cpu() if input.is_cuda else input
+        host_out = torch.empty_like(output, device="cpu")
+        self.gloo.alltoall_base(host_out, host_in, list(output_split_sizes or []), list(input_split_sizes or [])).wait()
+        output.copy_(host_out)
+        return _Work(output)
+
+    def _alltoallv_rows(self, output, input, in_splits, row_elems):
+        """Expert-dispatch shaped all_to_all_single: rows of dim 0 with per-peer counts. The split matrix travels over Gloo (a few
+        integers); the payload goes through b200collAllToAllv into a symmetric scratch buffer (peers write into it), then into `output`."""
+        n = self._size
+        mine = torch.tensor(in_splits, dtype=torch.int64)
+        allm = [torch.zeros(n, dtype=torch.int64) for _ in range(n)]
+        self.gloo.allgather([allm], [mine]).wait()
+        matrix = [m.tolist() for m in allm]
+        send_rows, send_off, recv_off_at_peer, max_recv = alltoallv_layout(matrix, self._rank)
+        row_bytes = row_elems * input.element_size()
+        need = max(1, max_recv) * row_bytes
+        cls = 1 << (need - 1).bit_length()                   # same on every rank: max_recv is a global quantity
+        scratch = self._scratch.get(cls)
+        if scratch is None:
+            scratch = self._scratch[cls] = self.comm.empty(cls, torch.uint8)
+        recv = scratch[:need].view(input.dtype)
+        self.comm.all_to_all_v(input.view(-1), recv, row_elems, send_rows, send_off, recv_off_at_peer)
+        got_rows = sum(matrix[s][self._rank] for s in range(n))
+        output.view(-1)[:got_rows * row_elems].copy_(recv[:got_rows * row_elems])
+        self.fast_calls += 1
+        return _Work(output)
+
+    def alltoall(self, output_tensors, input_tensors, opts=None):
+        same = len({(t.numel(), t.dtype) for t in list(output_tensors) + list(input_tensors)}) == 1
+        if same and all(t.is_cuda for t in list(output_tensors) + list(input_tensors)):
+            src = torch.cat([t.reshape(-1) for t in input_tensors])
+            dst = torch.empty_like(src)
+            self.alltoall_base(dst, src, [], [])
+            for o, piece in zip(output_tensors, dst.chunk(self._size)):
+                o.copy_(piece.view_as(o))
+            return _Work(output_tensors)
+        self.fallback_calls += 1
+        host_in = [t.detach().cpu() if t.is_cuda else t for t in input_tensors]
+        host_out = [torch.empty_like(t, device="cpu") for t in output_tensors]
+        self.gloo.alltoall(host_out, host_in).wait()
+        for o, h in zip(output_tensors, host_out):
+            o.copy_(h)
+        return _Work(output_tensors)
+
+    def barrier(self, opts=None):
+        if torch.cuda.is_available() and self._comm is not None:
+            self.comm.barrier()
+            self.fast_calls += 1
+            return _Work(None, sync_on_wait=True)
+        self.fallback_calls += 1
+        self.gloo.barrier().wait()
+        return _Work(None)
+
+    # ------------------------------------------------------------------ things only Gloo does
+    def gather(self, output_tensors, input_tensors, opts=None):
+        self.fallback_calls += 1
+        root = opts.rootRank if opts is not None else 0
+        gopts = dist.GatherOptions(); gopts.rootRank = root
+        host_in = [t.detach().cpu() if t.is_cuda else t for t in input_tensors]
+        host_out = [[torch.empty_like(o, device="cpu") for o in outs] for outs in output_tensors]
+        self.gloo.gather(host_out, host_in, gopts).wait()
+        for outs, hs in zip(output_tensors, host_out):
+            for o, h in zip(outs, hs):
+                o.copy_(h)
+        return _Work(output_tensors)
+
+    def scatter(self, output_tensors, input_tensors, opts=None):
+        self.fallback_calls += 1
+        root = opts.rootRank if opts is not None else 0
+        gopts = dist.ScatterOptions(); gopts.rootRank = root
+        host_out = [torch.empty_like(o, device="cpu") for o in output_tensors]
+        host_in = [[t.detach().cpu() if t.is_cuda else t for t in ins] for ins in input_tensors]
+        self.gloo.scatter(host_out, host_in, gopts).wait()
+        for o, h in zip(output_tensors, host_out):
+            o.copy_(h)
+        return _Work(output_tensors)
+
+    def send(self, tensors, dst_rank, tag=0):
+        self.fallback_calls += 1
+        self.gloo.send([t.detach().cpu() if t.is_cuda else t for t in tensors], dst_rank, tag).wait()
+        return _Work(tensors)
+
+    def recv(self, tensors, src_rank, tag=0):
+        self._via_gloo(tensors, lambda h: self.gloo.recv(h, src_rank, tag))
+        return _Work(tensors)
+
+
+def _create(store, rank, size, timeout):
+    return B200CollProcessGroup(store, rank, size, timeout)
+
+
+def register() -> None:
+    """Idempotent: make `backend="b200coll"` known to torch.distributed (also runs when this module is imported)."""
+    if BACKEND_NAME.upper() not in getattr(dist.Backend, "_plugins", {}):
+        dist.Backend.register_backend(BACKEND_NAME, _create, devices=["cpu", "cuda"])
+
+
+register()

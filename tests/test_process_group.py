@@ -1,0 +1,176 @@
+"""`torch.distributed` backend "b200coll" (parallel/process_group.py). On CPU every collective takes the Gloo fallback, which
+still exercises what is specific to a Python process group: registration, c10d -> trampoline dispatch, the option objects,
+Work / Future hand-back to c10d's C++ callers (DDP's reducer), and the all-to-all-v layout maths."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from container_engine_accelerators_b200.parallel import process_group as pgmod
+
+
+def _free_port() -> int:
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _run(fn, world, *args):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q, args)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    results = sorted(q.get() for _ in range(world))
+    assert all(p.exitcode == 0 for p in procs), results
+    assert all(r[1] == "ok" for r in results), results
+    return results
+
+
+def _entry(fn, rank, world, port, q, args):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        from container_engine_accelerators_b200.parallel import process_group  # noqa: F401  (registers the backend)
+        dist.init_process_group("b200coll", rank=rank, world_size=world)
+        out = fn(rank, world, *args)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok", out))
+    except Exception as e:      # surface the failure in the parent
+        import traceback
+        q.put((rank, "error", traceback.format_exc() + repr(e)))
+        sys.exit(1)
+
+
+def _collectives(rank, world):
+    pg = dist.group.WORLD
+    assert dist.get_backend() == "b200coll" and isinstance(pg, pgmod.B200CollProcessGroup)
+    t = torch.full((5,), float(rank + 1))
+    dist.all_reduce(t)
+    assert torch.equal(t, torch.full((5,), float(sum(range(1, world + 1)))))
+    t = torch.full((4,), float(rank + 1)); dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    assert torch.allclose(t, torch.full((4,), (world + 1) / 2))
+    t = torch.tensor([rank, 10 - rank]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.tolist() == [world - 1, 10]
+    b = torch.arange(6, dtype=torch.int64) * (rank + 1); dist.broadcast(b, src=world - 1)
+    assert torch.equal(b, torch.arange(6) * world)
+    r = torch.ones(3) * (rank + 1); dist.reduce(r, dst=0)
+    assert rank != 0 or torch.equal(r, torch.full((3,), float(sum(range(1, world + 1)))))
+    outs = [torch.empty(2) for _ in range(world)]; dist.all_gather(outs, torch.tensor([rank, rank + 0.5]))
+    assert [o.tolist() for o in outs] == [[float(s), s + 0.5] for s in range(world)]
+    big = torch.empty(3 * world); dist.all_gather_into_tensor(big, torch.full((3,), float(rank)))
+    assert big.tolist() == [float(s) for s in range(world) for _ in range(3)]
+    rs = torch.empty(2); dist.reduce_scatter_tensor(rs, torch.arange(2 * world, dtype=torch.float32) + rank)
+    assert rs.tolist() == [world * (2 * rank + k) + sum(range(world)) for k in range(2)]
+    a2a = torch.empty(world * 2); dist.all_to_all_single(a2a, torch.arange(world * 2, dtype=torch.float32) + 100 * rank)
+    assert a2a.tolist() == [100 * s + 2 * rank + k for s in range(world) for k in range(2)]
+    # uneven all_to_all_single: rank r sends (d + 1) rows of width 4 to rank d
+    in_splits = [d + 1 for d in range(world)]; out_splits = [rank + 1] * world
+    src = torch.arange(sum(in_splits) * 4, dtype=torch.float32).view(-1, 4) + 1000 * rank
+    dst = torch.empty(sum(out_splits), 4)
+    dist.all_to_all_single(dst, src, out_splits, in_splits)
+    off = sum(in_splits[:rank])
+    want = torch.cat([(torch.arange(sum(in_splits) * 4, dtype=torch.float32).view(-1, 4) + 1000 * s)[off:off + rank + 1] for s in range(world)])
+    assert torch.equal(dst, want)
+    g = [torch.empty(1) for _ in range(world)] if rank == 0 else None
+    dist.gather(torch.tensor([float(rank)]), g, dst=0)
+    assert rank != 0 or [x.item() for x in g] == [float(s) for s in range(world)]
+    sc = torch.empty(1); dist.scatter(sc, [torch.tensor([float(10 + s)]) for s in range(world)] if rank == 0 else None, src=0)
+    assert sc.item() == 10 + rank
+    if rank == 0:
+        dist.send(torch.tensor([42.0]), dst=1)
+    elif rank == 1:
+        m = torch.empty(1); dist.recv(m, src=0); assert m.item() == 42.0
+    objs = [{"cfg": rank}] if rank == 0 else [None]
+    dist.broadcast_object_list(objs, src=0)
+    assert objs == [{"cfg": 0}]
+    dist.barrier()
+    assert pg.fast_calls == 0 and pg.fallback_calls >= 12          # no GPU here: everything went through Gloo
+    return pg.fallback_calls
+
+
+def test_every_collective_through_the_registered_backend():
+    _run(_collectives, 2)
+
+
+def _ddp(rank, world):
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 2))
+    ddp = torch.nn.parallel.DistributedDataParallel(model)                  # C++ reducer calling into the Python process group
+    opt = torch.optim.SGD(ddp.parameters(), lr=0.1)
+    torch.manual_seed(100 + rank)
+    for _ in range(3):
+        x, y = torch.randn(4, 8), torch.randn(4, 2)
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(ddp(x), y).backward()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.allclose(g, gathered[0]) for g in gathered)            # replicas stayed in lock-step: gradients were averaged
+    return float(flat.abs().sum())
+
+
+def test_ddp_trains_in_lock_step_over_the_backend():
+    res = _run(_ddp, 2)
+    assert res[0][2] == pytest.approx(res[1][2])
+
+
+def test_alltoallv_layout():
+    m = [[1, 2, 0], [0, 3, 4], [5, 0, 6]]                                   # m[src][dst]
+    assert pgmod.alltoallv_layout(m, 0) == ([1, 2, 0], [0, 1, 3], [0, 0, 0], 10)
+    assert pgmod.alltoallv_layout(m, 1) == ([0, 3, 4], [0, 0, 3], [1, 2, 0], 10)
+    assert pgmod.alltoallv_layout(m, 2) == ([5, 0, 6], [0, 5, 5], [1, 5, 4], 10)
+
+
+def test_word_views_for_bit_exact_broadcast():
+    f = pgmod.B200CollProcessGroup._as_words
+    assert f(torch.zeros(4)) is None                                        # CPU tensors never take the device path
+
+
+def _gpu_pair(rank, world):
+    torch.cuda.set_device(0)                                                # two ranks share cuda:0 on a one-GPU box
+    pg = dist.group.WORLD
+    x = torch.full((1 << 16,), float(rank + 1), device="cuda", dtype=torch.bfloat16)
+    dist.all_reduce(x)
+    assert torch.equal(x.float(), torch.full_like(x, 3.0).float())
+    sym = pg.empty(1 << 20, torch.float32); sym.fill_(rank + 1.0)
+    dist.all_reduce(sym, op=dist.ReduceOp.AVG)
+    assert torch.equal(sym, torch.full_like(sym, 1.5))
+    ids = torch.arange(1001, device="cuda", dtype=torch.int64) * (rank + 1); dist.broadcast(ids, src=1)
+    assert torch.equal(ids, torch.arange(1001, device="cuda") * 2)
+    out = torch.empty(2 * 4096, device="cuda"); dist.all_gather_into_tensor(out, torch.full((4096,), float(rank), device="cuda"))
+    assert out[:4096].eq(0).all() and out[4096:].eq(1).all()
+    rs = torch.empty(4096, device="cuda"); dist.reduce_scatter_tensor(rs, torch.ones(2 * 4096, device="cuda") * (rank + 1))
+    assert rs.eq(3).all()
+    in_splits = [1, 3] if rank == 0 else [2, 2]; out_splits = [1, 2] if rank == 0 else [3, 2]
+    src = (torch.arange(4 * 64, device="cuda", dtype=torch.float32).view(4, 64) + 1000 * rank)
+    dst = torch.empty(sum(out_splits), 64, device="cuda")
+    dist.all_to_all_single(dst, src, out_splits, in_splits)
+    base = torch.arange(4 * 64, device="cuda", dtype=torch.float32).view(4, 64)
+    want = torch.cat([base[0:1], base[0:2] + 1000]) if rank == 0 else torch.cat([base[1:4], base[2:4] + 1000])
+    assert torch.equal(dst, want)
+    cnt = torch.tensor([rank], device="cuda"); dist.all_reduce(cnt, op=dist.ReduceOp.MAX)      # integer max: Gloo fallback from a CUDA tensor
+    assert cnt.item() == 1
+    model = torch.nn.Linear(32, 32).cuda()
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[0])
+    torch.manual_seed(rank); ddp(torch.randn(8, 32, device="cuda")).sum().backward()
+    g = model.weight.grad.clone(); gs = [torch.empty_like(g) for _ in range(world)]; dist.all_gather(gs, g)
+    assert torch.allclose(gs[0], gs[1])
+    torch.cuda.synchronize()
+    assert pg.fast_calls >= 6
+    return pg.fast_calls
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="process-group CUDA path has not run on hardware yet (round 1 GPU budget spent); set B200_RUN_UNVALIDATED=1")
+def test_cuda_fast_paths_two_ranks():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _run(_gpu_pair, 2)
