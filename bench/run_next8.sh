@@ -3,6 +3,7 @@
 #   1. rooted collectives on the NVLS path (multimem.st fan-out, root-side multimem.ld_reduce): correctness + busbw vs NCCL
 #   2. programmatic dependent launch (B200COLL_PDL=1) at one rank per GPU: small-message latency with and without
 #   3. the multi-process NVLS test that a one-GPU box skips
+#   4. the torch.distributed process group's CUDA paths (tests/test_process_group.py, opt-in until this has passed once)
 # Usage: gpurun --gpus 8 --timeout 600 -- 'bash bench/run_next8.sh 8'
 NG=${1:-8}
 mkdir -p gpurun_out; export B200COLL_TIMEOUT_MS=5000
@@ -11,6 +12,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-add
 ALL=$(python3 -c "print(','.join(str(i) for i in range($NG)))")
 echo "== $(date -u +%T) multi-process NVLS tests"
 timeout 300 python -m pytest tests/test_coll_gpu.py -q -k "multi_gpu" > ${O}_pytest_multi.log 2>&1; echo "pytest rc=$?"; tail -n 2 ${O}_pytest_multi.log
+echo "== $(date -u +%T) torch.distributed backend on CUDA (first run on hardware)"
+B200_RUN_UNVALIDATED=1 timeout 200 python -m pytest tests/test_process_group.py -q -m gpu > ${O}_pytest_pg.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_pg.log
 echo "== $(date -u +%T) rooted ops, both arms"
 timeout 200 $TR --master-port 29731 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --extra-ops reduce --extra-out ${O}_rooted_ours.json > ${O}_bcast.json 2> ${O}_bcast.err
 timeout 200 $TR --master-port 29732 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --impl reference --extra-ops reduce --extra-out ${O}_rooted_ref.json > ${O}_bcast_ref.json 2> ${O}_bcast_ref.err
