@@ -112,3 +112,35 @@ def test_native_injector_wire_path(tmp_path, native_build):
         except subprocess.TimeoutExpired:
             proc.kill()
     assert proc.returncode == 0           # exits cleanly when the runtime goes away
+
+
+def _mknod_or_skip(path, mode, major, minor):
+    try:
+        os.mknod(path, mode, os.makedev(major, minor))
+    except PermissionError:
+        pytest.skip("needs CAP_MKNOD (the reference runs this test under sudo: Makefile:97-102)")
+
+
+def test_real_device_nodes_python_and_native_agree(tmp_path, native_build):
+    """lstat on real char/block nodes (reference nri_device_injector_test.go:25-93): type, major and minor come from the node,
+    never from the annotation — checked for the Python plugin's helper and for the C++ binary over the wire."""
+    import subprocess
+    ch, blk = tmp_path / "nvidia7", tmp_path / "loop9"
+    _mknod_or_skip(ch, stat.S_IFCHR | 0o666, 195, 7)
+    _mknod_or_skip(blk, stat.S_IFBLK | 0o660, 7, 9)
+    d = nri.to_nri_device({"path": str(ch), "type": "b", "major": 1, "minor": 2})          # annotation lies: ignored
+    assert (d.type, d.major, d.minor) == ("c", 195, 7)
+    sock = str(tmp_path / "nri.sock")
+    rt = testing.FakeNriRuntime(sock)
+    proc = subprocess.Popen([os.path.join(native_build, "b200-nri-device-injector"), "--socket", sock], stderr=subprocess.PIPE)
+    try:
+        rt.wait_registered(); rt.configure(); rt.synchronize()
+        devs = rt.create_container("pod", "c", {KEY + "c": f"- path: {ch}\n  type: b\n  major: 1\n- path: {blk}\n  uid: 7\n"}).adjust.linux.devices
+        assert [(x.path, x.type, x.major, x.minor) for x in devs] == [(str(ch), "c", 195, 7), (str(blk), "b", 7, 9)]
+        assert devs[1].uid.value == 7 and not devs[0].HasField("uid")
+    finally:
+        rt.close()
+        try:
+            proc.wait(5)
+        except subprocess.TimeoutExpired:
+            proc.kill()
