@@ -24,6 +24,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <array>
 #include <deque>
 #include <fstream>
 #include <regex>
@@ -378,14 +379,77 @@ void apply_transport(const Config& cfg, const std::vector<Mount>& mounts, pb::Co
   if (!covered) r->mounts.push_back({cfg.lib_dir_container, cfg.lib_dir_host, true});
 }
 
+// ------------------------------------------------------------------------------------------------ preferred allocation (opt-in)
+// Same rules as container_engine_accelerators_b200/agent/preferred.py (the tests drive both with one table): must-include first; stay on
+// the NUMA nodes already used, else the smallest node that covers what is missing, else the fullest; `spread` takes the physical GPU
+// with most free replicas and avoids ones already chosen, `packed` the opposite; ties in natural id order.
+std::string g_preferred_policy = "none";
+
+std::vector<long> natural_key(const std::string& id, std::vector<std::string>* words) {
+  std::vector<long> nums; std::string cur; bool digits = false;
+  auto flush = [&] { if (cur.empty()) return; if (digits) nums.push_back(atol(cur.c_str())); else words->push_back(cur); cur.clear(); };
+  for (char ch : id) { const bool d = ch >= '0' && ch <= '9'; if (d != digits) flush(); digits = d; cur.push_back(ch); }
+  flush();
+  return nums;
+}
+bool natural_less(const std::string& a, const std::string& b) {
+  std::vector<std::string> wa, wb;
+  const std::vector<long> na = natural_key(a, &wa), nb = natural_key(b, &wb);
+  if (wa != wb) return wa < wb;
+  return na != nb ? na < nb : a < b;
+}
+std::string physical_of(const std::string& id) { return std::regex_replace(id, kVgpuSuffix, ""); }
+
+std::vector<std::string> preferred_allocation(const pb::PreferredRequest& rq, const std::map<std::string, pb::Device>& devices, const std::string& policy) {
+  auto numa_of = [&](const std::string& id) -> long { auto it = devices.find(id); return it != devices.end() && it->second.has_numa ? (long)it->second.numa : -1; };
+  std::vector<std::string> chosen;
+  for (auto& d : rq.must_include) if (std::find(chosen.begin(), chosen.end(), d) == chosen.end()) chosen.push_back(d);
+  std::vector<std::string> pool;
+  for (auto& d : rq.available) if (std::find(chosen.begin(), chosen.end(), d) == chosen.end() && std::find(pool.begin(), pool.end(), d) == pool.end()) pool.push_back(d);
+  std::sort(pool.begin(), pool.end(), natural_less);
+  const size_t want = (size_t)std::max<int64_t>(rq.size, 0);
+  while (chosen.size() < want && !pool.empty()) {
+    const long missing = (long)(want - chosen.size());
+    std::set<long> used_nodes; std::set<std::string> chosen_phys;
+    for (auto& d : chosen) { used_nodes.insert(numa_of(d)); chosen_phys.insert(physical_of(d)); }
+    std::map<long, long> free_node; std::map<std::string, long> free_phys;
+    for (auto& d : pool) { free_node[numa_of(d)]++; free_phys[physical_of(d)]++; }
+    auto key = [&](const std::string& d) {
+      const long node = numa_of(d), free = free_node[node];
+      long n0, n1;
+      if (used_nodes.count(node)) { n0 = 0; n1 = 0; } else if (free >= missing) { n0 = 1; n1 = free; } else { n0 = 2; n1 = -free; }
+      const std::string phys = physical_of(d);
+      long s0, s1;
+      if (policy == "spread") { s0 = chosen_phys.count(phys) ? 1 : 0; s1 = -free_phys[phys]; } else { s0 = chosen_phys.count(phys) ? 0 : 1; s1 = free_phys[phys]; }
+      return std::array<long, 4>{n0, n1, s0, s1};
+    };
+    size_t best = 0;                                   // pool is in natural order, so the first minimum is the natural-order tie-break
+    for (size_t i = 1; i < pool.size(); i++) if (key(pool[i]) < key(pool[best])) best = i;
+    chosen.push_back(pool[best]);
+    pool.erase(pool.begin() + (long)best);
+  }
+  if (chosen.size() > std::max(want, rq.must_include.size())) chosen.resize(std::max(want, rq.must_include.size()));
+  return chosen;
+}
+
 // ------------------------------------------------------------------------------------------------ gRPC service
 std::vector<pb::Device> device_vector(Manager* m) { std::vector<pb::Device> v; for (auto& kv : m->list_devices()) v.push_back(kv.second); return v; }
 
 void register_service(h2::Server* srv, Manager* ngm) {
   const std::string svc = "/v1beta1.DevicePlugin/";
-  srv->add_unary(svc + "GetDevicePluginOptions", [](const std::string&, std::string* resp) { resp->clear(); return h2::Status{}; });   // empty options
+  srv->add_unary(svc + "GetDevicePluginOptions", [](const std::string&, std::string* resp) { *resp = pb::encode_options(g_preferred_policy != "none"); return h2::Status{}; });   // empty unless opted in
   srv->add_unary(svc + "PreStartContainer", [](const std::string&, std::string* resp) { LOGE("device-plugin: PreStart should NOT be called for the B200 GPU device plugin"); resp->clear(); return h2::Status{}; });
-  srv->add_unary(svc + "GetPreferredAllocation", [](const std::string&, std::string* resp) { LOGE("device-plugin: GetPreferredAllocation should NOT be called for the B200 GPU device plugin"); resp->clear(); return h2::Status{}; });
+  srv->add_unary(svc + "GetPreferredAllocation", [ngm](const std::string& req, std::string* resp) {
+    resp->clear();
+    if (g_preferred_policy == "none") { LOGE("device-plugin: GetPreferredAllocation should NOT be called for the B200 GPU device plugin"); return h2::Status{}; }
+    std::vector<pb::PreferredRequest> rqs;
+    if (!pb::decode_preferred_request(req, &rqs)) return h2::Status{13, "malformed PreferredAllocationRequest"};
+    const auto devices = ngm->list_devices();
+    std::vector<std::vector<std::string>> out;
+    for (auto& rq : rqs) out.push_back(preferred_allocation(rq, devices, g_preferred_policy));
+    *resp = pb::encode_preferred_response(out);
+    return h2::Status{};
+  });
   srv->add_stream(svc + "ListAndWatch", [ngm](const std::string&, h2::ServerStream* stream) {
     LOGI("device-plugin: ListAndWatch start");
     if (!stream->send(pb::encode_list_and_watch(device_vector(ngm)))) return h2::Status{};
@@ -731,7 +795,7 @@ int serve(Manager* ngm, const std::string& plugin_dir, const std::string& kubele
     LOGI("device-plugin: serving on %s", sock.c_str());
     if (do_register) {
       std::string resp;
-      int st = h2::unary_call(kubelet_path, "/v1beta1.Registration/Register", pb::encode_register_request("v1beta1", plugin_endpoint, kResourceName), &resp, &err);
+      int st = h2::unary_call(kubelet_path, "/v1beta1.Registration/Register", pb::encode_register_request("v1beta1", plugin_endpoint, kResourceName, g_preferred_policy != "none"), &resp, &err);
       if (st != 0) { server.stop(); LOGE("device-plugin: cannot register to kubelet service: %s", err.c_str()); return 1; }   // pod restarts (reference: glog.Fatal)
       LOGI("device-plugin registered with the kubelet");
     }
@@ -794,6 +858,7 @@ int main(int argc, char** argv) {
     else if (a == "plugin-endpoint") plugin_endpoint = need();
     else if (a == "pod-resources-socket") pod_resources = need();
     else if (a == "coll-stats-dir") g_coll_stats_dir = need();
+    else if (a == "preferred-allocation-policy") { g_preferred_policy = need(); if (g_preferred_policy != "none" && g_preferred_policy != "spread" && g_preferred_policy != "packed") { fprintf(stderr, "bad -preferred-allocation-policy %s (none|spread|packed)\n", g_preferred_policy.c_str()); return 2; } }
     else if (a == "gpu-check-interval") ngm.gpu_check_interval = atof(need().c_str());
     else if (a == "socket-check-interval") ngm.socket_check_interval = atof(need().c_str());
     else if (a == "v") g_verbosity = atoi(need().c_str());

@@ -62,8 +62,35 @@ inline std::string encode_device(const Device& d) {
   return o;
 }
 inline std::string encode_list_and_watch(const std::vector<Device>& devs) { std::string o; for (auto& d : devs) put_bytes(&o, 1, encode_device(d)); return o; }
-inline std::string encode_register_request(const std::string& version, const std::string& endpoint, const std::string& resource) {
-  std::string o; put_string(&o, 1, version); put_string(&o, 2, endpoint); put_string(&o, 3, resource); return o;
+// DevicePluginOptions{pre_start_required = 1, get_preferred_allocation_available = 2}
+inline std::string encode_options(bool preferred_allocation) { std::string o; put_bool(&o, 2, preferred_allocation); return o; }
+inline std::string encode_register_request(const std::string& version, const std::string& endpoint, const std::string& resource, bool preferred_allocation = false) {
+  std::string o; put_string(&o, 1, version); put_string(&o, 2, endpoint); put_string(&o, 3, resource);
+  if (preferred_allocation) put_bytes(&o, 4, encode_options(true));      // the reference never sends options (field absent)
+  return o;
+}
+// PreferredAllocationRequest{repeated ContainerPreferredAllocationRequest{repeated available_deviceIDs = 1, repeated must_include_deviceIDs = 2, int32 allocation_size = 3} = 1}
+struct PreferredRequest { std::vector<std::string> available, must_include; int64_t size = 0; };
+inline bool decode_preferred_request(const std::string& in, std::vector<PreferredRequest>* out) {
+  std::vector<Field> fs;
+  if (!parse(in, &fs)) return false;
+  for (auto& f : fs) if (f.number == 1 && f.wire_type == 2) {
+    std::vector<Field> cf; if (!parse(f.bytes, &cf)) return false;
+    PreferredRequest r;
+    for (auto& x : cf) {
+      if (x.number == 1 && x.wire_type == 2) r.available.push_back(x.bytes);
+      if (x.number == 2 && x.wire_type == 2) r.must_include.push_back(x.bytes);
+      if (x.number == 3 && x.wire_type == 0) r.size = (int64_t)x.varint;
+    }
+    out->push_back(r);
+  }
+  return true;
+}
+// PreferredAllocationResponse{repeated ContainerPreferredAllocationResponse{repeated deviceIDs = 1} = 1}
+inline std::string encode_preferred_response(const std::vector<std::vector<std::string>>& rs) {
+  std::string o;
+  for (auto& ids : rs) { std::string c; for (auto& id : ids) put_bytes(&c, 1, id); put_bytes(&o, 1, c); }
+  return o;
 }
 inline std::string encode_allocate_response(const std::vector<ContainerAllocateResponse>& rs) {
   std::string o;

@@ -41,6 +41,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--proc-directory", default=PROC_DIR)
     p.add_argument("--status-only", action="store_true",
                    help="do not serve the kubelet API (the native b200-device-plugin does); only publish Kubernetes-side status: Xid Events + Node condition, driver-version annotations")
+    p.add_argument("--preferred-allocation-policy", choices=["none", "spread", "packed"], default="none",
+                   help="answer the kubelet's GetPreferredAllocation (NUMA-aligned; spread or pack shared GPUs). none = the reference's behaviour: no plugin options")
     p.add_argument("-v", "--verbosity", type=int, default=0)
     return p
 
@@ -57,7 +59,7 @@ def main(argv=None) -> int:
         log.error("failed to add HealthCriticalXid: %s", e)
     log.info("Using gpu config: %s", cfg)
     api = nvml.NativeNvml()
-    ngm = GPUManager(args.dev_directory, args.proc_directory, mounts, cfg, nvml=api)
+    ngm = GPUManager(args.dev_directory, args.proc_directory, mounts, cfg, nvml=api, preferred_allocation_policy=args.preferred_allocation_policy)
     while True:
         try:
             ngm.check_device_paths()

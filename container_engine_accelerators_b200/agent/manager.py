@@ -52,8 +52,10 @@ class AllocationError(ValueError):
 class GPUManager:
     def __init__(self, dev_dir: str, proc_dir: str, mount_paths: list, gpu_config: GPUConfig, nvml: Optional[nvmlmod.NvmlOperations] = None,
                  pci_root: str = nvmlmod.PCI_DEVICES_ROOT, mps_control_bin: str = MPS_CONTROL_BIN,
-                 gpu_check_interval: float = GPU_CHECK_INTERVAL, socket_check_interval: float = PLUGIN_SOCKET_CHECK_INTERVAL):
+                 gpu_check_interval: float = GPU_CHECK_INTERVAL, socket_check_interval: float = PLUGIN_SOCKET_CHECK_INTERVAL,
+                 preferred_allocation_policy: str = "none"):
         self.dev_dir, self.proc_dir = dev_dir, proc_dir
+        self.preferred_allocation_policy = preferred_allocation_policy     # "none" = the reference's contract (no plugin options)
         self.mount_paths: list = list(mount_paths)
         self.gpu_config = gpu_config
         self.nvml = nvml
@@ -255,7 +257,7 @@ class GPUManager:
             log.info("device-plugin: serving on %s", self.socket_path)
             if register:
                 try:
-                    register_with_kubelet(kubelet_path, plugin_endpoint, RESOURCE_NAME)
+                    register_with_kubelet(kubelet_path, plugin_endpoint, RESOURCE_NAME, preferred_allocation=self.preferred_allocation_policy != "none")
                     log.info("device-plugin registered with the kubelet")
                 except Exception as e:
                     self._stop_server()

@@ -170,8 +170,9 @@ class MockNvml:
     """Counts nvidiaN files in a temp /dev; minor == index; bus id settable per test."""
 
     def __init__(self, dev_dir: str, bus_id: str = "", mem_total: int = 80 << 30, uuids: Optional[list] = None, name: str = "NVIDIA B200",
-                 driver: str = "580.159.03"):
+                 driver: str = "580.159.03", bus_ids: Optional[list] = None):
         self.dev_dir, self.bus_id, self.mem_total, self.uuids, self.name, self.driver = dev_dir, bus_id, mem_total, uuids, name, driver
+        self.bus_ids = bus_ids                      # per-index bus ids (two-socket hosts); falls back to `bus_id`
         self.utilisation: dict = {}
         self.events: list = []
         self.events_supported = True
@@ -187,7 +188,8 @@ class MockNvml:
 
     def device(self, index: int) -> DeviceInfo:
         uuid = self.uuids[index] if self.uuids and index < len(self.uuids) else f"GPU-mock-{index}"
-        return DeviceInfo(index, index, uuid, self.name, self.bus_id, self.mem_total, 0, 0)
+        bus = self.bus_ids[index] if self.bus_ids and index < len(self.bus_ids) else self.bus_id
+        return DeviceInfo(index, index, uuid, self.name, bus, self.mem_total, 0, 0)
 
     def driver_version(self) -> str:
         return self.driver

@@ -2,6 +2,8 @@
 
 Contract: reference pkg/gpu/nvidia/beta_plugin.go:35-145:
   * GetDevicePluginOptions -> empty options (so the kubelet never calls PreStart / GetPreferredAllocation)
+    unless --preferred-allocation-policy is set: then get_preferred_allocation_available = true and
+    GetPreferredAllocation answers with agent/preferred.py (NUMA-aligned, sharing-aware; new in this build)
   * ListAndWatch -> full list, then the full list again on every health change
   * Allocate -> per container: requested device specs + default devices (nvidiactl, nvidia-uvm, [modeset,
     uvm-tools]) all "mrw" with HostPath == ContainerPath; mounts; MPS envs; whole RPC fails on the first bad id
@@ -17,7 +19,7 @@ import queue
 
 import grpc
 
-from . import protos, sharing, transport
+from . import preferred, protos, sharing, transport
 from .protos import deviceplugin as pb
 
 log = logging.getLogger("b200-device-plugin")
@@ -35,8 +37,12 @@ class DevicePluginService:
         self.ngm = manager
 
     # ------------------------------------------------------------------ handlers
+    @property
+    def policy(self) -> str:
+        return getattr(self.ngm, "preferred_allocation_policy", "none")
+
     def GetDevicePluginOptions(self, request, context):
-        return pb.DevicePluginOptions()
+        return pb.DevicePluginOptions(get_preferred_allocation_available=self.policy != "none")
 
     def _device_list(self) -> "pb.ListAndWatchResponse":
         resp = pb.ListAndWatchResponse()
@@ -84,8 +90,16 @@ class DevicePluginService:
         return pb.PreStartContainerResponse()
 
     def GetPreferredAllocation(self, request, context):
-        log.error("device-plugin: GetPreferredAllocation should NOT be called for the B200 GPU device plugin")
-        return pb.PreferredAllocationResponse()
+        resp = pb.PreferredAllocationResponse()
+        if self.policy == "none":
+            log.error("device-plugin: GetPreferredAllocation should NOT be called for the B200 GPU device plugin")
+            return resp
+        devices = self.ngm.list_devices()
+        numa_of = lambda d: devices[d].numa_node if d in devices else None
+        for rqt in request.container_requests:
+            ids = preferred.preferred_allocation(list(rqt.available_deviceIDs), list(rqt.must_include_deviceIDs), rqt.allocation_size, numa_of, self.policy)
+            resp.container_responses.add(deviceIDs=ids)
+        return resp
 
     # ------------------------------------------------------------------ wiring
     def register(self, server: grpc.Server) -> None:
@@ -100,12 +114,15 @@ class DevicePluginService:
         server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(protos.DEVICE_PLUGIN_SERVICE, handlers),))
 
 
-def register_with_kubelet(kubelet_socket: str, plugin_endpoint: str, resource_name: str, timeout: float = 10.0) -> None:
+def register_with_kubelet(kubelet_socket: str, plugin_endpoint: str, resource_name: str, timeout: float = 10.0, preferred_allocation: bool = False) -> None:
     with grpc.insecure_channel(f"unix:{kubelet_socket}") as ch:
         grpc.channel_ready_future(ch).result(timeout=timeout)
         call = ch.unary_unary(f"/{protos.REGISTRATION_SERVICE}/Register", request_serializer=pb.RegisterRequest.SerializeToString,
                               response_deserializer=pb.Empty.FromString)
-        call(pb.RegisterRequest(version=protos.DEVICE_PLUGIN_VERSION, endpoint=plugin_endpoint, resource_name=resource_name), timeout=timeout)
+        req = pb.RegisterRequest(version=protos.DEVICE_PLUGIN_VERSION, endpoint=plugin_endpoint, resource_name=resource_name)
+        if preferred_allocation:            # the reference never sets options; only the opt-in policy does
+            req.options.get_preferred_allocation_available = True
+        call(req, timeout=timeout)
 
 
 class DevicePluginClient:
@@ -117,6 +134,8 @@ class DevicePluginClient:
         self._options = self.channel.unary_unary(f"/{svc}/GetDevicePluginOptions", request_serializer=pb.Empty.SerializeToString, response_deserializer=pb.DevicePluginOptions.FromString)
         self._law = self.channel.unary_stream(f"/{svc}/ListAndWatch", request_serializer=pb.Empty.SerializeToString, response_deserializer=pb.ListAndWatchResponse.FromString)
         self._alloc = self.channel.unary_unary(f"/{svc}/Allocate", request_serializer=pb.AllocateRequest.SerializeToString, response_deserializer=pb.AllocateResponse.FromString)
+        self._pref = self.channel.unary_unary(f"/{svc}/GetPreferredAllocation", request_serializer=pb.PreferredAllocationRequest.SerializeToString,
+                                              response_deserializer=pb.PreferredAllocationResponse.FromString)
 
     def wait_ready(self, timeout: float = 10.0) -> None:
         grpc.channel_ready_future(self.channel).result(timeout=timeout)
@@ -132,6 +151,12 @@ class DevicePluginClient:
         for ids in container_device_ids:
             req.container_requests.add(devices_ids=list(ids))
         return self._alloc(req, timeout=5)
+
+    def preferred(self, available: list, must_include: list, size: int) -> list:
+        req = pb.PreferredAllocationRequest()
+        req.container_requests.add(available_deviceIDs=list(available), must_include_deviceIDs=list(must_include), allocation_size=size)
+        resps = self._pref(req, timeout=5).container_responses
+        return list(resps[0].deviceIDs) if resps else []
 
     def close(self) -> None:
         self.channel.close()

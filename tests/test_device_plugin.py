@@ -9,7 +9,7 @@ import grpc
 import pytest
 
 from container_engine_accelerators_b200.agent import manager as mgr
-from container_engine_accelerators_b200.agent import nvml, protos, sharing, testing
+from container_engine_accelerators_b200.agent import nvml, preferred, protos, sharing, testing
 from container_engine_accelerators_b200.agent.config import GPUConfig, GPUSharingConfig, TransportConfig
 from container_engine_accelerators_b200.agent.plugin import DevicePluginClient
 
@@ -17,7 +17,7 @@ MOUNTS = [mgr.Mount("/home/kubernetes/bin/nvidia", "/usr/local/nvidia", True), m
 
 
 class Harness:
-    def __init__(self, tmp_path, cfg: GPUConfig, gpus=2, mig_parts=0, with_kubelet=True):
+    def __init__(self, tmp_path, cfg: GPUConfig, gpus=2, mig_parts=0, with_kubelet=True, policy="none", numa=None):
         self.root = str(tmp_path)
         self.dev = testing.make_fake_dev(self.root, gpus)
         self.proc = testing.make_fake_mig(self.root, self.dev, gpus, mig_parts) if mig_parts else str(tmp_path / "proc")
@@ -26,7 +26,13 @@ class Harness:
         os.makedirs(self.plugin_dir, exist_ok=True)
         self.kubelet = testing.KubeletStub(self.plugin_dir).start() if with_kubelet else None
         cfg.add_defaults_and_validate()
-        self.ngm = mgr.GPUManager(self.dev, self.proc, list(MOUNTS), cfg, nvml=nvml.MockNvml(self.dev), gpu_check_interval=0.6, socket_check_interval=0.1)
+        pci_root, bus_ids = nvml.PCI_DEVICES_ROOT, None
+        if numa:                                    # [numa node per gpu index]: fake sysfs entries, one bus id per GPU
+            bus_ids = [f"0000:{0x1b + 0x10 * i:02x}:00.0" for i in range(gpus)]
+            for i, node in enumerate(numa):
+                pci_root = testing.make_fake_pci(self.root, bus_ids[i], node)
+        self.ngm = mgr.GPUManager(self.dev, self.proc, list(MOUNTS), cfg, nvml=nvml.MockNvml(self.dev, bus_ids=bus_ids), pci_root=pci_root, gpu_check_interval=0.6,
+                                  socket_check_interval=0.1, preferred_allocation_policy=policy)
         self.ngm.start()
         self.endpoint = "nvidiaGPU-test.sock"
         self.thread = threading.Thread(target=self.ngm.serve, args=(self.plugin_dir, "kubelet.sock", self.endpoint), daemon=True)
@@ -203,3 +209,51 @@ def test_transport_hook_exports_b200coll_profile(harness):
     assert env["B200COLL_LIB"] == "/usr/local/nvidia/lib64/libb200coll.so" and env["LD_LIBRARY_PATH"] == "/usr/local/nvidia/lib64"
     assert env["B200COLL_ALGO"] == "nvls"
     assert len(cr.mounts) == 2      # lib dir already covered by the /usr/local/nvidia mount
+
+
+# ------------------------------------------------------------------------------------------------- preferred allocation (opt-in)
+
+def test_preferred_allocation_policy_function():
+    numa = {f"nvidia{i}": (0 if i < 4 else 1) for i in range(8)}.get
+    free = [f"nvidia{i}" for i in range(8)]
+    # a 4-GPU request fits one socket: never straddle; natural order inside the node
+    assert preferred.preferred_allocation(free, [], 4, numa) == ["nvidia0", "nvidia1", "nvidia2", "nvidia3"]
+    # 2 free on socket 0, 4 on socket 1, want 3: socket 0 cannot cover it, socket 1 can -> all from socket 1
+    assert preferred.preferred_allocation(["nvidia1", "nvidia3", "nvidia4", "nvidia5", "nvidia6", "nvidia7"], [], 3, numa) == ["nvidia4", "nvidia5", "nvidia6"]
+    # must-include pins the socket; the rest follows it
+    assert preferred.preferred_allocation(free, ["nvidia6"], 3, numa) == ["nvidia6", "nvidia4", "nvidia5"]
+    # nothing fits one socket (want 6): take the fuller socket first, then spill
+    got = preferred.preferred_allocation(["nvidia0", "nvidia1", "nvidia4", "nvidia5", "nvidia6", "nvidia7", "nvidia2"], [], 6, numa)
+    assert got[:4] == ["nvidia4", "nvidia5", "nvidia6", "nvidia7"] and set(got[4:]) <= {"nvidia0", "nvidia1", "nvidia2"}
+    assert preferred.preferred_allocation(["nvidia10", "nvidia2"], [], 1, lambda d: None) == ["nvidia2"]                 # natural, not lexicographic, order
+    # shared GPUs: nvidia0 has 1 free replica (busy), nvidia1 has 3 (idle). spread -> the idle GPU; packed -> fill the busy one
+    shared = ["nvidia0/vgpu2", "nvidia1/vgpu0", "nvidia1/vgpu1", "nvidia1/vgpu2"]
+    assert preferred.preferred_allocation(shared, [], 1, lambda d: 0, "spread") == ["nvidia1/vgpu0"]
+    assert preferred.preferred_allocation(shared, [], 1, lambda d: 0, "packed") == ["nvidia0/vgpu2"]
+    # MPS pod asking for two replicas: packed keeps them on one physical GPU (the only legal MPS shape), spread would not
+    assert [preferred.physical_of(d) for d in preferred.preferred_allocation(shared[1:], [], 2, lambda d: 0, "packed")] == ["nvidia1", "nvidia1"]
+    assert len({preferred.physical_of(d) for d in preferred.preferred_allocation(shared, [], 2, lambda d: 0, "spread")}) == 2
+    assert preferred.preferred_allocation(["nvidia0"], [], 3, lambda d: 0) == ["nvidia0"]                               # fewer free than wanted
+    with pytest.raises(ValueError):
+        preferred.preferred_allocation(free, [], 1, numa, "none")
+
+
+def test_preferred_allocation_over_grpc_is_opt_in(harness):
+    h = harness(gpus=4, policy="spread", numa=[0, 0, 1, 1])
+    reg = h.kubelet.wait_registration()
+    assert reg.options.get_preferred_allocation_available and not reg.options.pre_start_required
+    c = h.connect()
+    assert c.options().get_preferred_allocation_available
+    _, devs = first_list(c)
+    assert [n.ID for n in devs["nvidia2"].topology.nodes] == [1]
+    assert c.preferred(["nvidia0", "nvidia2", "nvidia3"], [], 2) == ["nvidia2", "nvidia3"]          # the socket that can hold both
+    assert c.preferred(["nvidia0", "nvidia1", "nvidia2", "nvidia3"], ["nvidia3"], 2) == ["nvidia3", "nvidia2"]
+
+
+def test_without_the_flag_the_contract_is_the_references(harness):
+    h = harness()
+    reg = h.kubelet.wait_registration()
+    assert not reg.HasField("options")
+    c = h.connect()
+    assert not c.options().get_preferred_allocation_available
+    assert c.preferred(["nvidia0", "nvidia1"], [], 1) == []        # stub answer, as in the reference (logs an error)

@@ -445,3 +445,51 @@ def test_malformed_http2_traffic_does_not_take_the_plugin_down(native):
     stream = c2.list_and_watch()
     assert {d.ID for d in next(stream).devices} == {"nvidia0", "nvidia1"}
     stream.cancel(); c2.close()
+
+
+# ------------------------------------------------------------------------------------------------- preferred allocation (opt-in)
+def test_preferred_allocation_native_matches_the_python_policy(native, tmp_path):
+    """-preferred-allocation-policy: options advertised in Register and GetDevicePluginOptions, NUMA-aligned answers; the C++ and
+    Python implementations are compared on the same requests (agent/preferred.py is the specification)."""
+    from container_engine_accelerators_b200.agent import preferred
+    pci = None
+    for i, node in enumerate([0, 0, 1, 1]):                       # fake NVML bus ids are 00000000:1B+i:00.0
+        pci = testing.make_fake_pci(str(tmp_path), f"0000:{0x1b + i:02x}:00.0", node)
+    n = native(gpus=4, pci=pci, extra_args=["-preferred-allocation-policy", "spread"])
+    reg = n.kubelet.wait_registration()
+    assert reg.options.get_preferred_allocation_available and not reg.options.pre_start_required
+    c = n.connect()
+    assert c.options().get_preferred_allocation_available
+    numa = {"nvidia0": 0, "nvidia1": 0, "nvidia2": 1, "nvidia3": 1}.get
+    cases = [(["nvidia0", "nvidia2", "nvidia3"], [], 2), (["nvidia0", "nvidia1", "nvidia2", "nvidia3"], ["nvidia3"], 2), (["nvidia3", "nvidia1", "nvidia0"], [], 3),
+             (["nvidia1"], [], 2), (["nvidia0", "nvidia1", "nvidia2", "nvidia3"], [], 4), (["nvidia2", "nvidia0"], ["nvidia0", "nvidia0"], 1)]
+    for available, must, size in cases:
+        assert c.preferred(available, must, size) == preferred.preferred_allocation(available, must, size, numa, "spread"), (available, must, size)
+    assert c.preferred(["nvidia0", "nvidia2", "nvidia3"], [], 2) == ["nvidia2", "nvidia3"]
+    import random
+    rng = random.Random(11)
+    ids = ["nvidia0", "nvidia1", "nvidia2", "nvidia3"]
+    for _ in range(60):                                            # differential check on random requests
+        available = rng.sample(ids, rng.randint(0, 4))
+        must = rng.sample(available, rng.randint(0, min(2, len(available))))
+        size = rng.randint(len(must), 4)
+        assert c.preferred(available, must, size) == preferred.preferred_allocation(available, must, size, numa, "spread"), (available, must, size)
+
+
+@pytest.mark.parametrize("policy", ["spread", "packed"])
+def test_preferred_allocation_native_shared_gpus(native, policy):
+    from container_engine_accelerators_b200.agent import preferred
+    n = native(config={"GPUSharingConfig": {"GPUSharingStrategy": "time-sharing", "MaxSharedClientsPerGPU": 3}}, extra_args=["-preferred-allocation-policy", policy])
+    c = n.connect()
+    free = ["nvidia0/vgpu2", "nvidia1/vgpu0", "nvidia1/vgpu1", "nvidia1/vgpu2"]        # nvidia0 is busy (1 replica left), nvidia1 idle
+    for size in (1, 2, 3):
+        assert c.preferred(free, [], size) == preferred.preferred_allocation(free, [], size, lambda d: None, policy), (policy, size)
+    assert c.preferred(free, [], 1) == (["nvidia1/vgpu0"] if policy == "spread" else ["nvidia0/vgpu2"])
+
+
+def test_native_without_the_policy_flag_keeps_the_reference_contract(native):
+    n = native()
+    assert not n.kubelet.wait_registration().HasField("options")
+    c = n.connect()
+    assert not c.options().get_preferred_allocation_available and c.preferred(["nvidia0"], [], 1) == []
+    assert "GetPreferredAllocation should NOT be called" in n.logs()
