@@ -108,7 +108,9 @@ def main() -> int:
             "config": {"model": "none (collective benchmark: the reference has no model code)", "benchmark": f"{args.op}_perf", "sizes": f"{args.min}..{args.max} x2",
                        "global_batch": None, "seq_len": None, "parallelism": f"1 rank per GPU x{n}", "placements": "out-of-place + in-place",
                        "l2": "buffers rotate through a 192 MiB window (> 126 MB L2); sizes >= 192 MiB exceed L2 by themselves",
-                       "backend": backend.version, "aggregate": "nccl-tests bus bandwidth (per-link hardware rate), not multiplied by N"},
+                       "backend": backend.version, "aggregate": "nccl-tests bus bandwidth (per-link hardware rate), not multiplied by N",
+                       "scaling_note": "bus bandwidth is normalised per GPU by construction: perfect scaling is a CONSTANT value from 2 to 8 GPUs (aggregate_bus_gbs = value x N is the whole-job rate); "
+                                       "the 1-GPU value has no bus in it (an HBM copy with the fused epilogue) and is not a base for efficiency"},
             "peak_busbw": round(summ["peak_busbw"], 2), "aggregate_bus_gbs": round(summ["avg_busbw"] * n, 2), "verified_vs_torch_fp32": bool(verified),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "power_w_max": clocks["power_w_max"]},
             "gpu_launches": int(summ["measurements"] * args.steps) if args.impl == "ours" else 0, "gpu_launches_incl_warmup": int(launches), "e2e": e2e, "wall_s": round(wall, 2), "table": harness.rows_json(rows, args.op, n),
