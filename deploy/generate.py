@@ -641,6 +641,14 @@ def build_tree() -> dict:
     for v in cos:
         t[f"driver-installer/cos/daemonset-{v}.yaml"] = [cos_driver_ds(v)]
     t["driver-installer/cos/kustomization.yaml"] = [{"apiVersion": "kustomize.config.k8s.io/v1beta1", "kind": "Kustomization", "resources": ["daemonset-preloaded.yaml"]}]
+    # one-command install of the node side for an 8xB200 (a4-highgpu-8g) pool: `kubectl apply -k deploy/overlays/a4-b200`
+    t["overlays/a4-b200/kustomization.yaml"] = [{"apiVersion": "kustomize.config.k8s.io/v1beta1", "kind": "Kustomization", "namespace": "kube-system",
+                                                 "resources": ["../../device-plugin/rbac.yaml", "../../device-plugin/xid-config.yaml", "../../device-plugin/gpu-config-b200coll.yaml",
+                                                               "../../device-plugin/device-plugin-native.yaml", "../../transport/b200coll-installer.yaml",
+                                                               "../../nri-device-injector/nri-device-injector.yaml"]}]
+    t["overlays/a4-b200-mig/kustomization.yaml"] = [{"apiVersion": "kustomize.config.k8s.io/v1beta1", "kind": "Kustomization", "namespace": "kube-system",
+                                                     "resources": ["../../device-plugin/rbac.yaml", "../../device-plugin/xid-config.yaml", "../../device-plugin/gpu-config-mig-1g23gb.yaml",
+                                                                   "../../partition-gpu/partition-gpu.yaml", "../../device-plugin/device-plugin-native.yaml"]}]
     t["driver-installer/ubuntu/daemonset.yaml"] = [ubuntu_driver_ds(preloaded=False)]
     t["driver-installer/ubuntu/daemonset-preloaded.yaml"] = [ubuntu_driver_ds()]
     for rel, ver in (("R525", "525.147.05"), ("R535", "535.230.02"), ("R550", "550.144.03"), ("R570", "570.124.06")):
