@@ -122,6 +122,27 @@ def test_ddp_trains_in_lock_step_over_the_backend():
     assert res[0][2] == pytest.approx(res[1][2])
 
 
+def _subgroups(rank, world):
+    """TP x DP style: two disjoint pairs plus a cross group, each its own process group (and, on GPUs, its own communicator)."""
+    pairs = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    cross = dist.new_group([0, 2])
+    mine = pairs[rank // 2]
+    assert isinstance(mine, pgmod.B200CollProcessGroup) and mine.size() == 2 and mine.rank() == rank % 2
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t, group=mine)
+    assert t.item() == (1.0 if rank < 2 else 5.0)
+    if rank in (0, 2):
+        u = torch.tensor([10.0 + rank]); dist.all_reduce(u, group=cross)
+        assert u.item() == 22.0
+    w = torch.tensor([1.0]); dist.all_reduce(w)
+    assert w.item() == 4.0
+    return 0
+
+
+def test_sub_groups_are_independent_process_groups():
+    _run(_subgroups, 4)
+
+
 def test_alltoallv_layout():
     m = [[1, 2, 0], [0, 3, 4], [5, 0, 6]]                                   # m[src][dst]
     assert pgmod.alltoallv_layout(m, 0) == ([1, 2, 0], [0, 1, 3], [0, 0, 0], 10)
