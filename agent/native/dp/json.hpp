@@ -169,7 +169,17 @@ class Parser {
             cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
           }
           utf8(cp, out);
-        } else out->push_back(e == 'n' ? '\n' : e == 't' ? '\t' : e == 'r' ? '\r' : e == 'b' ? '\b' : e == 'f' ? '\f' : e);
+        } else {
+          switch (e) {
+            case 'n': out->push_back('\n'); break;
+            case 't': out->push_back('\t'); break;
+            case 'r': out->push_back('\r'); break;
+            case 'b': out->push_back('\b'); break;
+            case 'f': out->push_back('\f'); break;
+            case '"': case '\\': case '/': out->push_back(e); break;
+            default: err_ = "invalid escape in JSON string"; return false;
+          }
+        }
       } else out->push_back(s_[i_++]);
     }
     if (i_ >= s_.size()) return false;

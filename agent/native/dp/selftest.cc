@@ -140,7 +140,19 @@ static void test_pb() {
   CHECK(!pb::parse(hex("0a"), &f));
 }
 
-int main() {
+// `--json-roundtrip`: parse stdin, print the re-serialised document (or "ERR <reason>"): lets the Python tests compare this
+// reader/writer with the json module on generated documents.
+static int json_roundtrip() {
+  std::string in; char buf[65536]; size_t n;
+  while ((n = fread(buf, 1, sizeof buf, stdin)) > 0) in.append(buf, n);
+  json::Value v; std::string err;
+  if (!json::Parser(in).parse(&v, &err)) { printf("ERR %s\n", err.c_str()); return 0; }
+  fputs(json::dump(v).c_str(), stdout);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "--json-roundtrip") return json_roundtrip();
   test_json();
   test_kube();
   test_hpack();

@@ -244,3 +244,28 @@ int main() {{ return 0; }}
 """)
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I/usr/local/cuda/include", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_native_json_agrees_with_python_on_generated_documents(native_build):
+    """Property test: any JSON document Python can produce survives the C++ reader/writer with the same meaning (the Node objects
+    the health checker rewrites go through exactly this path)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    exe = os.path.join(native_build, "b200-native-selftest")
+    leaves = st.one_of(st.none(), st.booleans(), st.integers(min_value=-(2 ** 63), max_value=2 ** 63 - 1), st.floats(allow_nan=False, allow_infinity=False),
+                       st.text(max_size=40))
+    docs = st.recursive(leaves, lambda kids: st.one_of(st.lists(kids, max_size=6), st.dictionaries(st.text(max_size=12), kids, max_size=6)), max_leaves=40)
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(docs, st.booleans())
+    def check(doc, ascii_only):
+        text = json.dumps(doc, ensure_ascii=ascii_only)                 # ascii_only exercises \\uXXXX escapes and surrogate pairs
+        r = subprocess.run([exe, "--json-roundtrip"], input=text.encode("utf-8", "surrogatepass"), capture_output=True, timeout=20)
+        assert r.returncode == 0, r.stderr
+        out = r.stdout.decode("utf-8", "surrogatepass")
+        if out.startswith("ERR") and not text.startswith('"ERR'):
+            raise AssertionError(f"rejected valid JSON: {text!r}: {out}")
+        assert json.loads(out) == json.loads(text)
+    check()
+    for bad in ("{", "[1,]", '{"a" 1}', "tru", '"\\x"', "[1] 2", ""):
+        r = subprocess.run([exe, "--json-roundtrip"], input=bad.encode(), capture_output=True, timeout=20)
+        assert r.stdout.startswith(b"ERR"), (bad, r.stdout)
