@@ -55,11 +55,28 @@ std::string unquote(std::string v) { if (v.size() >= 2 && ((v.front() == '"' && 
 bool parse_devices(const std::string& text, std::vector<Dev>* out, std::string* err) {
   std::vector<std::map<std::string, std::string>> items;
   std::string t = trim(text);
-  auto add_kv = [&](std::map<std::string, std::string>* m, const std::string& kv) -> bool {
-    size_t c = kv.find(':');
+  // `key: value` with either side optionally quoted (JSON is YAML: {"path": "/dev/x"}) and a trailing " # comment" dropped
+  auto strip_comment = [](const std::string& v) {
+    char quote = 0;
+    for (size_t i = 0; i < v.size(); i++) {
+      if (quote) { if (v[i] == quote) quote = 0; continue; }
+      if (v[i] == '"' || v[i] == '\'') quote = v[i];
+      else if (v[i] == '#' && (i == 0 || v[i - 1] == ' ' || v[i - 1] == '\t')) return v.substr(0, i);
+    }
+    return v;
+  };
+  auto add_kv = [&](std::map<std::string, std::string>* m, const std::string& kv_in) -> bool {
+    const std::string kv = trim(strip_comment(kv_in));
+    size_t c = std::string::npos;
+    if (!kv.empty() && (kv[0] == '"' || kv[0] == '\'')) { size_t e = kv.find(kv[0], 1); if (e != std::string::npos) c = kv.find(':', e); }   // colon after the quoted key
+    else c = kv.find(':');
     if (c == std::string::npos) return false;
-    (*m)[trim(kv.substr(0, c))] = unquote(trim(kv.substr(c + 1)));
+    (*m)[unquote(trim(kv.substr(0, c)))] = unquote(trim(kv.substr(c + 1)));
     return true;
+  };
+  auto to_uint = [](const std::string& v) -> unsigned long {          // 438, 0666 (YAML 1.1 octal), 0o666 (YAML 1.2), 0x1b6
+    if (v.size() > 2 && v[0] == '0' && (v[1] == 'o' || v[1] == 'O')) return strtoul(v.c_str() + 2, nullptr, 8);
+    return strtoul(v.c_str(), nullptr, 0);
   };
   if (t.empty()) return true;
   if (t[0] == '[') {
@@ -93,9 +110,9 @@ bool parse_devices(const std::string& text, std::vector<Dev>* out, std::string* 
     Dev d; d.path = m.count("path") ? m["path"] : "";
     if (seen.count(d.path)) continue;                        // duplicate path: first wins
     seen.insert(d.path);
-    d.file_mode = m.count("file_mode") ? strtoul(m["file_mode"].c_str(), nullptr, 0) : 0;
-    d.uid = m.count("uid") ? strtoul(m["uid"].c_str(), nullptr, 0) : 0;
-    d.gid = m.count("gid") ? strtoul(m["gid"].c_str(), nullptr, 0) : 0;
+    d.file_mode = m.count("file_mode") ? to_uint(m["file_mode"]) : 0;
+    d.uid = m.count("uid") ? to_uint(m["uid"]) : 0;
+    d.gid = m.count("gid") ? to_uint(m["gid"]) : 0;
     out->push_back(d);
   }
   return true;
@@ -219,6 +236,14 @@ int main(int argc, char** argv) {
     if (a.rfind("socket", 0) == 0) sock_path = val();
     else if (a.rfind("name", 0) == 0) name = val();
     else if (a.rfind("idx", 0) == 0) idx = val();
+    else if (a == "parse-annotation") {       // debugging aid: read an annotation value from stdin, print what would be injected (one `path mode uid gid` per line)
+      std::string text; char buf[4096]; size_t n;
+      while ((n = fread(buf, 1, sizeof buf, stdin)) > 0) text.append(buf, n);
+      std::vector<Dev> devs; std::string err;
+      if (!parse_devices(text, &devs, &err)) { printf("ERR %s\n", err.c_str()); return 1; }
+      for (auto& d : devs) printf("%s %lu %lu %lu\n", d.path.c_str(), d.file_mode, d.uid, d.gid);
+      return 0;
+    }
     else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   int fd = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);

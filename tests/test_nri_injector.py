@@ -144,3 +144,51 @@ def test_real_device_nodes_python_and_native_agree(tmp_path, native_build):
             proc.wait(5)
         except subprocess.TimeoutExpired:
             proc.kill()
+
+
+def test_native_annotation_parser_agrees_with_pyyaml_on_generated_annotations(native_build):
+    """The C++ plugin has its own parser for the subset of YAML that annotations use (block lists of flat mappings, flow form,
+    JSON form, comments, quotes, octal modes). Property test: for generated documents in that subset it extracts exactly what
+    the Python plugin (PyYAML) extracts."""
+    import subprocess
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    exe = os.path.join(native_build, "b200-nri-device-injector")
+    seg = st.text(alphabet="abcdefghijklmnopqrstuvwxyz0123456789_-.", min_size=1, max_size=8)
+    path = st.builds(lambda parts, colon: "/dev/" + "/".join(parts) + (":" + parts[0] if colon else ""), st.lists(seg, min_size=1, max_size=3), st.booleans())
+    dev = st.fixed_dictionaries({"path": path}, optional={"file_mode": st.sampled_from([0o666, 0o660, 0o600, 438]), "uid": st.integers(0, 70000), "gid": st.integers(0, 70000),
+                                                       "type": st.sampled_from(["c", "b"]), "major": st.integers(0, 511)})
+    style = st.sampled_from(["block", "flow", "json", "block_comments", "block_quoted"])
+
+    def render(devs, how):
+        if how == "json":
+            import json as _json
+            return _json.dumps(devs)
+        if how == "flow":
+            return "[" + ", ".join("{" + ", ".join(f"{k}: {v}" for k, v in d.items()) + "}" for d in devs) + "]"
+        lines = []
+        for d in devs:
+            first = True
+            for k, v in d.items():
+                val = f'"{v}"' if how == "block_quoted" and k == "path" else (f"0o{v:o}" if k == "file_mode" and v != 438 and how == "block_comments" else str(v))
+                lines.append(("- " if first else "  ") + f"{k}: {val}" + ("   # note" if how == "block_comments" else ""))
+                first = False
+            if how == "block_comments":
+                lines.append("# between items")
+        return "\n".join(lines) + "\n"
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(st.lists(dev, min_size=1, max_size=4), style)
+    def check(devs, how):
+        text = render(devs, how)
+        if how == "block_comments":                    # 0o666 is YAML 1.2; PyYAML (1.1) would read it as a string: compare against the source data instead
+            want = [d for i, d in enumerate(devs) if d["path"] not in [x["path"] for x in devs[:i]]]
+        else:
+            want = nri.get_devices("c", {KEY + "c": text})
+        r = subprocess.run([exe, "--parse-annotation"], input=text.encode(), capture_output=True, timeout=20)
+        assert r.returncode == 0, (text, r.stdout)
+        got = [l.split(" ") for l in r.stdout.decode().splitlines()]
+        assert got == [[d["path"], str(int(d.get("file_mode") or 0)), str(int(d.get("uid") or 0)), str(int(d.get("gid") or 0))] for d in want], text
+    check()
+    for bad in ("just a string", "- path: [unclosed", "[{path: /dev/x}", "key: value"):
+        r = subprocess.run([exe, "--parse-annotation"], input=bad.encode(), capture_output=True, timeout=20)
+        assert r.returncode == 1 and r.stdout.startswith(b"ERR"), bad
