@@ -863,6 +863,20 @@ int main(int argc, char** argv) {
     else if (a == "socket-check-interval") ngm.socket_check_interval = atof(need().c_str());
     else if (a == "v") g_verbosity = atoi(need().c_str());
     else if (a == "logtostderr" || a == "alsologtostderr") {}
+    else if (a == "h" || a == "help") {
+      puts("b200-device-plugin: kubelet device plugin for nvidia.com/gpu (whole GPUs, MIG slices, time-shared / MPS replicas).\n"
+           "  -plugin-directory DIR (/device-plugin)   -gpu-config PATH (/etc/nvidia/gpu_config.json)\n"
+           "  -host-path DIR -container-path DIR       driver/library mount handed to containers (/home/kubernetes/bin/nvidia -> /usr/local/nvidia)\n"
+           "  -host-vulkan-icd-path DIR -container-vulkan-icd-path DIR\n"
+           "  -enable-health-monitoring                NVML Xid events -> Unhealthy, Node condition XidCriticalError, Events (env XID_CONFIG=\"31,79\", NODE_NAME)\n"
+           "  -enable-container-gpu-metrics            Prometheus gauges on -gpu-metrics-port (2112), every -gpu-metrics-collection-interval ms (30000)\n"
+           "  -publish-driver-version                  cloud.google.com/cuda.driver-version.* Node annotations\n"
+           "  -preferred-allocation-policy none|spread|packed   answer GetPreferredAllocation (default none: no plugin options, like the reference)\n"
+           "  -xid-heartbeat-interval S (60)  -pod-resources-socket PATH  -coll-stats-dir DIR (/dev/shm)  -v N\n"
+           "test seams: -dev-directory -proc-directory -pci-root -mps-control-bin -plugin-endpoint -gpu-check-interval -socket-check-interval;\n"
+           "Kubernetes API: in-cluster config, or B200_KUBE_URL / B200_KUBE_TOKEN_FILE / B200_KUBE_CA_FILE");
+      return 0;
+    }
     else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   signal(SIGINT, on_signal); signal(SIGTERM, on_signal); signal(SIGPIPE, SIG_IGN);

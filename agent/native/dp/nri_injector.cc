@@ -244,6 +244,14 @@ int main(int argc, char** argv) {
       for (auto& d : devs) printf("%s %lu %lu %lu\n", d.path.c_str(), d.file_mode, d.uid, d.gid);
       return 0;
     }
+    else if (a == "h" || a == "help") {
+      puts("b200-nri-device-injector: containerd NRI plugin. On CreateContainer it reads the pod annotation devices.gke.io/container.<name>\n"
+           "(YAML/JSON list of {path, file_mode?, uid?, gid?}) and injects those device nodes; type/major/minor always come from lstat.\n"
+           "  --socket PATH         NRI socket (default /var/run/nri/nri.sock)\n"
+           "  --name NAME --idx NN  plugin name and index (default device_injector_nri, 10)\n"
+           "  --parse-annotation    read an annotation value on stdin and print what would be injected");
+      return 0;
+    }
     else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   int fd = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);

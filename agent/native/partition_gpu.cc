@@ -209,6 +209,14 @@ int main(int argc, char** argv) {
     else if (a == "gpu-config") g_config = val;
     else if (a == "print-table") { for (const Profile& p : kProfiles) printf("%s %d %d %s\n", p.size, p.id, p.max_count, p.families); return 0; }
     else if (a == "logtostderr" || a == "v" || a == "alsologtostderr") { /* glog-compat no-ops */ }
+    else if (a == "h" || a == "help") {
+      puts("b200-partition-gpu: bring every GPU of the node to a uniform MIG layout (no-op when it already matches).\n"
+           "  -gpu-config PATH        JSON with GPUPartitionSize (default /etc/nvidia/gpu_config.json); missing file or empty size = nothing to do\n"
+           "  -nvidia-smi-path PATH   nvidia-smi to drive (default /usr/local/nvidia/bin/nvidia-smi)\n"
+           "  -print-table            list the supported sizes: size, profile id, instances per GPU, GPU families\n"
+           "exit status: 0 done / nothing to do, 1 failure or reboot requested");
+      return 0;
+    }
     else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   struct stat st;

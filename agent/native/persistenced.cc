@@ -173,6 +173,15 @@ int main(int argc, char** argv) {
     else if (a == "ready-delay-ms") { need(); g_ready_delay_ms = atol(val.c_str()); }
     else if (a == "oneshot") g_oneshot = true;
     else if (a == "logtostderr" || a == "v") { /* glog-compat */ }
+    else if (a == "h" || a == "help") {
+      puts("b200-persistenced: sidecar for confidential-GPU and vGPU nodes. Starts nvidia-persistenced (with --uvm-persistence-mode from R550),\n"
+           "sets the conf-compute ready state, reboots the node on \"No devices were found\", starts nvidia-gridd on G4 machine types, then waits for SIGTERM.\n"
+           "  -container-path PATH      where the driver directory is mounted (default /usr/local/nvidia)\n"
+           "  -cgpu-config PATH         confidential node type file: tdx | sev enables the daemon (default /etc/nvidia/confidential_node_type.txt)\n"
+           "  -machine-type-file PATH   machine type file for the gridd decision (default /etc/nvidia/machine_type.txt)\n"
+           "  -ready-delay-ms N         wait before setting the ready state (default 1000)");
+      return 0;
+    }
     else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   int enabled = confidential_enabled();

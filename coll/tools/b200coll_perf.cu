@@ -341,6 +341,18 @@ int main(int argc, char** argv) {
       }
     }
     else if (a == "--selfcheck") { char buf[4096]; b200collResult_t r = b200collSelfCheck(buf, sizeof(buf)); fputs(buf, stdout); return r == b200collSuccess ? 0 : 1; }
+    else if (a == "-h" || a == "--help") {
+      puts("b200coll_perf (also all_reduce_perf, all_gather_perf, reduce_scatter_perf, alltoall_perf, broadcast_perf, reduce_perf): nccl-tests style sweep on libb200coll\n"
+           "  --op NAME                 collective (implied by the name the binary is called by)\n"
+           "  -b/-e SIZE -f N           sweep from -b to -e bytes multiplying by -f (1K, 64M, 1G ...)\n"
+           "  -g N | --ranks N | --devs a,b,..   ranks in this process (threads); --procs forks one process per rank instead\n"
+           "  under mpirun / torchrun (OMPI_COMM_WORLD_*, PMI_*, RANK/WORLD_SIZE/LOCAL_RANK) each process is one rank; B200COLL_JOB_ID names the job\n"
+           "  -w N -n/--iters N -c 0|1  warm-up, timed iterations, check results against the host reference\n"
+           "  -d float|half|bfloat16    input type; --out-dtype T and --scale X fuse a cast / scale into the collective\n"
+           "  --algo auto|ll|ll2|oneshot|twoshot|nvls   --inplace 0|1|2   --max-ctas N   --sweep kind:ctas:threads,...   --json FILE   --window SIZE\n"
+           "  --selfcheck               report whether this node can run the NVLink fast paths (exit 1 if not)");
+      return 0;
+    }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 1; }
   }
   if (o.factor < 2) o.factor = 2;
