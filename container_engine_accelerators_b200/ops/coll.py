@@ -244,6 +244,16 @@ class Comm:
         t._b200coll_buf = buf   # keep the allocation discoverable
         return t
 
+    def release(self, tensor) -> None:
+        """Give a tensor from `empty()` back to the arena. Explicit on purpose: allocation is a collective contract (same order and
+        sizes on every rank keep the offsets identical), so it must not depend on when each rank's garbage collector runs.
+        The caller guarantees no collective is still using the tensor."""
+        buf = getattr(tensor, "_b200coll_buf", None)
+        if buf is None:
+            raise ValueError("tensor was not allocated with Comm.empty()")
+        self.free(buf)
+        tensor._b200coll_buf = None
+
     def is_symmetric(self, tensor) -> bool:
         return bool(load().b200collIsSymmetric(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size()))
 

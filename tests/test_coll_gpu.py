@@ -69,6 +69,11 @@ def test_self_check_and_arena_tensor_aliasing(torch_cuda, coll_mod):
     torch_cuda.cuda.synchronize()
     assert torch_cuda.equal(out, torch_cuda.full((1024,), 1.5, device="cuda"))
     assert c.stats()["kernel_launches"] == 1
+    first = t.data_ptr()
+    c.release(out); c.release(t)                                           # explicit, deterministic hand-back: the next allocation reuses the space
+    assert c.empty(1024, torch_cuda.bfloat16).data_ptr() == first
+    with pytest.raises(ValueError):
+        c.release(torch_cuda.empty(4, device="cuda"))
     c.destroy()
 
 
