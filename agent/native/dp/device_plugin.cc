@@ -685,6 +685,8 @@ void append_coll_stats(std::ostringstream& os) {
       if (!f.read(raw, sizeof raw) || memcmp(raw, "B200COLL", 8) != 0) continue;
       uint32_t hdr[6]; memcpy(hdr, raw + 8, sizeof hdr);
       const int nops = hdr[0] == 1 ? 4 : 6;
+      uint64_t updated = 0; if (hdr[0] >= 2) memcpy(&updated, raw + 32, sizeof updated);
+      if (updated && (uint64_t)time(nullptr) > updated + 3600) continue;      // left behind by a process that died without CommDestroy
       uint64_t v[21]; memcpy(v, raw + 64, sizeof v);
       Page p{}; p.pid = hdr[1]; p.rank = hdr[2];
       for (int i = 0; i < nops; i++) { p.calls[i] = v[i]; p.bytes[i] = v[nops + i]; }

@@ -115,6 +115,7 @@ static b200collResult_t check_common(b200collComm* c, const void* send, void* re
 // a call took (the reference only passes NCCL_DEBUG through to opaque payloads).
 static void account(b200collComm* c, b200collOp_t op, size_t bytes, b200collAlgo_t algo) {
   c->stats.calls[op]++; c->stats.bytes[op] += bytes; c->stats.algo_calls[algo]++;
+  if ((c->stats_tick++ & 0xFF) == 0) stats_page_publish(c);      // keep the exported counters fresh without the application polling
   static const bool nvtx = [] { const char* e = getenv("B200COLL_NVTX"); return e && *e && *e != '0'; }();
   if (nvtx || debug_level() >= 2) {
     static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce"};

@@ -170,12 +170,16 @@ static void stats_page_open(b200collComm* c) {
   c->stats_shm = p; c->stats_shm_name = name;
 }
 
-// Page layout: 64-byte header, then b200collStats. version 1 had 4 ops (17 counters), version 2 has 6 (21 counters).
-static void stats_page_publish(b200collComm* c) {
+// Page layout: 64-byte header, then b200collStats. version 1 had 4 ops (17 counters), version 2 has 6 (21 counters) and a
+// last-update time in the header so exporters can drop pages left behind by processes that died without CommDestroy.
+// Called at init, on CommStatsGet and from the collective path every 256 calls (collectives.cu account()).
+void stats_page_publish(b200collComm* c) {
   if (!c->stats_shm) return;
-  struct Header { char magic[8]; uint32_t version, pid, rank, nranks, device, nvls; } h = {};
+  struct Header { char magic[8]; uint32_t version, pid, rank, nranks, device, nvls; uint64_t updated_unix_s; } h = {};
+  static_assert(sizeof(Header) <= 64, "counters start at byte 64");
   memcpy(h.magic, "B200COLL", 8);
   h.version = 2; h.pid = (uint32_t)getpid(); h.rank = c->rank; h.nranks = c->nranks; h.device = c->device; h.nvls = c->nvls;
+  h.updated_unix_s = (uint64_t)time(nullptr);
   memcpy(c->stats_shm, &h, sizeof(h));
   memcpy(static_cast<char*>(c->stats_shm) + 64, &c->stats, sizeof(c->stats));
 }

@@ -83,6 +83,7 @@ struct b200collComm {
   std::shared_ptr<b200coll::SharedGroup> group;
   void* stats_shm = nullptr;       // exported stats page (metrics exporter reads it)
   std::string stats_shm_name;
+  uint32_t stats_tick = 0;              // collective calls since init; the counters page is refreshed every 256
 };
 
 namespace b200coll {
@@ -94,6 +95,7 @@ struct LaunchPlan {
 };
 
 // tuner.cc
+void stats_page_publish(b200collComm* c);   // comm.cu
 int tuner_blocks(b200collOp_t op, b200collAlgo_t algo, size_t work_vecs, int max_ctas, int unroll);
 
 // collectives.cu

@@ -62,8 +62,13 @@ def get_devices_for_all_containers(socket_path: str = POD_RESOURCES_SOCKET, time
     return out
 
 
-def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*") -> list:
-    """Parse the 4 KiB pages written by libb200coll (coll/src/comm.cu stats_page_publish)."""
+COLL_STATS_STALE_S = 3600      # pages of processes that died without CommDestroy stop being exported after this long without an update
+
+
+def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*", now=time.time) -> list:
+    """Parse the 4 KiB pages written by libb200coll (coll/src/comm.cu stats_page_publish). The library refreshes its page every 256
+    collective calls; a page whose header timestamp is older than COLL_STATS_STALE_S belongs to a dead or idle process and is skipped
+    (the exporter runs in its own PID namespace, so it cannot ask whether the pid is alive)."""
     pages = []
     for path in glob.glob(pattern):
         try:
@@ -73,6 +78,9 @@ def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*") -> list:
                 continue
             version, pid, rank, nranks, device, nvls = struct.unpack_from("<6I", raw, 8)
             nops = 4 if version == 1 else 6          # v1 pages (older library): no broadcast / reduce counters
+            updated = struct.unpack_from("<Q", raw, 32)[0] if version >= 2 else 0
+            if updated and now() - updated > COLL_STATS_STALE_S:
+                continue
             vals = struct.unpack_from(f"<{2 * nops + 9}Q", raw, 64)
             pad = (0,) * (len(COLL_OPS) - nops)
             pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "version": version,

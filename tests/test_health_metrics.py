@@ -212,6 +212,12 @@ def test_coll_stats_page_v2_has_broadcast_and_reduce(tmp_path):
     ms.update_metrics({})
     assert sample(reg, "b200coll_calls", {"pid": "77", "rank": "0", "op": "reduce"}) == 6
     assert sample(reg, "b200coll_bytes", {"pid": "77", "rank": "0", "op": "broadcast"}) == 50
+    # header timestamp: a fresh page is exported, one that has not been touched for more than an hour is a leftover of a dead process
+    import time as _time
+    struct.pack_into("<Q", page, 32, int(_time.time()) - 30); (tmp_path / "b200coll.77.0").write_bytes(page)
+    assert len(metrics.read_coll_stats_pages(str(tmp_path / "b200coll.*"))) == 1
+    struct.pack_into("<Q", page, 32, int(_time.time()) - 7200); (tmp_path / "b200coll.77.0").write_bytes(page)
+    assert metrics.read_coll_stats_pages(str(tmp_path / "b200coll.*")) == []
 
 
 # ------------------------------------------------------------------------------------------------- native binding

@@ -198,7 +198,10 @@ def test_metrics_endpoint(native, tmp_path):
         page = bytearray(4096); page[0:8] = b"B200COLL"
         struct.pack_into("<6I", page, 8, 2, 4242, 3, 8, 3, 1)
         struct.pack_into("<21Q", page, 64, 10, 0, 0, 2, 7, 1, 1 << 30, 0, 0, 4096, 512, 64, 0, 5, 0, 2, 13, 0, 0, 21, 0)
+        struct.pack_into("<Q", page, 32, int(time.time()))                      # freshly updated
         (shm / "b200coll.4242.3").write_bytes(page)
+        stale = bytearray(page); struct.pack_into("<6I", stale, 8, 2, 999, 0, 8, 0, 1); struct.pack_into("<Q", stale, 32, int(time.time()) - 7200)
+        (shm / "b200coll.999.0").write_bytes(stale)                            # a dead process's leftover: not exported
         n = native(extra_args=["-enable-container-gpu-metrics", "-gpu-metrics-port", str(port), "-gpu-metrics-collection-interval", "200", "--pod-resources-socket", sock,
                                "--coll-stats-dir", str(shm)], env={"FAKE_NVML_UTIL": "40,60,80"})
         n.connect()
@@ -219,6 +222,7 @@ def test_metrics_endpoint(native, tmp_path):
         assert 'b200coll_calls{pid="4242",rank="3",op="all_reduce"} 10' in body and 'b200coll_calls{pid="4242",rank="3",op="broadcast"} 7' in body
         assert f'b200coll_bytes{{pid="4242",rank="3",op="all_reduce"}} {1 << 30}' in body
         assert 'b200coll_algo_calls{pid="4242",rank="3",algo="nvls"} 13' in body
+        assert 'pid="999"' not in body
     finally:
         stub.server.stop(0)
 
