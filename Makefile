@@ -7,6 +7,9 @@ manifests:                   ## regenerate deploy/**.yaml from deploy/generate.p
 	$(PY) deploy/generate.py
 test: build                  ## CPU test-suite (GPU tests: `make test-gpu` on a B200 box)
 	$(PY) -m pytest tests -x -q -m "not gpu"
+conformance: build           ## the nine kubelet-side scenarios against both plugin implementations, as processes
+	$(PY) conformance/run.py --impl native
+	$(PY) conformance/run.py --impl python
 test-race: build             ## the native daemons under ThreadSanitizer, then AddressSanitizer+UBSan (role of `go test -race`, reference Makefile:21)
 	B200_NATIVE_SAN=thread $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -x -q
 	B200_NATIVE_SAN=address $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -x -q
@@ -45,4 +48,4 @@ sass:                        ## SASS listing of the collective kernels -> profil
 	cuobjdump -sass coll/lib/libb200coll.so > profiles/libb200coll.sass
 clean:
 	$(MAKE) -C coll clean; $(MAKE) -C tools clean; $(MAKE) -C agent/native clean
-.PHONY: all build manifests test test-race test-gpu vet presubmit bench containers push containers-multi-arch device-plugin partition-gpu nri-device-injector nvidia-persistenced-installer transport-installer sass clean
+.PHONY: all build manifests test conformance test-race test-gpu vet presubmit bench containers push containers-multi-arch device-plugin partition-gpu nri-device-injector nvidia-persistenced-installer transport-installer sass clean

@@ -1,0 +1,284 @@
+#!/usr/bin/env python3
+"""Device-plugin conformance runner: drives ANY implementation of the plugin as a real process over real Unix sockets.
+
+    python conformance/run.py --impl native            # build/agent/b200-device-plugin
+    python conformance/run.py --impl python            # python -m container_engine_accelerators_b200.agent.main
+    python conformance/run.py --command '/path/to/plugin -plugin-directory {plugin_dir} -gpu-config {gpu_config} \
+        --dev-directory {dev_dir} --proc-directory {proc_dir} --pci-root {pci_root} --plugin-endpoint {endpoint}'
+
+What it does (a language-neutral acceptance harness for BASELINE config 1; the scenarios are the reference's
+pkg/gpu/nvidia/beta_plugin_test.go:36-614 plus the behaviours in SURVEY Appendix A.1-A.4): for every scenario it builds a throw-away
+node — fake /dev (nvidiaN, nvidiactl, nvidia-uvm, ...), fake /proc MIG capability tree, fake /sys PCI tree, a gpu_config.json, a stub
+kubelet listening on <plugin_dir>/kubelet.sock — starts the plugin with the scripted NVML (libfake_nvml.so, selected through
+B200AGENT_NVML_LIB), plays the kubelet's side of the v1beta1 API with grpcio, and checks what comes back. Exit status 0 = all passed.
+A plugin written in another language passes if it honours the same flags (or --command maps them) and loads NVML through an
+overridable library path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shlex
+import signal
+import subprocess
+import sys
+import tempfile
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import grpc  # noqa: E402
+
+from container_engine_accelerators_b200.agent import testing  # noqa: E402
+from container_engine_accelerators_b200.agent.plugin import DevicePluginClient  # noqa: E402
+
+FLAGS = ("-plugin-directory {plugin_dir} -gpu-config {gpu_config} --dev-directory {dev_dir} --proc-directory {proc_dir} --pci-root {pci_root} "
+         "--plugin-endpoint {endpoint} --gpu-check-interval 0.6 --socket-check-interval 0.1")
+PRESETS = {
+    "native": os.path.join(ROOT, "build", "agent", "b200-device-plugin") + " " + FLAGS,
+    "python": f"{shlex.quote(sys.executable)} -m container_engine_accelerators_b200.agent.main " + FLAGS.replace(" -plugin-directory", " --plugin-directory").replace("-gpu-config", "--gpu-config"),
+}
+
+
+class Node:
+    """One throw-away node with a plugin process on it."""
+
+    def __init__(self, command: str, gpus: int = 2, mig_parts: int = 0, config=None, numa=None, extra: str = "", env=None, kubelet: bool = True):
+        self.tmp = tempfile.TemporaryDirectory(prefix="b200-conformance-")
+        root = self.tmp.name
+        self.dev = testing.make_fake_dev(root, gpus)
+        self.proc = testing.make_fake_mig(root, self.dev, gpus, mig_parts) if mig_parts else os.path.join(root, "proc")
+        self.plugin_dir = os.path.join(root, "device-plugins"); os.makedirs(self.plugin_dir)
+        self.pci_root = os.path.join(root, "nopci")
+        for i, node in enumerate(numa or []):                                  # the scripted NVML reports 00000000:<1B+i>:00.0
+            self.pci_root = testing.make_fake_pci(root, f"0000:{0x1b + i:02x}:00.0", node)
+        self.gpu_config = os.path.join(root, "gpu_config.json")
+        if config is not None:
+            with open(self.gpu_config, "w") as f:
+                f.write(config if isinstance(config, str) else json.dumps(config))
+        self.endpoint = "nvidiaGPU-conformance.sock"
+        self.kubelet = testing.KubeletStub(self.plugin_dir).start() if kubelet else None
+        self.log_path = os.path.join(root, "plugin.log")
+        self.log = open(self.log_path, "w")
+        argv = shlex.split(command.format(plugin_dir=self.plugin_dir, gpu_config=self.gpu_config, dev_dir=self.dev, proc_dir=self.proc, pci_root=self.pci_root,
+                                          endpoint=self.endpoint)) + shlex.split(extra)
+        native_dir = os.path.join(ROOT, "build", "agent")
+        penv = {**os.environ, "PYTHONPATH": ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), "B200AGENT_NVML_LIB": os.path.join(native_dir, "libfake_nvml.so"),
+                "B200AGENT_NATIVE_LIB": os.path.join(native_dir, "libb200agent_nvml.so"), "FAKE_NVML_DEV_DIR": self.dev, "KUBERNETES_SERVICE_HOST": "", **(env or {})}
+        self.process = subprocess.Popen(argv, env=penv, stdout=self.log, stderr=self.log)
+        self.client = None
+
+    def connect(self, timeout: float = 20.0) -> DevicePluginClient:
+        path = os.path.join(self.plugin_dir, self.endpoint)
+        deadline = time.time() + timeout
+        while not os.path.exists(path):
+            if time.time() > deadline or self.process.poll() is not None:
+                raise AssertionError("plugin never created its socket:\n" + self.logs()[-3000:])
+            time.sleep(0.05)
+        if self.client:
+            self.client.close()
+        self.client = DevicePluginClient(path)
+        self.client.wait_ready()
+        return self.client
+
+    def logs(self) -> str:
+        self.log.flush()
+        with open(self.log_path) as f:
+            return f.read()
+
+    def close(self) -> None:
+        if self.client:
+            self.client.close()
+        if self.process.poll() is None:
+            self.process.send_signal(signal.SIGTERM)
+            try:
+                self.process.wait(5)
+            except subprocess.TimeoutExpired:
+                self.process.kill()
+        if self.kubelet:
+            self.kubelet.stop()
+        self.log.close()
+        self.tmp.cleanup()
+
+
+def first_list(client):
+    stream = client.list_and_watch()
+    return stream, {d.ID: d for d in next(stream).devices}
+
+
+def expect_error(fn, needle: str) -> None:
+    try:
+        fn()
+    except grpc.RpcError as e:
+        assert needle in (e.details() or ""), f"wrong error: {e.details()!r}, wanted {needle!r}"
+        return
+    raise AssertionError(f"call succeeded, wanted an error containing {needle!r}")
+
+
+# ------------------------------------------------------------------------------------------------- scenarios
+def register_list_allocate(cmd):
+    """Register{v1beta1, endpoint, nvidia.com/gpu} without options; full device list; 5 device specs + 2 read-only mounts per GPU."""
+    n = Node(cmd)
+    try:
+        reg = n.kubelet.wait_registration(20)
+        assert (reg.version, reg.endpoint, reg.resource_name) == ("v1beta1", n.endpoint, "nvidia.com/gpu") and not reg.HasField("options")
+        c = n.connect()
+        stream, devs = first_list(c)
+        assert set(devs) == {"nvidia0", "nvidia1"} and all(d.health == "Healthy" for d in devs.values())
+        cr = c.allocate(["nvidia0"]).container_responses[0]
+        assert len(cr.devices) == 5 and len(cr.mounts) == 2 and dict(cr.envs) == {}
+        assert cr.devices[0].host_path.endswith("/nvidia0") and all(d.permissions == "mrw" and d.host_path == d.container_path for d in cr.devices)
+        assert all(m.read_only for m in cr.mounts) and cr.mounts[0].container_path == "/usr/local/nvidia"
+        assert [len(r.devices) for r in c.allocate(["nvidia0", "nvidia1"], ["nvidia1"]).container_responses] == [6, 5]
+        expect_error(lambda: c.allocate(["nvidia9"]), "invalid allocation request with non-existing device nvidia9")
+        stream.cancel()
+    finally:
+        n.close()
+
+
+def numa_topology(cmd):
+    """TopologyInfo carries the NUMA node read from <pci-root>/<bus id>/numa_node."""
+    n = Node(cmd, gpus=2, numa=[0, 1])
+    try:
+        _, devs = first_list(n.connect())
+        assert [[x.ID for x in devs[d].topology.nodes] for d in ("nvidia0", "nvidia1")] == [[0], [1]]
+    finally:
+        n.close()
+
+
+def time_sharing(cmd):
+    """<id>/vgpu<k> fan-out; one virtual device per request under time-sharing."""
+    n = Node(cmd, config={"GPUSharingConfig": {"GPUSharingStrategy": "time-sharing", "MaxSharedClientsPerGPU": 3}})
+    try:
+        c = n.connect()
+        _, devs = first_list(c)
+        assert set(devs) == {f"nvidia{g}/vgpu{k}" for g in range(2) for k in range(3)}
+        assert c.allocate(["nvidia1/vgpu2"]).container_responses[0].devices[0].host_path.endswith("/nvidia1")
+        expect_error(lambda: c.allocate(["nvidia0/vgpu0", "nvidia0/vgpu1"]), "time-sharing")
+    finally:
+        n.close()
+
+
+def mig_seven_slices(cmd):
+    """B200 1g.23gb: seven nvidia0/gi<N> resources, 7 device specs per slice (GPU + 2 caps + 4 defaults)."""
+    n = Node(cmd, gpus=1, mig_parts=7, config={"GPUPartitionSize": "1g.23gb"})
+    try:
+        c = n.connect()
+        _, devs = first_list(c)
+        assert set(devs) == {f"nvidia0/gi{i}" for i in range(1, 8)}
+        assert len(c.allocate(["nvidia0/gi3"]).container_responses[0].devices) == 7
+        expect_error(lambda: c.allocate(["nvidia0/gi9"]), "non-existing GPU partition: nvidia0/gi9")
+    finally:
+        n.close()
+
+
+def bad_config_falls_back(cmd):
+    """An unparsable gpu_config.json is logged and ignored: whole GPUs are served."""
+    n = Node(cmd, config="{broken json")
+    try:
+        _, devs = first_list(n.connect())
+        assert set(devs) == {"nvidia0", "nvidia1"}
+    finally:
+        n.close()
+
+
+def hot_add_and_socket_removal(cmd):
+    """A new /dev/nvidiaN or a deleted plugin socket makes the plugin re-serve and re-register."""
+    n = Node(cmd)
+    try:
+        n.kubelet.wait_registration(20)
+        c = n.connect()
+        testing.add_fake_gpu(n.dev, 2)
+        assert n.kubelet.wait_registration(20).endpoint == n.endpoint
+        _, devs = first_list(n.connect())
+        assert set(devs) == {"nvidia0", "nvidia1", "nvidia2"}
+        os.unlink(os.path.join(n.plugin_dir, n.endpoint))
+        assert n.kubelet.wait_registration(20).endpoint == n.endpoint
+        assert len(n.connect().allocate(["nvidia2"]).container_responses[0].devices) == 5
+        del c
+    finally:
+        n.close()
+
+
+def kubelet_appears_later(cmd):
+    """No kubelet.sock at start: serve anyway, register when it shows up."""
+    n = Node(cmd, kubelet=False)
+    try:
+        c = n.connect()
+        assert len(c.allocate(["nvidia0"]).container_responses[0].devices) == 5
+        n.kubelet = testing.KubeletStub(n.plugin_dir).start()
+        assert n.kubelet.wait_registration(20).endpoint == n.endpoint
+    finally:
+        n.close()
+
+
+def xid_marks_unhealthy(cmd):
+    """A health-critical Xid (XID_CONFIG) turns the device Unhealthy in the ListAndWatch stream and blocks its allocation; others are ignored."""
+    events = tempfile.NamedTemporaryFile("w", suffix=".events", delete=False)
+    events.close()
+    n = Node(cmd, extra="-enable-health-monitoring", env={"FAKE_NVML_EVENTS": events.name, "XID_CONFIG": "31"})
+    try:
+        c = n.connect()
+        stream, devs = first_list(c)
+        assert all(d.health == "Healthy" for d in devs.values())
+        time.sleep(1.0)
+        with open(events.name, "a") as f:
+            f.write("0 13\n1 31\n")
+        assert {d.ID: d.health for d in next(stream).devices} == {"nvidia0": "Healthy", "nvidia1": "Unhealthy"}
+        expect_error(lambda: c.allocate(["nvidia1"]), "unhealthy device nvidia1")
+        stream.cancel()
+    finally:
+        n.close()
+        os.unlink(events.name)
+
+
+def transport_profile(cmd):
+    """GPUConfig.Transport = b200coll: Allocate exports the collective library's environment."""
+    n = Node(cmd, config={"Transport": {"Name": "b200coll", "Env": {"B200COLL_ALGO": "nvls"}}})
+    try:
+        env = dict(n.connect().allocate(["nvidia0"]).container_responses[0].envs)
+        assert env.get("B200COLL_LIB") == "/usr/local/nvidia/lib64/libb200coll.so" and env.get("B200COLL_ALGO") == "nvls"
+    finally:
+        n.close()
+
+
+SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
+             xid_marks_unhealthy, transport_profile]
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("--impl", choices=sorted(PRESETS), help="one of this repository's two implementations")
+    ap.add_argument("--command", help="command line template with {plugin_dir} {gpu_config} {dev_dir} {proc_dir} {pci_root} {endpoint}")
+    ap.add_argument("--only", nargs="*", help="scenario names to run (default: all)")
+    ap.add_argument("--list", action="store_true")
+    args = ap.parse_args(argv)
+    if args.list:
+        for s in SCENARIOS:
+            print(f"{s.__name__:32s} {s.__doc__.strip()}")
+        return 0
+    cmd = args.command or PRESETS.get(args.impl or "")
+    if not cmd:
+        ap.error("give --impl or --command")
+    if not os.path.exists(os.path.join(ROOT, "build", "agent", "libfake_nvml.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "agent", "native"), "-j4"], check=True, capture_output=True)
+    failed = 0
+    for s in SCENARIOS:
+        if args.only and s.__name__ not in args.only:
+            continue
+        t0 = time.time()
+        try:
+            s(cmd)
+            print(f"PASS  {s.__name__:32s} {time.time() - t0:5.1f}s")
+        except Exception:
+            failed += 1
+            print(f"FAIL  {s.__name__:32s} {time.time() - t0:5.1f}s\n" + "\n".join("      " + l for l in traceback.format_exc().splitlines()[-12:]))
+    print(f"{'FAILED' if failed else 'OK'}: {failed} scenario(s) failed" if failed else "OK: all scenarios passed")
+    return 1 if failed else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import argparse
 import logging
+import os
 import sys
 import threading
 import time
@@ -39,16 +40,33 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--publish-driver-version", action="store_true")
     p.add_argument("--dev-directory", default=DEV_DIR)
     p.add_argument("--proc-directory", default=PROC_DIR)
+    # seams the conformance harness uses to run the agent as a real process against fake /dev, /proc, /sys trees (same names as the native binary)
+    p.add_argument("--pci-root", default=nvml.PCI_DEVICES_ROOT, help=argparse.SUPPRESS)
+    p.add_argument("--plugin-endpoint", default="", help=argparse.SUPPRESS)
+    p.add_argument("--gpu-check-interval", type=float, default=None, help=argparse.SUPPRESS)
+    p.add_argument("--socket-check-interval", type=float, default=None, help=argparse.SUPPRESS)
+    p.add_argument("--kube-url", default="", help="API server URL (default: in-cluster); B200_KUBE_URL is honoured too")
     p.add_argument("--status-only", action="store_true",
                    help="do not serve the kubelet API (the native b200-device-plugin does); only publish Kubernetes-side status: Xid Events + Node condition, driver-version annotations")
     p.add_argument("--preferred-allocation-policy", choices=["none", "spread", "packed"], default="none",
                    help="answer the kubelet's GetPreferredAllocation (NUMA-aligned; spread or pack shared GPUs). none = the reference's behaviour: no plugin options")
     p.add_argument("-v", "--verbosity", type=int, default=0)
+    for glog_flag in ("--logtostderr", "--alsologtostderr"):                # accepted for drop-in compatibility with the Go binary's manifests
+        p.add_argument(glog_flag, nargs="?", const="true", default="true", help=argparse.SUPPRESS)
     return p
 
 
+def go_style_argv(argv: list) -> list:
+    """The reference's binary is Go: `-enable-health-monitoring`, `-gpu-config=/x` (single dash). Accept that spelling too, so the
+    same args line drives either implementation; `-v 3` and other one-letter flags are left alone."""
+    out = []
+    for a in argv:
+        out.append("-" + a if len(a) > 2 and a[0] == "-" and a[1] != "-" and a[1].isalpha() and (a[2].isalpha() or a[2] == "-") else a)
+    return out
+
+
 def main(argv=None) -> int:
-    args = build_parser().parse_args(argv)
+    args = build_parser().parse_args(go_style_argv(list(sys.argv[1:] if argv is None else argv)))
     logging.basicConfig(stream=sys.stderr, level=logging.DEBUG if args.verbosity >= 3 else logging.INFO, format="%(asctime)s %(levelname).1s %(name)s] %(message)s")
     log.info("device-plugin started")
     mounts = [Mount(args.host_path, args.container_path, True), Mount(args.host_vulkan_icd_path, args.container_vulkan_icd_path, True)]
@@ -59,7 +77,8 @@ def main(argv=None) -> int:
         log.error("failed to add HealthCriticalXid: %s", e)
     log.info("Using gpu config: %s", cfg)
     api = nvml.NativeNvml()
-    ngm = GPUManager(args.dev_directory, args.proc_directory, mounts, cfg, nvml=api, preferred_allocation_policy=args.preferred_allocation_policy)
+    seams = {k: v for k, v in (("gpu_check_interval", args.gpu_check_interval), ("socket_check_interval", args.socket_check_interval)) if v is not None}
+    ngm = GPUManager(args.dev_directory, args.proc_directory, mounts, cfg, nvml=api, pci_root=args.pci_root, preferred_allocation_policy=args.preferred_allocation_policy, **seams)
     while True:
         try:
             ngm.check_device_paths()
@@ -88,7 +107,8 @@ def main(argv=None) -> int:
     kc = None
     if args.enable_health_monitoring or args.publish_driver_version:
         try:
-            kc = kube.KubeClient.in_cluster()
+            url = args.kube_url or os.environ.get("B200_KUBE_URL", "")
+            kc = kube.KubeClient(url) if url else kube.KubeClient.in_cluster()
         except Exception as e:
             log.error("failed to build kube client: %s", e)
     if args.enable_health_monitoring:
@@ -109,7 +129,7 @@ def main(argv=None) -> int:
         log.info("status-only mode: the kubelet-facing API is served by the native plugin")
         threading.Event().wait()
         return 0
-    ngm.serve(args.plugin_directory, KUBELET_ENDPOINT, f"{PLUGIN_ENDPOINT_PREFIX}-{int(time.time())}.sock")
+    ngm.serve(args.plugin_directory, KUBELET_ENDPOINT, args.plugin_endpoint or f"{PLUGIN_ENDPOINT_PREFIX}-{int(time.time())}.sock")
     return 0
 
 
