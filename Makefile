@@ -29,7 +29,7 @@ vet:                         ## static checks (role of reference Makefile:27-29 
 # nvidia_persistenced_installer*, fastsocket_installer). One Dockerfile per image under docker/; IMAGE-<name> builds one,
 # `containers` builds all, `push` pushes all, `containers-multi-arch` builds amd64+arm64 (GB200/GB300 nodes) with buildx.
 REGISTRY ?= gcr.io/b200-node-accelerators
-TAG ?= $(shell git describe --tags --always --dirty 2>/dev/null || echo dev)
+TAG ?= $(shell cat VERSION 2>/dev/null || echo dev)
 IMAGES := $(patsubst docker/%.Dockerfile,%,$(wildcard docker/*.Dockerfile))
 MULTI_ARCH_IMAGES := device-plugin-native nri-device-injector partition-gpu persistenced topology-scheduler device-plugin
 $(addprefix image-,$(IMAGES)): image-%:

@@ -33,7 +33,7 @@ SCRIPTS = HERE / "scripts"
 
 # ---------------------------------------------------------------------------------------------------- images
 REG = "ghcr.io/b200-node-accelerators"
-VERSION = "v0.1.0"
+VERSION = (HERE.parent / "VERSION").read_text().strip() if (HERE.parent / "VERSION").exists() else "v0.1.0"   # one version for images, manifests and the Makefile
 IMG = {
     "device-plugin": f"{REG}/b200-device-plugin:{VERSION}",
     "device-plugin-native": f"{REG}/b200-device-plugin-native:{VERSION}",
