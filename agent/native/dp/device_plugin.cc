@@ -720,7 +720,10 @@ std::string collect_metrics(Manager* ngm, const std::string& pod_resources_socke
   auto help = [&](const char* n, const char* h) { os << "# HELP " << n << " " << h << "\n# TYPE " << n << " gauge\n"; };
   std::vector<pb::ContainerDevices> cds;
   std::string resp, err;
-  if (h2::unary_call(pod_resources_socket, "/v1alpha1.PodResourcesLister/List", "", &resp, &err, 3000) == 0) pb::decode_pod_resources(resp, &cds);
+  // v1 first (kubelet >= 1.20; same field numbers for what is read here), then the reference's v1alpha1 (metrics/devices.go:33-34)
+  int st = h2::unary_call(pod_resources_socket, "/v1.PodResourcesLister/List", "", &resp, &err, 3000);
+  if (st == 12) st = h2::unary_call(pod_resources_socket, "/v1alpha1.PodResourcesLister/List", "", &resp, &err, 3000);      // 12 = UNIMPLEMENTED
+  if (st == 0) pb::decode_pod_resources(resp, &cds);
   else if (g_verbosity > 0) LOGE("Failed to get devices for containers: %s", err.c_str());
   std::map<std::string, std::vector<std::string>> per_ctr;   // label prefix -> physical ids
   std::map<std::string, size_t> requests;

@@ -43,12 +43,21 @@ def get_devices_for_all_containers(socket_path: str = POD_RESOURCES_SOCKET, time
     except Exception as e:
         raise RuntimeError(f"error connecting to kubelet PodResourceLister service: {e}") from e
     try:
-        call = channel.unary_unary(f"/{protos.POD_RESOURCES_SERVICE}/List", request_serializer=prpb.ListPodResourcesRequest.SerializeToString,
-                                   response_deserializer=prpb.ListPodResourcesResponse.FromString)
-        try:
-            resp = call(prpb.ListPodResourcesRequest(), timeout=timeout)
-        except grpc.RpcError as e:
-            raise RuntimeError(f"error listing pod resources: {e}") from e
+        # The reference speaks v1alpha1 (metrics/devices.go:33-34). Kubelets since 1.20 also serve v1, whose messages are a field-number
+        # compatible superset, and may stop serving v1alpha1: ask for v1 first and fall back when the kubelet does not know it.
+        resp, last = None, None
+        for service in (protos.POD_RESOURCES_SERVICE_V1, protos.POD_RESOURCES_SERVICE):
+            call = channel.unary_unary(f"/{service}/List", request_serializer=prpb.ListPodResourcesRequest.SerializeToString,
+                                       response_deserializer=prpb.ListPodResourcesResponse.FromString)
+            try:
+                resp = call(prpb.ListPodResourcesRequest(), timeout=timeout)
+                break
+            except grpc.RpcError as e:
+                last = e
+                if e.code() != grpc.StatusCode.UNIMPLEMENTED:
+                    break
+        if resp is None:
+            raise RuntimeError(f"error listing pod resources: {last}") from last
         for pod in resp.pod_resources:
             for c in pod.containers:
                 key = (pod.namespace, pod.name, c.name)

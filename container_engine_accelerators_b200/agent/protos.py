@@ -103,6 +103,7 @@ podresources = _NS(_build("v1alpha1", "b200/podresources_v1alpha1.proto", {
     "ContainerDevices": [("resource_name", 1, "string"), ("device_ids", 2, "string", True)],
 }))
 POD_RESOURCES_SERVICE = "v1alpha1.PodResourcesLister"
+POD_RESOURCES_SERVICE_V1 = "v1.PodResourcesLister"      # same List() request/response field numbers for what we read (name, namespace, containers.devices)
 
 # --------------------------------------------------------------------------- NRI (subset)
 # Field numbers follow containerd/nri pkg/api/api.proto (v0.5): only what a CreateContainer-time

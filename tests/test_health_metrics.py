@@ -128,7 +128,7 @@ def test_heartbeat_only_touches_true_condition(api, tmp_path):
 
 # ------------------------------------------------------------------------------------------------- metrics
 class PodResourcesStub:
-    def __init__(self, sock, pods):
+    def __init__(self, sock, pods, service=None):
         pr = protos.podresources
         resp = pr.ListPodResourcesResponse()
         for ns, pod, ctr, resource, ids in pods:
@@ -136,11 +136,22 @@ class PodResourcesStub:
             c = p.containers.add(name=ctr)
             c.devices.add(resource_name=resource, device_ids=ids)
         self.server = grpc.server(futures.ThreadPoolExecutor(max_workers=2))
-        h = grpc.method_handlers_generic_handler(protos.POD_RESOURCES_SERVICE, {"List": grpc.unary_unary_rpc_method_handler(
+        h = grpc.method_handlers_generic_handler(service or protos.POD_RESOURCES_SERVICE, {"List": grpc.unary_unary_rpc_method_handler(
             lambda req, ctx: resp, pr.ListPodResourcesRequest.FromString, pr.ListPodResourcesResponse.SerializeToString)})
         self.server.add_generic_rpc_handlers((h,))
         self.server.add_insecure_port(f"unix:{sock}")
         self.server.start()
+
+
+@pytest.mark.parametrize("service", [protos.POD_RESOURCES_SERVICE, protos.POD_RESOURCES_SERVICE_V1])
+def test_pod_resources_v1_and_v1alpha1_kubelets(tmp_path, service):
+    """A kubelet that serves only one of the two API versions is understood either way (v1 is tried first)."""
+    sock = str(tmp_path / "pr.sock")
+    stub = PodResourcesStub(sock, [("default", "p1", "c1", "nvidia.com/gpu", ["nvidia1"])], service=service)
+    try:
+        assert metrics.get_devices_for_all_containers(sock) == {("default", "p1", "c1"): ["nvidia1"]}
+    finally:
+        stub.server.stop(0)
 
 
 def test_container_device_map_filters_resource_and_virtual_ids(tmp_path):

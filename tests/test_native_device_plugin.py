@@ -186,10 +186,11 @@ def test_xid_event_streams_unhealthy_and_blocks_allocation(native, tmp_path):
     stream.cancel()
 
 
-def test_metrics_endpoint(native, tmp_path):
+@pytest.mark.parametrize("service", ["v1alpha1.PodResourcesLister", "v1.PodResourcesLister"])
+def test_metrics_endpoint(native, tmp_path, service):
     from tests.test_health_metrics import PodResourcesStub
     sock = str(tmp_path / "pr.sock")
-    stub = PodResourcesStub(sock, [("default", "p1", "c1", "nvidia.com/gpu", ["nvidia0"]), ("default", "p2", "c1", "nvidia.com/gpu", ["nvidia1/vgpu0"])])
+    stub = PodResourcesStub(sock, [("default", "p1", "c1", "nvidia.com/gpu", ["nvidia0"]), ("default", "p2", "c1", "nvidia.com/gpu", ["nvidia1/vgpu0"])], service=service)
     import socket as _s
     s = _s.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     try:
