@@ -45,6 +45,15 @@ struct CommDev {
   unsigned long long timeout_ns;
 };
 
+// How kernels receive the communicator. Default: by value (the compiler copies the 104-byte struct to the stack because peer[] is
+// indexed with a runtime value). -DB200COLL_VARIANT_GRIDCONST (make VARIANT=gridconst -> lib/libb200coll_gridconst.so) declares it
+// __grid_constant__ so the table is indexed in the constant bank instead; an A/B candidate, not the shipped build.
+#ifdef B200COLL_VARIANT_GRIDCONST
+#define COMM_PARAM const __grid_constant__ CommDev c
+#else
+#define COMM_PARAM CommDev c
+#endif
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -111,8 +120,49 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
+#ifdef B200COLL_VARIANT_MCBAR
+// A/B candidate (make VARIANT=mcbar -> lib/libb200coll_mcbar.so): with NVLS, a barrier is ONE multimem.red on a multicast
+// counter (the switch adds 1 to block b's counter on every rank) and ONE polled local word, instead of N remote stores + N polled flags.
+// Counters grow by nranks per barrier and are never reset; how many barriers block b has taken is kept next to them (only block b of
+// this rank touches that word, kernels of a communicator are stream-ordered). Both arrays live in the zero-initialised part of the flag
+// megabyte that the flag matrix does not use. Without a multicast mapping the classic flag exchange below is used.
+constexpr size_t kOffMcCounter = 64 << 10;    // u32[kMaxBlocks], multicast-addressed
+constexpr size_t kOffMcCalls = 128 << 10;     // u32[kMaxBlocks], local bookkeeping
+template <bool RELEASE>
+__device__ __forceinline__ bool barrier_blocks_mc(const CommDev& c, uint32_t op) {
+  if (c.mc == nullptr) return false;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* calls = reinterpret_cast<uint32_t*>(c.peer[c.rank] + kOffMcCalls) + blockIdx.x;
+    const uint32_t k = *calls + 1;
+    *calls = k;
+    char* counter_mc = c.mc + kOffMcCounter + 4 * (size_t)blockIdx.x;
+    if (RELEASE) asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(counter_mc), "r"(1u) : "memory");
+    else asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(counter_mc), "r"(1u) : "memory");
+    const uint32_t want = k * (uint32_t)c.nranks;
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.peer[c.rank] + kOffMcCounter) + blockIdx.x;
+    uint32_t v = ld_relaxed_sys(mine);
+    if ((int32_t)(v - want) < 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      uint32_t spins = 0;
+      while ((int32_t)((v = ld_relaxed_sys(mine)) - want) < 0) {
+        if (((++spins) & 0x3FF) == 0) {
+          if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 1, 0xFFu, want, v, op); break; }
+        }
+      }
+    }
+    (void)ld_acquire_sys(mine);
+  }
+  __syncthreads();
+  return true;
+}
+#endif
+
 template <bool RELEASE>
 __device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch, uint32_t op) {
+#ifdef B200COLL_VARIANT_MCBAR
+  if (barrier_blocks_mc<RELEASE>(c, op)) return;
+#endif
   __syncthreads();
   const int t = threadIdx.x;
   if (t < c.nranks) {

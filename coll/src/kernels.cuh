@@ -113,7 +113,7 @@ __device__ __forceinline__ void store_out_guarded(OutT* out, size_t i, size_t co
 // SLICED=false: every peer gets my whole `count`-element input (AR, AG). SLICED=true: peer p gets block p (RS, A2A).
 // SUM=true: out[i] = sum over sources (AR, RS). SUM=false: out[src*count + i] = source's data (AG, A2A).
 template <typename InT, typename OutT, bool SLICED, bool SUM, bool MC>
-__global__ void __launch_bounds__(kThreads) k_ll(CommDev c, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_ll(COMM_PARAM, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   const uint32_t k = load_seq(c, kSeqLL);
@@ -201,7 +201,7 @@ __device__ __forceinline__ void store_raw_guarded(OutT* out, size_t vec, size_t 
 }
 
 template <typename InT, typename OutT, bool MC>
-__global__ void __launch_bounds__(kThreads) k_ll_twoshot(CommDev c, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_ll_twoshot(COMM_PARAM, const InT* __restrict__ in, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
   pdl_prologue();
   static_assert(sizeof(InT) == sizeof(OutT), "two-shot LL keeps one vector geometry for both phases");
   constexpr int E = Epv<InT>::value;
@@ -294,7 +294,7 @@ __device__ __forceinline__ void ar_tail_rank0(const CommDev& c, size_t in_off, s
 // out_local[i] = scale * sum_r peer_r[in_off + i]   (one-shot all-reduce; reduce-scatter with in_off pointing at my slice)
 // FIXED_ORDER: sum in rank order so every rank computes bit-identical results (one-shot AR).
 template <typename InT, typename OutT, bool FIXED_ORDER, bool MC>
-__global__ void __launch_bounds__(kThreads) k_pull_reduce(CommDev c, size_t in_off, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_pull_reduce(COMM_PARAM, size_t in_off, OutT* __restrict__ out, size_t count, float scale, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int U = 2;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kThreads) k_pull_reduce(CommDev c, size_t in_o
 // applies scale/cast and pushes the finished vector into every peer's out. Bytes per GPU and direction:
 // S(N-1)/N pulled + S(N-1)/N pushed -> bus bandwidth bound = link bandwidth.
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(kThreads) k_ar_twoshot(CommDev c, size_t in_off, size_t out_off, size_t count, float scale, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_ar_twoshot(COMM_PARAM, size_t in_off, size_t out_off, size_t count, float scale, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_twoshot(CommDev c, size_t in_of
 // U = vectors in flight per thread. Large messages use U=4; mid sizes use U=1 so that a slice takes several passes and
 // the multimem.st of pass k (ingress-heavy) overlaps the ld_reduce of pass k+1 (egress-heavy) instead of running back to back.
 template <typename InT, typename OutT, int U>
-__global__ void __launch_bounds__(kThreads) k_ar_nvls(CommDev c, size_t in_off, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_ar_nvls(COMM_PARAM, size_t in_off, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_nvls(CommDev c, size_t in_off, 
 // All-gather push: my `count` elements land at element offset rank*count of every peer's out.
 // MC: one multimem.st per vector (egress S/N instead of S(N-1)/N).
 template <typename InT, typename OutT, bool MC>
-__global__ void __launch_bounds__(kThreads) k_ag_push(CommDev c, const InT* __restrict__ in, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_ag_push(COMM_PARAM, const InT* __restrict__ in, size_t out_off, size_t count, float scale, int identity, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
@@ -506,7 +506,7 @@ struct A2AvArgs {
   unsigned long long prefix[kMaxRanks + 1];   // prefix over the staggered order j = 0..nranks-1 (peer = rank+1+j)
 };
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(kThreads) k_a2av_push(CommDev c, const InT* __restrict__ in, size_t out_off, A2AvArgs a, float scale, int identity, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_a2av_push(COMM_PARAM, const InT* __restrict__ in, size_t out_off, A2AvArgs a, float scale, int identity, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kThreads) k_a2av_push(CommDev c, const InT* __
 // out-of-place behave the same). MC: one multimem.st per vector -> root egress S instead of S(N-1).
 // Every rank launches the same grid; non-root CTAs only take part in the two barriers.
 template <typename InT, typename OutT, bool MC>
-__global__ void __launch_bounds__(kThreads) k_bcast(CommDev c, const InT* __restrict__ in, size_t out_off, size_t count, float scale, int identity, int root, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_bcast(COMM_PARAM, const InT* __restrict__ in, size_t out_off, size_t count, float scale, int identity, int root, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(kThreads) k_bcast(CommDev c, const InT* __rest
 // the first tells the root my send buffer is ready, the second tells me the root has finished reading it.
 // MC: the root issues multimem.ld_reduce (the switch adds, the root receives S bytes instead of S(N-1)).
 template <typename InT, typename OutT, bool MC>
-__global__ void __launch_bounds__(kThreads) k_reduce_root(CommDev c, size_t in_off, OutT* __restrict__ out, size_t count, float scale, int root, uint32_t op) {
+__global__ void __launch_bounds__(kThreads) k_reduce_root(COMM_PARAM, size_t in_off, OutT* __restrict__ out, size_t count, float scale, int root, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
   constexpr int U = 2;
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_root(CommDev c, size_t in_o
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
-__global__ void k_barrier(CommDev c, uint32_t op) {
+__global__ void k_barrier(COMM_PARAM, uint32_t op) {
   pdl_prologue();
   const uint32_t s = load_seq(c, kSeqBarrier);
   barrier_blocks<true>(c, 2 * s + 2, op);
