@@ -25,10 +25,12 @@ for pdl in 0 1; do
 done
 echo "== $(date -u +%T) build variants (A/B candidates: kernel parameter in the constant bank; multicast barrier)"
 make -C coll variants -j2 > ${O}_variants_build.log 2>&1; echo "variants rc=$?"
+port=29740
 for v in "" _gridconst _mcbar; do
   lib=coll/lib/libb200coll${v}.so
   [ -f $lib ] || continue
-  B200COLL_LIB=$PWD/$lib timeout 120 $TR --master-port 2974${#v} bench.py --gpus $NG --steps 20 --warmup 5 --no-e2e --max 64M > ${O}_ab${v:-_shipped}.json 2> ${O}_ab${v:-_shipped}.err
+  port=$((port + 1))
+  B200COLL_LIB=$PWD/$lib timeout 120 $TR --master-port $port bench.py --gpus $NG --steps 20 --warmup 5 --no-e2e --max 64M > ${O}_ab${v:-_shipped}.json 2> ${O}_ab${v:-_shipped}.err
   python3 - "$lib" ${O}_ab${v:-_shipped}.json <<'PY'
 import json, sys
 try:
