@@ -19,6 +19,7 @@ presubmit: vet                ## header + style + manifest freshness
 	$(PY) build_tools/boilerplate.py
 	bash build_tools/check_style.sh
 	$(PY) deploy/generate.py --check
+	$(PY) build_tools/check_dockerfiles.py
 bench:
 	$(PY) bench.py --table
 vet:                         ## static checks (role of reference Makefile:27-29 `go vet`): warnings-as-errors syntax pass + byte-compile

@@ -45,3 +45,9 @@ def test_shipped_tuner_table_matches_builtin(coll_lib):
     over = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env={**os.environ, "B200COLL_TUNER_FILE": os.path.join(ROOT, "coll", "tuner", "b200_nvswitch.tbl")})
     assert base.returncode == 0 and over.returncode == 0, base.stderr + over.stderr
     assert base.stdout == over.stdout
+
+
+def test_dockerfiles_only_copy_files_that_exist():
+    import subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "build_tools", "check_dockerfiles.py")], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout
