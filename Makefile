@@ -29,22 +29,29 @@ vet:                         ## static checks (role of reference Makefile:27-29 
 # ---- images (role of reference Makefile:49-99: container, container-multi-arch, push*, partition-gpu*, nri-device-injector*,
 # nvidia_persistenced_installer*, fastsocket_installer). One Dockerfile per image under docker/; IMAGE-<name> builds one,
 # `containers` builds all, `push` pushes all, `containers-multi-arch` builds amd64+arm64 (GB200/GB300 nodes) with buildx.
-REGISTRY ?= gcr.io/b200-node-accelerators
+REGISTRY ?= ghcr.io/b200-node-accelerators
 TAG ?= $(shell cat VERSION 2>/dev/null || echo dev)
 IMAGES := $(patsubst docker/%.Dockerfile,%,$(wildcard docker/*.Dockerfile))
 MULTI_ARCH_IMAGES := device-plugin-native nri-device-injector partition-gpu persistenced topology-scheduler device-plugin
+# image names as the manifests reference them (deploy/generate.py IMG): b200-<dockerfile stem> unless listed here
+image_name = $(or $(IMAGE_NAME_$(1)),b200-$(1))
+IMAGE_NAME_b200coll-installer := b200coll-installer
+IMAGE_NAME_fastsocket-installer := fastsocket-installer
+IMAGE_NAME_driver-installer-ubuntu := b200-ubuntu-driver-installer
 $(addprefix image-,$(IMAGES)): image-%:
-	docker build -f docker/$*.Dockerfile -t $(REGISTRY)/b200-$*:$(TAG) .
-containers: $(addprefix image-,$(IMAGES))   ## build every image under docker/ (needs docker + network)
+	docker build -f docker/$*.Dockerfile -t $(REGISTRY)/$(call image_name,$*):$(TAG) .
+image-driver-installer-minikube:     ## same Dockerfile as the Ubuntu installer, other entrypoint
+	docker build -f docker/driver-installer-ubuntu.Dockerfile --build-arg ENTRY=minikube -t $(REGISTRY)/b200-minikube-driver-installer:$(TAG) .
+containers: $(addprefix image-,$(IMAGES)) image-driver-installer-minikube   ## build every image (needs docker + network)
 push: containers
-	for n in $(IMAGES); do docker push $(REGISTRY)/b200-$$n:$(TAG) || exit 1; done
+	for n in $(foreach i,$(IMAGES),$(call image_name,$(i))) b200-minikube-driver-installer; do docker push $(REGISTRY)/$$n:$(TAG) || exit 1; done
 containers-multi-arch:       ## CPU-only images for linux/amd64 + linux/arm64 (the CUDA images are built per arch by their base image)
 	for n in $(MULTI_ARCH_IMAGES); do docker buildx build --platform linux/amd64,linux/arm64 -f docker/$$n.Dockerfile -t $(REGISTRY)/b200-$$n:$(TAG) --push . || exit 1; done
 device-plugin: image-device-plugin image-device-plugin-native
 partition-gpu: image-partition-gpu
 nri-device-injector: image-nri-device-injector
 nvidia-persistenced-installer: image-persistenced
-transport-installer: image-b200coll-installer     ## the fastsocket_installer analogue
+transport-installer: image-b200coll-installer image-fastsocket-installer     ## the fastsocket_installer target's role
 sass:                        ## SASS listing of the collective kernels -> profiles/
 	cuobjdump -sass coll/lib/libb200coll.so > profiles/libb200coll.sass
 clean:

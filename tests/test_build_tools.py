@@ -51,3 +51,18 @@ def test_dockerfiles_only_copy_files_that_exist():
     import subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "build_tools", "check_dockerfiles.py")], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout
+
+
+def test_every_first_party_image_in_the_manifests_has_a_build_rule():
+    """deploy/generate.py names the images; the Makefile must build and push exactly those (same registry, name and tag)."""
+    import subprocess, sys
+    sys.path.insert(0, os.path.join(ROOT, "deploy"))
+    import generate
+    wanted = {v for v in generate.IMG.values() if v.startswith(generate.REG + "/")}
+    out = subprocess.run(["make", "-n", "push"], cwd=ROOT, capture_output=True, text=True, check=True).stdout
+    built = {w for line in out.splitlines() for w in line.split() if w.startswith(generate.REG + "/")}
+    pushed = out.strip().splitlines()[-1]
+    assert wanted <= built, sorted(wanted - built)
+    for image in wanted:
+        name = image.split("/")[-1].split(":")[0]
+        assert f" {name} " in pushed.replace(";", " ; ") or f" {name};" in pushed, (name, pushed)
