@@ -145,10 +145,12 @@ def test_b200coll_install_and_env_profile(tmp_path):
     src = tmp_path / "opt"; (src / "lib").mkdir(parents=True); (src / "bin").mkdir(); (src / "tuner").mkdir()
     for f in ("lib/libb200coll.so", "lib/libb200coll_nccl.so", "b200coll-env-profile.sh", "tuner/b200_nvswitch.tbl"):
         (src / f).write_text("x")
+    (src / "bin").mkdir(exist_ok=True); (src / "bin" / "mps_probe").write_text("x")
     perf = src / "bin" / "b200coll_perf"; perf.write_text("#!/bin/bash\necho selfcheck-ran > %s/selfcheck\nexit 0\n" % tmp_path); perf.chmod(0o755)
     env = {**os.environ, "B200COLL_SRC_DIR": str(src), "NCCL_INSTALL_DIR": str(tmp_path / "lib64"), "B200COLL_BIN_DIR": str(tmp_path / "bin")}
     assert subprocess.run(["bash", os.path.join(SCRIPTS, "b200coll-install.sh")], env=env).returncode == 0
     assert (tmp_path / "lib64/libb200coll.so").exists() and (tmp_path / "lib64/b200_nvswitch.tbl").exists() and (tmp_path / "selfcheck").exists()
+    assert (tmp_path / "bin" / "mps_probe").exists()
     for name in ("all_reduce_perf", "all_gather_perf", "reduce_scatter_perf", "alltoall_perf", "broadcast_perf", "reduce_perf"):       # nccl-tests names
         assert os.readlink(tmp_path / "bin" / name) == "b200coll_perf"
     out = subprocess.run(["bash", "-c", f"B200COLL_LIB_DIR={tmp_path}/lib64 source {SCRIPTS}/b200coll-env-profile.sh; echo $B200COLL_LIB $B200COLL_ALGO $B200COLL_TUNER_FILE"], capture_output=True, text=True).stdout.split()
@@ -238,3 +240,39 @@ def test_minikube_installer_builds_kernel_source(tmp_path):
     assert "https://cdn.kernel.org/pub/linux/kernel/v5.x/linux-5.10.tar.xz" in log and "make modules_prepare" in log
     assert f"--kernel-source-path={tmp_path}/ksrc" in log
     assert (tmp_path / "ksrc/include/generated/utsrelease.h").read_text().strip() == '#define UTS_RELEASE "5.10.0-minikube"'
+
+
+def test_commands_in_manifests_exist_in_the_images_they_run_in():
+    """A container command with an absolute path must be something its image's Dockerfile puts there, something the transport
+    installer drops into the host mount (/usr/local/nvidia/bin), or a base-image shell."""
+    import glob
+    import re
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "deploy"))
+    import generate
+    dockerfile_of = {"b200-device-plugin": "device-plugin", "b200-device-plugin-native": "device-plugin-native", "b200-partition-gpu": "partition-gpu",
+                     "b200-nri-device-injector": "nri-device-injector", "b200-persistenced": "persistenced", "b200coll-installer": "b200coll-installer",
+                     "b200-topology-scheduler": "topology-scheduler", "b200-xid-inject": "xid-inject", "b200-ubuntu-driver-installer": "driver-installer-ubuntu",
+                     "b200-minikube-driver-installer": "driver-installer-ubuntu", "fastsocket-installer": "fastsocket-installer"}
+    installed_on_host = set(re.findall(r'"\$\{BIN\}/([\w-]+)"|\$\{SRC\}/bin/([\w-]+)" "\$\{BIN\}/"', open(os.path.join(SCRIPTS, "b200coll-install.sh")).read()))
+    host_bins = {"/usr/local/nvidia/bin/" + (a or b) for a, b in installed_on_host} | {f"/usr/local/nvidia/bin/{n}_perf" for n in ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce")}
+    seen = 0
+    for path in glob.glob(os.path.join(ROOT, "deploy", "**", "*.yaml"), recursive=True):
+        for doc in yaml.safe_load_all(open(path)):
+            stack = [doc]
+            while stack:
+                o = stack.pop()
+                if isinstance(o, list):
+                    stack.extend(o)
+                elif isinstance(o, dict):
+                    stack.extend(o.values())
+                    image, cmd = o.get("image"), o.get("command") or []
+                    if isinstance(image, str) and image.startswith(generate.REG + "/") and cmd and cmd[0].startswith("/"):
+                        name = image.split("/")[-1].split(":")[0]
+                        assert name in dockerfile_of, f"{path}: no Dockerfile known for image {name}"
+                        dockerfile = open(os.path.join(ROOT, "docker", dockerfile_of[name] + ".Dockerfile")).read()
+                        ok = cmd[0] in ("/bin/bash", "/bin/sh", "/bin/true") or cmd[0] in host_bins or re.search(r"^COPY .*\s" + re.escape(cmd[0]) + r"\s*$", dockerfile, re.M) \
+                            or re.search(r"^COPY .*\s" + re.escape(os.path.dirname(cmd[0])) + r"/\s*$", dockerfile, re.M)
+                        assert ok, f"{os.path.relpath(path, ROOT)}: {cmd[0]} is not provided by docker/{dockerfile_of[name]}.Dockerfile nor by the transport installer"
+                        seen += 1
+    assert seen >= 8
