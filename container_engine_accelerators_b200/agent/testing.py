@@ -231,6 +231,25 @@ class FakeKubeApi:
             self._srv.shutdown(); self._srv.server_close(); self._srv = None
 
 
+def rbac_violations(cluster_role: dict, requests: list) -> list:
+    """Which of the (method, path, content-type) requests a fake API server saw would a real one have refused under this ClusterRole?
+    Keeps the generated RBAC manifests honest: every call an agent makes in the tests must be covered by the role it is deployed with."""
+    verb_of = {"GET": "get", "PUT": "update", "PATCH": "patch", "POST": "create", "DELETE": "delete"}
+    bad = []
+    for method, path, _ in requests:
+        parts = [p for p in path.split("/") if p]                      # api v1 [namespaces <ns>] <resource> [<name> [<subresource>]]
+        rest = parts[2:]
+        if rest[:1] == ["namespaces"] and len(rest) >= 3:
+            rest = rest[2:]
+        resource = rest[0] + ("/" + rest[2] if len(rest) >= 3 else "")
+        verb = verb_of[method]
+        if method == "GET" and len(rest) == 1:
+            verb = "list"
+        if not any(resource in r.get("resources", []) and (verb in r.get("verbs", []) or "*" in r.get("verbs", [])) and "" in r.get("apiGroups", [""]) for r in cluster_role.get("rules", [])):
+            bad.append((verb, resource, path))
+    return bad
+
+
 def make_self_signed_cert(directory: str, ip: str = "127.0.0.1", dns: str = "localhost"):
     """(cert.pem, key.pem) for a throwaway CA-less server certificate with IP and DNS subject-alt-names."""
     import datetime

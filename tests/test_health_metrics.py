@@ -19,6 +19,10 @@ def api():
     a = testing.FakeKubeApi().start()
     yield a
     a.stop()
+    import yaml                                   # whatever the agent did to the API server must be allowed by the role it ships with
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    role = next(d for d in yaml.safe_load_all(open(os.path.join(root, "deploy", "device-plugin", "rbac.yaml"))) if d["kind"] == "ClusterRole")
+    assert testing.rbac_violations(role, a.requests) == []
 
 
 def make_checker(api, tmp_path, devices, xids=(), mock=None, sleep=lambda s: None):

@@ -238,6 +238,12 @@ def _wait(pred, timeout=10.0, what=""):
     raise AssertionError(f"timed out waiting for {what}")
 
 
+def _device_plugin_role():
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return next(d for d in yaml.safe_load_all(open(os.path.join(root, "deploy", "device-plugin", "rbac.yaml"))) if d["kind"] == "ClusterRole")
+
+
 def _xid_condition(api, node="node-a"):
     return next((c for c in api.nodes[node]["status"]["conditions"] if c["type"] == "XidCriticalError"), None)
 
@@ -274,6 +280,7 @@ def test_xid_event_condition_and_heartbeat_through_kube_api(native, tmp_path):
         time.sleep(1.3)                                   # RFC 3339 stamps have 1 s resolution
         _wait(lambda: _xid_condition(api)["lastHeartbeatTime"] > first_beat, timeout=5, what="heartbeat refresh")
         assert ("PUT", "/api/v1/nodes/node-a/status", "application/json") in api.requests
+        assert testing.rbac_violations(_device_plugin_role(), api.requests) == []       # everything it did is covered by deploy/device-plugin/rbac.yaml
         stream.cancel()
     finally:
         api.stop()
@@ -316,6 +323,7 @@ def test_driver_version_annotations_by_server_side_apply(native):
         assert ann == {"keep": "me", "cloud.google.com/cuda.driver-version.major": "570", "cloud.google.com/cuda.driver-version.minor": "124",
                        "cloud.google.com/cuda.driver-version.revision": "06", "cloud.google.com/cuda.driver-version.full": "570.124.06"}
         assert ("PATCH", "/api/v1/nodes/node-a", "application/apply-patch+yaml") in api.requests
+        assert testing.rbac_violations(_device_plugin_role(), api.requests) == []
     finally:
         api.stop()
 

@@ -120,6 +120,13 @@ def test_job_grouping_order_and_leftovers():
     assert topo.group_pods_by_job(mixed) == {}                                      # different tolerations: job ignored
 
 
+def _scheduler_role():
+    import os
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return next(d for d in yaml.safe_load_all(open(os.path.join(root, "deploy", "topology-scheduler", "service-account.yaml"))) if d["kind"] == "ClusterRole")
+
+
 @pytest.fixture
 def api():
     a = testing.FakeKubeApi().start()
@@ -146,6 +153,7 @@ def test_end_to_end_bind_sets_affinity_and_removes_gate(api):
         term = spec["affinity"]["nodeAffinity"]["requiredDuringSchedulingIgnoredDuringExecution"]["nodeSelectorTerms"][0]["matchExpressions"][0]
         assert term == {"key": "kubernetes.io/hostname", "operator": "In", "values": [f"node{i}"]}
     assert api.pods[("kube-system", "ignored-0")]["spec"]["schedulingGates"] == [{"name": gate}]      # --ignored-namespace is honoured
+    assert testing.rbac_violations(_scheduler_role(), api.requests) == []                            # covered by deploy/topology-scheduler/service-account.yaml
 
 
 def test_not_enough_nodes_skips_job(api):
@@ -185,6 +193,7 @@ def test_labeler_from_metadata_and_nvml(api, tmp_path):
     api.add_node("gke-node-1", labels={"keep": "1"})
     labeler.update_node_labels_from_metadata(kube.KubeClient(api.url), session=FakeMeta())
     assert api.nodes["gke-node-1"]["metadata"]["labels"] == {"keep": "1", "topology.gke.io/cluster": "cl", "topology.gke.io/rack": "ra", "topology.gke.io/host": "ho"}
+    assert testing.rbac_violations(_scheduler_role(), api.requests) == []
     from container_engine_accelerators_b200.agent import nvml
     dev = testing.make_fake_dev(str(tmp_path), 8)
     pci = testing.make_fake_pci(str(tmp_path), "0000:1b:00.0", 1)
