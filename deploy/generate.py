@@ -124,6 +124,9 @@ def daemonset(name: str, *, namespace: str = "kube-system", init: list | None = 
         pod_spec["hostNetwork"] = True
     if host_pid:
         pod_spec["hostPID"] = True
+    if volumes:          # variants share volume lists: keep only what some container of this variant mounts
+        mounted = {m["name"] for c in (init or []) + (containers or []) for m in c.get("volumeMounts") or []}
+        volumes = [v for v in volumes if v["name"] in mounted]
     if volumes:
         pod_spec["volumes"] = volumes
     if init:

@@ -276,3 +276,61 @@ def test_commands_in_manifests_exist_in_the_images_they_run_in():
                         assert ok, f"{os.path.relpath(path, ROOT)}: {cmd[0]} is not provided by docker/{dockerfile_of[name]}.Dockerfile nor by the transport installer"
                         seen += 1
     assert seen >= 8
+
+
+def _pod_specs(doc):
+    kind = doc.get("kind")
+    if kind == "Pod":
+        yield doc["metadata"], doc["spec"], None
+    elif kind in ("DaemonSet", "Deployment", "StatefulSet", "Job"):
+        t = doc["spec"]["template"]
+        yield t.get("metadata", {}), t["spec"], doc["spec"].get("selector")
+    elif kind == "JobSet":
+        for rj in doc["spec"]["replicatedJobs"]:
+            t = rj["template"]["spec"]["template"]
+            yield t.get("metadata", {}), t["spec"], None
+
+
+def test_structural_validity_of_every_workload():
+    """What `kubectl apply --dry-run=server` would catch first: selectors that do not select their own pods, volumeMounts without a
+    volume, duplicate container names, probes/ports on unknown names, ConfigMap references nobody defines."""
+    import glob
+    configmaps, workloads = set(), 0
+    docs = []
+    for path in sorted(glob.glob(os.path.join(ROOT, "deploy", "**", "*.yaml"), recursive=True)):
+        for doc in yaml.safe_load_all(open(path)):
+            if isinstance(doc, dict) and "kind" in doc:
+                docs.append((os.path.relpath(path, ROOT), doc))
+                if doc["kind"] == "ConfigMap":
+                    configmaps.add(doc["metadata"]["name"])
+    for path, doc in docs:
+        assert doc.get("apiVersion") and doc.get("metadata", {}).get("name") or doc["kind"] in ("Kustomization",), path
+        for meta, spec, selector in _pod_specs(doc):
+            workloads += 1
+            if selector:
+                for k, v in (selector.get("matchLabels") or {}).items():
+                    assert (meta.get("labels") or {}).get(k) == v, f"{path}: selector {k}={v} does not match the pod template labels {meta.get('labels')}"
+            volumes = {v["name"] for v in spec.get("volumes") or []}
+            # ResourceClaims and generic ephemeral volumes also count as mountable names
+            containers = (spec.get("initContainers") or []) + (spec.get("containers") or [])
+            names = [c["name"] for c in containers]
+            assert len(names) == len(set(names)) and names, f"{path}: container names {names}"
+            for c in containers:
+                assert c.get("image"), f"{path}: container {c['name']} has no image"
+                for m in c.get("volumeMounts") or []:
+                    assert m["name"] in volumes, f"{path}: container {c['name']} mounts undeclared volume {m['name']} (have {sorted(volumes)})"
+                for e in c.get("env") or []:
+                    ref = ((e.get("valueFrom") or {}).get("configMapKeyRef") or {})
+                    if ref and not ref.get("optional"):
+                        assert ref["name"] in configmaps, f"{path}: env {e['name']} needs ConfigMap {ref['name']} which no manifest defines"
+                for e in c.get("envFrom") or []:
+                    ref = e.get("configMapRef") or {}
+                    if ref and not ref.get("optional"):
+                        assert ref["name"] in configmaps, f"{path}: envFrom ConfigMap {ref['name']} undefined"
+            for v in spec.get("volumes") or []:
+                cm = (v.get("configMap") or {}).get("name")
+                if cm and not (v.get("configMap") or {}).get("optional"):
+                    assert cm in configmaps, f"{path}: volume {v['name']} needs ConfigMap {cm} which no manifest defines"
+            used = {m["name"] for c in containers for m in c.get("volumeMounts") or []}
+            assert volumes <= used | {v["name"] for v in spec.get("volumes") or [] if "emptyDir" in v and False}, f"{path}: volumes declared but never mounted: {sorted(volumes - used)}"
+    assert workloads >= 50
