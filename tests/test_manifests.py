@@ -334,3 +334,17 @@ def test_structural_validity_of_every_workload():
             used = {m["name"] for c in containers for m in c.get("volumeMounts") or []}
             assert volumes <= used | {v["name"] for v in spec.get("volumes") or [] if "emptyDir" in v and False}, f"{path}: volumes declared but never mounted: {sorted(volumes - used)}"
     assert workloads >= 50
+
+
+def test_services_select_a_pod_defined_in_the_same_file_and_critical_priority_only_in_kube_system():
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "deploy", "**", "*.yaml"), recursive=True)):
+        docs = [d for d in yaml.safe_load_all(open(path)) if isinstance(d, dict)]
+        pods = [(m.get("labels") or {}) for d in docs for m, _, _ in _pod_specs(d)]
+        for d in docs:
+            if d.get("kind") == "Service" and (d["spec"].get("selector")):
+                sel = d["spec"]["selector"]
+                assert any(all(lab.get(k) == v for k, v in sel.items()) for lab in pods), f"{os.path.relpath(path, ROOT)}: Service {d['metadata']['name']} selects {sel}, no pod in the file has it"
+            for _, spec, _ in _pod_specs(d):
+                if spec.get("priorityClassName", "").startswith("system-"):
+                    assert d["metadata"].get("namespace") == "kube-system", f"{os.path.relpath(path, ROOT)}: {spec['priorityClassName']} is only admitted in kube-system"
