@@ -348,3 +348,68 @@ def test_services_select_a_pod_defined_in_the_same_file_and_critical_priority_on
             for _, spec, _ in _pod_specs(d):
                 if spec.get("priorityClassName", "").startswith("system-"):
                     assert d["metadata"].get("namespace") == "kube-system", f"{os.path.relpath(path, ROOT)}: {spec['priorityClassName']} is only admitted in kube-system"
+
+
+# ------------------------------------------------------------------------------------------------- remaining host scripts
+def test_cos_enable_kdump_is_idempotent_and_cos_only(tmp_path):
+    osr = tmp_path / "os-release"
+    script = os.path.join(SCRIPTS, "cos-enable-kdump.sh")
+    osr.write_text("ID=ubuntu\n")
+    env = {**os.environ, "OS_RELEASE": str(osr), "KDUMP_HELPER": stub(tmp_path, "kdump_helper"), "REBOOT": stub(tmp_path, "reboot")}
+    assert subprocess.run(["bash", script], env=env).returncode == 0 and not (tmp_path / "calls.log").exists()          # not COS: untouched
+    osr.write_text("ID=cos\n")
+    env["KDUMP_HELPER"] = stub(tmp_path, "kdump_helper", 'if [ "$1" = status ]; then echo "kdump is ready"; fi')
+    assert subprocess.run(["bash", script], env=env).returncode == 0
+    assert "reboot" not in (tmp_path / "calls.log").read_text()                                                          # already enabled: no reboot
+    (tmp_path / "calls.log").unlink()
+    env["KDUMP_HELPER"] = stub(tmp_path, "kdump_helper", 'if [ "$1" = status ]; then echo "kdump is not enabled"; fi')
+    assert subprocess.run(["bash", script], env=env).returncode == 0
+    log = (tmp_path / "calls.log").read_text()
+    assert "kdump_helper enable" in log and log.strip().endswith("reboot")                                              # enable, then one reboot
+
+
+def test_fix_hostname_writes_the_networkd_profile(tmp_path):
+    net = tmp_path / "network"; net.mkdir()
+    env = {**os.environ, "NETWORKD_DIR": str(net), "CURL": stub(tmp_path, "curl", "echo gke-a4-node-7.c.project.internal"), "HOSTNAMECTL": stub(tmp_path, "hostnamectl"),
+           "NETWORKCTL": stub(tmp_path, "networkctl")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "fix-hostname.sh")], env=env).returncode == 0
+    prof = (net / "97-temp.network").read_text()
+    assert "Name=!eth0" in prof and "UseHostname=false" in prof and "DHCP=yes" in prof
+    log = (tmp_path / "calls.log").read_text()
+    assert "hostnamectl set-hostname gke-a4-node-7" in log and "networkctl reload" in log and "Metadata-Flavor: Google" in log
+
+
+def test_vgpu_machine_type_file(tmp_path):
+    env = {**os.environ, "ROOT_MOUNT_DIR": str(tmp_path / "root"), "CURL": stub(tmp_path, "curl", "echo projects/123/machineTypes/g4-standard-12")}
+    assert subprocess.run(["bash", os.path.join(SCRIPTS, "vgpu-machine-type.sh")], env=env).returncode == 0
+    assert (tmp_path / "root/etc/nvidia/machine_type.txt").read_text().strip() == "g4-standard-12"      # what b200-persistenced's gridd decision reads
+
+
+def test_asapd_lite_supervisor_restarts_on_dad_failure(tmp_path):
+    daemon_pid = tmp_path / "daemon.pid"
+    run = stub(tmp_path, "run_asapd_lite.sh", f"echo $$ > {daemon_pid}; exec sleep 30")
+    ip = stub(tmp_path, "ip", 'case "$*" in "-o link show") echo "1: lo: <UP>"; echo "2: gpu0rdma0: <UP>";; "-6 addr show dev gpu0rdma0") echo "inet6 fe80::1/64 scope link dadfailed tentative";; esac')
+    env = {**os.environ, "ASAPD_RUN": run, "IP": ip, "ASAPD_POLL_S": "0.1"}
+    r = subprocess.run(["bash", os.path.join(SCRIPTS, "asapd-lite-run.sh")], env=env, capture_output=True, text=True, timeout=30)
+    assert r.returncode == 1 and "DAD failed on gpu0rdma0" in r.stdout                                   # exit 1 => kubelet restarts the pod
+    log = (tmp_path / "calls.log").read_text()
+    assert "ip link set dev gpu0rdma0 down" in log and "ip link set dev gpu0rdma0 up" in log and "--enable-hairpin-probe" in log
+    ip = stub(tmp_path, "ip", 'case "$*" in "-o link show") echo "2: gpu0rdma0: <UP>";; *) echo "inet6 fe80::1/64 scope link";; esac')
+    run = stub(tmp_path, "run_asapd_lite.sh", "sleep 0.3; exit 7")
+    r = subprocess.run(["bash", os.path.join(SCRIPTS, "asapd-lite-run.sh")], env={**env, "ASAPD_RUN": run, "IP": ip}, capture_output=True, text=True, timeout=30)
+    assert r.returncode == 7                                                                             # healthy links: the daemon's own exit status is propagated
+
+
+def test_run_nccl_builds_the_reference_mpirun_line(tmp_path):
+    """run-nccl.sh <bench> <ld path> <gpus/node> <nics> <min> <max> <nhosts>: np = gpus x hosts, TCPX env, nccl-tests flags (S12)."""
+    fake_bin = tmp_path / "bin"; fake_bin.mkdir()
+    for tool in ("mpirun", "taskset"):
+        (fake_bin / tool).write_text(f"#!/bin/bash\necho \"{tool} $*\" >> {tmp_path}/calls.log\n"); (fake_bin / tool).chmod(0o755)
+    env = {**os.environ, "PATH": f"{fake_bin}:{os.environ['PATH']}"}
+    r = subprocess.run(["bash", os.path.join(SCRIPTS, "run-nccl.sh"), "all_gather_perf", "/usr/local/nvidia/lib64", "8", "eth1,eth2,eth3,eth4", "1M", "512M", "2"], env=env,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    line = (tmp_path / "calls.log").read_text()
+    assert "-np 16 " in line and "--hostfile /scripts/hostfiles2/hostfile8" in line and "NCCL_GPUDIRECTTCPX_SOCKET_IFNAME=eth1,eth2,eth3,eth4" in line
+    assert "NCCL_ALGO=Ring" in line and "NCCL_PROTO=Simple" in line and "NCCL_BUFFSIZE=4194304" in line
+    assert line.rstrip().endswith("all_gather_perf -b 1M -e 512M -f 2 -g 1 -w 5 --iters 100 -c 0")
