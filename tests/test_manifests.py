@@ -413,3 +413,27 @@ def test_run_nccl_builds_the_reference_mpirun_line(tmp_path):
     assert "-np 16 " in line and "--hostfile /scripts/hostfiles2/hostfile8" in line and "NCCL_GPUDIRECTTCPX_SOCKET_IFNAME=eth1,eth2,eth3,eth4" in line
     assert "NCCL_ALGO=Ring" in line and "NCCL_PROTO=Simple" in line and "NCCL_BUFFSIZE=4194304" in line
     assert line.rstrip().endswith("all_gather_perf -b 1M -e 512M -f 2 -g 1 -w 5 --iters 100 -c 0")
+
+
+def test_jobset_worker_head_and_followers(tmp_path):
+    """Head: waits for every peer, writes `host slots=N` lines, runs mpirun with np = nodes x slots and the NCCL_* environment.
+    Follower: stays while the head answers ssh, exits 0 once it is gone (reference nccl-test-a4x-max-jobset.yaml:104-163)."""
+    script = os.path.join(SCRIPTS, "jobset-worker.sh")
+    base = {**os.environ, "NUM_NODES": "2", "GPUS_PER_NODE": "4", "JOBSET_NAME": "nccl", "SSHD_START": "true", "POLL_S": "0.05", "HOSTFILE": str(tmp_path / "hostfile"),
+            "NCCL_ENV_SCRIPT": str(tmp_path / "absent.sh"), "NCCL_DEBUG": "INFO"}
+    # head: the second peer answers only from the third attempt on
+    tries = tmp_path / "tries"
+    ssh = stub(tmp_path, "ssh", f'case "$*" in *nccl-w-0-1*) n=$(cat {tries} 2>/dev/null || echo 0); echo $((n+1)) > {tries}; [ "$n" -ge 2 ];; esac')
+    r = subprocess.run(["bash", script], env={**base, "JOB_COMPLETION_INDEX": "0", "SSH": ssh, "MPIRUN": stub(tmp_path, "mpirun")}, capture_output=True, text=True, timeout=30)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "hostfile").read_text().splitlines() == ["nccl-w-0-0.nccl slots=4", "nccl-w-0-1.nccl slots=4"]
+    assert "waiting for nccl-w-0-1.nccl" in r.stdout
+    line = [l for l in (tmp_path / "calls.log").read_text().splitlines() if l.startswith("mpirun")][0]
+    assert "-np 8 " in line and "-x NCCL_DEBUG" in line and "-x NCCL_TESTS_SPLIT_MASK=0x0" in line and line.endswith("all_gather_perf -b 1K -e 8G -f 2 -g 1 -w 5 --iters 100 -c 1")
+    # follower: head reachable for the first 4 probes, then gone
+    (tmp_path / "calls.log").unlink(); tries.write_text("0")
+    ssh = stub(tmp_path, "ssh", f'n=$(cat {tries}); echo $((n+1)) > {tries}; [ "$n" -lt 4 ]')
+    r = subprocess.run(["bash", script], env={**base, "JOB_COMPLETION_INDEX": "1", "SSH": ssh, "MPIRUN": stub(tmp_path, "mpirun")}, capture_output=True, text=True, timeout=30)
+    assert r.returncode == 0
+    log = (tmp_path / "calls.log").read_text()
+    assert log.count("ssh ") == 5 and "mpirun" not in log           # 4 successful probes + the failing one; followers never launch anything
