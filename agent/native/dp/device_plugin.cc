@@ -27,6 +27,7 @@
 #include <array>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <regex>
 #include <set>
 #include <sstream>
@@ -509,34 +510,42 @@ struct NodeStatus {
     json::Value* info = n.at("status").find("nodeInfo");
     return info ? info->get_string("bootID") : "";
   }
-  bool put(const json::Value& n, const char* why) {
-    kube::Response r = api.update_node_status(node, n);
-    if (!r.ok()) { LOGE("Failed to update node %s status %s: %s", node.c_str(), why, r.describe().c_str()); return false; }
-    return true;
+  // GET the Node, let `mutate` edit it (0 = nothing to write, 1 = write, -1 = give up), PUT the status. The PUT carries the GET's
+  // resourceVersion, so a write that raced with somebody else's (the kubelet's status updates) comes back 409: re-read and try again
+  // rather than lose the condition (the reference logs the error and gives up, health_checker.go:338-343). Returns 1 written, 0 no-op, -1 failed.
+  int update_status(const char* why, const std::function<int(json::Value&)>& mutate, int attempts = 4) {
+    for (int attempt = 0; attempt < attempts; attempt++) {
+      json::Value n;
+      if (!fetch(&n, why)) return -1;
+      const int verdict = mutate(n);
+      if (verdict <= 0) return verdict;
+      kube::Response r = api.update_node_status(node, n);
+      if (r.ok()) return 1;
+      if (r.status != 409 || attempt == attempts - 1) { LOGE("Failed to update node %s status %s: %s", node.c_str(), why, r.describe().c_str()); return -1; }
+      LOGI("Node %s changed under us (conflict); retrying the status update", node.c_str());
+    }
+    return -1;
   }
   // After a reboot (bootID differs from the one stored in the condition's message) the repair happened: drop the condition.
   bool reset_condition(bool* removed) {
-    json::Value n;
     *removed = false;
-    if (!fetch(&n, "to reset the XID condition")) return false;
-    const std::string boot = boot_id(n);
-    json::Value* conds = n.at("status").find("conditions");
-    if (conds && conds->kind == json::Value::Array) {
+    const int rc = update_status("to reset the XID condition", [&](json::Value& n) {
+      const std::string boot = boot_id(n);
+      json::Value* conds = n.at("status").find("conditions");
+      if (!conds || conds->kind != json::Value::Array) return 0;
       std::vector<json::Value> kept;
       for (auto& c : conds->arr) {
         const std::string last = c.get_string("message");
         if (c.get_string("type") == kXidCondition && c.get_string("status") == "True" && !boot.empty() && !last.empty() && boot != last) continue;
         kept.push_back(c);
       }
-      if (kept.size() != conds->arr.size()) {
-        conds->arr = kept;
-        if (!put(n, "to remove the XID condition")) return false;
-        *removed = true;
-        LOGI("Successfully removed XIDCriticalError condition from node %s.", node.c_str());
-        return true;
-      }
-    }
-    LOGI("XIDCriticalError condition doesn't exist for node %s.", node.c_str());
+      if (kept.size() == conds->arr.size()) return 0;
+      conds->arr = kept;
+      return 1;
+    });
+    if (rc < 0) return false;
+    if (rc == 1) { *removed = true; LOGI("Successfully removed XIDCriticalError condition from node %s.", node.c_str()); }
+    else LOGI("XIDCriticalError condition doesn't exist for node %s.", node.c_str());
     return true;
   }
   void reset_condition_with_backoff(std::atomic<bool>* stop, double timeout_s = 120.0) {
@@ -553,23 +562,20 @@ struct NodeStatus {
   // Adds the Xid to the condition's reason (a JSON object used as a set), creating the condition if needed.
   void monitor_xid(long xid) {
     if (std::find(std::begin(kMonitorXids), std::end(kMonitorXids), xid) == std::end(kMonitorXids)) return;
-    json::Value n;
-    if (!fetch(&n, "to record the XID condition")) return;
-    json::Value& conds = n.at("status").at("conditions");
-    if (conds.kind != json::Value::Array) conds = json::Value::array();
     const std::string key = std::to_string(xid);
-    bool found = false;
-    for (auto& c : conds.arr) {
-      if (c.get_string("type") != kXidCondition) continue;
-      found = true;
-      json::Value reason; std::string err, text = c.get_string("reason");
-      if (text.empty()) text = "{}";
-      if (!json::Parser(text).parse(&reason, &err) || reason.kind != json::Value::Object) { LOGE("Can't decode the value of condition.Reason %s", text.c_str()); return; }
-      if (reason.get(key)) { LOGI("XIDCriticalError condition already includes this XID %ld, skip", xid); return; }
-      reason.at(key) = json::Value::of(true);
-      c.at("reason") = json::Value::of(json::dump(reason));
-    }
-    if (!found) {
+    const int rc = update_status("to add the XIDCriticalError condition", [&](json::Value& n) {
+      json::Value& conds = n.at("status").at("conditions");
+      if (conds.kind != json::Value::Array) conds = json::Value::array();
+      for (auto& c : conds.arr) {
+        if (c.get_string("type") != kXidCondition) continue;
+        json::Value reason; std::string err, text = c.get_string("reason");
+        if (text.empty()) text = "{}";
+        if (!json::Parser(text).parse(&reason, &err) || reason.kind != json::Value::Object) { LOGE("Can't decode the value of condition.Reason %s", text.c_str()); return -1; }
+        if (reason.get(key)) { LOGI("XIDCriticalError condition already includes this XID %ld, skip", xid); return 0; }
+        reason.at(key) = json::Value::of(true);
+        c.at("reason") = json::Value::of(json::dump(reason));
+        return 1;
+      }
       const std::string now = kube::now_rfc3339();
       json::Value reason = json::Value::object(); reason.at(key) = json::Value::of(true);
       json::Value c = json::Value::object();
@@ -577,18 +583,19 @@ struct NodeStatus {
       c.at("lastHeartbeatTime") = json::Value::of(now); c.at("lastTransitionTime") = json::Value::of(now);
       c.at("reason") = json::Value::of(json::dump(reason)); c.at("message") = json::Value::of(boot_id(n));
       conds.arr.push_back(c);
-    }
-    if (put(n, "to add the XIDCriticalError condition")) LOGI("Successfully add XIDCriticalError condition on node %s.", node.c_str());
+      return 1;
+    });
+    if (rc == 1) LOGI("Successfully add XIDCriticalError condition on node %s.", node.c_str());
   }
   void heartbeat() {
-    json::Value n;
-    if (!fetch(&n, "for heartbeat update")) return;
-    json::Value* conds = n.at("status").find("conditions");
-    bool modified = false;
-    if (conds && conds->kind == json::Value::Array)
-      for (auto& c : conds->arr)
-        if (c.get_string("type") == kXidCondition && c.get_string("status") == "True") { c.at("lastHeartbeatTime") = json::Value::of(kube::now_rfc3339()); modified = true; }
-    if (modified) put(n, "to update the XIDCondition heartbeat");
+    update_status("to update the XIDCondition heartbeat", [&](json::Value& n) {
+      json::Value* conds = n.at("status").find("conditions");
+      int modified = 0;
+      if (conds && conds->kind == json::Value::Array)
+        for (auto& c : conds->arr)
+          if (c.get_string("type") == kXidCondition && c.get_string("status") == "True") { c.at("lastHeartbeatTime") = json::Value::of(kube::now_rfc3339()); modified = 1; }
+      return modified;
+    });
   }
   void record_event(long xid) {
     json::Value n;

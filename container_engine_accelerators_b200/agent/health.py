@@ -51,22 +51,40 @@ class GPUHealthChecker:
         self.wait_ms = wait_ms
 
     # ------------------------------------------------------------------ node condition
+    def _update_node_status(self, mutate, attempts: int = 4) -> bool:
+        """GET the Node, let `mutate(node)` edit it (return False for "nothing to write"), PUT the status. The PUT carries the
+        resourceVersion of the GET, so a write that raced with somebody else's (the kubelet's status updates) is refused with 409:
+        re-read and try again instead of losing the condition (the reference logs the error and gives up, health_checker.go:338-343)."""
+        for attempt in range(attempts):
+            node = self.kube.get_node(self.node_name)
+            if mutate(node) is False:
+                return False
+            try:
+                self.kube.update_node_status(node)
+                return True
+            except kubemod.KubeError as e:
+                if e.status != 409 or attempt == attempts - 1:
+                    raise
+                log.info("Node %s changed under us (conflict); retrying the status update", self.node_name)
+        return False
+
     def reset_xid_condition(self) -> bool:
         """Returns True if a condition was removed."""
-        node = self.kube.get_node(self.node_name)
-        status = node.setdefault("status", {})
-        boot_id = (status.get("nodeInfo") or {}).get("bootID", "")
-        conds = status.get("conditions") or []
-        kept = []
-        for c in conds:
-            if c.get("type") == XID_CONDITION_TYPE and c.get("status") == "True":
-                last = c.get("message", "")
-                if boot_id and last and boot_id != last:
-                    continue        # rebooted since the fault: auto-repair happened
-            kept.append(c)
-        if len(kept) != len(conds):
+        def mutate(node):
+            status = node.setdefault("status", {})
+            boot_id = (status.get("nodeInfo") or {}).get("bootID", "")
+            conds = status.get("conditions") or []
+            kept = []
+            for c in conds:
+                if c.get("type") == XID_CONDITION_TYPE and c.get("status") == "True":
+                    last = c.get("message", "")
+                    if boot_id and last and boot_id != last:
+                        continue        # rebooted since the fault: auto-repair happened
+                kept.append(c)
+            if len(kept) == len(conds):
+                return False
             status["conditions"] = kept
-            self.kube.update_node_status(node)
+        if self._update_node_status(mutate):
             log.info("Successfully removed XIDCriticalError condition from node %s.", self.node_name)
             return True
         log.info("XIDCriticalError condition doesn't exist for node %s.", self.node_name)
@@ -90,56 +108,49 @@ class GPUHealthChecker:
     def monitor_xid_event(self, xid: int) -> None:
         if xid not in self.monitor or self.kube is None:
             return
-        try:
-            node = self.kube.get_node(self.node_name)
-        except Exception as e:
-            log.error("Failed to get node %s: %s", self.node_name, e)
-            return
-        status = node.setdefault("status", {})
-        conds = status.setdefault("conditions", [])
-        found = False
-        for c in conds:
-            if c.get("type") == XID_CONDITION_TYPE:
-                found = True
-                try:
-                    reason = json.loads(c.get("reason") or "{}")
-                except ValueError:
-                    log.error("Can't decode the value of condition.Reason %s", c.get("reason"))
-                    return
-                if str(xid) in reason:
-                    log.info("XIDCriticalError condition already includes this XID %d, skip", xid)
-                    return
-                reason[str(xid)] = True
-                c["reason"] = json.dumps(reason, sort_keys=True, separators=(",", ":"))
-        if not found:
+
+        def mutate(node):
+            status = node.setdefault("status", {})
+            conds = status.setdefault("conditions", [])
+            for c in conds:
+                if c.get("type") == XID_CONDITION_TYPE:
+                    try:
+                        reason = json.loads(c.get("reason") or "{}")
+                    except ValueError:
+                        log.error("Can't decode the value of condition.Reason %s", c.get("reason"))
+                        return False
+                    if str(xid) in reason:
+                        log.info("XIDCriticalError condition already includes this XID %d, skip", xid)
+                        return False
+                    reason[str(xid)] = True
+                    c["reason"] = json.dumps(reason, sort_keys=True, separators=(",", ":"))
+                    return True
             now = kubemod.now_rfc3339()
             conds.append({"type": XID_CONDITION_TYPE, "status": "True", "lastHeartbeatTime": now, "lastTransitionTime": now,
                           "reason": json.dumps({str(xid): True}, separators=(",", ":")), "message": (status.get("nodeInfo") or {}).get("bootID", "")})
+            return True
         try:
-            self.kube.update_node_status(node)
-            log.info("Successfully add XIDCriticalError condition on node %s.", self.node_name)
+            if self._update_node_status(mutate):
+                log.info("Successfully add XIDCriticalError condition on node %s.", self.node_name)
         except Exception as e:
             log.error("Failed to update node %s status to add XIDCriticalError condition: %s", self.node_name, e)
 
     def update_last_heartbeat(self) -> bool:
         if self.kube is None:
             return False
+
+        def mutate(node):
+            modified = False
+            for c in (node.get("status") or {}).get("conditions") or []:
+                if c.get("type") == XID_CONDITION_TYPE and c.get("status") == "True":
+                    c["lastHeartbeatTime"] = kubemod.now_rfc3339()
+                    modified = True
+            return modified
         try:
-            node = self.kube.get_node(self.node_name)
+            return self._update_node_status(mutate)
         except Exception as e:
-            log.error("Failed to get node %s for heartbeat update: %s", self.node_name, e)
+            log.error("Failed to update node %s status to update XIDCondition heartbeat: %s", self.node_name, e)
             return False
-        modified = False
-        for c in (node.get("status") or {}).get("conditions") or []:
-            if c.get("type") == XID_CONDITION_TYPE and c.get("status") == "True":
-                c["lastHeartbeatTime"] = kubemod.now_rfc3339()
-                modified = True
-        if modified:
-            try:
-                self.kube.update_node_status(node)
-            except Exception as e:
-                log.error("Failed to update node %s status to update XIDCondition heartbeat: %s", self.node_name, e)
-        return modified
 
     def record_xid_event(self, xid: int) -> None:
         if self.kube is None:

@@ -118,11 +118,13 @@ class FakeKubeApi:
         self.requests: list = []    # (method, path, content-type)
         self.bearer_tokens: list = []
         self.fail_next_gets = 0
+        self.conflicts = 0          # PUTs refused because their resourceVersion was stale (optimistic concurrency, like the real API server)
+        self.stale_next_puts = 0    # make the next N node PUTs look stale: what a kubelet status write between our GET and PUT does
         self._srv = None
         self.url = ""
 
     def add_node(self, name: str, boot_id: str = "boot-1", labels=None, annotations=None, conditions=None, allocatable=None, taints=None) -> dict:
-        node = {"apiVersion": "v1", "kind": "Node", "metadata": {"name": name, "uid": f"uid-{name}", "labels": dict(labels or {}), "annotations": dict(annotations or {})},
+        node = {"apiVersion": "v1", "kind": "Node", "metadata": {"name": name, "uid": f"uid-{name}", "resourceVersion": "1", "labels": dict(labels or {}), "annotations": dict(annotations or {})},
                 "spec": {"taints": list(taints or [])},
                 "status": {"nodeInfo": {"bootID": boot_id}, "conditions": list(conditions or [{"type": "Ready", "status": "True"}]), "allocatable": dict(allocatable or {})}}
         self.nodes[name] = node
@@ -164,11 +166,24 @@ class FakeKubeApi:
                     if name not in api.nodes:
                         return self._send(404, {"message": "not found"})
                     body = self._body()
+                    def bump():
+                        meta = api.nodes[name].setdefault("metadata", {})
+                        meta["resourceVersion"] = str(int(meta.get("resourceVersion", "0")) + 1)
                     if method == "PUT":
+                        sent = (body.get("metadata") or {}).get("resourceVersion")
+                        current = api.nodes[name].get("metadata", {}).get("resourceVersion")
+                        if api.stale_next_puts > 0 or (sent is not None and current is not None and sent != current):
+                            if api.stale_next_puts > 0:
+                                api.stale_next_puts -= 1
+                                bump()
+                            api.conflicts += 1
+                            return self._send(409, {"kind": "Status", "reason": "Conflict", "message": f"Operation cannot be fulfilled on nodes \"{name}\": the object has been modified"})
                         if status:
                             api.nodes[name]["status"] = body.get("status", {})
                         else:
+                            body.setdefault("metadata", {})["resourceVersion"] = current
                             api.nodes[name] = body
+                        bump()
                         return self._send(200, api.nodes[name])
                     if method == "PATCH":
                         ctype = self.headers.get("Content-Type", "")
@@ -181,6 +196,7 @@ class FakeKubeApi:
                                     api.nodes[name]["metadata"].setdefault(key, {}).pop(k, None)
                                 else:
                                     api.nodes[name]["metadata"].setdefault(key, {})[k] = v
+                        bump()
                         return self._send(200, api.nodes[name])
                 if u.path == "/api/v1/nodes" and method == "GET":
                     return self._send(200, {"items": list(api.nodes.values())})

@@ -324,3 +324,58 @@ print(json.dumps({{k: v.health for k, v in ngm.list_devices().items()}}))
     r = run_py(code, {"FAKE_NVML_EVENTS": str(events)})
     assert r.returncode == 0, r.stderr
     assert json.loads(r.stdout.strip().splitlines()[-1]) == {"nvidia0": "Healthy", "nvidia1": "Healthy", "nvidia2": "Unhealthy"}
+
+
+def test_background_checker_lifecycle_and_api_failures(api, tmp_path, monkeypatch):
+    """start() in the background (reset + heartbeat + listener threads), an event arriving while it runs, API-server failures on
+    every path (logged, never fatal: the device still goes Unhealthy), and stop() joining the listener before the event set is freed."""
+    monkeypatch.setattr(health, "HEARTBEAT_S", 0.05)
+    stale = {"type": "XidCriticalError", "status": "True", "reason": '{"48":true}', "message": "boot-OLD", "lastHeartbeatTime": "2020-01-01T00:00:00Z"}
+    api.add_node("node-1", boot_id="boot-A", conditions=[{"type": "Ready", "status": "True"}, dict(stale)])
+    hc, m, reported = make_checker(api, tmp_path, PLAIN)
+    closed = []
+    orig_close = m.events_close
+    m.events_close = lambda h: (closed.append(h), orig_close(h))[1]
+    hc.start()                                                             # background=True
+    deadline = time.time() + 5
+    while time.time() < deadline and any(c["type"] == "XidCriticalError" for c in api.nodes["node-1"]["status"]["conditions"]):
+        time.sleep(0.02)
+    assert not any(c["type"] == "XidCriticalError" for c in api.nodes["node-1"]["status"]["conditions"])     # rebooted since: cleared at start-up
+    m.events.append(nvml.XidEvent("GPU-aaa", 48))
+    while time.time() < deadline and not reported:
+        time.sleep(0.02)
+    assert [(d.id, d.health) for d in reported] == [("nvidia0", "Unhealthy")]
+    cond = lambda: next(c for c in api.nodes["node-1"]["status"]["conditions"] if c["type"] == "XidCriticalError")
+    first = cond()["lastHeartbeatTime"]
+    time.sleep(1.2)
+    assert cond()["lastHeartbeatTime"] > first                              # heartbeat thread refreshes it
+    # the API server goes away: events keep marking devices, nothing raises
+    api.fail_next_gets = 10 ** 6
+    m.events.append(nvml.XidEvent("GPU-bbb", 79))                           # monitored only; needs the API for everything it does
+    m.events.append(nvml.XidEvent("GPU-bbb", 48))
+    while time.time() < deadline + 5 and len(reported) < 2:
+        time.sleep(0.02)
+    assert [(d.id, d.health) for d in reported][1] == ("nvidia1", "Unhealthy")
+    assert hc.update_last_heartbeat() is False
+    hc.stop()
+    assert closed and hc._event_set is None and not any(t.is_alive() for t in hc._threads)
+    api.fail_next_gets = 0
+
+
+def test_status_updates_survive_write_conflicts(api, tmp_path):
+    """A kubelet status write between our GET and PUT makes the API server answer 409: re-read and retry, do not lose the condition."""
+    api.add_node("node-1", boot_id="boot-A")
+    hc, m, reported = make_checker(api, tmp_path, PLAIN)
+    hc.start(background=False)
+    api.stale_next_puts = 2
+    m.events.append(nvml.XidEvent("GPU-aaa", 79))
+    hc.poll_once()
+    cond = [c for c in api.nodes["node-1"]["status"]["conditions"] if c["type"] == "XidCriticalError"]
+    assert cond and cond[0]["reason"] == '{"79":true}' and api.conflicts == 2
+    api.stale_next_puts = 1
+    assert hc.update_last_heartbeat() is True and api.conflicts == 3
+    api.stale_next_puts = 10                                     # persistent conflicts: give up after a few attempts, logged, not raised
+    m.events.append(nvml.XidEvent("GPU-aaa", 63))
+    hc.poll_once()
+    assert json.loads([c for c in api.nodes["node-1"]["status"]["conditions"] if c["type"] == "XidCriticalError"][0]["reason"]) == {"79": True}
+    api.stale_next_puts = 0

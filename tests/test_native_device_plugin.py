@@ -506,3 +506,24 @@ def test_native_without_the_policy_flag_keeps_the_reference_contract(native):
     c = n.connect()
     assert not c.options().get_preferred_allocation_available and c.preferred(["nvidia0"], [], 1) == []
     assert "GetPreferredAllocation should NOT be called" in n.logs()
+
+
+def test_native_status_updates_survive_write_conflicts(native, tmp_path):
+    """409 on the status PUT (somebody wrote the Node between our GET and PUT): the native plugin re-reads and retries."""
+    api = testing.FakeKubeApi().start()
+    try:
+        api.add_node("node-a", boot_id="boot-7")
+        events = tmp_path / "events.txt"; events.write_text("")
+        n = native(extra_args=["-enable-health-monitoring", "--xid-heartbeat-interval", "30"], env={"FAKE_NVML_EVENTS": str(events), "B200_KUBE_URL": api.url, "NODE_NAME": "node-a"})
+        c = n.connect()
+        stream = c.list_and_watch(); next(stream)
+        time.sleep(0.5)
+        api.stale_next_puts = 2
+        with open(events, "a") as f:
+            f.write("0 79\n")
+        _wait(lambda: _xid_condition(api) is not None, what="condition despite two conflicts")
+        assert json.loads(_xid_condition(api)["reason"]) == {"79": True} and api.conflicts == 2
+        assert "retrying the status update" in n.logs()
+        stream.cancel()
+    finally:
+        api.stop()
