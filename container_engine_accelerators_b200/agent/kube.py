@@ -32,9 +32,11 @@ class KubeClient:
         self.session = requests.Session()
         if token:
             self.session.headers["Authorization"] = f"Bearer {token}"
-        self.session.verify = ca_cert if ca_cert else True
+        # passed on every request: a session-level `verify` loses to REQUESTS_CA_BUNDLE / CURL_CA_BUNDLE from the environment
+        # (requests merges the environment in at request level), and the cluster CA must win over the image's CA bundle
+        self.verify = ca_cert if ca_cert else True
         if base_url.startswith("http://"):
-            self.session.verify = False
+            self.verify = False
 
     @classmethod
     def in_cluster(cls) -> "KubeClient":
@@ -47,6 +49,20 @@ class KubeClient:
             host = f"[{host}]"
         return cls(f"https://{host}:{port}", token, os.path.join(SA_DIR, "ca.crt"))
 
+    @classmethod
+    def from_env(cls, url: str = "") -> "KubeClient":
+        """Where every daemon gets its client: an explicit URL, else B200_KUBE_URL (+ B200_KUBE_TOKEN_FILE / B200_KUBE_CA_FILE: the same
+        overrides the native binary honours, agent/native/dp/kube.hpp), else the pod's in-cluster configuration."""
+        url = url or os.environ.get("B200_KUBE_URL", "")
+        if not url:
+            return cls.in_cluster()
+        token = None
+        token_file = os.environ.get("B200_KUBE_TOKEN_FILE", "")
+        if token_file:
+            with open(token_file) as f:
+                token = f.read().strip()
+        return cls(url, token, os.environ.get("B200_KUBE_CA_FILE") or None)
+
     # ------------------------------------------------------------------ plumbing
     def _req(self, method: str, path: str, what: str, body=None, headers=None, params=None, raw_body: Optional[str] = None):
         h = dict(headers or {})
@@ -54,7 +70,7 @@ class KubeClient:
         if body is not None:
             data = json.dumps(body)
             h.setdefault("Content-Type", "application/json")
-        r = self.session.request(method, self.base + path, data=data, headers=h, params=params, timeout=self.timeout)
+        r = self.session.request(method, self.base + path, data=data, headers=h, params=params, timeout=self.timeout, verify=self.verify)
         if r.status_code >= 300:
             raise KubeError(r.status_code, r.text, what)
         return r.json() if r.content else {}

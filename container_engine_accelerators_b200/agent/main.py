@@ -107,8 +107,7 @@ def main(argv=None) -> int:
     kc = None
     if args.enable_health_monitoring or args.publish_driver_version:
         try:
-            url = args.kube_url or os.environ.get("B200_KUBE_URL", "")
-            kc = kube.KubeClient(url) if url else kube.KubeClient.in_cluster()
+            kc = kube.KubeClient.from_env(args.kube_url)
         except Exception as e:
             log.error("failed to build kube client: %s", e)
     if args.enable_health_monitoring:

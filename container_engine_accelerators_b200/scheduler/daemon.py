@@ -107,11 +107,16 @@ def main(argv=None) -> int:
     ap.add_argument("-i", "--interval", type=float, default=1.0)
     ap.add_argument("--ignored-namespace", nargs="*", default=[])
     ap.add_argument("--legacy-placement-group-key", action="store_true", help="4-level key with gke-placement-group first (older TCPXO variant)")
-    ap.add_argument("--kube-url", default="", help="API server URL (default: in-cluster)")
+    ap.add_argument("--kube-url", default="", help="API server URL (default: B200_KUBE_URL, else in-cluster)")
+    ap.add_argument("--startup-cooloff", type=float, default=90.0, help="seconds to wait after start so pods placed before a restart show up on their nodes")
+    ap.add_argument("--gang-settle", type=float, default=5.0, help="seconds to let the rest of a gang appear once a gate is seen")
+    ap.add_argument("--gate-cooloff", type=float, default=60.0, help="seconds to wait after scheduling a gate")
+    ap.add_argument("--iterations", type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname).1s %(name)s] %(message)s")
-    kube = KubeClient(args.kube_url) if args.kube_url else KubeClient.in_cluster()
-    run_scheduling_loop(kube, args.gate, args.interval, tuple(args.ignored_namespace), args.legacy_placement_group_key)
+    kube = KubeClient.from_env(args.kube_url)
+    run_scheduling_loop(kube, args.gate, args.interval, tuple(args.ignored_namespace), args.legacy_placement_group_key, startup_cooloff=args.startup_cooloff,
+                        gang_settle=args.gang_settle, gate_cooloff=args.gate_cooloff, iterations=args.iterations)
     return 0
 
 

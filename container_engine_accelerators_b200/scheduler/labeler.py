@@ -72,9 +72,11 @@ def main(argv=None) -> int:
     ap.add_argument("--source", choices=["gce-metadata", "nvml"], default="gce-metadata")
     ap.add_argument("--period", type=int, default=PERIOD_S)
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--kube-url", default="", help="API server URL (default: B200_KUBE_URL, else in-cluster)")
+    ap.add_argument("--metadata-url", default=METADATA_URL, help="GCE metadata endpoint (tests, proxies)")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname).1s %(name)s] %(message)s")
-    kube = KubeClient.in_cluster()
+    kube = KubeClient.from_env(args.kube_url)
     api = None
     if args.source == "nvml":
         api = nvmlmod.NativeNvml(); api.init()
@@ -82,7 +84,7 @@ def main(argv=None) -> int:
         log.info("Starting node update")
         try:
             if args.source == "gce-metadata":
-                update_node_labels_from_metadata(kube)
+                update_node_labels_from_metadata(kube, args.metadata_url)
             else:
                 kube.patch_node_labels(node_name(), labels_from_nvml(api))
         except Exception as e:

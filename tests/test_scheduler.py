@@ -212,3 +212,86 @@ def test_expert_dispatch_plan_is_consistent():
     assert p.max_rows >= p.rows.sum(axis=0).max() and p.rows.sum(axis=0).max() > p.rows.sum(axis=0).mean()      # skewed
     u = uniform_plan(4, 10, 64)
     assert (u.rows == 10).all() and list(u.recv_off[2]) == [0, 10, 20, 30] and u.max_rows == 40
+
+
+# ------------------------------------------------------------------------------------------------- the daemons as processes
+def _root():
+    import os
+    return os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_scheduler_daemon_process_places_a_gang(api):
+    """`python -m ...scheduler.daemon` as a process (flags, client construction, loop): a gated two-pod job ends up pinned to the
+    two hosts that share a sub-block, and the gates are gone."""
+    import os, subprocess, sys, time
+    for i, lab in enumerate([("b1", "s1", "h1"), ("b2", "s9", "h7"), ("b1", "s1", "h2")]):
+        n = node(f"node{i}", *lab)
+        api.nodes[n["metadata"]["name"]] = n
+    gate = "gke.io/topology-aware-auto-llm"
+    for i in range(2):
+        api.add_pod(pod(f"llm-{i}", job="llm", index=i, gate=gate))
+    proc = subprocess.Popen([sys.executable, "-m", "container_engine_accelerators_b200.scheduler.daemon", "--kube-url", api.url, "--startup-cooloff", "0", "--gang-settle", "0",
+                             "--gate-cooloff", "0", "--interval", "0.1", "--iterations", "3"], cwd=_root(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    out, _ = proc.communicate(timeout=60)
+    assert proc.returncode == 0, out
+    placed = {}
+    for i in range(2):
+        spec = api.pods[("default", f"llm-{i}")]["spec"]
+        assert spec["schedulingGates"] == [], out
+        placed[i] = spec["affinity"]["nodeAffinity"]["requiredDuringSchedulingIgnoredDuringExecution"]["nodeSelectorTerms"][0]["matchExpressions"][0]["values"][0]
+    assert sorted(placed.values()) == ["node0", "node2"]                      # the two hosts of block b1 / sub-block s1, not the far one
+    assert testing.rbac_violations(_scheduler_role(), api.requests) == []
+
+
+def test_labeler_process_with_a_fake_metadata_server(api):
+    import subprocess, sys, threading
+    from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+    class Meta(BaseHTTPRequestHandler):
+        def log_message(self, *a):
+            pass
+
+        def do_GET(self):
+            ok = self.headers.get("Metadata-Flavor") == "Google"
+            body = {"/name": "gke-node-9", "/attributes/physical_host": "/cluster-x/rack-7/host-3"}.get(self.path)
+            self.send_response(200 if ok and body else 404); self.end_headers()
+            if ok and body:
+                self.wfile.write(body.encode())
+    srv = ThreadingHTTPServer(("127.0.0.1", 0), Meta)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        api.add_node("gke-node-9", labels={"keep": "1"})
+        r = subprocess.run([sys.executable, "-m", "container_engine_accelerators_b200.scheduler.labeler", "--once", "--kube-url", api.url,
+                            "--metadata-url", f"http://127.0.0.1:{srv.server_address[1]}"], cwd=_root(), capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        assert api.nodes["gke-node-9"]["metadata"]["labels"] == {"keep": "1", "topology.gke.io/cluster": "cluster-x", "topology.gke.io/rack": "rack-7", "topology.gke.io/host": "host-3"}
+        r = subprocess.run([sys.executable, "-m", "container_engine_accelerators_b200.scheduler.labeler", "--once", "--kube-url", api.url,
+                            "--metadata-url", f"http://127.0.0.1:{srv.server_address[1]}/missing"], cwd=_root(), capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and "Node name not found" in r.stderr          # logged, the daemon keeps going
+    finally:
+        srv.shutdown(); srv.server_close()
+
+
+def test_python_kube_client_over_tls_with_token_and_ca(tmp_path, monkeypatch):
+    """KubeClient.from_env with B200_KUBE_URL / TOKEN_FILE / CA_FILE (the overrides the native client has): verified TLS, bearer token sent;
+    a CA that does not cover the server is refused."""
+    import requests
+    certs = tmp_path / "pki"; certs.mkdir()
+    cert, key = testing.make_self_signed_cert(str(certs))
+    other = tmp_path / "other"; other.mkdir()
+    other_cert, _ = testing.make_self_signed_cert(str(other))
+    (tmp_path / "token").write_text("tok-123\n")
+    a = testing.FakeKubeApi().start(tls_cert=cert, tls_key=key)
+    try:
+        a.add_node("n1")
+        monkeypatch.setenv("B200_KUBE_URL", a.url); monkeypatch.setenv("B200_KUBE_TOKEN_FILE", str(tmp_path / "token")); monkeypatch.setenv("B200_KUBE_CA_FILE", cert)
+        kc = kube.KubeClient.from_env()
+        assert kc.get_node("n1")["metadata"]["name"] == "n1" and a.bearer_tokens[-1] == "Bearer tok-123"
+        monkeypatch.setenv("B200_KUBE_CA_FILE", other_cert)
+        with pytest.raises(requests.exceptions.SSLError):
+            kube.KubeClient.from_env().get_node("n1")
+        monkeypatch.delenv("B200_KUBE_URL"); monkeypatch.delenv("KUBERNETES_SERVICE_HOST", raising=False)
+        with pytest.raises(kube.KubeError, match="not running in a cluster"):
+            kube.KubeClient.from_env()
+    finally:
+        a.stop()
