@@ -66,3 +66,24 @@ def test_every_first_party_image_in_the_manifests_has_a_build_rule():
     for image in wanted:
         name = image.split("/")[-1].split(":")[0]
         assert f" {name} " in pushed.replace(";", " ; ") or f" {name};" in pushed, (name, pushed)
+
+
+def test_clock_sampler_without_nvml_and_with_the_nvidia_smi_fallback(tmp_path, monkeypatch):
+    """bench.py's clocks block: no NVML and no nvidia-smi -> an empty summary, never an exception; with only nvidia-smi available the
+    recipe's CSV is parsed (median of the upper half of the SM clock samples, throttle reasons collected)."""
+    import sys
+    import time
+    from container_engine_accelerators_b200.utils.clocks import ClockSampler
+    monkeypatch.setitem(sys.modules, "pynvml", None)                     # import pynvml -> ImportError
+    monkeypatch.setenv("PATH", str(tmp_path))
+    with ClockSampler(0) as c:
+        pass
+    assert c.summary() == {"sm_mhz": None, "sm_max_mhz": None, "power_w_max": None, "reasons": [], "samples": 0, "source": "none"}
+    smi = tmp_path / "nvidia-smi"
+    smi.write_text("#!/bin/bash\nfor mhz in 1200 1965 1965 1950; do echo \"0, $mhz, 1965, 700.5, 0x4, Not Active, Not Active, Not Active, Active\"; done\nsleep 5\n")
+    smi.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{tmp_path}:/usr/bin:/bin")
+    with ClockSampler(0) as c:
+        time.sleep(0.3)
+    s = c.summary()
+    assert s["source"] == "nvidia-smi" and s["samples"] == 4 and s["sm_mhz"] == 1965.0 and s["sm_max_mhz"] == 1965.0 and s["power_w_max"] == 700.5 and s["reasons"] == ["sw_power_cap"]

@@ -192,3 +192,28 @@ def test_native_annotation_parser_agrees_with_pyyaml_on_generated_annotations(na
     for bad in ("just a string", "- path: [unclosed", "[{path: /dev/x}", "key: value"):
         r = subprocess.run([exe, "--parse-annotation"], input=bad.encode(), capture_output=True, timeout=20)
         assert r.returncode == 1 and r.stdout.startswith(b"ERR"), bad
+
+
+def test_python_injector_as_a_process(tmp_path):
+    """`python -m container_engine_accelerators_b200.agent.nri --socket ...`: the entry point the Python image runs."""
+    import subprocess, sys
+    sock = str(tmp_path / "nri.sock")
+    rt = testing.FakeNriRuntime(sock)
+    fifo = tmp_path / "f"; os.mkfifo(fifo)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.Popen([sys.executable, "-m", "container_engine_accelerators_b200.agent.nri", "--socket", sock, "--idx", "10"], cwd=root, stderr=subprocess.PIPE, text=True)
+    try:
+        reg = rt.wait_registered(timeout=30)
+        assert (reg.plugin_name, reg.plugin_idx) == ("device_injector_nri", "10")
+        rt.configure(); rt.synchronize()
+        devs = rt.create_container("pod", "c", {KEY + "c": f'[{{"path": "{fifo}", "uid": 3}}]'}).adjust.linux.devices          # JSON-style annotation
+        assert len(devs) == 1 and devs[0].type == "p" and devs[0].uid.value == 3
+    finally:
+        rt.close()
+        try:
+            proc.wait(10)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+    assert proc.returncode == 0, proc.stderr.read()
+    missing = subprocess.run([sys.executable, "-m", "container_engine_accelerators_b200.agent.nri", "--socket", str(tmp_path / "absent.sock")], cwd=root, capture_output=True, text=True, timeout=60)
+    assert missing.returncode == 1 and "plugin exited with error" in missing.stderr
