@@ -235,6 +235,45 @@ def xid_marks_unhealthy(cmd):
         os.unlink(events.name)
 
 
+def mps_sharing(cmd):
+    """MPS: the plugin only starts when nvidia-cuda-mps-control answers; one replica per container on multi-GPU nodes, several on a
+    one-GPU node; allocations carry the thread-percentage / pinned-memory limits and the read-write /tmp/nvidia-mps mount."""
+    cfg = {"GPUSharingConfig": {"GPUSharingStrategy": "mps", "MaxSharedClientsPerGPU": 4}}
+    with tempfile.TemporaryDirectory() as d:
+        ctl = os.path.join(d, "nvidia-cuda-mps-control")
+        with open(ctl, "w") as f:
+            f.write("#!/bin/sh\ncat > /dev/null\necho 100.0\n")
+        os.chmod(ctl, 0o755)
+        n = Node(cmd, config=cfg, extra=f"--mps-control-bin {ctl}")
+        try:
+            c = n.connect()
+            _, devs = first_list(c)
+            assert len(devs) == 8 and "nvidia1/vgpu3" in devs
+            assert dict(c.allocate(["nvidia1/vgpu2"]).container_responses[0].envs)["CUDA_MPS_ACTIVE_THREAD_PERCENTAGE"] == "25"
+            expect_error(lambda: c.allocate(["nvidia0/vgpu0", "nvidia0/vgpu1"]), "at most 1 nvidia.com/gpu can be requested on multi-GPU nodes")
+        finally:
+            n.close()
+        n = Node(cmd, gpus=1, config=cfg, extra=f"--mps-control-bin {ctl}")          # a one-GPU node may hand several replicas to one container
+        try:
+            c = n.connect()
+            cr = c.allocate(["nvidia0/vgpu0", "nvidia0/vgpu1"]).container_responses[0]
+            env = dict(cr.envs)
+            total_mib = (183359 << 20) // (1 << 20)                                  # what the scripted NVML reports per GPU
+            assert env["CUDA_MPS_ACTIVE_THREAD_PERCENTAGE"] == "50" and env["CUDA_MPS_PINNED_DEVICE_MEM_LIMIT"] == f"0={2 * total_mib // 4}M", env
+            assert ("/tmp/nvidia-mps", False) in [(m.container_path, m.read_only) for m in cr.mounts] and len(cr.mounts) == 3
+        finally:
+            n.close()
+        with open(ctl, "w") as f:
+            f.write("#!/bin/sh\nexit 1\n")
+        n = Node(cmd, config=cfg, extra=f"--mps-control-bin {ctl}")
+        try:
+            time.sleep(1.5)
+            assert not os.path.exists(os.path.join(n.plugin_dir, n.endpoint)) and n.process.poll() is None, "must not serve (and must keep retrying) while MPS is down"
+            assert "MPS" in n.logs()
+        finally:
+            n.close()
+
+
 def transport_profile(cmd):
     """GPUConfig.Transport = b200coll: Allocate exports the collective library's environment."""
     n = Node(cmd, config={"Transport": {"Name": "b200coll", "Env": {"B200COLL_ALGO": "nvls"}}})
@@ -246,7 +285,7 @@ def transport_profile(cmd):
 
 
 SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
-             xid_marks_unhealthy, transport_profile]
+             xid_marks_unhealthy, mps_sharing, transport_profile]
 
 
 def main(argv=None) -> int:

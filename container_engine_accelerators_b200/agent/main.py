@@ -43,6 +43,7 @@ def build_parser() -> argparse.ArgumentParser:
     # seams the conformance harness uses to run the agent as a real process against fake /dev, /proc, /sys trees (same names as the native binary)
     p.add_argument("--pci-root", default=nvml.PCI_DEVICES_ROOT, help=argparse.SUPPRESS)
     p.add_argument("--plugin-endpoint", default="", help=argparse.SUPPRESS)
+    p.add_argument("--mps-control-bin", default=None, help=argparse.SUPPRESS)
     p.add_argument("--gpu-check-interval", type=float, default=None, help=argparse.SUPPRESS)
     p.add_argument("--socket-check-interval", type=float, default=None, help=argparse.SUPPRESS)
     p.add_argument("--kube-url", default="", help="API server URL (default: in-cluster); B200_KUBE_URL is honoured too")
@@ -77,7 +78,7 @@ def main(argv=None) -> int:
         log.error("failed to add HealthCriticalXid: %s", e)
     log.info("Using gpu config: %s", cfg)
     api = nvml.NativeNvml()
-    seams = {k: v for k, v in (("gpu_check_interval", args.gpu_check_interval), ("socket_check_interval", args.socket_check_interval)) if v is not None}
+    seams = {k: v for k, v in (("gpu_check_interval", args.gpu_check_interval), ("socket_check_interval", args.socket_check_interval), ("mps_control_bin", args.mps_control_bin)) if v is not None}
     ngm = GPUManager(args.dev_directory, args.proc_directory, mounts, cfg, nvml=api, pci_root=args.pci_root, preferred_allocation_policy=args.preferred_allocation_policy, **seams)
     while True:
         try:

@@ -230,7 +230,7 @@ def test_preferred_allocation_policy_function():
     shared = ["nvidia0/vgpu2", "nvidia1/vgpu0", "nvidia1/vgpu1", "nvidia1/vgpu2"]
     assert preferred.preferred_allocation(shared, [], 1, lambda d: 0, "spread") == ["nvidia1/vgpu0"]
     assert preferred.preferred_allocation(shared, [], 1, lambda d: 0, "packed") == ["nvidia0/vgpu2"]
-    # MPS pod asking for two replicas: packed keeps them on one physical GPU (the only legal MPS shape), spread would not
+    # two replicas: packed keeps them on one physical GPU, spread takes two different ones
     assert [preferred.physical_of(d) for d in preferred.preferred_allocation(shared[1:], [], 2, lambda d: 0, "packed")] == ["nvidia1", "nvidia1"]
     assert len({preferred.physical_of(d) for d in preferred.preferred_allocation(shared, [], 2, lambda d: 0, "spread")}) == 2
     assert preferred.preferred_allocation(["nvidia0"], [], 3, lambda d: 0) == ["nvidia0"]                               # fewer free than wanted
