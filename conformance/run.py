@@ -175,6 +175,21 @@ def mig_seven_slices(cmd):
         n.close()
 
 
+def mig_with_time_sharing(cmd):
+    """The fourth mode of the reference's matrix: MIG slices fanned out into time-shared replicas (nvidia0/gi<N>/vgpu<k>)."""
+    n = Node(cmd, gpus=1, mig_parts=7, config={"GPUPartitionSize": "1g.23gb", "GPUSharingConfig": {"GPUSharingStrategy": "time-sharing", "MaxSharedClientsPerGPU": 2}})
+    try:
+        c = n.connect()
+        _, devs = first_list(c)
+        assert set(devs) == {f"nvidia0/gi{i}/vgpu{k}" for i in range(1, 8) for k in range(2)}
+        cr = c.allocate(["nvidia0/gi5/vgpu1"]).container_responses[0]
+        assert len(cr.devices) == 7 and cr.devices[0].host_path.endswith("/nvidia0")
+        expect_error(lambda: c.allocate(["nvidia0/gi5/vgpu0", "nvidia0/gi5/vgpu1"]), "time-sharing")
+        expect_error(lambda: c.allocate(["nvidia0/gi9/vgpu0"]), "non-existing GPU partition")
+    finally:
+        n.close()
+
+
 def bad_config_falls_back(cmd):
     """An unparsable gpu_config.json is logged and ignored: whole GPUs are served."""
     n = Node(cmd, config="{broken json")
@@ -284,7 +299,7 @@ def transport_profile(cmd):
         n.close()
 
 
-SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
+SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
              xid_marks_unhealthy, mps_sharing, transport_profile]
 
 
