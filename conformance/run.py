@@ -250,6 +250,34 @@ def xid_marks_unhealthy(cmd):
         os.unlink(events.name)
 
 
+def xid_on_a_mig_slice(cmd):
+    """An Xid that NVML attributes to GPU instance 3 takes down that slice only; one without a device id takes down everything."""
+    events = tempfile.NamedTemporaryFile("w", suffix=".events", delete=False)
+    events.close()
+    n = Node(cmd, gpus=1, mig_parts=7, config={"GPUPartitionSize": "1g.23gb"}, extra="-enable-health-monitoring", env={"FAKE_NVML_EVENTS": events.name, "FAKE_NVML_MIG": "1"})
+    try:
+        c = n.connect()
+        stream, devs = first_list(c)
+        assert len(devs) == 7
+        time.sleep(1.0)
+        with open(events.name, "a") as f:
+            f.write("0 48 3 0\n")
+        health = {d.ID: d.health for d in next(stream).devices}
+        assert health["nvidia0/gi3"] == "Unhealthy" and sum(1 for h in health.values() if h == "Unhealthy") == 1, health
+        with open(events.name, "a") as f:
+            f.write("-1 48\n")                                       # no device attached to the event: every device goes Unhealthy
+        deadline = time.time() + 10
+        while time.time() < deadline:
+            health = {d.ID: d.health for d in next(stream).devices}
+            if all(h == "Unhealthy" for h in health.values()):
+                break
+        assert all(h == "Unhealthy" for h in health.values()), health
+        stream.cancel()
+    finally:
+        n.close()
+        os.unlink(events.name)
+
+
 def mps_sharing(cmd):
     """MPS: the plugin only starts when nvidia-cuda-mps-control answers; one replica per container on multi-GPU nodes, several on a
     one-GPU node; allocations carry the thread-percentage / pinned-memory limits and the read-write /tmp/nvidia-mps mount."""
@@ -300,7 +328,7 @@ def transport_profile(cmd):
 
 
 SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
-             xid_marks_unhealthy, mps_sharing, transport_profile]
+             xid_marks_unhealthy, xid_on_a_mig_slice, mps_sharing, transport_profile]
 
 
 def main(argv=None) -> int:
