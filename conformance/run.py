@@ -278,6 +278,54 @@ def xid_on_a_mig_slice(cmd):
         os.unlink(events.name)
 
 
+def metrics_endpoint(cmd):
+    """Prometheus text on the metrics port: per-container duty cycle / memory through the kubelet's PodResources API (virtual ids are not
+    attributed), per-node gauges for every GPU, and the counters of a libb200coll page found in the stats directory."""
+    import socket
+    import struct
+    import urllib.request
+    from concurrent import futures
+    from container_engine_accelerators_b200.agent import protos
+    with tempfile.TemporaryDirectory() as d:
+        pr = protos.podresources
+        resp = pr.ListPodResourcesResponse()
+        for ns, pod, ctr, ids in (("default", "trainer-0", "main", ["nvidia0"]), ("default", "shared-1", "main", ["nvidia1/vgpu0"])):
+            resp.pod_resources.add(name=pod, namespace=ns).containers.add(name=ctr).devices.add(resource_name="nvidia.com/gpu", device_ids=ids)
+        server = grpc.server(futures.ThreadPoolExecutor(max_workers=2))
+        server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(protos.POD_RESOURCES_SERVICE, {"List": grpc.unary_unary_rpc_method_handler(
+            lambda req, ctx: resp, pr.ListPodResourcesRequest.FromString, pr.ListPodResourcesResponse.SerializeToString)}),))
+        sock = os.path.join(d, "pod-resources.sock")
+        server.add_insecure_port(f"unix:{sock}")
+        server.start()
+        page = bytearray(4096); page[0:8] = b"B200COLL"
+        struct.pack_into("<6I", page, 8, 2, 4242, 3, 8, 3, 1); struct.pack_into("<Q", page, 32, int(time.time()))
+        struct.pack_into("<21Q", page, 64, 10, 0, 0, 2, 7, 1, 1 << 30, 0, 0, 4096, 512, 64, 0, 5, 0, 2, 13, 0, 0, 21, 0)
+        with open(os.path.join(d, "b200coll.4242.3"), "wb") as f:
+            f.write(page)
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        n = Node(cmd, extra=f"-enable-container-gpu-metrics -gpu-metrics-port {port} -gpu-metrics-collection-interval 200 --pod-resources-socket {sock} --coll-stats-dir {d}",
+                 env={"FAKE_NVML_UTIL": "40,60,80"})
+        try:
+            n.connect()
+            body, deadline = "", time.time() + 20
+            while time.time() < deadline and 'duty_cycle{' not in body:
+                try:
+                    body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=2).read().decode()
+                except OSError:
+                    pass
+                time.sleep(0.2)
+            lines = [l for l in body.splitlines() if not l.startswith("#")]
+            find = lambda name, *labels: [l for l in lines if l.startswith(name + "{") and all(x in l for x in labels)]
+            assert find("duty_cycle", 'pod="trainer-0"', 'container="main"', 'make="nvidia"', 'accelerator_id="GPU-fake-0"') and find("duty_cycle", 'pod="trainer-0"')[0].rsplit(" ", 1)[1] in ("60", "60.0"), body[-1500:]
+            assert find("request", 'pod="trainer-0"', 'resource_name="nvidia.com/gpu"')[0].rsplit(" ", 1)[1] in ("1", "1.0")
+            assert find("request", 'pod="shared-1"')[0].rsplit(" ", 1)[1] in ("0", "0.0") and not find("duty_cycle", 'pod="shared-1"')
+            assert len(find("memory_total_gpu_node")) == 2 and len(find("duty_cycle_gpu_node")) == 2
+            assert find("b200coll_calls", 'pid="4242"', 'rank="3"', 'op="all_reduce"')[0].rsplit(" ", 1)[1] in ("10", "10.0")
+        finally:
+            n.close()
+            server.stop(0)
+
+
 def mps_sharing(cmd):
     """MPS: the plugin only starts when nvidia-cuda-mps-control answers; one replica per container on multi-GPU nodes, several on a
     one-GPU node; allocations carry the thread-percentage / pinned-memory limits and the read-write /tmp/nvidia-mps mount."""
@@ -328,7 +376,7 @@ def transport_profile(cmd):
 
 
 SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
-             xid_marks_unhealthy, xid_on_a_mig_slice, mps_sharing, transport_profile]
+             xid_marks_unhealthy, xid_on_a_mig_slice, metrics_endpoint, mps_sharing, transport_profile]
 
 
 def main(argv=None) -> int:

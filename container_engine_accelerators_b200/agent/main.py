@@ -44,6 +44,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--pci-root", default=nvml.PCI_DEVICES_ROOT, help=argparse.SUPPRESS)
     p.add_argument("--plugin-endpoint", default="", help=argparse.SUPPRESS)
     p.add_argument("--mps-control-bin", default=None, help=argparse.SUPPRESS)
+    p.add_argument("--pod-resources-socket", default=metrics.POD_RESOURCES_SOCKET, help=argparse.SUPPRESS)
+    p.add_argument("--coll-stats-dir", default="/dev/shm", help=argparse.SUPPRESS)
     p.add_argument("--gpu-check-interval", type=float, default=None, help=argparse.SUPPRESS)
     p.add_argument("--socket-check-interval", type=float, default=None, help=argparse.SUPPRESS)
     p.add_argument("--kube-url", default="", help="API server URL (default: in-cluster); B200_KUBE_URL is honoured too")
@@ -102,7 +104,8 @@ def main(argv=None) -> int:
         else:
             log.info("Starting metrics server on port: %d, collection interval: %d", args.gpu_metrics_port, args.gpu_metrics_collection_interval)
             try:
-                metrics.MetricServer(api, args.gpu_metrics_collection_interval, args.gpu_metrics_port).start()
+                metrics.MetricServer(api, args.gpu_metrics_collection_interval, args.gpu_metrics_port, pod_resources_socket=args.pod_resources_socket,
+                                     coll_stats_glob=os.path.join(args.coll_stats_dir, "b200coll.*")).start()
             except Exception as e:
                 log.error("failed to start metric server: %s", e)
     kc = None
