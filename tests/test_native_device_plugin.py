@@ -357,6 +357,15 @@ def test_kube_client_over_tls_verifies_the_server(native, tmp_path):
         _wait(lambda: api.nodes["node-a"]["metadata"]["annotations"].get("cloud.google.com/cuda.driver-version.major") == "580", what="annotations over TLS")
         assert api.bearer_tokens[-1] == "Bearer s3cr3t"
         n.close()
+        # the same server reached by name: SNI + host-name verification against the certificate's DNS subject-alt-name
+        api.nodes["node-a"]["metadata"]["annotations"].clear()
+        by_name = Native(tmp_path / "c", os.path.dirname(n.proc_handle.args[0]), extra_args=["--publish-driver-version"],
+                         env={**env, "B200_KUBE_URL": api.url.replace("127.0.0.1", "localhost"), "B200_KUBE_CA_FILE": cert})
+        try:
+            by_name.connect()
+            _wait(lambda: api.nodes["node-a"]["metadata"]["annotations"].get("cloud.google.com/cuda.driver-version.major") == "580", what="annotations over TLS by host name")
+        finally:
+            by_name.close()
         api.nodes["node-a"]["metadata"]["annotations"].clear()
         n2 = Native(tmp_path / "b", os.path.dirname(n.proc_handle.args[0]), extra_args=["--publish-driver-version"], env={**env, "B200_KUBE_CA_FILE": other_cert})
         try:
