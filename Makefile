@@ -13,6 +13,10 @@ conformance: build           ## the thirteen kubelet-side scenarios against both
 test-race: build             ## the native daemons under ThreadSanitizer, then AddressSanitizer+UBSan (role of `go test -race`, reference Makefile:21)
 	B200_NATIVE_SAN=thread $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -x -q
 	B200_NATIVE_SAN=address $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -x -q
+coverage-native: build       ## line coverage of the C++ daemons under the conformance suites (gcov)
+	rm -rf build/agent-cov
+	B200_NATIVE_SAN=cov $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -q
+	cd agent/native && for g in ../../build/agent-cov/*.gcda; do gcov -o ../../build/agent-cov $$g 2>/dev/null | grep -A1 "File '\(dp/\|[a-z_0-9]*\.cc\)" | grep -v "^--"; done; rm -f *.gcov
 test-gpu: build
 	$(PY) -m pytest tests -x -q -m gpu
 presubmit: vet                ## header + style + manifest freshness
@@ -56,4 +60,4 @@ sass:                        ## SASS listing of the collective kernels -> profil
 	cuobjdump -sass coll/lib/libb200coll.so > profiles/libb200coll.sass
 clean:
 	$(MAKE) -C coll clean; $(MAKE) -C tools clean; $(MAKE) -C agent/native clean
-.PHONY: all build manifests test conformance test-race test-gpu vet presubmit bench containers push containers-multi-arch device-plugin partition-gpu nri-device-injector nvidia-persistenced-installer transport-installer sass clean
+.PHONY: all build manifests test conformance test-race coverage-native test-gpu vet presubmit bench containers push containers-multi-arch device-plugin partition-gpu nri-device-injector nvidia-persistenced-installer transport-installer sass clean
