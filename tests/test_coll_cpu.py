@@ -126,3 +126,32 @@ def test_nccl_shim_exports_the_api_nccl_tests_links_against(coll_lib):
         comms = (C.c_void_p * 1)()
         rc = L.ncclCommInitAll(comms, 1, (C.c_int * 1)(0))
         assert rc != 0 and L.ncclGetErrorString(rc)               # no driver: an error code, not a crash
+
+
+def test_harness_bandwidth_accounting_follows_nccl_tests():
+    """bench.py's numbers are only comparable with nccl-tests if the bus-bandwidth factors are the same: 2(n-1)/n for all_reduce,
+    (n-1)/n for all_gather / reduce_scatter / alltoall, 1 for the rooted ops, and the average is over every (size, placement) measured."""
+    from container_engine_accelerators_b200.parallel import harness as h
+    assert h.bus_factor("all_reduce", 8) == pytest.approx(1.75) and h.bus_factor("all_gather", 8) == pytest.approx(0.875)
+    assert h.bus_factor("reduce_scatter", 2) == 0.5 and h.bus_factor("alltoall", 4) == 0.75
+    assert h.bus_factor("broadcast", 8) == 1.0 and h.bus_factor("reduce", 8) == 1.0 and h.bus_factor("all_reduce", 1) == 1.0
+    rows = [h.Row(nbytes=1 << 20, count=1 << 19, algo="nvls", oop_us=10.0, ip_us=20.0), h.Row(nbytes=1 << 30, count=1 << 29, algo="nvls", oop_us=2000.0, ip_us=-1.0, e2e_us=40000.0)]
+    b = rows[0].bw("all_reduce", 8)
+    assert b["oop_algbw"] == pytest.approx((1 << 20) / 10.0 / 1e3) and b["oop_busbw"] == pytest.approx(b["oop_algbw"] * 1.75) and b["ip_busbw"] == pytest.approx(b["oop_busbw"] / 2)
+    s = h.summarize(rows, "all_reduce", 8)
+    per = [rows[0].bw("all_reduce", 8)["oop_busbw"], rows[0].bw("all_reduce", 8)["ip_busbw"], rows[1].bw("all_reduce", 8)["oop_busbw"]]
+    assert s["measurements"] == 3 and s["avg_busbw"] == pytest.approx(sum(per) / 3) and s["peak_busbw"] == pytest.approx(max(per))
+    assert s["sweep_ms"] == pytest.approx((10 + 20 + 2000) / 1e3) and s["avg_e2e_busbw"] == pytest.approx((1 << 30) / 40000.0 / 1e3 * 1.75)
+    table = h.format_table(rows, "all_reduce", 8, "title")
+    assert table.splitlines()[0] == "# title" and table.splitlines()[-1].startswith("# Avg bus bandwidth : ") and "nvls" in table
+    js = h.rows_json(rows, "all_reduce", 8)
+    assert js[0]["bytes"] == 1 << 20 and "e2e_us" not in js[0] and js[1]["e2e_us"] == 40000.0 and js[1]["ip_us"] == -1.0
+    assert h.OPS.index("broadcast") == coll_op_ids()["broadcast"] and h.OPS.index("alltoall") == coll_op_ids()["alltoall"]
+
+
+def coll_op_ids():
+    """b200collOp_t values from the public header (the harness indexes the tuner with OPS.index(op))."""
+    import re
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "coll", "include", "b200coll.h")).read()
+    names = {"AllReduce": "all_reduce", "AllGather": "all_gather", "ReduceScatter": "reduce_scatter", "AllToAll": "alltoall", "Broadcast": "broadcast", "Reduce": "reduce"}
+    return {names[m.group(1)]: int(m.group(2)) for m in re.finditer(r"b200collOp(\w+) = (\d+)", header) if m.group(1) in names}
