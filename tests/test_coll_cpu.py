@@ -155,3 +155,29 @@ def coll_op_ids():
     header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "coll", "include", "b200coll.h")).read()
     names = {"AllReduce": "all_reduce", "AllGather": "all_gather", "ReduceScatter": "reduce_scatter", "AllToAll": "alltoall", "Broadcast": "broadcast", "Reduce": "reduce"}
     return {names[m.group(1)]: int(m.group(2)) for m in re.finditer(r"b200collOp(\w+) = (\d+)", header) if m.group(1) in names}
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The Python binding restates the public structs; compile a probe against coll/include/b200coll.h (plain C, no CUDA) and compare
+    sizes, member offsets and enumerators, so a header change cannot silently shear the binding."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "b200coll.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(b200collStats), sizeof(b200collCommInfo), sizeof(b200collConfig), sizeof(b200collFault), sizeof(b200collEpilogue), sizeof(b200collUniqueId));
+  printf("%zu %zu %zu %zu\n", offsetof(b200collStats, bytes), offsetof(b200collStats, algo_calls), offsetof(b200collStats, kernel_launches), offsetof(b200collStats, staged_calls));
+  printf("%d %d %d %d %d %d %d\n", b200collNumOps, b200collNumAlgos, b200collFloat32, b200collFloat16, b200collBfloat16, b200collFloat8e4m3, b200collAvg);
+  printf("%d %d %d %d %d %d\n", b200collOpAllReduce, b200collOpAllGather, b200collOpReduceScatter, b200collOpAllToAll, b200collOpBroadcast, b200collOpReduce);
+  return 0;
+}''')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "coll", "include"), str(src), "-o", str(exe)], check=True)      # the header is valid C99
+    lines = [list(map(int, l.split())) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()]
+    assert lines[0] == [C.sizeof(coll.Stats), C.sizeof(coll.CommInfo), C.sizeof(coll.Config), C.sizeof(coll.Fault), C.sizeof(coll.Epilogue), C.sizeof(coll.UniqueId)]
+    assert lines[1] == [coll.Stats.bytes.offset, coll.Stats.algo_calls.offset, coll.Stats.kernel_launches.offset, coll.Stats.staged_calls.offset]
+    assert lines[2] == [len(coll.Stats().calls), len(coll.ALGO_NAMES), coll.F32, coll.F16, coll.BF16, coll.FP8_E4M3, coll.AVG]
+    assert lines[3][:4] == [coll.OP_ALLREDUCE, coll.OP_ALLGATHER, coll.OP_REDUCESCATTER, coll.OP_ALLTOALL] and lines[3][4:] == [4, 5]
