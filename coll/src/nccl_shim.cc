@@ -21,6 +21,8 @@ typedef struct { char internal[128]; } ncclUniqueId;
 typedef enum { ncclSuccess = 0, ncclUnhandledCudaError = 1, ncclSystemError = 2, ncclInternalError = 3, ncclInvalidArgument = 4, ncclInvalidUsage = 5, ncclRemoteError = 6, ncclInProgress = 7 } ncclResult_t;
 typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8, ncclBfloat16 = 9 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4 } ncclRedOp_t;
+typedef enum { ncclScalarDevice = 0, ncclScalarHostImmediate = 1 } ncclScalarResidence_t;
+typedef struct ncclConfig_opaque ncclConfig_t;      /* blocking, cgaClusterSize, ...: nothing in it has an analogue here */
 
 }  // extern "C"
 
@@ -136,22 +138,22 @@ ncclResult_t ncclCommDestroy(ncclComm_t comm) {
   return map_rc(r);
 }
 // Config structs, registration handles and splits of newer NCCL APIs: accepted where a no-op is faithful, refused where it is not.
-ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank, void* /*ncclConfig_t*: blocking, cgaClusterSize, ... have no analogue */) {
+ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank, ncclConfig_t* /*config*/) {
   return ncclCommInitRank(comm, nranks, id, rank);
 }
-ncclResult_t ncclCommSplit(ncclComm_t, int, int, ncclComm_t*, void*) { return ncclInvalidUsage; }      // one communicator per NVSwitch domain
+ncclResult_t ncclCommSplit(ncclComm_t /*comm*/, int /*color*/, int /*key*/, ncclComm_t* /*newcomm*/, ncclConfig_t* /*config*/) { return ncclInvalidUsage; }      // one communicator per NVSwitch domain
 ncclResult_t ncclCommRegister(const ncclComm_t comm, void* buff, size_t, void** handle) {              // arena memory is registered by construction
   if (!comm || !handle) return ncclInvalidArgument;
   *handle = buff;
   return ncclSuccess;
 }
 ncclResult_t ncclCommDeregister(const ncclComm_t, void*) { return ncclSuccess; }
-ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t* op, void* scalar, ncclDataType_t dt, int residence /* 0 device, 1 host immediate */, ncclComm_t comm) {
+ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t* op, void* scalar, ncclDataType_t dt, ncclScalarResidence_t residence, ncclComm_t comm) {
   if (!op || !scalar || !comm) return ncclInvalidArgument;
   unsigned char raw[8] = {};
   const size_t sz = dt == ncclFloat64 ? 8 : dt == ncclFloat32 ? 4 : (dt == ncclFloat16 || dt == ncclBfloat16) ? 2 : 0;
   if (!sz) return ncclInvalidArgument;
-  if (residence == 1) memcpy(raw, scalar, sz);
+  if (residence == ncclScalarHostImmediate) memcpy(raw, scalar, sz);
   else if (cudaMemcpy(raw, scalar, sz, cudaMemcpyDeviceToHost) != cudaSuccess) return ncclUnhandledCudaError;
   float v;
   if (dt == ncclFloat64) { double d; memcpy(&d, raw, 8); v = (float)d; }

@@ -181,3 +181,48 @@ int main(void) {
     assert lines[1] == [coll.Stats.bytes.offset, coll.Stats.algo_calls.offset, coll.Stats.kernel_launches.offset, coll.Stats.staged_calls.offset]
     assert lines[2] == [len(coll.Stats().calls), len(coll.ALGO_NAMES), coll.F32, coll.F16, coll.BF16, coll.FP8_E4M3, coll.AVG]
     assert lines[3][:4] == [coll.OP_ALLREDUCE, coll.OP_ALLGATHER, coll.OP_REDUCESCATTER, coll.OP_ALLTOALL] and lines[3][4:] == [4, 5]
+
+
+def test_nccl_shim_declarations_match_nccl_h(tmp_path, coll_lib):
+    """The shim re-declares NCCL's enums and prototypes (it cannot include nccl.h and define the same symbols). When a real nccl.h is
+    installed, check the enumerator values and that every prototype the shim exports is call-compatible with NCCL's declaration."""
+    import re
+    import subprocess
+    if not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("no system nccl.h to compare against")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = open(os.path.join(root, "coll", "src", "nccl_shim.cc")).read()
+    enums = dict(re.findall(r"\b(nccl[A-Z]\w+) = (\d+)", shim))
+    assert len(enums) >= 20
+    checks = "\n".join(f'_Static_assert({name} == {val}, "{name}");' for name, val in enums.items())
+    # call every exported entry point through NCCL's own prototypes: a signature mismatch is a compile error
+    src = tmp_path / "probe.c"
+    src.write_text(f'''
+#include <cuda_runtime.h>
+#include <nccl.h>
+{checks}
+void use(void) {{
+  ncclComm_t c = 0; ncclUniqueId id; int v; void* p = 0; ncclRedOp_t op; cudaStream_t s = 0; ncclResult_t r;
+  ncclGetVersion(&v); ncclGetUniqueId(&id); ncclCommInitRank(&c, 2, id, 0); ncclCommInitAll(&c, 1, 0); ncclCommDestroy(c); ncclCommFinalize(c); ncclCommAbort(c);
+  ncclCommCount(c, &v); ncclCommUserRank(c, &v); ncclCommCuDevice(c, &v); ncclCommGetAsyncError(c, &r); ncclMemAlloc(&p, 8); ncclMemFree(p);
+  ncclAllReduce(p, p, 1, ncclFloat, ncclSum, c, s); ncclAllGather(p, p, 1, ncclFloat, c, s); ncclReduceScatter(p, p, 1, ncclFloat, ncclSum, c, s);
+  ncclBroadcast(p, p, 1, ncclFloat, 0, c, s); ncclBcast(p, 1, ncclFloat, 0, c, s); ncclReduce(p, p, 1, ncclFloat, ncclSum, 0, c, s);
+  ncclSend(p, 1, ncclFloat, 0, c, s); ncclRecv(p, 1, ncclFloat, 0, c, s); ncclGroupStart(); ncclGroupEnd();
+  ncclRedOpCreatePreMulSum(&op, p, ncclFloat, ncclScalarHostImmediate, c); ncclRedOpDestroy(op, c); ncclCommRegister(c, p, 8, &p); ncclCommDeregister(c, p);
+  (void)ncclGetErrorString(r); (void)ncclGetLastError(c);
+}}
+int main(void) {{ return 0; }}
+''')
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I/usr/local/cuda/include", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    # the shim's own signatures, re-declared next to NCCL's: C linkage forbids two different parameter lists for one name
+    sigs = re.findall(r"^((?:ncclResult_t|const char\*) nccl\w+\([^)]*\))\s*\{", shim, re.M)
+    assert len(sigs) >= 28
+    decl = tmp_path / "decl.cc"
+    decl.write_text("#include <cuda_runtime.h>\n#include <nccl.h>\nextern \"C\" {\n" + "\n".join(re.sub(r"/\*.*?\*/", "", x) + ";" for x in sigs) + "\n}\nint main() { return 0; }\n")
+    r = subprocess.run(["g++", "-std=c++17", "-I/usr/local/cuda/include", "-fsyntax-only", str(decl)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    # and the shim defines each of those names
+    syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(os.path.dirname(coll_lib), "libb200coll_nccl.so")], capture_output=True, text=True, check=True).stdout
+    for name in re.findall(r"\b(nccl[A-Z]\w+)\(", src.read_text()):
+        assert f" T {name}\n" in syms, name
