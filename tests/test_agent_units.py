@@ -3,11 +3,13 @@ validation, MIG table. Table-test shape follows the reference (pkg/gpu/nvidia/ma
 gpusharing/gpusharing_test.go:24-119)."""
 import json
 
+import os
+
 import pytest
 
 from container_engine_accelerators_b200.agent import config as cfgmod
 from container_engine_accelerators_b200.agent import manager as mgr
-from container_engine_accelerators_b200.agent import mig, nvml, sharing, testing, util, version_visibility
+from container_engine_accelerators_b200.agent import mig, nvml, protos, sharing, testing, util, version_visibility
 from container_engine_accelerators_b200.agent.config import GPUConfig, GPUSharingConfig
 
 
@@ -165,3 +167,75 @@ def test_driver_version_annotations_preserve_others():
             version_visibility.parse_driver_annotations("not.a.version.x")
     finally:
         api.stop()
+
+
+# ------------------------------------------------------------------------------------------------- wire schemas vs upstream .proto files
+def _parse_proto(path):
+    """Minimal .proto reader: {message: {field name: (number, type, repeated)}} — enough to compare names, numbers, types and cardinality."""
+    import re
+    text = re.sub(r"//[^\n]*", "", open(path).read())
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"\[[^\]]*\]", "", text)                       # field options such as (gogoproto.customname)
+    out, stack = {}, []
+    for tok in re.finditer(r"message\s+(\w+)\s*\{|enum\s+(\w+)\s*\{|oneof\s+\w+\s*\{|\}|(repeated\s+|optional\s+)?(map\s*<\s*\w+\s*,\s*[\w.]+\s*>|[\w.]+)\s+(\w+)\s*=\s*(\d+)\s*;", text):
+        if tok.group(1):
+            stack.append(tok.group(1)); out.setdefault(tok.group(1), {})
+        elif tok.group(2):
+            stack.append("enum:" + tok.group(2)); out.setdefault("__enums__", set()).add(tok.group(2))
+        elif tok.group(0).startswith("oneof"):
+            stack.append("oneof")
+        elif tok.group(0) == "}":
+            if stack:
+                stack.pop()
+        else:
+            owner = next((s for s in reversed(stack) if not s.startswith("enum:") and s != "oneof"), None)
+            if owner is None or (stack and stack[-1].startswith("enum:")):
+                continue
+            typ = re.sub(r"\s+", "", tok.group(4))
+            out[owner][tok.group(5)] = (int(tok.group(6)), typ.split(".")[-1] if not typ.startswith("map<") else typ, bool(tok.group(3) and tok.group(3).strip() == "repeated"))
+    return out
+
+
+_SCALARS = {9: "string", 8: "bool", 3: "int64", 5: "int32", 13: "uint32", 4: "uint64", 12: "bytes", 1: "double", 2: "float"}
+
+
+def _our_fields(msg_cls):
+    fields = {}
+    for f in msg_cls.DESCRIPTOR.fields:
+        if f.message_type is not None and f.message_type.GetOptions().map_entry:
+            k, v = f.message_type.fields_by_name["key"], f.message_type.fields_by_name["value"]
+            vt = v.message_type.name if v.message_type is not None else _SCALARS[v.type]
+            fields[f.name] = (f.number, f"map<{_SCALARS[k.type]},{vt}>", False)
+        else:
+            typ = f.message_type.name if f.message_type is not None else (f.enum_type.name if f.enum_type is not None else _SCALARS[f.type])
+            fields[f.name] = (f.number, typ, bool(f.is_repeated) if hasattr(f, "is_repeated") else f.label == f.LABEL_REPEATED)
+    return fields
+
+
+@pytest.mark.parametrize("ours,upstream", [
+    ("deviceplugin", "k8s.io/kubelet/pkg/apis/deviceplugin/v1beta1/api.proto"),
+    ("podresources", "k8s.io/kubelet/pkg/apis/podresources/v1alpha1/api.proto"),
+    ("nri", "github.com/containerd/nri/pkg/api/api.proto"),
+])
+def test_kubelet_schemas_match_the_upstream_proto_files(ours, upstream):
+    """protos.py builds descriptors at run time from a hand-written table (the image has no protoc); every message and field in that
+    table must agree — name, number, type, repeated — with the schema the kubelet is compiled from. Fields we do not model are fine
+    (proto3 skips unknown fields); a wrong number or type is not."""
+    path = os.path.join("/root/reference/vendor", upstream)
+    if not os.path.exists(path):
+        pytest.skip("upstream .proto not available")
+    theirs = _parse_proto(path)
+    ns = getattr(protos, ours)
+    checked = 0
+    for name, cls in vars(ns).items():
+        if not hasattr(cls, "DESCRIPTOR"):
+            continue
+        assert name in theirs, f"{name} is not a message of {upstream}"
+        for fname, spec in _our_fields(cls).items():
+            assert fname in theirs[name], f"{name}.{fname} does not exist upstream (has {sorted(theirs[name])})"
+            up = theirs[name][fname]
+            if up[1] in theirs.get("__enums__", ()) and spec[1] == "int32":
+                up = (up[0], "int32", up[2])                  # an enum travels as an int32 varint: modelling it as int32 is wire-exact
+            assert up == spec, f"{name}.{fname}: ours {spec}, upstream {theirs[name][fname]}"
+            checked += 1
+    assert checked >= {"deviceplugin": 30, "podresources": 6, "nri": 15}[ours]
