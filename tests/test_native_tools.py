@@ -269,3 +269,24 @@ def test_native_json_agrees_with_python_on_generated_documents(native_build):
     for bad in ("{", "[1,]", '{"a" 1}', "tru", '"\\x"', "[1] 2", ""):
         r = subprocess.run([exe, "--json-roundtrip"], input=bad.encode(), capture_output=True, timeout=20)
         assert r.stdout.startswith(b"ERR"), (bad, r.stdout)
+
+
+def test_mig_table_covers_every_size_the_reference_knows():
+    """mig_profiles.inc is the single table behind the plugin and the partitioner; every (size -> profile id, max count) the reference
+    lists in its two tables (partition_gpu.go:37-139, pkg/gpu/nvidia/mig/mig.go:35-82) must be there with the same numbers."""
+    import re
+    ref = "/root/reference/partition_gpu/partition_gpu.go"
+    if not os.path.exists(ref):
+        pytest.skip("reference not available")
+    go = open(ref).read()
+    ids = dict(re.findall(r'"(\d+g\.\d+gb)":\s*"(\d+)"', go[go.index("partitionSizeToProfileID"):go.index("partitionSizeMaxCount")]))
+    counts = dict(re.findall(r'"(\d+g\.\d+gb)":\s*(\d+),', go[go.index("partitionSizeMaxCount"):]))
+    plugin_counts = dict(re.findall(r'"(\d+g\.\d+gb)":\s*(\d+),', open("/root/reference/pkg/gpu/nvidia/mig/mig.go").read()))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = {m.group(1): (m.group(2), m.group(3)) for m in re.finditer(r'MIG_PROFILE\("([\w.]+)",\s*(\d+),\s*(\d+),', open(os.path.join(root, "agent", "native", "mig_profiles.inc")).read())}
+    assert len(ids) >= 20 and set(ids) <= set(ours), sorted(set(ids) - set(ours))
+    for size, pid in ids.items():
+        assert ours[size] == (pid, counts[size]), (size, ours[size], pid, counts[size])
+    for size, n in plugin_counts.items():
+        assert ours[size][1] == n, (size, ours[size], n)
+    assert ours["1g.23gb"] == ("19", "7") and ours["7g.180gb"] == ("0", "1")          # the B200 rows the north-star names
