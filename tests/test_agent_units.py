@@ -239,3 +239,45 @@ def test_kubelet_schemas_match_the_upstream_proto_files(ours, upstream):
             assert up == spec, f"{name}.{fname}: ours {spec}, upstream {theirs[name][fname]}"
             checked += 1
     assert checked >= {"deviceplugin": 30, "podresources": 6, "nri": 15}[ours]
+
+
+def test_contract_constants_match_the_reference_sources():
+    """Names that other systems key on (Prometheus queries, node-problem-detector, the kubelet, job templates) must be the reference's
+    exactly, in the Python agent AND in the native binary: monitored Xids, gauge names, annotation keys, condition / event strings,
+    resource name, topology labels, NRI annotation prefix."""
+    import re
+    ref = "/root/reference"
+    if not os.path.exists(ref):
+        pytest.skip("reference not available")
+    from container_engine_accelerators_b200.agent import health, metrics, nri as nrimod
+    from container_engine_accelerators_b200.scheduler import topology as topo
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    native = open(os.path.join(root, "agent", "native", "dp", "device_plugin.cc")).read()
+    hc = open(f"{ref}/pkg/gpu/nvidia/health_check/health_checker.go").read()
+    xids = tuple(int(x) for x in re.search(r"monitorCriticalXid := \[\]int\{([^}]*)\}", hc).group(1).split(","))
+    assert health.MONITOR_XIDS == xids and "kMonitorXids[] = {" + ", ".join(map(str, xids)) + "}" in native
+    assert 'Type:               "XidCriticalError"' in hc or '"XidCriticalError"' in hc
+    assert health.XID_CONDITION_TYPE == "XidCriticalError" and 'kXidCondition = "XidCriticalError"' in native
+    assert '"nvidia-gpu-device-plugin"' in hc and health.EVENT_SOURCE == "nvidia-gpu-device-plugin" and 'kEventSource = "nvidia-gpu-device-plugin"' in native
+    gauges = re.findall(r'Name: "(\w+)"', open(f"{ref}/pkg/gpu/nvidia/metrics/metrics.go").read())
+    assert sorted(gauges) == sorted(["duty_cycle_gpu_node", "memory_total_gpu_node", "memory_used_gpu_node", "duty_cycle", "memory_total", "memory_used", "request"])
+    ours = {m._name for m in metrics.MetricServer(nvml.MockNvml("/nonexistent"))._all}
+    assert set(gauges) <= ours
+    for g in gauges:
+        assert f'"{g}"' in native or f'"{g.replace("_gpu_node", "")}"' in native, g
+    vv = open(f"{ref}/pkg/gpu/nvidia/version_visibility/version_visibility.go").read()
+    prefix = re.search(r'DriverVersionPrefix\s*=\s*"([^"]+)"', vv).group(1)
+    assert version_visibility.PREFIX == prefix + "." and f'"{prefix}."' in native
+    assert 'FieldManager: "gpu-device-plugin"' in vv or '"gpu-device-plugin"' in vv
+    assert version_visibility.FIELD_MANAGER == "gpu-device-plugin" and '"gpu-device-plugin"' in native
+    assert 'resourceName = "nvidia.com/gpu"' in open(f"{ref}/pkg/gpu/nvidia/manager.go").read().replace("\t", " ").replace("  ", " ") or "nvidia.com/gpu" in open(f"{ref}/pkg/gpu/nvidia/manager.go").read()
+    assert mgr.RESOURCE_NAME == "nvidia.com/gpu" and 'kResourceName = "nvidia.com/gpu"' in native
+    sched = open(f"{ref}/gke-topology-scheduler/schedule-daemon.py").read()
+    labels = dict(re.findall(r"^(\w+_LABEL) = '([^']+)'", sched, re.M))
+    assert topo.PRERELEASE_LABELS == (labels["PRERELEASE_CLUSTER_LABEL"], labels["PRERELEASE_RACK_LABEL"], labels["PRERELEASE_HOST_LABEL"])
+    assert topo.GA_LABELS == (labels["CLUSTER_LABEL"], labels["RACK_LABEL"], labels["HOST_LABEL"])
+    inj = open(f"{ref}/nri_device_injector/nri_device_injector.go").read()
+    key = re.search(r'ctrDeviceKeyPrefix\s*=\s*"([^"]+)"', inj)
+    if key:
+        assert nrimod.CTR_DEVICE_KEY_PREFIX == key.group(1)
+    assert nrimod.CTR_DEVICE_KEY_PREFIX == "devices.gke.io/container." and "devices.gke.io/container." in open(os.path.join(root, "agent", "native", "dp", "nri_injector.cc")).read()
