@@ -92,6 +92,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
         self._comm: Optional[coll.Comm] = None
         self._gloo = None
         self._scratch: dict = {}          # (nbytes class) -> symmetric uint8 tensor, for all-to-all-v receive staging
+        self._last_stream = None          # stream and completion event of the previous device collective (see _ordered)
+        self._last_event = None
         self.fast_calls = 0               # collectives that ran on libb200coll
         self.fallback_calls = 0           # collectives that ran on the Gloo group
 
@@ -129,6 +131,28 @@ class B200CollProcessGroup(dist.ProcessGroup):
 
     abort = shutdown
 
+    class _ordered:
+        """A communicator runs one collective at a time (its barrier epochs and Lamport buffers are per communicator, as NCCL's channels
+        are). Calls that stay on one stream are ordered by the stream. When the caller moves to another stream (FSDP all-gathers on its
+        unshard stream while reduce-scatters run on the post-backward stream) the new stream first waits for the previous collective."""
+
+        def __init__(self, pg):
+            self.pg = pg
+
+        def __enter__(self):
+            pg, cur = self.pg, torch.cuda.current_stream()
+            if pg._last_stream is not None and pg._last_stream != cur and pg._last_event is not None:
+                cur.wait_event(pg._last_event)
+            return cur
+
+        def __exit__(self, *exc):
+            pg, cur = self.pg, torch.cuda.current_stream()
+            if pg._last_event is None or pg._last_stream != cur:
+                pg._last_event = torch.cuda.Event()
+            pg._last_event.record(cur)
+            pg._last_stream = cur
+            return False
+
     def _via_gloo(self, tensors, run):
         """Run `run(cpu_tensors)` on the Gloo group and copy results back into the (possibly CUDA) originals."""
         self.fallback_calls += 1
@@ -146,8 +170,9 @@ class B200CollProcessGroup(dist.ProcessGroup):
     def allreduce(self, tensors, opts=None):
         op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
         if op is not None and all(_fast(t) for t in tensors):
-            for t in tensors:
-                self.comm.all_reduce(t, op=op)
+            with self._ordered(self):
+                for t in tensors:
+                    self.comm.all_reduce(t, op=op)
             self.fast_calls += 1
             return _Work(tensors)
         gopts = dist.AllreduceOptions()
@@ -172,7 +197,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
             words = self._as_words(t)
             if words is None:
                 break
-            self.comm.broadcast(words, root=root)
+            with self._ordered(self):
+                self.comm.broadcast(words, root=root)
             done.append(t)
         if len(done) == len(tensors):
             self.fast_calls += 1
@@ -204,8 +230,9 @@ class B200CollProcessGroup(dist.ProcessGroup):
         root = opts.rootRank if opts is not None else 0
         op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
         if op is not None and all(_fast(t) for t in tensors):
-            for t in tensors:
-                self.comm.reduce(t, root=root, op=op)
+            with self._ordered(self):
+                for t in tensors:
+                    self.comm.reduce(t, root=root, op=op)
             self.fast_calls += 1
             return _Work(tensors)
         gopts = dist.ReduceOptions()
@@ -218,7 +245,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
     def _allgather_base(self, output, input, opts=None):
         if _fast(output) and _fast(input) and output.dtype == input.dtype and (input.numel() * input.element_size()) % 16 == 0 \
                 and output.numel() == input.numel() * self._size:
-            self.comm.all_gather(input.view(-1), output.view(-1))
+            with self._ordered(self):
+                self.comm.all_gather(input.view(-1), output.view(-1))
             self.fast_calls += 1
             return _Work(output)
         chunks = list(output.view(-1).chunk(self._size))
@@ -230,7 +258,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
             same = all(o.shape == inp.shape and o.dtype == inp.dtype for o in outs)
             if same and _fast(inp) and all(o.is_cuda for o in outs) and (inp.numel() * inp.element_size()) % 16 == 0:
                 flat = torch.empty(inp.numel() * self._size, dtype=inp.dtype, device=inp.device)
-                self.comm.all_gather(inp.view(-1), flat)
+                with self._ordered(self):
+                    self.comm.all_gather(inp.view(-1), flat)
                 for o, piece in zip(outs, flat.chunk(self._size)):
                     o.copy_(piece.view_as(o))
                 self.fast_calls += 1
@@ -252,7 +281,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
         op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
         if op is not None and _fast(output) and _fast(input) and output.dtype == input.dtype and (output.numel() * output.element_size()) % 16 == 0 \
                 and input.numel() == output.numel() * self._size:
-            self.comm.reduce_scatter(input.view(-1), output.view(-1), op=op)
+            with self._ordered(self):
+                self.comm.reduce_scatter(input.view(-1), output.view(-1), op=op)
             self.fast_calls += 1
             return _Work(output)
         # generic: all-reduce a copy, keep my slice
@@ -277,7 +307,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
         even = not output_split_sizes and not input_split_sizes
         if even and _fast(output) and _fast(input) and output.dtype == input.dtype and output.data_ptr() != input.data_ptr() \
                 and input.numel() % n == 0 and (input.numel() // n * input.element_size()) % 16 == 0 and output.numel() == input.numel():
-            self.comm.all_to_all(input.view(-1), output.view(-1))
+            with self._ordered(self):
+                self.comm.all_to_all(input.view(-1), output.view(-1))
             self.fast_calls += 1
             return _Work(output)
         row_elems = input[0].numel() if input.dim() > 0 and input.shape[0] > 0 else 0
@@ -308,7 +339,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
         if scratch is None:
             scratch = self._scratch[cls] = self.comm.empty(cls, torch.uint8)
         recv = scratch[:need].view(input.dtype)
-        self.comm.all_to_all_v(input.view(-1), recv, row_elems, send_rows, send_off, recv_off_at_peer)
+        with self._ordered(self):
+            self.comm.all_to_all_v(input.view(-1), recv, row_elems, send_rows, send_off, recv_off_at_peer)
         got_rows = sum(matrix[s][self._rank] for s in range(n))
         output.view(-1)[:got_rows * row_elems].copy_(recv[:got_rows * row_elems])
         self.fast_calls += 1
@@ -333,7 +365,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
 
     def barrier(self, opts=None):
         if torch.cuda.is_available() and self._comm is not None:
-            self.comm.barrier()
+            with self._ordered(self):
+                self.comm.barrier()
             self.fast_calls += 1
             return _Work(None, sync_on_wait=True)
         self.fallback_calls += 1

@@ -184,7 +184,16 @@ def _gpu_pair(rank, world):
     torch.manual_seed(rank); ddp(torch.randn(8, 32, device="cuda")).sum().backward()
     g = model.weight.grad.clone(); gs = [torch.empty_like(g) for _ in range(world)]; dist.all_gather(gs, g)
     assert torch.allclose(gs[0], gs[1])
+    # collectives issued from two different streams back to back: the group orders them (one collective at a time per communicator)
+    side = torch.cuda.Stream()
+    a = torch.full((1 << 18,), float(rank + 1), device="cuda"); b = torch.full((1 << 18,), 10.0 * (rank + 1), device="cuda")
     torch.cuda.synchronize()
+    for _ in range(20):
+        dist.all_reduce(a)
+        with torch.cuda.stream(side):
+            dist.all_reduce(b)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all() and torch.isfinite(b).all() and a[0].item() == a[-1].item() and b[0].item() == b[-1].item()
     assert pg.fast_calls >= 6
     return pg.fast_calls
 
