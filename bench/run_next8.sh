@@ -24,7 +24,8 @@ for pdl in 0 1; do
   B200COLL_PDL=$pdl timeout 90 ./build/b200coll_perf --devs $ALL --procs --op all_reduce -b 1K -e 4M -f 4 --iters 200 --warmup 20 > ${O}_pdl${pdl}.txt 2>&1; echo "pdl=$pdl rc=$?"; grep -E "^ +[0-9]" ${O}_pdl${pdl}.txt | awk '{print $1, $4, $6}' | tr '\n' ';'; echo
 done
 echo "== $(date -u +%T) build variants (A/B candidates: kernel parameter in the constant bank; multicast barrier)"
-make -C coll variants -j2 > ${O}_variants_build.log 2>&1; echo "variants rc=$?"
+if [ -f coll/lib/libb200coll_gridconst.so ] && [ -f coll/lib/libb200coll_mcbar.so ]; then echo "variants: prebuilt libraries travelled with the snapshot"
+else make -C coll variants -j2 > ${O}_variants_build.log 2>&1; echo "variants rc=$?"; fi
 port=29740
 for v in "" _gridconst _mcbar; do
   lib=coll/lib/libb200coll${v}.so
