@@ -4,7 +4,7 @@
 #   2. programmatic dependent launch (B200COLL_PDL=1) at one rank per GPU: small-message latency with and without
 #   3. the multi-process NVLS test that a one-GPU box skips
 #   4. the torch.distributed process group's CUDA paths (tests/test_process_group.py, opt-in until this has passed once)
-#   5. A/B of the two compile-time variants (lib/libb200coll_gridconst.so, lib/libb200coll_mcbar.so) against the shipped build, 1 KiB - 64 MiB
+#   5. A/B of the two compile-time variants (lib/libb200coll_{gridconst,mcbar,bulk}.so) against the shipped build, 1 KiB - 64 MiB
 # Usage: gpurun --gpus 8 --timeout 600 -- 'bash bench/run_next8.sh 8'
 NG=${1:-8}
 mkdir -p gpurun_out; export B200COLL_TIMEOUT_MS=5000
@@ -24,20 +24,23 @@ for pdl in 0 1; do
   B200COLL_PDL=$pdl timeout 90 ./build/b200coll_perf --devs $ALL --procs --op all_reduce -b 1K -e 4M -f 4 --iters 200 --warmup 20 > ${O}_pdl${pdl}.txt 2>&1; echo "pdl=$pdl rc=$?"; grep -E "^ +[0-9]" ${O}_pdl${pdl}.txt | awk '{print $1, $4, $6}' | tr '\n' ';'; echo
 done
 echo "== $(date -u +%T) build variants (A/B candidates: kernel parameter in the constant bank; multicast barrier)"
-if [ -f coll/lib/libb200coll_gridconst.so ] && [ -f coll/lib/libb200coll_mcbar.so ]; then echo "variants: prebuilt libraries travelled with the snapshot"
+if [ -f coll/lib/libb200coll_gridconst.so ] && [ -f coll/lib/libb200coll_mcbar.so ] && [ -f coll/lib/libb200coll_bulk.so ]; then echo "variants: prebuilt libraries travelled with the snapshot"
 else make -C coll variants -j2 > ${O}_variants_build.log 2>&1; echo "variants rc=$?"; fi
 port=29740
-for v in "" _gridconst _mcbar; do
+for v in "" _gridconst _mcbar _bulk; do
   lib=coll/lib/libb200coll${v}.so
   [ -f $lib ] || continue
   port=$((port + 1))
-  B200COLL_LIB=$PWD/$lib timeout 120 $TR --master-port $port bench.py --gpus $NG --steps 20 --warmup 5 --no-e2e --max 64M > ${O}_ab${v:-_shipped}.json 2> ${O}_ab${v:-_shipped}.err
-  python3 - "$lib" ${O}_ab${v:-_shipped}.json <<'PY'
+  B200COLL_LIB=$PWD/$lib timeout 200 $TR --master-port $port bench.py --gpus $NG --steps 20 --warmup 5 --no-e2e --max 1G --extra-ops all_gather --extra-out ${O}_ab${v:-_shipped}_ag.json > ${O}_ab${v:-_shipped}.json 2> ${O}_ab${v:-_shipped}.err
+  python3 - "$lib" ${O}_ab${v:-_shipped}.json ${O}_ab${v:-_shipped}_ag.json <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
     t = {r["bytes"]: r["oop_us"] for r in d["table"]}
-    print(sys.argv[1], "avg busbw", d["value"], "verified", d["verified_vs_torch_fp32"], "| us at 1K/64K/1M/16M:", t.get(1024), t.get(65536), t.get(1 << 20), t.get(1 << 24))
+    print(sys.argv[1], "all_reduce avg busbw", d["value"], "peak", d["peak_busbw"], "verified", d["verified_vs_torch_fp32"], "| us at 1K/64K/1M/16M:", t.get(1024), t.get(65536), t.get(1 << 20), t.get(1 << 24))
+    ag = json.load(open(sys.argv[3]))["ops"]["all_gather"]
+    big = {r["bytes"]: r["oop_busbw"] for r in ag["table"]}
+    print(sys.argv[1], "all_gather avg busbw", round(ag["avg_busbw"], 1), "peak", round(ag["peak_busbw"], 1), "verified", ag["verified"], "| busbw at 16M/256M/1G:", big.get(1 << 24), big.get(1 << 28), big.get(1 << 30))
 except Exception as e:
     print(sys.argv[1], "no result:", e)
 PY

@@ -307,6 +307,16 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
       return b200collSuccess;
     });
   };
+#ifdef B200COLL_VARIANT_BULK
+  if (sym_out && identity && bytes >= (1u << 20) && algo != b200collAlgoNvls) {     // A/B candidate: copy-engine push (kernels.cuh k_ag_bulk)
+    account(c, b200collOpAllGather, bytes, algo);
+    const size_t chunks = (bytes + kBulkChunk - 1) / kBulkChunk;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(chunks, (size_t)std::min(c->max_ctas, 2 * std::max(1, c->sm_count))));
+    launch_k(k_ag_bulk, blocks, 128, st, c->dev, static_cast<const char*>(send), arena_off(c, recv), bytes, (uint32_t)b200collOpAllGather);
+    LAUNCH_CHECK(c);
+    return b200collSuccess;
+  }
+#endif
   if (sym_out) return push(send, recv, sendcount);
   // staged: gather chunks into staging half 1 laid out [nranks][chunk], then scatter locally into recv
   c->stats.staged_calls++;

@@ -679,6 +679,55 @@ __global__ void __launch_bounds__(kThreads) k_reduce_root(COMM_PARAM, size_t in_
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
+#ifdef B200COLL_VARIANT_BULK
+// ------------------------------------------------------------------------------------------------
+// A/B candidate (make VARIANT=bulk -> lib/libb200coll_bulk.so): all-gather push with the copy engine of the SM instead of
+// LDG/STG. One elected thread per CTA streams its share of the local buffer through a small shared-memory ring:
+//   cp.async.bulk global -> shared (completion on an mbarrier), then one cp.async.bulk shared -> peer global per rank, committed as a
+//   bulk group; a ring slot is reused once the group that read it has finished reading (cp.async.bulk.wait_group.read).
+// Loads of chunk k+1 overlap the stores of chunk k; no registers carry data, so a CTA is one warp's worth of control code.
+// Identity epilogue only (same dtype, scale 1): the bytes are never looked at.
+constexpr int kBulkStages = 4;
+constexpr uint32_t kBulkChunk = 8192;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(128) k_ag_bulk(COMM_PARAM, const char* __restrict__ in, size_t out_off, size_t bytes, uint32_t op) {
+  pdl_prologue();
+  __shared__ __align__(128) char ring[kBulkStages][kBulkChunk];
+  __shared__ __align__(8) unsigned long long full[kBulkStages];
+  const uint32_t s = load_seq(c, kSeqBarrier);
+  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBulkStages; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const size_t dst0 = out_off + (size_t)c.rank * bytes;
+    const size_t nchunks = (bytes + kBulkChunk - 1) / kBulkChunk;
+    uint32_t it = 0;
+    for (size_t i = blockIdx.x; i < nchunks; i += gridDim.x, it++) {
+      const int stage = (int)(it % kBulkStages);
+      const uint32_t parity = (it / kBulkStages) & 1u;
+      if (it >= (uint32_t)kBulkStages) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkStages - 1) : "memory");   // the stores that read this slot are done reading
+      const size_t off = i * (size_t)kBulkChunk;
+      const uint32_t n = (uint32_t)(bytes - off < kBulkChunk ? bytes - off : kBulkChunk);
+      const uint32_t bar = smem_u32(&full[stage]), dst_s = smem_u32(&ring[stage][0]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(in + off), "r"(n), "r"(bar) : "memory");
+      uint32_t done = 0;
+      while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#pragma unroll
+      for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) {
+        int r = c.rank + j; if (r >= c.nranks) r -= c.nranks;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(c.peer[r] + dst0 + off), "r"(dst_s), "r"(n) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // every store has been performed, not just read
+    asm volatile("fence.proxy.async.global;" ::: "memory");             // order the copy engine's writes before the flag stores of the barrier
+  }
+  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
+}
+#endif
+
 __global__ void k_barrier(COMM_PARAM, uint32_t op) {
   pdl_prologue();
   const uint32_t s = load_seq(c, kSeqBarrier);
