@@ -45,4 +45,7 @@ except Exception as e:
     print(sys.argv[1], "no result:", e)
 PY
 done
+echo "== $(date -u +%T) end-to-end step: copy-then-reduce vs pipelined Comm.all_reduce_from_host"
+B200_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_coll_gpu.py -q -k all_reduce_from_host > ${O}_pytest_e2e.log 2>&1; echo "pytest rc=$?"
+timeout 200 $TR --master-port 29760 bench/e2e_pipeline.py > ${O}_e2e_pipeline.jsonl 2> ${O}_e2e_pipeline.err; cat ${O}_e2e_pipeline.jsonl
 echo "== $(date -u +%T) done"

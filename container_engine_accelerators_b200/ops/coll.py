@@ -273,6 +273,37 @@ class Comm:
         _check(load().b200collAllReduce(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), op, self._h, self._stream(stream)), "AllReduce")
         return dst
 
+    def all_reduce_from_host(self, host_in, out, chunk_bytes: int = 32 << 20, scale: float = 1.0, op: int = SUM, stream=None):
+        """End-to-end step: `out` (device, ideally from `empty()`) = all-reduce of every rank's pinned host tensor `host_in`.
+        The host→device copy is pipelined with the collective: chunk i+1 crosses PCIe on a copy stream while chunk i is reduced out
+        of one of two arena staging buffers, so the step costs about the copy time instead of copy + collective. Same call (sizes,
+        chunking) on every rank. EXPERIMENTAL: composed from validated pieces (copies, events, `all_reduce`) but not yet timed on hardware."""
+        import torch
+        assert host_in.device.type == "cpu" and out.is_cuda and host_in.numel() == out.numel() and host_in.is_contiguous() and out.is_contiguous()
+        main = stream if stream is not None else torch.cuda.current_stream()
+        itemsize = host_in.element_size()
+        chunk = max(1, chunk_bytes // itemsize // 64 * 64)
+        if not hasattr(self, "_h2d"):
+            self._h2d = {"stream": torch.cuda.Stream(), "bufs": {}, "ready": [torch.cuda.Event(), torch.cuda.Event()], "free": [torch.cuda.Event(), torch.cuda.Event()]}
+        st = self._h2d
+        key = (chunk, host_in.dtype)
+        if key not in st["bufs"]:
+            st["bufs"][key] = [self.empty(chunk, host_in.dtype), self.empty(chunk, host_in.dtype)]
+        bufs, ready, free, copy_stream = st["bufs"][key], st["ready"], st["free"], st["stream"]
+        copy_stream.wait_stream(main)                       # staging buffers may still be in use by earlier work on the caller's stream
+        n_total, flat_in, flat_out = host_in.numel(), host_in.view(-1), out.view(-1)
+        for i, off in enumerate(range(0, n_total, chunk)):
+            k, n = i & 1, min(chunk, n_total - off)
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(free[k])         # the collective that read this staging buffer two chunks ago is done
+                bufs[k][:n].copy_(flat_in[off:off + n], non_blocking=True)
+                ready[k].record(copy_stream)
+            main.wait_event(ready[k])
+            self.all_reduce(bufs[k][:n], flat_out[off:off + n], scale=scale, op=op, stream=main)
+            free[k].record(main)
+        return out
+
     def all_gather(self, src, dst, scale: float = 1.0, stream=None):
         ep = self._ep(src, dst, scale)
         _check(load().b200collAllGather(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), self._h, self._stream(stream)), "AllGather")

@@ -354,6 +354,26 @@ def test_bench_contract_one_gpu(torch_cuda):
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
 
 
+@pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="pipelined host->device all-reduce has not run on hardware yet; set B200_RUN_UNVALIDATED=1")
+@pytest.mark.parametrize("group", [2], indirect=True)
+def test_all_reduce_from_host_pipelines_copy_and_collective(torch_cuda, group):
+    torch = torch_cuda
+    comms, streams = group
+    count = (5 << 20) + 1024                                     # several 4 MiB chunks and a ragged tail
+    hosts = [(((torch.arange(count) * (r + 2)) % 11) - 5).to(torch.bfloat16).pin_memory() for r in range(len(comms))]
+    outs = [c.empty(count, torch.bfloat16) for c in comms]
+    for rep in range(3):                                         # staging buffers are reused across calls
+        for r, c in enumerate(comms):
+            with torch.cuda.stream(streams[r]):
+                c.all_reduce_from_host(hosts[r], outs[r], chunk_bytes=4 << 20)
+        torch.cuda.synchronize()
+        want = sum(h.float() for h in hosts).cuda()
+        for o in outs:
+            assert torch.equal(o.float(), want)
+    for c in comms:
+        c.check_async_error()
+
+
 # ------------------------------------------------------------------------------------------------- NCCL-API shim
 class _NcclShim:
     """ctypes view of libb200coll_nccl.so with NCCL's own prototypes (what an nccl-tests binary would call)."""
