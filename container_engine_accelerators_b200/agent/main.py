@@ -10,6 +10,7 @@ from __future__ import annotations
 import argparse
 import logging
 import os
+import signal
 import sys
 import threading
 import time
@@ -128,9 +129,19 @@ def main(argv=None) -> int:
             except Exception as e:
                 log.error("failed to publish driver version annotations: %s", e)
         threading.Thread(target=publish, daemon=True).start()
+    # SIGTERM / SIGINT (pod deletion, rolling update): stop serving, remove the plugin socket, exit 0 — the kubelet sees the endpoint
+    # go away cleanly instead of a dangling socket file
+    stopping = threading.Event()
+
+    def on_signal(signum, frame):
+        log.info("received signal %d, shutting down", signum)
+        stopping.set()
+        ngm.stop()
+    signal.signal(signal.SIGTERM, on_signal)
+    signal.signal(signal.SIGINT, on_signal)
     if args.status_only:
         log.info("status-only mode: the kubelet-facing API is served by the native plugin")
-        threading.Event().wait()
+        stopping.wait()
         return 0
     ngm.serve(args.plugin_directory, KUBELET_ENDPOINT, args.plugin_endpoint or f"{PLUGIN_ENDPOINT_PREFIX}-{int(time.time())}.sock")
     return 0

@@ -64,7 +64,8 @@ def test_python_agent_process_with_kubernetes_side_effects(tmp_path, native_buil
         assert api.events[0]["message"] == "Caught XID error, XID=48"
         assert api.nodes["node-a"]["metadata"]["annotations"]["cloud.google.com/cuda.driver-version.major"] == "570"
         stream.cancel(); c.close()
-        p.send_signal(signal.SIGTERM); p.wait(10)
+        p.send_signal(signal.SIGTERM)
+        assert p.wait(10) == 0 and not sock.exists()                      # graceful: exit 0, plugin socket removed
         # status-only: no plugin socket, but the condition heartbeat / events path still runs
         api.events.clear()
         events2 = tmp_path / "events2.txt"; events2.write_text("")          # the scripted NVML replays its file from the start in a new process
