@@ -812,13 +812,15 @@ int serve(Manager* ngm, const std::string& plugin_dir, const std::string& kubele
       LOGI("device-plugin registered with the kubelet");
     }
     const ino_t kubelet_ino = inode_of(kubelet_path);
+    bool kubelet_gone = false;
     auto next_gpu_check = std::chrono::steady_clock::now() + std::chrono::milliseconds((int)(ngm->gpu_check_interval * 1000));
     bool rediscover = false;
     while (!g_stop) {
       usleep((useconds_t)(ngm->socket_check_interval * 1e6));
       if (!exists(sock)) { LOGI("plugin socket %s was removed; restarting the server", sock.c_str()); break; }
       const ino_t ino = inode_of(kubelet_path);
-      if (do_register && ino && ino != kubelet_ino) { LOGI("kubelet socket was re-created (kubelet restart); re-registering"); break; }
+      if (do_register && !ino) kubelet_gone = true;          // a restarting kubelet removes its socket first; the new one may get the SAME inode number back
+      if (do_register && ino && (ino != kubelet_ino || kubelet_gone)) { LOGI("kubelet socket was re-created (kubelet restart); re-registering"); break; }
       if (!do_register && ino) { do_register = true; LOGI("kubelet socket appeared; registering"); break; }
       if (std::chrono::steady_clock::now() >= next_gpu_check) {
         next_gpu_check = std::chrono::steady_clock::now() + std::chrono::milliseconds((int)(ngm->gpu_check_interval * 1000));

@@ -230,6 +230,22 @@ def kubelet_appears_later(cmd):
         n.close()
 
 
+def kubelet_restart(cmd):
+    """The kubelet restarts (kubelet.sock is re-created): the plugin notices and registers again with the new instance."""
+    n = Node(cmd)
+    try:
+        n.kubelet.wait_registration(20)
+        n.connect()
+        n.kubelet.stop()
+        time.sleep(0.3)
+        n.kubelet = testing.KubeletStub(n.plugin_dir).start()
+        reg = n.kubelet.wait_registration(20)
+        assert reg.endpoint == n.endpoint and reg.resource_name == "nvidia.com/gpu"
+        assert len(n.connect().allocate(["nvidia1"]).container_responses[0].devices) == 5
+    finally:
+        n.close()
+
+
 def xid_marks_unhealthy(cmd):
     """A health-critical Xid (XID_CONFIG) turns the device Unhealthy in the ListAndWatch stream and blocks its allocation; others are ignored."""
     events = tempfile.NamedTemporaryFile("w", suffix=".events", delete=False)
@@ -375,7 +391,7 @@ def transport_profile(cmd):
         n.close()
 
 
-SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later,
+SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later, kubelet_restart,
              xid_marks_unhealthy, xid_on_a_mig_slice, metrics_endpoint, mps_sharing, transport_profile]
 
 

@@ -264,6 +264,7 @@ class GPUManager:
                     raise RuntimeError(f"device-plugin: cannot register to kubelet service: {e}") from e
             self.serving.set()
             kubelet_ino = self._ino(kubelet_path)
+            kubelet_gone = False
             next_gpu_check = time.monotonic() + self.gpu_check_interval
             while not self._restart.is_set():
                 self._restart.wait(self.socket_check_interval)
@@ -273,7 +274,9 @@ class GPUManager:
                     log.info("plugin socket %s was removed; restarting the server", self.socket_path)
                     break
                 ino = self._ino(kubelet_path)
-                if register and ino is not None and ino != kubelet_ino:
+                if register and ino is None:
+                    kubelet_gone = True          # a restarting kubelet removes its socket first; the new one may get the same inode number back
+                if register and ino is not None and (ino != kubelet_ino or kubelet_gone):
                     log.info("kubelet socket was re-created (kubelet restart); re-registering")
                     break
                 if not register and ino is not None:
