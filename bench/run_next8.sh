@@ -49,3 +49,5 @@ echo "== $(date -u +%T) end-to-end step: copy-then-reduce vs pipelined Comm.all_
 B200_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_coll_gpu.py -q -k all_reduce_from_host > ${O}_pytest_e2e.log 2>&1; echo "pytest rc=$?"
 timeout 200 $TR --master-port 29760 bench/e2e_pipeline.py > ${O}_e2e_pipeline.jsonl 2> ${O}_e2e_pipeline.err; cat ${O}_e2e_pipeline.jsonl
 echo "== $(date -u +%T) done"
+echo "=== tools on hardware (fault injector last: it kills its own context on purpose) ==="
+B200_RUN_FAULT_INJECTION=1 timeout 300 python -m pytest tests/test_zz_tools_gpu.py -q -m gpu > ${O}_pytest_tools.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_tools.log
