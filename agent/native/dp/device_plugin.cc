@@ -682,14 +682,15 @@ std::string g_coll_stats_dir = "/dev/shm";
 void append_coll_stats(std::ostringstream& os) {
   static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce"};
   static const char* kAlgos[] = {"auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2"};
-  struct Page { uint32_t pid, rank; uint64_t calls[6], bytes[6], algo[7]; };
+  struct Page { uint32_t pid, rank; uint64_t calls[6], bytes[6], algo[7], p2p[3]; };
   std::vector<Page> pages;
   if (DIR* d = opendir(g_coll_stats_dir.c_str())) {
     while (dirent* e = readdir(d)) {
       if (strncmp(e->d_name, "b200coll.", 9) != 0) continue;
       std::ifstream f(join(g_coll_stats_dir, e->d_name), std::ios::binary);
-      char raw[64 + 21 * 8] = {};
-      if (!f.read(raw, sizeof raw) || memcmp(raw, "B200COLL", 8) != 0) continue;
+      char raw[64 + 24 * 8] = {};
+      f.read(raw, sizeof raw);                                                   // pages are 4 KiB; anything shorter than the v1 payload is not one
+      if (f.gcount() < 64 + 17 * 8 || memcmp(raw, "B200COLL", 8) != 0) continue;
       uint32_t hdr[6]; memcpy(hdr, raw + 8, sizeof hdr);
       const int nops = hdr[0] == 1 ? 4 : 6;
       uint64_t updated = 0; if (hdr[0] >= 2) memcpy(&updated, raw + 32, sizeof updated);
@@ -698,6 +699,7 @@ void append_coll_stats(std::ostringstream& os) {
       Page p{}; p.pid = hdr[1]; p.rank = hdr[2];
       for (int i = 0; i < nops; i++) { p.calls[i] = v[i]; p.bytes[i] = v[nops + i]; }
       for (int i = 0; i < 7; i++) p.algo[i] = v[2 * nops + i];
+      if (hdr[0] >= 2) memcpy(p.p2p, raw + 64 + 21 * 8, sizeof p.p2p);           // sends, recvs, bytes; zero on pages of a library without send / recv
       pages.push_back(p);
     }
     closedir(d);
@@ -710,6 +712,10 @@ void append_coll_stats(std::ostringstream& os) {
   for (auto& p : pages) for (int i = 0; i < 6; i++) os << "b200coll_bytes{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",op=\"" << kOps[i] << "\"} " << p.bytes[i] << "\n";
   help("b200coll_algo_calls", "libb200coll calls per chosen algorithm");
   for (auto& p : pages) for (int i = 0; i < 7; i++) os << "b200coll_algo_calls{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",algo=\"" << kAlgos[i] << "\"} " << p.algo[i] << "\n";
+  help("b200coll_p2p_calls", "Point-to-point operations issued through libb200coll");
+  for (auto& p : pages) for (int i = 0; i < 2; i++) os << "b200coll_p2p_calls{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",dir=\"" << (i ? "recv" : "send") << "\"} " << p.p2p[i] << "\n";
+  help("b200coll_p2p_bytes", "Bytes sent plus received by libb200coll point-to-point operations");
+  for (auto& p : pages) os << "b200coll_p2p_bytes{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\"} " << p.p2p[2] << "\n";
 }
 
 std::string collect_metrics(Manager* ngm, const std::string& pod_resources_socket) {
@@ -792,7 +798,14 @@ void metrics_server(Manager* ngm, int port, int interval_ms, const std::string& 
 std::atomic<bool> g_stop{false};
 void on_signal(int) { g_stop = true; }
 
-ino_t inode_of(const std::string& p) { struct stat st; return ::stat(p.c_str(), &st) == 0 ? st.st_ino : 0; }
+// Identity of a socket file: inode number mixed with its change time. The inode number alone is not enough — a kubelet that removes
+// and re-creates kubelet.sock between two polls usually gets the very same number back from the filesystem. 0 = no such file.
+uint64_t inode_of(const std::string& p) {
+  struct stat st;
+  if (::stat(p.c_str(), &st) != 0) return 0;
+  const uint64_t id = (uint64_t)st.st_ino ^ (((uint64_t)st.st_ctim.tv_sec * 1000000000ull + (uint64_t)st.st_ctim.tv_nsec) * 0x9E3779B97F4A7C15ull);
+  return id ? id : 1;
+}
 
 int serve(Manager* ngm, const std::string& plugin_dir, const std::string& kubelet_endpoint, const std::string& plugin_endpoint) {
   const std::string kubelet_path = join(plugin_dir, kubelet_endpoint);
@@ -805,21 +818,23 @@ int serve(Manager* ngm, const std::string& plugin_dir, const std::string& kubele
     std::string err;
     if (!server.listen_unix(sock, &err)) { LOGE("cannot listen on %s: %s", sock.c_str(), err.c_str()); return 1; }
     LOGI("device-plugin: serving on %s", sock.c_str());
+    // identity of the kubelet socket BEFORE registering: a kubelet that restarts right after our Register call then shows up as a
+    // different socket in the watch loop below (taken afterwards, the new kubelet would silently become the baseline)
+    const uint64_t kubelet_ino = inode_of(kubelet_path);
     if (do_register) {
       std::string resp;
       int st = h2::unary_call(kubelet_path, "/v1beta1.Registration/Register", pb::encode_register_request("v1beta1", plugin_endpoint, kResourceName, g_preferred_policy != "none"), &resp, &err);
       if (st != 0) { server.stop(); LOGE("device-plugin: cannot register to kubelet service: %s", err.c_str()); return 1; }   // pod restarts (reference: glog.Fatal)
       LOGI("device-plugin registered with the kubelet");
     }
-    const ino_t kubelet_ino = inode_of(kubelet_path);
     bool kubelet_gone = false;
     auto next_gpu_check = std::chrono::steady_clock::now() + std::chrono::milliseconds((int)(ngm->gpu_check_interval * 1000));
     bool rediscover = false;
     while (!g_stop) {
       usleep((useconds_t)(ngm->socket_check_interval * 1e6));
       if (!exists(sock)) { LOGI("plugin socket %s was removed; restarting the server", sock.c_str()); break; }
-      const ino_t ino = inode_of(kubelet_path);
-      if (do_register && !ino) kubelet_gone = true;          // a restarting kubelet removes its socket first; the new one may get the SAME inode number back
+      const uint64_t ino = inode_of(kubelet_path);
+      if (do_register && !ino) kubelet_gone = true;          // seen while the socket was absent: whatever appears next is a new kubelet
       if (do_register && ino && (ino != kubelet_ino || kubelet_gone)) { LOGI("kubelet socket was re-created (kubelet restart); re-registering"); break; }
       if (!do_register && ino) { do_register = true; LOGI("kubelet socket appeared; registering"); break; }
       if (std::chrono::steady_clock::now() >= next_gpu_check) {

@@ -239,7 +239,10 @@ def kubelet_restart(cmd):
         n.kubelet.stop()
         time.sleep(0.3)
         n.kubelet = testing.KubeletStub(n.plugin_dir).start()
-        reg = n.kubelet.wait_registration(20)
+        try:
+            reg = n.kubelet.wait_registration(20)
+        except TimeoutError as e:
+            raise AssertionError(f"{e}; plugin log:\n{n.logs()[-2000:]}") from None
         assert reg.endpoint == n.endpoint and reg.resource_name == "nvidia.com/gpu"
         assert len(n.connect().allocate(["nvidia1"]).container_responses[0].devices) == 5
     finally:

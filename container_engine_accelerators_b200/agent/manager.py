@@ -255,6 +255,9 @@ class GPUManager:
             server.start()
             self.grpc_server = server
             log.info("device-plugin: serving on %s", self.socket_path)
+            # identity of the kubelet socket BEFORE registering: a kubelet that restarts right after our Register call then shows up as a
+            # different socket in the watch loop below (taken afterwards, the new kubelet would silently become the baseline)
+            kubelet_ino = self._ino(kubelet_path)
             if register:
                 try:
                     register_with_kubelet(kubelet_path, plugin_endpoint, RESOURCE_NAME, preferred_allocation=self.preferred_allocation_policy != "none")
@@ -263,7 +266,6 @@ class GPUManager:
                     self._stop_server()
                     raise RuntimeError(f"device-plugin: cannot register to kubelet service: {e}") from e
             self.serving.set()
-            kubelet_ino = self._ino(kubelet_path)
             kubelet_gone = False
             next_gpu_check = time.monotonic() + self.gpu_check_interval
             while not self._restart.is_set():
@@ -275,7 +277,7 @@ class GPUManager:
                     break
                 ino = self._ino(kubelet_path)
                 if register and ino is None:
-                    kubelet_gone = True          # a restarting kubelet removes its socket first; the new one may get the same inode number back
+                    kubelet_gone = True          # seen while the socket was absent: whatever appears next is a new kubelet
                 if register and ino is not None and (ino != kubelet_ino or kubelet_gone):
                     log.info("kubelet socket was re-created (kubelet restart); re-registering")
                     break
@@ -303,8 +305,11 @@ class GPUManager:
                 break
 
     @staticmethod
-    def _ino(path: str) -> Optional[int]:
+    def _ino(path: str):
+        """Identity of a socket file: (inode, change time). The inode number alone is not enough: a kubelet that removes and re-creates
+        kubelet.sock between two polls usually gets the same number back from the filesystem."""
         try:
-            return os.stat(path).st_ino
+            st = os.stat(path)
+            return (st.st_ino, st.st_ctime_ns)
         except OSError:
             return None

@@ -91,10 +91,12 @@ def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*", now=time.time) -
             if updated and now() - updated > COLL_STATS_STALE_S:
                 continue
             vals = struct.unpack_from(f"<{2 * nops + 9}Q", raw, 64)
+            p2p = struct.unpack_from("<3Q", raw, 64 + 8 * 21) if version >= 2 and len(raw) >= 64 + 8 * 24 else (0, 0, 0)     # zero on pages of a library without send / recv
             pad = (0,) * (len(COLL_OPS) - nops)
             pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "version": version,
                           "calls": vals[0:nops] + pad, "bytes": vals[nops:2 * nops] + pad,
-                          "algo_calls": vals[2 * nops:2 * nops + 7], "kernel_launches": vals[2 * nops + 7], "staged_calls": vals[2 * nops + 8]})
+                          "algo_calls": vals[2 * nops:2 * nops + 7], "kernel_launches": vals[2 * nops + 7], "staged_calls": vals[2 * nops + 8],
+                          "p2p_sends": p2p[0], "p2p_recvs": p2p[1], "p2p_bytes": p2p[2]})
         except OSError:
             continue
     return pages
@@ -121,8 +123,10 @@ class MetricServer:
         self.coll_calls = g("b200coll_calls", "Collective calls issued through libb200coll", ["pid", "rank", "op"])
         self.coll_bytes = g("b200coll_bytes", "Bytes moved by libb200coll collectives", ["pid", "rank", "op"])
         self.coll_algo = g("b200coll_algo_calls", "libb200coll calls per chosen algorithm", ["pid", "rank", "algo"])
+        self.coll_p2p_calls = g("b200coll_p2p_calls", "Point-to-point operations issued through libb200coll", ["pid", "rank", "dir"])
+        self.coll_p2p_bytes = g("b200coll_p2p_bytes", "Bytes sent plus received by libb200coll point-to-point operations", ["pid", "rank"])
         self._all = [self.duty_cycle_node, self.memory_total_node, self.memory_used_node, self.duty_cycle, self.memory_total, self.memory_used,
-                     self.requests, self.coll_calls, self.coll_bytes, self.coll_algo]
+                     self.requests, self.coll_calls, self.coll_bytes, self.coll_algo, self.coll_p2p_calls, self.coll_p2p_bytes]
 
     def discover_gpu_devices(self) -> None:
         self.gpu_devices = {}
@@ -184,6 +188,9 @@ class MetricServer:
                 self.coll_bytes.labels(pid, rank, op).set(page["bytes"][i])
             for i, algo in enumerate(COLL_ALGOS):
                 self.coll_algo.labels(pid, rank, algo).set(page["algo_calls"][i])
+            self.coll_p2p_calls.labels(pid, rank, "send").set(page["p2p_sends"])
+            self.coll_p2p_calls.labels(pid, rank, "recv").set(page["p2p_recvs"])
+            self.coll_p2p_bytes.labels(pid, rank).set(page["p2p_bytes"])
 
     def collect_once(self) -> None:
         try:

@@ -51,7 +51,7 @@ class KubeletStub:
 
     def stop(self) -> None:
         if self._server:
-            self._server.stop(grace=0)
+            self._server.stop(grace=0.5).wait()      # let a Register call that is being answered finish: the caller treats a failed registration as fatal
             self._server = None
         try:
             os.unlink(self.socket_path)         # grpc may remove it itself while shutting down

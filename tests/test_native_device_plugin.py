@@ -199,6 +199,7 @@ def test_metrics_endpoint(native, tmp_path, service):
         page = bytearray(4096); page[0:8] = b"B200COLL"
         struct.pack_into("<6I", page, 8, 2, 4242, 3, 8, 3, 1)
         struct.pack_into("<21Q", page, 64, 10, 0, 0, 2, 7, 1, 1 << 30, 0, 0, 4096, 512, 64, 0, 5, 0, 2, 13, 0, 0, 21, 0)
+        struct.pack_into("<3Q", page, 64 + 21 * 8, 4, 5, 6000)                  # point-to-point: sends, recvs, bytes
         struct.pack_into("<Q", page, 32, int(time.time()))                      # freshly updated
         (shm / "b200coll.4242.3").write_bytes(page)
         stale = bytearray(page); struct.pack_into("<6I", stale, 8, 2, 999, 0, 8, 0, 1); struct.pack_into("<Q", stale, 32, int(time.time()) - 7200)
@@ -223,6 +224,7 @@ def test_metrics_endpoint(native, tmp_path, service):
         assert 'b200coll_calls{pid="4242",rank="3",op="all_reduce"} 10' in body and 'b200coll_calls{pid="4242",rank="3",op="broadcast"} 7' in body
         assert f'b200coll_bytes{{pid="4242",rank="3",op="all_reduce"}} {1 << 30}' in body
         assert 'b200coll_algo_calls{pid="4242",rank="3",algo="nvls"} 13' in body
+        assert 'b200coll_p2p_calls{pid="4242",rank="3",dir="send"} 4' in body and 'b200coll_p2p_bytes{pid="4242",rank="3"} 6000' in body
         assert 'pid="999"' not in body
     finally:
         stub.server.stop(0)
