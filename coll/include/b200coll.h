@@ -110,11 +110,12 @@ typedef struct {
   uint64_t algo_calls[b200collNumAlgos];
   uint64_t kernel_launches;
   uint64_t staged_calls;     /* calls that went through the staging copy (unregistered buffers) */
+  uint64_t p2p_sends, p2p_recvs, p2p_bytes;   /* point-to-point operations and the bytes they moved (sent + received) */
 } b200collStats;
 
 /* Device-written watchdog record (host-pinned). code != 0 means the comm is poisoned. */
 typedef struct {
-  uint32_t code;             /* 0 ok, 1 barrier timeout, 2 LL data timeout */
+  uint32_t code;             /* 0 ok, 1 barrier timeout, 2 LL data timeout, 3 send/recv peer never showed up, 4 send/recv sizes differ */
   uint32_t rank, peer, block;
   uint32_t expected, observed;
   uint32_t op, reserved;
@@ -175,11 +176,25 @@ b200collResult_t b200collReduce(const void* send, void* recv, size_t count, cons
                                 b200collRedOp_t op, int root, b200collComm_t comm, b200collStream_t stream);
 b200collResult_t b200collBarrier(b200collComm_t comm, b200collStream_t stream);
 
+/* --- point to point (ncclSend / ncclRecv / ncclGroupStart / ncclGroupEnd). `bytes` of opaque data; buffers 16-byte aligned.
+ * A send pairs with the peer's recv of the same size, in call order per pair. Everything between GroupStart and GroupEnd
+ * (a ring step, a pipeline hand-over, any mix of peers) becomes ONE kernel per communicator, launched at GroupEnd on the
+ * stream of the group's first operation; outside a group each call is a group of its own and blocks the stream until the
+ * peer arrives (so "send then recv" on both sides of a pair deadlocks exactly as it does with NCCL: group them).
+ * The receiver's buffer is written directly over NVLink when it lies in the symmetric arena; otherwise through staging. */
+b200collResult_t b200collGroupStart(void);
+b200collResult_t b200collGroupEnd(void);
+b200collResult_t b200collSend(const void* buf, size_t bytes, int peer, b200collComm_t comm, b200collStream_t stream);
+b200collResult_t b200collRecv(void* buf, size_t bytes, int peer, b200collComm_t comm, b200collStream_t stream);
+
 /* --- tuner (libnccl-tuner.so analogue). */
 b200collAlgo_t b200collTunerPick(b200collOp_t op, size_t bytes, int nranks, int nvls_available);
 /* Force an algorithm for subsequent calls on this comm (b200collAlgoAuto restores the table). */
 b200collResult_t b200collCommSetAlgo(b200collComm_t comm, b200collAlgo_t algo);
 b200collResult_t b200collCommSetMaxCtas(b200collComm_t comm, int max_ctas);
+/* Receives into buffers outside the arena go through two staging windows per operation; this caps the window size (a multiple of
+ * 512 bytes; 0 = an equal share of the 64 MiB staging area). A private choice of the receiver: the sender follows what is posted. */
+b200collResult_t b200collCommSetP2pWindow(b200collComm_t comm, size_t bytes);
 /* Launch shape per kernel family: kind 0 = NVLS all-reduce/all-gather, 1 = P2P pull/push kernels, 2 = LL, 3 = NVLS reduce-scatter.
  * max_ctas <= 0 keeps the current cap; threads == 0 lets the library pick {128,256,512} by work size.
  * Defaults come from the 8xB200 sweep in profiles/ (NVLS wants few CTAs: 32 x 256 threads). */

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -223,6 +224,134 @@ static b200collResult_t ar_symmetric(b200collComm* c, b200collAlgo_t algo, const
     return b200collSuccess;
   });
 }
+
+
+// ------------------------------------------------------------------------------------------------ point to point
+namespace {
+
+struct PendingP2p { bool send; const void* sbuf; void* rbuf; size_t bytes; int peer; b200collComm* comm; cudaStream_t st; };
+thread_local int g_group_depth = 0;
+thread_local std::vector<PendingP2p> g_group;
+
+// CTAs per operation: a pure function of the message size and of settings every rank shares, so CTA j of a send always
+// meets CTA j of the matching recv. Virtual ranks share one GPU's SMs between all their kernels: keep them small.
+int p2p_blocks(const b200collComm* c, size_t bytes) {
+  static const int env_max = [] { const char* e = getenv("B200COLL_P2P_MAX_BLOCKS"); return e ? atoi(e) : 0; }();
+  int cap = c->loopback ? 2 : kP2pMaxBlocks;
+  if (env_max >= 1 && env_max <= kP2pMaxBlocks) cap = env_max;
+  const size_t want = (bytes + (128u << 10) - 1) / (128u << 10);
+  return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)cap));
+}
+
+// One kernel for `ops` (at most one send and one recv per peer, no self operations, no empty messages).
+b200collResult_t p2p_launch(b200collComm* c, const std::vector<PendingP2p>& ops, cudaStream_t st) {
+  P2pArgs a = {};
+  int nstaged = 0;
+  for (const PendingP2p& o : ops) if (!o.send && !b200collIsSymmetric(c, o.rbuf, o.bytes)) nstaged++;
+  // staged receives share the two staging halves: each gets an equal slice, cut into two windows
+  const size_t share = nstaged ? (2 * kStageHalfBytes / (size_t)nstaged) / 1024 * 1024 : 0;
+  const size_t window = c->p2p_window ? std::min(c->p2p_window, share / 2) : share / 2;
+  int blocks = 0, staged_seen = 0;
+  size_t moved = 0;
+  for (int pass = 0; pass < 2; pass++) {          // sends first, then recvs
+    for (const PendingP2p& o : ops) {
+      if (o.send != (pass == 0)) continue;
+      const int i = a.nops++;
+      a.first_block[i] = blocks;
+      blocks += p2p_blocks(c, o.bytes);
+      a.peer[i] = o.peer;
+      a.bytes[i] = o.bytes;
+      moved += o.bytes;
+      if (o.send) {
+        a.nsend++;
+        a.src[i] = static_cast<const char*>(o.sbuf);
+        c->stats.p2p_sends++;
+      } else {
+        a.dst[i] = static_cast<char*>(o.rbuf);
+        c->stats.p2p_recvs++;
+        if (b200collIsSymmetric(c, o.rbuf, o.bytes)) {
+          a.staged[i] = 0; a.win_off[i] = arena_off(c, o.rbuf); a.win_bytes[i] = o.bytes;
+        } else {
+          a.staged[i] = 1; a.win_off[i] = kOffStage + (size_t)staged_seen * share; a.win_bytes[i] = window;
+          staged_seen++;
+          c->stats.staged_calls++;
+        }
+      }
+    }
+  }
+  a.first_block[a.nops] = blocks;
+  c->stats.p2p_bytes += moved;
+  static const bool nvtx = [] { const char* e = getenv("B200COLL_NVTX"); return e && *e && *e != '0'; }();
+  if (nvtx || debug_level() >= 2) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "b200coll p2p %d send %d recv %zu B", a.nsend, a.nops - a.nsend, moved);
+    if (nvtx) nvtxMarkA(msg);
+    dbg(2, "rank %d: %s (%d CTAs, %d staged)", c->rank, msg, blocks, nstaged);
+  }
+  if ((c->stats_tick++ & 0xFF) == 0) stats_page_publish(c);
+  launch_k(k_p2p, blocks, kP2pThreads, st, c->dev, a, (uint32_t)b200collNumOps);
+  LAUNCH_CHECK(c);
+  return b200collSuccess;
+}
+
+b200collResult_t p2p_flush(std::vector<PendingP2p>& all) {
+  // per communicator, in order of first appearance
+  while (!all.empty()) {
+    b200collComm* c = all.front().comm;
+    const cudaStream_t st = all.front().st;
+    std::vector<PendingP2p> mine, rest;
+    for (const PendingP2p& o : all) (o.comm == c ? mine : rest).push_back(o);
+    all.swap(rest);
+    if (c->fault_host && *const_cast<volatile uint32_t*>(&c->fault_host->code) != 0) { set_last_error("communicator is poisoned by an earlier watchdog fault"); return b200collRemoteError; }
+    // a group may span communicators on several GPUs of this process (nccl-tests -g N): launch each on its own device
+    struct DeviceGuard {
+      int prev = -1; bool switched = false;
+      explicit DeviceGuard(int want) { if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess; }
+      ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    } guard(c->device);
+    // self operations: the i-th send to myself pairs with the i-th recv from myself
+    std::vector<PendingP2p> self_s, self_r, remote;
+    for (const PendingP2p& o : mine) {
+      if (o.bytes == 0) continue;
+      if (o.peer == c->rank) (o.send ? self_s : self_r).push_back(o); else remote.push_back(o);
+    }
+    if (self_s.size() != self_r.size()) { set_last_error("send/recv to self must come in matching pairs inside one group"); return b200collInvalidUsage; }
+    for (size_t i = 0; i < self_s.size(); i++) {
+      if (self_s[i].bytes != self_r[i].bytes) { set_last_error("send/recv to self: sizes differ"); return b200collInvalidArgument; }
+      if (self_s[i].sbuf == self_r[i].rbuf) continue;
+      cudaError_t e = cudaMemcpyAsync(self_r[i].rbuf, self_s[i].sbuf, self_s[i].bytes, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
+    }
+    // rounds: a kernel carries at most one send and one recv per peer (they share a mailbox); later ones wait for the next round
+    while (!remote.empty()) {
+      bool has_send[kMaxRanks] = {}, has_recv[kMaxRanks] = {};
+      std::vector<PendingP2p> now, later;
+      for (const PendingP2p& o : remote) {
+        bool* seen = o.send ? has_send : has_recv;
+        if (seen[o.peer]) later.push_back(o); else { seen[o.peer] = true; now.push_back(o); }
+      }
+      b200collResult_t rc = p2p_launch(c, now, st);
+      if (rc != b200collSuccess) return rc;
+      remote.swap(later);
+    }
+  }
+  return b200collSuccess;
+}
+
+b200collResult_t p2p_enqueue(bool send, const void* sbuf, void* rbuf, size_t bytes, int peer, b200collComm* c, cudaStream_t st) {
+  const void* buf = send ? sbuf : rbuf;
+  if (!c || (!buf && bytes)) { set_last_error("null argument"); return b200collInvalidArgument; }
+  if (peer < 0 || peer >= c->nranks) { set_last_error("send/recv peer out of range"); return b200collInvalidArgument; }
+  if (!aligned(buf, 16)) { set_last_error("send/recv buffers must be 16-byte aligned"); return b200collInvalidArgument; }
+  if (bytes >> kP2pValueBits) { set_last_error("send/recv message too large"); return b200collInvalidArgument; }
+  g_group.push_back(PendingP2p{send, sbuf, rbuf, bytes, peer, c, st});
+  if (g_group_depth > 0) return b200collSuccess;
+  std::vector<PendingP2p> ops;
+  ops.swap(g_group);
+  return p2p_flush(ops);
+}
+
+}  // namespace
 
 }  // namespace b200coll
 
@@ -547,6 +676,21 @@ b200collResult_t b200collReduce(const void* send, void* recv, size_t count, cons
     if (rc != b200collSuccess) return rc;
   }
   return b200collSuccess;
+}
+
+b200collResult_t b200collGroupStart(void) { g_group_depth++; return b200collSuccess; }
+b200collResult_t b200collGroupEnd(void) {
+  if (g_group_depth == 0) { set_last_error("group end without a matching group start"); return b200collInvalidUsage; }
+  if (--g_group_depth > 0) return b200collSuccess;
+  std::vector<PendingP2p> ops;
+  ops.swap(g_group);
+  return p2p_flush(ops);
+}
+b200collResult_t b200collSend(const void* buf, size_t bytes, int peer, b200collComm_t c, b200collStream_t stream) {
+  return p2p_enqueue(true, buf, nullptr, bytes, peer, c, static_cast<cudaStream_t>(stream));
+}
+b200collResult_t b200collRecv(void* buf, size_t bytes, int peer, b200collComm_t c, b200collStream_t stream) {
+  return p2p_enqueue(false, nullptr, buf, bytes, peer, c, static_cast<cudaStream_t>(stream));
 }
 
 b200collResult_t b200collBarrier(b200collComm_t c, b200collStream_t stream) {

@@ -614,6 +614,12 @@ b200collResult_t b200collCommSetMaxCtas(b200collComm_t c, int m) {
   return b200collSuccess;
 }
 
+b200collResult_t b200collCommSetP2pWindow(b200collComm_t c, size_t bytes) {
+  if (!c || (bytes != 0 && bytes < 512)) return b200collInvalidArgument;
+  c->p2p_window = bytes / 512 * 512;
+  return b200collSuccess;
+}
+
 b200collResult_t b200collCommSetLaunchShape(b200collComm_t c, int kind, int max_ctas, int threads) {
   if (!c || kind < 0 || kind > 3) return b200collInvalidArgument;
   if (threads != 0 && (threads < 32 || threads > 512 || threads % 32)) return b200collInvalidArgument;

@@ -33,8 +33,21 @@ constexpr size_t kOffHeap = kOffStage + 2 * kStageHalfBytes;   // user heap star
 constexpr uint32_t kLLSentinel = 0xFFFFFFFFu;           // a NaN pattern in f32/f16x2/bf16x2; payload words equal to it are rewritten
 constexpr uint32_t kLLSanitized = 0x7FFF7FFFu;          // still NaN in every supported type
 
+// Point-to-point mailboxes, in the zero-initialised part of the first megabyte that the flag matrix does not use.
+//   post: u64 [receiver rank][CTA][2 slots][2 words], written by the RECEIVER into the SENDER's arena ("write n bytes at this offset of mine")
+//   done: u32 [sender rank][CTA],                      written by the SENDER into the RECEIVER's arena ("chunk number seq has landed")
+constexpr int kP2pMaxBlocks = 16;                       // CTAs per send or recv operation
+constexpr size_t kOffP2pPost = 256 << 10;
+constexpr size_t kP2pPostBytes = (size_t)kMaxRanks * kP2pMaxBlocks * 2 * 2 * 8;
+constexpr size_t kOffP2pDone = kOffP2pPost + kP2pPostBytes;
+constexpr size_t kP2pDoneBytes = (size_t)kMaxRanks * kP2pMaxBlocks * 4;
+static_assert(kOffP2pDone + kP2pDoneBytes <= kOffLL, "p2p mailboxes must fit below the Lamport scratch");
+constexpr int kP2pTagBits = 24, kP2pValueBits = 40;     // each post word = (chunk sequence number mod 2^24) << 40 | value
+
 // local (non-symmetric) per-comm state words
-enum { kSeqBarrier = 0, kSeqLL = 1, kTicket = 2, kLLUsedLo0 = 3 /* 3,4,5 */, kLLUsedHi0 = 6 /* 6,7,8 */, kStateWords = 16 };
+enum { kSeqBarrier = 0, kSeqLL = 1, kTicket = 2, kLLUsedLo0 = 3 /* 3,4,5 */, kLLUsedHi0 = 6 /* 6,7,8 */,
+       kP2pSendSeq0 = 16 /* [peer][CTA]: chunks sent so far */, kP2pRecvSeq0 = kP2pSendSeq0 + kMaxRanks * kP2pMaxBlocks /* chunks received so far */,
+       kStateWords = kP2pRecvSeq0 + kMaxRanks * kP2pMaxBlocks };
 
 struct CommDev {
   int rank, nranks;
@@ -95,6 +108,23 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -71,28 +72,61 @@ bool map_op(ncclRedOp_t op, b200collRedOp_t* rop, float* scale) {
   return true;
 }
 
+size_t nccl_type_size(ncclDataType_t dt) {
+  switch ((int)dt) {
+    case ncclInt8: case ncclUint8: case 10 /* ncclFloat8e4m3 */: case 11 /* ncclFloat8e5m2 */: return 1;
+    case ncclFloat16: case ncclBfloat16: return 2;
+    case ncclInt32: case ncclUint32: case ncclFloat32: return 4;
+    case ncclInt64: case ncclUint64: case ncclFloat64: return 8;
+    default: return 0;
+  }
+}
+
+// nccl-tests' alltoall (and most MoE glue) is a group of one send and one recv per peer, equal counts, contiguous blocks: that is
+// the library's fused all-to-all kernel. Every rank of such a group sees the same shape, so the decision is the same everywhere.
+// B200COLL_SHIM_FUSE_ALLTOALL=0 turns the shortcut off (needed only if ranks mix this shape with other group shapes in one step).
+bool group_is_alltoall(const std::vector<P2pOp>& ops, const void** send0, void** recv0, size_t* count, b200collDataType_t* dt) {
+  static const bool fuse = [] { const char* e = getenv("B200COLL_SHIM_FUSE_ALLTOALL"); return !(e && *e == '0'); }();
+  if (!fuse || ops.empty()) return false;
+  ShimComm* c = ops[0].comm;
+  const int n = c->nranks;
+  if ((int)ops.size() != 2 * n || !map_dt(ops[0].dt, dt)) return false;
+  std::vector<const P2pOp*> sends(n, nullptr), recvs(n, nullptr);
+  for (const P2pOp& o : ops) {
+    if (o.comm != c || o.peer < 0 || o.peer >= n || o.dt != ops[0].dt || o.stream != ops[0].stream) return false;
+    const P2pOp*& slot = (o.send ? sends : recvs)[o.peer];
+    if (slot) return false;
+    slot = &o;
+  }
+  const size_t cnt = ops[0].count, esz = b200collTypeSize(*dt);
+  if (cnt == 0 || (cnt * esz) % 16 != 0) return false;
+  for (int p = 0; p < n; p++) {
+    if (!sends[p] || !recvs[p] || sends[p]->count != cnt || recvs[p]->count != cnt) return false;
+    if ((const char*)sends[p]->sbuf != (const char*)sends[0]->sbuf + (size_t)p * cnt * esz) return false;
+    if ((char*)recvs[p]->rbuf != (char*)recvs[0]->rbuf + (size_t)p * cnt * esz) return false;
+  }
+  *send0 = sends[0]->sbuf; *recv0 = recvs[0]->rbuf; *count = cnt;
+  return true;
+}
+
 ncclResult_t flush_group() {
   std::vector<P2pOp> ops;
   ops.swap(g_group_ops);
   if (ops.empty()) return ncclSuccess;
-  // The only grouped pattern nccl-tests issues is alltoall: one send and one recv per peer, equal counts, contiguous blocks.
-  ShimComm* c = ops[0].comm;
-  const int n = c->nranks;
-  std::vector<const P2pOp*> sends(n, nullptr), recvs(n, nullptr);
+  const void* s0; void* r0; size_t count; b200collDataType_t dt;
+  if (group_is_alltoall(ops, &s0, &r0, &count, &dt)) {
+    b200collEpilogue ep{dt, dt, 1.0f};
+    return map_rc(b200collAllToAll(s0, r0, count, &ep, ops[0].comm->comm, ops[0].stream));
+  }
+  // anything else (ring steps, pipeline hand-overs, irregular exchanges): the library's point-to-point kernel, one launch per communicator
+  b200collResult_t rc = b200collGroupStart();
   for (const P2pOp& o : ops) {
-    if (o.comm != c || o.peer < 0 || o.peer >= n) return ncclInvalidUsage;
-    (o.send ? sends : recvs)[o.peer] = &o;
+    if (rc != b200collSuccess) break;
+    const size_t bytes = o.count * nccl_type_size(o.dt);
+    rc = o.send ? b200collSend(o.sbuf, bytes, o.peer, o.comm->comm, o.stream) : b200collRecv(o.rbuf, bytes, o.peer, o.comm->comm, o.stream);
   }
-  b200collDataType_t dt;
-  if ((int)ops.size() != 2 * n || !map_dt(ops[0].dt, &dt)) return ncclInvalidUsage;
-  const size_t count = ops[0].count, esz = b200collTypeSize(dt);
-  for (int p = 0; p < n; p++) {
-    if (!sends[p] || !recvs[p] || sends[p]->count != count || recvs[p]->count != count) return ncclInvalidUsage;
-    if ((const char*)sends[p]->sbuf != (const char*)sends[0]->sbuf + (size_t)p * count * esz) return ncclInvalidUsage;
-    if ((char*)recvs[p]->rbuf != (char*)recvs[0]->rbuf + (size_t)p * count * esz) return ncclInvalidUsage;
-  }
-  b200collEpilogue ep{dt, dt, 1.0f};
-  return map_rc(b200collAllToAll(sends[0]->sbuf, recvs[0]->rbuf, count, &ep, c->comm, ops[0].stream));
+  const b200collResult_t rc_end = b200collGroupEnd();
+  return map_rc(rc != b200collSuccess ? rc : rc_end);
 }
 
 }  // namespace
@@ -252,16 +286,14 @@ ncclResult_t ncclGroupEnd(void) {
   return flush_group();
 }
 ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm, cudaStream_t stream) {
-  if (!comm) return ncclInvalidArgument;
-  if (g_group_depth == 0) return ncclInvalidUsage;   // lone send/recv would need a matching call on the peer: only grouped all-to-all is mapped
+  if (!comm || nccl_type_size(dt) == 0) return ncclInvalidArgument;
   g_group_ops.push_back(P2pOp{true, buf, nullptr, count, dt, peer, reinterpret_cast<ShimComm*>(comm), stream});
-  return ncclSuccess;
+  return g_group_depth > 0 ? ncclSuccess : flush_group();      // outside a group: a group of one (blocks the stream until the peer's recv)
 }
 ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm, cudaStream_t stream) {
-  if (!comm) return ncclInvalidArgument;
-  if (g_group_depth == 0) return ncclInvalidUsage;
+  if (!comm || nccl_type_size(dt) == 0) return ncclInvalidArgument;
   g_group_ops.push_back(P2pOp{false, nullptr, buf, count, dt, peer, reinterpret_cast<ShimComm*>(comm), stream});
-  return ncclSuccess;
+  return g_group_depth > 0 ? ncclSuccess : flush_group();
 }
 
 }  // extern "C"

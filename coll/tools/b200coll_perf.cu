@@ -116,6 +116,7 @@ struct RankCtx { int rank, nranks; b200collComm_t comm; int dev; };
 static float expected(const Opts& o, int rank, int n, size_t e, size_t count) {
   if (o.op == "all_reduce" || o.op == "reduce") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, e); return s * o.scale; }
   if (o.op == "broadcast") return gen(kRoot, e) * o.scale;
+  if (o.op == "sendrecv") return gen((rank + n - 1) % n, e);      // ring step: my output is my left neighbour's input, untouched
   if (o.op == "all_gather") { int src = (int)(e / count); return gen(src, e % count) * o.scale; }
   if (o.op == "reduce_scatter") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, (size_t)rank * count + e); return s * o.scale; }
   /* alltoall */ { int src = (int)(e / count); return gen(src, (size_t)rank * count + e % count) * o.scale; }
@@ -131,8 +132,9 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
   }
   if (o.max_ctas > 0) CC(b200collCommSetMaxCtas(ctx.comm, o.max_ctas));
   const size_t is = b200collTypeSize(o.in_dt), os = b200collTypeSize(o.out_dt);
-  const bool is_bc = o.op == "broadcast", is_rd = o.op == "reduce";
-  const bool is_ar = o.op == "all_reduce" || is_bc || is_rd;      // "whole message" geometry: count elements in, count out
+  const bool is_bc = o.op == "broadcast", is_rd = o.op == "reduce", is_sr = o.op == "sendrecv";
+  if (is_sr && (o.in_dt != o.out_dt || o.scale != 1.0f)) { fprintf(stderr, "sendrecv moves opaque bytes: --in and --out must match and --scale must be 1\n"); return 2; }
+  const bool is_ar = o.op == "all_reduce" || is_bc || is_rd || is_sr;      // "whole message" geometry: count elements in, count out
   const bool is_ag = o.op == "all_gather", is_rs = o.op == "reduce_scatter";
   if (!is_ar && !is_ag && !is_rs && o.op != "alltoall") { fprintf(stderr, "unknown --op %s\n", o.op.c_str()); return 2; }
   // nccl-tests convention: "size" is the larger of the two buffers in bytes of the input type
@@ -176,7 +178,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
     const char* algo_used = "?";
     for (int ip = 0; ip < 2; ip++) {
       if ((ip == 0 && o.inplace == 1) || (ip == 1 && o.inplace == 0)) continue;
-      if (ip == 1 && (o.op == "alltoall" || is != os)) continue;
+      if (ip == 1 && (o.op == "alltoall" || is_sr || is != os)) continue;
       auto sbuf = [&](int slot) -> char* {
         char* base = ip ? (char*)recv : (char*)send;
         size_t off = (size_t)slot * slot_b;
@@ -189,7 +191,13 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
         return (char*)recv + off;
       };
       auto launch = [&](int slot) {
-        if (is_bc) CC(b200collBroadcast(sbuf(slot), rbuf(slot), count, &ep, kRoot, ctx.comm, st));
+        if (is_sr) {      // nccl-tests sendrecv_perf: one grouped send to the right neighbour and recv from the left one
+          CC(b200collGroupStart());
+          CC(b200collSend(sbuf(slot), count * is, (rank + 1) % n, ctx.comm, st));
+          CC(b200collRecv(rbuf(slot), count * is, (rank + n - 1) % n, ctx.comm, st));
+          CC(b200collGroupEnd());
+        }
+        else if (is_bc) CC(b200collBroadcast(sbuf(slot), rbuf(slot), count, &ep, kRoot, ctx.comm, st));
         else if (is_rd) CC(b200collReduce(sbuf(slot), rbuf(slot), count, &ep, b200collSum, kRoot, ctx.comm, st));
         else if (is_ar) CC(b200collAllReduce(sbuf(slot), rbuf(slot), count, &ep, b200collSum, ctx.comm, st));
         else if (is_ag) CC(b200collAllGather(sbuf(slot), rbuf(slot), count, &ep, ctx.comm, st));
@@ -243,8 +251,9 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
     if (rank == 0) {
       size_t tb = is_ar ? count * is : count * is * n;   // nccl-tests "size"
       b200collOp_t opid = is_bc ? b200collOpBroadcast : is_rd ? b200collOpReduce : is_ar ? b200collOpAllReduce : is_ag ? b200collOpAllGather : is_rs ? b200collOpReduceScatter : b200collOpAllToAll;
-      if (o.algo == "auto") algo_used = b200collAlgoName(b200collTunerPick(opid, is_ar ? count * is : count * is, n, info.nvls)); else algo_used = o.algo.c_str();
-      const double factor = (is_bc || is_rd) ? 1.0 : is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
+      if (is_sr) algo_used = "p2p";
+      else if (o.algo == "auto") algo_used = b200collAlgoName(b200collTunerPick(opid, is_ar ? count * is : count * is, n, info.nvls)); else algo_used = o.algo.c_str();
+      const double factor = (is_bc || is_rd || is_sr) ? 1.0 : is_ar ? 2.0 * (n - 1) / n : (double)(n - 1) / n;
       double ab[2], bb[2];
       for (int ip = 0; ip < 2; ip++) { ab[ip] = res_us[ip] > 0 ? tb / res_us[ip] / 1e3 : 0; bb[ip] = n > 1 ? ab[ip] * factor : ab[ip]; if (res_us[ip] > 0) { busbw_sum += bb[ip]; busbw_n++; } }
       if (!o.shapes.empty()) printf("[k%d c%d t%d] ", o.shapes[si].kind, o.shapes[si].ctas, o.shapes[si].threads);
@@ -278,7 +287,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
 static const char* op_from_argv0(const char* argv0) {
   const char* base = strrchr(argv0, '/'); base = base ? base + 1 : argv0;
   static const struct { const char* name; const char* op; } kNames[] = {{"all_reduce_perf", "all_reduce"}, {"all_gather_perf", "all_gather"}, {"reduce_scatter_perf", "reduce_scatter"},
-                                                                        {"alltoall_perf", "alltoall"}, {"broadcast_perf", "broadcast"}, {"reduce_perf", "reduce"}};
+                                                                        {"alltoall_perf", "alltoall"}, {"broadcast_perf", "broadcast"}, {"reduce_perf", "reduce"}, {"sendrecv_perf", "sendrecv"}};
   for (auto& k : kNames) if (!strcmp(base, k.name)) return k.op;
   return nullptr;
 }
@@ -342,7 +351,7 @@ int main(int argc, char** argv) {
     }
     else if (a == "--selfcheck") { char buf[4096]; b200collResult_t r = b200collSelfCheck(buf, sizeof(buf)); fputs(buf, stdout); return r == b200collSuccess ? 0 : 1; }
     else if (a == "-h" || a == "--help") {
-      puts("b200coll_perf (also all_reduce_perf, all_gather_perf, reduce_scatter_perf, alltoall_perf, broadcast_perf, reduce_perf): nccl-tests style sweep on libb200coll\n"
+      puts("b200coll_perf (also all_reduce_perf, all_gather_perf, reduce_scatter_perf, alltoall_perf, broadcast_perf, reduce_perf, sendrecv_perf): nccl-tests style sweep on libb200coll\n"
            "  --op NAME                 collective (implied by the name the binary is called by)\n"
            "  -b/-e SIZE -f N           sweep from -b to -e bytes multiplying by -f (1K, 64M, 1G ...)\n"
            "  -g N | --ranks N | --devs a,b,..   ranks in this process (threads); --procs forks one process per rank instead\n"

@@ -53,7 +53,7 @@ class CommInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("calls", C.c_uint64 * 6), ("bytes", C.c_uint64 * 6), ("algo_calls", C.c_uint64 * 7), ("kernel_launches", C.c_uint64),
-                ("staged_calls", C.c_uint64)]
+                ("staged_calls", C.c_uint64), ("p2p_sends", C.c_uint64), ("p2p_recvs", C.c_uint64), ("p2p_bytes", C.c_uint64)]
 
 
 class Fault(C.Structure):
@@ -119,10 +119,14 @@ def load() -> C.CDLL:
     L.b200collBroadcast.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
     L.b200collReduce.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, ci, vp, vp]
     L.b200collBarrier.argtypes = [vp, vp]
+    L.b200collGroupStart.argtypes = []; L.b200collGroupEnd.argtypes = []
+    L.b200collSend.argtypes = [vp, sz, ci, vp, vp]
+    L.b200collRecv.argtypes = [vp, sz, ci, vp, vp]
     L.b200collTunerPick.argtypes = [ci, sz, ci, ci]; L.b200collTunerPick.restype = ci
     L.b200collCommSetAlgo.argtypes = [vp, ci]
     L.b200collCommSetMaxCtas.argtypes = [vp, ci]
     L.b200collCommSetLaunchShape.argtypes = [vp, ci, ci, ci]
+    L.b200collCommSetP2pWindow.argtypes = [vp, sz]
     L.b200collAlgoName.argtypes = [ci]; L.b200collAlgoName.restype = C.c_char_p
     L.b200collTypeSize.argtypes = [ci]; L.b200collTypeSize.restype = sz
     L.b200collSelfCheck.argtypes = [C.c_char_p, sz]
@@ -133,6 +137,22 @@ def _check(rc: int, what: str) -> None:
     if rc != SUCCESS:
         L = load()
         raise B200CollError(rc, f"{what}: {L.b200collGetErrorString(rc).decode()}", L.b200collGetLastError().decode())
+
+
+class group:
+    """`with coll.group(): comm.send(...); comm.recv(...)`: every send / recv issued inside (by this thread, on any communicator)
+    becomes one kernel per communicator at exit (ncclGroupStart / ncclGroupEnd). Needed whenever a rank both sends and receives in
+    one step: outside a group each call waits for its peer before the next one is launched."""
+
+    def __enter__(self):
+        _check(load().b200collGroupStart(), "GroupStart")
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        rc = load().b200collGroupEnd()
+        if exc_type is None:
+            _check(rc, "GroupEnd")
+        return False
 
 
 def tuner_pick(op: int, nbytes: int, nranks: int, nvls: bool) -> str:
@@ -341,6 +361,16 @@ class Comm:
         _check(load().b200collReduce(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), op, root, self._h, self._stream(stream)), "Reduce")
         return dst
 
+    def send(self, src, peer: int, stream=None) -> None:
+        """Send the bytes of (contiguous) `src` to rank `peer` (ncclSend). Pairs with the peer's recv of the same size, in call order.
+        Outside `group()` the call blocks the stream until the peer's recv runs."""
+        _check(load().b200collSend(C.c_void_p(src.data_ptr()), src.numel() * src.element_size(), peer, self._h, self._stream(stream)), "Send")
+
+    def recv(self, dst, peer: int, stream=None):
+        """Receive into (contiguous) `dst` from rank `peer` (ncclRecv): written over NVLink in place when dst is an arena tensor, else staged."""
+        _check(load().b200collRecv(C.c_void_p(dst.data_ptr()), dst.numel() * dst.element_size(), peer, self._h, self._stream(stream)), "Recv")
+        return dst
+
     def barrier(self, stream=None) -> None:
         _check(load().b200collBarrier(self._h, self._stream(stream)), "Barrier")
 
@@ -354,6 +384,10 @@ class Comm:
     def set_max_ctas(self, n: int) -> None:
         _check(load().b200collCommSetMaxCtas(self._h, n), "CommSetMaxCtas")
 
+    def set_p2p_window(self, nbytes: int) -> None:
+        """Staging-window size for receives into tensors outside the arena (0 = automatic)."""
+        _check(load().b200collCommSetP2pWindow(self._h, nbytes), "CommSetP2pWindow")
+
     def set_launch_shape(self, kind: str, max_ctas: int = 0, threads: int = 0) -> None:
         _check(load().b200collCommSetLaunchShape(self._h, {"nvls": 0, "p2p": 1, "ll": 2, "nvls_rs": 3}[kind], max_ctas, threads), "CommSetLaunchShape")
 
@@ -361,7 +395,8 @@ class Comm:
         s = Stats()
         _check(load().b200collCommStatsGet(self._h, C.byref(s)), "CommStatsGet")
         return {"calls": list(s.calls), "bytes": list(s.bytes), "algo_calls": dict(zip(ALGO_NAMES, s.algo_calls)),
-                "kernel_launches": s.kernel_launches, "staged_calls": s.staged_calls}
+                "kernel_launches": s.kernel_launches, "staged_calls": s.staged_calls,
+                "p2p_sends": s.p2p_sends, "p2p_recvs": s.p2p_recvs, "p2p_bytes": s.p2p_bytes}
 
     def check_async_error(self) -> None:
         f = Fault()

@@ -21,16 +21,18 @@ import time
 from dataclasses import dataclass, field
 
 OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce")   # index = b200collOp_t
+P2P_OPS = ("sendrecv",)     # nccl-tests sendrecv_perf: a ring step (send right, receive from the left) through the point-to-point kernel
+ALL_OPS = OPS + P2P_OPS
 ROOT = 0   # rooted ops are measured from rank 0, as nccl-tests does by default
-FULL_MESSAGE_OPS = ("all_reduce", "broadcast", "reduce")   # count = whole message; the others split it over the ranks
+FULL_MESSAGE_OPS = ("all_reduce", "broadcast", "reduce", "sendrecv")   # count = whole message; the others split it over the ranks
 WINDOW = 192 << 20
 
 
 def bus_factor(op: str, n: int) -> float:
     if n <= 1:
         return 1.0   # nccl-tests prints busbw 0 for one rank; we report algbw there and say so
-    if op in ("broadcast", "reduce"):
-        return 1.0   # nccl-tests: rooted ops move the whole message over one rank's links, busbw = algbw
+    if op in ("broadcast", "reduce", "sendrecv"):
+        return 1.0   # nccl-tests: rooted ops (and a ring step) move the whole message over one rank's links, busbw = algbw
     return 2.0 * (n - 1) / n if op == "all_reduce" else (n - 1) / n
 
 
@@ -121,12 +123,20 @@ class OursBackend:
         self.version = f"libb200coll {self.L.b200collGetVersion()} nvls={int(self.nvls)}"
 
     def algo(self, op: str, nbytes_per_rank: int) -> str:
+        if op in P2P_OPS:
+            return "p2p"
         opid = OPS.index(op)
         return self.coll.tuner_pick(opid, nbytes_per_rank, self.comm.nranks, self.nvls)
 
     def launch(self, op: str, send_ptr: int, recv_ptr: int, count: int, stream: int) -> None:
         L, ep = self.L, C.byref(self.ep)
-        if op == "all_reduce":
+        if op == "sendrecv":
+            n, r, nbytes = self.comm.nranks, self.comm.rank, count * self.send.element_size()
+            rc = L.b200collGroupStart()
+            rc = rc or L.b200collSend(send_ptr, nbytes, (r + 1) % n, self.h, stream)
+            rc = rc or L.b200collRecv(recv_ptr, nbytes, (r - 1) % n, self.h, stream)
+            rc = L.b200collGroupEnd() or rc
+        elif op == "all_reduce":
             rc = L.b200collAllReduce(send_ptr, recv_ptr, count, ep, 0, self.h, stream)
         elif op == "all_gather":
             rc = L.b200collAllGather(send_ptr, recv_ptr, count, ep, self.h, stream)
@@ -191,7 +201,9 @@ class NcclBackend:
 
     def launch(self, op: str, send_ptr: int, recv_ptr: int, count: int, stream: int) -> None:
         c = self.comm
-        if op == "all_reduce":
+        if op == "sendrecv":
+            c.send_recv(send_ptr, (c.rank + 1) % c.nranks, recv_ptr, (c.rank - 1) % c.nranks, count, self.dt, stream)
+        elif op == "all_reduce":
             c.all_reduce(send_ptr, recv_ptr, count, self.dt, stream)
         elif op == "all_gather":
             c.all_gather(send_ptr, recv_ptr, count, self.dt, stream)
@@ -251,6 +263,8 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
         want = sum(gen(r, idx) for r in range(n))
     elif op == "broadcast":
         want = gen(ROOT, idx)
+    elif op == "sendrecv":
+        want = gen((rank - 1) % n, idx)
     elif op == "reduce":                                   # only the root's recv is defined
         want = sum(gen(r, idx) for r in range(n)) if rank == ROOT else torch.full_like(got, 77.0)
     elif op == "all_gather":
@@ -302,7 +316,7 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
         row = Row(total, count, backend.algo(op, per_rank_bytes), in_bytes=in_elems * itemsize)
         sbase, rbase = backend.send.data_ptr(), backend.recv.data_ptr()
         for ip in placements:
-            if ip == 1 and (op == "alltoall" or n == 1):
+            if ip == 1 and (op in ("alltoall", "sendrecv") or n == 1):
                 continue
 
             def ptrs(slot: int):

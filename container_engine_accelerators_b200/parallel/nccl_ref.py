@@ -100,6 +100,13 @@ class NcclComm:
     def reduce(self, send: int, recv: int, count: int, dtype: int, root: int, stream: int) -> None:
         self._ck(self.lib.ncclReduce(send, recv, count, dtype, NCCL_SUM, root, self.comm, stream), "ncclReduce")
 
+    def send_recv(self, send: int, to: int, recv: int, frm: int, count: int, dtype: int, stream: int) -> None:
+        # nccl-tests' sendrecv: one grouped send and recv (a ring step)
+        self._ck(self.lib.ncclGroupStart(), "ncclGroupStart")
+        self._ck(self.lib.ncclSend(send, count, dtype, to, self.comm, stream), "ncclSend")
+        self._ck(self.lib.ncclRecv(recv, count, dtype, frm, self.comm, stream), "ncclRecv")
+        self._ck(self.lib.ncclGroupEnd(), "ncclGroupEnd")
+
     def all_to_all(self, send: int, recv: int, count: int, dtype: int, elem_size: int, stream: int) -> None:
         # nccl-tests' alltoall: grouped ncclSend/ncclRecv to every peer
         self._ck(self.lib.ncclGroupStart(), "ncclGroupStart")

@@ -9,7 +9,8 @@ tests use for Python process groups). CUDA tensors that the library can take as 
 bf16, sum or avg — go straight to the collective kernels **on the caller's current stream**, so ordering with the surrounding compute
 is plain stream order and `Work.wait()` has nothing to wait for (NCCL's side stream + event dance is not needed). Tensors allocated
 with `pg.empty()` live in the symmetric arena and take the zero-copy / NVLS paths; any other device tensor is staged by the library.
-Everything else (CPU tensors, integer reductions, min/max/product, point-to-point, gather/scatter, odd shapes) is executed by an
+Point-to-point on CUDA tensors uses the library's grouped send / recv kernel (queued until the first wait, so an isend + irecv pair
+is one launch). Everything else (CPU tensors, integer reductions, min/max/product, gather/scatter, odd shapes) is executed by an
 internal Gloo group over host copies: slow but correct, which keeps DDP's bookkeeping collectives and object broadcasts working.
 
 Status: the fallback and dispatch logic is exercised on CPU (tests/test_process_group.py); the CUDA fast paths reuse the calls the GPU
@@ -62,6 +63,18 @@ class _Work(dist._Work):
         return self._future
 
 
+class _P2pWork(_Work):
+    """Handle of a queued send / recv: waiting launches everything queued so far as one grouped kernel (stream-ordered afterwards)."""
+
+    def __init__(self, pg, result):
+        super().__init__(result)
+        self._pg = pg
+
+    def wait(self, timeout: Optional[timedelta] = None) -> bool:
+        self._pg._flush_p2p()
+        return True
+
+
 def _fast(t: torch.Tensor) -> bool:
     return t.is_cuda and t.is_contiguous() and t.dtype in _FAST_DTYPES and t.data_ptr() % 16 == 0 and t.numel() > 0
 
@@ -94,6 +107,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
         self._scratch: dict = {}          # (nbytes class) -> symmetric uint8 tensor, for all-to-all-v receive staging
         self._last_stream = None          # stream and completion event of the previous device collective (see _ordered)
         self._last_event = None
+        self._pending: list = []          # queued point-to-point operations: (kind, tensor, peer), launched as one group
         self.fast_calls = 0               # collectives that ran on libb200coll
         self.fallback_calls = 0           # collectives that ran on the Gloo group
 
@@ -124,6 +138,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
 
     def shutdown(self) -> None:
         if self._comm is not None:
+            self._flush_p2p()
             torch.cuda.synchronize()
             self._scratch.clear()
             self._comm.destroy()
@@ -143,6 +158,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
             pg, cur = self.pg, torch.cuda.current_stream()
             if pg._last_stream is not None and pg._last_stream != cur and pg._last_event is not None:
                 cur.wait_event(pg._last_event)
+            pg._launch_pending()          # queued sends / recvs keep their place in the order of calls
             return cur
 
         def __exit__(self, *exc):
@@ -397,14 +413,55 @@ class B200CollProcessGroup(dist.ProcessGroup):
             o.copy_(h)
         return _Work(output_tensors)
 
+    # ------------------------------------------------------------------ point to point
+    # CUDA tensors go through the library's send / recv kernel (tags are ignored, as ProcessGroupNCCL does: messages of a pair match in
+    # call order). The decision "library or Gloo" uses only what both sides of a message share (device type), never layout: a tensor
+    # that is not contiguous or not 16-byte aligned travels through a temporary. Operations are queued and launched together — as ONE
+    # grouped kernel — by the first `wait()` (blocking `dist.send` / `dist.recv` wait at once) or by the next collective, so
+    # `isend(right); irecv(left); wait both` cannot deadlock the way two separately launched, stream-blocking kernels would, also
+    # through `batch_isend_irecv` (which, for a Python process group, just calls isend / irecv in a loop).
     def send(self, tensors, dst_rank, tag=0):
+        if all(t.is_cuda for t in tensors):
+            self._pending.extend(("send", t, dst_rank) for t in tensors)
+            self.fast_calls += 1
+            return _P2pWork(self, tensors)
         self.fallback_calls += 1
         self.gloo.send([t.detach().cpu() if t.is_cuda else t for t in tensors], dst_rank, tag).wait()
         return _Work(tensors)
 
     def recv(self, tensors, src_rank, tag=0):
+        if all(t.is_cuda for t in tensors):
+            self._pending.extend(("recv", t, src_rank) for t in tensors)
+            self.fast_calls += 1
+            return _P2pWork(self, tensors)
         self._via_gloo(tensors, lambda h: self.gloo.recv(h, src_rank, tag))
         return _Work(tensors)
+
+    def _flush_p2p(self) -> None:
+        if self._pending:
+            with self._ordered(self):       # entering the ordered section launches what is queued
+                pass
+
+    def _launch_pending(self) -> None:
+        ops, self._pending = self._pending, []
+        if not ops:
+            return
+        comm, copy_out = self.comm, []
+        direct = lambda t: t.is_contiguous() and t.data_ptr() % 16 == 0
+        with coll.group():
+            for kind, t, peer in ops:
+                if t.numel() == 0:
+                    continue
+                if kind == "send":
+                    comm.send(t if direct(t) else t.contiguous().clone(), peer)      # clone(): a fresh allocation is aligned
+                elif direct(t):
+                    comm.recv(t, peer)
+                else:
+                    tmp = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+                    comm.recv(tmp, peer)
+                    copy_out.append((t, tmp))
+        for t, tmp in copy_out:
+            t.copy_(tmp)
 
 
 def _create(store, rank, size, timeout):

@@ -481,3 +481,187 @@ def test_nccl_api_shim_collectives(torch_cuda, coll_lib):
         torch.cuda.synchronize()
         for c in comms:
             L.ncclCommDestroy(c)
+
+
+# ------------------------------------------------------------------------------------------------- point to point
+_P2P_GATE = pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="the send/recv kernel has not run on hardware yet; set B200_RUN_UNVALIDATED=1")
+
+
+def _pattern(torch, nbytes, seed):
+    return ((torch.arange(nbytes, device="cuda", dtype=torch.int64) * (2 * seed + 7) + seed * 31) % 251).to(torch.uint8)
+
+
+@_P2P_GATE
+@pytest.mark.parametrize("group", [2, 4], indirect=True)
+@pytest.mark.parametrize("nbytes", [16, 1003, (1 << 20) + 48, (3 << 20) + 5])
+@pytest.mark.parametrize("arena_recv", [True, False])
+def test_send_recv_ring_step(torch_cuda, coll_mod, group, nbytes, arena_recv):
+    """Grouped send to the right / recv from the left (nccl-tests sendrecv): bytes arrive untouched, for sizes that are not a multiple
+    of a vector, in place in the arena or through staging windows smaller than the message; repeated so sequence numbers advance."""
+    torch = torch_cuda
+    comms, streams = group
+    n = len(comms)
+    for c in comms:
+        c.set_p2p_window(1 << 20)                   # 3 MiB + 5 B through 1 MiB windows: four chunks, both windows reused
+    srcs = [c.empty(nbytes, torch.uint8) for c in comms]
+    dsts = [c.empty(nbytes, torch.uint8) if arena_recv else torch.empty(nbytes, dtype=torch.uint8, device="cuda") for c in comms]
+    for rep in range(3):
+        for r in range(n):
+            srcs[r].copy_(_pattern(torch, nbytes, r + 10 * rep))
+            dsts[r].fill_(0xEE)
+        torch.cuda.synchronize()
+        with coll_mod.group():
+            for r, c in enumerate(comms):
+                c.send(srcs[r], (r + 1) % n, stream=streams[r])
+                c.recv(dsts[r], (r - 1) % n, stream=streams[r])
+        torch.cuda.synchronize()
+        for r, c in enumerate(comms):
+            c.check_async_error()
+            assert torch.equal(dsts[r], srcs[(r - 1) % n]), (rep, r)
+    st = comms[0].stats()
+    assert st["p2p_sends"] == 3 and st["p2p_recvs"] == 3 and st["p2p_bytes"] == 6 * nbytes
+    assert (st["staged_calls"] > 0) == (not arena_recv)
+
+
+@_P2P_GATE
+@pytest.mark.parametrize("group", [2], indirect=True)
+def test_send_recv_pipeline_handover_and_self(torch_cuda, coll_mod, group):
+    """Ungrouped calls: rank 0 sends, rank 1 receives (each blocks its own stream until the other arrives); then the reverse direction
+    with another size; send/recv to self inside a group is a local copy."""
+    torch = torch_cuda
+    comms, streams = group
+    a = comms[0].empty(1 << 16, torch.float32); a.copy_(torch.arange(1 << 16, device="cuda", dtype=torch.float32))
+    b = comms[1].empty(1 << 16, torch.float32); b.zero_()
+    comms[0].send(a, 1, stream=streams[0])
+    comms[1].recv(b, 0, stream=streams[1])
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    back = torch.empty(100, dtype=torch.bfloat16, device="cuda")            # 200 bytes, not in the arena
+    comms[1].send(b[:50].view(torch.bfloat16), 0, stream=streams[1])
+    comms[0].recv(back, 1, stream=streams[0])
+    torch.cuda.synchronize()
+    assert torch.equal(back.view(torch.float32), a[:50])
+    mine = torch.empty(1 << 10, dtype=torch.float32, device="cuda")
+    with coll_mod.group():
+        comms[0].send(a[:1 << 10], 0, stream=streams[0])
+        comms[0].recv(mine, 0, stream=streams[0])
+    torch.cuda.synchronize()
+    assert torch.equal(mine, a[:1 << 10])
+    for c in comms:
+        c.check_async_error()
+
+
+@_P2P_GATE
+@pytest.mark.parametrize("group", [4], indirect=True)
+def test_send_recv_irregular_group_and_graph_replay(torch_cuda, coll_mod, group):
+    """One group with different sizes per pair and two messages for one pair (second one runs in a follow-up kernel); then a captured
+    ring step replayed five times."""
+    torch = torch_cuda
+    comms, streams = group
+    n = len(comms)
+    size = lambda s, d: 4096 * (1 + s) + 16 * d
+    out = {(s, d): comms[s].empty(size(s, d), torch.uint8) for s in range(n) for d in range(n) if s != d}
+    inn = {(s, d): comms[d].empty(size(s, d), torch.uint8) for s in range(n) for d in range(n) if s != d}
+    for (s, d), t in out.items():
+        t.copy_(_pattern(torch, t.numel(), 17 * s + d))
+    extra_out = comms[0].empty(777, torch.uint8); extra_out.copy_(_pattern(torch, 777, 99))
+    extra_in = torch.zeros(777, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    with coll_mod.group():
+        for r, c in enumerate(comms):
+            for p in range(n):
+                if p != r:
+                    c.send(out[(r, p)], p, stream=streams[r])
+                    c.recv(inn[(p, r)], p, stream=streams[r])
+        comms[0].send(extra_out, 1, stream=streams[0])                      # a second message 0 -> 1 in the same group
+        comms[1].recv(extra_in, 0, stream=streams[1])
+    torch.cuda.synchronize()
+    for k in out:
+        assert torch.equal(out[k], inn[k]), k
+    assert torch.equal(extra_in, extra_out)
+    # graph replay: sequence numbers live in device memory
+    count = 1 << 14
+    srcs = [c.empty(count, torch.float32) for c in comms]
+    dsts = [c.empty(count, torch.float32) for c in comms]
+    graphs = []
+    for r, c in enumerate(comms):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=streams[r]):
+            with coll_mod.group():
+                c.send(srcs[r], (r + 1) % n, stream=streams[r])
+                c.recv(dsts[r], (r - 1) % n, stream=streams[r])
+        graphs.append(g)
+    for it in range(5):
+        for r in range(n):
+            srcs[r].fill_(float(10 * it + r))
+        torch.cuda.synchronize()
+        for r, g in enumerate(graphs):
+            with torch.cuda.stream(streams[r]):
+                g.replay()
+        torch.cuda.synchronize()
+        for r in range(n):
+            assert torch.equal(dsts[r], srcs[(r - 1) % n]), (it, r)
+    for c in comms:
+        c.check_async_error()
+
+
+@_P2P_GATE
+def test_send_without_a_receiver_times_out(torch_cuda, coll_mod):
+    torch = torch_cuda
+    comms = coll_mod.Comm.init_all([0, 0], arena_mb=32, timeout_ms=300)
+    src = comms[0].empty(1024, torch.bfloat16); src.fill_(1.0)
+    comms[0].send(src, 1)
+    torch.cuda.synchronize()
+    with pytest.raises(coll_mod.B200CollError, match="code=3"):
+        comms[0].check_async_error()
+    for c in comms:
+        c.destroy()
+
+
+@_P2P_GATE
+def test_sendrecv_perf_virtual_ranks_zero_errors(torch_cuda, coll_lib):
+    exe = os.path.join(ROOT, "build", "sendrecv_perf")
+    assert os.path.islink(exe)
+    r = subprocess.run([exe, "--devs", "0,0,0,0", "-b", "64", "-e", "4M", "-f", "4", "-w", "2", "-n", "5", "-c", "1"], capture_output=True, text=True, timeout=300,
+                       env={**{k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}, "B200COLL_TIMEOUT_MS": "5000"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "op=sendrecv" in r.stdout and "# Out of bounds values : 0 OK" in r.stdout, r.stdout
+
+
+@_P2P_GATE
+def test_nccl_api_shim_send_recv(torch_cuda, coll_lib):
+    """ncclSend / ncclRecv through the shim for shapes that are not the all-to-all pattern: a lone pair outside any group (uint8, odd
+    count) and a grouped exchange of int64 with different counts per direction, issued for both communicators inside one group."""
+    torch = torch_cuda
+    s = _NcclShim()
+    C, L, n = s.C, s.L, 2
+    comms = (C.c_void_p * n)()
+    s.ck(L.ncclCommInitAll(comms, n, (C.c_int * n)(0, 0)))
+    try:
+        streams = [torch.cuda.Stream() for _ in range(n)]
+        st = [C.c_void_p(x.cuda_stream) for x in streams]
+        p = lambda t: C.c_void_p(t.data_ptr())
+        a = _pattern(torch, 1001, 3)
+        b = torch.zeros(1001, dtype=torch.uint8, device="cuda")
+        s.ck(L.ncclSend(p(a), 1001, s.U8, 1, comms[0], st[0]))
+        s.ck(L.ncclRecv(p(b), 1001, s.U8, 0, comms[1], st[1]))
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        x01 = torch.arange(300, device="cuda", dtype=torch.int64) * 3 - 1
+        x10 = torch.arange(5000, device="cuda", dtype=torch.int64) * -7
+        y01 = torch.zeros(300, dtype=torch.int64, device="cuda")
+        y10 = torch.zeros(5000, dtype=torch.int64, device="cuda")
+        s.ck(L.ncclGroupStart())
+        s.ck(L.ncclSend(p(x01), 300, s.I64, 1, comms[0], st[0])); s.ck(L.ncclRecv(p(y10), 5000, s.I64, 1, comms[0], st[0]))
+        s.ck(L.ncclSend(p(x10), 5000, s.I64, 0, comms[1], st[1])); s.ck(L.ncclRecv(p(y01), 300, s.I64, 0, comms[1], st[1]))
+        s.ck(L.ncclGroupEnd())
+        torch.cuda.synchronize()
+        assert torch.equal(x01, y01) and torch.equal(x10, y10)
+        for r in range(n):
+            err = C.c_int(-1)
+            s.ck(L.ncclCommGetAsyncError(comms[r], C.byref(err)))
+            assert err.value == 0
+    finally:
+        torch.cuda.synchronize()
+        for c in comms:
+            L.ncclCommDestroy(c)

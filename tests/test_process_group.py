@@ -194,7 +194,28 @@ def _gpu_pair(rank, world):
             dist.all_reduce(b)
     torch.cuda.synchronize()
     assert torch.isfinite(a).all() and torch.isfinite(b).all() and a[0].item() == a[-1].item() and b[0].item() == b[-1].item()
-    assert pg.fast_calls >= 6
+    # point to point: blocking pair, then a ring step as isend + irecv (queued, one grouped kernel at the first wait), a strided tensor,
+    # and batch_isend_irecv
+    other = 1 - rank
+    msg = torch.arange(1 << 12, device="cuda", dtype=torch.float32) + 100 * rank
+    got = torch.empty_like(msg)
+    if rank == 0:
+        dist.send(msg, dst=1); dist.recv(got, src=1)
+    else:
+        dist.recv(got, src=0); dist.send(msg, dst=0)
+    assert torch.equal(got, torch.arange(1 << 12, device="cuda", dtype=torch.float32) + 100 * other)
+    before = pg.fallback_calls
+    strided = torch.zeros(64, 2, device="cuda")[:, 0]
+    reqs = [dist.isend(msg[:64], other), dist.irecv(strided, other)]
+    for r in reqs:
+        r.wait()
+    assert torch.equal(strided, (torch.arange(64, device="cuda", dtype=torch.float32) + 100 * other))
+    big = torch.empty(1 << 20, device="cuda", dtype=torch.bfloat16)
+    ops = [dist.P2POp(dist.isend, torch.full((1 << 20,), float(rank + 1), device="cuda", dtype=torch.bfloat16), other), dist.P2POp(dist.irecv, big, other)]
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    assert big.eq(float(other + 1)).all() and pg.fallback_calls == before
+    assert pg.fast_calls >= 12
     return pg.fast_calls
 
 
