@@ -4,7 +4,8 @@
 #   2. programmatic dependent launch (B200COLL_PDL=1) at one rank per GPU: small-message latency with and without
 #   3. the multi-process NVLS test that a one-GPU box skips
 #   4. the torch.distributed process group's CUDA paths (tests/test_process_group.py, opt-in until this has passed once)
-#   5. A/B of the two compile-time variants (lib/libb200coll_{gridconst,mcbar,bulk}.so) against the shipped build, 1 KiB - 64 MiB
+#   5. point to point (k_p2p): virtual-rank tests, then sendrecv_perf protocol on both arms
+#   6. A/B of the compile-time variants (lib/libb200coll_{gridconst,mcbar,bulk}.so) against the shipped build, 1 KiB - 64 MiB
 # Usage: gpurun --gpus 8 --timeout 600 -- 'bash bench/run_next8.sh 8'
 NG=${1:-8}
 mkdir -p gpurun_out; export B200COLL_TIMEOUT_MS=5000
@@ -49,5 +50,10 @@ echo "== $(date -u +%T) end-to-end step: copy-then-reduce vs pipelined Comm.all_
 B200_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_coll_gpu.py -q -k all_reduce_from_host > ${O}_pytest_e2e.log 2>&1; echo "pytest rc=$?"
 timeout 200 $TR --master-port 29760 bench/e2e_pipeline.py > ${O}_e2e_pipeline.jsonl 2> ${O}_e2e_pipeline.err; cat ${O}_e2e_pipeline.jsonl
 echo "== $(date -u +%T) done"
+echo "=== point to point: virtual-rank tests, then sendrecv on both arms ==="
+B200_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_coll_gpu.py -q -k "send_recv or sendrecv" > ${O}_pytest_p2p.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_p2p.log
+for impl in reference ours; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --op sendrecv --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
+done
 echo "=== tools on hardware (fault injector last: it kills its own context on purpose) ==="
 B200_RUN_FAULT_INJECTION=1 timeout 300 python -m pytest tests/test_zz_tools_gpu.py -q -m gpu > ${O}_pytest_tools.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_tools.log
