@@ -186,6 +186,10 @@ b200collResult_t b200collGroupStart(void);
 b200collResult_t b200collGroupEnd(void);
 b200collResult_t b200collSend(const void* buf, size_t bytes, int peer, b200collComm_t comm, b200collStream_t stream);
 b200collResult_t b200collRecv(void* buf, size_t bytes, int peer, b200collComm_t comm, b200collStream_t stream);
+/* Test hook (no GPU needed): plans one group of point-to-point operations for `rank` on a stand-in communicator and writes the
+ * launches it would make as text: CTA ranges per operation, direct or staged receive, window layout, follow-up kernels. */
+b200collResult_t b200collDebugPlanP2p(int rank, int nranks, int loopback, size_t window, int nops, const int* is_send, const int* peer,
+                                      const size_t* bytes, const int* in_arena, char* out, size_t outlen);
 
 /* --- tuner (libnccl-tuner.so analogue). */
 b200collAlgo_t b200collTunerPick(b200collOp_t op, size_t bytes, int nranks, int nvls_available);

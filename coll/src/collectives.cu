@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
@@ -232,6 +233,7 @@ namespace {
 struct PendingP2p { bool send; const void* sbuf; void* rbuf; size_t bytes; int peer; b200collComm* comm; cudaStream_t st; };
 thread_local int g_group_depth = 0;
 thread_local std::vector<PendingP2p> g_group;
+thread_local std::string* g_p2p_dry = nullptr;     // b200collDebugPlanP2p: describe the launches instead of making them (no CUDA call at all)
 
 // CTAs per operation: a pure function of the message size and of settings every rank shares, so CTA j of a send always
 // meets CTA j of the matching recv. Virtual ranks share one GPU's SMs between all their kernels: keep them small.
@@ -281,6 +283,19 @@ b200collResult_t p2p_launch(b200collComm* c, const std::vector<PendingP2p>& ops,
   }
   a.first_block[a.nops] = blocks;
   c->stats.p2p_bytes += moved;
+  if (g_p2p_dry) {
+    char line[192];
+    snprintf(line, sizeof line, "launch ctas=%d sends=%d recvs=%d staged=%d\n", blocks, a.nsend, a.nops - a.nsend, nstaged);
+    *g_p2p_dry += line;
+    for (int i = 0; i < a.nops; i++) {
+      const unsigned long long chunks = (i < a.nsend || a.bytes[i] <= a.win_bytes[i]) ? 1 : (a.bytes[i] + a.win_bytes[i] - 1) / a.win_bytes[i];
+      if (i < a.nsend) snprintf(line, sizeof line, "  send peer=%d bytes=%llu ctas=[%d,%d)\n", a.peer[i], a.bytes[i], a.first_block[i], a.first_block[i + 1]);
+      else if (!a.staged[i]) snprintf(line, sizeof line, "  recv peer=%d bytes=%llu ctas=[%d,%d) direct off=%llu\n", a.peer[i], a.bytes[i], a.first_block[i], a.first_block[i + 1], a.win_off[i]);
+      else snprintf(line, sizeof line, "  recv peer=%d bytes=%llu ctas=[%d,%d) staged off=%llu window=%llu chunks=%llu\n", a.peer[i], a.bytes[i], a.first_block[i], a.first_block[i + 1], a.win_off[i], a.win_bytes[i], chunks);
+      *g_p2p_dry += line;
+    }
+    return b200collSuccess;
+  }
   static const bool nvtx = [] { const char* e = getenv("B200COLL_NVTX"); return e && *e && *e != '0'; }();
   if (nvtx || debug_level() >= 2) {
     char msg[96];
@@ -306,7 +321,7 @@ b200collResult_t p2p_flush(std::vector<PendingP2p>& all) {
     // a group may span communicators on several GPUs of this process (nccl-tests -g N): launch each on its own device
     struct DeviceGuard {
       int prev = -1; bool switched = false;
-      explicit DeviceGuard(int want) { if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess; }
+      explicit DeviceGuard(int want) { if (!g_p2p_dry && cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess; }
       ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
     } guard(c->device);
     // self operations: the i-th send to myself pairs with the i-th recv from myself
@@ -319,6 +334,7 @@ b200collResult_t p2p_flush(std::vector<PendingP2p>& all) {
     for (size_t i = 0; i < self_s.size(); i++) {
       if (self_s[i].bytes != self_r[i].bytes) { set_last_error("send/recv to self: sizes differ"); return b200collInvalidArgument; }
       if (self_s[i].sbuf == self_r[i].rbuf) continue;
+      if (g_p2p_dry) { *g_p2p_dry += "self copy bytes=" + std::to_string(self_s[i].bytes) + "\n"; continue; }
       cudaError_t e = cudaMemcpyAsync(self_r[i].rbuf, self_s[i].sbuf, self_s[i].bytes, cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return b200collUnhandledCudaError; }
     }
@@ -691,6 +707,32 @@ b200collResult_t b200collSend(const void* buf, size_t bytes, int peer, b200collC
 }
 b200collResult_t b200collRecv(void* buf, size_t bytes, int peer, b200collComm_t c, b200collStream_t stream) {
   return p2p_enqueue(false, nullptr, buf, bytes, peer, c, static_cast<cudaStream_t>(stream));
+}
+
+b200collResult_t b200collDebugPlanP2p(int rank, int nranks, int loopback, size_t window, int nops, const int* is_send, const int* peer, const size_t* bytes,
+                                      const int* in_arena, char* out, size_t outlen) {
+  if (!out || outlen == 0 || nops < 0 || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return b200collInvalidArgument;
+  b200collComm fake;                                   // never touches the GPU: no arena, no streams, only the fields the planner reads
+  fake.rank = rank; fake.nranks = nranks; fake.loopback = loopback != 0; fake.p2p_window = window / 512 * 512;
+  fake.peer_va[rank] = (CUdeviceptr)1 << 40; fake.arena.total = (size_t)64 << 30;
+  std::string text;
+  size_t heap = kOffHeap, outside = (size_t)1 << 44;
+  b200collResult_t rc = b200collSuccess;
+  g_p2p_dry = &text;
+  g_group_depth++;
+  for (int i = 0; i < nops && rc == b200collSuccess; i++) {
+    size_t& cursor = in_arena[i] ? heap : outside;
+    void* buf = reinterpret_cast<void*>((in_arena[i] ? (size_t)fake.peer_va[rank] : 0) + cursor);
+    cursor += (bytes[i] + 4095) / 4096 * 4096 + 4096;
+    rc = is_send[i] ? b200collSend(buf, bytes[i], peer[i], &fake, nullptr) : b200collRecv(buf, bytes[i], peer[i], &fake, nullptr);
+  }
+  g_group_depth--;
+  std::vector<PendingP2p> ops;
+  ops.swap(g_group);
+  if (rc == b200collSuccess) rc = p2p_flush(ops);
+  g_p2p_dry = nullptr;
+  snprintf(out, outlen, "%s", text.c_str());
+  return rc;
 }
 
 b200collResult_t b200collBarrier(b200collComm_t c, b200collStream_t stream) {

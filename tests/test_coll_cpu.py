@@ -226,3 +226,59 @@ int main(void) {{ return 0; }}
     syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(os.path.dirname(coll_lib), "libb200coll_nccl.so")], capture_output=True, text=True, check=True).stdout
     for name in re.findall(r"\b(nccl[A-Z]\w+)\(", src.read_text()):
         assert f" T {name}\n" in syms, name
+
+
+def _plan_p2p(lib_path, rank, n, ops, loopback=0, window=0):
+    """ops: (is_send, peer, nbytes, in_arena). Returns (rc, [launch dicts]) from the library's planner hook (no GPU involved)."""
+    import ctypes as C
+    import re
+    L = C.CDLL(lib_path)
+    k = len(ops)
+    out = C.create_string_buffer(1 << 16)
+    arr = lambda t, xs: (t * k)(*xs)
+    rc = L.b200collDebugPlanP2p(rank, n, loopback, C.c_size_t(window), k, arr(C.c_int, [o[0] for o in ops]), arr(C.c_int, [o[1] for o in ops]),
+                                arr(C.c_size_t, [o[2] for o in ops]), arr(C.c_int, [o[3] for o in ops]), out, len(out))
+    launches = []
+    for line in out.value.decode().splitlines():
+        kv = {k_: int(v) for k_, v in re.findall(r"(\w+)=(\d+)", line)}
+        cta = re.search(r"ctas=\[(\d+),(\d+)\)", line)
+        if line.startswith("launch"):
+            launches.append({**kv, "ops": []})
+        elif line.startswith("self copy"):
+            launches.append({"self_copy": kv["bytes"], "ops": []})
+        else:
+            launches[-1]["ops"].append({**kv, "kind": line.split()[0], "staged": " staged " in line, "ctas": (int(cta.group(1)), int(cta.group(2)))})
+    return rc, launches
+
+
+def test_point_to_point_planner_layout_and_rounds(coll_lib):
+    """Host side of send / recv (coll/src/collectives.cu p2p_flush / p2p_launch), checked without a GPU: CTA counts depend only on the
+    message size (so both ends of a pair agree), sends occupy the low CTAs, staged receives get disjoint window pairs inside the staging
+    area, a second message for the same pair waits for a follow-up kernel, self pairs are local copies."""
+    MiB = 1 << 20
+    for nbytes, want in [(16, 1), (128 << 10, 1), ((128 << 10) + 1, 2), (MiB, 8), (2 * MiB, 16), (1 << 30, 16)]:
+        rc, (send,) = _plan_p2p(coll_lib, 0, 8, [(1, 3, nbytes, 1)])
+        rc2, (recv,) = _plan_p2p(coll_lib, 3, 8, [(0, 0, nbytes, 1)])
+        assert rc == 0 and rc2 == 0 and send["ctas"] == want and recv["ctas"] == want, nbytes       # CTA j of the send meets CTA j of the recv
+    assert _plan_p2p(coll_lib, 0, 4, [(1, 1, 1 << 30, 1)], loopback=1)[1][0]["ctas"] == 2                     # virtual ranks share one GPU's SMs
+    # a ring step: one launch, send in the low CTAs, arena receive written in place
+    rc, (ring,) = _plan_p2p(coll_lib, 0, 8, [(0, 7, MiB, 1), (1, 1, MiB, 1)])
+    assert rc == 0 and [o["kind"] for o in ring["ops"]] == ["send", "recv"] and ring["ops"][0]["ctas"] == (0, 8) and ring["ops"][1]["ctas"] == (8, 16)
+    assert not ring["ops"][1]["staged"] and ring["staged"] == 0
+    # three receives outside the arena: three window pairs, disjoint, inside the 64 MiB staging area that starts at 25 MiB
+    rc, (l,) = _plan_p2p(coll_lib, 1, 4, [(0, p, 40 * MiB, 0) for p in (0, 2, 3)])
+    assert rc == 0 and l["staged"] == 3
+    spans = sorted((o["off"], o["off"] + 2 * o["window"]) for o in l["ops"])
+    assert spans[0][0] == 25 * MiB and spans[-1][1] <= 89 * MiB and all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert all(o["window"] % 512 == 0 and o["chunks"] == -(-40 * MiB // o["window"]) for o in l["ops"])
+    # the receiver may cap its windows; a message that fits one window is a single chunk
+    rc, (l,) = _plan_p2p(coll_lib, 1, 2, [(0, 0, 3 * MiB + 5, 0)], window=MiB)
+    assert l["ops"][0]["window"] == MiB and l["ops"][0]["chunks"] == 4
+    assert _plan_p2p(coll_lib, 1, 2, [(0, 0, 1000, 0)], window=MiB)[1][0]["ops"][0]["chunks"] == 1
+    # two messages 0 -> 1 in one group share a mailbox: the second runs in a follow-up kernel; empty messages vanish; self pairs are copies
+    rc, ls = _plan_p2p(coll_lib, 0, 2, [(1, 1, 4096, 1), (1, 1, 777, 1), (0, 1, 64, 1), (1, 1, 0, 1), (1, 0, 256, 1), (0, 0, 256, 0)])
+    assert rc == 0 and ls[0] == {"self_copy": 256, "ops": []}
+    assert [(len(l["ops"]), l["sends"], l["recvs"]) for l in ls[1:]] == [(2, 1, 1), (1, 1, 0)] and ls[2]["ops"][0]["bytes"] == 777
+    # misuse is refused before anything is launched
+    assert _plan_p2p(coll_lib, 0, 2, [(1, 0, 64, 1)])[0] == 5               # send to self without the matching recv: invalid usage
+    assert _plan_p2p(coll_lib, 0, 2, [(1, 2, 64, 1)])[0] == 4               # peer out of range: invalid argument
