@@ -13,6 +13,7 @@ conformance: build           ## the fourteen kubelet-side scenarios against both
 test-race: build             ## the native daemons under ThreadSanitizer, then AddressSanitizer+UBSan (role of `go test -race`, reference Makefile:21)
 	B200_NATIVE_SAN=thread $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -x -q
 	B200_NATIVE_SAN=address $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -x -q
+	$(MAKE) -C coll emu-tsan    # the send/recv kernel source, every CTA a host thread, under ThreadSanitizer
 coverage-native: build       ## line coverage of the C++ daemons under the conformance suites (gcov)
 	rm -rf build/agent-cov
 	B200_NATIVE_SAN=cov $(PY) -m pytest tests/test_native_device_plugin.py tests/test_nri_injector.py tests/test_native_tools.py -q

@@ -524,7 +524,13 @@ inline int unary_call(const std::string& socket_path, const std::string& path, c
       }
       if (f.type == HEADERS && (f.flags & END_STREAM)) done = true;
     } else if (f.type == RST_STREAM && f.stream == 1) { *err = "stream reset by peer"; ::close(fd); return -1; }
-    else if (f.type == GOAWAY) { if (!done) { *err = "GOAWAY from peer"; } break; }
+    else if (f.type == GOAWAY) {
+      // A server that shuts down gracefully (a kubelet restarting) announces it with GOAWAY(NO_ERROR, last-stream-id) and still answers the
+      // streams up to that id: ours is stream 1, so keep reading. Anything else ends the call.
+      auto be32 = [&](size_t o) { return f.payload.size() >= o + 4 ? ((uint32_t)(uint8_t)f.payload[o] << 24) | ((uint32_t)(uint8_t)f.payload[o + 1] << 16) | ((uint32_t)(uint8_t)f.payload[o + 2] << 8) | (uint8_t)f.payload[o + 3] : 0u; };
+      const uint32_t last = be32(0) & 0x7FFFFFFFu, code = f.payload.size() >= 8 ? be32(4) : 2u;
+      if (code != 0 || last < 1) { *err = "GOAWAY from peer (error code " + std::to_string(code) + ")"; break; }
+    }
   }
   ::close(fd);
   if (status < 0) { if (err->empty()) *err = "connection closed before a grpc-status arrived"; return -1; }

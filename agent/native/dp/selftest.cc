@@ -4,6 +4,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <thread>
 
 #include "h2.hpp"
 #include "json.hpp"
@@ -151,8 +152,55 @@ static int json_roundtrip() {
   return 0;
 }
 
+// A scripted HTTP/2 peer on a Unix socket: swallows whatever the client sends, answers with `script`, closes.
+static std::string serve_script_once(const std::string& path, const std::string& script, std::thread* t) {
+  ::unlink(path.c_str());
+  int lfd = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+  sockaddr_un a{}; a.sun_family = AF_UNIX; strncpy(a.sun_path, path.c_str(), sizeof(a.sun_path) - 1);
+  if (lfd < 0 || ::bind(lfd, reinterpret_cast<sockaddr*>(&a), sizeof(a)) < 0 || ::listen(lfd, 1) < 0) return "cannot listen on " + path;
+  *t = std::thread([lfd, script] {
+    int c = ::accept(lfd, nullptr, nullptr);
+    if (c >= 0) {
+      char buf[4096]; (void)!::read(c, buf, sizeof buf);           // preface + SETTINGS + HEADERS + DATA arrive in one write
+      h2::write_all(c, script.data(), script.size());
+      ::shutdown(c, SHUT_WR);
+      while (::read(c, buf, sizeof buf) > 0) {}
+      ::close(c);
+    }
+    ::close(lfd);
+  });
+  return "";
+}
+
+static void test_h2_client_goaway() {
+  using namespace h2;
+  const std::string path = "/tmp/b200-selftest-" + std::to_string(getpid()) + ".sock";
+  const std::string answer = frame_bytes(HEADERS, END_HEADERS, 1, hpack_encode({{":status", "200"}, {"content-type", "application/grpc"}})) +
+                             frame_bytes(DATA, 0, 1, grpc_message("ok")) + frame_bytes(HEADERS, END_HEADERS | END_STREAM, 1, hpack_encode({{"grpc-status", "0"}}));
+  struct Case { std::string goaway; int want; const char* what; } cases[] = {
+      {frame_bytes(GOAWAY, 0, 0, u32be(0x7FFFFFFF) + u32be(0)) + frame_bytes(GOAWAY, 0, 0, u32be(1) + u32be(0)), 0, "graceful shutdown that still covers stream 1: the answer is read"},
+      {frame_bytes(GOAWAY, 0, 0, u32be(0) + u32be(0)), -1, "stream 1 will not be processed"},
+      {frame_bytes(GOAWAY, 0, 0, u32be(1) + u32be(2)), -1, "INTERNAL_ERROR"},
+  };
+  for (const Case& k : cases) {
+    std::thread t;
+    std::string e = serve_script_once(path, frame_bytes(SETTINGS, 0, 0, "") + k.goaway + answer, &t);
+    CHECK(e.empty());
+    if (!e.empty()) continue;
+    std::string resp, err;
+    const int st = unary_call(path, "/v1beta1.Registration/Register", "x", &resp, &err, 3000);
+    t.join();
+    if (st != k.want) fprintf(stderr, "  case: %s -> status %d (%s)\n", k.what, st, err.c_str());
+    CHECK(st == k.want);
+    CHECK(k.want != 0 || resp == "ok");
+    CHECK(k.want == 0 || err.find("GOAWAY") != std::string::npos);
+  }
+  ::unlink(path.c_str());
+}
+
 int main(int argc, char** argv) {
   if (argc > 1 && std::string(argv[1]) == "--json-roundtrip") return json_roundtrip();
+  test_h2_client_goaway();
   test_json();
   test_kube();
   test_hpack();

@@ -3,6 +3,7 @@ Unix-socket rendezvous (SCM_RIGHTS) exercised across real processes with memfd d
 import ctypes as C
 import multiprocessing as mp
 import os
+import subprocess
 
 import pytest
 
@@ -282,3 +283,26 @@ def test_point_to_point_planner_layout_and_rounds(coll_lib):
     # misuse is refused before anything is launched
     assert _plan_p2p(coll_lib, 0, 2, [(1, 0, 64, 1)])[0] == 5               # send to self without the matching recv: invalid usage
     assert _plan_p2p(coll_lib, 0, 2, [(1, 2, 64, 1)])[0] == 4               # peer out of range: invalid argument
+
+
+def test_point_to_point_protocol_under_host_emulation(coll_lib):
+    """coll/src/p2p.cuh — the text nvcc compiles into k_p2p — built by g++ with every CTA of every rank a thread (coll/tests/p2p_emu.cc):
+    ring steps with growing and shrinking sizes, staged receives through windows far smaller than the message, all-pairs groups,
+    lone send / recv, watchdog and size-mismatch faults. Then the same under ThreadSanitizer where the toolchain has it: every payload
+    byte must be ordered by a release/acquire pair on a flag. (This harness found the first version's window-sharing bug before any GPU
+    saw the kernel.)"""
+    import shutil
+    root = os.path.dirname(os.path.dirname(coll_lib))
+    r = subprocess.run(["make", "-C", root, "../build/p2p_emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = os.path.join(os.path.dirname(root), "build", "p2p_emu")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "all scenarios passed" in r.stdout, r.stdout + r.stderr
+    if shutil.which("/usr/bin/g++") is None:
+        pytest.skip("no system g++ for the ThreadSanitizer flavour")
+    b = subprocess.run(["make", "-C", root, "../build/p2p_emu_tsan"], capture_output=True, text=True)
+    if b.returncode != 0 and "tsan" in (b.stdout + b.stderr).lower():
+        pytest.skip("toolchain has no libtsan")
+    assert b.returncode == 0, b.stdout + b.stderr
+    r = subprocess.run([exe + "_tsan", "--quick"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "data race" not in r.stderr and "all scenarios passed" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
