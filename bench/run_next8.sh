@@ -51,7 +51,7 @@ B200_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_coll_gpu.py -q -k
 timeout 200 $TR --master-port 29760 bench/e2e_pipeline.py > ${O}_e2e_pipeline.jsonl 2> ${O}_e2e_pipeline.err; cat ${O}_e2e_pipeline.jsonl
 echo "== $(date -u +%T) done"
 echo "=== point to point: virtual-rank tests, then sendrecv on both arms ==="
-B200_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_coll_gpu.py -q -k "send_recv or sendrecv" > ${O}_pytest_p2p.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_p2p.log
+B200_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_coll_gpu.py -q -k "send_recv or sendrecv or comm_split" > ${O}_pytest_p2p.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_p2p.log
 for impl in reference ours; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --op sendrecv --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
 done

@@ -135,6 +135,11 @@ b200collResult_t b200collCommInitRank(b200collComm_t* comm, int nranks, const b2
                                       const b200collConfig* cfg);
 /* --- single process: n ranks, one per entry of devs (entries may repeat: virtual ranks on one GPU for tests). */
 b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* devs, const b200collConfig* cfg);
+/* ncclCommSplit: a collective call on a multi-process communicator. Ranks that pass the same color >= 0 form a new communicator
+ * (its own arena: cfg, or the parent's settings when NULL), ordered by (key, rank in the parent); color < 0 takes part and gets none. */
+b200collResult_t b200collCommSplit(b200collComm_t comm, int color, int key, b200collComm_t* newcomm, const b200collConfig* cfg);
+/* Test hook: the (rank, size) a split would give `rank`, from everybody's colors and keys. */
+b200collResult_t b200collDebugSplitPlan(int nranks, int rank, const int* colors, const int* keys, int* new_rank, int* new_size);
 b200collResult_t b200collCommDestroy(b200collComm_t comm);
 b200collResult_t b200collCommInfoGet(b200collComm_t comm, b200collCommInfo* info);
 b200collResult_t b200collCommStatsGet(b200collComm_t comm, b200collStats* stats);

@@ -327,6 +327,7 @@ b200collResult_t b200collCommInitRank(b200collComm_t* out, int nranks, const b20
   c->boot.reset(new Bootstrap());
   std::string name(id->internal, strnlen(id->internal, sizeof(id->internal)));
   BOOT_TRY(c->boot->init(name, rank, nranks, std::max(c->cfg.timeout_ms, 60000)));
+  c->boot_name = name;
 
   struct Info { unsigned char uuid[16]; int mc; int p2p_all; unsigned long long arena_bytes; } mine = {};
   {
@@ -512,6 +513,48 @@ b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* de
   for (int i = 0; i < n; i++) comms[i] = cs[i].release();
   cudaSetDevice(prev_dev);
   return b200collSuccess;
+}
+
+// Who ends up where after a split: ranks with my colour, ordered by (key, old rank). Pure, so it is testable without a GPU.
+static void split_plan(int nranks, int rank, const int* colors, const int* keys, int* new_rank, int* new_size) {
+  std::vector<std::pair<std::pair<int, int>, int>> members;          // ((key, old rank), old rank)
+  for (int r = 0; r < nranks; r++) if (colors[r] == colors[rank]) members.push_back({{keys[r], r}, r});
+  std::sort(members.begin(), members.end());
+  *new_size = (int)members.size();
+  *new_rank = 0;
+  for (size_t i = 0; i < members.size(); i++) if (members[i].second == rank) *new_rank = (int)i;
+}
+
+b200collResult_t b200collDebugSplitPlan(int nranks, int rank, const int* colors, const int* keys, int* new_rank, int* new_size) {
+  if (nranks < 1 || nranks > B200COLL_MAX_RANKS || rank < 0 || rank >= nranks || !colors || !keys || !new_rank || !new_size) return b200collInvalidArgument;
+  split_plan(nranks, rank, colors, keys, new_rank, new_size);
+  return b200collSuccess;
+}
+
+b200collResult_t b200collCommSplit(b200collComm_t parent, int color, int key, b200collComm_t* out, const b200collConfig* cfg) {
+  if (!parent || !out) { set_last_error("null argument"); return b200collInvalidArgument; }
+  *out = nullptr;
+  if (!parent->boot) { set_last_error("only communicators created with CommInitRank can be split (in-process groups: call CommInitAll on the subset)"); return b200collInvalidUsage; }
+  struct Mine { int color, key; } mine = {color, key};
+  std::vector<char> all;
+  std::string e = parent->boot->allgather(&mine, sizeof(mine), &all);
+  if (!e.empty()) { set_last_error("bootstrap: " + e); return b200collSystemError; }
+  const uint32_t seq = parent->split_seq++;
+  if (color < 0) return b200collSuccess;                               // NCCL_SPLIT_NOCOLOR: took part in the exchange, gets no communicator
+  int colors[B200COLL_MAX_RANKS], keys[B200COLL_MAX_RANKS];
+  for (int r = 0; r < parent->nranks; r++) { Mine m; memcpy(&m, all.data() + r * sizeof(Mine), sizeof(Mine)); colors[r] = m.color; keys[r] = m.key; }
+  int new_rank = 0, new_size = 0;
+  split_plan(parent->nranks, parent->rank, colors, keys, &new_rank, &new_size);
+  b200collUniqueId id;
+  const std::string name = parent->boot_name + "/split" + std::to_string(seq) + "/color" + std::to_string(color);
+  b200collUniqueIdFromString(name.c_str(), &id);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != parent->device) cudaSetDevice(parent->device);          // the child lives on the parent's GPU
+  const b200collConfig child_cfg = cfg ? *cfg : parent->cfg;
+  const b200collResult_t rc = b200collCommInitRank(out, new_size, &id, new_rank, &child_cfg);
+  if (prev != parent->device) cudaSetDevice(prev);
+  return rc;
 }
 
 b200collResult_t b200collCommDestroy(b200collComm_t c) {

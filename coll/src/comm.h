@@ -83,6 +83,8 @@ struct b200collComm {
   std::shared_ptr<b200coll::SharedGroup> group;
   void* stats_shm = nullptr;       // exported stats page (metrics exporter reads it)
   std::string stats_shm_name;
+  std::string boot_name;                // rendezvous name this communicator was created under (multi-process only); splits derive theirs from it
+  uint32_t split_seq = 0;               // CommSplit calls so far (a collective call, so the same on every rank)
   size_t p2p_window = 0;                // staged receives: bytes per staging window; 0 = an equal share of the staging area
   uint32_t stats_tick = 0;              // collective calls since init; the counters page is refreshed every 256
 };

@@ -175,7 +175,20 @@ ncclResult_t ncclCommDestroy(ncclComm_t comm) {
 ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank, ncclConfig_t* /*config*/) {
   return ncclCommInitRank(comm, nranks, id, rank);
 }
-ncclResult_t ncclCommSplit(ncclComm_t /*comm*/, int /*color*/, int /*key*/, ncclComm_t* /*newcomm*/, ncclConfig_t* /*config*/) { return ncclInvalidUsage; }      // one communicator per NVSwitch domain
+ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newcomm, ncclConfig_t* /*config*/) {
+  if (!comm || !newcomm) return ncclInvalidArgument;
+  ShimComm* parent = reinterpret_cast<ShimComm*>(comm);
+  *newcomm = nullptr;
+  b200collComm_t child = nullptr;
+  const b200collResult_t r = b200collCommSplit(parent->comm, color, key, &child, nullptr);
+  if (r != b200collSuccess || !child) return map_rc(r);        // NCCL_SPLIT_NOCOLOR: success with a NULL communicator
+  b200collCommInfo info;
+  if (b200collCommInfoGet(child, &info) != b200collSuccess) { b200collCommDestroy(child); return ncclInternalError; }
+  ShimComm* s = new ShimComm{child, info.nranks, info.rank, info.device};
+  { std::lock_guard<std::mutex> lk(g_mu); g_last_comm = s; }
+  *newcomm = reinterpret_cast<ncclComm_t>(s);
+  return ncclSuccess;
+}
 ncclResult_t ncclCommRegister(const ncclComm_t comm, void* buff, size_t, void** handle) {              // arena memory is registered by construction
   if (!comm || !handle) return ncclInvalidArgument;
   *handle = buff;

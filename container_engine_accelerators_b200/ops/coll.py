@@ -104,6 +104,8 @@ def load() -> C.CDLL:
     L.b200collCommInitRank.argtypes = [C.POINTER(vp), ci, C.POINTER(UniqueId), ci, C.POINTER(Config)]
     L.b200collCommInitAll.argtypes = [C.POINTER(vp), ci, C.POINTER(ci), C.POINTER(Config)]
     L.b200collCommDestroy.argtypes = [vp]
+    L.b200collCommSplit.argtypes = [vp, ci, ci, C.POINTER(vp), C.POINTER(Config)]
+    L.b200collDebugSplitPlan.argtypes = [ci, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
     L.b200collCommInfoGet.argtypes = [vp, C.POINTER(CommInfo)]
     L.b200collCommStatsGet.argtypes = [vp, C.POINTER(Stats)]
     L.b200collCommGetAsyncError.argtypes = [vp, C.POINTER(Fault)]
@@ -237,6 +239,15 @@ class Comm:
         cfg = cls.make_config(arena_mb, **kw)
         _check(L.b200collCommInitAll(hs, n, devs, C.byref(cfg)), "CommInitAll")
         return [cls(hs[i]) for i in range(n)]
+
+    def split(self, color: int, key: int = 0, arena_mb: Optional[int] = None, **kw) -> Optional["Comm"]:
+        """ncclCommSplit: every rank of this (multi-process) communicator calls it; ranks with the same color >= 0 get a new communicator
+        with its own arena, ordered by (key, rank here). A negative color takes part and returns None. Tensor-parallel and data-parallel
+        groups of one job are two splits of the world communicator."""
+        cfg = self.make_config(arena_mb, **kw) if (arena_mb is not None or kw) else None
+        h = C.c_void_p()
+        _check(load().b200collCommSplit(self._h, color, key, C.byref(h), C.byref(cfg) if cfg is not None else None), "CommSplit")
+        return type(self)(h.value) if h.value else None
 
     def destroy(self) -> None:
         if self._h:

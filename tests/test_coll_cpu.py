@@ -306,3 +306,30 @@ def test_point_to_point_protocol_under_host_emulation(coll_lib):
     assert b.returncode == 0, b.stdout + b.stderr
     r = subprocess.run([exe + "_tsan", "--quick"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "data race" not in r.stderr and "all scenarios passed" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_comm_split_plan_orders_by_key_then_rank(coll_lib):
+    """b200collCommSplit's membership rule (ncclCommSplit's): same color -> same communicator, ranks ordered by (key, old rank)."""
+    import itertools
+    L = C.CDLL(coll_lib)
+
+    def plan(colors, keys, rank):
+        n = len(colors)
+        nr, ns = C.c_int(-1), C.c_int(-1)
+        rc = L.b200collDebugSplitPlan(n, rank, (C.c_int * n)(*colors), (C.c_int * n)(*keys), C.byref(nr), C.byref(ns))
+        assert rc == 0
+        return nr.value, ns.value
+
+    # tensor-parallel pairs out of 8 ranks, and the data-parallel groups across them
+    assert [plan([r // 2 for r in range(8)], [0] * 8, r) for r in range(8)] == [(r % 2, 2) for r in range(8)]
+    assert [plan([r % 2 for r in range(8)], [0] * 8, r) for r in range(8)] == [(r // 2, 4) for r in range(8)]
+    # keys reverse the order inside a colour; equal keys fall back to the old rank
+    assert [plan([0, 0, 0, 1], [5, 3, 3, 0], r) for r in range(4)] == [(2, 3), (0, 3), (1, 3), (0, 1)]
+    # exhaustively for 4 ranks and small colour / key alphabets: new ranks of a colour are exactly 0..size-1, ordered by (key, rank)
+    for colors in itertools.product(range(2), repeat=4):
+        for keys in itertools.product(range(2), repeat=4):
+            got = [plan(colors, keys, r) for r in range(4)]
+            for col in set(colors):
+                members = sorted((keys[r], r) for r in range(4) if colors[r] == col)
+                assert [got[r] for _, r in members] == [(i, len(members)) for i in range(len(members))]
+    assert L.b200collDebugSplitPlan(9, 0, None, None, None, None) != 0

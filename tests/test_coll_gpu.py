@@ -665,3 +665,49 @@ def test_nccl_api_shim_send_recv(torch_cuda, coll_lib):
         torch.cuda.synchronize()
         for c in comms:
             L.ncclCommDestroy(c)
+
+
+# ------------------------------------------------------------------------------------------------- communicator split
+def _split_rank(rank, world, key, q):
+    try:
+        import torch
+        from container_engine_accelerators_b200.ops import coll
+        torch.cuda.set_device(0)
+        comm = coll.Comm.init_rank(rank, world, key, arena_mb=32, timeout_ms=10000)
+        pair = comm.split(color=rank // 2, key=-rank, arena_mb=16)               # {0,1} and {2,3}; negative keys reverse the order inside
+        assert pair is not None and pair.nranks == 2 and pair.rank == 1 - rank % 2
+        x = pair.empty(4096, torch.float32); x.fill_(float(rank + 1))
+        pair.all_reduce(x)
+        torch.cuda.synchronize()
+        want = float((rank // 2) * 4 + 3)                                         # 1+2 or 3+4
+        assert torch.equal(x, torch.full_like(x, want)), (rank, x[0].item(), want)
+        lone = comm.split(color=0 if rank == 3 else -1)                           # everybody takes part, only rank 3 gets a communicator
+        assert (lone is None) == (rank != 3) and (lone is None or lone.nranks == 1)
+        y = comm.empty(1024, torch.float32); y.fill_(1.0)
+        comm.all_reduce(y)                                                        # the parent still works after two splits
+        torch.cuda.synchronize()
+        assert torch.equal(y, torch.full_like(y, float(world)))
+        for c in (lone, pair, comm):
+            if c is not None:
+                c.check_async_error(); c.destroy()
+        q.put((rank, "ok"))
+    except Exception as e:                                                        # noqa: BLE001 - reported to the parent
+        import traceback
+        q.put((rank, traceback.format_exc() + repr(e)))
+
+
+@pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="CommSplit has not run on hardware yet; set B200_RUN_UNVALIDATED=1")
+def test_comm_split_four_processes(torch_cuda, coll_mod):
+    """ncclCommSplit semantics across four processes (sharing cuda:0 on a one-GPU box): colours, key ordering, a rank without a colour,
+    and the parent staying usable."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    key = f"split-test-{os.getpid()}"
+    procs = [ctx.Process(target=_split_rank, args=(r, 4, key, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(30)
+    assert results == {r: "ok" for r in range(4)}, results
