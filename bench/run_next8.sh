@@ -55,5 +55,9 @@ B200_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_coll_gpu.py -q -k
 for impl in reference ours; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --op sendrecv --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
 done
+echo "--- CTAs per send/recv operation (B200COLL_P2P_MAX_BLOCKS): pick the default from this"
+for cap in 4 8 16; do
+  B200COLL_P2P_MAX_BLOCKS=$cap timeout 200 ./build/sendrecv_perf --devs $ALL --procs -b 64K -e 1G -f 4 -w 3 -n 10 -c 0 > ${O}_sendrecv_cap$cap.txt 2>&1; echo "cap=$cap rc=$?"; tail -n 4 ${O}_sendrecv_cap$cap.txt
+done
 echo "=== tools on hardware (fault injector last: it kills its own context on purpose) ==="
 B200_RUN_FAULT_INJECTION=1 timeout 300 python -m pytest tests/test_zz_tools_gpu.py -q -m gpu > ${O}_pytest_tools.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_tools.log
