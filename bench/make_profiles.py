@@ -5,7 +5,6 @@ Roofline: bytes that must cross NVLink per GPU and direction / link bandwidth, w
 all-to-all busbw <= 770."""
 from __future__ import annotations
 
-import glob
 import json
 import os
 import re

@@ -15,10 +15,8 @@ Two arms, same harness, same buffers sizes, same ctypes-level call overhead:
 from __future__ import annotations
 
 import ctypes as C
-import json
 import os
-import time
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce")   # index = b200collOp_t
 P2P_OPS = ("sendrecv",)     # nccl-tests sendrecv_perf: a ring step (send right, receive from the left) through the point-to-point kernel

@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import logging
 import re
-from typing import Any, Optional
 
 from .quantity import parse_quantity
 
