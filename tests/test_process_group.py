@@ -225,3 +225,70 @@ def test_cuda_fast_paths_two_ranks():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     _run(_gpu_pair, 2)
+
+
+# ------------------------------------------------------------------------------------------------- point-to-point queueing (no GPU)
+class _DeviceLike(torch.Tensor):
+    """A CPU tensor that answers is_cuda=True, so the process group takes its CUDA branch while the test stays on CPU."""
+    is_cuda = property(lambda self: True)
+
+    @staticmethod
+    def of(t):
+        return torch.Tensor._make_subclass(_DeviceLike, t)
+
+
+class _RecordingComm:
+    def __init__(self):
+        self.calls, self.in_group = [], 0
+
+    def send(self, t, peer):
+        self.calls.append(("send", peer, t.numel() * t.element_size(), t.is_contiguous() and t.data_ptr() % 16 == 0, self.in_group))
+
+    def recv(self, t, peer):
+        self.calls.append(("recv", peer, t.numel() * t.element_size(), t.is_contiguous() and t.data_ptr() % 16 == 0, self.in_group))
+        t.fill_(7.0)                                  # "data from the peer"
+        return t
+
+    def barrier(self):
+        self.calls.append(("barrier",))
+
+
+def test_point_to_point_calls_are_queued_and_launched_as_one_group(monkeypatch):
+    """isend / irecv on device tensors are queued; the first wait() (or the next collective) launches everything queued inside ONE
+    library group, in call order; tensors the kernel cannot take as they are travel through an aligned contiguous temporary."""
+    class _Stream:
+        def wait_event(self, e): pass
+        def synchronize(self): pass
+    class _Event:
+        def record(self, s): pass
+    stream = _Stream()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: stream)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    comm = _RecordingComm()
+    groups = []
+
+    class _Group:                                      # stands in for ops.coll.group: counts how often a library group is opened
+        def __enter__(self): comm.in_group += 1; groups.append(len(comm.calls)); return self
+        def __exit__(self, *exc): comm.in_group -= 1; return False
+    monkeypatch.setattr(pgmod.coll, "group", _Group)
+    pg = pgmod.B200CollProcessGroup(store=None, rank=0, size=2)
+    pg._comm = comm
+    out = _DeviceLike.of(torch.arange(64, dtype=torch.float32))
+    strided = _DeviceLike.of(torch.zeros(32, 2))[:, 0]                   # not contiguous
+    inn = _DeviceLike.of(torch.zeros(64))
+    w1 = pg.send([out], 1)
+    w2 = pg.recv([strided], 1)
+    w3 = pg.recv([inn], 1)
+    assert comm.calls == [] and len(pg._pending) == 3                     # nothing launched yet
+    assert w2.wait() and comm.calls == [("send", 1, 256, True, 1), ("recv", 1, 128, True, 1), ("recv", 1, 256, True, 1)]
+    assert groups == [0] and pg._pending == []                            # one group for all three, in call order
+    assert strided.eq(7.0).all() and inn.eq(7.0).all()                    # the strided tensor was filled through its temporary
+    assert w1.wait() and w3.wait() and len(comm.calls) == 3               # later waits have nothing left to launch
+    # a collective issued while sends are queued launches them first (they keep their place in the order of calls)
+    pg.send([out], 1)
+    pg.barrier().wait()
+    assert [c[0] for c in comm.calls[3:]] == ["send", "barrier"] and pg.fast_calls == 5 and pg.fallback_calls == 0
+    # empty tensors never reach the library
+    pg.send([_DeviceLike.of(torch.zeros(0))], 1).wait()
+    assert len(comm.calls) == 5
