@@ -115,7 +115,7 @@ typedef struct {
 
 /* Device-written watchdog record (host-pinned). code != 0 means the comm is poisoned. */
 typedef struct {
-  uint32_t code;             /* 0 ok, 1 barrier timeout, 2 LL data timeout, 3 send/recv peer never showed up, 4 send/recv sizes differ */
+  uint32_t code;             /* 0 ok, 1 barrier timeout, 2 LL data timeout, 3 send/recv peer never showed up, 4 send/recv sizes differ, 5 bulk copy never completed (bulk variant) */
   uint32_t rank, peer, block;
   uint32_t expected, observed;
   uint32_t op, reserved;

@@ -453,7 +453,7 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
     });
   };
 #ifdef B200COLL_VARIANT_BULK
-  if (sym_out && identity && bytes >= (1u << 20) && algo != b200collAlgoNvls) {     // A/B candidate: copy-engine push (kernels.cuh k_ag_bulk)
+  if (sym_out && identity && bytes >= (1u << 20) && bytes % 16 == 0 && algo != b200collAlgoNvls) {     // A/B candidate: copy-engine push (kernels.cuh k_ag_bulk)
     account(c, b200collOpAllGather, bytes, algo);
     const size_t chunks = (bytes + kBulkChunk - 1) / kBulkChunk;
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>(chunks, (size_t)std::min(c->max_ctas, 2 * std::max(1, c->sm_count))));

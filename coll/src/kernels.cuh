@@ -712,8 +712,13 @@ __global__ void __launch_bounds__(128) k_ag_bulk(COMM_PARAM, const char* __restr
       const uint32_t bar = smem_u32(&full[stage]), dst_s = smem_u32(&ring[stage][0]);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(in + off), "r"(n), "r"(bar) : "memory");
-      uint32_t done = 0;
-      while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      uint32_t done = 0, spins = 0;
+      const unsigned long long t0 = globaltimer_ns();
+      while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ((++spins) & 0x3FF) == 0 && globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 5, (uint32_t)c.rank, n, stage, op); break; }   // the copy engine never delivered: report, do not hang
+      }
+      if (!done) break;
 #pragma unroll
       for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) {
         int r = c.rank + j; if (r >= c.nranks) r -= c.nranks;
