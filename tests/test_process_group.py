@@ -292,3 +292,18 @@ def test_point_to_point_calls_are_queued_and_launched_as_one_group(monkeypatch):
     # empty tensors never reach the library
     pg.send([_DeviceLike.of(torch.zeros(0))], 1).wait()
     assert len(comm.calls) == 5
+
+
+def test_ddp_demo_trains_on_the_backend():
+    """demo/gpu-training/ddp_b200coll.py under torchrun with two ranks (CPU here: the process group's Gloo fallback carries DDP's bucket
+    all-reduces): the loss moves and both replicas end with identical weights."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                        os.path.join(root, "demo", "gpu-training", "ddp_b200coll.py"), "--steps", "6", "--batch", "2", "--seq", "32", "--dim", "64", "--layers", "2", "--vocab", "256"],
+                       capture_output=True, text=True, timeout=300, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["backend"] == "b200coll" and out["world"] == 2 and out["replicas_in_sync"] is True
+    assert out["last_loss"] < out["first_loss"] and out["fallback_calls"] > 0
