@@ -15,7 +15,7 @@ ALL=$(python3 -c "print(','.join(str(i) for i in range($NG)))")
 echo "== $(date -u +%T) multi-process NVLS tests"
 timeout 300 python -m pytest tests/test_coll_gpu.py -q -k "multi_gpu" > ${O}_pytest_multi.log 2>&1; echo "pytest rc=$?"; tail -n 2 ${O}_pytest_multi.log
 echo "== $(date -u +%T) torch.distributed backend on CUDA (first run on hardware)"
-B200_RUN_UNVALIDATED=1 timeout 200 python -m pytest tests/test_process_group.py -q -m gpu > ${O}_pytest_pg.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_pg.log
+B200_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_process_group.py -q -m gpu > ${O}_pytest_pg.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_pg.log
 echo "== $(date -u +%T) rooted ops, both arms"
 timeout 200 $TR --master-port 29731 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --extra-ops reduce --extra-out ${O}_rooted_ours.json > ${O}_bcast.json 2> ${O}_bcast.err
 timeout 200 $TR --master-port 29732 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --impl reference --extra-ops reduce --extra-out ${O}_rooted_ref.json > ${O}_bcast_ref.json 2> ${O}_bcast_ref.err
@@ -58,6 +58,10 @@ done
 echo "--- CTAs per send/recv operation (B200COLL_P2P_MAX_BLOCKS): pick the default from this"
 for cap in 4 8 16; do
   B200COLL_P2P_MAX_BLOCKS=$cap timeout 200 ./build/sendrecv_perf --devs $ALL --procs -b 64K -e 1G -f 4 -w 3 -n 10 -c 0 > ${O}_sendrecv_cap$cap.txt 2>&1; echo "cap=$cap rc=$?"; tail -n 4 ${O}_sendrecv_cap$cap.txt
+done
+echo "=== DDP demo: our backend vs NCCL on the same box ==="
+for be in b200coll nccl; do
+  timeout 300 $TR --master-port $((29900 + RANDOM % 90)) demo/gpu-training/ddp_b200coll.py --steps 30 --backend $be 2> ${O}_ddp_$be.err | tail -n 1 | tee ${O}_ddp_$be.json
 done
 echo "=== tools on hardware (fault injector last: it kills its own context on purpose) ==="
 B200_RUN_FAULT_INJECTION=1 timeout 300 python -m pytest tests/test_zz_tools_gpu.py -q -m gpu > ${O}_pytest_tools.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_tools.log
