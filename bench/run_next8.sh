@@ -60,6 +60,7 @@ for cap in 4 8 16; do
   B200COLL_P2P_MAX_BLOCKS=$cap timeout 200 ./build/sendrecv_perf --devs $ALL --procs -b 64K -e 1G -f 4 -w 3 -n 10 -c 0 > ${O}_sendrecv_cap$cap.txt 2>&1; echo "cap=$cap rc=$?"; tail -n 4 ${O}_sendrecv_cap$cap.txt
 done
 echo "=== DDP demo: our backend vs NCCL on the same box ==="
+timeout 300 $TR --master-port $((29900 + RANDOM % 90)) demo/gpu-training/ddp_b200coll.py --steps 30 --arena-pool 2> ${O}_ddp_pool.err | tail -n 1 | tee ${O}_ddp_pool.json
 for be in b200coll nccl; do
   timeout 300 $TR --master-port $((29900 + RANDOM % 90)) demo/gpu-training/ddp_b200coll.py --steps 30 --backend $be 2> ${O}_ddp_$be.err | tail -n 1 | tee ${O}_ddp_$be.json
 done

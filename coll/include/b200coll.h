@@ -150,6 +150,11 @@ b200collResult_t b200collHostBarrier(b200collComm_t comm);
 /* --- symmetric memory: collective calls, same order and size on every rank (ncclMemAlloc analogue). */
 b200collResult_t b200collMemAlloc(b200collComm_t comm, void** ptr, size_t bytes);
 b200collResult_t b200collMemFree(b200collComm_t comm, void* ptr);
+/* PyTorch glue: `torch.cuda.memory.CUDAPluggableAllocator(lib, "b200collTorchAlloc", "b200collTorchFree")` + `torch.cuda.MemPool` put
+ * tensors into the arena of the communicator named by SetAllocatorComm (same allocation sequence on every rank, as for MemAlloc). */
+b200collResult_t b200collSetAllocatorComm(b200collComm_t comm);
+void* b200collTorchAlloc(size_t size, int device, void* stream);
+void b200collTorchFree(void* ptr, size_t size, int device, void* stream);
 /* 1 if [ptr, ptr+bytes) lies in this rank's symmetric arena. */
 int b200collIsSymmetric(b200collComm_t comm, const void* ptr, size_t bytes);
 

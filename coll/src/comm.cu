@@ -557,8 +557,11 @@ b200collResult_t b200collCommSplit(b200collComm_t parent, int color, int key, b2
   return rc;
 }
 
+static std::atomic<b200collComm*> g_alloc_comm{nullptr};      // communicator behind b200collTorchAlloc / b200collTorchFree (below)
+
 b200collResult_t b200collCommDestroy(b200collComm_t c) {
   if (!c) return b200collInvalidArgument;
+  { b200collComm* expected = c; g_alloc_comm.compare_exchange_strong(expected, nullptr); }      // frees arriving later become no-ops instead of touching a dead arena
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
@@ -642,6 +645,22 @@ int b200collIsSymmetric(b200collComm_t c, const void* ptr, size_t bytes) {
   if (!c || !ptr) return 0;
   const CUdeviceptr p = reinterpret_cast<CUdeviceptr>(ptr), base = c->peer_va[c->rank];
   return p >= base + kOffStage && p + bytes <= base + c->arena.total;
+}
+
+// ---- PyTorch pluggable allocator (torch.cuda.memory.CUDAPluggableAllocator + torch.cuda.MemPool): tensors created under the pool live in
+// the symmetric arena of the communicator named here, so the collectives on them are zero-copy and NVLS-capable without the application
+// calling MemAlloc itself (what ncclMemAlloc is to PyTorch's NCCL pools). Symmetry needs the same allocation sequence on every rank, which
+// SPMD training code has by construction. One allocator communicator per process.
+b200collResult_t b200collSetAllocatorComm(b200collComm_t c) { g_alloc_comm.store(c); return b200collSuccess; }
+void* b200collTorchAlloc(size_t size, int /*device*/, void* /*stream*/) {
+  b200collComm* c = g_alloc_comm.load();
+  void* p = nullptr;
+  if (!c || b200collMemAlloc(c, &p, size) != b200collSuccess) return nullptr;       // PyTorch turns nullptr into its out-of-memory error
+  return p;
+}
+void b200collTorchFree(void* ptr, size_t /*size*/, int /*device*/, void* /*stream*/) {
+  b200collComm* c = g_alloc_comm.load();
+  if (c && ptr) b200collMemFree(c, ptr);
 }
 
 b200collResult_t b200collCommSetAlgo(b200collComm_t c, b200collAlgo_t a) {

@@ -113,6 +113,9 @@ def load() -> C.CDLL:
     L.b200collMemAlloc.argtypes = [vp, C.POINTER(vp), sz]
     L.b200collMemFree.argtypes = [vp, vp]
     L.b200collIsSymmetric.argtypes = [vp, vp, sz]
+    L.b200collSetAllocatorComm.argtypes = [vp]
+    L.b200collTorchAlloc.argtypes = [sz, ci, vp]; L.b200collTorchAlloc.restype = vp
+    L.b200collTorchFree.argtypes = [vp, sz, ci, vp]; L.b200collTorchFree.restype = None
     L.b200collAllReduce.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
     L.b200collAllGather.argtypes = [vp, vp, sz, C.POINTER(Epilogue), vp, vp]
     L.b200collReduceScatter.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
@@ -239,6 +242,19 @@ class Comm:
         cfg = cls.make_config(arena_mb, **kw)
         _check(L.b200collCommInitAll(hs, n, devs, C.byref(cfg)), "CommInitAll")
         return [cls(hs[i]) for i in range(n)]
+
+    def mem_pool(self):
+        """A `torch.cuda.MemPool` whose memory is this communicator's symmetric arena (PyTorch's pluggable-allocator hook calling
+        b200collMemAlloc). Tensors created under `torch.cuda.use_mem_pool(pool)` — a model's parameters, DDP's gradient buckets with
+        `gradient_as_bucket_view=True` — are then arena tensors: collectives on them skip staging and may use NVLS. Every rank must
+        allocate the same sizes in the same order inside the pool (SPMD code does). One pool-backed communicator per process."""
+        import torch
+        from torch.cuda.memory import CUDAPluggableAllocator
+        if getattr(self, "_pool", None) is None:
+            _check(load().b200collSetAllocatorComm(self._h), "SetAllocatorComm")
+            self._pool_allocator = CUDAPluggableAllocator(lib_path(), "b200collTorchAlloc", "b200collTorchFree")
+            self._pool = torch.cuda.MemPool(self._pool_allocator.allocator())
+        return self._pool
 
     def split(self, color: int, key: int = 0, arena_mb: Optional[int] = None, **kw) -> Optional["Comm"]:
         """ncclCommSplit: every rank of this (multi-process) communicator calls it; ranks with the same color >= 0 get a new communicator

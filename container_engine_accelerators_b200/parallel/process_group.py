@@ -136,6 +136,11 @@ class B200CollProcessGroup(dist.ProcessGroup):
         """A tensor in the symmetric arena (same call order and sizes on every rank): zero-copy collectives, NVLS capable."""
         return self.comm.empty(numel, dtype)
 
+    def mem_pool(self):
+        """`with torch.cuda.use_mem_pool(pg.mem_pool()): ...` allocates in the symmetric arena (see `Comm.mem_pool`): wrap model and
+        DDP construction in it and the gradient all-reduces become zero-copy."""
+        return self.comm.mem_pool()
+
     def shutdown(self) -> None:
         if self._comm is not None:
             self._flush_p2p()

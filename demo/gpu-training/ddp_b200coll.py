@@ -57,6 +57,7 @@ def main() -> int:
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--vocab", type=int, default=8192)
     ap.add_argument("--backend", default="b200coll", help="b200coll (default) or nccl, for an A/B on the same box")
+    ap.add_argument("--arena-pool", action="store_true", help="allocate parameters and DDP's gradient buckets in the transport's symmetric arena (zero-copy, NVLS-capable all-reduce)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29511")
@@ -66,8 +67,13 @@ def main() -> int:
     device = torch.device("cuda", local) if cuda else torch.device("cpu")
     dist.init_process_group(args.backend if cuda or args.backend == "b200coll" else "gloo", rank=rank, world_size=world)
     torch.manual_seed(1234)                                       # same initial weights everywhere; DDP would broadcast them anyway
-    model = Model(args.vocab, args.dim, args.layers).to(device)
-    ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local] if cuda else None)
+    import contextlib
+    pool = contextlib.nullcontext()
+    if args.arena_pool and cuda and args.backend == "b200coll":
+        pool = torch.cuda.use_mem_pool(dist.group.WORLD.mem_pool())      # same allocation sequence on every rank: this is SPMD code
+    with pool:
+        model = Model(args.vocab, args.dim, args.layers).to(device)
+        ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local] if cuda else None, gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(ddp.parameters(), lr=3e-4)
     gen = torch.Generator(device=device).manual_seed(100 + rank)   # each rank draws its own shard of the synthetic stream
     losses, t0 = [], None

@@ -333,3 +333,16 @@ def test_comm_split_plan_orders_by_key_then_rank(coll_lib):
                 members = sorted((keys[r], r) for r in range(4) if colors[r] == col)
                 assert [got[r] for _, r in members] == [(i, len(members)) for i in range(len(members))]
     assert L.b200collDebugSplitPlan(9, 0, None, None, None, None) != 0
+
+
+def test_pytorch_pluggable_allocator_entry_points(coll_lib):
+    """b200collTorchAlloc / b200collTorchFree have the signature torch.cuda.memory.CUDAPluggableAllocator wants; without an allocator
+    communicator they fail softly (nullptr = PyTorch's out-of-memory path), never crash."""
+    L = C.CDLL(coll_lib)
+    L.b200collTorchAlloc.argtypes = [C.c_size_t, C.c_int, C.c_void_p]; L.b200collTorchAlloc.restype = C.c_void_p
+    L.b200collTorchFree.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]; L.b200collTorchFree.restype = None
+    assert L.b200collTorchAlloc(1 << 20, 0, None) is None
+    L.b200collTorchFree(None, 0, 0, None); L.b200collTorchFree(C.c_void_p(0x1000), 16, 0, None)      # no communicator: ignored
+    from torch.cuda.memory import CUDAPluggableAllocator
+    alloc = CUDAPluggableAllocator(coll_lib, "b200collTorchAlloc", "b200collTorchFree")                # resolves both symbols
+    assert alloc.allocator() is not None

@@ -215,7 +215,16 @@ def _gpu_pair(rank, world):
     for r in dist.batch_isend_irecv(ops):
         r.wait()
     assert big.eq(float(other + 1)).all() and pg.fallback_calls == before
-    assert pg.fast_calls >= 12
+    # tensors created under the group's memory pool live in the symmetric arena: collectives on them are not staged
+    staged_before = pg.comm.stats()["staged_calls"]
+    with torch.cuda.use_mem_pool(pg.mem_pool()):
+        pooled = torch.full((8 << 20,), float(rank + 1), device="cuda")                   # 32 MiB: far beyond the Lamport path
+    assert pg.comm.is_symmetric(pooled)
+    dist.all_reduce(pooled)
+    torch.cuda.synchronize()
+    assert pooled.eq(3.0).all() and pg.comm.stats()["staged_calls"] == staged_before
+    del pooled
+    assert pg.fast_calls >= 13
     return pg.fast_calls
 
 
