@@ -7,7 +7,7 @@ manifests:                   ## regenerate deploy/**.yaml from deploy/generate.p
 	$(PY) deploy/generate.py
 test: build                  ## CPU test-suite (GPU tests: `make test-gpu` on a B200 box)
 	$(PY) -m pytest tests -x -q -m "not gpu"
-conformance: build           ## the fourteen kubelet-side scenarios against both plugin implementations, as processes
+conformance: build           ## the fifteen kubelet-side scenarios against both plugin implementations, as processes
 	$(PY) conformance/run.py --impl native
 	$(PY) conformance/run.py --impl python
 test-race: build             ## the native daemons under ThreadSanitizer, then AddressSanitizer+UBSan (role of `go test -race`, reference Makefile:21)

@@ -249,6 +249,28 @@ def kubelet_restart(cmd):
         n.close()
 
 
+def sigterm_clean_exit(cmd):
+    """SIGTERM (pod deletion, rolling update): the plugin stops serving, removes its socket and exits 0 — also with a watch stream open."""
+    n = Node(cmd)
+    try:
+        n.kubelet.wait_registration(20)
+        c = n.connect()
+        stream, devs = first_list(c)
+        assert len(devs) == 2
+        sock = os.path.join(n.plugin_dir, n.endpoint)
+        assert os.path.exists(sock)
+        n.process.send_signal(signal.SIGTERM)
+        try:
+            rc = n.process.wait(10)
+        except subprocess.TimeoutExpired:
+            raise AssertionError("plugin still running 10 s after SIGTERM; log:\n" + n.logs()[-2000:]) from None
+        assert rc == 0, f"exit code {rc}; log:\n{n.logs()[-2000:]}"
+        assert not os.path.exists(sock), "plugin socket left behind"
+        stream.cancel()
+    finally:
+        n.close()
+
+
 def xid_marks_unhealthy(cmd):
     """A health-critical Xid (XID_CONFIG) turns the device Unhealthy in the ListAndWatch stream and blocks its allocation; others are ignored."""
     events = tempfile.NamedTemporaryFile("w", suffix=".events", delete=False)
@@ -394,7 +416,7 @@ def transport_profile(cmd):
         n.close()
 
 
-SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later, kubelet_restart,
+SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later, kubelet_restart, sigterm_clean_exit,
              xid_marks_unhealthy, xid_on_a_mig_slice, metrics_endpoint, mps_sharing, transport_profile]
 
 

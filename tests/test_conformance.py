@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_conformance_suite(impl, native_build):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "conformance", "run.py"), "--impl", impl], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK: all scenarios passed" in r.stdout, r.stdout + r.stderr
-    assert r.stdout.count("PASS") == 14
+    assert r.stdout.count("PASS") == 15
 
 
 def test_go_style_flags_are_accepted_by_the_python_agent():
