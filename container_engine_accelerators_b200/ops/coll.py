@@ -407,6 +407,27 @@ class Comm:
     # ---------------------------------------------------------------- control / introspection
     def set_algo(self, name: str) -> None:
         _check(load().b200collCommSetAlgo(self._h, ALGO_NAMES.index(name)), "CommSetAlgo")
+        self._algo = name
+
+    class _BitExact:
+        """Payloads that are not floating point (token ids, masks) must not take the Lamport path: it recognises empty slots by a NaN bit
+        pattern and rewrites payload words that collide with it (harmless for floats, fatal for an int64 -1), and it passes data through
+        fp32 registers. The barrier-based push kernels forward 16-byte vectors untouched when the epilogue is the identity."""
+
+        def __init__(self, comm):
+            self.comm, self.prev = comm, getattr(comm, "_algo", "auto")
+
+        def __enter__(self):
+            self.comm.set_algo("twoshot")
+            return self.comm
+
+        def __exit__(self, *exc):
+            self.comm.set_algo(self.prev)
+            return False
+
+    def bit_exact(self) -> "Comm._BitExact":
+        """`with comm.bit_exact(): comm.all_gather(words, out)` — moves arbitrary bits (viewed as fp16 / fp32 words) unchanged."""
+        return Comm._BitExact(self)
 
     def set_max_ctas(self, n: int) -> None:
         _check(load().b200collCommSetMaxCtas(self._h, n), "CommSetMaxCtas")

@@ -247,6 +247,18 @@ class B200CollProcessGroup(dist.ProcessGroup):
             return raw.view(torch.float16)
         return None
 
+    @classmethod
+    def _word_views(cls, *tensors):
+        """All-gather and all-to-all only move bits, so any dtype can ride the fp kernels: the same word type for every tensor, or None."""
+        views = [cls._as_words(t) for t in tensors]
+        if any(v is None for v in views):
+            return None
+        if len({v.dtype for v in views}) > 1:                  # e.g. one tensor's byte count is only a multiple of 2: use the narrower word
+            views = [t.view(-1).view(torch.uint8).view(torch.float16) if (t.numel() * t.element_size()) % 2 == 0 else None for t in tensors]
+            if any(v is None for v in views):
+                return None
+        return views
+
     def reduce(self, tensors, opts=None):
         root = opts.rootRank if opts is not None else 0
         op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
@@ -268,6 +280,13 @@ class B200CollProcessGroup(dist.ProcessGroup):
                 and output.numel() == input.numel() * self._size:
             with self._ordered(self):
                 self.comm.all_gather(input.view(-1), output.view(-1))
+            self.fast_calls += 1
+            return _Work(output)
+        words = self._word_views(output, input) if output.dtype == input.dtype and output.numel() == input.numel() * self._size \
+            and (input.numel() * input.element_size()) % 16 == 0 else None
+        if words is not None:                                   # integer / bool / fp8 payloads (token ids, masks): moved as raw words
+            with self._ordered(self), self.comm.bit_exact():
+                self.comm.all_gather(words[1], words[0])
             self.fast_calls += 1
             return _Work(output)
         chunks = list(output.view(-1).chunk(self._size))
@@ -330,6 +349,13 @@ class B200CollProcessGroup(dist.ProcessGroup):
                 and input.numel() % n == 0 and (input.numel() // n * input.element_size()) % 16 == 0 and output.numel() == input.numel():
             with self._ordered(self):
                 self.comm.all_to_all(input.view(-1), output.view(-1))
+            self.fast_calls += 1
+            return _Work(output)
+        words = self._word_views(output, input) if even and output.dtype == input.dtype and output.data_ptr() != input.data_ptr() and input.numel() % n == 0 \
+            and (input.numel() // n * input.element_size()) % 16 == 0 and output.numel() == input.numel() else None
+        if words is not None:
+            with self._ordered(self), self.comm.bit_exact():
+                self.comm.all_to_all(words[1], words[0])
             self.fast_calls += 1
             return _Work(output)
         row_elems = input[0].numel() if input.dim() > 0 and input.shape[0] > 0 else 0

@@ -215,6 +215,13 @@ def _gpu_pair(rank, world):
     for r in dist.batch_isend_irecv(ops):
         r.wait()
     assert big.eq(float(other + 1)).all() and pg.fallback_calls == before
+    # integer payloads ride the same kernels as raw words, bit for bit (an int64 -1 is all ones: the Lamport path would rewrite it)
+    before = pg.fallback_calls
+    ids = torch.full((4096,), -1, device="cuda", dtype=torch.int64); ids[::7] = rank
+    gathered = torch.empty(2 * 4096, device="cuda", dtype=torch.int64)
+    dist.all_gather_into_tensor(gathered, ids)
+    want0 = torch.full((4096,), -1, device="cuda", dtype=torch.int64); want1 = want0.clone(); want0[::7] = 0; want1[::7] = 1
+    assert torch.equal(gathered, torch.cat([want0, want1])) and pg.fallback_calls == before
     # tensors created under the group's memory pool live in the symmetric arena: collectives on them are not staged
     staged_before = pg.comm.stats()["staged_calls"]
     with torch.cuda.use_mem_pool(pg.mem_pool()):
@@ -316,3 +323,37 @@ def test_ddp_demo_trains_on_the_backend():
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["backend"] == "b200coll" and out["world"] == 2 and out["replicas_in_sync"] is True
     assert out["last_loss"] < out["first_loss"] and out["fallback_calls"] > 0
+
+
+def test_integer_payloads_move_as_words_and_never_take_the_lamport_path(monkeypatch):
+    """all_gather_into_tensor / all_to_all_single of int64 token ids on device tensors: viewed as fp32 words, with the communicator switched
+    to the bit-exact (barrier-based, identity epilogue) kernels for the duration of the call — the Lamport path rewrites words that look
+    like its empty-slot marker, which an int64 -1 does."""
+    class _Stream:
+        def wait_event(self, e): pass
+    class _Event:
+        def record(self, s): pass
+    stream = _Stream()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: stream)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    log = []
+
+    class _Comm:
+        nranks = 2
+        _algo = "auto"
+        def set_algo(self, name): log.append(("algo", name)); self._algo = name
+        def bit_exact(self): return pgmod.coll.Comm._BitExact(self)
+        def all_gather(self, src, dst): log.append(("all_gather", src.dtype, src.numel(), dst.numel()))
+        def all_to_all(self, src, dst): log.append(("all_to_all", src.dtype, src.numel(), dst.numel()))
+    pg = pgmod.B200CollProcessGroup(store=None, rank=0, size=2)
+    pg._comm = _Comm()
+    ids = _DeviceLike.of(torch.full((64,), -1, dtype=torch.int64))
+    out = _DeviceLike.of(torch.zeros(128, dtype=torch.int64))
+    pg._allgather_base(out, ids)
+    assert log == [("algo", "twoshot"), ("all_gather", torch.float32, 128, 256), ("algo", "auto")]
+    del log[:]
+    pg.alltoall_base(_DeviceLike.of(torch.zeros(64, dtype=torch.int64)), ids, [], [])
+    assert log == [("algo", "twoshot"), ("all_to_all", torch.float32, 128, 128), ("algo", "auto")]
+    del log[:]
+    flt = _DeviceLike.of(torch.zeros(64)); pg._allgather_base(_DeviceLike.of(torch.zeros(128)), flt)      # real floats keep the tuner's choice
+    assert log == [("all_gather", torch.float32, 64, 128)] and pg.fast_calls == 3 and pg.fallback_calls == 0
