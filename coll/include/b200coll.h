@@ -205,6 +205,7 @@ b200collResult_t b200collDebugPlanP2p(int rank, int nranks, int loopback, size_t
 b200collAlgo_t b200collTunerPick(b200collOp_t op, size_t bytes, int nranks, int nvls_available);
 /* Force an algorithm for subsequent calls on this comm (b200collAlgoAuto restores the table). */
 b200collResult_t b200collCommSetAlgo(b200collComm_t comm, b200collAlgo_t algo);
+b200collAlgo_t b200collCommGetAlgo(b200collComm_t comm);   /* what SetAlgo (or B200COLL_ALGO) last forced; Auto = the tuner decides */
 b200collResult_t b200collCommSetMaxCtas(b200collComm_t comm, int max_ctas);
 /* Receives into buffers outside the arena go through two staging windows per operation; this caps the window size (a multiple of
  * 512 bytes; 0 = an equal share of the 64 MiB staging area). A private choice of the receiver: the sender follows what is posted. */

@@ -663,6 +663,8 @@ void b200collTorchFree(void* ptr, size_t /*size*/, int /*device*/, void* /*strea
   if (c && ptr) b200collMemFree(c, ptr);
 }
 
+b200collAlgo_t b200collCommGetAlgo(b200collComm_t c) { return c ? c->forced_algo : b200collAlgoAuto; }
+
 b200collResult_t b200collCommSetAlgo(b200collComm_t c, b200collAlgo_t a) {
   if (!c || a < 0 || a >= b200collNumAlgos) return b200collInvalidArgument;
   c->forced_algo = a;

@@ -249,11 +249,27 @@ ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataT
   b200collEpilogue ep{t, t, scale};
   return map_rc(b200collAllReduce(send, recv, count, &ep, rop, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
+static bool map_dt_as_words(ncclDataType_t dt, size_t count, b200collDataType_t* t, size_t* n);
+// All-gather moves bits, so integer types ride the fp kernels as words — on the barrier-based kernels only: the Lamport path marks empty
+// slots with a NaN pattern and rewrites payload words equal to it (harmless for floats, wrong for an int32 -1).
+struct BitExactScope {
+  b200collComm_t c; b200collAlgo_t prev;
+  explicit BitExactScope(b200collComm_t comm) : c(comm), prev(b200collCommGetAlgo(comm)) { b200collCommSetAlgo(c, b200collAlgoTwoShot); }
+  ~BitExactScope() { b200collCommSetAlgo(c, prev); }
+};
 ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t dt, ncclComm_t comm, cudaStream_t stream) {
+  if (!comm) return ncclInvalidArgument;
+  b200collComm_t c = reinterpret_cast<ShimComm*>(comm)->comm;
   b200collDataType_t t;
-  if (!comm || !map_dt(dt, &t)) return ncclInvalidArgument;
+  if (map_dt(dt, &t)) {
+    b200collEpilogue ep{t, t, 1.0f};
+    return map_rc(b200collAllGather(send, recv, sendcount, &ep, c, stream));
+  }
+  size_t n = 0;
+  if (!map_dt_as_words(dt, sendcount, &t, &n)) return ncclInvalidArgument;
   b200collEpilogue ep{t, t, 1.0f};
-  return map_rc(b200collAllGather(send, recv, sendcount, &ep, reinterpret_cast<ShimComm*>(comm)->comm, stream));
+  BitExactScope exact(c);
+  return map_rc(b200collAllGather(send, recv, n, &ep, c, stream));
 }
 ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;

@@ -129,6 +129,7 @@ def load() -> C.CDLL:
     L.b200collRecv.argtypes = [vp, sz, ci, vp, vp]
     L.b200collTunerPick.argtypes = [ci, sz, ci, ci]; L.b200collTunerPick.restype = ci
     L.b200collCommSetAlgo.argtypes = [vp, ci]
+    L.b200collCommGetAlgo.argtypes = [vp]; L.b200collCommGetAlgo.restype = ci
     L.b200collCommSetMaxCtas.argtypes = [vp, ci]
     L.b200collCommSetLaunchShape.argtypes = [vp, ci, ci, ci]
     L.b200collCommSetP2pWindow.argtypes = [vp, sz]
@@ -415,7 +416,8 @@ class Comm:
         fp32 registers. The barrier-based push kernels forward 16-byte vectors untouched when the epilogue is the identity."""
 
         def __init__(self, comm):
-            self.comm, self.prev = comm, getattr(comm, "_algo", "auto")
+            self.comm = comm
+            self.prev = getattr(comm, "_algo", None) or ALGO_NAMES[load().b200collCommGetAlgo(comm._h)]      # B200COLL_ALGO may have forced one at init
 
         def __enter__(self):
             self.comm.set_algo("twoshot")

@@ -657,6 +657,15 @@ def test_nccl_api_shim_send_recv(torch_cuda, coll_lib):
         s.ck(L.ncclGroupEnd())
         torch.cuda.synchronize()
         assert torch.equal(x01, y01) and torch.equal(x10, y10)
+        # integer all-gather: words on the bit-exact kernels (an int64 -1 must survive; small enough that floats would take the Lamport path)
+        part = [torch.full((1000,), -1, device="cuda", dtype=torch.int64) for _ in range(n)]
+        for r in range(n):
+            part[r][::3] = r + 5
+        full = [torch.zeros(1000 * n, dtype=torch.int64, device="cuda") for _ in range(n)]
+        for r in range(n):
+            s.ck(L.ncclAllGather(p(part[r]), p(full[r]), 1000, s.I64, comms[r], st[r]))
+        torch.cuda.synchronize()
+        assert all(torch.equal(f, torch.cat(part)) for f in full)
         for r in range(n):
             err = C.c_int(-1)
             s.ck(L.ncclCommGetAsyncError(comms[r], C.byref(err)))
