@@ -56,7 +56,7 @@ for impl in reference ours; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --op sendrecv --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
 done
 echo "--- CTAs per send/recv operation (B200COLL_P2P_MAX_BLOCKS): pick the default from this"
-for cap in 4 8 16; do
+for cap in 8 16 32; do
   B200COLL_P2P_MAX_BLOCKS=$cap timeout 200 ./build/sendrecv_perf --devs $ALL --procs -b 64K -e 1G -f 4 -w 3 -n 10 -c 0 > ${O}_sendrecv_cap$cap.txt 2>&1; echo "cap=$cap rc=$?"; tail -n 4 ${O}_sendrecv_cap$cap.txt
 done
 echo "=== DDP demo: our backend vs NCCL on the same box ==="

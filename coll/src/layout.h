@@ -27,7 +27,7 @@ constexpr uint32_t kLLSanitized = 0x7FFF7FFFu;          // still NaN in every su
 // Point-to-point mailboxes, in the zero-initialised part of the first megabyte that the flag matrix does not use.
 //   post: u64 [receiver rank][CTA][2 slots][2 words], written by the RECEIVER into the SENDER's arena ("write n bytes at this offset of mine")
 //   done: u32 [sender rank][CTA],                      written by the SENDER into the RECEIVER's arena ("chunk number seq has landed")
-constexpr int kP2pMaxBlocks = 16;                       // CTAs per send or recv operation
+constexpr int kP2pMaxBlocks = 32;                       // CTAs per send or recv operation: mailbox capacity (the default cap is lower, see p2p_blocks)
 constexpr size_t kOffP2pPost = 256 << 10;
 constexpr size_t kP2pPostBytes = (size_t)kMaxRanks * kP2pMaxBlocks * 2 * 2 * 8;
 constexpr size_t kOffP2pDone = kOffP2pPost + kP2pPostBytes;
