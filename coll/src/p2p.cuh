@@ -32,6 +32,10 @@ struct P2pArgs {
   unsigned long long win_off[2 * kMaxRanks];     // recv: arena offset of the (first) window
   unsigned long long win_bytes[2 * kMaxRanks];   // recv: bytes per window (>= bytes when not staged)
 };
+struct P2pShared { unsigned long long off, n; int bad; };
+#ifndef P2P_SHARED                               // the host emulator maps this to per-CTA storage shared by the CTA's threads
+#define P2P_SHARED(name) __shared__ P2pShared name
+#endif
 constexpr int kP2pThreads = 512;
 constexpr unsigned long long kP2pValueMask = (1ull << kP2pValueBits) - 1;
 
@@ -65,8 +69,7 @@ __device__ __forceinline__ void p2p_move_share(char* dst, const char* src, unsig
 
 __global__ void __launch_bounds__(kP2pThreads) k_p2p(COMM_PARAM, const __grid_constant__ P2pArgs a, uint32_t op) {
   pdl_prologue();
-  __shared__ unsigned long long sh_off, sh_n;
-  __shared__ int sh_bad;
+  P2P_SHARED(sh);                                // per-CTA: what thread 0 learnt from a mailbox, for the other threads
   int o = 0;
   while (o + 1 < a.nops && (int)blockIdx.x >= a.first_block[o + 1]) o++;
   const int sub = (int)blockIdx.x - a.first_block[o], nb = a.first_block[o + 1] - a.first_block[o];
@@ -101,12 +104,12 @@ __global__ void __launch_bounds__(kP2pThreads) k_p2p(COMM_PARAM, const __grid_co
           }
         }
         (void)ld_acquire_sys_u64(box + 1);       // the receiver finished with the window's previous contents before it posted
-        sh_off = (wa & kP2pValueMask) * 16; sh_n = wb & kP2pValueMask; sh_bad = bad;
+        sh.off = (wa & kP2pValueMask) * 16; sh.n = wb & kP2pValueMask; sh.bad = bad;
       }
       __syncthreads();
-      const unsigned long long off = sh_off, n = sh_n;
-      const int bad = sh_bad;
-      __syncthreads();                           // sh_* are rewritten in the next round
+      const unsigned long long off = sh.off, n = sh.n;
+      const int bad = sh.bad;
+      __syncthreads();                           // sh is rewritten in the next round
       if (bad) break;
       if (n == 0 || n > total - sent) {          // the two sides disagree about the message size
         if (threadIdx.x == 0) record_fault(c, 4, (uint32_t)peer, (uint32_t)(total - sent), (uint32_t)n, op);
@@ -159,10 +162,10 @@ __global__ void __launch_bounds__(kP2pThreads) k_p2p(COMM_PARAM, const __grid_co
           }
         }
         (void)ld_acquire_sys(done);
-        sh_bad = bad;
+        sh.bad = bad;
       }
       __syncthreads();
-      const int bad = sh_bad;
+      const int bad = sh.bad;
       __syncthreads();
       if (bad) break;
       if (staged) {

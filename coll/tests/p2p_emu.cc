@@ -1,5 +1,6 @@
 // Host emulation of the point-to-point protocol: compiles coll/src/p2p.cuh — the very text nvcc compiles for sm_100a — with g++,
-// every CTA of every rank a std::thread (one "CUDA thread" per CTA: thread 0 is the one that runs the protocol), arenas in host memory,
+// every CTA of every rank a group of std::threads (--threads N per CTA, default 1; thread 0 runs the protocol, the others move data and
+// meet it at __syncthreads), arenas in host memory,
 // the cross-GPU flag primitives mapped to C++ atomics of the same strength (relaxed / release / acquire). The scenarios below are the
 // ones tests/test_coll_gpu.py runs on hardware; here they run under a real scheduler and, in the `tsan` build, under ThreadSanitizer,
 // which checks exactly what the protocol promises: every plain payload access is ordered by a release/acquire pair on a flag.
@@ -13,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -22,14 +24,29 @@
 struct uint4 { uint32_t x, y, z, w; };
 struct Dim { unsigned x; };
 static thread_local Dim threadIdx{0}, blockIdx{0}, blockDim{1}, gridDim{1};
+// A CTA is a group of host threads that share one P2pShared and one barrier (bar.sync). The barrier is a plain sense-reversing counter on
+// C++ atomics (acq_rel), so ThreadSanitizer sees exactly the ordering __syncthreads() gives and flags anything that relies on more.
+struct CtaBarrier {
+  std::atomic<unsigned> arrived{0}, phase{0};
+  unsigned n = 1;
+  void wait() {
+    const unsigned p = phase.load(std::memory_order_acquire);
+    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == n) { arrived.store(0, std::memory_order_relaxed); phase.store(p + 1, std::memory_order_release); }
+    else while (phase.load(std::memory_order_acquire) == p) std::this_thread::yield();
+  }
+};
+struct CtaCtx;
+static thread_local CtaCtx* g_cta = nullptr;
 #define __global__
 #define __device__
 #define __forceinline__ inline
 #define __launch_bounds__(n)
 #define __grid_constant__
-#define __shared__ static thread_local      /* one thread per CTA: per-CTA storage is per-thread storage */
 #define COMM_PARAM CommDev c
-static inline void __syncthreads() {}
+#define P2P_SHARED(name) P2pShared& name = emu_shared()
+namespace b200coll { struct P2pShared; }
+static inline b200coll::P2pShared& emu_shared();
+static inline void __syncthreads();
 
 namespace b200coll {
 static inline void pdl_prologue() {}
@@ -56,6 +73,11 @@ static inline void st_vec(void* p, const uint4& v) { memcpy(p, &v, 16); }
 #include "../src/p2p.cuh"
 
 using namespace b200coll;
+
+struct CtaCtx { CtaBarrier bar; P2pShared shared{}; };
+static inline P2pShared& emu_shared() { return g_cta->shared; }
+static inline void __syncthreads() { g_cta->bar.wait(); }
+static unsigned g_threads_per_cta = 1;      // --threads N: N host threads per CTA (exercises the bar.sync placement and the strided loops)
 
 // ---- a "machine": n ranks, each with an arena, state words and a fault record -----------------------------------------------------
 struct Rank {
@@ -112,15 +134,23 @@ static void launch_all(Machine& m, const std::vector<std::vector<Op>>& per_rank,
   std::vector<std::thread> threads;
   std::vector<P2pArgs> args(m.n);
   for (int r = 0; r < m.n; r++) args[r] = plan(m, r, per_rank[r], cap, window_cap);
+  std::vector<std::unique_ptr<CtaCtx>> ctas;
+  const unsigned T = g_threads_per_cta;
   for (int r = 0; r < m.n; r++) {
     if (per_rank[r].empty()) continue;
     const int grid = args[r].first_block[args[r].nops];
-    for (int b = 0; b < grid; b++)
-      threads.emplace_back([&m, &args, r, b, grid, skew_us] {
-        if (skew_us && (r + b) % 3 == 0) { timespec t{0, (long)skew_us * 1000}; nanosleep(&t, nullptr); }
-        threadIdx.x = 0; blockDim.x = 1; blockIdx.x = (unsigned)b; gridDim.x = (unsigned)grid;
-        k_p2p(m.ranks[r].dev, args[r], 6u);
-      });
+    for (int b = 0; b < grid; b++) {
+      ctas.emplace_back(new CtaCtx());
+      CtaCtx* ctx = ctas.back().get();
+      ctx->bar.n = T;
+      for (unsigned t = 0; t < T; t++)
+        threads.emplace_back([&m, &args, ctx, r, b, t, T, grid, skew_us] {
+          if (skew_us && (r + b + t) % 3 == 0) { timespec ts{0, (long)skew_us * 1000}; nanosleep(&ts, nullptr); }
+          g_cta = ctx;
+          threadIdx.x = t; blockDim.x = T; blockIdx.x = (unsigned)b; gridDim.x = (unsigned)grid;
+          k_p2p(m.ranks[r].dev, args[r], 6u);
+        });
+    }
   }
   for (auto& t : threads) t.join();
 }
@@ -217,7 +247,12 @@ static void scenario_faults() {
 }
 
 int main(int argc, char** argv) {
-  const bool quick = argc > 1 && !strcmp(argv[1], "--quick");
+  bool quick = false;
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "--quick")) quick = true;
+    else if (!strcmp(argv[i], "--threads") && i + 1 < argc) g_threads_per_cta = (unsigned)atoi(argv[++i]);
+  }
+  if (g_threads_per_cta < 1 || g_threads_per_cta > 8) { fprintf(stderr, "--threads 1..8\n"); return 2; }
   for (int n : {2, 4}) {
     scenario_ring(n, true, 0, 16);
     scenario_ring(n, false, 1u << 20, 16);       // 3 MiB + 5 B through 1 MiB windows: 4 chunks, both windows reused

@@ -296,16 +296,18 @@ def test_point_to_point_protocol_under_host_emulation(coll_lib):
     r = subprocess.run(["make", "-C", root, "../build/p2p_emu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     exe = os.path.join(os.path.dirname(root), "build", "p2p_emu")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "all scenarios passed" in r.stdout, r.stdout + r.stderr
+    for extra in ([], ["--quick", "--threads", "4"]):            # one host thread per CTA, then four (bar.sync placement, strided loops)
+        r = subprocess.run([exe] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "all scenarios passed" in r.stdout, r.stdout + r.stderr
     if shutil.which("/usr/bin/g++") is None:
         pytest.skip("no system g++ for the ThreadSanitizer flavour")
     b = subprocess.run(["make", "-C", root, "../build/p2p_emu_tsan"], capture_output=True, text=True)
     if b.returncode != 0 and "tsan" in (b.stdout + b.stderr).lower():
         pytest.skip("toolchain has no libtsan")
     assert b.returncode == 0, b.stdout + b.stderr
-    r = subprocess.run([exe + "_tsan", "--quick"], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "data race" not in r.stderr and "all scenarios passed" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    for extra in (["--quick"], ["--quick", "--threads", "2"]):
+        r = subprocess.run([exe + "_tsan"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "data race" not in r.stderr and "all scenarios passed" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_comm_split_plan_orders_by_key_then_rank(coll_lib):
