@@ -348,3 +348,21 @@ def test_pytorch_pluggable_allocator_entry_points(coll_lib):
     from torch.cuda.memory import CUDAPluggableAllocator
     alloc = CUDAPluggableAllocator(coll_lib, "b200collTorchAlloc", "b200collTorchFree")                # resolves both symbols
     assert alloc.allocator() is not None
+
+
+def test_epoch_barrier_under_host_emulation_classic_and_multicast_counter(coll_lib):
+    """coll/src/barrier.cuh (what every barrier-based kernel calls) compiled for the host, CTAs as thread groups, under ThreadSanitizer:
+    the shipped flag exchange, and the multicast-counter variant (-DB200COLL_VARIANT_MCBAR, an A/B candidate that has never met a GPU)
+    with multimem.red emulated as an add to the same word of every arena. Launches alternate grid sizes and ranks enter late; stamps
+    written between the two barriers must be readable by every peer right after the second one."""
+    import shutil
+    if shutil.which("/usr/bin/g++") is None:
+        pytest.skip("no system g++ for the ThreadSanitizer build")
+    root = os.path.dirname(os.path.dirname(coll_lib))
+    for target, what in (("barrier_emu_tsan", "(flags)"), ("barrier_emu_tsan_mc", "(flags + multicast counter)")):
+        b = subprocess.run(["make", "-C", root, f"../build/{target}"], capture_output=True, text=True)
+        if b.returncode != 0 and "tsan" in (b.stdout + b.stderr).lower():
+            pytest.skip("toolchain has no libtsan")
+        assert b.returncode == 0, b.stdout + b.stderr
+        r = subprocess.run([os.path.join(os.path.dirname(root), "build", target), "5"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "data race" not in r.stderr and f"barrier_emu {what}: all launches consistent" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
