@@ -1,29 +1,46 @@
 #!/bin/bash
-# Open items that need a multi-GPU box (none of them has been measured on NVLink yet):
-#   1. rooted collectives on the NVLS path (multimem.st fan-out, root-side multimem.ld_reduce): correctness + busbw vs NCCL
-#   2. programmatic dependent launch (B200COLL_PDL=1) at one rank per GPU: small-message latency with and without
-#   3. the multi-process NVLS test that a one-GPU box skips
-#   4. the torch.distributed process group's CUDA paths (tests/test_process_group.py, opt-in until this has passed once)
-#   5. point to point (k_p2p): virtual-rank tests, then sendrecv_perf protocol on both arms
-#   6. A/B of the compile-time variants (lib/libb200coll_{gridconst,mcbar,bulk}.so) against the shipped build, 1 KiB - 64 MiB
-# Usage: gpurun --gpus 8 --timeout 600 -- 'bash bench/run_next8.sh 8'
+# Everything that was written after the GPU time of round 1 ran out, or needs more than one GPU. Sections (second argument, comma
+# separated; default = all):
+#   tests1    virtual-rank tests of send/recv and CommSplit, the process group's CUDA paths, pipelined e2e, tools   (any box, 1 GPU is enough)
+#   multi     multi-process NVLS tests a one-GPU box skips                                                         (>= 2 GPUs)
+#   rooted    broadcast / reduce on the NVLS path, both arms                                                       (>= 3 GPUs for multicast)
+#   pdl       B200COLL_PDL=0/1 small-message latency                                                               (>= 2 GPUs)
+#   variants  shipped build vs libb200coll_{gridconst,mcbar,bulk}.so, all_reduce + all_gather                      (mcbar needs multicast)
+#   e2e       copy-then-reduce vs Comm.all_reduce_from_host                                                        (>= 2 GPUs)
+#   p2p       sendrecv on both arms + CTAs-per-operation sweep                                                     (>= 2 GPUs)
+#   ddp       DDP demo: arena pool / plain / NCCL                                                                  (>= 2 GPUs)
+# GPU-minutes are charged per GPU, so spend them in this order:
+#   gpurun --timeout 900 -- 'bash bench/run_next8.sh 1 tests1'                                  # ~6 min x 1
+#   gpurun --gpus 2 --timeout 900 -- 'bash bench/run_next8.sh 2 multi,pdl,e2e,p2p,ddp'          # ~8 min x 2
+#   gpurun --gpus 8 --timeout 600 -- 'bash bench/run_next8.sh 8 multi,rooted,pdl,variants,p2p'  # ~8 min x 8: the numbers that go into profiles/
 NG=${1:-8}
 mkdir -p gpurun_out; export B200COLL_TIMEOUT_MS=5000
 O=gpurun_out/x${NG}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
 ALL=$(python3 -c "print(','.join(str(i) for i in range($NG)))")
+SECTIONS=",${2:-tests1,multi,rooted,pdl,variants,e2e,p2p,ddp},"
+want() { case "$SECTIONS" in *",$1,"*) return 0;; *) return 1;; esac; }
+if want multi; then
 echo "== $(date -u +%T) multi-process NVLS tests"
 timeout 300 python -m pytest tests/test_coll_gpu.py -q -k "multi_gpu" > ${O}_pytest_multi.log 2>&1; echo "pytest rc=$?"; tail -n 2 ${O}_pytest_multi.log
+fi
+if want tests1; then
 echo "== $(date -u +%T) torch.distributed backend on CUDA (first run on hardware)"
 B200_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_process_group.py -q -m gpu > ${O}_pytest_pg.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_pg.log
+fi
+if want rooted; then
 echo "== $(date -u +%T) rooted ops, both arms"
 timeout 200 $TR --master-port 29731 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --extra-ops reduce --extra-out ${O}_rooted_ours.json > ${O}_bcast.json 2> ${O}_bcast.err
 timeout 200 $TR --master-port 29732 bench.py --gpus $NG --op broadcast --steps 20 --warmup 5 --table --no-e2e --impl reference --extra-ops reduce --extra-out ${O}_rooted_ref.json > ${O}_bcast_ref.json 2> ${O}_bcast_ref.err
 grep -h "Avg bus" ${O}_bcast.err ${O}_bcast_ref.err
+fi
+if want pdl; then
 echo "== $(date -u +%T) PDL off / on, all_reduce 1 KiB .. 4 MiB"
 for pdl in 0 1; do
   B200COLL_PDL=$pdl timeout 90 ./build/b200coll_perf --devs $ALL --procs --op all_reduce -b 1K -e 4M -f 4 --iters 200 --warmup 20 > ${O}_pdl${pdl}.txt 2>&1; echo "pdl=$pdl rc=$?"; grep -E "^ +[0-9]" ${O}_pdl${pdl}.txt | awk '{print $1, $4, $6}' | tr '\n' ';'; echo
 done
+fi
+if want variants; then
 echo "== $(date -u +%T) build variants (A/B candidates: kernel parameter in the constant bank; multicast barrier)"
 if [ -f coll/lib/libb200coll_gridconst.so ] && [ -f coll/lib/libb200coll_mcbar.so ] && [ -f coll/lib/libb200coll_bulk.so ]; then echo "variants: prebuilt libraries travelled with the snapshot"
 else make -C coll variants -j2 > ${O}_variants_build.log 2>&1; echo "variants rc=$?"; fi
@@ -46,12 +63,17 @@ except Exception as e:
     print(sys.argv[1], "no result:", e)
 PY
 done
+fi
+if want tests1; then
+echo "== $(date -u +%T) virtual-rank tests: send/recv, CommSplit, pipelined host all-reduce"
+B200_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_coll_gpu.py -q -k "send_recv or sendrecv or comm_split or all_reduce_from_host" > ${O}_pytest_p2p.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_p2p.log
+fi
+if want e2e; then
 echo "== $(date -u +%T) end-to-end step: copy-then-reduce vs pipelined Comm.all_reduce_from_host"
-B200_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_coll_gpu.py -q -k all_reduce_from_host > ${O}_pytest_e2e.log 2>&1; echo "pytest rc=$?"
 timeout 200 $TR --master-port 29760 bench/e2e_pipeline.py > ${O}_e2e_pipeline.jsonl 2> ${O}_e2e_pipeline.err; cat ${O}_e2e_pipeline.jsonl
-echo "== $(date -u +%T) done"
-echo "=== point to point: virtual-rank tests, then sendrecv on both arms ==="
-B200_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_coll_gpu.py -q -k "send_recv or sendrecv or comm_split" > ${O}_pytest_p2p.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_p2p.log
+fi
+if want p2p; then
+echo "== $(date -u +%T) sendrecv on both arms"
 for impl in reference ours; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --op sendrecv --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
 done
@@ -59,10 +81,16 @@ echo "--- CTAs per send/recv operation (B200COLL_P2P_MAX_BLOCKS): pick the defau
 for cap in 8 16 32; do
   B200COLL_P2P_MAX_BLOCKS=$cap timeout 200 ./build/sendrecv_perf --devs $ALL --procs -b 64K -e 1G -f 4 -w 3 -n 10 -c 0 > ${O}_sendrecv_cap$cap.txt 2>&1; echo "cap=$cap rc=$?"; tail -n 4 ${O}_sendrecv_cap$cap.txt
 done
-echo "=== DDP demo: our backend vs NCCL on the same box ==="
+fi
+if want ddp; then
+echo "== $(date -u +%T) DDP demo: our backend (arena pool, plain) vs NCCL on the same box"
 timeout 300 $TR --master-port $((29900 + RANDOM % 90)) demo/gpu-training/ddp_b200coll.py --steps 30 --arena-pool 2> ${O}_ddp_pool.err | tail -n 1 | tee ${O}_ddp_pool.json
 for be in b200coll nccl; do
   timeout 300 $TR --master-port $((29900 + RANDOM % 90)) demo/gpu-training/ddp_b200coll.py --steps 30 --backend $be 2> ${O}_ddp_$be.err | tail -n 1 | tee ${O}_ddp_$be.json
 done
-echo "=== tools on hardware (fault injector last: it kills its own context on purpose) ==="
+fi
+if want tests1; then
+echo "== $(date -u +%T) tools on hardware (fault injector last: it kills its own context on purpose)"
 B200_RUN_FAULT_INJECTION=1 timeout 300 python -m pytest tests/test_zz_tools_gpu.py -q -m gpu > ${O}_pytest_tools.log 2>&1; echo "pytest rc=$?"; tail -n 3 ${O}_pytest_tools.log
+fi
+echo "== $(date -u +%T) done"
