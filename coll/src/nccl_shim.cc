@@ -23,6 +23,8 @@ typedef enum { ncclSuccess = 0, ncclUnhandledCudaError = 1, ncclSystemError = 2,
 typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8, ncclBfloat16 = 9 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4 } ncclRedOp_t;
 typedef enum { ncclScalarDevice = 0, ncclScalarHostImmediate = 1 } ncclScalarResidence_t;
+typedef struct ncclWindow_vidmem* ncclWindow_t;
+typedef struct ncclSimInfo_opaque ncclSimInfo_t;
 typedef struct ncclConfig_opaque ncclConfig_t;      /* blocking, cgaClusterSize, ...: nothing in it has an analogue here */
 
 }  // extern "C"
@@ -307,6 +309,63 @@ ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType
   // NCCL lets non-root ranks pass recv == NULL; the library wants an aligned pointer it will not touch
   return map_rc(b200collReduce(send, recv ? recv : const_cast<void*>(send), count, &ep, rop, root, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
+
+// ---- NCCL 2.28 additions that an nccl-tests built against that header references
+ncclResult_t ncclAlltoAll(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclComm_t comm, cudaStream_t stream) {
+  if (!comm) return ncclInvalidArgument;
+  b200collComm_t c = reinterpret_cast<ShimComm*>(comm)->comm;
+  b200collDataType_t t;
+  if (map_dt(dt, &t)) {
+    b200collEpilogue ep{t, t, 1.0f};
+    return map_rc(b200collAllToAll(send, recv, count, &ep, c, stream));
+  }
+  size_t n = 0;
+  if (!map_dt_as_words(dt, count, &t, &n)) return ncclInvalidArgument;
+  b200collEpilogue ep{t, t, 1.0f};
+  BitExactScope exact(c);
+  return map_rc(b200collAllToAll(send, recv, n, &ep, c, stream));
+}
+// Gather / scatter are one group of sends and receives around the root (the root's own block is a local copy inside the same group).
+ncclResult_t ncclGather(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t comm, cudaStream_t stream) {
+  const size_t esz = nccl_type_size(dt);
+  if (!comm || !esz) return ncclInvalidArgument;
+  ShimComm* s = reinterpret_cast<ShimComm*>(comm);
+  if (root < 0 || root >= s->nranks) return ncclInvalidArgument;
+  b200collResult_t rc = b200collGroupStart();
+  if (rc == b200collSuccess) rc = b200collSend(send, count * esz, root, s->comm, stream);
+  if (s->rank == root)
+    for (int p = 0; p < s->nranks && rc == b200collSuccess; p++) rc = b200collRecv(static_cast<char*>(recv) + (size_t)p * count * esz, count * esz, p, s->comm, stream);
+  const b200collResult_t rc_end = b200collGroupEnd();
+  return map_rc(rc != b200collSuccess ? rc : rc_end);
+}
+ncclResult_t ncclScatter(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t comm, cudaStream_t stream) {
+  const size_t esz = nccl_type_size(dt);
+  if (!comm || !esz) return ncclInvalidArgument;
+  ShimComm* s = reinterpret_cast<ShimComm*>(comm);
+  if (root < 0 || root >= s->nranks) return ncclInvalidArgument;
+  b200collResult_t rc = b200collGroupStart();
+  if (s->rank == root)
+    for (int p = 0; p < s->nranks && rc == b200collSuccess; p++) rc = b200collSend(static_cast<const char*>(send) + (size_t)p * count * esz, count * esz, p, s->comm, stream);
+  if (rc == b200collSuccess) rc = b200collRecv(recv, count * esz, root, s->comm, stream);
+  const b200collResult_t rc_end = b200collGroupEnd();
+  return map_rc(rc != b200collSuccess ? rc : rc_end);
+}
+// Symmetric windows: memory from ncclMemAlloc is symmetric by construction, anything else is staged by the library — nothing to register.
+ncclResult_t ncclCommWindowRegister(ncclComm_t comm, void* buff, size_t, ncclWindow_t* win, int) {
+  if (!comm || !win) return ncclInvalidArgument;
+  *win = reinterpret_cast<ncclWindow_t>(buff);
+  return ncclSuccess;
+}
+ncclResult_t ncclCommWindowDeregister(ncclComm_t, ncclWindow_t) { return ncclSuccess; }
+ncclResult_t ncclCommInitRankScalable(ncclComm_t* comm, int nranks, int rank, int nid, ncclUniqueId* ids, ncclConfig_t*) {      // several ids only speed up NCCL's own bootstrap
+  if (!ids || nid < 1) return ncclInvalidArgument;
+  return ncclCommInitRank(comm, nranks, ids[0], rank);
+}
+// Shrinking around ranks that no longer answer needs a rendezvous that does not involve them; this transport's bootstrap is a star through
+// rank 0 of the parent, so it cannot promise that. Create the smaller communicator with ncclCommInitRank (or ncclCommSplit while all are alive).
+ncclResult_t ncclCommShrink(ncclComm_t, int*, int, ncclComm_t* newcomm, ncclConfig_t*, int) { if (newcomm) *newcomm = nullptr; return ncclInvalidUsage; }
+ncclResult_t ncclCommRevoke(ncclComm_t comm, int) { return ncclCommAbort(comm); }
+ncclResult_t ncclGroupSimulateEnd(ncclSimInfo_t*) { return ncclInvalidUsage; }                                                   // no cost model to query
 
 ncclResult_t ncclGroupStart(void) { g_group_depth++; return ncclSuccess; }
 ncclResult_t ncclGroupEnd(void) {

@@ -116,7 +116,16 @@ def test_nccl_shim_exports_the_api_nccl_tests_links_against(coll_lib):
     need = {"ncclGetVersion", "ncclGetUniqueId", "ncclGetErrorString", "ncclGetLastError", "ncclCommInitRank", "ncclCommInitRankConfig", "ncclCommInitAll", "ncclCommDestroy",
             "ncclCommFinalize", "ncclCommAbort", "ncclCommCount", "ncclCommUserRank", "ncclCommCuDevice", "ncclCommGetAsyncError", "ncclCommSplit", "ncclCommRegister",
             "ncclCommDeregister", "ncclMemAlloc", "ncclMemFree", "ncclAllReduce", "ncclAllGather", "ncclReduceScatter", "ncclBroadcast", "ncclBcast", "ncclReduce", "ncclSend",
-            "ncclRecv", "ncclGroupStart", "ncclGroupEnd", "ncclRedOpCreatePreMulSum", "ncclRedOpDestroy"}
+            "ncclRecv", "ncclGroupStart", "ncclGroupEnd", "ncclRedOpCreatePreMulSum", "ncclRedOpDestroy",
+            # NCCL 2.28 (the version the shim advertises): an nccl-tests built against that header references these as well
+            "ncclAlltoAll", "ncclGather", "ncclScatter", "ncclCommWindowRegister", "ncclCommWindowDeregister", "ncclCommInitRankScalable", "ncclCommShrink",
+            "ncclCommRevoke", "ncclGroupSimulateEnd"}
+    # and nothing the installed NCCL header declares is missing from the shim
+    import re
+    hdr = next((p for p in ("/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/include/nccl.h", "/usr/include/nccl.h") if os.path.exists(p)), None)
+    if hdr:
+        declared = set(re.findall(r"^\s*(?:ncclResult_t|const char\*)\s+(nccl[A-Za-z]+)\s*\(", open(hdr).read(), re.M))
+        assert declared <= syms, sorted(declared - syms)
     assert need <= syms, sorted(need - syms)
     L = C.CDLL(shim)
     L.ncclGetErrorString.restype = C.c_char_p

@@ -395,6 +395,9 @@ class _NcclShim:
         L.ncclReduce.argtypes = [vp, vp, sz, ci, ci, ci, vp, vp]
         L.ncclSend.argtypes = [vp, sz, ci, ci, vp, vp]
         L.ncclRecv.argtypes = [vp, sz, ci, ci, vp, vp]
+        L.ncclAlltoAll.argtypes = [vp, vp, sz, ci, vp, vp]
+        L.ncclGather.argtypes = [vp, vp, sz, ci, ci, vp, vp]
+        L.ncclScatter.argtypes = [vp, vp, sz, ci, ci, vp, vp]
         L.ncclRedOpCreatePreMulSum.argtypes = [C.POINTER(ci), vp, ci, ci, vp]
         L.ncclRedOpDestroy.argtypes = [ci, vp]
         L.ncclCommCount.argtypes = [vp, C.POINTER(ci)]
@@ -666,6 +669,28 @@ def test_nccl_api_shim_send_recv(torch_cuda, coll_lib):
             s.ck(L.ncclAllGather(p(part[r]), p(full[r]), 1000, s.I64, comms[r], st[r]))
         torch.cuda.synchronize()
         assert all(torch.equal(f, torch.cat(part)) for f in full)
+        # NCCL 2.28 host APIs: gather to rank 1, scatter from rank 0 (both inside one group across the two communicators), int64 all-to-all
+        gathered = [torch.zeros(1000 * n, dtype=torch.int64, device="cuda") for _ in range(n)]
+        s.ck(L.ncclGroupStart())
+        for r in range(n):
+            s.ck(L.ncclGather(p(part[r]), p(gathered[r]), 1000, s.I64, 1, comms[r], st[r]))
+        s.ck(L.ncclGroupEnd())
+        torch.cuda.synchronize()
+        assert torch.equal(gathered[1], torch.cat(part)) and gathered[0].eq(0).all()
+        pieces = [torch.zeros(1000, dtype=torch.int64, device="cuda") for _ in range(n)]
+        s.ck(L.ncclGroupStart())
+        for r in range(n):
+            s.ck(L.ncclScatter(p(gathered[1]) if r == 0 else None, p(pieces[r]), 1000, s.I64, 0, comms[r], st[r]))
+        s.ck(L.ncclGroupEnd())
+        torch.cuda.synchronize()
+        assert all(torch.equal(pieces[r], part[r]) for r in range(n))                             # rank 0 scattered what rank 1 had gathered
+        a2a_in = [torch.arange(2048 * n, device="cuda", dtype=torch.int64) * (1 if r == 0 else -1) for r in range(n)]
+        a2a_out = [torch.zeros(2048 * n, dtype=torch.int64, device="cuda") for _ in range(n)]
+        for r in range(n):
+            s.ck(L.ncclAlltoAll(p(a2a_in[r]), p(a2a_out[r]), 2048, s.I64, comms[r], st[r]))
+        torch.cuda.synchronize()
+        for r in range(n):
+            assert torch.equal(a2a_out[r], torch.cat([a2a_in[q][r * 2048:(r + 1) * 2048] for q in range(n)]))
         for r in range(n):
             err = C.c_int(-1)
             s.ck(L.ncclCommGetAsyncError(comms[r], C.byref(err)))
