@@ -10,7 +10,8 @@ bf16, sum or avg — go straight to the collective kernels **on the caller's cur
 is plain stream order and `Work.wait()` has nothing to wait for (NCCL's side stream + event dance is not needed). Tensors allocated
 with `pg.empty()` live in the symmetric arena and take the zero-copy / NVLS paths; any other device tensor is staged by the library.
 Point-to-point on CUDA tensors uses the library's grouped send / recv kernel (queued until the first wait, so an isend + irecv pair
-is one launch). Everything else (CPU tensors, integer reductions, min/max/product, gather/scatter, odd shapes) is executed by an
+is one launch); gather / scatter are one such group around the root. Everything else (CPU tensors, integer reductions, min/max/product,
+odd shapes) is executed by an
 internal Gloo group over host copies: slow but correct, which keeps DDP's bookkeeping collectives and object broadcasts working.
 
 Status: the fallback and dispatch logic is exercised on CPU (tests/test_process_group.py); the CUDA fast paths reuse the calls the GPU
@@ -422,8 +423,16 @@ class B200CollProcessGroup(dist.ProcessGroup):
 
     # ------------------------------------------------------------------ things only Gloo does
     def gather(self, output_tensors, input_tensors, opts=None):
-        self.fallback_calls += 1
         root = opts.rootRank if opts is not None else 0
+        if all(t.is_cuda for t in input_tensors) and all(o.is_cuda for outs in output_tensors for o in outs):
+            # one group around the root: everybody sends, the root receives from everybody (its own block is a local copy in the library)
+            for i, inp in enumerate(input_tensors):
+                self._pending.append(("send", inp, root))
+                if self._rank == root:
+                    self._pending.extend(("recv", o, p) for p, o in enumerate(output_tensors[i]))
+            self.fast_calls += 1
+            return _P2pWork(self, output_tensors)
+        self.fallback_calls += 1
         gopts = dist.GatherOptions(); gopts.rootRank = root
         host_in = [t.detach().cpu() if t.is_cuda else t for t in input_tensors]
         host_out = [[torch.empty_like(o, device="cpu") for o in outs] for outs in output_tensors]
@@ -434,8 +443,15 @@ class B200CollProcessGroup(dist.ProcessGroup):
         return _Work(output_tensors)
 
     def scatter(self, output_tensors, input_tensors, opts=None):
-        self.fallback_calls += 1
         root = opts.rootRank if opts is not None else 0
+        if all(o.is_cuda for o in output_tensors) and all(t.is_cuda for ins in input_tensors for t in ins):
+            for i, out in enumerate(output_tensors):
+                if self._rank == root:
+                    self._pending.extend(("send", t, p) for p, t in enumerate(input_tensors[i]))
+                self._pending.append(("recv", out, root))
+            self.fast_calls += 1
+            return _P2pWork(self, output_tensors)
+        self.fallback_calls += 1
         gopts = dist.ScatterOptions(); gopts.rootRank = root
         host_out = [torch.empty_like(o, device="cpu") for o in output_tensors]
         host_in = [[t.detach().cpu() if t.is_cuda else t for t in ins] for ins in input_tensors]

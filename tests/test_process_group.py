@@ -215,6 +215,16 @@ def _gpu_pair(rank, world):
     for r in dist.batch_isend_irecv(ops):
         r.wait()
     assert big.eq(float(other + 1)).all() and pg.fallback_calls == before
+    # gather / scatter: one grouped kernel around the root
+    before = pg.fallback_calls
+    mine = torch.full((2048,), float(rank + 1), device="cuda")
+    parts = [torch.empty(2048, device="cuda") for _ in range(world)] if rank == 1 else None
+    dist.gather(mine, parts, dst=1)
+    if rank == 1:
+        assert parts[0].eq(1).all() and parts[1].eq(2).all()
+    piece = torch.empty(2048, device="cuda")
+    dist.scatter(piece, [torch.full((2048,), 10.0 + r, device="cuda") for r in range(world)] if rank == 0 else None, src=0)
+    assert piece.eq(10.0 + rank).all() and pg.fallback_calls == before
     # integer payloads ride the same kernels as raw words, bit for bit (an int64 -1 is all ones: the Lamport path would rewrite it)
     before = pg.fallback_calls
     ids = torch.full((4096,), -1, device="cuda", dtype=torch.int64); ids[::7] = rank
@@ -308,6 +318,14 @@ def test_point_to_point_calls_are_queued_and_launched_as_one_group(monkeypatch):
     # empty tensors never reach the library
     pg.send([_DeviceLike.of(torch.zeros(0))], 1).wait()
     assert len(comm.calls) == 5
+    # gather / scatter: one group around the root (this rank is rank 0 of 2)
+    go = dist.GatherOptions(); go.rootRank = 0
+    outs = [_DeviceLike.of(torch.zeros(8)), _DeviceLike.of(torch.zeros(8))]
+    pg.gather([outs], [_DeviceLike.of(torch.ones(8))], go).wait()
+    assert [(c[0], c[1]) for c in comm.calls[5:]] == [("send", 0), ("recv", 0), ("recv", 1)] and groups[-1] == 5
+    so = dist.ScatterOptions(); so.rootRank = 1
+    pg.scatter([_DeviceLike.of(torch.zeros(8))], [[]], so).wait()                               # not the root: just one receive from it
+    assert [(c[0], c[1]) for c in comm.calls[8:]] == [("recv", 1)] and pg.fallback_calls == 0
 
 
 def test_ddp_demo_trains_on_the_backend():
