@@ -623,12 +623,13 @@ def test_send_without_a_receiver_times_out(torch_cuda, coll_mod):
 
 @_P2P_GATE
 def test_sendrecv_perf_virtual_ranks_zero_errors(torch_cuda, coll_lib):
-    exe = os.path.join(ROOT, "build", "sendrecv_perf")
-    assert os.path.islink(exe)
-    r = subprocess.run([exe, "--devs", "0,0,0,0", "-b", "64", "-e", "4M", "-f", "4", "-w", "2", "-n", "5", "-c", "1"], capture_output=True, text=True, timeout=300,
-                       env={**{k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}, "B200COLL_TIMEOUT_MS": "5000"})
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "op=sendrecv" in r.stdout and "# Out of bounds values : 0 OK" in r.stdout, r.stdout
+    for op in ("sendrecv", "gather", "scatter"):                       # nccl-tests names; all three are groups of send / recv
+        exe = os.path.join(ROOT, "build", f"{op}_perf")
+        assert os.path.islink(exe)
+        r = subprocess.run([exe, "--devs", "0,0,0,0", "-b", "64", "-e", "4M", "-f", "4", "-w", "2", "-n", "5", "-c", "1"], capture_output=True, text=True, timeout=300,
+                           env={**{k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}, "B200COLL_TIMEOUT_MS": "5000"})
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"op={op}" in r.stdout and "# Out of bounds values : 0 OK" in r.stdout, r.stdout
 
 
 @_P2P_GATE
