@@ -260,7 +260,8 @@ b200collResult_t p2p_launch(b200collComm* c, const std::vector<PendingP2p>& ops,
       if (o.send != (pass == 0)) continue;
       const int i = a.nops++;
       a.first_block[i] = blocks;
-      blocks += p2p_blocks(c, o.bytes);
+      a.lanes[i] = p2p_blocks(c, o.bytes);
+      blocks += (!o.send && b200collIsSymmetric(c, o.rbuf, o.bytes)) ? 1 : a.lanes[i];      // a direct receive only exchanges flags: one CTA for all lanes
       a.peer[i] = o.peer;
       a.bytes[i] = o.bytes;
       moved += o.bytes;
@@ -289,9 +290,9 @@ b200collResult_t p2p_launch(b200collComm* c, const std::vector<PendingP2p>& ops,
     *g_p2p_dry += line;
     for (int i = 0; i < a.nops; i++) {
       const unsigned long long chunks = (i < a.nsend || a.bytes[i] <= a.win_bytes[i]) ? 1 : (a.bytes[i] + a.win_bytes[i] - 1) / a.win_bytes[i];
-      if (i < a.nsend) snprintf(line, sizeof line, "  send peer=%d bytes=%llu ctas=[%d,%d)\n", a.peer[i], a.bytes[i], a.first_block[i], a.first_block[i + 1]);
-      else if (!a.staged[i]) snprintf(line, sizeof line, "  recv peer=%d bytes=%llu ctas=[%d,%d) direct off=%llu\n", a.peer[i], a.bytes[i], a.first_block[i], a.first_block[i + 1], a.win_off[i]);
-      else snprintf(line, sizeof line, "  recv peer=%d bytes=%llu ctas=[%d,%d) staged off=%llu window=%llu chunks=%llu\n", a.peer[i], a.bytes[i], a.first_block[i], a.first_block[i + 1], a.win_off[i], a.win_bytes[i], chunks);
+      if (i < a.nsend) snprintf(line, sizeof line, "  send peer=%d bytes=%llu lanes=%d ctas=[%d,%d)\n", a.peer[i], a.bytes[i], a.lanes[i], a.first_block[i], a.first_block[i + 1]);
+      else if (!a.staged[i]) snprintf(line, sizeof line, "  recv peer=%d bytes=%llu lanes=%d ctas=[%d,%d) direct off=%llu\n", a.peer[i], a.bytes[i], a.lanes[i], a.first_block[i], a.first_block[i + 1], a.win_off[i]);
+      else snprintf(line, sizeof line, "  recv peer=%d bytes=%llu lanes=%d ctas=[%d,%d) staged off=%llu window=%llu chunks=%llu\n", a.peer[i], a.bytes[i], a.lanes[i], a.first_block[i], a.first_block[i + 1], a.win_off[i], a.win_bytes[i], chunks);
       *g_p2p_dry += line;
     }
     return b200collSuccess;

@@ -15,8 +15,9 @@ namespace b200coll {
 //   sender CTA j     waits for the post with the next sequence number, pushes its 1/nb share of the n bytes straight into the
 //                    receiver's memory (plain 16-byte stores to the peer mapping), then st.release.sys the sequence number into
 //                    done [me][j] of the RECEIVER's arena;
-//   receiver CTA j   waits for that number. A buffer inside the symmetric arena is the window itself (zero copy, one chunk);
-//                    any other buffer is received through two staging windows that the CTA empties into it while the next
+//   receiver CTA j   waits for that number. A buffer inside the symmetric arena is the window itself (zero copy, one chunk, and a single
+//                    receiver CTA whose thread j plays "CTA j" for the flags: there is nothing to move on this side);
+//                    any other buffer is received through two staging windows that CTA j empties into it while the next
 //                    chunk is already in flight.
 // Sequence numbers live in device memory per (peer, CTA) and only ever grow, so a captured graph can be replayed; both sides
 // derive the CTA count from the message size alone, so CTA j always meets CTA j. Every rank runs this same kernel whatever its
@@ -26,6 +27,8 @@ struct P2pArgs {
   int first_block[2 * kMaxRanks + 1];            // prefix sum of CTAs per operation
   int peer[2 * kMaxRanks];
   int staged[2 * kMaxRanks];                     // recv: 1 = two staging windows + copy-out, 0 = peers write the buffer itself
+  int lanes[2 * kMaxRanks];                      // how many sender CTAs move this message (a function of its size). Sends and staged recvs run
+                                                 // one CTA per lane; a direct recv has nothing to move, so ONE CTA serves all its lanes
   unsigned long long bytes[2 * kMaxRanks];       // message size; must be the same on both sides
   const char* src[2 * kMaxRanks];                // send: local source (any device memory)
   char* dst[2 * kMaxRanks];                      // recv: destination buffer
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(kP2pThreads) k_p2p(COMM_PARAM, const __grid_co
   P2P_SHARED(sh);                                // per-CTA: what thread 0 learnt from a mailbox, for the other threads
   int o = 0;
   while (o + 1 < a.nops && (int)blockIdx.x >= a.first_block[o + 1]) o++;
-  const int sub = (int)blockIdx.x - a.first_block[o], nb = a.first_block[o + 1] - a.first_block[o];
+  const int sub = (int)blockIdx.x - a.first_block[o], nb = a.lanes[o];
   const int peer = a.peer[o];
   const unsigned long long total = a.bytes[o];
   char* my = c.peer[c.rank];
@@ -128,11 +131,42 @@ __global__ void __launch_bounds__(kP2pThreads) k_p2p(COMM_PARAM, const __grid_co
     if (threadIdx.x == 0) *seqp = seq;
   } else {
     // ------------------------------------------------------------------ receiver
+    if (!a.staged[o]) {
+      // The buffer is in the arena: every lane gets the same post ("the whole message goes at this offset") and this one CTA then waits
+      // for each lane's done flag — thread j looks after lane j (a loop only so that the host emulation can run with fewer threads).
+      const unsigned long long off16 = a.win_off[o] / 16;
+      for (int j = (int)threadIdx.x; j < nb; j += (int)blockDim.x) {
+        const uint32_t seq = ld_volatile_u32(c.state + kP2pRecvSeq0 + peer * kP2pMaxBlocks + j) + 1;
+        const unsigned long long tag = (unsigned long long)(seq & ((1u << kP2pTagBits) - 1)) << kP2pValueBits;
+        unsigned long long* b = reinterpret_cast<unsigned long long*>(c.peer[peer] + kOffP2pPost) + (((size_t)c.rank * kP2pMaxBlocks + j) * 2 + (seq & 1u)) * 2;
+        st_relaxed_sys_u64(b, tag | off16);
+        st_release_sys_u64(b + 1, tag | total);
+      }
+      for (int j = (int)threadIdx.x; j < nb; j += (int)blockDim.x) {
+        uint32_t* seqp = c.state + kP2pRecvSeq0 + peer * kP2pMaxBlocks + j;
+        const uint32_t want = ld_volatile_u32(seqp) + 1;
+        const uint32_t* done = reinterpret_cast<const uint32_t*>(my + kOffP2pDone) + peer * kP2pMaxBlocks + j;
+        uint32_t v = ld_relaxed_sys(done);
+        if ((int32_t)(v - want) < 0) {
+          const unsigned long long t0 = globaltimer_ns();
+          uint32_t spins = 0;
+          while ((int32_t)((v = ld_relaxed_sys(done)) - want) < 0) {
+            if (((++spins) & 0x3FF) == 0 && (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns)) {
+              record_fault(c, 3, (uint32_t)peer, want, v, op);        // the peer never sent (or died half-way)
+              break;
+            }
+          }
+        }
+        (void)ld_acquire_sys(done);
+        *seqp = want;
+      }
+      return;
+    }
     uint32_t* seqp = c.state + kP2pRecvSeq0 + peer * kP2pMaxBlocks + sub;
     const uint32_t base = ld_volatile_u32(seqp);
     const unsigned long long win = a.win_bytes[o];
     const unsigned long long chunks = total <= win ? 1 : (total + win - 1) / win;
-    const int staged = a.staged[o];
+    const int staged = 1;                        // direct receives returned above
     unsigned long long* box = reinterpret_cast<unsigned long long*>(c.peer[peer] + kOffP2pPost) + ((size_t)c.rank * kP2pMaxBlocks + sub) * 4;
     const uint32_t* done = reinterpret_cast<const uint32_t*>(my + kOffP2pDone) + peer * kP2pMaxBlocks + sub;
     auto post = [&](unsigned long long k) {      // thread 0: chunk k may now be written into window k & 1

@@ -116,7 +116,7 @@ static P2pArgs plan(const Machine& m, int rank, const std::vector<Op>& ops, int 
     for (const Op& o : ops) {
       if (o.send != (pass == 0)) continue;
       const int i = a.nops++;
-      a.first_block[i] = blocks; blocks += blocks_for(o.bytes, cap);
+      a.first_block[i] = blocks; a.lanes[i] = blocks_for(o.bytes, cap); blocks += (!o.send && o.in_arena) ? 1 : a.lanes[i];
       a.peer[i] = o.peer; a.bytes[i] = o.bytes;
       if (o.send) { a.nsend++; a.src[i] = o.buf; }
       else {

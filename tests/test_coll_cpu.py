@@ -269,11 +269,12 @@ def test_point_to_point_planner_layout_and_rounds(coll_lib):
     for nbytes, want in [(16, 1), (128 << 10, 1), ((128 << 10) + 1, 2), (MiB, 8), (2 * MiB, 16), (1 << 30, 16)]:
         rc, (send,) = _plan_p2p(coll_lib, 0, 8, [(1, 3, nbytes, 1)])
         rc2, (recv,) = _plan_p2p(coll_lib, 3, 8, [(0, 0, nbytes, 1)])
-        assert rc == 0 and rc2 == 0 and send["ctas"] == want and recv["ctas"] == want, nbytes       # CTA j of the send meets CTA j of the recv
+        assert rc == 0 and rc2 == 0 and send["ctas"] == want and send["ops"][0]["lanes"] == want == recv["ops"][0]["lanes"], nbytes      # lane j of the send meets lane j of the recv
+        assert recv["ctas"] == 1                     # a receive into the arena only exchanges flags: one CTA looks after all its lanes
     assert _plan_p2p(coll_lib, 0, 4, [(1, 1, 1 << 30, 1)], loopback=1)[1][0]["ctas"] == 2                     # virtual ranks share one GPU's SMs
     # a ring step: one launch, send in the low CTAs, arena receive written in place
     rc, (ring,) = _plan_p2p(coll_lib, 0, 8, [(0, 7, MiB, 1), (1, 1, MiB, 1)])
-    assert rc == 0 and [o["kind"] for o in ring["ops"]] == ["send", "recv"] and ring["ops"][0]["ctas"] == (0, 8) and ring["ops"][1]["ctas"] == (8, 16)
+    assert rc == 0 and [o["kind"] for o in ring["ops"]] == ["send", "recv"] and ring["ops"][0]["ctas"] == (0, 8) and ring["ops"][1]["ctas"] == (8, 9) and ring["ops"][1]["lanes"] == 8
     assert not ring["ops"][1]["staged"] and ring["staged"] == 0
     # three receives outside the arena: three window pairs, disjoint, inside the 64 MiB staging area that starts at 25 MiB
     rc, (l,) = _plan_p2p(coll_lib, 1, 4, [(0, p, 40 * MiB, 0) for p in (0, 2, 3)])
