@@ -35,7 +35,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--op", default="all_reduce", choices=["all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce", "sendrecv"])
+    ap.add_argument("--op", default="all_reduce", choices=["all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce", "sendrecv", "gather", "scatter"])
     ap.add_argument("--min", default="1K")
     ap.add_argument("--max", default="1G")
     ap.add_argument("--no-e2e", action="store_true")

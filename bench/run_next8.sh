@@ -75,7 +75,7 @@ fi
 if want p2p; then
 echo "== $(date -u +%T) sendrecv on both arms"
 for impl in reference ours; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --op sendrecv --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus $NG --steps 20 --warmup 5 --no-e2e --op sendrecv --extra-ops gather,scatter --extra-out ${O}_p2p_extra_$impl.json --impl $impl > ${O}_sendrecv_$impl.json 2> ${O}_sendrecv_$impl.err; echo "sendrecv $impl rc=$?"
 done
 echo "--- CTAs per send/recv operation (B200COLL_P2P_MAX_BLOCKS): pick the default from this"
 for cap in 8 16 32; do

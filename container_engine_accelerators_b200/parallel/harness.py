@@ -19,10 +19,10 @@ import os
 from dataclasses import dataclass
 
 OPS = ("all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce")   # index = b200collOp_t
-P2P_OPS = ("sendrecv",)     # nccl-tests sendrecv_perf: a ring step (send right, receive from the left) through the point-to-point kernel
+P2P_OPS = ("sendrecv", "gather", "scatter")     # nccl-tests sendrecv_perf (a ring step), gather_perf, scatter_perf: groups of send / recv through the point-to-point kernel
 ALL_OPS = OPS + P2P_OPS
 ROOT = 0   # rooted ops are measured from rank 0, as nccl-tests does by default
-FULL_MESSAGE_OPS = ("all_reduce", "broadcast", "reduce", "sendrecv")   # count = whole message; the others split it over the ranks
+FULL_MESSAGE_OPS = ("all_reduce", "broadcast", "reduce", "sendrecv")   # gather / scatter split the message over the ranks like all_gather / reduce_scatter   # count = whole message; the others split it over the ranks
 WINDOW = 192 << 20
 
 
@@ -128,11 +128,20 @@ class OursBackend:
 
     def launch(self, op: str, send_ptr: int, recv_ptr: int, count: int, stream: int) -> None:
         L, ep = self.L, C.byref(self.ep)
-        if op == "sendrecv":
+        if op in P2P_OPS:
             n, r, nbytes = self.comm.nranks, self.comm.rank, count * self.send.element_size()
             rc = L.b200collGroupStart()
-            rc = rc or L.b200collSend(send_ptr, nbytes, (r + 1) % n, self.h, stream)
-            rc = rc or L.b200collRecv(recv_ptr, nbytes, (r - 1) % n, self.h, stream)
+            if op == "sendrecv":
+                rc = rc or L.b200collSend(send_ptr, nbytes, (r + 1) % n, self.h, stream)
+                rc = rc or L.b200collRecv(recv_ptr, nbytes, (r - 1) % n, self.h, stream)
+            elif op == "gather":
+                rc = rc or L.b200collSend(send_ptr, nbytes, ROOT, self.h, stream)
+                for p in (range(n) if r == ROOT else ()):
+                    rc = rc or L.b200collRecv(recv_ptr + p * nbytes, nbytes, p, self.h, stream)
+            else:
+                for p in (range(n) if r == ROOT else ()):
+                    rc = rc or L.b200collSend(send_ptr + p * nbytes, nbytes, p, self.h, stream)
+                rc = rc or L.b200collRecv(recv_ptr, nbytes, ROOT, self.h, stream)
             rc = L.b200collGroupEnd() or rc
         elif op == "all_reduce":
             rc = L.b200collAllReduce(send_ptr, recv_ptr, count, ep, 0, self.h, stream)
@@ -201,6 +210,8 @@ class NcclBackend:
         c = self.comm
         if op == "sendrecv":
             c.send_recv(send_ptr, (c.rank + 1) % c.nranks, recv_ptr, (c.rank - 1) % c.nranks, count, self.dt, stream)
+        elif op in ("gather", "scatter"):
+            c.gather_scatter(op, send_ptr, recv_ptr, count, self.dt, self.itemsize, ROOT, stream)
         elif op == "all_reduce":
             c.all_reduce(send_ptr, recv_ptr, count, self.dt, stream)
         elif op == "all_gather":
@@ -242,9 +253,9 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
     count = max(E, count // E * E)
     if op in FULL_MESSAGE_OPS:
         in_elems, out_elems = count, count
-    elif op == "all_gather":
+    elif op in ("all_gather", "gather"):
         in_elems, out_elems = count, count * n
-    elif op == "reduce_scatter":
+    elif op in ("reduce_scatter", "scatter"):
         in_elems, out_elems = count * n, count
     else:
         in_elems, out_elems = count * n, count * n
@@ -265,9 +276,13 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
         want = gen((rank - 1) % n, idx)
     elif op == "reduce":                                   # only the root's recv is defined
         want = sum(gen(r, idx) for r in range(n)) if rank == ROOT else torch.full_like(got, 77.0)
-    elif op == "all_gather":
+    elif op == "all_gather" or (op == "gather" and rank == ROOT):
         j = torch.arange(count, device=dev)
         want = torch.cat([gen(r, j) for r in range(n)])
+    elif op == "gather":                                   # only the root's recv is defined
+        want = torch.full_like(got, 77.0)
+    elif op == "scatter":
+        want = gen(ROOT, torch.arange(count, device=dev) + rank * count)
     elif op == "reduce_scatter":
         j = torch.arange(count, device=dev) + rank * count
         want = sum(gen(r, j) for r in range(n))
@@ -302,8 +317,8 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
             in_elems = out_elems = count
         else:
             count = nbytes // itemsize // n // E * E
-            in_elems = count if op == "all_gather" else count * n
-            out_elems = count if op == "reduce_scatter" else count * n
+            in_elems = count if op in ("all_gather", "gather") else count * n
+            out_elems = count if op in ("reduce_scatter", "scatter") else count * n
         if count == 0:
             nbytes *= factor
             continue
@@ -314,7 +329,7 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
         row = Row(total, count, backend.algo(op, per_rank_bytes), in_bytes=in_elems * itemsize)
         sbase, rbase = backend.send.data_ptr(), backend.recv.data_ptr()
         for ip in placements:
-            if ip == 1 and (op in ("alltoall", "sendrecv") or n == 1):
+            if ip == 1 and (op in ("alltoall",) + P2P_OPS or n == 1):
                 continue
 
             def ptrs(slot: int):

@@ -107,6 +107,19 @@ class NcclComm:
         self._ck(self.lib.ncclRecv(recv, count, dtype, frm, self.comm, stream), "ncclRecv")
         self._ck(self.lib.ncclGroupEnd(), "ncclGroupEnd")
 
+    def gather_scatter(self, op: str, send: int, recv: int, count: int, dtype: int, elem_size: int, root: int, stream: int) -> None:
+        # nccl-tests' gather / scatter: grouped ncclSend / ncclRecv around the root (works on every NCCL that has send/recv)
+        self._ck(self.lib.ncclGroupStart(), "ncclGroupStart")
+        if op == "gather":
+            self._ck(self.lib.ncclSend(send, count, dtype, root, self.comm, stream), "ncclSend")
+            for p in (range(self.nranks) if self.rank == root else ()):
+                self._ck(self.lib.ncclRecv(recv + p * count * elem_size, count, dtype, p, self.comm, stream), "ncclRecv")
+        else:
+            for p in (range(self.nranks) if self.rank == root else ()):
+                self._ck(self.lib.ncclSend(send + p * count * elem_size, count, dtype, p, self.comm, stream), "ncclSend")
+            self._ck(self.lib.ncclRecv(recv, count, dtype, root, self.comm, stream), "ncclRecv")
+        self._ck(self.lib.ncclGroupEnd(), "ncclGroupEnd")
+
     def all_to_all(self, send: int, recv: int, count: int, dtype: int, elem_size: int, stream: int) -> None:
         # nccl-tests' alltoall: grouped ncclSend/ncclRecv to every peer
         self._ck(self.lib.ncclGroupStart(), "ncclGroupStart")

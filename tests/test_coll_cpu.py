@@ -145,6 +145,8 @@ def test_harness_bandwidth_accounting_follows_nccl_tests():
     assert h.bus_factor("all_reduce", 8) == pytest.approx(1.75) and h.bus_factor("all_gather", 8) == pytest.approx(0.875)
     assert h.bus_factor("reduce_scatter", 2) == 0.5 and h.bus_factor("alltoall", 4) == 0.75
     assert h.bus_factor("broadcast", 8) == 1.0 and h.bus_factor("reduce", 8) == 1.0 and h.bus_factor("all_reduce", 1) == 1.0
+    assert h.bus_factor("sendrecv", 8) == 1.0 and h.bus_factor("gather", 8) == pytest.approx(0.875) and h.bus_factor("scatter", 4) == 0.75      # nccl-tests' factors
+    assert set(h.P2P_OPS) == {"sendrecv", "gather", "scatter"} and h.ALL_OPS[:6] == h.OPS
     rows = [h.Row(nbytes=1 << 20, count=1 << 19, algo="nvls", oop_us=10.0, ip_us=20.0), h.Row(nbytes=1 << 30, count=1 << 29, algo="nvls", oop_us=2000.0, ip_us=-1.0, e2e_us=40000.0)]
     b = rows[0].bw("all_reduce", 8)
     assert b["oop_algbw"] == pytest.approx((1 << 20) / 10.0 / 1e3) and b["oop_busbw"] == pytest.approx(b["oop_algbw"] * 1.75) and b["ip_busbw"] == pytest.approx(b["oop_busbw"] / 2)
