@@ -117,7 +117,7 @@ static float expected(const Opts& o, int rank, int n, size_t e, size_t count) {
   if (o.op == "all_reduce" || o.op == "reduce") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, e); return s * o.scale; }
   if (o.op == "broadcast") return gen(kRoot, e) * o.scale;
   if (o.op == "sendrecv") return gen((rank + n - 1) % n, e);      // ring step: my output is my left neighbour's input, untouched
-  if (o.op == "all_gather" || o.op == "gather") { int src = (int)(e / count); return gen(src, e % count) * o.scale; }
+  if (o.op == "all_gather" || o.op == "gather" || o.op == "hypercube") { int src = (int)(e / count); return gen(src, e % count) * o.scale; }
   if (o.op == "scatter") return gen(kRoot, (size_t)rank * count + e);
   if (o.op == "reduce_scatter") { float s = 0; for (int r = 0; r < n; r++) s += gen(r, (size_t)rank * count + e); return s * o.scale; }
   /* alltoall */ { int src = (int)(e / count); return gen(src, (size_t)rank * count + e % count) * o.scale; }
@@ -136,7 +136,9 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
   const bool is_bc = o.op == "broadcast", is_rd = o.op == "reduce", is_sr = o.op == "sendrecv";
   if (is_sr && (o.in_dt != o.out_dt || o.scale != 1.0f)) { fprintf(stderr, "sendrecv moves opaque bytes: --in and --out must match and --scale must be 1\n"); return 2; }
   const bool is_ar = o.op == "all_reduce" || is_bc || is_rd || is_sr;      // "whole message" geometry: count elements in, count out
-  const bool is_ga = o.op == "gather", is_sc = o.op == "scatter";                 // nccl-tests gather_perf / scatter_perf: one send/recv group around the root
+  const bool is_hc = o.op == "hypercube";          // nccl-tests hypercube_perf: an all-gather made of log2(n) pairwise exchanges of doubling size
+  if (is_hc && (n & (n - 1))) { fprintf(stderr, "hypercube needs a power-of-two number of ranks\n"); return 2; }
+  const bool is_ga = o.op == "gather" || is_hc, is_sc = o.op == "scatter";                 // nccl-tests gather_perf / scatter_perf: one send/recv group around the root
   if ((is_ga || is_sc) && (o.in_dt != o.out_dt || o.scale != 1.0f)) { fprintf(stderr, "%s moves opaque bytes: --in and --out must match and --scale must be 1\n", o.op.c_str()); return 2; }
   const bool is_ag = o.op == "all_gather" || is_ga, is_rs = o.op == "reduce_scatter" || is_sc;      // same buffer geometry
   if (!is_ar && !is_ag && !is_rs && o.op != "alltoall") { fprintf(stderr, "unknown --op %s\n", o.op.c_str()); return 2; }
@@ -194,7 +196,16 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
         return (char*)recv + off;
       };
       auto launch = [&](int slot) {
-        if (is_ga) {
+        if (is_hc) {
+          RT(cudaMemcpyAsync(rbuf(slot) + (size_t)rank * count * is, sbuf(slot), count * is, cudaMemcpyDeviceToDevice, st));
+          for (int mask = 1; mask < n; mask <<= 1) {      // after the step with this mask every rank holds the 2*mask blocks of its sub-cube
+            const int peer = rank ^ mask, mine0 = rank & ~(mask - 1), theirs0 = peer & ~(mask - 1);
+            CC(b200collGroupStart());
+            CC(b200collSend(rbuf(slot) + (size_t)mine0 * count * is, (size_t)mask * count * is, peer, ctx.comm, st));
+            CC(b200collRecv(rbuf(slot) + (size_t)theirs0 * count * is, (size_t)mask * count * is, peer, ctx.comm, st));
+            CC(b200collGroupEnd());
+          }
+        } else if (is_ga) {
           CC(b200collGroupStart());
           CC(b200collSend(sbuf(slot), count * is, kRoot, ctx.comm, st));
           if (rank == kRoot) for (int p = 0; p < n; p++) CC(b200collRecv(rbuf(slot) + (size_t)p * count * is, count * is, p, ctx.comm, st));
@@ -234,7 +245,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
         b200collFault f;
         if (b200collCommGetAsyncError(ctx.comm, &f) != b200collSuccess) { fprintf(stderr, "rank %d WATCHDOG code=%u peer=%u block=%u expected=%u observed=%u op=%u\n", rank, f.code, f.peer, f.block, f.expected, f.observed, f.op); _exit(5); }
         const char* outp = (ip && is_rs) ? rbuf(0) : (ip ? (char*)recv : rbuf(0));
-        const size_t check_elems = ((is_rd || is_ga) && rank != kRoot) ? 0 : out_elems;   // a rooted reduce defines the root's output only
+        const size_t check_elems = ((is_rd || (is_ga && !is_hc)) && rank != kRoot) ? 0 : out_elems;   // a rooted reduce defines the root's output only
         host.resize(check_elems * os);
         RT(cudaMemcpy(host.data(), outp, check_elems * os, cudaMemcpyDeviceToHost));
         const size_t stride = check_elems > (1u << 22) ? 61 : 1;   // sample large buffers
@@ -301,7 +312,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
 static const char* op_from_argv0(const char* argv0) {
   const char* base = strrchr(argv0, '/'); base = base ? base + 1 : argv0;
   static const struct { const char* name; const char* op; } kNames[] = {{"all_reduce_perf", "all_reduce"}, {"all_gather_perf", "all_gather"}, {"reduce_scatter_perf", "reduce_scatter"},
-                                                                        {"alltoall_perf", "alltoall"}, {"broadcast_perf", "broadcast"}, {"reduce_perf", "reduce"}, {"sendrecv_perf", "sendrecv"}, {"gather_perf", "gather"}, {"scatter_perf", "scatter"}};
+                                                                        {"alltoall_perf", "alltoall"}, {"broadcast_perf", "broadcast"}, {"reduce_perf", "reduce"}, {"sendrecv_perf", "sendrecv"}, {"gather_perf", "gather"}, {"scatter_perf", "scatter"}, {"hypercube_perf", "hypercube"}};
   for (auto& k : kNames) if (!strcmp(base, k.name)) return k.op;
   return nullptr;
 }
@@ -365,7 +376,7 @@ int main(int argc, char** argv) {
     }
     else if (a == "--selfcheck") { char buf[4096]; b200collResult_t r = b200collSelfCheck(buf, sizeof(buf)); fputs(buf, stdout); return r == b200collSuccess ? 0 : 1; }
     else if (a == "-h" || a == "--help") {
-      puts("b200coll_perf (also all_reduce_perf, all_gather_perf, reduce_scatter_perf, alltoall_perf, broadcast_perf, reduce_perf, sendrecv_perf, gather_perf, scatter_perf): nccl-tests style sweep on libb200coll\n"
+      puts("b200coll_perf (also all_reduce_perf, all_gather_perf, reduce_scatter_perf, alltoall_perf, broadcast_perf, reduce_perf, sendrecv_perf, gather_perf, scatter_perf, hypercube_perf): nccl-tests style sweep on libb200coll\n"
            "  --op NAME                 collective (implied by the name the binary is called by)\n"
            "  -b/-e SIZE -f N           sweep from -b to -e bytes multiplying by -f (1K, 64M, 1G ...)\n"
            "  -g N | --ranks N | --devs a,b,..   ranks in this process (threads); --procs forks one process per rank instead\n"

@@ -11,7 +11,7 @@ cp "${SRC}/lib/libb200coll.so" "${SRC}/lib/libb200coll_nccl.so" "${DST}/"
 cp "${SRC}/bin/b200coll_perf" "${BIN}/"
 if [ -f "${SRC}/bin/mps_probe" ]; then cp "${SRC}/bin/mps_probe" "${BIN}/"; fi      # deploy/example/cuda-mps/mps-probe.yaml runs it from the host mount
 # nccl-tests names, so `run-nccl.sh all_gather_perf ...` style scripts keep working (the binary dispatches on argv[0])
-for n in all_reduce_perf all_gather_perf reduce_scatter_perf alltoall_perf broadcast_perf reduce_perf sendrecv_perf gather_perf scatter_perf; do ln -sf b200coll_perf "${BIN}/${n}"; done
+for n in all_reduce_perf all_gather_perf reduce_scatter_perf alltoall_perf broadcast_perf reduce_perf sendrecv_perf gather_perf scatter_perf hypercube_perf; do ln -sf b200coll_perf "${BIN}/${n}"; done
 cp "${SRC}/b200coll-env-profile.sh" "${DST}/"
 if [ -f "${SRC}/tuner/b200_nvswitch.tbl" ]; then cp "${SRC}/tuner/b200_nvswitch.tbl" "${DST}/"; fi
 if [ "${B200COLL_SKIP_SELFCHECK:-0}" != "1" ]; then

@@ -623,7 +623,7 @@ def test_send_without_a_receiver_times_out(torch_cuda, coll_mod):
 
 @_P2P_GATE
 def test_sendrecv_perf_virtual_ranks_zero_errors(torch_cuda, coll_lib):
-    for op in ("sendrecv", "gather", "scatter"):                       # nccl-tests names; all three are groups of send / recv
+    for op in ("sendrecv", "gather", "scatter", "hypercube"):                      # nccl-tests names; all of them are groups of send / recv
         exe = os.path.join(ROOT, "build", f"{op}_perf")
         assert os.path.islink(exe)
         r = subprocess.run([exe, "--devs", "0,0,0,0", "-b", "64", "-e", "4M", "-f", "4", "-w", "2", "-n", "5", "-c", "1"], capture_output=True, text=True, timeout=300,

@@ -151,7 +151,7 @@ def test_b200coll_install_and_env_profile(tmp_path):
     assert subprocess.run(["bash", os.path.join(SCRIPTS, "b200coll-install.sh")], env=env).returncode == 0
     assert (tmp_path / "lib64/libb200coll.so").exists() and (tmp_path / "lib64/b200_nvswitch.tbl").exists() and (tmp_path / "selfcheck").exists()
     assert (tmp_path / "bin" / "mps_probe").exists()
-    for name in ("all_reduce_perf", "all_gather_perf", "reduce_scatter_perf", "alltoall_perf", "broadcast_perf", "reduce_perf", "sendrecv_perf", "gather_perf", "scatter_perf"):       # nccl-tests names
+    for name in ("all_reduce_perf", "all_gather_perf", "reduce_scatter_perf", "alltoall_perf", "broadcast_perf", "reduce_perf", "sendrecv_perf", "gather_perf", "scatter_perf", "hypercube_perf"):       # nccl-tests names
         assert os.readlink(tmp_path / "bin" / name) == "b200coll_perf"
     out = subprocess.run(["bash", "-c", f"B200COLL_LIB_DIR={tmp_path}/lib64 source {SCRIPTS}/b200coll-env-profile.sh; echo $B200COLL_LIB $B200COLL_ALGO $B200COLL_TUNER_FILE"], capture_output=True, text=True).stdout.split()
     assert out == [f"{tmp_path}/lib64/libb200coll.so", "auto", f"{tmp_path}/lib64/b200_nvswitch.tbl"]
