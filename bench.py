@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
         bench.py --gpus 8 --steps 20 --warmup 5
-    ... --impl reference      # stock NCCL through its C API under the reference's env profile (see nccl_ref.py)
+    ... --impl reference      # stock NCCL through its C API, NCCL's own defaults (see nccl_ref.py); reference-sym adds ncclMemAlloc + symmetric windows
 
 A "step" is one pass over the 21-size sweep (1 KB..1 GB, x2), out-of-place and in-place. Following the
 reference's nccl-tests protocol each size's `--steps` iterations are launched back to back and timed with
@@ -34,7 +34,7 @@ def main() -> int:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-sym"], help="reference = stock NCCL on plain buffers (what nccl-tests does); reference-sym = the same on ncclMemAlloc memory with symmetric windows registered (NCCL's own fast path)")
     ap.add_argument("--op", default="all_reduce", choices=["all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce", "sendrecv", "gather", "scatter"])
     ap.add_argument("--min", default="1K")
     ap.add_argument("--max", default="1G")
@@ -67,7 +67,9 @@ def main() -> int:
     min_b, max_b = parse_size(args.min), parse_size(args.max)
     cap = max(max_b, harness.WINDOW) // 2 + 4096
 
-    if args.impl == "reference":
+    if args.impl == "reference-sym":
+        os.environ["B200_REF_SYM"] = "1"
+    if args.impl.startswith("reference"):
         try:
             backend = harness.NcclBackend(dist, cap, dtype)
         except Exception as e:
@@ -78,7 +80,7 @@ def main() -> int:
         backend = harness.OursBackend(dist, cap, dtype)   # raises if libb200coll.so is missing: no silent fallback
 
     n = dist.world
-    verified = harness.verify(backend, dist, args.op, dtype) if n > 1 else True
+    verified = harness.verify(backend, dist, args.op, dtype)
     launches0 = backend.launches()
     t_wall = time.time()
     with ClockSampler(dist.local_rank) as clk:
@@ -86,12 +88,23 @@ def main() -> int:
     launches = backend.launches() - launches0
     clocks = clk.summary()
     e2e = None
+    e2e_rows = []
     if not args.no_e2e:
-        e2e_rows = harness.sweep(backend, dist, args.op, dtype, max(2, min(args.steps, 10)), min(warmup, 3), min_b, max_b, placements=(), e2e=True)
+        e2e_ok = harness.verify_e2e(backend, dist, dtype) if args.op == "all_reduce" else True
+        hl0 = backend.launches()
+        e2e_steps = max(2, min(args.steps, 10))
+        e2e_rows = harness.sweep(backend, dist, args.op, dtype, e2e_steps, min(warmup, 3), min_b, max_b, placements=(), e2e=True)
         s2 = harness.summarize(e2e_rows, args.op, n)
-        h2d = sum(r.in_bytes for r in e2e_rows)
-        e2e = {"value": round(s2["avg_e2e_busbw"] or 0.0, 3), "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4096 * len(e2e_rows),
-               "note": "per size: pinned-host->device copy of the input, the collective, 4 KiB device->host read of the result, all on one stream"}
+        e2e = {"value": round(s2["avg_e2e_busbw"] or 0.0, 3), "unit": "GB/s", "h2d_bytes_per_step": int(sum(r.in_bytes for r in e2e_rows)),
+               "d2h_bytes_per_step": int(sum(r.out_bytes for r in e2e_rows)), "steps": e2e_steps, "verified_vs_torch_fp32": bool(e2e_ok),
+               "peak_busbw": round(max((r.bw(args.op, n)["e2e_busbw"] for r in e2e_rows), default=0.0), 2),
+               "gpu_launches_incl_warmup": int(backend.launches() - hl0),
+               "note": ("per size, every step: this rank's input starts in pinned host memory and the WHOLE result ends in pinned host memory. "
+                        + ("ours: one call of the public API per step, Comm.all_reduce_host (b200collAllReduceHost: a zero-copy kernel over PCIe for tiny messages; "
+                           "host->device copy, all-reduce and device->host copy overlapped chunk by chunk for large ones)" if args.impl == "ours" and args.op == "all_reduce"
+                           else "copy in, the collective, copy the result back, on one stream (what a user of a device-pointer collective API writes)")),
+               "table": [{"bytes": r.nbytes, "e2e_us": round(r.e2e_us, 2), "e2e_busbw": round(r.bw(args.op, n)["e2e_busbw"], 2)} for r in e2e_rows]}
+        verified = verified and e2e_ok
     wall = time.time() - t_wall
     summ = harness.summarize(rows, args.op, n)
     if dist.rank == 0:
@@ -104,21 +117,22 @@ def main() -> int:
             "metric": metric, "value": round(summ["avg_busbw"], 3), "unit": "GB/s", "n_gpus": n, "steps": args.steps, "warmup": warmup,
             "ms_per_step": round(summ["sweep_ms"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (deterministic random-like bf16 buffers; no network, no dataset)",
-            "impl": "reference" if args.impl == "reference" else "ours",
+            "impl": "reference" if args.impl.startswith("reference") else "ours", "backend": backend.version,
             "config": {"model": "none (collective benchmark: the reference has no model code)", "benchmark": f"{args.op}_perf", "sizes": f"{args.min}..{args.max} x2",
                        "global_batch": None, "seq_len": None, "parallelism": f"1 rank per GPU x{n}", "placements": "out-of-place + in-place",
                        "l2": "buffers rotate through a 192 MiB window (> 126 MB L2); sizes >= 192 MiB exceed L2 by themselves",
-                       "backend": backend.version, "aggregate": "nccl-tests bus bandwidth (per-link hardware rate), not multiplied by N",
+                       "aggregate": "nccl-tests bus bandwidth (per-link hardware rate), not multiplied by N",
                        "scaling_note": "bus bandwidth is normalised per GPU by construction: perfect scaling is a CONSTANT value from 2 to 8 GPUs (aggregate_bus_gbs = value x N is the whole-job rate); "
                                        "the 1-GPU value has no bus in it (an HBM copy with the fused epilogue) and is not a base for efficiency"},
             "peak_busbw": round(summ["peak_busbw"], 2), "aggregate_bus_gbs": round(summ["avg_busbw"] * n, 2), "verified_vs_torch_fp32": bool(verified),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "power_w_max": clocks["power_w_max"]},
-            "gpu_launches": int(summ["measurements"] * args.steps) if args.impl == "ours" else 0, "gpu_launches_incl_warmup": int(launches), "e2e": e2e, "wall_s": round(wall, 2), "table": harness.rows_json(rows, args.op, n),
+            "gpu_launches": int(summ["measurements"] * args.steps) if args.impl == "ours" else 0,
+            "verify": "random bf16 data (sums not exact in bf16) vs an fp32 torch reference within 1 bf16 ulp, at sizes taking the Lamport, NVLS / two-shot and scalar-tail paths" if args.op == "all_reduce" else "vs fp32 torch reference", "gpu_launches_incl_warmup": int(launches), "e2e": e2e, "wall_s": round(wall, 2), "table": harness.rows_json(rows, args.op, n),
         }
-        if args.impl == "reference":
+        if args.impl.startswith("reference"):
             out["reference_note"] = ("the reference repo ships no collective code or Python package; its nccl-test manifests run NCCL's *_perf on the node "
                                      "(net plugins are off the intra-node path), so this arm is the image's stock libnccl called through its C API with the "
-                                     "reference's NCCL env profile (gpudirect-tcpxo/README.md:71-103); pip install of /root/reference: see DESIGN.md")
+                                     "NCCL's own defaults (B200_REF_PROFILE=1 applies the reference's multi-node env profile, gpudirect-tcpxo/README.md:71-103); pip install of /root/reference: see DESIGN.md")
         print(json.dumps(out), flush=True)
     if args.extra_ops:
         extra = {}

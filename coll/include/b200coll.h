@@ -89,7 +89,7 @@ typedef struct {
   size_t arena_bytes;        /* symmetric user heap per rank (default: env B200COLL_ARENA_MB or 2560 MiB) */
   int enable_nvls;           /* -1 auto (probe), 0 off, 1 require */
   int max_ctas;              /* 0 = auto */
-  int timeout_ms;            /* device-side watchdog for every cross-GPU spin (default 20000) */
+  int timeout_ms;            /* device-side watchdog for every cross-GPU spin and the rendezvous: default 600000 (env B200COLL_TIMEOUT_MS), 0 = none, < 0 = default */
   int debug;                 /* 0 quiet, 1 info, 2 trace (env B200COLL_DEBUG) */
 } b200collConfig;
 
@@ -111,6 +111,8 @@ typedef struct {
   uint64_t kernel_launches;
   uint64_t staged_calls;     /* calls that went through the staging copy (unregistered buffers) */
   uint64_t p2p_sends, p2p_recvs, p2p_bytes;   /* point-to-point operations and the bytes they moved (sent + received) */
+  uint64_t host_calls, host_bytes;            /* b200collAllReduceHost calls and the input bytes they carried */
+  uint64_t host_zero_copy, host_pipelined;    /* ... of which: one-kernel zero-copy calls / chunked three-leg pipelines */
 } b200collStats;
 
 /* Device-written watchdog record (host-pinned). code != 0 means the comm is poisoned. */
@@ -185,6 +187,21 @@ b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, c
 b200collResult_t b200collReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep,
                                 b200collRedOp_t op, int root, b200collComm_t comm, b200collStream_t stream);
 b200collResult_t b200collBarrier(b200collComm_t comm, b200collStream_t stream);
+
+/* --- host path (src/hostpath.cu). CommInitRank binds the calling thread to the CPUs of the GPU's NUMA node (B200COLL_AFFINITY=0:
+ * leave it alone, 2: restore the previous mask after init). HostAlloc returns pinned, device-mapped host memory on that node.
+ * AllReduceHost is the end-to-end step "pinned host -> GPU -> all-reduce -> pinned host" as one asynchronous call on `stream`:
+ * tiny messages run as ONE kernel that reads and writes host memory over PCIe, large ones are chunked so that the host-to-device
+ * copy of chunk i+1, the all-reduce of chunk i and the copy-back of chunk i-1 overlap. Same call on every rank; staging comes from
+ * the symmetric heap on first use (a collective contract, like MemAlloc). */
+b200collResult_t b200collHostAlloc(b200collComm_t comm, void** ptr, size_t bytes);
+b200collResult_t b200collHostFree(b200collComm_t comm, void* ptr);
+b200collResult_t b200collAllReduceHost(const void* host_send, void* host_recv, size_t count, const b200collEpilogue* ep,
+                                       b200collRedOp_t op, b200collComm_t comm, b200collStream_t stream);
+/* NUMA node of this rank's GPU (-1 unknown) and its local CPU list as sysfs prints it. */
+b200collResult_t b200collCommNumaGet(b200collComm_t comm, int* numa_node, char* cpulist, size_t len);
+/* Test hook: parse a sysfs cpulist ("0-31,64-95") into at most `max` CPU numbers; returns how many. */
+int b200collDebugParseCpuList(const char* s, int* cpus, int max);
 
 /* --- point to point (ncclSend / ncclRecv / ncclGroupStart / ncclGroupEnd). `bytes` of opaque data; buffers 16-byte aligned.
  * A send pairs with the peer's recv of the same size, in call order per pair. Everything between GroupStart and GroupEnd

@@ -30,9 +30,10 @@ __device__ __forceinline__ bool last_block_ticket(const CommDev& c) {
 constexpr size_t kOffMcCounter = 64 << 10;    // u32[kMaxBlocks], multicast-addressed
 constexpr size_t kOffMcCalls = 128 << 10;     // u32[kMaxBlocks], local bookkeeping
 template <bool RELEASE>
-__device__ __forceinline__ bool barrier_blocks_mc(const CommDev& c, uint32_t op) {
-  if (c.mc == nullptr) return false;
+__device__ __forceinline__ int barrier_blocks_mc(const CommDev& c, uint32_t op) {      // -1: no multicast mapping, use the flag exchange; 1 ok; 0 watchdog
+  if (c.mc == nullptr) return -1;
   __syncthreads();
+  int bad = 0;
   if (threadIdx.x == 0) {
     uint32_t* calls = reinterpret_cast<uint32_t*>(c.peer[c.rank] + kOffMcCalls) + blockIdx.x;
     const uint32_t k = *calls + 1;
@@ -47,24 +48,26 @@ __device__ __forceinline__ bool barrier_blocks_mc(const CommDev& c, uint32_t op)
       uint32_t spins = 0;
       while ((int32_t)((v = ld_relaxed_sys(mine)) - want) < 0) {
         if (((++spins) & 0x3FF) == 0) {
-          if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 1, 0xFFu, want, v, op); break; }
+          if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 1, 0xFFu, want, v, op); bad = 1; break; }
         }
       }
     }
     (void)ld_acquire_sys(mine);
   }
-  __syncthreads();
-  return true;
+  return __syncthreads_or(bad) ? 0 : 1;
 }
 #endif
 
+// Returns false when the watchdog fired (a peer never arrived): the caller must not touch peer data and returns at once — the
+// communicator is poisoned, the host reports b200collRemoteError, and nothing unsynchronised is read or written.
 template <bool RELEASE>
-__device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch, uint32_t op) {
+__device__ __forceinline__ bool barrier_blocks(const CommDev& c, uint32_t epoch, uint32_t op) {
 #ifdef B200COLL_VARIANT_MCBAR
-  if (barrier_blocks_mc<RELEASE>(c, op)) return;
+  { const int r = barrier_blocks_mc<RELEASE>(c, op); if (r >= 0) return r != 0; }
 #endif
   __syncthreads();
   const int t = threadIdx.x;
+  int bad = 0;
   if (t < c.nranks) {
     uint32_t* remote = reinterpret_cast<uint32_t*>(c.peer[t] + kOffFlags) + (size_t)blockIdx.x * kMaxRanks + c.rank;
     if (RELEASE) st_release_sys(remote, epoch); else st_relaxed_sys(remote, epoch);
@@ -77,13 +80,13 @@ __device__ __forceinline__ void barrier_blocks(const CommDev& c, uint32_t epoch,
       uint32_t spins = 0;
       while ((int32_t)((v = ld_relaxed_sys(mine)) - epoch) < 0) {
         if (((++spins) & 0x3FF) == 0) {
-          if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 1, t, epoch, v, op); break; }
+          if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 1, t, epoch, v, op); bad = 1; break; }
         }
       }
     }
     (void)ld_acquire_sys(mine);
   }
-  __syncthreads();
+  return __syncthreads_or(bad) == 0;
 }
 
 }  // namespace b200coll

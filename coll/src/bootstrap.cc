@@ -3,6 +3,7 @@
 
 #include <errno.h>
 #include <poll.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/socket.h>
 #include <sys/un.h>
@@ -21,10 +22,10 @@ static long long now_ms() {
   return (long long)ts.tv_sec * 1000 + ts.tv_nsec / 1000000;
 }
 
-static bool wait_readable(int fd, int timeout_ms) {
+static bool wait_readable(int fd, int timeout_ms) {      // timeout_ms <= 0: wait for ever
   pollfd p{fd, POLLIN, 0};
   while (true) {
-    int r = poll(&p, 1, timeout_ms);
+    int r = poll(&p, 1, timeout_ms > 0 ? timeout_ms : -1);
     if (r > 0) return true;
     if (r == 0) return false;
     if (errno != EINTR) return false;
@@ -103,6 +104,26 @@ static socklen_t make_addr(const std::string& name, sockaddr_un* a) {
   return (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + n);
 }
 
+// Who is on the other end of a connected Unix socket. The rendezvous name is derived from values other processes on the host can
+// guess (MASTER_ADDR:PORT), and what travels over this channel — SCM_RIGHTS descriptors of every rank's GPU arena — is the job's
+// memory, so a connection only counts when it comes from this user and proves it knows the job's token (below).
+static bool same_user(int fd) {
+  ucred cr{};
+  socklen_t len = sizeof(cr);
+  if (getsockopt(fd, SOL_SOCKET, SO_PEERCRED, &cr, &len) != 0) return false;
+  return cr.uid == geteuid();
+}
+
+// Second, independent hash of the rendezvous name plus an optional secret every rank of the job shares (B200COLL_RENDEZVOUS_SECRET,
+// e.g. from the Job's env): sent in the hello, checked by rank 0. With the secret set, knowing MASTER_ADDR:PORT is not enough to join.
+static unsigned long long job_token(const std::string& name) {
+  const char* secret = getenv("B200COLL_RENDEZVOUS_SECRET");
+  const std::string text = name + "|" + (secret ? secret : "");
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (unsigned char ch : text) { h ^= ch; h *= 0x100000001B3ull; h ^= h >> 29; }
+  return h;
+}
+
 Bootstrap::~Bootstrap() { close_all(); }
 
 void Bootstrap::close_all() {
@@ -117,7 +138,10 @@ std::string Bootstrap::init(const std::string& name, int rank, int nranks, int t
   if (nranks == 1) return "";
   sockaddr_un addr;
   socklen_t alen = make_addr(name, &addr);
+  const bool forever = timeout_ms <= 0;
   const long long deadline = now_ms() + timeout_ms;
+  const unsigned long long token = job_token(name);
+  struct Hello { int rank, nranks; unsigned long long token; };
   if (rank == 0) {
     listen_fd_ = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
     if (listen_fd_ < 0) return errstr("socket");
@@ -126,14 +150,16 @@ std::string Bootstrap::init(const std::string& name, int rank, int nranks, int t
     peer_fd_.assign(nranks, -1);
     for (int joined = 1; joined < nranks;) {
       long long left = deadline - now_ms();
-      if (left <= 0 || !wait_readable(listen_fd_, (int)left)) return "bootstrap: timed out waiting for ranks to join";
+      if (!forever && left <= 0) return "bootstrap: timed out waiting for ranks to join";
+      if (!wait_readable(listen_fd_, forever ? 0 : (int)left)) return "bootstrap: timed out waiting for ranks to join";
       int fd = accept4(listen_fd_, nullptr, nullptr, SOCK_CLOEXEC);
       if (fd < 0) { if (errno == EINTR) continue; return errstr("accept"); }
-      int hello[2] = {0, 0};
-      std::string e = uds_recv_all(fd, hello, sizeof(hello), timeout_ms);
-      if (!e.empty()) { close(fd); return e; }
-      if (hello[0] <= 0 || hello[0] >= nranks || hello[1] != nranks || peer_fd_[hello[0]] >= 0) { close(fd); return "bootstrap: bad hello from peer"; }
-      peer_fd_[hello[0]] = fd;
+      // A stranger must not be able to join, and must not be able to abort the job by trying: drop the connection and keep waiting.
+      if (!same_user(fd)) { close(fd); rejected_++; continue; }
+      Hello hello{};
+      std::string e = uds_recv_all(fd, &hello, sizeof(hello), 2000);
+      if (!e.empty() || hello.token != token || hello.rank <= 0 || hello.rank >= nranks || hello.nranks != nranks || peer_fd_[hello.rank] >= 0) { close(fd); rejected_++; continue; }
+      peer_fd_[hello.rank] = fd;
       joined++;
     }
     close(listen_fd_); listen_fd_ = -1;
@@ -143,11 +169,12 @@ std::string Bootstrap::init(const std::string& name, int rank, int nranks, int t
       if (hub_fd_ < 0) return errstr("socket");
       if (connect(hub_fd_, reinterpret_cast<sockaddr*>(&addr), alen) == 0) break;
       close(hub_fd_); hub_fd_ = -1;
-      if (now_ms() > deadline) return "bootstrap: timed out connecting to rank 0";
+      if (!forever && now_ms() > deadline) return "bootstrap: timed out connecting to rank 0";
       usleep(2000);
     }
-    int hello[2] = {rank, nranks};
-    std::string e = uds_send_all(hub_fd_, hello, sizeof(hello));
+    if (!same_user(hub_fd_)) return "bootstrap: the rendezvous socket is held by another user (name squatting?); refusing to hand over arena descriptors";
+    Hello hello{rank, nranks, token};
+    std::string e = uds_send_all(hub_fd_, &hello, sizeof(hello));
     if (!e.empty()) return e;
   }
   return barrier();

@@ -29,9 +29,11 @@ class Bootstrap {
   void close_all();
   int rank() const { return rank_; }
   int nranks() const { return nranks_; }
+  int rejected() const { return rejected_; }   // rank 0: connections dropped during init (wrong user, wrong token, malformed hello)
 
  private:
   int rank_ = -1, nranks_ = 0, timeout_ms_ = 0;
+  int rejected_ = 0;
   int listen_fd_ = -1;
   int hub_fd_ = -1;                 // non-root: connection to rank 0
   std::vector<int> peer_fd_;        // root: connection per rank (index = rank; [0] unused)

@@ -205,7 +205,7 @@ static void finalize_comm(b200collComm* c) {
   d.mc = c->nvls ? reinterpret_cast<char*>(c->mc_va) : nullptr;
   d.state = c->state_dev;
   d.fault = c->fault_dev;
-  d.timeout_ns = (unsigned long long)c->cfg.timeout_ms * 1000000ull;
+  d.timeout_ns = c->cfg.timeout_ms == 0 ? ~0ull : (unsigned long long)c->cfg.timeout_ms * 1000000ull;   // 0 = no watchdog
   c->free_list.clear();
   c->free_list.push_back({kOffHeap, c->arena.total - kOffHeap});
   cudaDeviceProp prop;
@@ -235,6 +235,7 @@ std::atomic<int> g_loopback_comms{0};
 
 static void destroy_resources(b200collComm* c) {
   const Drv& d = drv();
+  hostpath_destroy(c);
   if (c->loopback_counted) { c->loopback_counted = false; g_loopback_comms.fetch_sub(1); }
   if (c->mc_va) { unmap_va(c->mc_va, c->arena.total); c->mc_va = 0; }
   if (c->mc_bound && c->mc_handle) {
@@ -285,7 +286,7 @@ void b200collConfigDefault(b200collConfig* cfg) {
   cfg->arena_bytes = (size_t)env_long("B200COLL_ARENA_MB", 2560) << 20;
   cfg->enable_nvls = (int)env_long("B200COLL_NVLS", -1);
   cfg->max_ctas = (int)env_long("B200COLL_MAX_CTAS", 0);
-  cfg->timeout_ms = (int)env_long("B200COLL_TIMEOUT_MS", 20000);
+  cfg->timeout_ms = (int)env_long("B200COLL_TIMEOUT_MS", 600000);   // c10d / NCCL scale: ordinary rank skew (checkpoints, evaluation) must not trip it; 0 = never
   cfg->debug = debug_level();
 }
 
@@ -318,15 +319,16 @@ b200collResult_t b200collCommInitRank(b200collComm_t* out, int nranks, const b20
   std::unique_ptr<b200collComm> c(new b200collComm());
   c->rank = rank; c->nranks = nranks;
   if (cfg_in) c->cfg = *cfg_in; else b200collConfigDefault(&c->cfg);
-  if (c->cfg.timeout_ms <= 0) c->cfg.timeout_ms = 20000;
+  if (c->cfg.timeout_ms < 0) c->cfg.timeout_ms = (int)env_long("B200COLL_TIMEOUT_MS", 600000);
   RT_TRY(cudaGetDevice(&c->device));
   RT_TRY(cudaFree(0));
   CUdevice cudev;
   CU_TRY(d.cuDeviceGet(&cudev, c->device));
+  bind_to_gpu_numa(c.get(), true);      // before anything is allocated: host-side buffers created from here on land on the GPU's node
 
   c->boot.reset(new Bootstrap());
   std::string name(id->internal, strnlen(id->internal, sizeof(id->internal)));
-  BOOT_TRY(c->boot->init(name, rank, nranks, std::max(c->cfg.timeout_ms, 60000)));
+  BOOT_TRY(c->boot->init(name, rank, nranks, c->cfg.timeout_ms == 0 ? 0 : std::max(c->cfg.timeout_ms, 60000)));   // 0 = wait for ever
   c->boot_name = name;
 
   struct Info { unsigned char uuid[16]; int mc; int p2p_all; unsigned long long arena_bytes; } mine = {};
@@ -433,6 +435,7 @@ b200collResult_t b200collCommInitRank(b200collComm_t* out, int nranks, const b20
     for (auto& sh : c->shape) sh.max_ctas = std::min(sh.max_ctas, c->max_ctas);
   }
   BOOT_TRY(c->boot->barrier());
+  restore_affinity_after_init(c.get());
   *out = c.release();
   return b200collSuccess;
 }
@@ -451,7 +454,7 @@ b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* de
     std::unique_ptr<b200collComm> c(new b200collComm());
     c->rank = i; c->nranks = n; c->device = devs ? devs[i] : i;
     if (cfg_in) c->cfg = *cfg_in; else b200collConfigDefault(&c->cfg);
-    if (c->cfg.timeout_ms <= 0) c->cfg.timeout_ms = 20000;
+    if (c->cfg.timeout_ms < 0) c->cfg.timeout_ms = (int)env_long("B200COLL_TIMEOUT_MS", 600000);
     c->group = group;
     for (int q = 0; q < i; q++) if (cs[q]->device == c->device) dup = true;
     CUdevice cudev; int mc = 0;
@@ -509,6 +512,9 @@ b200collResult_t b200collCommInitAll(b200collComm_t* comms, int n, const int* de
       for (auto& sh : c->shape) sh.max_ctas = std::min(sh.max_ctas, c->max_ctas);
     }
   }
+  bool one_gpu = true;
+  for (auto& c : cs) one_gpu &= c->device == cs[0]->device;
+  for (auto& c : cs) bind_to_gpu_numa(c.get(), one_gpu && c->rank == 0);   // one process driving several GPUs cannot sit on all their nodes
   group->alive = n;
   for (int i = 0; i < n; i++) comms[i] = cs[i].release();
   cudaSetDevice(prev_dev);
@@ -734,6 +740,10 @@ b200collResult_t b200collSelfCheck(char* buf, size_t buflen) {
 
 // Test hook (CPU-only): run the rendezvous protocol with arbitrary descriptors (memfd in the unit tests) so the
 // SCM_RIGHTS plumbing is covered without a GPU. out_fds must hold nranks ints; bcast_fd receives rank 0's descriptor.
+// How many connections rank 0's last BootstrapSelfTest dropped (wrong user / token / malformed hello).
+static std::atomic<int> g_selftest_rejected{0};
+extern "C" int b200collBootstrapSelfTestRejected(void) { return g_selftest_rejected.load(); }
+
 extern "C" int b200collBootstrapSelfTest(const char* name, int rank, int nranks, int my_fd, int* out_fds, int* bcast_fd, int timeout_ms) {
   b200coll::Bootstrap b;
   std::string e = b.init(name ? name : "selftest", rank, nranks, timeout_ms);
@@ -747,5 +757,6 @@ extern "C" int b200collBootstrapSelfTest(const char* name, int rank, int nranks,
   for (int r = 0; r < nranks; r++) out_fds[r] = fds[r];
   if (!(e = b.broadcast_fd(0, rank == 0 ? my_fd : -1, bcast_fd)).empty()) { b200coll::set_last_error(e); return 5; }
   if (!(e = b.barrier()).empty()) { b200coll::set_last_error(e); return 6; }
+  g_selftest_rejected.store(b.rejected());
   return 0;
 }

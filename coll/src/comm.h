@@ -1,6 +1,7 @@
 // Host-side communicator state for libb200coll.
 #pragma once
 #include <cuda.h>
+#include <sched.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -46,6 +47,15 @@ struct Arena {
   int device = -1;
 };
 
+// Host path (hostpath.cu): copy streams, events and the two staging pairs of b200collAllReduceHost.
+struct HostPath {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_in_ready[2] = {}, ev_in_free[2] = {}, ev_out_free[2] = {};
+  void* in[2] = {};
+  void* out[2] = {};
+  size_t chunk_bytes = 0;
+};
+
 extern std::atomic<int> g_loopback_comms;   // live communicators whose ranks share a GPU (virtual ranks): PDL stays off
 
 struct SharedGroup;   // in-process groups (InitAll) share ownership bookkeeping
@@ -87,6 +97,12 @@ struct b200collComm {
   uint32_t split_seq = 0;               // CommSplit calls so far (a collective call, so the same on every rank)
   size_t p2p_window = 0;                // staged receives: bytes per staging window; 0 = an equal share of the staging area
   uint32_t stats_tick = 0;              // collective calls since init; the counters page is refreshed every 256
+  int numa_node = -1;                   // of this rank's GPU (sysfs), -1 unknown
+  std::string local_cpulist;            // GPU-local CPUs as sysfs prints them
+  cpu_set_t affinity_saved;             // the calling thread's mask before CommInitRank narrowed it
+  bool affinity_changed = false;
+  b200coll::HostPath host;
+  std::map<void*, size_t> host_allocs;  // HostAlloc: base -> mapped length
 };
 
 namespace b200coll {
@@ -100,6 +116,11 @@ struct LaunchPlan {
 // tuner.cc
 void stats_page_publish(b200collComm* c);   // comm.cu
 int tuner_blocks(b200collOp_t op, b200collAlgo_t algo, size_t work_vecs, int max_ctas, int unroll);
+
+// hostpath.cu
+void bind_to_gpu_numa(b200collComm* c, bool allow_bind);   // allow_bind=false: only record the node (in-process groups spanning GPUs)
+void restore_affinity_after_init(b200collComm* c);
+void hostpath_destroy(b200collComm* c);
 
 // collectives.cu
 b200collResult_t launch_fill_sentinel(b200collComm* c, cudaStream_t s);

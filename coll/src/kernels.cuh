@@ -81,7 +81,7 @@ __device__ __forceinline__ uint4 ll_wait(const CommDev& c, const char* slot, int
       v = ld_vec_volatile(slot);
       if (ll_ready(v)) break;
       if (((++spins) & 0x3FF) == 0) {
-        if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 2, src, 0, v.x, op); break; }
+        if (c.fault->code != 0 || globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 2, src, 0, v.x, op); v = make_uint4(0, 0, 0, 0); break; }   // never hand a half-written slot to the reduction
       }
     }
   }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) k_pull_reduce(COMM_PARAM, size_t in_
   constexpr int E = Epv<InT>::value;
   constexpr int U = 2;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   const size_t nvec = count / E;
   const size_t stride = (size_t)gridDim.x * blockDim.x * U;
   for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kThreads) k_pull_reduce(COMM_PARAM, size_t in_
       out[e] = from_float<OutT>(acc * scale);
     }
   }
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_twoshot(COMM_PARAM, size_t in_o
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 2;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   const size_t nvec = count / E;
   const size_t v0 = nvec * c.rank / c.nranks, v1 = nvec * (c.rank + 1) / c.nranks;
   const size_t stride = (size_t)gridDim.x * blockDim.x * U;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_twoshot(COMM_PARAM, size_t in_o
     }
   }
   ar_tail_rank0<InT, OutT>(c, in_off, out_off, nvec * E, count, scale);
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_nvls(COMM_PARAM, size_t in_off,
   constexpr int E = Epv<InT>::value;
   constexpr int W = Pack<OutT, E>::W;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   const size_t nvec = count / E;
   const size_t v0 = nvec * c.rank / c.nranks, v1 = nvec * (c.rank + 1) / c.nranks;
   const size_t stride = (size_t)gridDim.x * blockDim.x * U;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) k_ar_nvls(COMM_PARAM, size_t in_off,
     }
   }
   ar_tail_rank0<InT, OutT>(c, in_off, out_off, nvec * E, count, scale);
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kThreads) k_ag_push(COMM_PARAM, const InT* __r
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 4;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   const size_t nvec = count / E;
   const size_t dst0 = out_off + (size_t)c.rank * count * sizeof(OutT);
   const size_t stride = (size_t)gridDim.x * blockDim.x * U;
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kThreads) k_ag_push(COMM_PARAM, const InT* __r
       }
     }
   }
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) k_a2av_push(COMM_PARAM, const InT* _
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 4;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   const size_t total = a.prefix[c.nranks];
   const size_t stride = (size_t)gridDim.x * blockDim.x * U;
   for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < total; base += stride) {
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) k_a2av_push(COMM_PARAM, const InT* _
       }
     }
   }
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kThreads) k_bcast(COMM_PARAM, const InT* __res
   constexpr int W = Pack<OutT, E>::W;
   constexpr int U = 4;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);          // every rank is done with the previous contents of its out
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;          // every rank is done with the previous contents of its out
   if (c.rank == root) {
     const size_t nvec = count / E;
     const size_t stride = (size_t)gridDim.x * blockDim.x * U;
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kThreads) k_bcast(COMM_PARAM, const InT* __res
       }
     }
   }
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_root(COMM_PARAM, size_t in_
   constexpr int E = Epv<InT>::value;
   constexpr int U = 2;
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   if (c.rank == root) {
     const size_t nvec = count / E;
     const size_t stride = (size_t)gridDim.x * blockDim.x * U;
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_root(COMM_PARAM, size_t in_
       }
     }
   }
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(128) k_ag_bulk(COMM_PARAM, const char* __restr
   __shared__ __align__(128) char ring[kBulkStages][kBulkChunk];
   __shared__ __align__(8) unsigned long long full[kBulkStages];
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<false>(c, 2 * s + 1, op);
+  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBulkStages; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(128) k_ag_bulk(COMM_PARAM, const char* __restr
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // every store has been performed, not just read
     asm volatile("fence.proxy.async.global;" ::: "memory");             // order the copy engine's writes before the flag stores of the barrier
   }
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 #endif
@@ -743,7 +743,7 @@ namespace b200coll {
 __global__ void k_barrier(COMM_PARAM, uint32_t op) {
   pdl_prologue();
   const uint32_t s = load_seq(c, kSeqBarrier);
-  barrier_blocks<true>(c, 2 * s + 2, op);
+  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 

@@ -23,6 +23,7 @@ struct Dim { unsigned x; };
 static thread_local Dim threadIdx{0}, blockIdx{0}, blockDim{1}, gridDim{1};
 struct CtaBarrier {
   std::atomic<unsigned> arrived{0}, phase{0};
+  std::atomic<int> any{0};            // __syncthreads_or: sticky (a watchdog hit is terminal)
   unsigned n = 1;
   void wait() {
     const unsigned p = phase.load(std::memory_order_acquire);
@@ -34,6 +35,7 @@ static thread_local CtaBarrier* g_bar = nullptr;
 #define __device__
 #define __forceinline__ inline
 static inline void __syncthreads() { g_bar->wait(); }
+static inline int __syncthreads_or(int pred) { if (pred) g_bar->any.store(1, std::memory_order_relaxed); g_bar->wait(); return g_bar->any.load(std::memory_order_relaxed); }
 static inline void __threadfence() {}      /* ThreadSanitizer does not model fences; the ticket below is an acq_rel RMW, which it does */
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 

@@ -53,7 +53,8 @@ class CommInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("calls", C.c_uint64 * 6), ("bytes", C.c_uint64 * 6), ("algo_calls", C.c_uint64 * 7), ("kernel_launches", C.c_uint64),
-                ("staged_calls", C.c_uint64), ("p2p_sends", C.c_uint64), ("p2p_recvs", C.c_uint64), ("p2p_bytes", C.c_uint64)]
+                ("staged_calls", C.c_uint64), ("p2p_sends", C.c_uint64), ("p2p_recvs", C.c_uint64), ("p2p_bytes", C.c_uint64),
+                ("host_calls", C.c_uint64), ("host_bytes", C.c_uint64), ("host_zero_copy", C.c_uint64), ("host_pipelined", C.c_uint64)]
 
 
 class Fault(C.Structure):
@@ -124,6 +125,11 @@ def load() -> C.CDLL:
     L.b200collBroadcast.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
     L.b200collReduce.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, ci, vp, vp]
     L.b200collBarrier.argtypes = [vp, vp]
+    L.b200collHostAlloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.b200collHostFree.argtypes = [vp, vp]
+    L.b200collAllReduceHost.argtypes = [vp, vp, sz, C.POINTER(Epilogue), ci, vp, vp]
+    L.b200collCommNumaGet.argtypes = [vp, C.POINTER(ci), C.c_char_p, sz]
+    L.b200collDebugParseCpuList.argtypes = [C.c_char_p, C.POINTER(ci), ci]
     L.b200collGroupStart.argtypes = []; L.b200collGroupEnd.argtypes = []
     L.b200collSend.argtypes = [vp, sz, ci, vp, vp]
     L.b200collRecv.argtypes = [vp, sz, ci, vp, vp]
@@ -352,6 +358,48 @@ class Comm:
             free[k].record(main)
         return out
 
+    def host_empty(self, numel: int, dtype):
+        """A pinned, device-mapped CPU tensor on the NUMA node of this rank's GPU (b200collHostAlloc): the buffer to hand to
+        `all_reduce_host`. On a two-socket 8-GPU box this placement is what keeps eight concurrent host<->device copies at link rate."""
+        import torch
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        nbytes = max(1, numel * itemsize)
+        p = C.c_void_p()
+        _check(load().b200collHostAlloc(self._h, C.byref(p), nbytes), "HostAlloc")
+        raw = (C.c_uint8 * nbytes).from_address(p.value)
+        t = torch.frombuffer(raw, dtype=torch.uint8).view(dtype)[:numel]
+        t._b200coll_host = p.value
+        self._host_allocs = getattr(self, "_host_allocs", {})
+        self._host_allocs[p.value] = raw
+        return t
+
+    def host_release(self, tensor) -> None:
+        p = getattr(tensor, "_b200coll_host", None)
+        if p is None:
+            raise ValueError("tensor was not allocated with Comm.host_empty()")
+        _check(load().b200collHostFree(self._h, C.c_void_p(p)), "HostFree")
+        self._host_allocs.pop(p, None)
+        tensor._b200coll_host = None
+
+    def numa(self) -> tuple[int, str]:
+        """(NUMA node of this rank's GPU or -1, its local CPU list as sysfs prints it)."""
+        node = C.c_int(-1)
+        buf = C.create_string_buffer(256)
+        _check(load().b200collCommNumaGet(self._h, C.byref(node), buf, len(buf)), "CommNumaGet")
+        return node.value, buf.value.decode()
+
+    def all_reduce_host(self, host_in, host_out=None, scale: float = 1.0, op: int = SUM, stream=None):
+        """The end-to-end step as one library call: `host_out` (pinned CPU tensor, default in place) = cast(scale * sum over ranks
+        of `host_in`). Asynchronous on `stream`; tiny messages run as one zero-copy kernel over PCIe, large ones are chunked so that
+        the copy in, the all-reduce and the copy back overlap (b200collAllReduceHost, coll/src/hostpath.cu). Same call on every rank."""
+        host_out = host_in if host_out is None else host_out
+        assert host_in.device.type == "cpu" and host_out.device.type == "cpu" and host_in.is_contiguous() and host_out.is_contiguous()
+        assert host_in.numel() == host_out.numel()
+        ep = self._ep(host_in, host_out, scale)
+        _check(load().b200collAllReduceHost(C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr()), host_in.numel(), C.byref(ep), op, self._h,
+                                            self._stream(stream)), "AllReduceHost")
+        return host_out
+
     def all_gather(self, src, dst, scale: float = 1.0, stream=None):
         ep = self._ep(src, dst, scale)
         _check(load().b200collAllGather(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(), C.byref(ep), self._h, self._stream(stream)), "AllGather")
@@ -446,7 +494,8 @@ class Comm:
         _check(load().b200collCommStatsGet(self._h, C.byref(s)), "CommStatsGet")
         return {"calls": list(s.calls), "bytes": list(s.bytes), "algo_calls": dict(zip(ALGO_NAMES, s.algo_calls)),
                 "kernel_launches": s.kernel_launches, "staged_calls": s.staged_calls,
-                "p2p_sends": s.p2p_sends, "p2p_recvs": s.p2p_recvs, "p2p_bytes": s.p2p_bytes}
+                "p2p_sends": s.p2p_sends, "p2p_recvs": s.p2p_recvs, "p2p_bytes": s.p2p_bytes,
+                "host_calls": s.host_calls, "host_bytes": s.host_bytes, "host_zero_copy": s.host_zero_copy, "host_pipelined": s.host_pipelined}
 
     def check_async_error(self) -> None:
         f = Fault()

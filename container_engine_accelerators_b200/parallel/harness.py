@@ -43,6 +43,7 @@ class Row:
     ip_us: float = -1.0
     e2e_us: float = -1.0
     in_bytes: int = 0
+    out_bytes: int = 0
 
     def bw(self, op: str, n: int) -> dict:
         f = bus_factor(op, n)
@@ -161,11 +162,31 @@ class OursBackend:
     def launches(self) -> int:
         return int(self.comm.stats()["kernel_launches"])
 
+    def host_buffers(self, in_elems: int, out_elems: int, dtype):
+        # pinned host memory on the NUMA node of this rank's GPU (b200collHostAlloc): part of the library's public API
+        return self.comm.host_empty(in_elems, dtype), self.comm.host_empty(out_elems, dtype)
+
+    def e2e_step(self, op: str, h_in, h_out, count: int, dev_off: int, stream) -> None:
+        """One end-to-end step through the public API. all_reduce: ONE call, b200collAllReduceHost (zero-copy kernel for tiny messages,
+        copy-in | all-reduce | copy-back pipelined over chunks for large ones). Other ops: copy in, collective, copy the whole result back."""
+        if op == "all_reduce":
+            self.comm.all_reduce_host(h_in, h_out, stream=stream)
+            return
+        _copy_launch_copy(self, op, h_in, h_out, count, dev_off, stream)
+
     def check(self) -> None:
         self.comm.check_async_error()
 
     def close(self):
         self.comm.destroy()
+
+
+def _copy_launch_copy(backend, op: str, h_in, h_out, count: int, dev_off: int, stream) -> None:
+    """What a user of a device-pointer collective API writes: pinned host -> device, the collective, the whole result -> pinned host."""
+    s, r = backend.send[dev_off:dev_off + h_in.numel()], backend.recv[dev_off:dev_off + h_out.numel()]
+    s.copy_(h_in, non_blocking=True)
+    backend.launch(op, s.data_ptr(), r.data_ptr(), count, stream.cuda_stream)
+    h_out.copy_(r, non_blocking=True)
 
 
 class NcclBackend:
@@ -175,16 +196,17 @@ class NcclBackend:
         import torch
         from . import nccl_ref
         self.torch = torch
-        for k, v in nccl_ref.REFERENCE_ENV.items():
-            os.environ.setdefault(k, v)
-        if os.environ.get("B200_REF_PROFILE", "1") == "0":      # stock NCCL defaults instead of the reference's env profile
-            for k in nccl_ref.REFERENCE_ENV:
-                os.environ.pop(k, None)
-        # NCCL prints "NCCL version ..." on stdout at any debug level >= VERSION: keep stdout to the one JSON line
+        # Default: stock NCCL settings (its own tuning for one NVSwitch node). B200_REF_PROFILE=1 applies the reference's multi-node
+        # env profile (gpudirect-tcpxo/README.md:71-103; it turns the LL protocol off) — both are measured in profiles/allreduce_sweep.md.
+        if os.environ.get("B200_REF_PROFILE", "0") == "1":
+            for k, v in nccl_ref.REFERENCE_ENV.items():
+                os.environ.setdefault(k, v)
+        # NCCL's INFO log is evidence (rank count, algorithm, NVLS): keep it, but on stderr — stdout carries exactly one JSON line.
         if "B200_REF_NCCL_DEBUG" in os.environ:
             os.environ["NCCL_DEBUG"] = os.environ["B200_REF_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
@@ -194,9 +216,17 @@ class NcclBackend:
         finally:
             os.dup2(saved, 1)
             os.close(saved)
-        self.profile = "reference env profile" if os.environ.get("B200_REF_PROFILE", "1") != "0" else "NCCL defaults"
-        self.send = torch.empty(capacity_elems, dtype=dtype, device="cuda")
-        self.recv = torch.empty(capacity_elems, dtype=dtype, device="cuda")
+        self.profile = "reference env profile" if os.environ.get("B200_REF_PROFILE", "0") == "1" else "NCCL defaults"
+        self.windows = []
+        if os.environ.get("B200_REF_SYM", "0") == "1":
+            # NCCL's own fast path for registered memory: ncclMemAlloc + ncclCommWindowRegister(NCCL_WIN_COLL_SYMMETRIC) (2.27+)
+            itemsize = torch.empty((), dtype=dtype).element_size()
+            self.send = self.comm.sym_tensor(capacity_elems, dtype, itemsize, self.windows)
+            self.recv = self.comm.sym_tensor(capacity_elems, dtype, itemsize, self.windows)
+            self.profile += ", ncclMemAlloc + symmetric windows"
+        else:
+            self.send = torch.empty(capacity_elems, dtype=dtype, device="cuda")
+            self.recv = torch.empty(capacity_elems, dtype=dtype, device="cuda")
         self.dt = {torch.bfloat16: nccl_ref.NCCL_BFLOAT16, torch.float16: nccl_ref.NCCL_FLOAT16, torch.float32: nccl_ref.NCCL_FLOAT32}[dtype]
         self.itemsize = self.send.element_size()
         self.nvls = None
@@ -229,28 +259,70 @@ class NcclBackend:
     def launches(self) -> int:
         return 0   # NCCL's kernels are not ours
 
+    def host_buffers(self, in_elems: int, out_elems: int, dtype):
+        return self.torch.empty(in_elems, dtype=dtype).pin_memory(), self.torch.empty(out_elems, dtype=dtype).pin_memory()
+
+    def e2e_step(self, op: str, h_in, h_out, count: int, dev_off: int, stream) -> None:
+        _copy_launch_copy(self, op, h_in, h_out, count, dev_off, stream)
+
     def check(self):
         pass
 
     def close(self):
+        for win, p in self.windows:
+            self.comm.lib.ncclCommWindowDeregister(self.comm.comm, win)
+            self.comm.lib.ncclMemFree(p)
         self.comm.destroy()
 
 
 def _gen_expected(torch, op, rank, n, count, device):
-    """Deterministic integers in [-8, 8] x 0.25: sums over <= 8 ranks are exact in bf16."""
+    """Pseudo-random bf16-representable values in (-4, 4) from an integer hash of (rank, index): every rank can compute every other
+    rank's input, and — unlike small multiples of 0.25 — sums of them are NOT exactly representable in bf16, so the accumulate precision
+    and the final rounding of a reduction are actually tested."""
     def gen(r, idx):
-        return (((idx * 7 + r * 13 + (idx >> 9)) % 17) - 8).to(torch.float32) * 0.25
+        h = (idx * 2654435761 + (r + 1) * 40503 + ((idx >> 7) * 977)) & 0xFFFF
+        v = (h.to(torch.float32) - 32768.0) / 8192.0
+        return v.to(torch.bfloat16).to(torch.float32)
     return gen
 
 
-def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
-    """One correctness pass against a plain PyTorch fp32 reference of the same op."""
+def bf16_ulp(torch, x):
+    """Spacing of bf16 numbers around |x| (8 significand bits), as fp32."""
+    e = torch.floor(torch.log2(x.abs().clamp_min(2.0 ** -126)))
+    return torch.exp2(e - 7)
+
+
+def reduction_ok(torch, got32, want32, out_dtype, nranks: int, max_abs_in: float = 4.0):
+    """got32 (the kernel's output widened to fp32) must lie within ONE ulp of the output type around the fp32-accumulated reference:
+    a correctly rounded fp32 accumulation lands within half an ulp whatever the summation order; accumulating in bf16 / fp16 (e.g. a
+    multimem.ld_reduce without .acc::f32) is off by several ulps on a large share of the elements and fails. The absolute slack covers
+    fp32 reassociation when a sum cancels to almost nothing."""
+    err = (got32 - want32).abs()
+    ulp = bf16_ulp(torch, want32) if out_dtype == torch.bfloat16 else (want32.abs() * 2.0 ** -10 if out_dtype == torch.float16 else want32.abs() * 2.0 ** -22)
+    tol = ulp + nranks * max_abs_in * 2.0 ** -22
+    return bool((err <= tol).all().item())
+
+
+VERIFY_COUNTS = {"all_reduce": (1 << 16, (1 << 21) + 8, (1 << 20) + 13)}   # Lamport path; NVLS / two-shot body; a count that leaves a scalar tail
+
+
+def verify(backend, dist: Dist, op: str, dtype, count: int | None = None) -> bool:
+    """Correctness against a plain PyTorch fp32 reference of the same op, on the sizes listed in VERIFY_COUNTS (all_reduce: one per
+    algorithm family that the timed sweep uses) with data whose sums are not exact in bf16."""
+    import torch
+    counts = (count,) if count else VERIFY_COUNTS.get(op, (1 << 16,))
+    ok = all(_verify_one(backend, dist, op, dtype, c) for c in counts)
+    return dist.sum_([1.0 if ok else 0.0])[0] == dist.world
+
+
+def _verify_one(backend, dist: Dist, op: str, dtype, count: int) -> bool:
     import torch
     n, rank = dist.world, dist.rank
     dev = backend.send.device
     gen = _gen_expected(torch, op, rank, n, count, dev)
     E = 8
-    count = max(E, count // E * E)
+    if op != "all_reduce":
+        count = max(E, count // E * E)
     if op in FULL_MESSAGE_OPS:
         in_elems, out_elems = count, count
     elif op in ("all_gather", "gather"):
@@ -268,14 +340,16 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
     torch.cuda.synchronize(); dist.barrier()
     backend.check()
     got = backend.recv[:out_elems].float()
+    reduced = False
     if op == "all_reduce":
-        want = sum(gen(r, idx) for r in range(n))
+        want = sum(gen(r, idx) for r in range(n)); reduced = True
     elif op == "broadcast":
         want = gen(ROOT, idx)
     elif op == "sendrecv":
         want = gen((rank - 1) % n, idx)
     elif op == "reduce":                                   # only the root's recv is defined
         want = sum(gen(r, idx) for r in range(n)) if rank == ROOT else torch.full_like(got, 77.0)
+        reduced = rank == ROOT
     elif op == "all_gather" or (op == "gather" and rank == ROOT):
         j = torch.arange(count, device=dev)
         want = torch.cat([gen(r, j) for r in range(n)])
@@ -285,13 +359,36 @@ def verify(backend, dist: Dist, op: str, dtype, count: int = 1 << 16) -> bool:
         want = gen(ROOT, torch.arange(count, device=dev) + rank * count)
     elif op == "reduce_scatter":
         j = torch.arange(count, device=dev) + rank * count
-        want = sum(gen(r, j) for r in range(n))
+        want = sum(gen(r, j) for r in range(n)); reduced = True
     else:
         j = torch.arange(count, device=dev) + rank * count
         want = torch.cat([gen(r, j) for r in range(n)])
-    ok = bool(torch.equal(got, want.to(dtype).float()))
-    oks = dist.sum_([1.0 if ok else 0.0])[0]
-    return oks == n
+    if reduced and n > 1:
+        return reduction_ok(torch, got, want, dtype, n)
+    return bool(torch.equal(got, want.to(dtype).float()))
+
+
+def verify_e2e(backend, dist: Dist, dtype) -> bool:
+    """The end-to-end all-reduce (host in, host out) at one size per regime: zero-copy kernel, single chunk, chunked pipeline."""
+    import torch
+    n, rank = dist.world, dist.rank
+    ok = True
+    counts = (1 << 14, (1 << 19) + 24, (5 << 20) + 13)
+    h_in, h_out = backend.host_buffers(max(counts), max(counts), dtype)
+    gen = _gen_expected(torch, "all_reduce", rank, n, 0, "cpu")
+    stream = torch.cuda.current_stream()
+    for count in counts:
+        idx = torch.arange(count)
+        h_in[:count] = gen(rank, idx).to(dtype)
+        h_out[:count] = 77.0
+        torch.cuda.synchronize(); dist.barrier()
+        backend.e2e_step("all_reduce", h_in[:count], h_out[:count], count, 0, stream)
+        torch.cuda.synchronize(); dist.barrier()
+        backend.check()
+        want = sum(gen(r, idx) for r in range(n))
+        got = h_out[:count].float()
+        ok = ok and (reduction_ok(torch, got, want, dtype, n) if n > 1 else bool(torch.equal(got, want.to(dtype).float())))
+    return dist.sum_([1.0 if ok else 0.0])[0] == dist.world
 
 
 def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_bytes: int, max_bytes: int, factor: int = 2,
@@ -306,9 +403,16 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     host_in = host_out = None
     if e2e:
-        host_in = torch.empty(max_bytes // itemsize, dtype=dtype).pin_memory()
+        # sized for the largest row of the sweep; the rows below use prefixes
+        n_max = max_bytes // itemsize
+        if op in FULL_MESSAGE_OPS:
+            cap_in = cap_out = n_max
+        else:
+            cap_in = n_max if op not in ("all_gather", "gather") else n_max // n + 64
+            cap_out = n_max if op not in ("reduce_scatter", "scatter") else n_max // n + 64
+        host_in, host_out = backend.host_buffers(cap_in, cap_out, dtype)
         host_in.fill_(0.25)
-        host_out = torch.empty(4096 // itemsize, dtype=dtype).pin_memory()
+        host_out.zero_()
     nbytes = min_bytes
     while nbytes <= max_bytes:
         E = 16 // itemsize
@@ -353,18 +457,15 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
             torch.cuda.synchronize()
             raw.append((len(rows), "ip" if ip else "oop", e0.elapsed_time(e1) / steps))
         if e2e:
-            # the user-visible call: pinned host -> device, collective, small device -> host read of the result
+            # the user-visible step: this rank's input starts in pinned host memory and the whole result ends there
+            h_in, h_out = host_in[:in_elems], host_out[:out_elems]
+            row.out_bytes = out_elems * itemsize
             for i in range(min(warmup, 2)):
-                backend.send[:in_elems].copy_(host_in[:in_elems], non_blocking=True)
-                backend.launch(op, sbase, rbase, count, st)
-                host_out.copy_(backend.recv[:host_out.numel()], non_blocking=True)
+                backend.e2e_step(op, h_in, h_out, count, 0, stream)
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
             e0.record(stream)
             for i in range(steps):
-                off = (i % slots) * slot_elems
-                backend.send[off:off + in_elems].copy_(host_in[:in_elems], non_blocking=True)
-                backend.launch(op, sbase + off * itemsize, rbase + off * itemsize, count, st)
-                host_out.copy_(backend.recv[off:off + host_out.numel()], non_blocking=True)
+                backend.e2e_step(op, h_in, h_out, count, (i % slots) * slot_elems, stream)
             e1.record(stream)
             torch.cuda.synchronize()
             raw.append((len(rows), "e2e", e0.elapsed_time(e1) / steps))
@@ -403,4 +504,4 @@ def format_table(rows: list[Row], op: str, n: int, title: str) -> str:
 
 def rows_json(rows: list[Row], op: str, n: int) -> list[dict]:
     return [{"bytes": r.nbytes, "algo": r.algo, "oop_us": round(r.oop_us, 3), "ip_us": round(r.ip_us, 3), "oop_busbw": round(r.bw(op, n)["oop_busbw"], 2),
-             "ip_busbw": round(r.bw(op, n)["ip_busbw"], 2), **({"e2e_us": round(r.e2e_us, 3)} if r.e2e_us > 0 else {})} for r in rows]
+             "ip_busbw": round(r.bw(op, n)["ip_busbw"], 2), **({"e2e_us": round(r.e2e_us, 3), "e2e_busbw": round(r.bw(op, n)["e2e_busbw"], 2)} if r.e2e_us > 0 else {})} for r in rows]

@@ -63,6 +63,12 @@ class NcclComm:
         L.ncclSend.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
         L.ncclRecv.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
         L.ncclCommDestroy.argtypes = [vp]
+        if hasattr(L, "ncclMemAlloc"):
+            L.ncclMemAlloc.argtypes = [C.POINTER(vp), C.c_size_t]
+            L.ncclMemFree.argtypes = [vp]
+        if hasattr(L, "ncclCommWindowRegister"):
+            L.ncclCommWindowRegister.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp), C.c_int]
+            L.ncclCommWindowDeregister.argtypes = [vp, vp]
         uid = NcclUniqueId()
         C.memmove(C.byref(uid), uid_bytes, 128)
         self.comm = vp()
@@ -127,6 +133,22 @@ class NcclComm:
             self._ck(self.lib.ncclSend(send + p * count * elem_size, count, dtype, p, self.comm, stream), "ncclSend")
             self._ck(self.lib.ncclRecv(recv + p * count * elem_size, count, dtype, p, self.comm, stream), "ncclRecv")
         self._ck(self.lib.ncclGroupEnd(), "ncclGroupEnd")
+
+    def sym_tensor(self, numel: int, dtype, itemsize: int, windows: list):
+        """A torch tensor on ncclMemAlloc memory registered as a symmetric window (NCCL_WIN_COLL_SYMMETRIC): NCCL 2.27+'s own
+        zero-copy / symmetric-kernel path, i.e. the NCCL counterpart of our arena tensors. A collective call (same order on every rank)."""
+        import torch
+        nbytes = (numel * itemsize + 4095) // 4096 * 4096
+        p = C.c_void_p()
+        self._ck(self.lib.ncclMemAlloc(C.byref(p), nbytes), "ncclMemAlloc")
+        win = C.c_void_p()
+        self._ck(self.lib.ncclCommWindowRegister(self.comm, p, nbytes, C.byref(win), 0x01), "ncclCommWindowRegister")
+        windows.append((win, p))
+
+        class _Arr:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Arr(p.value, nbytes), device="cuda").view(dtype)[:numel]
 
     def destroy(self) -> None:
         if self.comm:

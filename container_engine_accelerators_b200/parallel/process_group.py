@@ -37,15 +37,18 @@ _FAST_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
 class _Work(dist._Work):
     """Completed-at-enqueue work handle: the collective is already ordered on the caller's stream."""
 
-    def __init__(self, result, sync_on_wait: bool = False):
+    def __init__(self, result, sync_on_wait: bool = False, comm=None):
         super().__init__()
         self._result = result
         self._sync = sync_on_wait
+        self._comm = comm               # when set: wait() raises if the library's watchdog has fired (a peer never arrived)
         self._future: Optional[torch.futures.Future] = None
 
     def wait(self, timeout: Optional[timedelta] = None) -> bool:
         if self._sync and torch.cuda.is_available():
             torch.cuda.current_stream().synchronize()
+        if self._comm is not None:
+            self._comm.check_async_error()
         return True
 
     def is_completed(self) -> bool:
@@ -113,6 +116,10 @@ class B200CollProcessGroup(dist.ProcessGroup):
         self.fallback_calls = 0           # collectives that ran on the Gloo group
 
     # ------------------------------------------------------------------ plumbing
+    def _work(self, result, **kw) -> _Work:
+        # every handle checks the communicator's fault record in wait(): a watchdog hit on an earlier collective surfaces as an exception
+        return _Work(result, comm=self._comm, **kw)
+
     def getBackendName(self) -> str:
         return BACKEND_NAME
 
@@ -124,7 +131,11 @@ class B200CollProcessGroup(dist.ProcessGroup):
                 self._store.set("b200coll/key", uuid.uuid4().hex)
             key = self._store.get("b200coll/key").decode()
             arena = os.environ.get("B200COLL_ARENA_MB")
-            self._comm = coll.Comm.init_rank(self._rank, self._size, f"pg/{key}", arena_mb=int(arena) if arena else None)
+            # the process group's timeout (c10d default: 10 min) is the library's watchdog and rendezvous timeout too
+            timeout_ms = int(self._timeout.total_seconds() * 1000) if self._timeout is not None else None
+            if "B200COLL_TIMEOUT_MS" in os.environ:
+                timeout_ms = None             # an explicit environment setting wins (tests use a short one)
+            self._comm = coll.Comm.init_rank(self._rank, self._size, f"pg/{key}", arena_mb=int(arena) if arena else None, timeout_ms=timeout_ms)
         return self._comm
 
     @property
@@ -196,7 +207,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
                 for t in tensors:
                     self.comm.all_reduce(t, op=op)
             self.fast_calls += 1
-            return _Work(tensors)
+            return self._work(tensors)
         gopts = dist.AllreduceOptions()
         if opts is not None:
             gopts.reduceOp = opts.reduceOp
@@ -207,7 +218,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
         if avg:
             for t in tensors:
                 t.div_(self._size)
-        return _Work(tensors)
+        return self._work(tensors)
 
     def allreduce_coalesced(self, tensors, opts=None):
         return self.allreduce(tensors, opts)
@@ -224,14 +235,14 @@ class B200CollProcessGroup(dist.ProcessGroup):
             done.append(t)
         if len(done) == len(tensors):
             self.fast_calls += 1
-            return _Work(tensors)
+            return self._work(tensors)
         gopts = dist.BroadcastOptions()
         gopts.rootRank = root
         def run(host):
             for x in host:
                 self.gloo.broadcast([x], gopts).wait()
         self._via_gloo(tensors[len(done):], run)
-        return _Work(tensors)
+        return self._work(tensors)
 
     @staticmethod
     def _as_words(t: torch.Tensor) -> Optional[torch.Tensor]:
@@ -268,13 +279,13 @@ class B200CollProcessGroup(dist.ProcessGroup):
                 for t in tensors:
                     self.comm.reduce(t, root=root, op=op)
             self.fast_calls += 1
-            return _Work(tensors)
+            return self._work(tensors)
         gopts = dist.ReduceOptions()
         gopts.rootRank = root
         if opts is not None:
             gopts.reduceOp = opts.reduceOp
         self._via_gloo(tensors, lambda h: self.gloo.reduce(h, gopts))
-        return _Work(tensors)
+        return self._work(tensors)
 
     def _allgather_base(self, output, input, opts=None):
         if _fast(output) and _fast(input) and output.dtype == input.dtype and (input.numel() * input.element_size()) % 16 == 0 \
@@ -282,17 +293,17 @@ class B200CollProcessGroup(dist.ProcessGroup):
             with self._ordered(self):
                 self.comm.all_gather(input.view(-1), output.view(-1))
             self.fast_calls += 1
-            return _Work(output)
+            return self._work(output)
         words = self._word_views(output, input) if output.dtype == input.dtype and output.numel() == input.numel() * self._size \
             and (input.numel() * input.element_size()) % 16 == 0 else None
         if words is not None:                                   # integer / bool / fp8 payloads (token ids, masks): moved as raw words
             with self._ordered(self), self.comm.bit_exact():
                 self.comm.all_gather(words[1], words[0])
             self.fast_calls += 1
-            return _Work(output)
+            return self._work(output)
         chunks = list(output.view(-1).chunk(self._size))
         self.allgather([chunks], [input.view(-1)])
-        return _Work(output)
+        return self._work(output)
 
     def allgather(self, output_tensors, input_tensors, opts=None):
         for outs, inp in zip(output_tensors, input_tensors):
@@ -311,12 +322,12 @@ class B200CollProcessGroup(dist.ProcessGroup):
                 self.gloo.allgather([host_out], [host_in]).wait()
                 for o, h in zip(outs, host_out):
                     o.copy_(h)
-        return _Work(output_tensors)
+        return self._work(output_tensors)
 
     def allgather_into_tensor_coalesced(self, outputs, inputs, opts=None):
         for o, i in zip(outputs, inputs):
             self._allgather_base(o, i, opts)
-        return _Work(outputs)
+        return self._work(outputs)
 
     def _reduce_scatter_base(self, output, input, opts=None):
         op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
@@ -325,23 +336,23 @@ class B200CollProcessGroup(dist.ProcessGroup):
             with self._ordered(self):
                 self.comm.reduce_scatter(input.view(-1), output.view(-1), op=op)
             self.fast_calls += 1
-            return _Work(output)
+            return self._work(output)
         # generic: all-reduce a copy, keep my slice
         tmp = input.detach().clone().view(-1)
         self.allreduce([tmp], opts)
         output.view(-1).copy_(tmp.chunk(self._size)[self._rank])
-        return _Work(output)
+        return self._work(output)
 
     def reduce_scatter(self, output_tensors, input_tensors, opts=None):
         for out, ins in zip(output_tensors, input_tensors):
             flat = torch.cat([i.reshape(-1) for i in ins])
             self._reduce_scatter_base(out, flat, opts)
-        return _Work(output_tensors)
+        return self._work(output_tensors)
 
     def reduce_scatter_tensor_coalesced(self, outputs, inputs, opts=None):
         for o, i in zip(outputs, inputs):
             self._reduce_scatter_base(o, i, opts)
-        return _Work(outputs)
+        return self._work(outputs)
 
     def alltoall_base(self, output, input, output_split_sizes, input_split_sizes, opts=None):
         n = self._size
@@ -351,14 +362,14 @@ class B200CollProcessGroup(dist.ProcessGroup):
             with self._ordered(self):
                 self.comm.all_to_all(input.view(-1), output.view(-1))
             self.fast_calls += 1
-            return _Work(output)
+            return self._work(output)
         words = self._word_views(output, input) if even and output.dtype == input.dtype and output.data_ptr() != input.data_ptr() and input.numel() % n == 0 \
             and (input.numel() // n * input.element_size()) % 16 == 0 and output.numel() == input.numel() else None
         if words is not None:
             with self._ordered(self), self.comm.bit_exact():
                 self.comm.all_to_all(words[1], words[0])
             self.fast_calls += 1
-            return _Work(output)
+            return self._work(output)
         row_elems = input[0].numel() if input.dim() > 0 and input.shape[0] > 0 else 0
         if not even and row_elems and _fast(input) and output.is_cuda and output.is_contiguous() and output.dtype == input.dtype \
                 and (row_elems * input.element_size()) % 16 == 0:
@@ -369,7 +380,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
         host_out = torch.empty_like(output, device="cpu")
         self.gloo.alltoall_base(host_out, host_in, list(output_split_sizes or []), list(input_split_sizes or [])).wait()
         output.copy_(host_out)
-        return _Work(output)
+        return self._work(output)
 
     def _alltoallv_rows(self, output, input, in_splits, row_elems):
         """Expert-dispatch shaped all_to_all_single: rows of dim 0 with per-peer counts. The split matrix travels over Gloo (a few
@@ -392,7 +403,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
         got_rows = sum(matrix[s][self._rank] for s in range(n))
         output.view(-1)[:got_rows * row_elems].copy_(recv[:got_rows * row_elems])
         self.fast_calls += 1
-        return _Work(output)
+        return self._work(output)
 
     def alltoall(self, output_tensors, input_tensors, opts=None):
         same = len({(t.numel(), t.dtype) for t in list(output_tensors) + list(input_tensors)}) == 1
@@ -402,24 +413,24 @@ class B200CollProcessGroup(dist.ProcessGroup):
             self.alltoall_base(dst, src, [], [])
             for o, piece in zip(output_tensors, dst.chunk(self._size)):
                 o.copy_(piece.view_as(o))
-            return _Work(output_tensors)
+            return self._work(output_tensors)
         self.fallback_calls += 1
         host_in = [t.detach().cpu() if t.is_cuda else t for t in input_tensors]
         host_out = [torch.empty_like(t, device="cpu") for t in output_tensors]
         self.gloo.alltoall(host_out, host_in).wait()
         for o, h in zip(output_tensors, host_out):
             o.copy_(h)
-        return _Work(output_tensors)
+        return self._work(output_tensors)
 
     def barrier(self, opts=None):
         if torch.cuda.is_available() and self._comm is not None:
             with self._ordered(self):
                 self.comm.barrier()
             self.fast_calls += 1
-            return _Work(None, sync_on_wait=True)
+            return self._work(None, sync_on_wait=True)
         self.fallback_calls += 1
         self.gloo.barrier().wait()
-        return _Work(None)
+        return self._work(None)
 
     # ------------------------------------------------------------------ things only Gloo does
     def gather(self, output_tensors, input_tensors, opts=None):
@@ -440,7 +451,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
         for outs, hs in zip(output_tensors, host_out):
             for o, h in zip(outs, hs):
                 o.copy_(h)
-        return _Work(output_tensors)
+        return self._work(output_tensors)
 
     def scatter(self, output_tensors, input_tensors, opts=None):
         root = opts.rootRank if opts is not None else 0
@@ -458,7 +469,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
         self.gloo.scatter(host_out, host_in, gopts).wait()
         for o, h in zip(output_tensors, host_out):
             o.copy_(h)
-        return _Work(output_tensors)
+        return self._work(output_tensors)
 
     # ------------------------------------------------------------------ point to point
     # CUDA tensors go through the library's send / recv kernel (tags are ignored, as ProcessGroupNCCL does: messages of a pair match in
@@ -474,7 +485,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
             return _P2pWork(self, tensors)
         self.fallback_calls += 1
         self.gloo.send([t.detach().cpu() if t.is_cuda else t for t in tensors], dst_rank, tag).wait()
-        return _Work(tensors)
+        return self._work(tensors)
 
     def recv(self, tensors, src_rank, tag=0):
         if all(t.is_cuda for t in tensors):
@@ -482,7 +493,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
             self.fast_calls += 1
             return _P2pWork(self, tensors)
         self._via_gloo(tensors, lambda h: self.gloo.recv(h, src_rank, tag))
-        return _Work(tensors)
+        return self._work(tensors)
 
     def _flush_p2p(self) -> None:
         if self._pending:
@@ -493,14 +504,17 @@ class B200CollProcessGroup(dist.ProcessGroup):
         ops, self._pending = self._pending, []
         if not ops:
             return
-        comm, copy_out = self.comm, []
+        comm, copy_out, keep = self.comm, [], []
         direct = lambda t: t.is_contiguous() and t.data_ptr() % 16 == 0
         with coll.group():
             for kind, t, peer in ops:
                 if t.numel() == 0:
                     continue
                 if kind == "send":
-                    comm.send(t if direct(t) else t.contiguous().clone(), peer)      # clone(): a fresh allocation is aligned
+                    if not direct(t):
+                        t = t.contiguous().clone()      # clone(): a fresh allocation is aligned
+                        keep.append(t)                  # Comm.send only records the pointer; the kernel is launched when the group closes,
+                    comm.send(t, peer)                  # so the temporary must stay allocated (and un-reused) until then
                 elif direct(t):
                     comm.recv(t, peer)
                 else:
@@ -509,6 +523,7 @@ class B200CollProcessGroup(dist.ProcessGroup):
                     copy_out.append((t, tmp))
         for t, tmp in copy_out:
             t.copy_(tmp)
+        del keep                                        # the grouped kernel is enqueued: the caching allocator's stream ordering takes over
 
 
 def _create(store, rank, size, timeout):

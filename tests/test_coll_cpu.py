@@ -3,6 +3,8 @@ Unix-socket rendezvous (SCM_RIGHTS) exercised across real processes with memfd d
 import ctypes as C
 import multiprocessing as mp
 import os
+import time
+import struct
 import subprocess
 
 import pytest
@@ -96,6 +98,63 @@ def test_bootstrap_fd_exchange_across_processes(coll_lib, n):
     want = [f"payload-from-rank-{r}" for r in range(n)] + ["payload-from-rank-0"]
     for rank, rc, got in results:
         assert rc == 0 and got == want, (rank, rc, got)
+
+
+def _boot_rank_env(lib_path, name, rank, n, q, secret, timeout_ms):
+    if secret is not None:
+        os.environ["B200COLL_RENDEZVOUS_SECRET"] = secret
+    L = C.CDLL(lib_path)
+    fd = os.memfd_create(f"r{rank}")
+    out = (C.c_int * n)()
+    bc = C.c_int(-1)
+    rc = L.b200collBootstrapSelfTest(name.encode(), rank, n, fd, out, C.byref(bc), timeout_ms)
+    q.put((rank, rc, L.b200collBootstrapSelfTestRejected()))
+
+
+def test_bootstrap_drops_strangers_and_keeps_waiting(coll_lib):
+    """The rendezvous name can be guessed by other processes on the host (it is derived from MASTER_ADDR:PORT). A connection that does
+    not carry the job's token is dropped — it neither joins (it would receive every rank's arena descriptor) nor aborts the job."""
+    import socket
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    name = f"pytest-intruder-{os.getpid()}"
+    p0 = ctx.Process(target=_boot_rank_env, args=(coll_lib, name, 0, 2, q, "s3cret", 20000))
+    p0.start()
+    addr = b"\0b200coll-" + name.encode()
+    deadline = time.time() + 10
+    while True:                                   # the stranger: right socket, plausible rank numbers, no token
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        try:
+            s.connect(addr)
+            break
+        except OSError:
+            s.close()
+            assert time.time() < deadline
+            time.sleep(0.01)
+    s.sendall(struct.pack("iiQ", 1, 2, 0x1234))
+    time.sleep(0.2)
+    p1 = ctx.Process(target=_boot_rank_env, args=(coll_lib, name, 1, 2, q, "s3cret", 20000))
+    p1.start()
+    results = sorted(q.get(timeout=60) for _ in range(2))
+    p0.join(10); p1.join(10)
+    assert s.recv(16) == b""                      # closed by rank 0, nothing was sent to it
+    s.close()
+    assert results[0][:2] == (0, 0) and results[1][:2] == (1, 0), results
+    assert results[0][2] == 1                     # rank 0 counted exactly one rejected connection
+
+
+def test_bootstrap_rank_with_the_wrong_secret_cannot_join(coll_lib):
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    name = f"pytest-secret-{os.getpid()}"
+    procs = [ctx.Process(target=_boot_rank_env, args=(coll_lib, name, 0, 2, q, "right", 1500)),
+             ctx.Process(target=_boot_rank_env, args=(coll_lib, name, 1, 2, q, "wrong", 1500))]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=60) for _ in range(2))
+    for p in procs:
+        p.join(10)
+    assert results[0][1] != 0 and results[1][1] != 0, results      # rank 0 timed out waiting; rank 1 was dropped
 
 
 def test_bootstrap_times_out_when_a_rank_is_missing(coll_lib):

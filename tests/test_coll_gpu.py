@@ -354,7 +354,7 @@ def test_bench_contract_one_gpu(torch_cuda):
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
 
 
-@pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="pipelined host->device all-reduce has not run on hardware yet; set B200_RUN_UNVALIDATED=1")
+
 @pytest.mark.parametrize("group", [2], indirect=True)
 def test_all_reduce_from_host_pipelines_copy_and_collective(torch_cuda, group):
     torch = torch_cuda
@@ -372,6 +372,59 @@ def test_all_reduce_from_host_pipelines_copy_and_collective(torch_cuda, group):
             assert torch.equal(o.float(), want)
     for c in comms:
         c.check_async_error()
+
+
+@pytest.mark.parametrize("group", [2], indirect=True)
+def test_all_reduce_host_zero_copy_single_chunk_and_pipeline(torch_cuda, group, monkeypatch):
+    """b200collAllReduceHost (coll/src/hostpath.cu): pinned host in, pinned host out, one call. Three regimes — a single kernel that
+    reads and writes host memory over PCIe, copy/all-reduce/copy on the caller's stream, and the chunked three-leg pipeline (ragged last
+    chunk, staging rings reused and regrown across calls) — against an fp32 reference on data whose sums are not exact in bf16."""
+    torch = torch_cuda
+    from container_engine_accelerators_b200.parallel import harness
+    comms, streams = group
+    n = len(comms)
+    gen = harness._gen_expected(torch, "all_reduce", 0, n, 0, "cpu")
+    for count in (1 << 12, (1 << 19) + 24, (3 << 20) + 13, (5 << 20) + 13):
+        idx = torch.arange(count)
+        ins = [gen(r, idx).to(torch.bfloat16) for r in range(n)]
+        h_in = [comms[0].host_empty(count, torch.bfloat16), torch.empty(count, dtype=torch.bfloat16).pin_memory()]      # the library's NUMA-placed memory and plain torch pinned memory
+        h_out = [torch.empty(count, dtype=torch.bfloat16).pin_memory(), comms[1].host_empty(count, torch.bfloat16)]
+        for r in range(n):
+            h_in[r].copy_(ins[r]); h_out[r].fill_(77.0)
+        for rep in range(2):
+            for r, c in enumerate(comms):
+                c.all_reduce_host(h_in[r], h_out[r], stream=streams[r])
+            torch.cuda.synchronize()
+            want = sum(x.float() for x in ins)
+            for r in range(n):
+                assert harness.reduction_ok(torch, h_out[r].float(), want, torch.bfloat16, n), (count, rep, r)
+        comms[0].host_release(h_in[0]); comms[1].host_release(h_out[1])
+    st = comms[0].stats()
+    assert st["host_calls"] == 8 and st["host_zero_copy"] == 2 and st["host_pipelined"] == 4, st
+    for c in comms:
+        c.check_async_error()
+    node, cpus = comms[0].numa()
+    assert node >= -1 and isinstance(cpus, str)
+
+
+def test_all_reduce_host_one_rank_fused_epilogue(torch_cuda, coll_mod):
+    """One rank: the host step is copy-in | fused scale/cast kernel | copy-back; bf16 in, fp32 out, scale 0.5, in the pipelined regime."""
+    torch = torch_cuda
+    (c,) = coll_mod.Comm.init_all([0], arena_mb=64)
+    count = (6 << 20) + 5
+    h_in = c.host_empty(count, torch.bfloat16)
+    h_in.copy_(((torch.arange(count) % 251) - 125).to(torch.bfloat16))
+    h_out = c.host_empty(count, torch.float32)
+    c.all_reduce_host(h_in, h_out, scale=0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(h_out, h_in.float() * 0.5)
+    tiny_in, tiny_out = h_in[:1000], h_out[:1000]
+    tiny_out.zero_()
+    c.all_reduce_host(tiny_in, tiny_out, scale=2.0)                # zero-copy regime: the copy kernel reads and writes host memory
+    torch.cuda.synchronize()
+    assert torch.equal(tiny_out, tiny_in.float() * 2.0)
+    assert c.stats()["host_zero_copy"] == 1 and c.stats()["host_pipelined"] == 1
+    c.destroy()
 
 
 # ------------------------------------------------------------------------------------------------- NCCL-API shim
@@ -487,14 +540,12 @@ def test_nccl_api_shim_collectives(torch_cuda, coll_lib):
 
 
 # ------------------------------------------------------------------------------------------------- point to point
-_P2P_GATE = pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="the send/recv kernel has not run on hardware yet; set B200_RUN_UNVALIDATED=1")
 
 
 def _pattern(torch, nbytes, seed):
     return ((torch.arange(nbytes, device="cuda", dtype=torch.int64) * (2 * seed + 7) + seed * 31) % 251).to(torch.uint8)
 
 
-@_P2P_GATE
 @pytest.mark.parametrize("group", [2, 4], indirect=True)
 @pytest.mark.parametrize("nbytes", [16, 1003, (1 << 20) + 48, (3 << 20) + 5])
 @pytest.mark.parametrize("arena_recv", [True, False])
@@ -526,7 +577,6 @@ def test_send_recv_ring_step(torch_cuda, coll_mod, group, nbytes, arena_recv):
     assert (st["staged_calls"] > 0) == (not arena_recv)
 
 
-@_P2P_GATE
 @pytest.mark.parametrize("group", [2], indirect=True)
 def test_send_recv_pipeline_handover_and_self(torch_cuda, coll_mod, group):
     """Ungrouped calls: rank 0 sends, rank 1 receives (each blocks its own stream until the other arrives); then the reverse direction
@@ -554,7 +604,6 @@ def test_send_recv_pipeline_handover_and_self(torch_cuda, coll_mod, group):
         c.check_async_error()
 
 
-@_P2P_GATE
 @pytest.mark.parametrize("group", [4], indirect=True)
 def test_send_recv_irregular_group_and_graph_replay(torch_cuda, coll_mod, group):
     """One group with different sizes per pair and two messages for one pair (second one runs in a follow-up kernel); then a captured
@@ -608,7 +657,6 @@ def test_send_recv_irregular_group_and_graph_replay(torch_cuda, coll_mod, group)
         c.check_async_error()
 
 
-@_P2P_GATE
 def test_send_without_a_receiver_times_out(torch_cuda, coll_mod):
     torch = torch_cuda
     comms = coll_mod.Comm.init_all([0, 0], arena_mb=32, timeout_ms=300)
@@ -621,7 +669,6 @@ def test_send_without_a_receiver_times_out(torch_cuda, coll_mod):
         c.destroy()
 
 
-@_P2P_GATE
 def test_sendrecv_perf_virtual_ranks_zero_errors(torch_cuda, coll_lib):
     for op in ("sendrecv", "gather", "scatter", "hypercube"):                      # nccl-tests names; all of them are groups of send / recv
         exe = os.path.join(ROOT, "build", f"{op}_perf")
@@ -632,7 +679,6 @@ def test_sendrecv_perf_virtual_ranks_zero_errors(torch_cuda, coll_lib):
         assert f"op={op}" in r.stdout and "# Out of bounds values : 0 OK" in r.stdout, r.stdout
 
 
-@_P2P_GATE
 def test_nccl_api_shim_send_recv(torch_cuda, coll_lib):
     """ncclSend / ncclRecv through the shim for shapes that are not the all-to-all pattern: a lone pair outside any group (uint8, odd
     count) and a grouped exchange of int64 with different counts per direction, issued for both communicators inside one group."""
@@ -731,7 +777,7 @@ def _split_rank(rank, world, key, q):
         q.put((rank, traceback.format_exc() + repr(e)))
 
 
-@pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="CommSplit has not run on hardware yet; set B200_RUN_UNVALIDATED=1")
+
 def test_comm_split_four_processes(torch_cuda, coll_mod):
     """ncclCommSplit semantics across four processes (sharing cuda:0 on a one-GPU box): colours, key ordering, a rank without a colour,
     and the parent staying usable."""

@@ -246,7 +246,7 @@ def _gpu_pair(rank, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("B200_RUN_UNVALIDATED") != "1", reason="process-group CUDA path has not run on hardware yet (round 1 GPU budget spent); set B200_RUN_UNVALIDATED=1")
+
 def test_cuda_fast_paths_two_ranks():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -266,6 +266,9 @@ class _DeviceLike(torch.Tensor):
 class _RecordingComm:
     def __init__(self):
         self.calls, self.in_group = [], 0
+
+    def check_async_error(self):
+        pass
 
     def send(self, t, peer):
         self.calls.append(("send", peer, t.numel() * t.element_size(), t.is_contiguous() and t.data_ptr() % 16 == 0, self.in_group))

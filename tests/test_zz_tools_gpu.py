@@ -33,7 +33,7 @@ def test_nvls_probe_describes_the_box():
     assert "driver_version" in r.stdout and "multicast=" in r.stdout and "sms=148" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.skipif(os.environ.get("B200_RUN_FAULT_INJECTION") != "1", reason="raises a real Xid on this GPU; set B200_RUN_FAULT_INJECTION=1")
+
 @pytest.mark.parametrize("mode", ["oob-store", "oob-load", "trap"])
 def test_xid_inject_faults_its_own_context_only(mode):
     """Reference demo/gpu-error/illegal-memory-access/vectorAdd.cu:28-70: the out-of-bounds store must be reported by the driver;
