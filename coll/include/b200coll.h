@@ -113,6 +113,7 @@ typedef struct {
   uint64_t p2p_sends, p2p_recvs, p2p_bytes;   /* point-to-point operations and the bytes they moved (sent + received) */
   uint64_t host_calls, host_bytes;            /* b200collAllReduceHost calls and the input bytes they carried */
   uint64_t host_zero_copy, host_pipelined;    /* ... of which: one-kernel zero-copy calls / chunked three-leg pipelines */
+  uint64_t bulk_launches;                     /* kernels that moved their payload with the copy engine (cp.async.bulk ring) */
 } b200collStats;
 
 /* Device-written watchdog record (host-pinned). code != 0 means the comm is poisoned. */

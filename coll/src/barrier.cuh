@@ -1,5 +1,5 @@
-// Epoch barrier between the namesake CTAs of all ranks, the launch-sequence bookkeeping, and (B200COLL_VARIANT_MCBAR) the one-instruction
-// multicast flavour. Included by device.cuh after the flag primitives; also compiled for the HOST by coll/tests/barrier_emu.cc (CTAs as
+// Epoch barrier between the namesake CTAs of all ranks, the launch-sequence bookkeeping, and the one-instruction multicast flavour
+// (CommDev::mcbar). Included by device.cuh after the flag primitives; also compiled for the HOST by coll/tests/barrier_emu.cc (CTAs as
 // thread groups, arenas in host memory, ThreadSanitizer) — keep this file to those primitives, layout.h and plain C++.
 #pragma once
 
@@ -21,8 +21,7 @@ __device__ __forceinline__ bool last_block_ticket(const CommDev& c) {
 // Block b of every rank meets block b of every other rank. RELEASE=true publishes this block's prior
 // writes (local or peer) system-wide before signalling; the wait side is always an acquire.
 
-#ifdef B200COLL_VARIANT_MCBAR
-// A/B candidate (make VARIANT=mcbar -> lib/libb200coll_mcbar.so): with NVLS, a barrier is ONE multimem.red on a multicast
+// Multicast barrier (CommDev::mcbar, B200COLL_MCBAR=0 turns it off): with NVLS, a barrier is ONE multimem.red on a multicast
 // counter (the switch adds 1 to block b's counter on every rank) and ONE polled local word, instead of N remote stores + N polled flags.
 // Counters grow by nranks per barrier and are never reset; how many barriers block b has taken is kept next to them (only block b of
 // this rank touches that word, kernels of a communicator are stream-ordered). Both arrays live in the zero-initialised part of the flag
@@ -56,15 +55,12 @@ __device__ __forceinline__ int barrier_blocks_mc(const CommDev& c, uint32_t op) 
   }
   return __syncthreads_or(bad) ? 0 : 1;
 }
-#endif
 
 // Returns false when the watchdog fired (a peer never arrived): the caller must not touch peer data and returns at once — the
 // communicator is poisoned, the host reports b200collRemoteError, and nothing unsynchronised is read or written.
 template <bool RELEASE>
 __device__ __forceinline__ bool barrier_blocks(const CommDev& c, uint32_t epoch, uint32_t op) {
-#ifdef B200COLL_VARIANT_MCBAR
-  { const int r = barrier_blocks_mc<RELEASE>(c, op); if (r >= 0) return r != 0; }
-#endif
+  if (c.mcbar) { const int r = barrier_blocks_mc<RELEASE>(c, op); if (r >= 0) return r != 0; }
   __syncthreads();
   const int t = threadIdx.x;
   int bad = 0;

@@ -57,14 +57,26 @@ static b200collResult_t dispatch_types(b200collDataType_t in, b200collDataType_t
 struct Grid { int blocks, threads; };
 
 // Every kernel goes through cudaLaunchKernelEx so that back-to-back collectives can use programmatic dependent launch
-// (B200COLL_PDL=1): the next kernel's launch latency overlaps the current kernel's execution; each kernel starts with
+// (on by default, B200COLL_PDL=0 disables): the next kernel's launch latency overlaps the current kernel's execution; each kernel starts with
 // griddepcontrol.launch_dependents + griddepcontrol.wait, so it still observes its predecessor's completed memory.
 // Never with virtual ranks (several communicators on one GPU): a pre-launched dependent grid parks its CTAs on SMs
 // that another rank's current kernel still needs, and ranks that spin on each other then deadlock (seen at 1 MiB with
 // 4 ranks on one B200). With one rank per GPU every CTA of kernel i is resident before kernel i+1 may start.
 static bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("B200COLL_PDL"); return e && *e && *e != '0'; }();
+  static const bool on = [] { const char* e = getenv("B200COLL_PDL"); return !(e && *e == '0'); }();      // on unless B200COLL_PDL=0
   return on && g_loopback_comms.load(std::memory_order_relaxed) == 0;
+}
+template <typename... KArgs, typename... Args>
+static void launch_k_smem(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr;
+  if (pdl_enabled()) {
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+  }
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t st, Args&&... args) {
@@ -128,9 +140,53 @@ static void account(b200collComm* c, b200collOp_t op, size_t bytes, b200collAlgo
   }
 }
 
+// ------------------------------------------------------------------------------------------------ copy-engine path (k_bulk)
+// B200COLL_BULK=0 turns it off (A/B against the LDG/STG kernels); B200COLL_BULK_MIN_KB moves the threshold (default 1024: below it the
+// ring's set-up costs more than it saves). Only for the identity epilogue and sizes that are multiples of 16 bytes.
+static bool bulk_enabled() {
+  static const bool on = [] { const char* e = getenv("B200COLL_BULK"); return !(e && *e == '0'); }();
+  return on;
+}
+static size_t bulk_min_bytes() {
+  static const size_t v = [] { const char* e = getenv("B200COLL_BULK_MIN_KB"); return (size_t)(e && *e ? atol(e) : 1024) << 10; }();
+  return v;
+}
+static b200collResult_t launch_bulk(b200collComm* c, BulkArgs& a, bool sync, b200collOp_t op, cudaStream_t st) {
+  static const bool attr_set = [] {
+    cudaFuncSetAttribute(k_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes);
+    cudaFuncSetAttribute(k_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes);
+    return true;
+  }();
+  (void)attr_set;
+  a.chunk_prefix[0] = 0;
+  for (int g = 0; g < a.nseg; g++) a.chunk_prefix[g + 1] = a.chunk_prefix[g] + (a.bytes[g] + kBulkChunk - 1) / kBulkChunk;
+  for (int g = a.nseg + 1; g <= kMaxRanks; g++) a.chunk_prefix[g] = a.chunk_prefix[a.nseg];
+  static const int env_ctas = [] { const char* e = getenv("B200COLL_BULK_CTAS"); return e ? atoi(e) : 0; }();
+  // 3 CTAs of 64 KiB shared memory fit on an SM; peers: stay within the collective cap so that every rank's grid is co-resident
+  int cap = sync ? std::min(c->max_ctas, 2 * std::max(1, c->sm_count)) : 3 * std::max(1, c->sm_count);
+  if (env_ctas > 0) cap = std::min(env_ctas, sync ? c->max_ctas : env_ctas);
+  // every rank must launch the same grid (block b meets block b in the barriers): size it from what all ranks know — for rooted and
+  // personalised ops the caller passes the symmetric chunk count in chunk_prefix[kMaxRanks] ... the largest segment list is the same on
+  // every rank for all-gather / all-to-all (equal counts); broadcast and all-to-all-v pass `grid_hint`.
+  const unsigned long long chunks = std::max<unsigned long long>(a.chunk_prefix[a.nseg], c->bulk_grid_hint);
+  c->bulk_grid_hint = 0;
+  const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(chunks, (unsigned long long)cap));
+  if (sync) launch_k_smem(k_bulk<true>, blocks, kBulkThreads, kBulkSmemBytes, st, c->dev, a, (uint32_t)op);
+  else launch_k_smem(k_bulk<false>, blocks, kBulkThreads, kBulkSmemBytes, st, c->dev, a, (uint32_t)op);
+  LAUNCH_CHECK(c);
+  c->stats.bulk_launches++;
+  return b200collSuccess;
+}
+
 // ------------------------------------------------------------------------------------------------ nranks == 1
 static b200collResult_t copy_scale(b200collComm* c, const void* send, void* recv, size_t count, const b200collEpilogue* ep, float scale, cudaStream_t st) {
   if (send == recv && ep->in_dtype == ep->out_dtype && scale == 1.0f) return b200collSuccess;
+  const size_t nbytes = count * b200collTypeSize(ep->in_dtype);
+  if (bulk_enabled() && ep->in_dtype == ep->out_dtype && scale == 1.0f && nbytes >= bulk_min_bytes() && nbytes % 16 == 0 && aligned(recv, 16)) {
+    BulkArgs a = {};
+    a.nseg = 1; a.src[0] = static_cast<const char*>(send); a.bytes[0] = nbytes; a.dst_local = static_cast<char*>(recv);
+    return launch_bulk(c, a, false, b200collOpAllReduce, st);
+  }
   return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
     // streaming copy: no peers to wait for, so oversubscribe the chip (8 CTAs of 256 threads per SM) instead of the collective cap
@@ -453,16 +509,13 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
       return b200collSuccess;
     });
   };
-#ifdef B200COLL_VARIANT_BULK
-  if (sym_out && identity && bytes >= (1u << 20) && bytes % 16 == 0 && algo != b200collAlgoNvls) {     // A/B candidate: copy-engine push (kernels.cuh k_ag_bulk)
+  if (bulk_enabled() && sym_out && identity && bytes >= bulk_min_bytes() && bytes % 16 == 0 && algo != b200collAlgoNvls) {     // copy-engine push (kernels.cuh k_bulk)
     account(c, b200collOpAllGather, bytes, algo);
-    const size_t chunks = (bytes + kBulkChunk - 1) / kBulkChunk;
-    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(chunks, (size_t)std::min(c->max_ctas, 2 * std::max(1, c->sm_count))));
-    launch_k(k_ag_bulk, blocks, 128, st, c->dev, static_cast<const char*>(send), arena_off(c, recv), bytes, (uint32_t)b200collOpAllGather);
-    LAUNCH_CHECK(c);
-    return b200collSuccess;
+    BulkArgs a = {};
+    a.nseg = 1; a.src[0] = static_cast<const char*>(send); a.bytes[0] = bytes;
+    a.dst_off[0] = arena_off(c, recv) + (size_t)c->rank * bytes; a.dst_mask[0] = (1u << c->nranks) - 1;
+    return launch_bulk(c, a, true, b200collOpAllGather, st);
   }
-#endif
   if (sym_out) return push(send, recv, sendcount);
   // staged: gather chunks into staging half 1 laid out [nranks][chunk], then scatter locally into recv
   c->stats.staged_calls++;
@@ -523,11 +576,14 @@ b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recv
   return b200collSuccess;
 }
 
-static b200collResult_t a2av_launch(b200collComm* c, const void* send, void* recv_sym, const A2AvArgs& a, const b200collEpilogue* ep, cudaStream_t st) {
+// symmetric: every rank moves the same amount, so the grid may follow the work. Otherwise (all-to-all-v: each rank only knows its own
+// rows) every rank launches the full P2P shape — block b of one rank meets block b of every other rank in the barriers, so the grids
+// must agree, and CTAs without work only take the two barriers.
+static b200collResult_t a2av_launch(b200collComm* c, const void* send, void* recv_sym, const A2AvArgs& a, const b200collEpilogue* ep, cudaStream_t st, bool symmetric) {
   const int identity = (ep->in_dtype == ep->out_dtype && ep->scale == 1.0f) ? 1 : 0;
   return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
     using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-    Grid g = pick_grid(c, kShapeP2p, (size_t)a.prefix[c->nranks] + 1, 4);
+    Grid g = pick_grid(c, kShapeP2p, symmetric ? (size_t)a.prefix[c->nranks] + 1 : ~(size_t)0 >> 8, 4);
     launch_k(k_a2av_push<InT, OutT>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(send), arena_off(c, recv_sym), a, ep->scale, identity, b200collOpAllToAll);
     LAUNCH_CHECK(c);
     return b200collSuccess;
@@ -567,8 +623,19 @@ b200collResult_t b200collAllToAll(const void* send, void* recv, size_t count, co
     for (int p = 0; p < c->nranks; p++) { a.src_vec[p] = (unsigned long long)p * s_stride_elems / E; a.dst_vec[p] = (unsigned long long)c->rank * n / E; nv[p] = n / E; }
     a2av_prefix(c, nv, &a);
     account(c, b200collOpAllToAll, n * is * c->nranks, algo);
-    return a2av_launch(c, s, r_sym, a, ep, st);
+    return a2av_launch(c, s, r_sym, a, ep, st, true);
   };
+  if (bulk_enabled() && sym_out && is == os && ep->in_dtype == ep->out_dtype && ep->scale == 1.0f && bytes * c->nranks >= bulk_min_bytes() && bytes % 16 == 0) {
+    account(c, b200collOpAllToAll, bytes * c->nranks, algo);
+    BulkArgs a = {};
+    a.nseg = c->nranks;
+    for (int j = 0; j < c->nranks; j++) {             // staggered: segment j goes to rank+1+j, the last one is my own block
+      int p = c->rank + 1 + j; if (p >= c->nranks) p -= c->nranks;
+      a.src[j] = static_cast<const char*>(send) + (size_t)p * bytes; a.bytes[j] = bytes;
+      a.dst_off[j] = arena_off(c, recv) + (size_t)c->rank * bytes; a.dst_mask[j] = 1u << p;
+    }
+    return launch_bulk(c, a, true, b200collOpAllToAll, st);
+  }
   if (sym_out) return run(send, count, recv, count);
   c->stats.staged_calls++;
   const size_t chunk = (kStageHalfBytes / os / c->nranks) / 64 * 64;
@@ -615,7 +682,7 @@ b200collResult_t b200collAllToAllv(const void* send, void* recv, size_t row_elem
   }
   a2av_prefix(c, nv, &a);
   account(c, b200collOpAllToAll, total_bytes, b200collAlgoTwoShot);
-  return a2av_launch(c, send, recv, a, ep, st);
+  return a2av_launch(c, send, recv, a, ep, st, false);
 }
 
 b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, const b200collEpilogue* ep, int root, b200collComm_t c, b200collStream_t stream) {
@@ -643,6 +710,13 @@ b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, c
       return b200collSuccess;
     });
   };
+  if (bulk_enabled() && algo == b200collAlgoTwoShot && identity && count * is >= bulk_min_bytes() && (count * is) % 16 == 0 && b200collIsSymmetric(c, recv, count * os)) {
+    account(c, b200collOpBroadcast, count * is, algo);
+    BulkArgs a = {};
+    if (c->rank == root) { a.nseg = 1; a.src[0] = static_cast<const char*>(send); a.bytes[0] = count * is; a.dst_off[0] = arena_off(c, recv); a.dst_mask[0] = (1u << c->nranks) - 1; }
+    c->bulk_grid_hint = (count * is + kBulkChunk - 1) / kBulkChunk;      // non-root ranks carry no segment but must launch the root's grid
+    return launch_bulk(c, a, true, b200collOpBroadcast, st);
+  }
   if (b200collIsSymmetric(c, recv, count * os)) return push(send, recv, count);
   // staged: the root pushes a chunk into everybody's staging half 1, each rank copies it out locally
   c->stats.staged_calls++;

@@ -205,6 +205,7 @@ static void finalize_comm(b200collComm* c) {
   d.mc = c->nvls ? reinterpret_cast<char*>(c->mc_va) : nullptr;
   d.state = c->state_dev;
   d.fault = c->fault_dev;
+  d.mcbar = (c->nvls && env_long("B200COLL_MCBAR", 1) != 0) ? 1 : 0;
   d.timeout_ns = c->cfg.timeout_ms == 0 ? ~0ull : (unsigned long long)c->cfg.timeout_ms * 1000000ull;   // 0 = no watchdog
   c->free_list.clear();
   c->free_list.push_back({kOffHeap, c->arena.total - kOffHeap});

@@ -97,6 +97,7 @@ struct b200collComm {
   uint32_t split_seq = 0;               // CommSplit calls so far (a collective call, so the same on every rank)
   size_t p2p_window = 0;                // staged receives: bytes per staging window; 0 = an equal share of the staging area
   uint32_t stats_tick = 0;              // collective calls since init; the counters page is refreshed every 256
+  unsigned long long bulk_grid_hint = 0; // chunks the largest rank of a rooted / personalised bulk launch has (set by the caller, consumed by launch_bulk)
   int numa_node = -1;                   // of this rank's GPU (sysfs), -1 unknown
   std::string local_cpulist;            // GPU-local CPUs as sysfs prints them
   cpu_set_t affinity_saved;             // the calling thread's mask before CommInitRank narrowed it

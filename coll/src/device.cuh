@@ -17,13 +17,14 @@
 
 namespace b200coll {
 
-// How kernels receive the communicator. Default: by value (the compiler copies the 104-byte struct to the stack because peer[] is
-// indexed with a runtime value). -DB200COLL_VARIANT_GRIDCONST (make VARIANT=gridconst -> lib/libb200coll_gridconst.so) declares it
-// __grid_constant__ so the table is indexed in the constant bank instead; an A/B candidate, not the shipped build.
-#ifdef B200COLL_VARIANT_GRIDCONST
-#define COMM_PARAM const __grid_constant__ CommDev c
-#else
+// How kernels receive the communicator: as a __grid_constant__ parameter, so that peer[t] with a run-time t is an indexed load from
+// the constant bank (LDC c[0x0][R+0x380]). Passed by value the compiler copies the 104-byte struct to the stack of every thread
+// (STACK:104 in cuobjdump --dump-resource-usage) and every lookup becomes a local-memory load; -DB200COLL_VARIANT_BYVALUE
+// (make VARIANT=byvalue -> lib/libb200coll_byvalue.so) keeps that form for A/B runs.
+#ifdef B200COLL_VARIANT_BYVALUE
 #define COMM_PARAM CommDev c
+#else
+#define COMM_PARAM const __grid_constant__ CommDev c
 #endif
 
 // ---------------------------------------------------------------- misc

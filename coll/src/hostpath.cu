@@ -202,9 +202,9 @@ b200collResult_t b200collHostFree(b200collComm_t c, void* ptr) {
 // host_recv = cast(scale * sum over ranks of host_send). Both buffers are pinned host memory (HostAlloc, cudaHostAlloc or
 // cudaHostRegister); host_recv == host_send is allowed for equal-size types. Asynchronous on `stream`: the result is in host_recv
 // when the stream reaches the point after this call. The same call (count, types) on every rank.
-//   <= B200COLL_HOST_ZEROCOPY_KB (default 128): one kernel, reads and writes host memory directly (no copy engine, no staging)
-//   <= B200COLL_HOST_PIPELINE_KB (default 2048): copy in, all-reduce, copy out on `stream`
-//   larger: chunks of B200COLL_HOST_CHUNK_KB (default: total/8 clamped to [1 MiB, 8 MiB]) through two staging pairs, three legs overlapped
+//   <= B200COLL_HOST_ZEROCOPY_KB (default 4096) and within reach of a Lamport kernel: one kernel, reads and writes host memory directly
+//   <  B200COLL_HOST_PIPELINE_KB (default 8192): copy in, all-reduce, copy out on `stream`
+//   larger: chunks of B200COLL_HOST_CHUNK_KB (default: total/6 clamped to [4 MiB, 16 MiB]) through two staging pairs, three legs overlapped
 b200collResult_t b200collAllReduceHost(const void* host_send, void* host_recv, size_t count, const b200collEpilogue* ep, b200collRedOp_t rop,
                                        b200collComm_t c, b200collStream_t stream) {
   if (!c || !host_send || !host_recv || !ep) { set_last_error("null argument"); return b200collInvalidArgument; }
@@ -214,21 +214,28 @@ b200collResult_t b200collAllReduceHost(const void* host_send, void* host_recv, s
   if (host_send == host_recv && is != os) { set_last_error("in-place host all-reduce needs in_dtype and out_dtype of equal size"); return b200collInvalidArgument; }
   cudaStream_t main = static_cast<cudaStream_t>(stream);
   const size_t bytes = count * is;
-  static const size_t zc_max = (size_t)env_l("B200COLL_HOST_ZEROCOPY_KB", 128) << 10;
-  static const size_t pipe_min = (size_t)env_l("B200COLL_HOST_PIPELINE_KB", 2048) << 10;
+  // Measured on one B200 (profiles/host_path.md): the copy engines move 55.6 GB/s in and 57.3 GB/s out, 49 GB/s each way when both run;
+  // a chunk boundary costs ~20 us of bubble (event hand-over between three streams), so the pipeline wants 4-8 big chunks; below 8 MiB
+  // there is nothing to win with DMA, but a kernel that reads and writes pinned host memory itself overlaps both directions by nature
+  // and needs one launch instead of copy + kernel + copy.
+  static const size_t zc_max = (size_t)env_l("B200COLL_HOST_ZEROCOPY_KB", 4096) << 10;
+  static const size_t pipe_min = (size_t)env_l("B200COLL_HOST_PIPELINE_KB", 8192) << 10;
   static const size_t chunk_env = (size_t)env_l("B200COLL_HOST_CHUNK_KB", 0) << 10;
   c->stats.host_calls++; c->stats.host_bytes += bytes;
 
-  if (bytes <= zc_max && bytes <= kLLOneShotMaxBytes) {
+  // One kernel, no copy engine: nranks > 1 takes a Lamport kernel (they only ever read `in` and write `out` locally, so both may be
+  // host memory): one-shot up to 512 KiB, two-shot up to 512 KiB x nranks when the types have equal size. One rank: the copy kernel.
+  const bool zc_feasible = c->nranks == 1 || bytes <= kLLOneShotMaxBytes || (is == os && bytes <= kLLOneShotMaxBytes * (size_t)c->nranks);
+  if (bytes <= zc_max && zc_feasible) {
     void *din = nullptr, *dout = nullptr;
     if (cudaHostGetDevicePointer(&din, const_cast<void*>(host_send), 0) == cudaSuccess && cudaHostGetDevicePointer(&dout, host_recv, 0) == cudaSuccess) {
       c->stats.host_zero_copy++;
-      return b200collAllReduce(din, dout, count, ep, rop, c, stream);      // nranks > 1: Lamport kernel (only ever reads `in` locally); 1 rank: the copy kernel
+      return b200collAllReduce(din, dout, count, ep, rop, c, stream);
     }
     (void)cudaGetLastError();                                              // not mapped: fall through to the copy engines
   }
-  size_t chunk = chunk_env ? chunk_env : std::min<size_t>(8u << 20, std::max<size_t>(1u << 20, bytes / 8));
-  if (bytes <= pipe_min) chunk = bytes;
+  size_t chunk = chunk_env ? chunk_env : std::min<size_t>(16u << 20, std::max<size_t>(4u << 20, bytes / 6));
+  if (bytes < pipe_min) chunk = bytes;
   chunk = (chunk + 1023) / 1024 * 1024;
   const size_t chunk_elems = chunk / is;
   const size_t out_chunk_bytes = chunk_elems * os;

@@ -11,6 +11,7 @@
 //   k_a2av_push       all-to-all(v)                per-peer row ranges, flattened for load balance
 //   k_bcast           broadcast                    root pushes (P2P or one multimem.st per vector); the others only synchronise
 //   k_reduce_root     reduce                       the root pulls (or multimem.ld_reduce) the whole buffer; the others only synchronise
+//   k_bulk            identity epilogue, >= 1 MiB   all-gather / broadcast / all-to-all(v) / one-rank copy through the copy engine (cp.async.bulk ring)
 //   k_p2p             send / recv (grouped)        receiver posts where to write, sender pushes over NVLink and signals; no all-rank barrier
 //   k_barrier
 #pragma once
@@ -680,59 +681,105 @@ __global__ void __launch_bounds__(kThreads) k_reduce_root(COMM_PARAM, size_t in_
   if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
 }
 
-#ifdef B200COLL_VARIANT_BULK
 // ------------------------------------------------------------------------------------------------
-// A/B candidate (make VARIANT=bulk -> lib/libb200coll_bulk.so): all-gather push with the copy engine of the SM instead of
-// LDG/STG. One elected thread per CTA streams its share of the local buffer through a small shared-memory ring:
-//   cp.async.bulk global -> shared (completion on an mbarrier), then one cp.async.bulk shared -> peer global per rank, committed as a
-//   bulk group; a ring slot is reused once the group that read it has finished reading (cp.async.bulk.wait_group.read).
-// Loads of chunk k+1 overlap the stores of chunk k; no registers carry data, so a CTA is one warp's worth of control code.
-// Identity epilogue only (same dtype, scale 1): the bytes are never looked at.
+// Copy-engine data movement (TMA bulk copies): all-gather, broadcast, all-to-all(v) and the one-rank copy when the epilogue is the
+// identity (same dtype, scale 1) — the bytes are never looked at, so no register ever holds them. One elected thread per CTA drives a
+// shared-memory ring:   cp.async.bulk global -> shared (completion counted on an mbarrier)      [SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64]
+//                       cp.async.bulk shared -> (peer) global, one per destination, one bulk group per chunk            [UBLKCP.G.S]
+// Loads run kStages-1 chunks ahead of the stores; a slot is reloaded once the group that stored from it has finished READING it
+// (cp.async.bulk.wait_group.read), so up to (kStages-1) loads and 2 store groups per CTA are in flight — enough outstanding bytes per SM
+// for HBM (one rank) and for NVLink (peers) without spending registers or issue slots on the payload.
+// The work is a list of segments (source range -> set of destinations), flattened into chunks and dealt round-robin to the CTAs:
+//   one-rank copy   1 segment, local destination            all-gather   1 segment -> every rank's out[rank]
+//   broadcast       root: 1 segment -> every rank; others: none (barriers only)
+//   all-to-all(v)   one segment per peer (staggered start so that all ranks do not hit the same peer at once)
+struct BulkArgs {
+  int nseg;
+  const char* src[kMaxRanks];
+  unsigned long long bytes[kMaxRanks];            // multiple of 16
+  unsigned long long chunk_prefix[kMaxRanks + 1]; // chunks before segment g
+  unsigned long long dst_off[kMaxRanks];          // arena offset at the destination rank(s)
+  unsigned dst_mask[kMaxRanks];                   // bit r: copy to rank r (peer[r] + dst_off)
+  char* dst_local;                                // one-rank copy: plain local destination instead of arena destinations (nseg == 1)
+};
 constexpr int kBulkStages = 4;
-constexpr uint32_t kBulkChunk = 8192;
+constexpr uint32_t kBulkChunk = 16384;
+constexpr int kBulkThreads = 32;
+constexpr size_t kBulkSmemBytes = (size_t)kBulkStages * kBulkChunk;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(128) k_ag_bulk(COMM_PARAM, const char* __restrict__ in, size_t out_off, size_t bytes, uint32_t op) {
+
+template <bool SYNC>
+__global__ void __launch_bounds__(kBulkThreads) k_bulk(COMM_PARAM, const __grid_constant__ BulkArgs a, uint32_t op) {
   pdl_prologue();
-  __shared__ __align__(128) char ring[kBulkStages][kBulkChunk];
+  extern __shared__ __align__(128) char ring[];                  // [kBulkStages][kBulkChunk]
   __shared__ __align__(8) unsigned long long full[kBulkStages];
-  const uint32_t s = load_seq(c, kSeqBarrier);
-  if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
-  if (threadIdx.x == 0) {
+  uint32_t s = 0;
+  if (SYNC) {
+    s = load_seq(c, kSeqBarrier);
+    if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;        // every rank is done with the previous contents of the destination
+  }
+  if (threadIdx.x == 0 && a.nseg > 0) {
     for (int i = 0; i < kBulkStages; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const size_t dst0 = out_off + (size_t)c.rank * bytes;
-    const size_t nchunks = (bytes + kBulkChunk - 1) / kBulkChunk;
-    uint32_t it = 0;
-    for (size_t i = blockIdx.x; i < nchunks; i += gridDim.x, it++) {
-      const int stage = (int)(it % kBulkStages);
-      const uint32_t parity = (it / kBulkStages) & 1u;
-      if (it >= (uint32_t)kBulkStages) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkStages - 1) : "memory");   // the stores that read this slot are done reading
-      const size_t off = i * (size_t)kBulkChunk;
-      const uint32_t n = (uint32_t)(bytes - off < kBulkChunk ? bytes - off : kBulkChunk);
-      const uint32_t bar = smem_u32(&full[stage]), dst_s = smem_u32(&ring[stage][0]);
+    const unsigned long long nchunks = a.chunk_prefix[a.nseg];
+    const unsigned long long mine = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks blockIdx.x, +gridDim.x, ...
+    auto locate = [&](unsigned long long k, int* seg, unsigned long long* off, uint32_t* n) {
+      const unsigned long long g = blockIdx.x + k * gridDim.x;
+      int sgi = 0;
+#pragma unroll
+      for (int q = 1; q < kMaxRanks; q++) if (q < a.nseg && g >= a.chunk_prefix[q]) sgi = q;
+      const unsigned long long o = (g - a.chunk_prefix[sgi]) * kBulkChunk;
+      *seg = sgi; *off = o;
+      *n = (uint32_t)(a.bytes[sgi] - o < kBulkChunk ? a.bytes[sgi] - o : kBulkChunk);
+    };
+    auto load = [&](unsigned long long k) {
+      int seg; unsigned long long off; uint32_t n;
+      locate(k, &seg, &off, &n);
+      const int slot = (int)(k % kBulkStages);
+      const uint32_t bar = smem_u32(&full[slot]), dst_s = smem_u32(ring + (size_t)slot * kBulkChunk);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(in + off), "r"(n), "r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(a.src[seg] + off), "r"(n), "r"(bar) : "memory");
+    };
+    const unsigned long long ahead = kBulkStages - 1;
+    for (unsigned long long k = 0; k < mine && k < ahead; k++) load(k);
+    bool dead = false;
+    for (unsigned long long k = 0; k < mine && !dead; k++) {
+      const int slot = (int)(k % kBulkStages);
+      const uint32_t parity = (uint32_t)((k / kBulkStages) & 1u);
+      const uint32_t bar = smem_u32(&full[slot]), src_s = smem_u32(ring + (size_t)slot * kBulkChunk);
       uint32_t done = 0, spins = 0;
       const unsigned long long t0 = globaltimer_ns();
       while (!done) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && ((++spins) & 0x3FF) == 0 && globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 5, (uint32_t)c.rank, n, stage, op); break; }   // the copy engine never delivered: report, do not hang
+        if (!done && ((++spins) & 0x3FF) == 0 && globaltimer_ns() - t0 > c.timeout_ns) { record_fault(c, 5, (uint32_t)c.rank, (uint32_t)k, slot, op); dead = true; break; }   // the copy engine never delivered: report, do not hang
       }
-      if (!done) break;
+      if (dead) break;
+      int seg; unsigned long long off; uint32_t n;
+      locate(k, &seg, &off, &n);
+      if (a.dst_local) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.dst_local + off), "r"(src_s), "r"(n) : "memory");
+      } else {
+        const unsigned mask = a.dst_mask[seg];
 #pragma unroll
-      for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) {
-        int r = c.rank + j; if (r >= c.nranks) r -= c.nranks;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(c.peer[r] + dst0 + off), "r"(dst_s), "r"(n) : "memory");
+        for (int j = 0; j < kMaxRanks; j++) if (j < c.nranks) {
+          int r = c.rank + j; if (r >= c.nranks) r -= c.nranks;
+          if (mask & (1u << r)) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(c.peer[r] + a.dst_off[seg] + off), "r"(src_s), "r"(n) : "memory");
+        }
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (k + ahead < mine) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every group but the one just committed has finished reading its slot: slot (k-1) % kStages is free
+        load(k + ahead);
+      }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // every store has been performed, not just read
     asm volatile("fence.proxy.async.global;" ::: "memory");             // order the copy engine's writes before the flag stores of the barrier
   }
-  if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
-  if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
+  if (SYNC) {
+    if (!barrier_blocks<true>(c, 2 * s + 2, op)) return;
+    if (threadIdx.x == 0 && last_block_ticket(c)) c.state[kSeqBarrier] = s + 1;
+  }
 }
-#endif
 
 }  // namespace b200coll
 

@@ -47,6 +47,7 @@ struct CommDev {
   uint32_t* state;            // local words, see enum above
   b200collFault* fault;       // host-pinned
   unsigned long long timeout_ns;
+  int mcbar;                  // 1: cross-rank barriers are one multimem.red on a multicast counter + one polled local word (needs mc); 0: flag exchange
 };
 
 }  // namespace b200coll

@@ -69,7 +69,7 @@ struct Machine {
     for (auto& r : ranks) r.arena = static_cast<char*>(calloc(1, 2u << 20));
     for (int i = 0; i < n; i++) {
       CommDev& d = ranks[i].dev;
-      d.rank = i; d.nranks = n; d.mc = mc_base; d.state = ranks[i].state.data(); d.fault = &ranks[i].fault; d.timeout_ns = 20000ull * 1000000ull;
+      d.rank = i; d.nranks = n; d.mc = mc_base; d.state = ranks[i].state.data(); d.fault = &ranks[i].fault; d.timeout_ns = 20000ull * 1000000ull; d.mcbar = multicast ? 1 : 0;
       for (int p = 0; p < kMaxRanks; p++) d.peer[p] = ranks[p < n ? p : i].arena;
     }
   }

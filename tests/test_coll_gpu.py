@@ -157,6 +157,58 @@ def test_all_gather_reduce_scatter_all_to_all(torch_cuda, group, algo):
 
 
 @pytest.mark.parametrize("group", [2, 4], indirect=True)
+def test_copy_engine_path_all_gather_all_to_all_broadcast(torch_cuda, group):
+    """Identity epilogue and >= 1 MiB: the payload moves through the cp.async.bulk ring (k_bulk) instead of LDG/STG — all-gather, all-to-all
+    and the P2P broadcast, odd chunk counts so the last chunk of a segment is short; bit-exact against plain tensor ops."""
+    torch = torch_cuda
+    comms, streams = group
+    n = len(comms)
+    count = (1 << 20) + 40 * 8                                      # 2 MiB + 640 B per rank: 129 chunks of 16 KiB, the last one short
+    srcs = []
+    for r, c in enumerate(comms):
+        t = c.empty(count * n, torch.bfloat16)
+        t.copy_(((torch.arange(count * n, device="cuda") * (2 * r + 3) + 7 * r) % 251 - 125).to(torch.bfloat16))
+        srcs.append(t)
+    torch.cuda.synchronize()
+    before = comms[0].stats()["bulk_launches"]
+    gat = [c.empty(count * n, torch.bfloat16) for c in comms]
+    run_all(torch, comms, streams, lambda r, c, st: c.all_gather(srcs[r][:count], gat[r], stream=st))
+    for g in gat:
+        assert torch.equal(g, torch.cat([s[:count] for s in srcs]))
+    a2a = [c.empty(count * n, torch.bfloat16) for c in comms]
+    for rep in range(2):                                            # twice: the ring's mbarrier phases and the barrier epochs carry over
+        run_all(torch, comms, streams, lambda r, c, st: c.all_to_all(srcs[r], a2a[r], stream=st))
+        for r in range(n):
+            assert torch.equal(a2a[r], torch.cat([srcs[s][r * count:(r + 1) * count] for s in range(n)]))
+    for root in range(n):
+        outs = [c.empty(count, torch.bfloat16) for c in comms]
+        run_all(torch, comms, streams, lambda r, c, st: c.broadcast(srcs[r][:count], outs[r], root=root, stream=st))
+        for o in outs:
+            assert torch.equal(o, srcs[root][:count])
+        for c, o in zip(comms, outs):
+            c.release(o)
+    assert comms[0].stats()["bulk_launches"] - before == 1 + 2 + n   # every one of those calls took the copy-engine kernel
+
+
+def test_copy_engine_path_one_rank_copy(torch_cuda, coll_mod):
+    torch = torch_cuda
+    (c,) = coll_mod.Comm.init_all([0], arena_mb=96)
+    count = (12 << 20) + 8 * 37
+    src = c.empty(count, torch.bfloat16)
+    src.copy_((torch.arange(count, device="cuda") % 509 - 254).to(torch.bfloat16))
+    dst = c.empty(count, torch.bfloat16)
+    dst.zero_()
+    c.all_reduce(src, dst)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src) and c.stats()["bulk_launches"] == 1
+    plain = torch.empty(count, dtype=torch.bfloat16, device="cuda")      # destination outside the arena
+    c.all_reduce(src, plain)
+    torch.cuda.synchronize()
+    assert torch.equal(plain, src) and c.stats()["bulk_launches"] == 2
+    c.destroy()
+
+
+@pytest.mark.parametrize("group", [2, 4], indirect=True)
 @pytest.mark.parametrize("count", [8, 1003, 1 << 16])
 def test_broadcast_and_reduce_rooted(torch_cuda, group, count):
     """ncclBroadcast / ncclReduce semantics incl. a count that is not a whole number of 16-byte vectors, every root,
@@ -384,7 +436,7 @@ def test_all_reduce_host_zero_copy_single_chunk_and_pipeline(torch_cuda, group, 
     comms, streams = group
     n = len(comms)
     gen = harness._gen_expected(torch, "all_reduce", 0, n, 0, "cpu")
-    for count in (1 << 12, (1 << 19) + 24, (3 << 20) + 13, (5 << 20) + 13):
+    for count in (1 << 12, (1 << 18) + 8, (1 << 19) + 24, (5 << 20) + 13, (9 << 20) + 5):      # one-shot / two-shot Lamport zero-copy, one chunk, 3 and 5 chunks with a ragged tail
         idx = torch.arange(count)
         ins = [gen(r, idx).to(torch.bfloat16) for r in range(n)]
         h_in = [comms[0].host_empty(count, torch.bfloat16), torch.empty(count, dtype=torch.bfloat16).pin_memory()]      # the library's NUMA-placed memory and plain torch pinned memory
@@ -400,7 +452,7 @@ def test_all_reduce_host_zero_copy_single_chunk_and_pipeline(torch_cuda, group, 
                 assert harness.reduction_ok(torch, h_out[r].float(), want, torch.bfloat16, n), (count, rep, r)
         comms[0].host_release(h_in[0]); comms[1].host_release(h_out[1])
     st = comms[0].stats()
-    assert st["host_calls"] == 8 and st["host_zero_copy"] == 2 and st["host_pipelined"] == 4, st
+    assert st["host_calls"] == 10 and st["host_zero_copy"] == 4 and st["host_pipelined"] == 4, st
     for c in comms:
         c.check_async_error()
     node, cpus = comms[0].numa()
