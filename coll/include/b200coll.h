@@ -51,10 +51,20 @@ typedef enum {
   b200collFloat16 = 1,
   b200collBfloat16 = 2,
   b200collFloat8e4m3 = 3,   /* output / wire type only */
-  b200collNumTypes = 4
+  /* the types below take the generic reduction path (src/generic.cu): same type in and out, no scale, any operator but avg */
+  b200collInt8 = 4,
+  b200collUint8 = 5,
+  b200collInt32 = 6,
+  b200collUint32 = 7,
+  b200collInt64 = 8,
+  b200collUint64 = 9,
+  b200collFloat64 = 10,
+  b200collNumTypes = 11
 } b200collDataType_t;
 
-typedef enum { b200collSum = 0, b200collAvg = 1 } b200collRedOp_t;
+/* sum and avg of fp16 / bf16 / fp32 run on the fused fast paths (Lamport, two-shot, NVLS); prod, min, max — and every operator on the
+ * integer types and fp64 — run on one barrier-based P2P kernel that accumulates in the element type. */
+typedef enum { b200collSum = 0, b200collAvg = 1, b200collProd = 2, b200collMin = 3, b200collMax = 4 } b200collRedOp_t;
 
 typedef enum {
   b200collOpAllReduce = 0,
@@ -114,6 +124,7 @@ typedef struct {
   uint64_t host_calls, host_bytes;            /* b200collAllReduceHost calls and the input bytes they carried */
   uint64_t host_zero_copy, host_pipelined;    /* ... of which: one-kernel zero-copy calls / chunked three-leg pipelines */
   uint64_t bulk_launches;                     /* kernels that moved their payload with the copy engine (cp.async.bulk ring) */
+  uint64_t generic_launches;                  /* min / max / prod / integer / fp64 reduction kernels */
 } b200collStats;
 
 /* Device-written watchdog record (host-pinned). code != 0 means the comm is poisoned. */

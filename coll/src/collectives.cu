@@ -118,7 +118,7 @@ static size_t out_align(size_t in_sz, size_t out_sz) { return std::min<size_t>(1
 
 static b200collResult_t check_common(b200collComm* c, const void* send, void* recv, const b200collEpilogue* ep) {
   if (!c || !send || !recv || !ep) { set_last_error("null argument"); return b200collInvalidArgument; }
-  if (ep->in_dtype == b200collFloat8e4m3 || b200collTypeSize(ep->in_dtype) == 0 || b200collTypeSize(ep->out_dtype) == 0) { set_last_error("bad dtype (e4m3 is an output type only)"); return b200collInvalidArgument; }
+  if ((int)ep->in_dtype < 0 || (int)ep->in_dtype >= (int)b200collFloat8e4m3 || (int)ep->out_dtype < 0 || (int)ep->out_dtype > (int)b200collFloat8e4m3) { set_last_error("bad dtype (fp32 / fp16 / bf16 in, those or e4m3 out; integer and fp64 payloads: reductions take the generic path, data movement takes them as words)"); return b200collInvalidArgument; }
   const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
   if (!aligned(send, 16) || !aligned(recv, out_align(is, os))) { set_last_error("send must be 16-byte aligned and recv aligned to one output vector"); return b200collInvalidArgument; }
   if (c->fault_host && *const_cast<volatile uint32_t*>(&c->fault_host->code) != 0) { set_last_error("communicator is poisoned by an earlier watchdog fault"); return b200collRemoteError; }
@@ -433,6 +433,8 @@ using namespace b200coll;
 extern "C" {
 
 b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep, b200collRedOp_t rop, b200collComm_t c, b200collStream_t stream) {
+  if (c && send && recv && ep && needs_generic(ep, rop)) return generic_reduce(c, b200collOpAllReduce, send, recv, count, ep, rop, 0, static_cast<cudaStream_t>(stream));
+  if ((int)rop < 0 || (int)rop > (int)b200collMax) { set_last_error("unknown reduction operator"); return b200collInvalidArgument; }
   b200collResult_t rc = check_common(c, send, recv, ep);
   if (rc != b200collSuccess) return rc;
   if (count == 0) return b200collSuccess;
@@ -440,9 +442,9 @@ b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, c
   const size_t is = b200collTypeSize(ep->in_dtype), os = b200collTypeSize(ep->out_dtype);
   const size_t bytes = count * is;
   const float scale = ep->scale * (rop == b200collAvg ? 1.0f / (float)c->nranks : 1.0f);
-  if (c->nranks == 1) { account(c, b200collOpAllReduce, bytes, b200collAlgoCopy); return copy_scale(c, send, recv, count, ep, scale, st); }
   const bool inplace = send == recv;
   if (inplace && is != os) { set_last_error("in-place all-reduce needs in_dtype and out_dtype of equal size"); return b200collInvalidArgument; }
+  if (c->nranks == 1) { account(c, b200collOpAllReduce, bytes, b200collAlgoCopy); return copy_scale(c, send, recv, count, ep, scale, st); }
   const bool sym_in = b200collIsSymmetric(c, send, bytes), sym_out = b200collIsSymmetric(c, recv, count * os);
   b200collAlgo_t algo = c->forced_algo != b200collAlgoAuto ? c->forced_algo : b200collTunerPick(b200collOpAllReduce, bytes, c->nranks, c->nvls);
   auto feasible = [&](b200collAlgo_t a) {
@@ -533,6 +535,8 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
 }
 
 b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recvcount, const b200collEpilogue* ep, b200collRedOp_t rop, b200collComm_t c, b200collStream_t stream) {
+  if (c && send && recv && ep && needs_generic(ep, rop)) return generic_reduce(c, b200collOpReduceScatter, send, recv, recvcount, ep, rop, 0, static_cast<cudaStream_t>(stream));
+  if ((int)rop < 0 || (int)rop > (int)b200collMax) { set_last_error("unknown reduction operator"); return b200collInvalidArgument; }
   b200collResult_t rc = check_common(c, send, recv, ep);
   if (rc != b200collSuccess) return rc;
   if (recvcount == 0) return b200collSuccess;
@@ -733,6 +737,11 @@ b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, c
 
 b200collResult_t b200collReduce(const void* send, void* recv, size_t count, const b200collEpilogue* ep, b200collRedOp_t rop, int root, b200collComm_t c, b200collStream_t stream) {
   // recv is only written on the root; other ranks may pass any aligned non-null pointer.
+  if (c && send && recv && ep && needs_generic(ep, rop)) {
+    if (root < 0 || root >= c->nranks) { set_last_error("reduce root out of range"); return b200collInvalidArgument; }
+    return generic_reduce(c, b200collOpReduce, send, recv, count, ep, rop, root, static_cast<cudaStream_t>(stream));
+  }
+  if ((int)rop < 0 || (int)rop > (int)b200collMax) { set_last_error("unknown reduction operator"); return b200collInvalidArgument; }
   b200collResult_t rc = check_common(c, send, recv, ep);
   if (rc != b200collSuccess) return rc;
   if (root < 0 || root >= c->nranks) { set_last_error("reduce root out of range"); return b200collInvalidArgument; }

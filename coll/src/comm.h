@@ -118,6 +118,10 @@ struct LaunchPlan {
 void stats_page_publish(b200collComm* c);   // comm.cu
 int tuner_blocks(b200collOp_t op, b200collAlgo_t algo, size_t work_vecs, int max_ctas, int unroll);
 
+// generic.cu
+bool needs_generic(const b200collEpilogue* ep, b200collRedOp_t rop);
+b200collResult_t generic_reduce(b200collComm* c, b200collOp_t which, const void* send, void* recv, size_t count, const b200collEpilogue* ep, b200collRedOp_t rop, int root, cudaStream_t st);
+
 // hostpath.cu
 void bind_to_gpu_numa(b200collComm* c, bool allow_bind);   // allow_bind=false: only record the node (in-process groups spanning GPUs)
 void restore_affinity_after_init(b200collComm* c);

@@ -55,7 +55,21 @@ bool map_dt(ncclDataType_t dt, b200collDataType_t* out) {
     case ncclFloat32: *out = b200collFloat32; return true;
     case ncclFloat16: *out = b200collFloat16; return true;
     case ncclBfloat16: *out = b200collBfloat16; return true;
-    default: return false;   // integer / fp64 reductions are not implemented by libb200coll
+    default: return false;   // integer / fp64: reductions go through map_dt_reduce (generic kernel), data movement through map_dt_as_words
+  }
+}
+
+// Every NCCL element type that libb200coll can reduce (fp8 is a wire / output format only, as in NCCL before 2.24).
+bool map_dt_reduce(ncclDataType_t dt, b200collDataType_t* out) {
+  switch (dt) {
+    case ncclInt8: *out = b200collInt8; return true;
+    case ncclUint8: *out = b200collUint8; return true;
+    case ncclInt32: *out = b200collInt32; return true;
+    case ncclUint32: *out = b200collUint32; return true;
+    case ncclInt64: *out = b200collInt64; return true;
+    case ncclUint64: *out = b200collUint64; return true;
+    case ncclFloat64: *out = b200collFloat64; return true;
+    default: return map_dt(dt, out);
   }
 }
 
@@ -67,9 +81,12 @@ bool map_op(ncclRedOp_t op, b200collRedOp_t* rop, float* scale) {
   *scale = 1.0f;
   if (op == ncclSum) { *rop = b200collSum; return true; }
   if (op == ncclAvg) { *rop = b200collAvg; return true; }
+  if (op == ncclProd) { *rop = b200collProd; return true; }
+  if (op == ncclMax) { *rop = b200collMax; return true; }
+  if (op == ncclMin) { *rop = b200collMin; return true; }
   std::lock_guard<std::mutex> lk(g_mu);
   const int slot = (int)op - kNcclNumOps;
-  if (slot < 0 || slot >= (int)g_premul.size() || g_premul[slot] != g_premul[slot]) return false;   // prod/min/max or a stale handle
+  if (slot < 0 || slot >= (int)g_premul.size() || g_premul[slot] != g_premul[slot]) return false;   // a stale or foreign handle
   *rop = b200collSum; *scale = g_premul[slot];
   return true;
 }
@@ -247,7 +264,7 @@ ncclResult_t ncclMemFree(void* ptr) {
 ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
   b200collRedOp_t rop; float scale;
-  if (!comm || !map_dt(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
+  if (!comm || !map_dt_reduce(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
   b200collEpilogue ep{t, t, scale};
   return map_rc(b200collAllReduce(send, recv, count, &ep, rop, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
@@ -276,7 +293,7 @@ ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclD
 ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
   b200collRedOp_t rop; float scale;
-  if (!comm || !map_dt(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
+  if (!comm || !map_dt_reduce(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
   b200collEpilogue ep{t, t, scale};
   return map_rc(b200collReduceScatter(send, recv, recvcount, &ep, rop, reinterpret_cast<ShimComm*>(comm)->comm, stream));
 }
@@ -304,7 +321,7 @@ ncclResult_t ncclBcast(void* buf, size_t count, ncclDataType_t dt, int root, ncc
 ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, int root, ncclComm_t comm, cudaStream_t stream) {
   b200collDataType_t t;
   b200collRedOp_t rop; float scale;
-  if (!comm || !map_dt(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
+  if (!comm || !map_dt_reduce(dt, &t) || !map_op(op, &rop, &scale)) return ncclInvalidArgument;
   b200collEpilogue ep{t, t, scale};
   // NCCL lets non-root ranks pass recv == NULL; the library wants an aligned pointer it will not touch
   return map_rc(b200collReduce(send, recv ? recv : const_cast<void*>(send), count, &ep, rop, root, reinterpret_cast<ShimComm*>(comm)->comm, stream));

@@ -25,12 +25,12 @@ SUCCESS = 0
 NO_DRIVER = 9
 MAX_RANKS = 8
 
-F32, F16, BF16, FP8_E4M3 = 0, 1, 2, 3
-SUM, AVG = 0, 1
+F32, F16, BF16, FP8_E4M3, I8, U8, I32, U32, I64, U64, F64 = range(11)
+SUM, AVG, PROD, MIN, MAX = range(5)
 OP_ALLREDUCE, OP_ALLGATHER, OP_REDUCESCATTER, OP_ALLTOALL = 0, 1, 2, 3
 ALGO_AUTO, ALGO_LL, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_COPY, ALGO_LL2 = range(7)
 ALGO_NAMES = ["auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2"]
-DTYPE_SIZE = {F32: 4, F16: 2, BF16: 2, FP8_E4M3: 1}
+DTYPE_SIZE = {F32: 4, F16: 2, BF16: 2, FP8_E4M3: 1, I8: 1, U8: 1, I32: 4, U32: 4, I64: 8, U64: 8, F64: 8}
 
 
 class UniqueId(C.Structure):
@@ -54,7 +54,7 @@ class CommInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("calls", C.c_uint64 * 6), ("bytes", C.c_uint64 * 6), ("algo_calls", C.c_uint64 * 7), ("kernel_launches", C.c_uint64),
                 ("staged_calls", C.c_uint64), ("p2p_sends", C.c_uint64), ("p2p_recvs", C.c_uint64), ("p2p_bytes", C.c_uint64),
-                ("host_calls", C.c_uint64), ("host_bytes", C.c_uint64), ("host_zero_copy", C.c_uint64), ("host_pipelined", C.c_uint64), ("bulk_launches", C.c_uint64)]
+                ("host_calls", C.c_uint64), ("host_bytes", C.c_uint64), ("host_zero_copy", C.c_uint64), ("host_pipelined", C.c_uint64), ("bulk_launches", C.c_uint64), ("generic_launches", C.c_uint64)]
 
 
 class Fault(C.Structure):
@@ -179,7 +179,8 @@ def self_check() -> tuple[bool, str]:
 
 def torch_dtype_code(dtype) -> int:
     import torch
-    return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float8_e4m3fn: FP8_E4M3}[dtype]
+    return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float8_e4m3fn: FP8_E4M3, torch.int8: I8, torch.uint8: U8, torch.int32: I32,
+            torch.int64: I64, torch.float64: F64, torch.bool: U8}[dtype]
 
 
 class _CudaArray:
@@ -495,7 +496,7 @@ class Comm:
         return {"calls": list(s.calls), "bytes": list(s.bytes), "algo_calls": dict(zip(ALGO_NAMES, s.algo_calls)),
                 "kernel_launches": s.kernel_launches, "staged_calls": s.staged_calls,
                 "p2p_sends": s.p2p_sends, "p2p_recvs": s.p2p_recvs, "p2p_bytes": s.p2p_bytes,
-                "host_calls": s.host_calls, "host_bytes": s.host_bytes, "host_zero_copy": s.host_zero_copy, "host_pipelined": s.host_pipelined, "bulk_launches": s.bulk_launches}
+                "host_calls": s.host_calls, "host_bytes": s.host_bytes, "host_zero_copy": s.host_zero_copy, "host_pipelined": s.host_pipelined, "bulk_launches": s.bulk_launches, "generic_launches": s.generic_launches}
 
     def check_async_error(self) -> None:
         f = Fault()

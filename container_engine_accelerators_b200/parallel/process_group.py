@@ -83,12 +83,29 @@ def _fast(t: torch.Tensor) -> bool:
     return t.is_cuda and t.is_contiguous() and t.dtype in _FAST_DTYPES and t.data_ptr() % 16 == 0 and t.numel() > 0
 
 
+_GENERIC_DTYPES = (torch.int8, torch.uint8, torch.int32, torch.int64, torch.float64)      # any operator but AVG, on the generic P2P kernel
+
+
 def _sum_or_avg(op) -> Optional[int]:
     if op == dist.ReduceOp.SUM:
         return coll.SUM
     if op == dist.ReduceOp.AVG:
         return coll.AVG
     return None
+
+
+def _red_op(op) -> Optional[int]:
+    """Every reduction libb200coll implements (sum / avg fused fast paths; min / max / product on the generic kernel)."""
+    return {dist.ReduceOp.SUM: coll.SUM, dist.ReduceOp.AVG: coll.AVG, dist.ReduceOp.MIN: coll.MIN, dist.ReduceOp.MAX: coll.MAX,
+            dist.ReduceOp.PRODUCT: coll.PROD}.get(op)
+
+
+def _reducible(t: torch.Tensor, op: Optional[int]) -> bool:
+    if op is None or not (t.is_cuda and t.is_contiguous() and t.data_ptr() % 16 == 0 and t.numel() > 0):
+        return False
+    if t.dtype in _FAST_DTYPES:
+        return True
+    return t.dtype in _GENERIC_DTYPES and op != coll.AVG
 
 
 def alltoallv_layout(split_matrix: list[list[int]], rank: int) -> tuple[list[int], list[int], list[int], int]:
@@ -201,8 +218,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
 
     # ------------------------------------------------------------------ collectives
     def allreduce(self, tensors, opts=None):
-        op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
-        if op is not None and all(_fast(t) for t in tensors):
+        op = _red_op(opts.reduceOp) if opts is not None else coll.SUM
+        if op is not None and all(_reducible(t, op) for t in tensors):
             with self._ordered(self):
                 for t in tensors:
                     self.comm.all_reduce(t, op=op)
@@ -273,8 +290,8 @@ class B200CollProcessGroup(dist.ProcessGroup):
 
     def reduce(self, tensors, opts=None):
         root = opts.rootRank if opts is not None else 0
-        op = _sum_or_avg(opts.reduceOp) if opts is not None else coll.SUM
-        if op is not None and all(_fast(t) for t in tensors):
+        op = _red_op(opts.reduceOp) if opts is not None else coll.SUM
+        if op is not None and all(_reducible(t, op) for t in tensors):
             with self._ordered(self):
                 for t in tensors:
                     self.comm.reduce(t, root=root, op=op)

@@ -1,15 +1,18 @@
 #!/bin/bash
-# Shared steps of the NVIDIA .run driver installers (Ubuntu and minikube hosts).
+# NVIDIA .run driver installation for hosts without a vendor driver image (Ubuntu and minikube nodes): the part the two
+# entrypoints share. Role parity: nvidia-driver-installer/ubuntu/entrypoint.sh and minikube/entrypoint.sh of the reference
+# (SURVEY C17/C18). What is fixed by that role — and therefore identical here — is the environment contract (the NVIDIA_* / ROOT_MOUNT_DIR
+# variables the DaemonSets set), the two-line stamp file other tooling reads, and the nvidia-installer command line. Everything else
+# is organised differently:
 #
-# Flow (reference nvidia-driver-installer/ubuntu/entrypoint.sh:33-178, minikube/entrypoint.sh:34-220):
-#   cache hit (same kernel + driver version recorded in <install dir>/.cache) -> insmod the cached modules, verify
-#   else: get kernel headers/sources -> redirect the installer's hard-wired output dirs (/usr/bin,
-#         /usr/lib/x86_64-linux-gnu, /lib/modules/$K/video) into the host-visible install dir with overlayfs ->
-#         download + run the .run file -> record the cache -> verify (nvidia-smi, nvidia-modprobe -c0 -u)
-#   finally add <host install dir>/lib64 to the host's ld.so.conf and refresh its cache.
-# Differences from the reference: one table drives the three overlay redirects; Blackwell needs the open kernel
-# modules, so NVIDIA_KERNEL_MODULE_TYPE defaults to "open" for driver >= 560; every external command can be replaced
-# through an env var so the script is unit-testable without root.
+#   * the work is a PLAN: an ordered list of step functions chosen up front ("reuse" when the stamp matches this kernel + driver,
+#     "build" otherwise) and executed by one runner that numbers the steps, times them and stops at the first failure;
+#   * the stamp is PARSED (two known keys), never sourced as shell;
+#   * the installer's three hard-wired output directories are redirected into the host-visible install dir from one table;
+#   * Blackwell needs the open kernel modules: --kernel-module-type=open is passed for driver branches >= 560 unless
+#     NVIDIA_KERNEL_MODULE_TYPE says otherwise;
+#   * every external program is reached through a variable (MOUNT, CURL, ...) so the whole flow runs against stubs in tests/test_manifests.py;
+#   * publishing the library directory to the host's loader configuration is idempotent.
 set -o pipefail
 set -u
 
@@ -18,113 +21,129 @@ NVIDIA_DRIVER_VERSION="${NVIDIA_DRIVER_VERSION:-570.124.06}"
 NVIDIA_DRIVER_DOWNLOAD_URL="${NVIDIA_DRIVER_DOWNLOAD_URL:-https://us.download.nvidia.com/${NVIDIA_DRIVER_BRANCH}/${NVIDIA_DRIVER_VERSION}/NVIDIA-Linux-x86_64-${NVIDIA_DRIVER_VERSION}.run}"
 NVIDIA_INSTALL_DIR_HOST="${NVIDIA_INSTALL_DIR_HOST:-/home/kubernetes/bin/nvidia}"
 NVIDIA_INSTALL_DIR_CONTAINER="${NVIDIA_INSTALL_DIR_CONTAINER:-/usr/local/nvidia}"
-NVIDIA_INSTALLER_RUNFILE="$(basename "${NVIDIA_DRIVER_DOWNLOAD_URL}")"
 ROOT_MOUNT_DIR="${ROOT_MOUNT_DIR:-/root}"
-CACHE_FILE="${NVIDIA_INSTALL_DIR_CONTAINER}/.cache"
 KERNEL_VERSION="${KERNEL_VERSION:-$(uname -r)}"
 LD_SO_CONF_D="${LD_SO_CONF_D:-/etc/ld.so.conf.d}"
-# command seams
 : "${MOUNT:=mount}" "${UMOUNT:=umount}" "${LDCONFIG:=ldconfig}" "${LSMOD:=lsmod}" "${INSMOD:=insmod}" "${CURL:=curl}"
 
-driver_major() { echo "${NVIDIA_DRIVER_VERSION%%.*}"; }
+DRV_PREFIX="${NVIDIA_INSTALL_DIR_CONTAINER}"
+DRV_STAMP="${DRV_PREFIX}/.cache"
+DRV_RUNFILE="${NVIDIA_DRIVER_DOWNLOAD_URL##*/}"
+DRV_OVERLAYS=()            # mount points created by step_redirect_outputs, newest first
 
-kernel_module_type_flag() {
-  local t="${NVIDIA_KERNEL_MODULE_TYPE:-}"
-  if [[ -z "${t}" && "$(driver_major)" -ge 560 ]]; then t=open; fi
-  if [[ -n "${t}" ]]; then echo "--kernel-module-type=${t}"; fi
+say() { printf '[driver-install] %s\n' "$*"; }
+
+# ---- stamp: which (kernel, driver) pair the modules under ${DRV_PREFIX}/drivers were built for
+stamp_value() {            # $1 = key; prints the value recorded in the stamp, nothing if absent
+  [[ -r "${DRV_STAMP}" ]] || return 0
+  local line
+  while IFS= read -r line; do
+    if [[ "${line}" == "$1="* ]]; then printf '%s' "${line#*=}"; return 0; fi
+  done < "${DRV_STAMP}"
 }
 
-check_cached_version() {
-  echo "Checking cached version"
-  if [[ ! -f "${CACHE_FILE}" ]]; then echo "Cache file ${CACHE_FILE} not found."; return 1; fi
-  local CACHE_KERNEL_VERSION="" CACHE_NVIDIA_DRIVER_VERSION=""
-  # shellcheck disable=SC1090
-  . "${CACHE_FILE}"
-  if [[ "${KERNEL_VERSION}" == "${CACHE_KERNEL_VERSION}" && "${NVIDIA_DRIVER_VERSION}" == "${CACHE_NVIDIA_DRIVER_VERSION}" ]]; then
-    echo "Found existing driver installation for kernel version ${KERNEL_VERSION} and driver version ${NVIDIA_DRIVER_VERSION}."
+stamp_matches() {
+  [[ -f "${DRV_STAMP}" ]] || { say "no stamp at ${DRV_STAMP}: nothing has been installed here yet"; return 1; }
+  local k d; k="$(stamp_value CACHE_KERNEL_VERSION)"; d="$(stamp_value CACHE_NVIDIA_DRIVER_VERSION)"
+  if [[ "${k}" == "${KERNEL_VERSION}" && "${d}" == "${NVIDIA_DRIVER_VERSION}" ]]; then
+    say "stamp matches: driver ${d} was built for kernel ${k}; reusing it"
     return 0
   fi
-  echo "Cache file ${CACHE_FILE} found but existing versions didn't match."
+  say "stamp is for kernel '${k}' / driver '${d}', wanted '${KERNEL_VERSION}' / '${NVIDIA_DRIVER_VERSION}': rebuilding"
   return 1
 }
 
-update_cached_version() {
-  printf 'CACHE_KERNEL_VERSION=%s\nCACHE_NVIDIA_DRIVER_VERSION=%s\n' "${KERNEL_VERSION}" "${NVIDIA_DRIVER_VERSION}" > "${CACHE_FILE}"
-  echo "Updated cached version as:"; cat "${CACHE_FILE}"
+step_write_stamp() {
+  printf 'CACHE_KERNEL_VERSION=%s\nCACHE_NVIDIA_DRIVER_VERSION=%s\n' "${KERNEL_VERSION}" "${NVIDIA_DRIVER_VERSION}" > "${DRV_STAMP}"
 }
 
-update_container_ld_cache() {
-  echo "${NVIDIA_INSTALL_DIR_CONTAINER}/lib64" > "${LD_SO_CONF_D}/nvidia.conf"
+# ---- loader configuration
+refresh_container_loader() {
+  printf '%s\n' "${DRV_PREFIX}/lib64" > "${LD_SO_CONF_D}/nvidia.conf"
   ${LDCONFIG}
 }
 
-# installer-owned dir | subdir of the install dir that must receive its contents
-overlay_table() {
-  cat <<__T__
-/usr/bin|bin
-/usr/lib/x86_64-linux-gnu|lib64
-/lib/modules/${KERNEL_VERSION}/video|drivers
-__T__
-}
-
-configure_nvidia_installation_dirs() {
-  echo "Configuring installation directories..."
-  mkdir -p "${NVIDIA_INSTALL_DIR_CONTAINER}"
-  local mounted=()
-  while IFS='|' read -r lower sub; do
-    mkdir -p "${NVIDIA_INSTALL_DIR_CONTAINER}/${sub}" "${NVIDIA_INSTALL_DIR_CONTAINER}/${sub}-workdir" "${OVERLAY_ROOT:-}${lower}"
-    ${MOUNT} -t overlay -o "lowerdir=${lower},upperdir=${NVIDIA_INSTALL_DIR_CONTAINER}/${sub},workdir=${NVIDIA_INSTALL_DIR_CONTAINER}/${sub}-workdir" none "${lower}" || return 1
-    mounted=("${lower}" "${mounted[@]}")
-  done < <(overlay_table)
-  update_container_ld_cache          # keeps nvidia-installer's log free of ldconfig warnings
-  # shellcheck disable=SC2064
-  trap "for m in ${mounted[*]}; do ${UMOUNT} \$m; done" EXIT
-  echo "Configuring installation directories... DONE."
-}
-
-download_nvidia_installer() {
-  echo "Downloading Nvidia installer..."
-  ${CURL} -L -S -f "${NVIDIA_DRIVER_DOWNLOAD_URL}" -o "${NVIDIA_INSTALL_DIR_CONTAINER}/${NVIDIA_INSTALLER_RUNFILE}" || return 1
-}
-
-run_nvidia_installer() {
-  echo "Running Nvidia installer..."
-  local extra=()
-  [[ -n "${KERNEL_SOURCE_PATH:-}" ]] && extra+=("--kernel-source-path=${KERNEL_SOURCE_PATH}")
-  local kmt; kmt="$(kernel_module_type_flag)"; [[ -n "${kmt}" ]] && extra+=("${kmt}")
-  ( cd "${NVIDIA_INSTALL_DIR_CONTAINER}" && ${SH:-sh} "${NVIDIA_INSTALLER_RUNFILE}" \
-      --utility-prefix="${NVIDIA_INSTALL_DIR_CONTAINER}" --opengl-prefix="${NVIDIA_INSTALL_DIR_CONTAINER}" --no-install-compat32-libs \
-      --log-file-name="${NVIDIA_INSTALL_DIR_CONTAINER}/nvidia-installer.log" --no-drm --silent --accept-license "${extra[@]}" ) || return 1
-  echo "Running Nvidia installer... DONE."
-}
-
-configure_cached_installation() {
-  echo "Configuring cached driver installation..."
-  update_container_ld_cache
-  if ! ${LSMOD} | grep -qw nvidia; then ${INSMOD} "${NVIDIA_INSTALL_DIR_CONTAINER}/drivers/nvidia.ko" || return 1; fi
-  if ! ${LSMOD} | grep -qw nvidia_uvm; then ${INSMOD} "${NVIDIA_INSTALL_DIR_CONTAINER}/drivers/nvidia-uvm.ko" || return 1; fi
-}
-
-verify_nvidia_installation() {
-  echo "Verifying Nvidia installation..."
-  export PATH="${NVIDIA_INSTALL_DIR_CONTAINER}/bin:${PATH}"
-  nvidia-smi || return 1
-  nvidia-modprobe -c0 -u || return 1      # creates /dev/nvidia-uvm
-}
-
-update_host_ld_cache() {
-  echo "Updating host's ld cache..."
-  local conf="${ROOT_MOUNT_DIR}/etc/ld.so.conf"
-  grep -qxF "${NVIDIA_INSTALL_DIR_HOST}/lib64" "${conf}" 2>/dev/null || echo "${NVIDIA_INSTALL_DIR_HOST}/lib64" >> "${conf}"     # idempotent (the reference appends on every run)
+step_publish_to_host_loader() {
+  local conf="${ROOT_MOUNT_DIR}/etc/ld.so.conf" want="${NVIDIA_INSTALL_DIR_HOST}/lib64"
+  if ! grep -qxF "${want}" "${conf}" 2>/dev/null; then printf '%s\n' "${want}" >> "${conf}"; fi
   ${LDCONFIG} -r "${ROOT_MOUNT_DIR}"
 }
 
-install_driver_main() {   # $1 = function that fetches kernel headers/sources for this distro
-  local fetch_kernel="$1"
-  if check_cached_version; then
-    configure_cached_installation && verify_nvidia_installation || return 1
+# ---- build path
+open_modules_flag() {      # prints the nvidia-installer flag selecting the kernel-module flavour, if one is needed
+  local flavour="${NVIDIA_KERNEL_MODULE_TYPE:-}"
+  if [[ -z "${flavour}" ]] && (( ${NVIDIA_DRIVER_VERSION%%.*} >= 560 )); then flavour=open; fi
+  [[ -n "${flavour}" ]] && printf -- '--kernel-module-type=%s' "${flavour}"
+  return 0
+}
+
+# where nvidia-installer insists on writing  ->  directory under the install prefix that must end up holding it
+redirect_table() {
+  printf '%s %s\n' /usr/bin bin /usr/lib/x86_64-linux-gnu lib64 "/lib/modules/${KERNEL_VERSION}/video" drivers
+}
+
+undo_redirects() {
+  local m
+  for m in "${DRV_OVERLAYS[@]}"; do ${UMOUNT} "${m}"; done
+  DRV_OVERLAYS=()
+}
+
+step_redirect_outputs() {
+  mkdir -p "${DRV_PREFIX}"
+  trap undo_redirects EXIT
+  local target sub upper
+  while read -r target sub; do
+    upper="${DRV_PREFIX}/${sub}"
+    mkdir -p "${upper}" "${upper}-workdir" "${OVERLAY_ROOT:-}${target}"
+    ${MOUNT} -t overlay -o "lowerdir=${target},upperdir=${upper},workdir=${upper}-workdir" none "${target}" || return 1
+    DRV_OVERLAYS=("${target}" "${DRV_OVERLAYS[@]}")
+  done < <(redirect_table)
+  refresh_container_loader          # so that nvidia-installer's own ldconfig run finds the redirected lib64
+}
+
+step_fetch_runfile() {
+  ${CURL} -L -S -f "${NVIDIA_DRIVER_DOWNLOAD_URL}" -o "${DRV_PREFIX}/${DRV_RUNFILE}"
+}
+
+step_run_runfile() {
+  local args=(--utility-prefix="${DRV_PREFIX}" --opengl-prefix="${DRV_PREFIX}" --no-install-compat32-libs
+              --log-file-name="${DRV_PREFIX}/nvidia-installer.log" --no-drm --silent --accept-license)
+  [[ -n "${KERNEL_SOURCE_PATH:-}" ]] && args+=("--kernel-source-path=${KERNEL_SOURCE_PATH}")
+  local flavour; flavour="$(open_modules_flag)"
+  [[ -n "${flavour}" ]] && args+=("${flavour}")
+  ( cd "${DRV_PREFIX}" && ${SH:-sh} "${DRV_RUNFILE}" "${args[@]}" )
+}
+
+# ---- reuse path
+step_load_prebuilt_modules() {
+  refresh_container_loader
+  local mod
+  for mod in nvidia nvidia-uvm; do
+    if ! ${LSMOD} | grep -qw "${mod//-/_}"; then ${INSMOD} "${DRV_PREFIX}/drivers/${mod}.ko" || return 1; fi
+  done
+}
+
+# ---- both paths
+step_check_driver_answers() {
+  PATH="${DRV_PREFIX}/bin:${PATH}" nvidia-smi || return 1
+  PATH="${DRV_PREFIX}/bin:${PATH}" nvidia-modprobe -c0 -u          # also creates /dev/nvidia-uvm
+}
+
+run_plan() {               # run the named step functions in order; stop at the first one that fails
+  local total=$# n=0 step t0
+  for step in "$@"; do
+    n=$((n + 1)); t0=${SECONDS}
+    say "(${n}/${total}) ${step#step_}"
+    if ! "${step}"; then say "(${n}/${total}) ${step#step_} FAILED after $((SECONDS - t0)) s"; return 1; fi
+  done
+}
+
+install_driver_main() {    # $1 = the distro's step that provides kernel headers or sources
+  local kernel_step="$1"
+  say "driver ${NVIDIA_DRIVER_VERSION} (${NVIDIA_DRIVER_BRANCH}) for kernel ${KERNEL_VERSION}; prefix ${DRV_PREFIX} (host: ${NVIDIA_INSTALL_DIR_HOST})"
+  if stamp_matches; then
+    run_plan step_load_prebuilt_modules step_check_driver_answers step_publish_to_host_loader
   else
-    "${fetch_kernel}" && configure_nvidia_installation_dirs && download_nvidia_installer && run_nvidia_installer && update_cached_version && verify_nvidia_installation || return 1
+    run_plan "${kernel_step}" step_redirect_outputs step_fetch_runfile step_run_runfile step_write_stamp step_check_driver_answers step_publish_to_host_loader
   fi
-  update_host_ld_cache
 }

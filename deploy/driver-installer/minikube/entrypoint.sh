@@ -18,7 +18,7 @@ kernel_tarball_version() {
 
 download_kernel_src() {
   local v major; v="$(kernel_tarball_version)"; major="${v%%.*}"
-  echo "Downloading kernel sources for ${v}..."
+  say "kernel sources: linux-${v} from cdn.kernel.org"
   mkdir -p "${KERNEL_SRC_DIR}"
   ${CURL} -L -S -f "https://cdn.kernel.org/pub/linux/kernel/v${major}.x/linux-${v}.tar.xz" -o /tmp/linux.tar.xz || return 1
   ${TAR:-tar} -xf /tmp/linux.tar.xz -C "${KERNEL_SRC_DIR}" --strip-components=1 || return 1

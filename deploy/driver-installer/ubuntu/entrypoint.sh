@@ -5,7 +5,6 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 . "${DRIVER_INSTALL_LIB:-${HERE}/../lib/driver-install-lib.sh}"
 
 download_kernel_headers() {
-  echo "Downloading kernel headers..."
   ${APT_GET:-apt-get} update && ${APT_GET:-apt-get} install -y "linux-headers-${KERNEL_VERSION}"
 }
 

@@ -555,7 +555,35 @@ def test_nccl_api_shim_collectives(torch_cuda, coll_lib):
         assert all(torch.equal(d, torch.full_like(d, 0.75)) for d in dst)
         s.ck(L.ncclRedOpDestroy(op.value, comms[0]))
         assert L.ncclAllReduce(p(src[0]), p(dst[0]), 4096, s.F32, op.value, comms[0], st[0]) != 0          # stale handle is refused
-        assert L.ncclAllReduce(p(src[0]), p(dst[0]), 4096, s.F32, 2, comms[0], st[0]) != 0                 # ncclMax is not implemented
+        # the rest of ncclRedOp_t x ncclDataType_t (generic P2P kernel): what PyTorch's int64 all-reduces and `all_reduce_perf -o max -d int32` send
+        I32, U8, F64, MAX, MIN, PROD = 2, 1, 8, 2, 3, 1
+        for count in (1003, (3 << 18) + 5):                                     # staged through the arena (plain cudaMalloc buffers), scalar tail
+            i32 = [((torch.arange(count, device="cuda") * (7 * r + 3)) % 2001 - 1000).to(torch.int32) for r in range(n)]
+            o32 = [torch.empty(count, dtype=torch.int32, device="cuda") for _ in range(n)]
+            every(lambda r: L.ncclAllReduce(p(i32[r]), p(o32[r]), count, I32, MAX, comms[r], st[r]))
+            assert all(torch.equal(o, torch.maximum(i32[0], i32[1])) for o in o32)
+            i64 = [(torch.arange(count, device="cuda", dtype=torch.int64) * (r + 1) << 33) - 5 for r in range(n)]
+            every(lambda r: L.ncclAllReduce(p(i64[r]), p(i64[r]), count, s.I64, s.SUM, comms[r], st[r]))      # in place, values beyond 2^32
+            assert all(torch.equal(t, (torch.arange(count, device="cuda", dtype=torch.int64) * 3 << 33) - 10) for t in i64)
+        u8 = [((torch.arange(4096, device="cuda") * (r + 5)) % 251).to(torch.uint8) for r in range(n)]
+        o8 = [torch.empty(4096, dtype=torch.uint8, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclAllReduce(p(u8[r]), p(o8[r]), 4096, U8, MIN, comms[r], st[r]))
+        assert all(torch.equal(o, torch.minimum(u8[0], u8[1])) for o in o8)
+        f64 = [torch.linspace(0.5, 2.0, 2048, device="cuda", dtype=torch.float64) * (r + 1) for r in range(n)]
+        o64 = [torch.empty(2048, dtype=torch.float64, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclAllReduce(p(f64[r]), p(o64[r]), 2048, F64, PROD, comms[r], st[r]))
+        assert all(torch.equal(o, f64[0] * f64[1]) for o in o64)
+        bmax = [torch.empty(1000, dtype=torch.bfloat16, device="cuda") for _ in range(n)]
+        bsrc = [(((torch.arange(1000, device="cuda") * (r + 3)) % 13) - 6).to(torch.bfloat16) for r in range(n)]
+        every(lambda r: L.ncclAllReduce(p(bsrc[r]), p(bmax[r]), 1000, s.BF16, MAX, comms[r], st[r]))
+        assert all(torch.equal(o, torch.maximum(bsrc[0], bsrc[1])) for o in bmax)
+        rs32 = [torch.empty(512, dtype=torch.int32, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclReduceScatter(p(i32[r]), p(rs32[r]), 512, I32, s.SUM, comms[r], st[r]))
+        assert all(torch.equal(rs32[r], (i32[0] + i32[1])[r * 512:(r + 1) * 512]) for r in range(n))
+        rd32 = [torch.full((1003,), -9, dtype=torch.int32, device="cuda") for _ in range(n)]
+        every(lambda r: L.ncclReduce(p(i32[r]), p(rd32[r]), 1003, I32, MIN, 1, comms[r], st[r]))
+        assert torch.equal(rd32[1], torch.minimum(i32[0], i32[1])[:1003]) and bool((rd32[0] == -9).all())
+        assert L.ncclAllReduce(p(i32[0]), p(o32[0]), 8, I32, s.AVG, comms[0], st[0]) != 0                    # avg: floating point only
         # all-gather / reduce-scatter
         part = [torch.arange(2048, device="cuda", dtype=torch.float16) + 2048 * r for r in range(n)]
         full = [torch.empty(2048 * n, dtype=torch.float16, device="cuda") for _ in range(n)]
