@@ -372,7 +372,7 @@ class Manager {
 void apply_transport(const Config& cfg, const std::vector<Mount>& mounts, pb::ContainerAllocateResponse* r) {
   if (cfg.transport != "b200coll") return;
   std::map<std::string, std::string> env = {{"B200COLL_LIB_DIR", cfg.lib_dir_container}, {"B200COLL_LIB", cfg.lib_dir_container + "/libb200coll.so"}, {"LD_LIBRARY_PATH", cfg.lib_dir_container},
-                                            {"B200COLL_NVLS", "-1"}, {"B200COLL_ALGO", "auto"}, {"B200COLL_TIMEOUT_MS", "20000"}, {"B200COLL_DEBUG", "WARN"}};
+                                            {"B200COLL_NVLS", "-1"}, {"B200COLL_ALGO", "auto"}, {"B200COLL_TIMEOUT_MS", "600000"}, {"B200COLL_DEBUG", "WARN"}};
   for (auto& kv : cfg.transport_env) env[kv.first] = kv.second;
   for (auto& kv : env) r->envs.insert(kv);
   bool covered = false;

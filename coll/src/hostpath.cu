@@ -167,7 +167,7 @@ b200collResult_t b200collHostAlloc(b200collComm_t c, void** ptr, size_t bytes) {
   if (!c || !ptr || bytes == 0) return b200collInvalidArgument;
   const size_t len = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
   void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-  if (p == MAP_FAILED) { set_last_error("HostAlloc: mmap failed"); return b200collSystemError; }
+  if (p == MAP_FAILED) { set_last_error("host alloc: mmap failed"); return b200collSystemError; }
   (void)madvise(p, len, MADV_HUGEPAGE);
   bool placed = false;
   if (c->numa_node >= 0 && c->numa_node < 64) {
@@ -183,7 +183,7 @@ b200collResult_t b200collHostAlloc(b200collComm_t c, void** ptr, size_t bytes) {
   memset(p, 0, len);                                  // first touch: pages are allocated now, on the preferred / current node
   if (moved) sched_setaffinity(0, sizeof(have), &have);
   cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped);
-  if (e != cudaSuccess) { munmap(p, len); set_last_error(std::string("HostAlloc: cudaHostRegister failed: ") + cudaGetErrorString(e)); (void)cudaGetLastError(); return b200collUnhandledCudaError; }
+  if (e != cudaSuccess) { munmap(p, len); set_last_error(std::string("host alloc: cudaHostRegister failed: ") + cudaGetErrorString(e)); (void)cudaGetLastError(); return b200collUnhandledCudaError; }
   { std::lock_guard<std::mutex> lk(c->mu); c->host_allocs[p] = len; }
   dbg(1, "rank %d: %zu MiB of pinned host memory on node %d (%s)", c->rank, len >> 20, c->numa_node, placed ? "mbind" : "first touch");
   *ptr = p;

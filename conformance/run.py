@@ -46,15 +46,21 @@ PRESETS = {
 class Node:
     """One throw-away node with a plugin process on it."""
 
-    def __init__(self, command: str, gpus: int = 2, mig_parts: int = 0, config=None, numa=None, extra: str = "", env=None, kubelet: bool = True):
+    def __init__(self, command: str, gpus: int = 2, mig_parts: int = 0, config=None, numa=None, extra: str = "", env=None, kubelet: bool = True, real: bool = False):
+        """real=True: no fakes on the device side — the host's /dev, /proc, /sys and the installed libnvidia-ml (tests/test_agent_gpu.py,
+        run on a GPU box); the kubelet is still the stub."""
         self.tmp = tempfile.TemporaryDirectory(prefix="b200-conformance-")
         root = self.tmp.name
-        self.dev = testing.make_fake_dev(root, gpus)
-        self.proc = testing.make_fake_mig(root, self.dev, gpus, mig_parts) if mig_parts else os.path.join(root, "proc")
+        self.real = real
         self.plugin_dir = os.path.join(root, "device-plugins"); os.makedirs(self.plugin_dir)
-        self.pci_root = os.path.join(root, "nopci")
-        for i, node in enumerate(numa or []):                                  # the scripted NVML reports 00000000:<1B+i>:00.0
-            self.pci_root = testing.make_fake_pci(root, f"0000:{0x1b + i:02x}:00.0", node)
+        if real:
+            self.dev, self.proc, self.pci_root = "/dev", "/proc", "/sys/bus/pci/devices"
+        else:
+            self.dev = testing.make_fake_dev(root, gpus)
+            self.proc = testing.make_fake_mig(root, self.dev, gpus, mig_parts) if mig_parts else os.path.join(root, "proc")
+            self.pci_root = os.path.join(root, "nopci")
+            for i, node in enumerate(numa or []):                              # the scripted NVML reports 00000000:<1B+i>:00.0
+                self.pci_root = testing.make_fake_pci(root, f"0000:{0x1b + i:02x}:00.0", node)
         self.gpu_config = os.path.join(root, "gpu_config.json")
         if config is not None:
             with open(self.gpu_config, "w") as f:
@@ -68,6 +74,9 @@ class Node:
         native_dir = os.path.join(ROOT, "build", "agent")
         penv = {**os.environ, "PYTHONPATH": ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), "B200AGENT_NVML_LIB": os.path.join(native_dir, "libfake_nvml.so"),
                 "B200AGENT_NATIVE_LIB": os.path.join(native_dir, "libb200agent_nvml.so"), "FAKE_NVML_DEV_DIR": self.dev, "KUBERNETES_SERVICE_HOST": "", **(env or {})}
+        if real:
+            for k in ("B200AGENT_NVML_LIB", "FAKE_NVML_DEV_DIR"):
+                penv.pop(k, None)
         self.process = subprocess.Popen(argv, env=penv, stdout=self.log, stderr=self.log)
         self.client = None
 

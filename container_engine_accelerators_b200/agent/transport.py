@@ -13,7 +13,7 @@ DEFAULT_ENV = {
     "B200COLL_LIB": "/usr/local/nvidia/lib64/libb200coll.so",
     "B200COLL_NVLS": "-1",          # probe; 0 forces P2P paths (NCCL_NVLS_ENABLE analogue)
     "B200COLL_ALGO": "auto",        # NCCL_ALGO analogue: auto|ll|oneshot|twoshot|nvls
-    "B200COLL_TIMEOUT_MS": "20000",
+    "B200COLL_TIMEOUT_MS": "600000",
     "B200COLL_DEBUG": "WARN",
 }
 

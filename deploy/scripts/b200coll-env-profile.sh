@@ -7,6 +7,6 @@ export B200COLL_LIB="${B200COLL_LIB_DIR}/libb200coll.so"
 export LD_LIBRARY_PATH="${B200COLL_LIB_DIR}${LD_LIBRARY_PATH:+:${LD_LIBRARY_PATH}}"
 export B200COLL_NVLS="${B200COLL_NVLS:--1}"          # -1 probe, 0 P2P only, 1 require multicast
 export B200COLL_ALGO="${B200COLL_ALGO:-auto}"         # auto | ll | ll2 | oneshot | twoshot | nvls
-export B200COLL_TIMEOUT_MS="${B200COLL_TIMEOUT_MS:-20000}"
+export B200COLL_TIMEOUT_MS="${B200COLL_TIMEOUT_MS:-600000}"
 export B200COLL_DEBUG="${B200COLL_DEBUG:-WARN}"
 if [ -f "${B200COLL_LIB_DIR}/b200_nvswitch.tbl" ]; then export B200COLL_TUNER_FILE="${B200COLL_TUNER_FILE:-${B200COLL_LIB_DIR}/b200_nvswitch.tbl}"; fi

@@ -437,3 +437,43 @@ def test_epoch_barrier_under_host_emulation_classic_and_multicast_counter(coll_l
         assert b.returncode == 0, b.stdout + b.stderr
         r = subprocess.run([os.path.join(os.path.dirname(root), "build", target), "5"], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "data race" not in r.stderr and f"barrier_emu {what}: all launches consistent" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_cpulist_parser_matches_sysfs_format(coll_lib):
+    """coll/src/hostpath.cu binds a rank to its GPU's CPUs from sysfs' local_cpulist ("0-31,64-95"); the parser is pure."""
+    L = C.CDLL(coll_lib)
+    L.b200collDebugParseCpuList.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int]
+    out = (C.c_int * 512)()
+
+    def parse(text):
+        n = L.b200collDebugParseCpuList(text.encode(), out, 512)
+        return list(out[:n])
+    assert parse("0-31,64-95") == list(range(32)) + list(range(64, 96))
+    assert parse("3") == [3] and parse("") == [] and parse("0,2,4-5\n") == [0, 2, 4, 5]
+    assert parse("7-7,1") == [1, 7] and parse("garbage") == [] and parse("2-") == []
+
+
+def test_benchmark_self_check_rejects_low_precision_accumulation():
+    """bench.py verifies reductions with data whose sums are not exact in bf16, within one bf16 ulp of the fp32-accumulated result
+    (harness.reduction_ok). A reduction that accumulates in bf16 — what multimem.ld_reduce does without .acc::f32 — must fail it,
+    a correctly rounded fp32 accumulation in any order must pass."""
+    import torch
+    from container_engine_accelerators_b200.parallel import harness as h
+    n = 8
+    gen = h._gen_expected(torch, "all_reduce", 0, n, 0, "cpu")
+    idx = torch.arange(1 << 16)
+    ins = [gen(r, idx) for r in range(n)]
+    assert all(torch.equal(x, x.to(torch.bfloat16).float()) for x in ins)                 # inputs are bf16 values
+    want = sum(ins)
+    assert (want.to(torch.bfloat16).float() != want).float().mean() > 0.5                 # most sums need rounding: the check has teeth
+    assert h.reduction_ok(torch, want.to(torch.bfloat16).float(), want, torch.bfloat16, n)
+    assert h.reduction_ok(torch, sum(reversed(ins)).to(torch.bfloat16).float(), want, torch.bfloat16, n)
+    acc = torch.zeros_like(want).to(torch.bfloat16)
+    for x in ins:
+        acc = (acc.float() + x).to(torch.bfloat16)
+    assert not h.reduction_ok(torch, acc.float(), want, torch.bfloat16, n)
+    half = torch.zeros_like(want).to(torch.float16)
+    for x in ins:
+        half = (half.float() + x).to(torch.float16)
+    off_by_two = want.to(torch.bfloat16).float() + 2 * h.bf16_ulp(torch, want)
+    assert not h.reduction_ok(torch, off_by_two, want, torch.bfloat16, n)
