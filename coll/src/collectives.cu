@@ -62,9 +62,18 @@ struct Grid { int blocks, threads; };
 // Never with virtual ranks (several communicators on one GPU): a pre-launched dependent grid parks its CTAs on SMs
 // that another rank's current kernel still needs, and ranks that spin on each other then deadlock (seen at 1 MiB with
 // 4 ranks on one B200). With one rank per GPU every CTA of kernel i is resident before kernel i+1 may start.
+// Measured on 2 x B200 (profiles/latency_ab.md): the overlap wins ~1 us per back-to-back call up to 4 KiB (4.4 vs 5.5 us at 1 KiB) and
+// LOSES 0.5 - 1 us from 16 KiB up (the early-launched grid sits on the SMs while its predecessor still needs them, and its
+// griddepcontrol.wait returns only after the predecessor's memory flush). So only launches whose message is at most
+// B200COLL_PDL_MAX_KB (default 8) carry the attribute; launch_ll sets the flag for the launch it is about to make.
+static thread_local bool t_pdl_small = false;
+static size_t pdl_max_bytes() {
+  static const size_t v = [] { const char* e = getenv("B200COLL_PDL_MAX_KB"); return (size_t)(e && *e ? atol(e) : 8) << 10; }();
+  return v;
+}
 static bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("B200COLL_PDL"); return !(e && *e == '0'); }();      // on unless B200COLL_PDL=0
-  return on && g_loopback_comms.load(std::memory_order_relaxed) == 0;
+  return on && t_pdl_small && g_loopback_comms.load(std::memory_order_relaxed) == 0;
 }
 template <typename... KArgs, typename... Args>
 static void launch_k_smem(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t st, Args&&... args) {
@@ -207,6 +216,7 @@ static b200collResult_t launch_ll(b200collComm* c, b200collOp_t op, const void* 
     Grid g = pick_grid(c, kShapeLL, nv, 1);
     const InT* in = static_cast<const InT*>(send); OutT* out = static_cast<OutT*>(recv);
     const bool mc = c->nvls;
+    struct PdlScope { PdlScope(bool v) { t_pdl_small = v; } ~PdlScope() { t_pdl_small = false; } } pdl_scope(count * sizeof(InT) <= pdl_max_bytes());
     switch (op) {
       case b200collOpAllReduce:
         if (mc) launch_k(k_ll<InT, OutT, false, true, true>, g.blocks, g.threads, st, c->dev, in, out, count, scale, op);

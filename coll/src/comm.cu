@@ -205,7 +205,9 @@ static void finalize_comm(b200collComm* c) {
   d.mc = c->nvls ? reinterpret_cast<char*>(c->mc_va) : nullptr;
   d.state = c->state_dev;
   d.fault = c->fault_dev;
-  d.mcbar = (c->nvls && env_long("B200COLL_MCBAR", 1) != 0) ? 1 : 0;
+  // one multimem.red per barrier instead of N flag stores + N polled flags: pays from 5 ranks up; at 2 ranks the detour through the
+  // switch costs ~1 us per kernel against two direct flag stores (profiles/latency_ab.md). B200COLL_MCBAR=0/1 forces it.
+  d.mcbar = (c->nvls && env_long("B200COLL_MCBAR", c->nranks >= 5 ? 1 : 0) != 0) ? 1 : 0;
   d.timeout_ns = c->cfg.timeout_ms == 0 ? ~0ull : (unsigned long long)c->cfg.timeout_ms * 1000000ull;   // 0 = no watchdog
   c->free_list.clear();
   c->free_list.push_back({kOffHeap, c->arena.total - kOffHeap});

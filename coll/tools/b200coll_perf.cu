@@ -298,6 +298,7 @@ static int run_rank(const Opts& o, RankCtx ctx, Shared* sh) {
     printf("# Out of bounds values : %ld %s\n", total_errors, total_errors ? "FAILED" : "OK");
     printf("# Avg bus bandwidth    : %g\n", busbw_n ? busbw_sum / busbw_n : 0.0);
     printf("# launches=%llu staged_calls=%llu errors=%ld\n", (unsigned long long)s.kernel_launches, (unsigned long long)s.staged_calls, total_errors);
+    fflush(stdout);      // --procs children leave through _exit(): nothing buffered survives it
   }
   CC(b200collMemFree(ctx.comm, recv));
   CC(b200collMemFree(ctx.comm, send));
