@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -161,12 +162,14 @@ static size_t bulk_min_bytes() {
   return v;
 }
 static b200collResult_t launch_bulk(b200collComm* c, BulkArgs& a, bool sync, b200collOp_t op, cudaStream_t st) {
-  static const bool attr_set = [] {
+  // the opt-in to 64 KiB of dynamic shared memory is per device (one process may drive several GPUs: InitAll, nccl-tests -g N)
+  static std::atomic<unsigned long long> attr_done{0};
+  const unsigned long long bit = 1ull << (c->device & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     cudaFuncSetAttribute(k_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes);
     cudaFuncSetAttribute(k_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes);
-    return true;
-  }();
-  (void)attr_set;
+    attr_done.fetch_or(bit, std::memory_order_release);
+  }
   a.chunk_prefix[0] = 0;
   for (int g = 0; g < a.nseg; g++) a.chunk_prefix[g + 1] = a.chunk_prefix[g] + (a.bytes[g] + kBulkChunk - 1) / kBulkChunk;
   for (int g = a.nseg + 1; g <= kMaxRanks; g++) a.chunk_prefix[g] = a.chunk_prefix[a.nseg];

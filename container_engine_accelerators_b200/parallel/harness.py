@@ -204,8 +204,9 @@ class NcclBackend:
         # NCCL's INFO log is evidence (rank count, algorithm, NVLS): keep it, but on stderr — stdout carries exactly one JSON line.
         if "B200_REF_NCCL_DEBUG" in os.environ:
             os.environ["NCCL_DEBUG"] = os.environ["B200_REF_NCCL_DEBUG"]
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):      # images often preset WARN: the rank count and the algorithm lines need INFO
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         saved = os.dup(1)
         os.dup2(2, 1)

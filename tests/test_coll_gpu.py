@@ -388,6 +388,10 @@ def test_multi_gpu_procs_nvls(torch_cuda, coll_lib):
         r = subprocess.run([PERF, "--devs", devs, "--procs", "--op", "all_reduce", "--algo", algo, "-b", "1K", "-e", "64M", "-f", "16", "--iters", "3", "--warmup", "1"],
                            capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
         assert r.returncode == 0 and "errors=0" in r.stdout, r.stdout + r.stderr
+    for op in ("all_gather", "alltoall", "broadcast"):     # one process driving every GPU (threads): the copy-engine kernel's shared-memory opt-in is per device
+        r = subprocess.run([PERF, "--devs", devs, "--op", op, "-b", "4M", "-e", "64M", "-f", "16", "--iters", "2", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
+        assert r.returncode == 0 and "errors=0" in r.stdout, r.stdout + r.stderr
     for op in ("broadcast", "reduce"):                     # multimem.st fan-out / multimem.ld_reduce by the root (N >= 3) or P2P (N == 2)
         r = subprocess.run([PERF, "--devs", devs, "--procs", "--op", op, "-b", "1K", "-e", "64M", "-f", "16", "--iters", "3", "--warmup", "1"],
                            capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "5000"})
