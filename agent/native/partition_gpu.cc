@@ -131,8 +131,11 @@ bool parse_lgi(const std::string& text, std::map<std::string, std::vector<std::s
   return true;
 }
 
+bool tolerated(const std::string& out);
+
 bool matches_desired(const Profile& want) {
   Result r = run({"mig", "-lgi"});
+  if (r.rc != 0 && tolerated(r.out)) { logi("No GPU instances exist yet (nvidia-smi mig -lgi: " + r.out.substr(0, r.out.find('\n')) + ")"); return false; }   // a real B200 in fresh MIG mode answers with a non-zero status
   if (r.rc != 0) { loge("failed to execute 'nvidia-smi mig -lgi'"); return false; }
   logi("Output:\n " + r.out);
   std::map<std::string, std::vector<std::string>> by_gpu;
