@@ -121,6 +121,7 @@ def main() -> int:
             "config": {"model": "none (collective benchmark: the reference has no model code)", "benchmark": f"{args.op}_perf", "sizes": f"{args.min}..{args.max} x2",
                        "global_batch": None, "seq_len": None, "parallelism": f"1 rank per GPU x{n}", "placements": "out-of-place + in-place",
                        "l2": "buffers rotate through a 192 MiB window (> 126 MB L2); sizes >= 192 MiB exceed L2 by themselves",
+                       "timed_region": "per size: host barrier + device synchronize, then a device-side rendezvous of all ranks' streams, then the first event; the same on both arms",
                        "aggregate": "nccl-tests bus bandwidth (per-link hardware rate), not multiplied by N",
                        "scaling_note": "bus bandwidth is normalised per GPU by construction: perfect scaling is a CONSTANT value from 2 to 8 GPUs (aggregate_bus_gbs = value x N is the whole-job rate); "
                                        "the 1-GPU value has no bus in it (an HBM copy with the fused epilogue) and is not a base for efficiency"},
@@ -149,7 +150,7 @@ def main() -> int:
                 json.dump({"impl": args.impl, "n_gpus": n, "backend": backend.version, "ops": extra}, f)
     backend.close()
     dist.close()
-    return 0 if verified else 3
+    return 0 if (verified or args.impl.startswith("reference")) else 3      # the reference arm's numerics are reported (verified_vs_torch_fp32), not enforced
 
 
 if __name__ == "__main__":

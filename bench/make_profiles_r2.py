@@ -144,7 +144,7 @@ def bench_tables():
         out += [f"## {n} x B200", "", f"| | ours | NCCL | NCCL sym |", "|---|---:|---:|---:|",
                 f"| value (avg busbw GB/s) | {o['value']} | {r['value']} | {s['value'] if s else ''} |",
                 f"| peak busbw GB/s | {o['peak_busbw']} | {r['peak_busbw']} | {s['peak_busbw'] if s else ''} |",
-                f"| e2e avg busbw GB/s | {o['e2e']['value']} | {r['e2e']['value']} | {s['e2e']['value'] if s else ''} |",
+                f"| e2e avg busbw GB/s | {o['e2e']['value']} | {r['e2e']['value']} | {(s.get('e2e') or {}).get('value', 'not run') if s else ''} |",
                 f"| verified (random bf16, 1 ulp of fp32 reference) | {o['verified_vs_torch_fp32']} | {r['verified_vs_torch_fp32']} | {s['verified_vs_torch_fp32'] if s else ''} |", "",
                 "| bytes | algo | ours us | NCCL us | NCCL sym us | ours / best NCCL | ours e2e us | NCCL e2e us | e2e ratio |", "|---:|---|---:|---:|---:|---:|---:|---:|---:|"]
         st = {x["bytes"]: x for x in (s["table"] if s else [])}
@@ -193,6 +193,42 @@ def ncu_ranks():
     open(os.path.join(P, "ncu_collectives.md"), "w").write("\n".join(out) + "\n")
 
 
+def other_ops():
+    out = ["# Every other collective at 8 x B200, both arms (round 2)", "",
+           "`bench.py --gpus 8 --steps 10 --warmup 3 --no-e2e --op all_gather --min 64K --extra-ops reduce_scatter,alltoall,broadcast,reduce,sendrecv,gather,scatter [--impl reference]`: "
+           "bf16, 64 KiB ... 1 GiB x2, out-of-place and in-place where the op has one, bus bandwidth by the nccl-tests factors (rooted ops and sendrecv: busbw = algbw). "
+           "`verified` = the op's result on pseudo-random data against a PyTorch fp32 reference (reductions within 1 bf16 ulp; NCCL's ring reductions round at every hop and miss that bound, "
+           "which is what `False` on its arm means — see `bench_r2.md`).", ""]
+    arms = {}
+    for impl in ("ours", "reference"):
+        try:
+            ag = bench(os.path.join(G, f"r2c5_n8_ops_ag_{impl}.json"))
+            ops = json.load(open(os.path.join(G, f"r2c5_n8_ops_{impl}.json")))["ops"]
+            ops = {"all_gather": {"avg_busbw": ag["value"], "peak_busbw": ag["peak_busbw"], "verified": ag["verified_vs_torch_fp32"], "table": ag["table"]}, **ops}
+            arms[impl] = ops
+        except Exception:
+            pass
+    if len(arms) == 2:
+        out += ["| op | ours avg / peak GB/s | NCCL avg / peak GB/s | ours / NCCL (avg) | verified ours / NCCL |", "|---|---:|---:|---:|---|"]
+        for op in arms["ours"]:
+            o, r = arms["ours"][op], arms["reference"].get(op)
+            if r:
+                out.append(f"| {op} | {o['avg_busbw']:.1f} / {o['peak_busbw']:.1f} | {r['avg_busbw']:.1f} / {r['peak_busbw']:.1f} | {o['avg_busbw'] / r['avg_busbw']:.2f} | {o['verified']} / {r['verified']} |")
+        out.append("")
+        for op in arms["ours"]:
+            o, r = arms["ours"][op], arms["reference"].get(op)
+            if not r:
+                continue
+            out += [f"## {op}", "", "| bytes | algo | ours us | busbw | NCCL us | busbw |", "|---:|---|---:|---:|---:|---:|"]
+            rt = {x["bytes"]: x for x in r["table"]}
+            for x in o["table"]:
+                y = rt.get(x["bytes"])
+                if y and x["bytes"] >= 1 << 20:
+                    out.append(f"| {size(x['bytes'])} | {x['algo']} | {x['oop_us']:.1f} | {x['oop_busbw']:.1f} | {y['oop_us']:.1f} | {y['oop_busbw']:.1f} |")
+            out.append("")
+    open(os.path.join(P, "other_ops_n8_r2.md"), "w").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
-    host_path(); latency_ab(); bench_tables(); ncu_ranks()
+    host_path(); latency_ab(); bench_tables(); ncu_ranks(); other_ops()
     print("profiles written")

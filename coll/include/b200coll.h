@@ -239,7 +239,7 @@ b200collResult_t b200collCommSetMaxCtas(b200collComm_t comm, int max_ctas);
 /* Receives into buffers outside the arena go through two staging windows per operation; this caps the window size (a multiple of
  * 512 bytes; 0 = an equal share of the 64 MiB staging area). A private choice of the receiver: the sender follows what is posted. */
 b200collResult_t b200collCommSetP2pWindow(b200collComm_t comm, size_t bytes);
-/* Launch shape per kernel family: kind 0 = NVLS all-reduce/all-gather, 1 = P2P pull/push kernels, 2 = LL, 3 = NVLS reduce-scatter.
+/* Launch shape per kernel family: kind 0 = NVLS all-reduce/all-gather, 1 = P2P pull/push kernels, 2 = LL, 3 = NVLS reduce-scatter, 4 = NVLS broadcast / reduce (root only).
  * max_ctas <= 0 keeps the current cap; threads == 0 lets the library pick {128,256,512} by work size.
  * Defaults come from the 8xB200 sweep in profiles/ (NVLS wants few CTAs: 32 x 256 threads). */
 b200collResult_t b200collCommSetLaunchShape(b200collComm_t comm, int kind, int max_ctas, int threads);

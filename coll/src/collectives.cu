@@ -103,7 +103,7 @@ static void launch_k(void (*kernel)(KArgs...), int blocks, int threads, cudaStre
 
 // Pick the smallest block size that still covers `vecs` with <= max_ctas blocks (small work spreads over more SMs),
 // unless the family's shape pins the thread count.
-enum { kShapeNvls = 0, kShapeP2p = 1, kShapeLL = 2, kShapeNvlsRs = 3 };
+enum { kShapeNvls = 0, kShapeP2p = 1, kShapeLL = 2, kShapeNvlsRs = 3, kShapeRooted = 4 };
 static Grid pick_grid(const b200collComm* c, int kind, size_t vecs, int unroll) {
   static const int forced = [] { const char* e = getenv("B200COLL_FORCE_THREADS"); return e ? atoi(e) : 0; }();
   const int max_ctas = std::max(1, std::min(c->shape[kind].max_ctas > 0 ? c->shape[kind].max_ctas : c->max_ctas, c->max_ctas));
@@ -720,7 +720,7 @@ b200collResult_t b200collBroadcast(const void* send, void* recv, size_t count, c
     account(c, b200collOpBroadcast, n * is, algo);
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvls : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), 4);
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeRooted : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), 4);
       if (algo == b200collAlgoNvls) launch_k(k_bcast<InT, OutT, true>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(s), arena_off(c, r_sym), n, scale, identity, root, b200collOpBroadcast);
       else launch_k(k_bcast<InT, OutT, false>, g.blocks, g.threads, st, c->dev, static_cast<const InT*>(s), arena_off(c, r_sym), n, scale, identity, root, b200collOpBroadcast);
       LAUNCH_CHECK(c);
@@ -770,7 +770,7 @@ b200collResult_t b200collReduce(const void* send, void* recv, size_t count, cons
     account(c, b200collOpReduce, n * is, algo);
     return dispatch_types(ep->in_dtype, ep->out_dtype, [&](auto ti, auto to) -> b200collResult_t {
       using InT = typename decltype(ti)::type; using OutT = typename decltype(to)::type;
-      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeNvlsRs : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), 2);
+      Grid g = pick_grid(c, algo == b200collAlgoNvls ? kShapeRooted : kShapeP2p, std::max<size_t>(1, n / Epv<InT>::value), algo == b200collAlgoNvls ? 4 : 2);
       if (algo == b200collAlgoNvls) launch_k(k_reduce_root<InT, OutT, true>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, root, b200collOpReduce);
       else launch_k(k_reduce_root<InT, OutT, false>, g.blocks, g.threads, st, c->dev, arena_off(c, s_sym), static_cast<OutT*>(r), n, scale, root, b200collOpReduce);
       LAUNCH_CHECK(c);

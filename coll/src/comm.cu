@@ -205,9 +205,10 @@ static void finalize_comm(b200collComm* c) {
   d.mc = c->nvls ? reinterpret_cast<char*>(c->mc_va) : nullptr;
   d.state = c->state_dev;
   d.fault = c->fault_dev;
-  // one multimem.red per barrier instead of N flag stores + N polled flags: pays from 5 ranks up; at 2 ranks the detour through the
-  // switch costs ~1 us per kernel against two direct flag stores (profiles/latency_ab.md). B200COLL_MCBAR=0/1 forces it.
-  d.mcbar = (c->nvls && env_long("B200COLL_MCBAR", c->nranks >= 5 ? 1 : 0) != 0) ? 1 : 0;
+  // one multimem.red per barrier instead of N flag stores + N polled flags. Measured (profiles/latency_ab.md): ~1 us SLOWER per kernel at
+  // 2 ranks (a detour through the switch against two direct stores) and no faster at 8 (6.12 vs 6.15 us at 1 KiB, 23.5 vs 23.2 at 4 MiB):
+  // the barrier is bound by the NVLink round trip, not by the number of flag stores. Off unless B200COLL_MCBAR=1.
+  d.mcbar = (c->nvls && env_long("B200COLL_MCBAR", 0) != 0) ? 1 : 0;
   d.timeout_ns = c->cfg.timeout_ms == 0 ? ~0ull : (unsigned long long)c->cfg.timeout_ms * 1000000ull;   // 0 = no watchdog
   c->free_list.clear();
   c->free_list.push_back({kOffHeap, c->arena.total - kOffHeap});
@@ -223,6 +224,8 @@ static void finalize_comm(b200collComm* c) {
   c->shape[1].threads = (int)env_long("B200COLL_P2P_THREADS", 0);
   c->shape[2].max_ctas = std::min(c->shape[2].max_ctas, c->max_ctas);
   c->shape[3].max_ctas = std::min(c->shape[3].max_ctas, c->max_ctas);
+  c->shape[4].max_ctas = std::min<int>((int)env_long("B200COLL_ROOTED_CTAS", c->shape[4].max_ctas), c->max_ctas);
+  c->shape[4].threads = (int)env_long("B200COLL_ROOTED_THREADS", c->shape[4].threads);
   const char* fa = getenv("B200COLL_ALGO");
   if (fa && *fa) {
     for (int a = 0; a < b200collNumAlgos; a++) if (!strcasecmp(fa, b200collAlgoName((b200collAlgo_t)a))) c->forced_algo = (b200collAlgo_t)a;
@@ -694,7 +697,7 @@ b200collResult_t b200collCommSetP2pWindow(b200collComm_t c, size_t bytes) {
 }
 
 b200collResult_t b200collCommSetLaunchShape(b200collComm_t c, int kind, int max_ctas, int threads) {
-  if (!c || kind < 0 || kind > 3) return b200collInvalidArgument;
+  if (!c || kind < 0 || kind > 4) return b200collInvalidArgument;
   if (threads != 0 && (threads < 32 || threads > 512 || threads % 32)) return b200collInvalidArgument;
   if (max_ctas > 0) c->shape[kind].max_ctas = std::min(max_ctas, kMaxBlocks);
   c->shape[kind].threads = threads;

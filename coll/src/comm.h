@@ -88,7 +88,7 @@ struct b200collComm {
   // NVLS all-reduce/all-gather, P2P, LL, NVLS reduce-scatter. Measured on 8xB200 (profiles/launch_shapes_n8.md): the
   // multimem all-reduce saturates with 16-64 CTAs x 256 threads and degrades above ~100 CTAs; the ld_reduce-only
   // reduce-scatter kernel (2 loads in flight per thread) needs 64 x 512.
-  struct Shape { int max_ctas; int threads; } shape[4] = {{32, 256}, {0, 0}, {148, 0}, {64, 512}};
+  struct Shape { int max_ctas; int threads; } shape[5] = {{32, 256}, {0, 0}, {148, 0}, {64, 512}, {148, 512}};   // [4]: rooted NVLS ops — only the root moves data, so ONE rank must keep the link busy: 148 x 512 threads x 2-4 vectors = 2.4-4.8 MB in flight (at 32 x 256 the 8-GPU broadcast stopped at 372 GB/s, NCCL 655)
   b200collStats stats{};
   std::shared_ptr<b200coll::SharedGroup> group;
   void* stats_shm = nullptr;       // exported stats page (metrics exporter reads it)

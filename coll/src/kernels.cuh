@@ -630,7 +630,7 @@ template <typename InT, typename OutT, bool MC>
 __global__ void __launch_bounds__(kThreads) k_reduce_root(COMM_PARAM, size_t in_off, OutT* __restrict__ out, size_t count, float scale, int root, uint32_t op) {
   pdl_prologue();
   constexpr int E = Epv<InT>::value;
-  constexpr int U = 2;
+  constexpr int U = MC ? 4 : 2;      // the root alone must keep the link busy: four ld_reduce vectors in flight per thread on the NVLS path
   const uint32_t s = load_seq(c, kSeqBarrier);
   if (!barrier_blocks<false>(c, 2 * s + 1, op)) return;
   if (c.rank == root) {

@@ -488,7 +488,7 @@ class Comm:
         _check(load().b200collCommSetP2pWindow(self._h, nbytes), "CommSetP2pWindow")
 
     def set_launch_shape(self, kind: str, max_ctas: int = 0, threads: int = 0) -> None:
-        _check(load().b200collCommSetLaunchShape(self._h, {"nvls": 0, "p2p": 1, "ll": 2, "nvls_rs": 3}[kind], max_ctas, threads), "CommSetLaunchShape")
+        _check(load().b200collCommSetLaunchShape(self._h, {"nvls": 0, "p2p": 1, "ll": 2, "nvls_rs": 3, "rooted": 4}[kind], max_ctas, threads), "CommSetLaunchShape")
 
     def stats(self) -> dict:
         s = Stats()

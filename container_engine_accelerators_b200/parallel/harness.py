@@ -162,6 +162,12 @@ class OursBackend:
     def launches(self) -> int:
         return int(self.comm.stats()["kernel_launches"])
 
+    def device_rendezvous(self, stream) -> None:
+        """Every rank's stream meets every other rank's on the device (k_barrier): the timed region that follows starts at the same moment
+        everywhere, so the microseconds by which ranks leave the host barrier apart are not charged to the first timed call."""
+        if self.comm.nranks > 1:
+            self.comm.barrier(stream)
+
     def host_buffers(self, in_elems: int, out_elems: int, dtype):
         # pinned host memory on the NUMA node of this rank's GPU (b200collHostAlloc): part of the library's public API
         return self.comm.host_empty(in_elems, dtype), self.comm.host_empty(out_elems, dtype)
@@ -191,6 +197,9 @@ def _copy_launch_copy(backend, op: str, h_in, h_out, count: int, dev_off: int, s
 
 class NcclBackend:
     name = "nccl"
+    # NCCL's ring / tree kernels round the running sum to bf16 at every hop (measured: its 8-GPU all-reduce, reduce-scatter and reduce
+    # miss the 1-ulp bound that an fp32-accumulated reduction meets), so the reference arm is held to one ulp per rank instead.
+    verify_ulps = 8.0
 
     def __init__(self, dist: Dist, capacity_elems: int, dtype):
         import torch
@@ -260,6 +269,12 @@ class NcclBackend:
     def launches(self) -> int:
         return 0   # NCCL's kernels are not ours
 
+    def device_rendezvous(self, stream) -> None:
+        if self.comm.nranks > 1:      # the same alignment for the NCCL arm: a one-vector all-reduce on a private scratch buffer
+            if not hasattr(self, "_sync_buf"):
+                self._sync_buf = self.torch.zeros(8, dtype=self.torch.float32, device="cuda")
+            self.comm.all_reduce(self._sync_buf.data_ptr(), self._sync_buf.data_ptr(), 8, 7, stream.cuda_stream)      # 7 = ncclFloat32
+
     def host_buffers(self, in_elems: int, out_elems: int, dtype):
         return self.torch.empty(in_elems, dtype=dtype).pin_memory(), self.torch.empty(out_elems, dtype=dtype).pin_memory()
 
@@ -293,14 +308,14 @@ def bf16_ulp(torch, x):
     return torch.exp2(e - 7)
 
 
-def reduction_ok(torch, got32, want32, out_dtype, nranks: int, max_abs_in: float = 4.0):
+def reduction_ok(torch, got32, want32, out_dtype, nranks: int, max_abs_in: float = 4.0, ulps: float = 1.0):
     """got32 (the kernel's output widened to fp32) must lie within ONE ulp of the output type around the fp32-accumulated reference:
     a correctly rounded fp32 accumulation lands within half an ulp whatever the summation order; accumulating in bf16 / fp16 (e.g. a
     multimem.ld_reduce without .acc::f32) is off by several ulps on a large share of the elements and fails. The absolute slack covers
     fp32 reassociation when a sum cancels to almost nothing."""
     err = (got32 - want32).abs()
     ulp = bf16_ulp(torch, want32) if out_dtype == torch.bfloat16 else (want32.abs() * 2.0 ** -10 if out_dtype == torch.float16 else want32.abs() * 2.0 ** -22)
-    tol = ulp + nranks * max_abs_in * 2.0 ** -22
+    tol = ulps * ulp + nranks * max_abs_in * 2.0 ** -22
     return bool((err <= tol).all().item())
 
 
@@ -365,7 +380,7 @@ def _verify_one(backend, dist: Dist, op: str, dtype, count: int) -> bool:
         j = torch.arange(count, device=dev) + rank * count
         want = torch.cat([gen(r, j) for r in range(n)])
     if reduced and n > 1:
-        return reduction_ok(torch, got, want, dtype, n)
+        return reduction_ok(torch, got, want, dtype, n, ulps=getattr(backend, "verify_ulps", 1.0))
     return bool(torch.equal(got, want.to(dtype).float()))
 
 
@@ -388,7 +403,7 @@ def verify_e2e(backend, dist: Dist, dtype) -> bool:
         backend.check()
         want = sum(gen(r, idx) for r in range(n))
         got = h_out[:count].float()
-        ok = ok and (reduction_ok(torch, got, want, dtype, n) if n > 1 else bool(torch.equal(got, want.to(dtype).float())))
+        ok = ok and (reduction_ok(torch, got, want, dtype, n, ulps=getattr(backend, "verify_ulps", 1.0)) if n > 1 else bool(torch.equal(got, want.to(dtype).float())))
     return dist.sum_([1.0 if ok else 0.0])[0] == dist.world
 
 
@@ -450,6 +465,7 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
                 s, r = ptrs(i % slots)
                 backend.launch(op, s, r, count, st)
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            backend.device_rendezvous(stream)
             e0.record(stream)
             for i in range(steps):
                 s, r = ptrs(i % slots)
@@ -464,6 +480,7 @@ def sweep(backend, dist: Dist, op: str, dtype, steps: int, warmup: int, min_byte
             for i in range(min(warmup, 2)):
                 backend.e2e_step(op, h_in, h_out, count, 0, stream)
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            backend.device_rendezvous(stream)
             e0.record(stream)
             for i in range(steps):
                 backend.e2e_step(op, h_in, h_out, count, (i % slots) * slot_elems, stream)
