@@ -21,12 +21,21 @@ sys.path.insert(0, ROOT)
 BUILD = os.path.join(ROOT, "build")
 
 
+def _minors():
+    return sorted(int(m.group(1)) for m in (re.fullmatch(r"nvidia(\d+)", f) for f in os.listdir("/dev")) if m)
+
+
 @pytest.fixture(scope="module")
 def gpu_count():
     import torch
-    if not torch.cuda.is_available() or not os.path.exists("/dev/nvidia0"):
-        pytest.skip("no CUDA device / no /dev/nvidia0")
+    if not torch.cuda.is_available() or not _minors():
+        pytest.skip("no CUDA device / no /dev/nvidia<N>")
     return torch.cuda.device_count()
+
+
+def _first_gpu() -> str:
+    """The plugin names devices after their /dev node; a one-GPU lease of an eight-GPU host may expose /dev/nvidia5 only."""
+    return f"nvidia{_minors()[0]}"
 
 
 def _busy(seconds: float) -> None:
@@ -82,13 +91,13 @@ def test_device_plugin_serves_the_real_gpus_to_a_stub_kubelet(gpu_count, impl):
         assert (reg.version, reg.resource_name) == ("v1beta1", "nvidia.com/gpu")
         c = n.connect()
         stream, devs = conf.first_list(c)
-        minors = sorted(int(m.group(1)) for m in (re.fullmatch(r"nvidia(\d+)", f) for f in os.listdir("/dev")) if m)
-        assert set(devs) == {f"nvidia{i}" for i in minors} and all(d.health == "Healthy" for d in devs.values()), devs
-        topo = [x.ID for x in devs["nvidia0"].topology.nodes]
+        assert set(devs) == {f"nvidia{i}" for i in _minors()} and all(d.health == "Healthy" for d in devs.values()), devs
+        gpu = _first_gpu()
+        topo = [x.ID for x in devs[gpu].topology.nodes]
         assert topo in ([], [0], [1], [2], [3])                 # the NUMA node sysfs reports for the GPU's PCI function (absent on single-node hosts)
-        cr = c.allocate(["nvidia0"]).container_responses[0]
+        cr = c.allocate([gpu]).container_responses[0]
         paths = [d.host_path for d in cr.devices]
-        assert paths[0] == "/dev/nvidia0" and "/dev/nvidiactl" in paths and "/dev/nvidia-uvm" in paths
+        assert paths[0] == f"/dev/{gpu}" and "/dev/nvidiactl" in paths and "/dev/nvidia-uvm" in paths
         assert all(os.path.exists(p) for p in paths), paths      # only device nodes that exist on this host are handed to the container
         assert all(d.permissions == "mrw" for d in cr.devices) and len(cr.mounts) == 2
         conf.expect_error(lambda: c.allocate(["nvidia99"]), "non-existing device nvidia99")
@@ -135,7 +144,8 @@ def test_real_xid_marks_the_device_unhealthy(gpu_count):
     try:
         c = n.connect()
         stream, devs = conf.first_list(c)
-        assert devs["nvidia0"].health == "Healthy"
+        gpu = _first_gpu()
+        assert devs[gpu].health == "Healthy"
         time.sleep(2.0)                                           # the health loop registers for events after the first list is out
         r = subprocess.run([inject, "--mode", "oob-store"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "fault raised as expected" in r.stderr, r.stdout + r.stderr
@@ -146,7 +156,7 @@ def test_real_xid_marks_the_device_unhealthy(gpu_count):
             try:
                 for resp in stream:
                     health = {d.ID: d.health for d in resp.devices}
-                    if health.get("nvidia0") == "Unhealthy":
+                    if health.get(gpu) == "Unhealthy":
                         got["health"] = health
                         return
             except Exception as e:      # stream cancelled at the end of the test
@@ -158,9 +168,9 @@ def test_real_xid_marks_the_device_unhealthy(gpu_count):
             log = n.logs()
             if "Xid" not in log and "xid" not in log:
                 pytest.skip("this container does not receive NVML Xid events for the fault (no event in 30 s); plugin log:\n" + log[-1500:])
-            raise AssertionError("the plugin saw an Xid but never reported nvidia0 Unhealthy:\n" + log[-3000:])
-        assert got["health"]["nvidia0"] == "Unhealthy"
-        conf.expect_error(lambda: c.allocate(["nvidia0"]), "unhealthy device nvidia0")
+            raise AssertionError(f"the plugin saw an Xid but never reported {gpu} Unhealthy:\n" + log[-3000:])
+        assert got["health"][gpu] == "Unhealthy"
+        conf.expect_error(lambda: c.allocate([gpu]), f"unhealthy device {gpu}")
         stream.cancel()
     finally:
         n.close()
