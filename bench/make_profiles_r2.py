@@ -133,7 +133,7 @@ def bench_tables():
     out = ["# bench.py, round 2: ours vs stock NCCL (defaults) vs stock NCCL on ncclMemAlloc + symmetric windows", "",
            "`python -m torch.distributed.run ... bench.py --gpus N --steps 10 --warmup 3 [--impl reference | reference-sym]`; bf16 sum all-reduce, out-of-place us (device-timed, max over ranks) "
            "and the end-to-end step (pinned host in, the whole result back in pinned host memory; ours: one `Comm.all_reduce_host` call, NCCL: copy, ncclAllReduce, copy).", ""]
-    for n, pat in ((1, "r2c4_bench_{}.json"), (2, "r2c3_n2_bench_{}.json"), (4, "r2c5_n4_bench_{}.json"), (8, "r2c5_n8_bench_{}.json")):
+    for n, pat in ((1, "r2c4_bench_{}.json"), (2, "r2c3_n2_bench_{}.json"), (4, "r2c5_n4_bench_{}.json"), (8, "r2c5_n8_bench_{}.json"), ("8 (final tree: device-side rendezvous before the timed region, --steps 20 --warmup 5)", "r2c7_n8_bench_{}.json")):
         arms = {a: bench(os.path.join(G, pat.format(a))) for a in ("ours", "reference", "reference-sym", "ref")}
         arms = {k: v for k, v in arms.items() if v}
         if "ref" in arms:
