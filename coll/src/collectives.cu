@@ -308,7 +308,7 @@ thread_local std::string* g_p2p_dry = nullptr;     // b200collDebugPlanP2p: desc
 // meets CTA j of the matching recv. Virtual ranks share one GPU's SMs between all their kernels: keep them small.
 int p2p_blocks(const b200collComm* c, size_t bytes) {
   static const int env_max = [] { const char* e = getenv("B200COLL_P2P_MAX_BLOCKS"); return e ? atoi(e) : 0; }();
-  int cap = c->loopback ? 2 : 16;                 // default until the 8-GPU sweep says otherwise (bench/run_next8.sh tries 8 / 16 / 32)
+  int cap = c->loopback ? 2 : 16;                 // 16 CTAs per operation: sendrecv at 8 GPUs reaches 647 GB/s with it (profiles/other_ops_n8_r2.md); B200COLL_P2P_MAX_BLOCKS overrides
   if (env_max >= 1 && env_max <= kP2pMaxBlocks) cap = env_max;
   const size_t want = (bytes + (128u << 10) - 1) / (128u << 10);
   return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)cap));

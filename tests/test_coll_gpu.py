@@ -623,6 +623,21 @@ def test_nccl_api_shim_collectives(torch_cuda, coll_lib):
             L.ncclCommDestroy(c)
 
 
+def test_unmodified_nccl_program_runs_on_the_shim(torch_cuda, coll_lib):
+    """coll/tests/nccl_client.c includes the SYSTEM's <nccl.h> and speaks only the NCCL C API (ncclCommInitAll, grouped per-device
+    calls like nccl-tests in one-process mode): int32 max / sum, int64 sum, uint8 min, float sum / prod, double max, broadcast,
+    all-gather, a send/recv ring. Linked against libb200coll_nccl.so it must pass its own host-side checks (the drop-in claim of the
+    transport installer, reference: gpudirect-tcpx/nccl-config.yaml:22,61 — the benchmark binary is whatever NCCL program the pod runs)."""
+    client = os.path.join(ROOT, "build", "nccl_client")
+    if not os.path.exists(client):
+        pytest.skip("build/nccl_client not built (no system nccl.h)")
+    n = torch_cuda.cuda.device_count()
+    args = [client, "2"] if n >= 2 else [client, "2", "--same-device"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=180, env={**os.environ, "B200COLL_TIMEOUT_MS": "8000", "B200COLL_ARENA_MB": "256"})
+    assert r.returncode == 0 and "all checks passed" in r.stdout and "WRONG" not in r.stdout, r.stdout + r.stderr
+    assert r.stdout.count(" ok") >= 10
+
+
 # ------------------------------------------------------------------------------------------------- point to point
 
 
