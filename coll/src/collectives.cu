@@ -1,6 +1,7 @@
 // libb200coll collective entry points: argument validation, algorithm choice (tuner table +
 // feasibility), staging for buffers outside the symmetric arena, type dispatch, kernel launch.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <atomic>
@@ -148,6 +149,31 @@ static void account(b200collComm* c, b200collOp_t op, size_t bytes, b200collAlgo
     if (nvtx) nvtxMarkA(msg);
     dbg(2, "rank %d: %s", c->rank, msg);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ symmetry cross-check (debug)
+// The zero-copy paths address peers by MY arena offset and pick the algorithm from MY view of the buffers: ranks that pass different
+// offsets (allocation order drifted), counts or placements would read and write wrong peer addresses or run different kernels with
+// different barrier counts. B200COLL_CHECK=1 compares (op, algorithm, count, offsets) across ranks over the bootstrap channel before
+// every such launch and fails the call with InvalidUsage instead (host-synchronous, multi-process communicators only: a debugging aid).
+static b200collResult_t cross_check(b200collComm* c, b200collOp_t op, b200collAlgo_t algo, size_t count, size_t off_a, size_t off_b) {
+  static const bool on = [] { const char* e = getenv("B200COLL_CHECK"); return e && *e && *e != '0'; }();
+  if (!on || !c->boot || c->nranks == 1) return b200collSuccess;
+  struct Sig { unsigned long long op, algo, count, a, b; } mine = {(unsigned long long)op, (unsigned long long)algo, count, off_a, off_b};
+  std::vector<char> all;
+  const std::string e = c->boot->allgather(&mine, sizeof(mine), &all);
+  if (!e.empty()) { set_last_error("cross-check: bootstrap: " + e); return b200collSystemError; }
+  for (int r = 0; r < c->nranks; r++) {
+    Sig s; memcpy(&s, all.data() + (size_t)r * sizeof(Sig), sizeof(Sig));
+    if (memcmp(&s, &mine, sizeof(Sig)) != 0) {
+      char msg[256];
+      snprintf(msg, sizeof msg, "ranks disagree on a symmetric collective: rank %d has (op %llu, algo %s, count %llu, offsets %llu / %llu), rank %d has (op %llu, algo %s, count %llu, offsets %llu / %llu)",
+               c->rank, mine.op, b200collAlgoName((b200collAlgo_t)mine.algo), mine.count, mine.a, mine.b, r, s.op, b200collAlgoName((b200collAlgo_t)s.algo), s.count, s.a, s.b);
+      set_last_error(msg);
+      return b200collInvalidUsage;
+    }
+  }
+  return b200collSuccess;
 }
 
 // ------------------------------------------------------------------------------------------------ copy-engine path (k_bulk)
@@ -477,7 +503,12 @@ b200collResult_t b200collAllReduce(const void* send, void* recv, size_t count, c
   }
   if (algo == b200collAlgoLL) { account(c, b200collOpAllReduce, bytes, algo); return launch_ll(c, b200collOpAllReduce, send, recv, count, ep, scale, st); }
   if (algo == b200collAlgoLL2) { account(c, b200collOpAllReduce, bytes, algo); return launch_ll2(c, send, recv, count, ep, scale, st); }
-  if (algo != b200collAlgoAuto) { account(c, b200collOpAllReduce, bytes, algo); return ar_symmetric(c, algo, send, recv, count, ep, scale, st); }
+  if (algo != b200collAlgoAuto) {
+    rc = cross_check(c, b200collOpAllReduce, algo, count, arena_off(c, send), arena_off(c, recv));
+    if (rc != b200collSuccess) return rc;
+    account(c, b200collOpAllReduce, bytes, algo);
+    return ar_symmetric(c, algo, send, recv, count, ep, scale, st);
+  }
   // ---- staged: buffers outside the arena and too big for LL. Chunk through the two staging halves.
   c->stats.staged_calls++;
   b200collAlgo_t inner = (c->nvls && c->nranks > 2) ? b200collAlgoNvls : b200collAlgoTwoShot;
@@ -524,6 +555,10 @@ b200collResult_t b200collAllGather(const void* send, void* recv, size_t sendcoun
       return b200collSuccess;
     });
   };
+  if (sym_out) {
+    rc = cross_check(c, b200collOpAllGather, algo, sendcount, arena_off(c, recv), 0);
+    if (rc != b200collSuccess) return rc;
+  }
   if (bulk_enabled() && sym_out && identity && bytes >= bulk_min_bytes() && bytes % 16 == 0 && algo != b200collAlgoNvls) {     // copy-engine push (kernels.cuh k_bulk)
     account(c, b200collOpAllGather, bytes, algo);
     BulkArgs a = {};
@@ -577,7 +612,11 @@ b200collResult_t b200collReduceScatter(const void* send, void* recv, size_t recv
       return b200collSuccess;
     });
   };
-  if (sym_in) return pull(static_cast<const char*>(send) + (size_t)c->rank * bytes, recv, recvcount);
+  if (sym_in) {
+    rc = cross_check(c, b200collOpReduceScatter, algo, recvcount, arena_off(c, send), 0);
+    if (rc != b200collSuccess) return rc;
+    return pull(static_cast<const char*>(send) + (size_t)c->rank * bytes, recv, recvcount);
+  }
   // staged: copy chunk j of every slice into staging half 0 laid out [nranks][chunk]; each rank pulls its row
   c->stats.staged_calls++;
   const size_t chunk = (kStageHalfBytes / is / c->nranks) / 64 * 64;
@@ -642,6 +681,10 @@ b200collResult_t b200collAllToAll(const void* send, void* recv, size_t count, co
     account(c, b200collOpAllToAll, n * is * c->nranks, algo);
     return a2av_launch(c, s, r_sym, a, ep, st, true);
   };
+  if (sym_out) {
+    rc = cross_check(c, b200collOpAllToAll, algo, count, arena_off(c, recv), 0);
+    if (rc != b200collSuccess) return rc;
+  }
   if (bulk_enabled() && sym_out && is == os && ep->in_dtype == ep->out_dtype && ep->scale == 1.0f && bytes * c->nranks >= bulk_min_bytes() && bytes % 16 == 0) {
     account(c, b200collOpAllToAll, bytes * c->nranks, algo);
     BulkArgs a = {};

@@ -177,8 +177,13 @@ def _gpu_pair(rank, world):
     base = torch.arange(4 * 64, device="cuda", dtype=torch.float32).view(4, 64)
     want = torch.cat([base[0:1], base[0:2] + 1000]) if rank == 0 else torch.cat([base[1:4], base[2:4] + 1000])
     assert torch.equal(dst, want)
-    cnt = torch.tensor([rank], device="cuda"); dist.all_reduce(cnt, op=dist.ReduceOp.MAX)      # integer max: Gloo fallback from a CUDA tensor
-    assert cnt.item() == 1
+    fb = pg.fallback_calls
+    cnt = torch.tensor([rank], device="cuda"); dist.all_reduce(cnt, op=dist.ReduceOp.MAX)      # integer max: the library's generic reduction kernel, not Gloo
+    assert cnt.item() == 1 and pg.fallback_calls == fb
+    steps = torch.tensor([3 + rank, 10 - rank, 7], device="cuda", dtype=torch.int32); dist.all_reduce(steps, op=dist.ReduceOp.MIN)
+    assert steps.tolist() == [3, 9, 7] and pg.fallback_calls == fb
+    prod = torch.full((1000,), 1.5 + rank, device="cuda", dtype=torch.float64); dist.all_reduce(prod, op=dist.ReduceOp.PRODUCT)
+    assert torch.equal(prod, torch.full_like(prod, 1.5 * 2.5)) and pg.fallback_calls == fb
     model = torch.nn.Linear(32, 32).cuda()
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[0])
     torch.manual_seed(rank); ddp(torch.randn(8, 32, device="cuda")).sum().backward()
