@@ -408,6 +408,10 @@ def test_bench_contract_one_gpu(torch_cuda):
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
         assert k in d
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["e2e"]["d2h_bytes_per_step"] == d["e2e"]["h2d_bytes_per_step"]          # the whole result comes back, not a sample of it
+    assert d["verified_vs_torch_fp32"] is True and d["e2e"]["verified_vs_torch_fp32"] is True
+    assert len(d["e2e"]["table"]) == len(d["table"]) and all(r["e2e_us"] > 0 for r in d["e2e"]["table"])      # per-size end-to-end rows are published
+    assert d["impl"] == "ours" and d["backend"].startswith("libb200coll") and "backend" not in d["config"]   # config is identical on both arms
 
 
 

@@ -57,7 +57,9 @@ def test_native_nvml_binding_on_the_installed_driver(gpu_count):
         n = nvml.NativeNvml()
         n.init()
         assert n.device_count() >= gpu_count >= 1
-        d = n.device(0)
+        minors = _minors()
+        d = next((x for x in (n.device(i) for i in range(n.device_count())) if x.minor in minors), None)     # NVML may list GPUs this container has no node for
+        assert d is not None, "no NVML device matches a /dev/nvidia<N> node"
         assert "B200" in d.name and d.uuid.startswith("GPU-") and re.fullmatch(r"[0-9A-Fa-f]{8}:[0-9A-Fa-f]{2}:[0-9A-Fa-f]{2}\.[0-9]", d.bus_id), d
         assert 170 << 30 < d.mem_total < 200 << 30 and d.minor >= 0 and os.path.exists(f"/dev/nvidia{d.minor}")
         assert re.match(r"\d+\.\d+", n.driver_version())
@@ -73,7 +75,7 @@ def test_native_nvml_binding_on_the_installed_driver(gpu_count):
         with pytest.raises(nvml.NvmlError):                    # a window with no samples is an error code (the reference's cgo helper divided by zero here)
             n.average_usage(d.uuid, int((time.time() + 3600) * 1e6))
         h = n.events_open()
-        assert n.events_register(h, 0) is True                  # a B200 supports Xid events
+        assert n.events_register(h, d.index) is True            # a B200 supports Xid events
         assert n.events_wait(h, 200) is None                    # nothing is wrong: timeout, not an error
         n.events_close(h)
         n.shutdown()
