@@ -95,9 +95,14 @@ def _sum_or_avg(op) -> Optional[int]:
 
 
 def _red_op(op) -> Optional[int]:
-    """Every reduction libb200coll implements (sum / avg fused fast paths; min / max / product on the generic kernel)."""
-    return {dist.ReduceOp.SUM: coll.SUM, dist.ReduceOp.AVG: coll.AVG, dist.ReduceOp.MIN: coll.MIN, dist.ReduceOp.MAX: coll.MAX,
-            dist.ReduceOp.PRODUCT: coll.PROD}.get(op)
+    """Every reduction libb200coll implements (sum / avg fused fast paths; min / max / product on the generic kernel).
+    Compared with ==, not looked up in a dict: the option structs carry a `ReduceOp` object, which equals the `ReduceOp.SUM`
+    constants but does not hash like them."""
+    for theirs, ours in ((dist.ReduceOp.SUM, coll.SUM), (dist.ReduceOp.AVG, coll.AVG), (dist.ReduceOp.MIN, coll.MIN), (dist.ReduceOp.MAX, coll.MAX),
+                         (dist.ReduceOp.PRODUCT, coll.PROD)):
+        if op == theirs:
+            return ours
+    return None
 
 
 def _reducible(t: torch.Tensor, op: Optional[int]) -> bool:

@@ -143,6 +143,17 @@ def test_sub_groups_are_independent_process_groups():
     _run(_subgroups, 4)
 
 
+def test_reduce_ops_of_option_structs_map_to_library_operators():
+    """The ReduceOp inside an options struct equals the ReduceOp.SUM constants but does not hash like them: the mapping must use ==
+    (a dict lookup silently sent every all-reduce to the Gloo fallback)."""
+    o = dist.AllreduceOptions()
+    want = {"SUM": pgmod.coll.SUM, "AVG": pgmod.coll.AVG, "MIN": pgmod.coll.MIN, "MAX": pgmod.coll.MAX, "PRODUCT": pgmod.coll.PROD, "BAND": None}
+    for name, ours in want.items():
+        o.reduceOp = getattr(dist.ReduceOp, name)
+        assert pgmod._red_op(o.reduceOp) == ours, name
+        assert pgmod._red_op(getattr(dist.ReduceOp, name)) == ours, name
+
+
 def test_alltoallv_layout():
     m = [[1, 2, 0], [0, 3, 4], [5, 0, 6]]                                   # m[src][dst]
     assert pgmod.alltoallv_layout(m, 0) == ([1, 2, 0], [0, 1, 3], [0, 0, 0], 10)
