@@ -682,13 +682,13 @@ std::string g_coll_stats_dir = "/dev/shm";
 void append_coll_stats(std::ostringstream& os) {
   static const char* kOps[] = {"all_reduce", "all_gather", "reduce_scatter", "alltoall", "broadcast", "reduce"};
   static const char* kAlgos[] = {"auto", "ll", "oneshot", "twoshot", "nvls", "copy", "ll2"};
-  struct Page { uint32_t pid, rank; uint64_t calls[6], bytes[6], algo[7], p2p[3]; };
+  struct Page { uint32_t pid, rank; uint64_t calls[6], bytes[6], algo[7], p2p[3], ext[6]; };   // ext: host calls / bytes / zero-copy / pipelined, bulk launches, generic launches
   std::vector<Page> pages;
   if (DIR* d = opendir(g_coll_stats_dir.c_str())) {
     while (dirent* e = readdir(d)) {
       if (strncmp(e->d_name, "b200coll.", 9) != 0) continue;
       std::ifstream f(join(g_coll_stats_dir, e->d_name), std::ios::binary);
-      char raw[64 + 24 * 8] = {};
+      char raw[64 + 30 * 8] = {};
       f.read(raw, sizeof raw);                                                   // pages are 4 KiB; anything shorter than the v1 payload is not one
       if (f.gcount() < 64 + 17 * 8 || memcmp(raw, "B200COLL", 8) != 0) continue;
       uint32_t hdr[6]; memcpy(hdr, raw + 8, sizeof hdr);
@@ -700,6 +700,7 @@ void append_coll_stats(std::ostringstream& os) {
       for (int i = 0; i < nops; i++) { p.calls[i] = v[i]; p.bytes[i] = v[nops + i]; }
       for (int i = 0; i < 7; i++) p.algo[i] = v[2 * nops + i];
       if (hdr[0] >= 2) memcpy(p.p2p, raw + 64 + 21 * 8, sizeof p.p2p);           // sends, recvs, bytes; zero on pages of a library without send / recv
+      if (hdr[0] >= 2 && f.gcount() >= 64 + 30 * 8) memcpy(p.ext, raw + 64 + 24 * 8, sizeof p.ext);   // appended in round 2; zero on older pages
       pages.push_back(p);
     }
     closedir(d);
@@ -716,6 +717,14 @@ void append_coll_stats(std::ostringstream& os) {
   for (auto& p : pages) for (int i = 0; i < 2; i++) os << "b200coll_p2p_calls{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",dir=\"" << (i ? "recv" : "send") << "\"} " << p.p2p[i] << "\n";
   help("b200coll_p2p_bytes", "Bytes sent plus received by libb200coll point-to-point operations");
   for (auto& p : pages) os << "b200coll_p2p_bytes{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\"} " << p.p2p[2] << "\n";
+  help("b200coll_host_calls", "End-to-end host all-reduces (b200collAllReduceHost) by path");
+  static const char* kPaths[] = {"total", "zero_copy", "pipelined"};
+  for (auto& p : pages) for (int i = 0; i < 3; i++) os << "b200coll_host_calls{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",path=\"" << kPaths[i] << "\"} " << p.ext[i == 0 ? 0 : i + 1] << "\n";
+  help("b200coll_host_bytes", "Input bytes of the end-to-end host all-reduces");
+  for (auto& p : pages) os << "b200coll_host_bytes{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\"} " << p.ext[1] << "\n";
+  help("b200coll_kernel_family_launches", "Launches of the copy-engine (bulk) and generic-reduction kernels");
+  for (auto& p : pages) { os << "b200coll_kernel_family_launches{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",family=\"bulk\"} " << p.ext[4] << "\n";
+                          os << "b200coll_kernel_family_launches{pid=\"" << p.pid << "\",rank=\"" << p.rank << "\",family=\"generic\"} " << p.ext[5] << "\n"; }
 }
 
 std::string collect_metrics(Manager* ngm, const std::string& pod_resources_socket) {

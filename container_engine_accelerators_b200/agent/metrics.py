@@ -92,11 +92,16 @@ def read_coll_stats_pages(pattern: str = "/dev/shm/b200coll.*", now=time.time) -
                 continue
             vals = struct.unpack_from(f"<{2 * nops + 9}Q", raw, 64)
             p2p = struct.unpack_from("<3Q", raw, 64 + 8 * 21) if version >= 2 and len(raw) >= 64 + 8 * 24 else (0, 0, 0)     # zero on pages of a library without send / recv
+            # appended in round 2 (same version: older libraries leave these words zero): host-path calls / bytes / zero-copy / pipelined,
+            # copy-engine launches, generic-reduction launches
+            ext = struct.unpack_from("<6Q", raw, 64 + 8 * 24) if version >= 2 and len(raw) >= 64 + 8 * 30 else (0,) * 6
             pad = (0,) * (len(COLL_OPS) - nops)
             pages.append({"pid": pid, "rank": rank, "nranks": nranks, "device": device, "nvls": nvls, "version": version,
                           "calls": vals[0:nops] + pad, "bytes": vals[nops:2 * nops] + pad,
                           "algo_calls": vals[2 * nops:2 * nops + 7], "kernel_launches": vals[2 * nops + 7], "staged_calls": vals[2 * nops + 8],
-                          "p2p_sends": p2p[0], "p2p_recvs": p2p[1], "p2p_bytes": p2p[2]})
+                          "p2p_sends": p2p[0], "p2p_recvs": p2p[1], "p2p_bytes": p2p[2],
+                          "host_calls": ext[0], "host_bytes": ext[1], "host_zero_copy": ext[2], "host_pipelined": ext[3],
+                          "bulk_launches": ext[4], "generic_launches": ext[5]})
         except OSError:
             continue
     return pages
@@ -125,8 +130,12 @@ class MetricServer:
         self.coll_algo = g("b200coll_algo_calls", "libb200coll calls per chosen algorithm", ["pid", "rank", "algo"])
         self.coll_p2p_calls = g("b200coll_p2p_calls", "Point-to-point operations issued through libb200coll", ["pid", "rank", "dir"])
         self.coll_p2p_bytes = g("b200coll_p2p_bytes", "Bytes sent plus received by libb200coll point-to-point operations", ["pid", "rank"])
+        self.coll_host_calls = g("b200coll_host_calls", "End-to-end host all-reduces (b200collAllReduceHost) by path", ["pid", "rank", "path"])
+        self.coll_host_bytes = g("b200coll_host_bytes", "Input bytes of the end-to-end host all-reduces", ["pid", "rank"])
+        self.coll_family = g("b200coll_kernel_family_launches", "Launches of the copy-engine (bulk) and generic-reduction kernels", ["pid", "rank", "family"])
         self._all = [self.duty_cycle_node, self.memory_total_node, self.memory_used_node, self.duty_cycle, self.memory_total, self.memory_used,
-                     self.requests, self.coll_calls, self.coll_bytes, self.coll_algo, self.coll_p2p_calls, self.coll_p2p_bytes]
+                     self.requests, self.coll_calls, self.coll_bytes, self.coll_algo, self.coll_p2p_calls, self.coll_p2p_bytes,
+                     self.coll_host_calls, self.coll_host_bytes, self.coll_family]
 
     def discover_gpu_devices(self) -> None:
         self.gpu_devices = {}
@@ -191,6 +200,11 @@ class MetricServer:
             self.coll_p2p_calls.labels(pid, rank, "send").set(page["p2p_sends"])
             self.coll_p2p_calls.labels(pid, rank, "recv").set(page["p2p_recvs"])
             self.coll_p2p_bytes.labels(pid, rank).set(page["p2p_bytes"])
+            for path, key in (("total", "host_calls"), ("zero_copy", "host_zero_copy"), ("pipelined", "host_pipelined")):
+                self.coll_host_calls.labels(pid, rank, path).set(page[key])
+            self.coll_host_bytes.labels(pid, rank).set(page["host_bytes"])
+            self.coll_family.labels(pid, rank, "bulk").set(page["bulk_launches"])
+            self.coll_family.labels(pid, rank, "generic").set(page["generic_launches"])
 
     def collect_once(self) -> None:
         try:

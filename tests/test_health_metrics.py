@@ -219,6 +219,7 @@ def test_coll_stats_page_v2_has_broadcast_and_reduce(tmp_path):
     #                                 calls (6 ops)        bytes (6 ops)                     algo_calls (7)        launches staged
     struct.pack_into("<21Q", page, 64, 1, 2, 3, 4, 5, 6, 10, 20, 30, 40, 50, 60, 0, 1, 0, 2, 9, 0, 0, 21, 3)
     struct.pack_into("<3Q", page, 64 + 21 * 8, 7, 8, 9000)                     # p2p sends, recvs, bytes (appended to the v2 payload)
+    struct.pack_into("<6Q", page, 64 + 24 * 8, 11, 1 << 33, 4, 5, 13, 17)      # host calls / bytes / zero-copy / pipelined, bulk launches, generic launches
     (tmp_path / "b200coll.77.0").write_bytes(page)
     pg = metrics.read_coll_stats_pages(str(tmp_path / "b200coll.*"))[0]
     assert (pg["p2p_sends"], pg["p2p_recvs"], pg["p2p_bytes"]) == (7, 8, 9000)
@@ -230,6 +231,9 @@ def test_coll_stats_page_v2_has_broadcast_and_reduce(tmp_path):
     assert sample(reg, "b200coll_calls", {"pid": "77", "rank": "0", "op": "reduce"}) == 6
     assert sample(reg, "b200coll_bytes", {"pid": "77", "rank": "0", "op": "broadcast"}) == 50
     assert sample(reg, "b200coll_p2p_calls", {"pid": "77", "rank": "0", "dir": "recv"}) == 8 and sample(reg, "b200coll_p2p_bytes", {"pid": "77", "rank": "0"}) == 9000
+    assert (pg["host_calls"], pg["host_bytes"], pg["host_zero_copy"], pg["host_pipelined"], pg["bulk_launches"], pg["generic_launches"]) == (11, 1 << 33, 4, 5, 13, 17)
+    assert sample(reg, "b200coll_host_calls", {"pid": "77", "rank": "0", "path": "pipelined"}) == 5 and sample(reg, "b200coll_host_bytes", {"pid": "77", "rank": "0"}) == 1 << 33
+    assert sample(reg, "b200coll_kernel_family_launches", {"pid": "77", "rank": "0", "family": "generic"}) == 17
     # header timestamp: a fresh page is exported, one that has not been touched for more than an hour is a leftover of a dead process
     import time as _time
     struct.pack_into("<Q", page, 32, int(_time.time()) - 30); (tmp_path / "b200coll.77.0").write_bytes(page)

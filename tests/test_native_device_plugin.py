@@ -200,6 +200,7 @@ def test_metrics_endpoint(native, tmp_path, service):
         struct.pack_into("<6I", page, 8, 2, 4242, 3, 8, 3, 1)
         struct.pack_into("<21Q", page, 64, 10, 0, 0, 2, 7, 1, 1 << 30, 0, 0, 4096, 512, 64, 0, 5, 0, 2, 13, 0, 0, 21, 0)
         struct.pack_into("<3Q", page, 64 + 21 * 8, 4, 5, 6000)                  # point-to-point: sends, recvs, bytes
+        struct.pack_into("<6Q", page, 64 + 24 * 8, 9, 1 << 32, 3, 2, 40, 41)    # host path: calls / bytes / zero-copy / pipelined; bulk and generic launches
         struct.pack_into("<Q", page, 32, int(time.time()))                      # freshly updated
         (shm / "b200coll.4242.3").write_bytes(page)
         stale = bytearray(page); struct.pack_into("<6I", stale, 8, 2, 999, 0, 8, 0, 1); struct.pack_into("<Q", stale, 32, int(time.time()) - 7200)
@@ -225,6 +226,9 @@ def test_metrics_endpoint(native, tmp_path, service):
         assert f'b200coll_bytes{{pid="4242",rank="3",op="all_reduce"}} {1 << 30}' in body
         assert 'b200coll_algo_calls{pid="4242",rank="3",algo="nvls"} 13' in body
         assert 'b200coll_p2p_calls{pid="4242",rank="3",dir="send"} 4' in body and 'b200coll_p2p_bytes{pid="4242",rank="3"} 6000' in body
+        assert 'b200coll_host_calls{pid="4242",rank="3",path="total"} 9' in body and 'b200coll_host_calls{pid="4242",rank="3",path="pipelined"} 2' in body
+        assert f'b200coll_host_bytes{{pid="4242",rank="3"}} {1 << 32}' in body
+        assert 'b200coll_kernel_family_launches{pid="4242",rank="3",family="bulk"} 40' in body and 'family="generic"} 41' in body
         assert 'pid="999"' not in body
     finally:
         stub.server.stop(0)
