@@ -161,9 +161,10 @@ def ncu_ranks():
            "one pass, `--clock-control none --cache-control none`. Findings on this pool (driver 580.159, ncu 2025.2):", "",
            "* metric sets that fit one pass (DRAM bytes, L2 sectors arriving from the fabric, occupancy, launch shape) are collected per rank while the peers run un-profiled at full speed;",
            "* anything that needs a second pass fails with `==ERROR== UnknownError / Failed to profile` — kernel replay has to save and restore device memory, and a symmetric arena is "
-           "VMM memory imported from other processes plus a multicast binding, which ncu cannot snapshot; the per-warp stall ratios and `nvlrx__bytes` / `nvltx__bytes` fall in this class "
-           "(the NVLink counters also fail alone on a single GPU, see below), so NVLink traffic is read from `lts__t_sectors_srcunit_ltcfabric` (32-byte sectors entering this GPU's L2 "
-           "from the fabric = bytes this GPU receives over NVLink);",
+           "VMM memory imported from other processes plus a multicast binding, which ncu cannot snapshot; the per-warp stall ratios, and `nvlrx__bytes` + `nvltx__bytes` + "
+           "`gpu__time_duration` requested together, fell in this class on the 2-GPU runs (on ONE GPU the two NVLink counters alone are collected in a single pass, see the end: they exist, "
+           "they just cannot be combined with a second counter domain here), so NVLink traffic is read from `lts__t_sectors_srcunit_ltcfabric` (32-byte sectors entering this GPU's L2 "
+           "from the fabric: the responses to this GPU's peer loads, and peers' stores landing here);",
            "* the two ranks are not in lock-step under the tool (the profiled launch of one rank may meet a warm-up launch of the other), so only the rank whose capture shows the expected fabric volume is quoted.", ""]
     rows = []
     for f in sorted(glob.glob(os.path.join(G, "ncu_n*_mem_r*.csv"))):
@@ -185,7 +186,11 @@ def ncu_ranks():
         for r in rows:
             out.append(f"| {r[0]} | {r[1]} | {r[2]} | `{r[3]}` | {r[4]} | {r[5]} | {r[6]} | {r[7] / 1e6:.1f} | {r[8] / 1e6:.1f} | {r[9] / 1e6:.1f} | {r[10]} |")
         out += ["", "Reading the 2-GPU rows (64 MiB messages): `k_ar_twoshot` rank 0 receives 34.8 MB over NVLink for 33.6 MB algorithmic (its half of the buffer pulled from the peer; the pushed half is egress) — "
-                "1.04 x; the P2P reduce-scatter pull shows the same 34.8 MB. `uncontrolled caches` means the DRAM columns include write-backs of lines the previous launch left dirty in L2; they bound, not equal, this launch's traffic.", ""]
+                "1.04 x; the P2P reduce-scatter pull shows the same 34.8 MB; the broadcast root's 32 MiB push arrives as 23.8 / 24.3 MB on the two ranks within the profiled window. `uncontrolled caches` means the DRAM columns "
+                "include write-backs of lines the previous launch left dirty in L2; they bound, not equal, this launch's traffic. "
+                "The 8-GPU rows are kept for the launch shapes and register counts only: with eight tools attached the ranks lose lock-step (a profiled launch meets peers that are seconds away, "
+                "and since round 2 a kernel whose barrier times out returns without moving data), and switch-side traffic (`multimem.ld_reduce` / `multimem.st`) does not show up as fabric sectors at all — "
+                "their fabric column reads ~0 although the same kernels move 843 GB/s when timed.", ""]
     probe = os.path.join(G, "r2c4_ncu_nvl_probe.txt")
     if os.path.exists(probe):
         txt = open(probe).read()
