@@ -225,7 +225,8 @@ b200collResult_t b200collAllReduceHost(const void* host_send, void* host_recv, s
 
   // One kernel, no copy engine: nranks > 1 takes a Lamport kernel (they only ever read `in` and write `out` locally, so both may be
   // host memory): one-shot up to 512 KiB, two-shot up to 512 KiB x nranks when the types have equal size. One rank: the copy kernel.
-  const bool zc_feasible = c->nranks == 1 || bytes <= kLLOneShotMaxBytes || (is == os && bytes <= kLLOneShotMaxBytes * (size_t)c->nranks);
+  // (the generic reductions — min / max / prod, integer, fp64 — stage non-arena buffers with device-to-device copies: copy engines for them)
+  const bool zc_feasible = !needs_generic(ep, rop) && (c->nranks == 1 || bytes <= kLLOneShotMaxBytes || (is == os && bytes <= kLLOneShotMaxBytes * (size_t)c->nranks));
   if (bytes <= zc_max && zc_feasible) {
     void *din = nullptr, *dout = nullptr;
     if (cudaHostGetDevicePointer(&din, const_cast<void*>(host_send), 0) == cudaSuccess && cudaHostGetDevicePointer(&dout, host_recv, 0) == cudaSuccess) {
