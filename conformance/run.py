@@ -425,6 +425,26 @@ def transport_profile(cmd):
         n.close()
 
 
+def real_hardware(cmd):
+    """(--real only) No fakes on the device side: the host's /dev/nvidia*, /proc, /sys and the installed NVML; the stub kubelet must see every GPU node Healthy and get its device nodes on Allocate."""
+    import re
+    minors = sorted(int(m.group(1)) for m in (re.fullmatch(r"nvidia(\d+)", f) for f in os.listdir("/dev")) if m)
+    assert minors, "no /dev/nvidia<N> on this host"
+    n = Node(cmd, real=True)
+    try:
+        reg = n.kubelet.wait_registration(30)
+        assert (reg.version, reg.resource_name) == ("v1beta1", "nvidia.com/gpu")
+        c = n.connect()
+        stream, devs = first_list(c)
+        assert set(devs) == {f"nvidia{i}" for i in minors} and all(d.health == "Healthy" for d in devs.values()), devs
+        first = f"nvidia{minors[0]}"
+        paths = [d.host_path for d in c.allocate([first]).container_responses[0].devices]
+        assert paths[0] == f"/dev/{first}" and "/dev/nvidiactl" in paths and all(os.path.exists(p) for p in paths), paths
+        stream.cancel()
+    finally:
+        n.close()
+
+
 SCENARIOS = [register_list_allocate, numa_topology, time_sharing, mig_seven_slices, mig_with_time_sharing, bad_config_falls_back, hot_add_and_socket_removal, kubelet_appears_later, kubelet_restart, sigterm_clean_exit,
              xid_marks_unhealthy, xid_on_a_mig_slice, metrics_endpoint, mps_sharing, transport_profile]
 
@@ -435,6 +455,7 @@ def main(argv=None) -> int:
     ap.add_argument("--command", help="command line template with {plugin_dir} {gpu_config} {dev_dir} {proc_dir} {pci_root} {endpoint}")
     ap.add_argument("--only", nargs="*", help="scenario names to run (default: all)")
     ap.add_argument("--list", action="store_true")
+    ap.add_argument("--real", action="store_true", help="on a GPU node: run the one scenario that uses the host's real /dev, /proc, /sys and NVML instead of the fifteen fake-node scenarios")
     args = ap.parse_args(argv)
     if args.list:
         for s in SCENARIOS:
@@ -446,7 +467,7 @@ def main(argv=None) -> int:
     if not os.path.exists(os.path.join(ROOT, "build", "agent", "libfake_nvml.so")):
         subprocess.run(["make", "-C", os.path.join(ROOT, "agent", "native"), "-j4"], check=True, capture_output=True)
     failed = 0
-    for s in SCENARIOS:
+    for s in ([real_hardware] if args.real else SCENARIOS):
         if args.only and s.__name__ not in args.only:
             continue
         t0 = time.time()
