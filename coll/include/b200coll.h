@@ -212,6 +212,9 @@ b200collResult_t b200collAllReduceHost(const void* host_send, void* host_recv, s
                                        b200collRedOp_t op, b200collComm_t comm, b200collStream_t stream);
 /* NUMA node of this rank's GPU (-1 unknown) and its local CPU list as sysfs prints it. */
 b200collResult_t b200collCommNumaGet(b200collComm_t comm, int* numa_node, char* cpulist, size_t len);
+/* Test hook (no GPU needed): what CommInitRank does with the GPU's sysfs directory (files numa_node, local_cpulist): returns the NUMA node
+ * read (-1 if absent); with mode != 0 the calling thread's affinity is narrowed to the listed CPUs it is allowed to use (*changed = 1 if so). */
+int b200collDebugApplyLocality(const char* sysfs_dir, int mode, int* changed);
 /* Test hook: parse a sysfs cpulist ("0-31,64-95") into at most `max` CPU numbers; returns how many. */
 int b200collDebugParseCpuList(const char* s, int* cpus, int max);
 

@@ -65,12 +65,9 @@ static std::string gpu_sysfs_dir(int device) {
   return std::string(root && *root ? root : "/sys/bus/pci/devices") + "/" + bus;
 }
 
-void bind_to_gpu_numa(b200collComm* c, bool allow_bind) {
-  c->numa_node = -1;
-  const char* e = getenv("B200COLL_AFFINITY");
-  const int mode = !allow_bind ? 0 : (e && *e) ? atoi(e) : 1;
-  const std::string dir = gpu_sysfs_dir(c->device);
-  if (dir.empty()) return;
+// The part of bind_to_gpu_numa that needs no GPU: read <dir>/numa_node and <dir>/local_cpulist, and (mode != 0) narrow the calling
+// thread's affinity to the listed CPUs that its current mask allows. Unit-tested on CPU through b200collDebugApplyLocality.
+static void apply_gpu_locality(b200collComm* c, const std::string& dir, int mode) {
   const std::string node = read_small_file(dir + "/numa_node");
   if (!node.empty()) c->numa_node = atoi(node.c_str());
   const std::string cpus = read_small_file(dir + "/local_cpulist");
@@ -85,6 +82,15 @@ void bind_to_gpu_numa(b200collComm* c, bool allow_bind) {
   c->affinity_saved = have; c->affinity_changed = true;
   if (sched_setaffinity(0, sizeof(both), &both) != 0) { c->affinity_changed = false; dbg(1, "rank %d: sched_setaffinity failed; affinity unchanged", c->rank); return; }
   dbg(1, "rank %d: bound to the CPUs of NUMA node %d (%s)", c->rank, c->numa_node, cpus.c_str());
+}
+
+void bind_to_gpu_numa(b200collComm* c, bool allow_bind) {
+  c->numa_node = -1;
+  const char* e = getenv("B200COLL_AFFINITY");
+  const int mode = !allow_bind ? 0 : (e && *e) ? atoi(e) : 1;
+  const std::string dir = gpu_sysfs_dir(c->device);
+  if (dir.empty()) return;
+  apply_gpu_locality(c, dir, mode);
 }
 
 void restore_affinity_after_init(b200collComm* c) {
@@ -152,6 +158,16 @@ int b200collDebugParseCpuList(const char* s, int* cpus, int max) {
   int n = 0;
   for (int i = 0; i < CPU_SETSIZE && n < max; i++) if (CPU_ISSET(i, &set)) cpus[n++] = i;
   return n;
+}
+
+// Test hook (no GPU): apply the locality rules to the calling thread from a directory laid out like /sys/bus/pci/devices/<gpu>
+// (files numa_node, local_cpulist). Returns the node read (-1 if none); *changed says whether the thread's affinity was narrowed.
+int b200collDebugApplyLocality(const char* sysfs_dir, int mode, int* changed) {
+  b200collComm fake;
+  fake.numa_node = -1;
+  apply_gpu_locality(&fake, sysfs_dir ? sysfs_dir : "", mode);
+  if (changed) *changed = fake.affinity_changed ? 1 : 0;
+  return fake.numa_node;
 }
 
 b200collResult_t b200collCommNumaGet(b200collComm_t c, int* numa_node, char* cpulist, size_t len) {
