@@ -479,18 +479,20 @@ def test_benchmark_self_check_rejects_low_precision_accumulation():
     assert not h.reduction_ok(torch, off_by_two, want, torch.bfloat16, n)
 
 
-def _locality_worker(lib_path, root, q):
-    L = C.CDLL(lib_path)
-    L.b200collDebugApplyLocality.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
-    out = {}
-    start = sorted(os.sched_getaffinity(0))
-    changed = C.c_int(-1)
-    out["missing"] = (L.b200collDebugApplyLocality(os.path.join(root, "nope").encode(), 1, C.byref(changed)), changed.value, sorted(os.sched_getaffinity(0)) == start)
-    out["observe_only"] = (L.b200collDebugApplyLocality(os.path.join(root, "gpu").encode(), 0, C.byref(changed)), changed.value, sorted(os.sched_getaffinity(0)) == start)
-    out["outside"] = (L.b200collDebugApplyLocality(os.path.join(root, "far").encode(), 1, C.byref(changed)), changed.value, sorted(os.sched_getaffinity(0)) == start)
-    out["bind"] = (L.b200collDebugApplyLocality(os.path.join(root, "gpu").encode(), 1, C.byref(changed)), changed.value, sorted(os.sched_getaffinity(0)))
-    out["again"] = (L.b200collDebugApplyLocality(os.path.join(root, "gpu").encode(), 1, C.byref(changed)), changed.value, sorted(os.sched_getaffinity(0)))
-    q.put((start, out))
+_LOCALITY_SCRIPT = r"""
+import ctypes as C, json, os, sys
+lib_path, root = sys.argv[1], sys.argv[2]
+L = C.CDLL(lib_path)
+L.b200collDebugApplyLocality.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+start = sorted(os.sched_getaffinity(0))
+changed = C.c_int(-1)
+out = {}
+def run(name, sub, mode):
+    node = L.b200collDebugApplyLocality(os.path.join(root, sub).encode(), mode, C.byref(changed))
+    out[name] = [node, changed.value, sorted(os.sched_getaffinity(0))]
+run("missing", "nope", 1); run("observe_only", "gpu", 0); run("outside", "far", 1); run("bind", "gpu", 1); run("again", "gpu", 1)
+print(json.dumps({"start": start, "out": out}))
+"""
 
 
 def test_rank_is_bound_to_the_cpus_of_its_gpu(coll_lib, tmp_path):
@@ -504,16 +506,17 @@ def test_rank_is_bound_to_the_cpus_of_its_gpu(coll_lib, tmp_path):
     local = cpus[:2]
     (tmp_path / "gpu").mkdir(); (tmp_path / "gpu" / "numa_node").write_text("1\n"); (tmp_path / "gpu" / "local_cpulist").write_text(f"{local[0]},{local[1]}\n")
     (tmp_path / "far").mkdir(); (tmp_path / "far" / "numa_node").write_text("0\n"); (tmp_path / "far" / "local_cpulist").write_text("4090-4095\n")
-    ctx = mp.get_context("fork")
-    q = ctx.Queue()
-    p = ctx.Process(target=_locality_worker, args=(coll_lib, str(tmp_path), q))
-    p.start()
-    start, out = q.get(timeout=30)
-    p.join(10)
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", _LOCALITY_SCRIPT, coll_lib, str(tmp_path)], capture_output=True, text=True, timeout=60)      # its own process: the affinity change must not leak
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout)
+    start, out = res["start"], res["out"]
     assert start == cpus
-    assert out["missing"] == (-1, 0, True)
-    assert out["observe_only"] == (1, 0, True)
-    assert out["outside"] == (0, 0, True)
-    assert out["bind"] == (1, 1, local)
-    assert out["again"] == (1, 0, local)                     # already there: nothing to change
+    assert out["missing"] == [-1, 0, cpus]
+    assert out["observe_only"] == [1, 0, cpus]
+    assert out["outside"] == [0, 0, cpus]
+    assert out["bind"] == [1, 1, local]
+    assert out["again"] == [1, 0, local]                     # already there: nothing to change
     assert sorted(os.sched_getaffinity(0)) == cpus           # the test process itself was never touched
